@@ -1,0 +1,536 @@
+"""CPU restatement of tn4ml's batched product-state contraction (fwd + bwd).
+
+TEST INFRASTRUCTURE ONLY -- see ``oracle/__init__.py``.  PARITY UNPINNED (no
+reference golden vectors exist and the reference cannot be imported here).
+
+Every function cites the reference file:line (relative to /root/reference) it
+restates.  Arithmetic is torch on the CPU (float64 unless a dtype is passed);
+gradients come from torch autograd *and*, independently, from the explicit
+environment-based VJP in :func:`mps_env_vjp` / :func:`smpo_env_vjp`.
+
+Conventions
+-----------
+``phi``      [B, L, d]   embedded, normalised product state (one row per sample)
+MPS sites    list of L tensors, reference shapes:
+             classifier (tn4ml/models/mps.py:308-390)  (chi_l, chi_r, d) with the
+             class site (chi_l, chi_r, d, C); boundaries carry bond 1.
+             plain MPS   (tn4ml/models/mps.py:412-464)  site 0 (chi, d) [r,p],
+             bulk (chi_l, chi_r, d), last (chi, d) [l,p]   (boundaries squeezed).
+SMPO sites   (tn4ml/models/smpo.py:161-205, 496-573, squeezed at :728)
+             site 0 (chi, d, d_o) [r,u,d]; i % S == 0 -> (chi_l, chi_r, d, d_o);
+             otherwise (chi_l, chi_r, d); last (chi, d) [l,u] or (chi, d, d_o).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Sequence
+
+import numpy as np
+import torch
+
+# ----------------------------------------------------------------------------
+# Embeddings  (tn4ml/embeddings.py)
+# ----------------------------------------------------------------------------
+
+
+@dataclass(frozen=True)
+class EmbSpec:
+    """Static description of one feature map (the four on the hot path)."""
+
+    kind: str  # "trig" | "fourier" | "poly" | "rbf"
+    k: int = 1  # trig: number of frequencies (dim = 2k)
+    p: int = 2  # fourier: dim = p
+    degree: int = 1  # poly
+    include_bias: bool = False  # poly
+    gamma: float = 1.0  # rbf
+    centers: tuple = field(default_factory=tuple)  # rbf
+
+    @property
+    def dim(self) -> int:
+        if self.kind == "trig":
+            return 2 * self.k  # embeddings.py:317-320
+        if self.kind == "fourier":
+            return self.p  # embeddings.py:385-387 (returns p, not 2p)
+        if self.kind == "poly":
+            return self.degree + (1 if self.include_bias else 0)  # :655-673, n=1
+        if self.kind == "rbf":
+            return len(self.centers)  # embeddings.py:581-583
+        raise ValueError(self.kind)
+
+
+def feature_map(x: torch.Tensor, spec: EmbSpec) -> torch.Tensor:
+    """phi(x) for every scalar in ``x`` -> [..., d], *before* embed()'s normaliser."""
+    x = x.unsqueeze(-1)
+    dt = x.dtype
+    if spec.kind == "trig":
+        # embeddings.py:340-351 : 1/sqrt(k) * [cos(pi x/2^i) i=1..k, sin(pi x/2^i) i=1..k]
+        i = torch.arange(1, spec.k + 1, dtype=dt)
+        ang = math.pi * x / (2.0**i)
+        return torch.cat([torch.cos(ang), torch.sin(ang)], dim=-1) / math.sqrt(spec.k)
+    if spec.kind == "fourier":
+        # embeddings.py:407-423 : (1/p) |sum_k exp(2 pi i k ((p-1)x - j)/p)|, j=0..p-1
+        p = spec.p
+        j = torch.arange(p, dtype=dt)
+        kk = torch.arange(p, dtype=dt).reshape(p, 1)
+        ang = 2.0 * math.pi * kk * (((p - 1) * x - j) / p).unsqueeze(-2)  # [..., k, j]
+        re = torch.cos(ang).sum(dim=-2)
+        im = torch.sin(ang).sum(dim=-2)
+        return torch.sqrt(re * re + im * im) / p
+    if spec.kind == "poly":
+        # embeddings.py:693-717 with n=1, no cross terms: [1?] + [x, x^2, ..., x^degree]
+        feats = []
+        if spec.include_bias:
+            feats.append(torch.ones_like(x))
+        for dgr in range(1, spec.degree + 1):
+            feats.append(x**dgr)
+        return torch.cat(feats, dim=-1)
+    if spec.kind == "rbf":
+        # embeddings.py:601-602 : exp(-gamma (x - c_j)) (no square), then / ||.||
+        c = torch.tensor(spec.centers, dtype=dt)
+        v = torch.exp(-spec.gamma * (x - c))
+        return v / torch.linalg.norm(v, dim=-1, keepdim=True)
+    raise ValueError(spec.kind)
+
+
+def embed_batch(x: torch.Tensor, spec: EmbSpec) -> torch.Tensor:
+    """embed() for a batch: x [B, L] -> normalised product state phi [B, L, d].
+
+    embeddings.py:1354-1358 builds one (1,1,d) tensor per feature; :1374-1387
+    normalises: L <= 200 divides every site by norm**(1/L), norm = prod_i ||phi_i||
+    (the MPS norm of a product state); L > 200 normalises site by site interleaved
+    with QRs whose signs cancel pairwise.  Both give the unit-norm product state.
+    """
+    phi = feature_map(x, spec)  # [B, L, d]
+    L = phi.shape[1]
+    site_norm = torch.linalg.norm(phi, dim=-1)  # [B, L]
+    if L > 200:
+        return phi / site_norm.unsqueeze(-1)
+    log_norm = torch.log(site_norm).sum(dim=1, keepdim=True)  # log prod ||phi_i||
+    scale = torch.exp(log_norm / L)  # norm ** (1/L)
+    return phi / scale.unsqueeze(-1)
+
+
+# ----------------------------------------------------------------------------
+# Site-tensor canonicalisation (layouts only)
+# ----------------------------------------------------------------------------
+
+
+def canon_mps_sites(arrays: Sequence[torch.Tensor]) -> tuple[list[torch.Tensor], int]:
+    """Bring MPS site tensors to 4-D (chi_l, chi_r, d, C); return (sites, class_site).
+
+    class_site = -1 when no site carries a class leg (plain MPS, mps.py:412-464).
+    """
+    L = len(arrays)
+    out, cls = [], -1
+    for i, a in enumerate(arrays):
+        if a.ndim == 2:  # squeezed boundary of a plain MPS (mps.py:451)
+            a = a.unsqueeze(0) if i == 0 else a.unsqueeze(1)  # (1,r,p) / (l,1,p)
+            if L == 1:
+                raise ValueError("single-site MPS not supported")
+        if a.ndim == 3:
+            a = a.unsqueeze(-1)
+        elif a.ndim == 4:
+            if cls >= 0:
+                raise ValueError("more than one class site")
+            cls = i
+        else:
+            raise ValueError(f"site {i}: ndim {a.ndim}")
+        out.append(a)
+    return out, cls
+
+
+def canon_smpo_sites(arrays: Sequence[torch.Tensor], spacing: int) -> list[torch.Tensor]:
+    """Bring SMPO site tensors to 4-D (chi_l, chi_r, d, d_o or 1)."""
+    L = len(arrays)
+    out = []
+    for i, a in enumerate(arrays):
+        has_out = i % spacing == 0
+        if i == 0:
+            a = a.unsqueeze(0)  # (chi, d, d_o) -> (1, chi, d, d_o)   smpo.py:186
+        elif i == L - 1:
+            a = a.unsqueeze(1)  # (chi, d[, d_o]) -> (chi, 1, d[, d_o])  smpo.py:199
+        if not has_out:
+            a = a.unsqueeze(-1)
+        if a.ndim != 4:
+            raise ValueError(f"SMPO site {i}: bad shape {tuple(a.shape)}")
+        out.append(a)
+    return out
+
+
+# ----------------------------------------------------------------------------
+# MPS contraction  (metrics.py:47, :473-476 ; model.py:312-316)
+# ----------------------------------------------------------------------------
+
+
+def mps_outputs(phi: torch.Tensor, arrays: Sequence[torch.Tensor], order: str = "gemm") -> torch.Tensor:
+    """(model & data) ^ all for every sample -> y [B, C] (C = 1 without a class site).
+
+    order="ref"  : what XLA receives from quimb -- materialise the per-sample site
+                   matrices M_i[b] = sum_s A_i[:,:,s] phi_i[b,s], then a batched
+                   vector-matrix chain.
+    order="gemm" : (L_i[b,:] @ A_i) then the phi-weighted sum over s.
+    """
+    sites, cls = canon_mps_sites(arrays)
+    B = phi.shape[0]
+    L = len(sites)
+    c = cls if cls >= 0 else L - 1
+
+    def step_left(v, A, ph):  # v [B,chi_l], A (chi_l,chi_r,d,1) -> [B,chi_r]
+        A3 = A[..., 0]
+        if order == "ref":
+            M = torch.einsum("lrs,bs->blr", A3, ph)
+            return torch.bmm(v.unsqueeze(1), M).squeeze(1)
+        T = (v @ A3.reshape(A3.shape[0], -1)).reshape(B, A3.shape[1], A3.shape[2])
+        return (T * ph.unsqueeze(1)).sum(-1)
+
+    def step_right(v, A, ph):  # v [B,chi_r] -> [B,chi_l]
+        A3 = A[..., 0]
+        if order == "ref":
+            M = torch.einsum("lrs,bs->blr", A3, ph)
+            return torch.bmm(M, v.unsqueeze(2)).squeeze(2)
+        At = A3.permute(1, 0, 2).reshape(A3.shape[1], -1)
+        T = (v @ At).reshape(B, A3.shape[0], A3.shape[2])
+        return (T * ph.unsqueeze(1)).sum(-1)
+
+    lv = torch.ones(B, 1, dtype=phi.dtype)
+    for i in range(c):
+        lv = step_left(lv, sites[i], phi[:, i])
+    rv = torch.ones(B, 1, dtype=phi.dtype)
+    for i in range(L - 1, c, -1):
+        rv = step_right(rv, sites[i], phi[:, i])
+    Ac = sites[c]  # (chi_l, chi_r, d, C)
+    Mc = torch.einsum("lrsk,bs->blrk", Ac, phi[:, c])
+    return torch.einsum("bl,blrk,br->bk", lv, Mc, rv)
+
+
+# ----------------------------------------------------------------------------
+# SMPO / MPO contraction  (smpo.py:269-404 ; metrics.py:56-81)
+# ----------------------------------------------------------------------------
+
+
+def smpo_sqnorm(phi: torch.Tensor, arrays: Sequence[torch.Tensor], spacing: int) -> torch.Tensor:
+    """n[b] = <v|v>, v = model.apply(data)  (the MPS over the output legs).
+
+    apply_mps contracts every physical leg (smpo.py:302-303), merges the leg-less
+    matrices of each spacing window into its output tensor (:309-331) and returns an
+    MPS with one (chi, chi, d_o) tensor per window; <v|v> is its double-layer
+    contraction (metrics.py:81 then squares it).
+    """
+    sites = canon_smpo_sites(arrays, spacing)
+    B = phi.shape[0]
+    E = torch.ones(B, 1, 1, dtype=phi.dtype)
+    L = len(sites)
+    i = 0
+    while i < L:
+        A = sites[i]
+        T = torch.einsum("lrso,bs->bolr", A, phi[:, i])  # [B, d_o, chi_l, chi_r]
+        j = i + 1
+        while j < L and j % spacing != 0:
+            M = torch.einsum("lrs,bs->blr", sites[j][..., 0], phi[:, j])
+            T = torch.einsum("bolm,bmr->bolr", T, M)
+            j += 1
+        E = torch.einsum("bolr,blm,bomn->brn", T, E, T)
+        i = j
+    return E[:, 0, 0]
+
+
+# ----------------------------------------------------------------------------
+# Loss heads  (tn4ml/metrics.py)
+# ----------------------------------------------------------------------------
+
+HEADS = (
+    "nll",  # NegLogLikelihood            metrics.py:17-53
+    "softmax_xent",  # OptaxWrapper(optax.softmax_cross_entropy)  :423-487
+    "softmax_xent_weighted",  # CrossEntropyWeighted       :490-532
+    "xent_softmax_argmax",  # CrossEntropySoftmax          :291-333
+    "mse",  # MeanSquaredError                             :336-396
+    "tsn",  # TransformedSquaredNorm                       :56-81
+    "logquad",  # LogQuadNorm                              :171-187
+    "quad",  # QuadNorm                                    :190-206
+)
+
+
+def head_loss(out: torch.Tensor, head: str, targets: torch.Tensor | None = None,
+              class_weights: torch.Tensor | None = None) -> torch.Tensor:
+    """Per-sample loss from the contraction result (``y`` [B,C] or ``n`` [B])."""
+    if head == "nll":
+        s = out.reshape(out.shape[0])
+        return -torch.log(s**2)  # metrics.py:53
+    if head == "tsn":
+        return out**2  # metrics.py:81
+    if head == "logquad":
+        return (torch.log(out**2) - 1.0) ** 2  # metrics.py:187
+    if head == "quad":
+        return (out**2 - 1.0) ** 2  # metrics.py:206
+    yhat = out / torch.linalg.norm(out, dim=-1, keepdim=True)  # metrics.py:479 / :331 / :394
+    if head in ("softmax_xent", "softmax_xent_weighted"):
+        # optax.softmax_cross_entropy(logits, labels) = -sum(labels * log_softmax(logits))
+        l = -(targets * torch.log_softmax(yhat, dim=-1)).sum(-1)
+        if head == "softmax_xent_weighted":
+            l = l * (targets * class_weights).sum(-1)  # metrics.py:520-527
+        return l
+    if head == "xent_softmax_argmax":
+        idx = targets.argmax(dim=-1)  # metrics.py:333
+        return -torch.log_softmax(yhat, dim=-1).gather(1, idx[:, None]).squeeze(1)
+    if head == "mse":
+        return ((yhat - targets) ** 2).mean(-1)  # metrics.py:396
+    raise ValueError(head)
+
+
+# ----------------------------------------------------------------------------
+# loss_fn / value_and_grad  (models/model.py:723-751, 554-566)
+# ----------------------------------------------------------------------------
+
+
+@dataclass
+class Problem:
+    kind: str  # "mps" | "smpo"
+    emb: EmbSpec
+    head: str
+    spacing: int = 0  # smpo only (1 == MPO)
+    class_weights: tuple | None = None
+
+
+def per_sample_loss(prob: Problem, x: torch.Tensor, arrays: Sequence[torch.Tensor],
+                    targets: torch.Tensor | None = None, order: str = "gemm") -> torch.Tensor:
+    """evaluate()'s closure (model.py:1048-1076): embed, contract, head -> [B]."""
+    phi = embed_batch(x, prob.emb)
+    if prob.kind == "mps":
+        out = mps_outputs(phi, arrays, order=order)
+    elif prob.kind == "smpo":
+        out = smpo_sqnorm(phi, arrays, prob.spacing)
+    else:
+        raise ValueError(prob.kind)
+    cw = None if prob.class_weights is None else torch.tensor(prob.class_weights, dtype=x.dtype)
+    return head_loss(out, prob.head, targets, cw)
+
+
+def loss_fn(prob: Problem, x, arrays, targets=None, order: str = "gemm") -> torch.Tensor:
+    """train()'s closure (model.py:723-751): mean over the batch of the per-sample loss."""
+    return per_sample_loss(prob, x, arrays, targets, order).mean()
+
+
+def value_and_grad(prob: Problem, x, arrays, targets=None, order: str = "gemm"):
+    """create_train_step.value_and_grad (model.py:554-566): loss and one grad per site."""
+    leaves = [a.detach().clone().requires_grad_(True) for a in arrays]
+    loss = loss_fn(prob, x, leaves, targets, order)
+    grads = torch.autograd.grad(loss, leaves)
+    return loss.detach(), [g.detach() for g in grads]
+
+
+# ----------------------------------------------------------------------------
+# Independent gradient route: explicit left/right environments (no autograd
+# through the chain).  Used to validate autograd (SURVEY 8c route iii) and as the
+# blueprint of the CUDA VJP kernels.
+# ----------------------------------------------------------------------------
+
+
+def mps_env_vjp(phi: torch.Tensor, arrays: Sequence[torch.Tensor], dy: torch.Tensor):
+    """Given dLoss/dy [B,C], return [dLoss/dA_i] by environments.
+
+    F[j] = env on bond j (left env for j <= c, right env for j >= c+1);
+    G[j] = its adjoint.  dA_j = sum_b F[j] (x) phi_j (x) G[j+1]   (j < c)
+           dA_j = sum_b G[j] (x) phi_j (x) F[j+1]   (j > c)
+           dA_c = sum_b F[c] (x) phi_c (x) F[c+1] (x) dy.
+    """
+    sites, cls = canon_mps_sites(arrays)
+    B, L = phi.shape[0], len(sites)
+    c = cls if cls >= 0 else L - 1
+    one = torch.ones(B, 1, dtype=phi.dtype)
+    M = [torch.einsum("lrsk,bs->blrk", sites[i], phi[:, i]) for i in range(L)]
+    F = [None] * (L + 1)
+    F[0], F[L] = one, one
+    for i in range(c):
+        F[i + 1] = torch.einsum("bl,blr->br", F[i], M[i][..., 0])
+    for i in range(L - 1, c, -1):
+        F[i] = torch.einsum("blr,br->bl", M[i][..., 0], F[i + 1])
+    G = [None] * (L + 1)
+    G[c] = torch.einsum("bk,blrk,br->bl", dy, M[c], F[c + 1])
+    G[c + 1] = torch.einsum("bk,blrk,bl->br", dy, M[c], F[c])
+    for i in range(c - 1, 0, -1):
+        G[i] = torch.einsum("blr,br->bl", M[i][..., 0], G[i + 1])
+    for i in range(c + 1, L - 1):
+        G[i + 1] = torch.einsum("bl,blr->br", G[i], M[i][..., 0])
+    grads = []
+    for i in range(L):
+        if i < c:
+            g = torch.einsum("bl,bs,br->lrs", F[i], phi[:, i], G[i + 1]).unsqueeze(-1)
+        elif i > c:
+            g = torch.einsum("bl,bs,br->lrs", G[i], phi[:, i], F[i + 1]).unsqueeze(-1)
+        else:
+            g = torch.einsum("bl,bs,br,bk->lrsk", F[c], phi[:, c], F[c + 1], dy)
+        grads.append(g.reshape(arrays[i].shape))
+    return grads
+
+
+def smpo_env_vjp(phi: torch.Tensor, arrays: Sequence[torch.Tensor], spacing: int, dn: torch.Tensor):
+    """Given dLoss/dn [B], return [dLoss/dA_i] by window environments (no autograd)."""
+    sites = canon_smpo_sites(arrays, spacing)
+    B, L = phi.shape[0], len(sites)
+    starts = list(range(0, L, spacing))
+    # forward, keeping per-window intermediates
+    E = [torch.ones(B, 1, 1, dtype=phi.dtype)]
+    win = []
+    for w0 in starts:
+        w1 = min(w0 + spacing, L)
+        Mo = torch.einsum("lrso,bs->bolr", sites[w0], phi[:, w0])
+        Ms = [torch.einsum("lrs,bs->blr", sites[j][..., 0], phi[:, j]) for j in range(w0 + 1, w1)]
+        Q = [None]  # prefix products Q_k = M_1 ... M_k ; Q_0 = identity (None)
+        for Mj in Ms:
+            Q.append(Mj if Q[-1] is None else torch.bmm(Q[-1], Mj))
+        P = Q[-1]
+        T = Mo if P is None else torch.einsum("bolm,bmr->bolr", Mo, P)
+        U = torch.einsum("blm,bomr->bolr", E[-1], T)
+        E.append(torch.einsum("bolr,boln->brn", T, U))
+        win.append((w0, w1, Mo, Ms, Q, T, U))
+    grads = [None] * L
+    dE = dn.reshape(B, 1, 1).clone()
+    for (w0, w1, Mo, Ms, Q, T, U), Ew in zip(reversed(win), reversed(E[:-1])):
+        dEs = 0.5 * (dE + dE.transpose(1, 2))
+        dT = 2.0 * torch.einsum("bolr,brn->boln", U, dEs)
+        dE = torch.einsum("bolr,brn,bomn->blm", T, dEs, T)
+        P = Q[-1]
+        if P is None:
+            dMo = dT
+        else:
+            dMo = torch.einsum("boln,bmn->bolm", dT, P)
+            Gm = torch.einsum("bolm,boln->bmn", Mo, dT)  # dP
+            for k in range(len(Ms), 0, -1):
+                dMk = Gm if Q[k - 1] is None else torch.bmm(Q[k - 1].transpose(1, 2), Gm)
+                j = w0 + k
+                grads[j] = torch.einsum("blr,bs->lrs", dMk, phi[:, j]).reshape(arrays[j].shape)
+                Gm = torch.bmm(Gm, Ms[k - 1].transpose(1, 2))
+        grads[w0] = torch.einsum("bolr,bs->lrso", dMo, phi[:, w0]).reshape(arrays[w0].shape)
+    return grads
+
+
+# ----------------------------------------------------------------------------
+# Brute-force dense contraction for tiny L (validation route i).
+# util.from_mps_to_dense (tn4ml/util.py:336-365) shows the amplitude convention.
+# ----------------------------------------------------------------------------
+
+
+def mps_dense_outputs(phi: torch.Tensor, arrays: Sequence[torch.Tensor]) -> torch.Tensor:
+    """Build the full d^L x C amplitude tensor of the MPS and contract it with the
+    product state explicitly (exponential; L <= 10)."""
+    sites, cls = canon_mps_sites(arrays)
+    L = len(sites)
+    if L > 10:
+        raise ValueError("dense route is exponential")
+    # amplitude tensor psi[s_0..s_{L-1}, k]
+    cur = torch.ones(1, 1, 1, dtype=phi.dtype)  # [config, bond, k]
+    for A in sites:
+        # cur [n, l, k] x A (l, r, s, k') -> [n, s, r, k*k'] ; only one site has k' > 1
+        nxt = torch.einsum("nlk,lrsq->nsrkq", cur, A)
+        n, s, r, k, q = nxt.shape
+        cur = nxt.reshape(n * s, r, k * q)
+    psi = cur[:, 0, :]  # [d^L, C]
+    B = phi.shape[0]
+    amp = torch.ones(B, 1, dtype=phi.dtype)
+    for i in range(L):
+        amp = (amp.unsqueeze(-1) * phi[:, i].unsqueeze(1)).reshape(B, -1)
+    return amp @ psi
+
+
+def smpo_dense_sqnorm(phi: torch.Tensor, arrays: Sequence[torch.Tensor], spacing: int) -> torch.Tensor:
+    """v = P|phi> built as an explicit dense vector over all output legs, then <v|v>."""
+    sites = canon_smpo_sites(arrays, spacing)
+    L = len(sites)
+    if L > 12:
+        raise ValueError("dense route is exponential")
+    B = phi.shape[0]
+    cur = torch.ones(B, 1, 1, dtype=phi.dtype)  # [b, outcfg, bond]
+    for i, A in enumerate(sites):
+        M = torch.einsum("lrso,bs->bolr", A, phi[:, i])
+        nxt = torch.einsum("bnl,bolr->bnor", cur, M)
+        cur = nxt.reshape(B, -1, nxt.shape[-1])
+    v = cur[:, :, 0]
+    return (v * v).sum(-1)
+
+
+# ----------------------------------------------------------------------------
+# Synthetic problems of the five BASELINE.json configs
+# ----------------------------------------------------------------------------
+
+
+def make_mps_arrays(L, chi, d, class_site=None, C=None, std=1e-2, seed=42, dtype=torch.float64,
+                    squeeze_ends=False, shape_method="even"):
+    """A_i = I delta_{s,0} + std N(0,1) (mps.py:348-355 add_identity), then a global
+    division by norm^(1/L) as Model.normalize does (tn.py:103-107)."""
+    g = torch.Generator().manual_seed(seed)
+    arrays = []
+    for i in range(L):
+        if shape_method == "even":
+            cl = 1 if i == 0 else chi
+            cr = 1 if i == L - 1 else chi
+        else:  # mps.py:124-151 ("noteven": bonds truncated to min(chi, d^j))
+            pos = i + 1
+            j = (L + 1 - abs(2 * pos - L - 1)) // 2 if pos > L // 2 else pos
+            chir, chil = min(chi, d**j), min(chi, d ** (j - 1))
+            if pos > L // 2:
+                chil, chir = chir, chil
+            cl = 1 if pos == 1 else chil
+            cr = 1 if pos == L else chir
+        shape = (cl, cr, d) + ((C,) if class_site == i else ())
+        a = std * torch.randn(shape, generator=g, dtype=torch.float64)
+        eye = torch.eye(cl, cr, dtype=torch.float64)
+        if a.ndim == 3:
+            a[:, :, 0] += eye
+        else:
+            a[:, :, 0, :] += eye.unsqueeze(-1)
+        arrays.append(a)
+    # global normalisation <A|A> = 1, spread over sites
+    nrm2 = mps_model_sqnorm(arrays)
+    scale = torch.exp(-0.5 * torch.log(nrm2) / L)
+    arrays = [(a * scale).to(dtype) for a in arrays]
+    if squeeze_ends and class_site is None:
+        arrays[0] = arrays[0].squeeze(0)
+        arrays[-1] = arrays[-1].squeeze(1)
+    return arrays
+
+
+def mps_model_sqnorm(arrays) -> torch.Tensor:
+    """<A|A> of the model alone (tn.py:66-80): transfer-matrix sweep."""
+    sites, _ = canon_mps_sites(arrays)
+    E = torch.ones(1, 1, dtype=sites[0].dtype)
+    for A in sites:
+        E = torch.einsum("lm,lrsk,mnsk->rn", E, A, A)
+    return E[0, 0]
+
+
+def make_smpo_arrays(L, chi, d, d_o, spacing, std=1e-2, seed=42, dtype=torch.float64):
+    """SMPO site tensors in the reference's squeezed shapes, identity-plus-noise."""
+    g = torch.Generator().manual_seed(seed)
+    arrays = []
+    for i in range(L):
+        cl = 1 if i == 0 else chi
+        cr = 1 if i == L - 1 else chi
+        has_out = i % spacing == 0
+        shape = (cl, cr, d) + ((d_o,) if has_out else ())
+        a = std * torch.randn(shape, generator=g, dtype=torch.float64)
+        eye = torch.eye(cl, cr, dtype=torch.float64)
+        if has_out:
+            a[:, :, 0, :] += eye.unsqueeze(-1) / math.sqrt(d_o)
+        else:
+            a[:, :, 0] += eye
+        arrays.append(a)
+    arrays[0] = arrays[0].squeeze(0)
+    arrays[-1] = arrays[-1].squeeze(1)
+    # crude normalisation so that n = O(1): divide every site by its Frobenius norm^(1/..)
+    # (SMPO_initialize divides each tensor by its norm, smpo.py:728); here we keep the
+    # spectral scale near 1 so the chain neither explodes nor vanishes.
+    return [a.to(dtype) for a in arrays]
+
+
+def make_inputs(B, L, seed, dtype=torch.float64):
+    """x ~ U(0,1]  (avoids the phi=0 NaN of bias-free polynomials at x=0)."""
+    rng = np.random.default_rng(seed)
+    x = 1.0 - rng.random((B, L))
+    return torch.tensor(x, dtype=dtype)
+
+
+def make_labels(B, C, seed=7, dtype=torch.float64):
+    rng = np.random.default_rng(seed)
+    idx = rng.integers(0, C, size=B)
+    return torch.nn.functional.one_hot(torch.tensor(idx), C).to(dtype)
