@@ -1,0 +1,135 @@
+/*
+ * tn4ml_b200 -- C ABI of the B200-native tn4ml hot path.
+ *
+ * The reference (bsc-quantic/tn4ml v1.1.1) is pure Python and has no FFI of its
+ * own; the seam this library replaces is the pair
+ *     loss_fn(data, targets, *params) -> scalar          tn4ml/models/model.py:723-751
+ *     value_and_grad(params, data, targets)              tn4ml/models/model.py:554-566
+ * plus the forward-only closures of evaluate() (model.py:1048-1076) and
+ * predict()/forward() (model.py:278-368).  Every entry point below is what a
+ * jax.ffi / ctypes binding for that seam would bind.
+ *
+ * Rules of the boundary
+ *   - plain pointers and sizes only; every buffer (inputs, outputs, workspace)
+ *     is DEVICE memory owned by the caller; the library never allocates, frees
+ *     or retains device memory and never synchronises the stream;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - every call returns 0 on success, non-zero otherwise; the message is read
+ *     with tnb_last_error() (thread-local); no exceptions cross the boundary;
+ *   - all calls are re-entrant and CUDA-graph capturable.
+ */
+#ifndef TN4ML_B200_H
+#define TN4ML_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TNB_MAX_PHYS 16 /* max physical (embedding) dimension d          */
+#define TNB_MAX_OUT 32  /* max class dimension C / SMPO output-leg d_o   */
+
+/* tnb_problem.kind */
+enum { TNB_KIND_MPS = 0, TNB_KIND_SMPO = 1 };
+/* tnb_problem.dtype */
+enum { TNB_F32 = 0, TNB_F64 = 1 };
+/* tnb_problem.precision (f32 only): arithmetic of the chain GEMMs */
+enum { TNB_PREC_SIMT = 0, TNB_PREC_TENSOR = 1 };
+/* tnb_embedding.kind -- tn4ml/embeddings.py:287-351, 354-423, 605-717, 544-602 */
+enum { TNB_EMB_TRIG = 0, TNB_EMB_FOURIER = 1, TNB_EMB_POLY = 2, TNB_EMB_RBF = 3 };
+/* tnb_problem.head -- tn4ml/metrics.py */
+enum {
+  TNB_HEAD_NLL = 0,                 /* NegLogLikelihood            metrics.py:17-53   */
+  TNB_HEAD_SOFTMAX_XENT = 1,        /* OptaxWrapper(softmax_cross_entropy) :423-487   */
+  TNB_HEAD_SOFTMAX_XENT_WEIGHTED = 2, /* CrossEntropyWeighted      metrics.py:490-532 */
+  TNB_HEAD_XENT_SOFTMAX_ARGMAX = 3, /* CrossEntropySoftmax         metrics.py:291-333 */
+  TNB_HEAD_MSE = 4,                 /* MeanSquaredError            metrics.py:336-396 */
+  TNB_HEAD_TSN = 5,                 /* TransformedSquaredNorm      metrics.py:56-81   */
+  TNB_HEAD_LOGQUAD = 6,             /* LogQuadNorm                 metrics.py:171-187 */
+  TNB_HEAD_QUAD = 7                 /* QuadNorm                    metrics.py:190-206 */
+};
+
+/* One feature map; replaces Embedding.__call__ + embed()'s normaliser
+ * (tn4ml/embeddings.py:1321-1389).  The embedded tensor never reaches HBM. */
+typedef struct tnb_embedding {
+  int32_t kind;
+  int32_t k;            /* trig: number of frequencies, d = 2k          */
+  int32_t p;            /* fourier: d = p                               */
+  int32_t degree;       /* poly: d = degree + include_bias (n = 1)      */
+  int32_t include_bias; /* poly                                         */
+  int32_t n_centers;    /* rbf: d = n_centers                           */
+  double gamma;         /* rbf                                          */
+  double centers[TNB_MAX_PHYS];
+} tnb_embedding;
+
+/* Static description of one contraction problem (the jax.ffi attributes). */
+typedef struct tnb_problem {
+  int32_t kind;      /* TNB_KIND_*                                              */
+  int32_t dtype;     /* TNB_F32 / TNB_F64 : type of x, params, grads, outputs   */
+  int32_t precision; /* TNB_PREC_*                                              */
+  int32_t L;         /* number of sites                                         */
+  int32_t chi;       /* bond dimension of the packed layout (max over bonds)    */
+  int32_t d;         /* physical dimension (== embedding dimension)             */
+  int32_t n_out;     /* MPS: class dimension C (1 = no class leg); SMPO: d_o    */
+  int32_t out_site;  /* MPS: 0-based class site (any site when n_out == 1)      */
+  int32_t spacing;   /* SMPO: output leg on sites i % spacing == 0 (1 == MPO)   */
+  int32_t head;      /* TNB_HEAD_*                                              */
+  tnb_embedding emb;
+  double class_weights[TNB_MAX_OUT]; /* TNB_HEAD_SOFTMAX_XENT_WEIGHTED          */
+} tnb_problem;
+
+/* Packed parameter layout (also the layout of the gradients):
+ *   site i occupies chi*chi*d*(n_i) elements, C-contiguous [a][r][s][o] with
+ *   a = left bond, r = right bond, s = physical, o = class/output leg (n_i = n_out on
+ *   sites that carry one, else 1).  Sites with smaller bonds (boundaries, "noteven"
+ *   shapes, tn4ml/models/mps.py:124-151) are zero padded.  Sites are concatenated
+ *   in order 0..L-1. */
+
+const char *tnb_version(void);
+const char *tnb_last_error(void);
+
+/* Number of elements of the packed parameter (and gradient) buffer. */
+int64_t tnb_param_count(const tnb_problem *prob);
+/* Element offset of site `site` inside the packed buffer, and its n_i. */
+int64_t tnb_site_offset(const tnb_problem *prob, int32_t site);
+int32_t tnb_site_nout(const tnb_problem *prob, int32_t site);
+
+/* Bytes of caller-provided device scratch for a batch of `batch` samples.
+ * need_grad = 0: forward only (evaluate / predict); 1: forward + backward. */
+int64_t tnb_workspace_bytes(const tnb_problem *prob, int64_t batch, int32_t need_grad);
+
+/* Forward: embed + contract + head for `batch` samples.
+ *   x        [batch, L]        raw features (dtype)
+ *   targets  [batch, n_out]    one-hot / soft labels (dtype) or NULL
+ *   params   packed site tensors (dtype)
+ *   loss     [batch]           per-sample loss (dtype)            (evaluate(): model.py:1048-1076)
+ *   loss_sum [1] float64       sum_b loss_b, ADDED to the existing value, or NULL
+ *   out      [batch, n_out]    MPS: mantissa of y = out * 2^out_exp;  SMPO: [batch] mantissa of n
+ *   out_exp  [batch] int32     binary exponent carried by the in-chain rescaling
+ *   keep_stash != 0 keeps the environments in `workspace` for tnb_backward.
+ */
+int tnb_forward(const tnb_problem *prob, int64_t batch, const void *x, const void *targets,
+                const void *params, void *loss, double *loss_sum, void *out, int32_t *out_exp,
+                int32_t keep_stash, void *workspace, int64_t workspace_bytes, void *stream);
+
+/* Backward: gradients of  loss_scale * sum_b loss_b  w.r.t. every site tensor, from the
+ * environments left in `workspace` by tnb_forward(..., keep_stash=1, ...) on the same
+ * arguments.  grads is the packed layout; accumulate != 0 adds to its contents
+ * (micro-batching / gradient accumulation), otherwise it is overwritten. */
+int tnb_backward(const tnb_problem *prob, int64_t batch, const void *x, const void *targets,
+                 const void *params, double loss_scale, void *grads, int32_t accumulate,
+                 void *workspace, int64_t workspace_bytes, void *stream);
+
+/* Embedding.__call__ for n scalars: phi [n, d] (dtype), before embed()'s normaliser. */
+int tnb_embed(const tnb_embedding *emb, int32_t dtype, int64_t n, const void *x, void *phi,
+              void *stream);
+
+/* Number of kernel launches issued by this library since load (all threads). */
+int64_t tnb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TN4ML_B200_H */

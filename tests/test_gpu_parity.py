@@ -1,0 +1,156 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): relative error <= 1e-10 in float64, <= 1e-4 in float32,
+on the loss and on every gradient tensor (max-abs error scaled by max-abs of the oracle gradient).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import tn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float64: 1e-10, torch.float32: 1e-4}
+
+
+def _heads():
+    from tn4ml_b200 import metrics as M
+    return {
+        "nll": M.NegLogLikelihood,
+        "softmax_xent": lambda *a, **k: M.OptaxWrapper(M.softmax_cross_entropy)(*a, **k).mean(),
+        "xent_softmax_argmax": M.CrossEntropySoftmax,
+        "mse": M.MeanSquaredError,
+        "tsn": M.TransformedSquaredNorm,
+        "logquad": M.LogQuadNorm,
+        "quad": M.QuadNorm,
+    }
+
+
+def _emb(spec):
+    import tn4ml_b200 as T
+    if spec.kind == "trig":
+        return T.TrigonometricEmbedding(k=spec.k)
+    if spec.kind == "fourier":
+        return T.FourierEmbedding(p=spec.p)
+    if spec.kind == "poly":
+        return T.PolynomialEmbedding(degree=spec.degree, n=1, include_bias=spec.include_bias)
+    return T.GaussianRBFEmbedding(centers=np.array(spec.centers), gamma=spec.gamma)
+
+
+def _check(model, prob, loss_fn, x, arrays, t, dtype, scale_tol=1.0):
+    tol = TOL[dtype] * scale_tol
+    arr64 = [a.double() for a in arrays]
+    loss_ref, grads_ref = O.value_and_grad(prob, x.double(), arr64, None if t is None else t.double())
+    per_ref = O.per_sample_loss(prob, x.double(), arr64, None if t is None else t.double())
+    eng, _ = model._engine(_emb(prob.emb), loss_fn, t is not None, dtype)
+    B = x.shape[0]
+    loss_sum, g = eng.value_and_grad(model._packed, x.to(dtype), None if t is None else t.to(dtype))
+    loss = float(loss_sum.item()) / B
+    assert abs(loss - float(loss_ref)) <= tol * max(1.0, abs(float(loss_ref))), (loss, float(loss_ref))
+    for i, (a, b) in enumerate(zip(model._views(g), grads_ref)):
+        assert a.shape == b.shape
+        err = float((a.double().cpu() - b).abs().max())
+        ref = float(b.abs().max())
+        gmax = max(float(q.abs().max()) for q in grads_ref)
+        assert err <= tol * max(ref, 1e-3 * gmax), f"site {i}: err {err:.3e} ref {ref:.3e}"
+    per, out, oexp = eng.forward(model._packed, x.to(dtype), None if t is None else t.to(dtype))
+    assert torch.allclose(per.double().cpu(), per_ref, rtol=tol * 10, atol=tol * 10)
+    return loss
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("case", [
+    dict(L=12, chi=6, d=2, cls=5, C=3, B=40, emb=O.EmbSpec("trig"), head="softmax_xent"),
+    dict(L=7, chi=4, d=3, cls=0, C=4, B=9, emb=O.EmbSpec("poly", degree=2, include_bias=True), head="mse"),
+    dict(L=7, chi=5, d=4, cls=6, C=2, B=33, emb=O.EmbSpec("trig", k=2), head="xent_softmax_argmax"),
+    dict(L=30, chi=32, d=3, cls=14, C=2, B=32, emb=O.EmbSpec("poly", degree=2, include_bias=True),
+         head="softmax_xent_weighted", cw=(0.7, 1.6)),                      # cfg 2
+    dict(L=20, chi=12, d=3, cls=9, C=5, B=130, emb=O.EmbSpec("rbf", gamma=0.8, centers=(0.0, 0.5, 1.0)),
+         head="softmax_xent", shape_method="noteven"),
+    dict(L=10, chi=40, d=2, cls=4, C=3, B=70, emb=O.EmbSpec("trig"), head="softmax_xent"),
+], ids=["small", "cls_first", "cls_last", "cfg2", "noteven_rbf", "chi40"])
+def test_mps_classifier_parity(case, dtype):
+    import tn4ml_b200 as T
+    from tn4ml_b200 import metrics as M
+    arrays = O.make_mps_arrays(case["L"], case["chi"], case["d"], class_site=case["cls"], C=case["C"], std=0.2,
+                               seed=3, shape_method=case.get("shape_method", "even"))
+    x = O.make_inputs(case["B"], case["L"], seed=5)
+    t = O.make_labels(case["B"], case["C"])
+    cw = case.get("cw")
+    prob = O.Problem("mps", case["emb"], case["head"], class_weights=cw)
+    loss_fn = M.CrossEntropyWeighted(cw) if cw else _heads()[case["head"]]
+    model = T.TensorNetwork(arrays, dtype=dtype, device="cuda:0")
+    _check(model, prob, loss_fn, x, arrays, t, dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+def test_cfg1_mnist_shaped_classifier(dtype):
+    """BASELINE config 1: L=196, trig d=2, chi=10, 10 classes at site 97, batch 64."""
+    import tn4ml_b200 as T
+    arrays = O.make_mps_arrays(196, 10, 2, class_site=97, C=10, std=1e-2, seed=42)
+    x = O.make_inputs(64, 196, seed=1235)
+    t = O.make_labels(64, 10)
+    prob = O.Problem("mps", O.EmbSpec("trig"), "softmax_xent")
+    model = T.TensorNetwork(arrays, dtype=dtype, device="cuda:0")
+    _check(model, prob, _heads()["softmax_xent"], x, arrays, t, dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("case", [
+    dict(L=16, chi=16, d=8, B=100, emb=O.EmbSpec("fourier", p=8)),         # cfg 4 shape, reduced chi
+    dict(L=16, chi=64, d=8, B=257, emb=O.EmbSpec("fourier", p=8)),         # cfg 4 at full chi
+    dict(L=9, chi=7, d=2, B=5, emb=O.EmbSpec("trig"), shape_method="noteven"),
+], ids=["fourier16", "cfg4", "noteven"])
+def test_mps_nll_parity(case, dtype):
+    import tn4ml_b200 as T
+    arrays = O.make_mps_arrays(case["L"], case["chi"], case["d"], std=0.05, seed=4, squeeze_ends=True,
+                               shape_method=case.get("shape_method", "even"))
+    x = O.make_inputs(case["B"], case["L"], seed=6)
+    prob = O.Problem("mps", case["emb"], "nll")
+    model = T.MatrixProductState(arrays, dtype=dtype, device="cuda:0")
+    _check(model, prob, _heads()["nll"], x, arrays, None, dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("case", [
+    dict(L=16, S=4, chi=8, d=2, do=2, B=10, head="logquad"),
+    dict(L=17, S=4, chi=6, d=2, do=3, B=7, head="tsn"),        # output leg on the last site
+    dict(L=12, S=1, chi=5, d=2, do=2, B=9, head="quad"),       # MPO
+    dict(L=64, S=8, chi=32, d=2, do=2, B=11, head="logquad"),  # cfg 3 shape, shorter chain
+    dict(L=10, S=5, chi=20, d=3, do=2, B=6, head="logquad"),
+], ids=["s4", "s4_lastout", "mpo", "cfg3_short", "chi20"])
+def test_smpo_parity(case, dtype):
+    import tn4ml_b200 as T
+    arrays = O.make_smpo_arrays(case["L"], case["chi"], case["d"], case["do"], case["S"], std=0.05, seed=8)
+    x = O.make_inputs(case["B"], case["L"], seed=9)
+    prob = O.Problem("smpo", O.EmbSpec("trig") if case["d"] == 2 else O.EmbSpec("poly", degree=3), case["head"],
+                     spacing=case["S"])
+    cls = T.MatrixProductOperator if case["S"] == 1 else T.SpacedMatrixProductOperator
+    kw = {} if case["S"] == 1 else {"spacing": case["S"]}
+    model = cls(arrays, dtype=dtype, device="cuda:0", **kw)
+    _check(model, prob, _heads()[case["head"]], x, arrays, None, dtype, scale_tol=10.0 if dtype == torch.float32 else 1.0)
+
+
+def test_long_chain_does_not_leave_fp32_range():
+    """H2: a 784-site chain whose raw product underflows float32 is carried by the exponent."""
+    import tn4ml_b200 as T
+    L = 784
+    arrays = [0.05 * a for a in O.make_mps_arrays(L, 8, 2, std=0.05, seed=2, squeeze_ends=True)]
+    x = O.make_inputs(16, L, seed=3)
+    prob = O.Problem("mps", O.EmbSpec("trig"), "nll")
+    per_ref = O.per_sample_loss(prob, x, arrays)
+    model = T.MatrixProductState(arrays, dtype=torch.float32, device="cuda:0")
+    eng, _ = model._engine(T.TrigonometricEmbedding(), _heads()["nll"], False, torch.float32)
+    per, out, oexp = eng.forward(model._packed, x.float())
+    assert torch.isfinite(per).all()
+    assert torch.allclose(per.double().cpu(), per_ref, rtol=1e-4)
+
+
+def test_embedding_call_matches_oracle():
+    import tn4ml_b200 as T
+    x = torch.linspace(0.01, 1, 57, dtype=torch.float64)
+    for spec in [O.EmbSpec("trig", k=2), O.EmbSpec("fourier", p=8), O.EmbSpec("poly", degree=3),
+                 O.EmbSpec("rbf", gamma=0.5, centers=(0.1, 0.9))]:
+        phi = _emb(spec)(x.numpy())
+        assert torch.allclose(phi.cpu(), O.feature_map(x, spec), atol=1e-12)

@@ -1,0 +1,355 @@
+// C-ABI of the tn4ml hot path (see include/tn4ml_b200.h for the contract).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <atomic>
+#include <mutex>
+
+#include "common.cuh"
+#include "mps_simt.cuh"
+#include "smpo_simt.cuh"
+
+namespace tnb {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+static int fail(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+#define TNB_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) return fail("%s failed: %s", #expr, cudaGetErrorString(_e));  \
+  } while (0)
+
+#define TNB_LAUNCH_CHECK(name)                                                           \
+  do {                                                                                   \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                  \
+    cudaError_t _e = cudaGetLastError();                                                 \
+    if (_e != cudaSuccess) return fail("launch %s failed: %s", name, cudaGetErrorString(_e)); \
+  } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline size_t esize(const tnb_problem *p) { return p->dtype == TNB_F64 ? 8 : 4; }
+
+static int emb_dim(const tnb_embedding &e) {
+  switch (e.kind) {
+    case TNB_EMB_TRIG: return 2 * e.k;
+    case TNB_EMB_FOURIER: return e.p;
+    case TNB_EMB_POLY: return e.degree + (e.include_bias ? 1 : 0);
+    case TNB_EMB_RBF: return e.n_centers;
+  }
+  return -1;
+}
+
+static int validate(const tnb_problem *p) {
+  if (!p) return fail("null problem");
+  if (p->dtype != TNB_F32 && p->dtype != TNB_F64) return fail("dtype must be TNB_F32 or TNB_F64");
+  if (p->L < 2) return fail("L must be >= 2 (got %d)", p->L);
+  if (p->chi < 1 || p->chi > 512) return fail("chi must be in [1, 512] (got %d)", p->chi);
+  if (p->d < 1 || p->d > TNB_MAX_PHYS) return fail("d must be in [1, %d] (got %d)", TNB_MAX_PHYS, p->d);
+  if (p->n_out < 1 || p->n_out > TNB_MAX_OUT) return fail("n_out must be in [1, %d]", TNB_MAX_OUT);
+  int ed = emb_dim(p->emb);
+  if (ed != p->d)
+    return fail("physical dimension of the model (%d) does not match the embedding dimension (%d)", p->d, ed);
+  if (p->kind == TNB_KIND_MPS) {
+    if (p->out_site < 0 || p->out_site >= p->L) return fail("out_site out of range");
+    if (p->head > TNB_HEAD_MSE || p->head < 0) return fail("head %d is not an MPS head", p->head);
+    if (p->head == TNB_HEAD_NLL && p->n_out != 1) return fail("NLL head needs n_out == 1");
+  } else if (p->kind == TNB_KIND_SMPO) {
+    if (p->spacing < 1) return fail("spacing must be >= 1");
+    if (p->head < TNB_HEAD_TSN || p->head > TNB_HEAD_QUAD) return fail("head %d is not an SMPO head", p->head);
+    if (p->chi > 64) return fail("SMPO kernels support chi <= 64 (got %d)", p->chi);
+  } else {
+    return fail("unknown kind %d", p->kind);
+  }
+  return 0;
+}
+
+template <typename T> static void fill_emb(const tnb_embedding &e, EmbParams<T> &o, int d) {
+  o.kind = e.kind; o.k = e.k; o.p = e.p; o.degree = e.degree; o.include_bias = e.include_bias;
+  o.n_centers = e.n_centers; o.d = d; o.gamma = (T)e.gamma;
+  for (int i = 0; i < kMaxPhys; ++i) o.centers[i] = (T)e.centers[i];
+}
+
+// ------------------------------------------------------------------------------------
+// MPS workspace plan
+// ------------------------------------------------------------------------------------
+struct MpsPlan {
+  int chip, nslab, TN, NG, NT, BT, KT;
+  size_t off_Wn, off_Wt, off_F, off_G, off_exps, off_esum, off_y, off_dy, total;
+  size_t smem_sweep, smem_class;
+};
+
+static MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
+  MpsPlan P{};
+  const size_t w = esize(p);
+  P.chip = (p->chi + 3) / 4 * 4;
+  P.nslab = p->L - 1 + p->n_out;
+  int ngroups = P.chip / kRN;
+  P.TN = 1;
+  while (P.TN < ngroups && P.TN < 32) P.TN <<= 1;
+  int ng = (ngroups + P.TN - 1) / P.TN;
+  P.NG = ng <= 1 ? 1 : (ng <= 2 ? 2 : 4);
+  P.NT = 256;
+  while (P.NT > 32) {
+    long long bt = (long long)(P.NT / P.TN) * kRB;
+    if ((B + bt - 1) / bt >= 148) break;
+    P.NT >>= 1;
+  }
+  if (P.NT < P.TN) P.NT = P.TN < 32 ? 32 : P.TN;
+  P.BT = P.NT / P.TN * kRB;
+  size_t row = (size_t)p->d * P.chip * w;
+  long kt = (long)(16384 / row);
+  P.KT = kt < 1 ? 1 : (kt > 16 ? 16 : (int)kt);
+  if (P.KT > P.chip) P.KT = P.chip;
+  size_t slab = (size_t)P.chip * p->d * P.chip * w;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+  P.off_Wn = take(slab * P.nslab);
+  P.off_Wt = take(slab * P.nslab);
+  size_t fslots = need_grad ? (size_t)p->L + 1 : 2;
+  P.off_F = take(fslots * B * P.chip * w);
+  P.off_G = need_grad ? take(((size_t)p->L + 1) * B * P.chip * w) : 0;
+  P.off_exps = take((size_t)p->L * B * sizeof(int));
+  P.off_esum = take((size_t)2 * B * sizeof(int));
+  P.off_y = take((size_t)B * p->n_out * w);
+  P.off_dy = need_grad ? take((size_t)B * p->n_out * w) : 0;
+  P.total = o;
+  size_t base = ((size_t)P.BT * P.chip + (size_t)2 * P.KT * p->d * P.chip + (size_t)P.BT * p->d +
+                 (size_t)P.BT * p->n_out) * w;
+  P.smem_sweep = base;
+  P.smem_class = base + (size_t)P.BT * P.chip * w;
+  return P;
+}
+
+template <typename T>
+static void fill_mps_args(const tnb_problem *p, const MpsPlan &P, long long B, const void *x, const void *targets,
+                          void *ws, MpsArgs<T> &A) {
+  char *w = (char *)ws;
+  A.L = p->L; A.chi = p->chi; A.chip = P.chip; A.D = p->d; A.C = p->n_out; A.c = p->out_site; A.head = p->head;
+  A.B = B;
+  fill_emb<T>(p->emb, A.emb, p->d);
+  for (int i = 0; i < kMaxOut; ++i) A.cw[i] = (T)p->class_weights[i];
+  A.x = (const T *)x; A.targets = (const T *)targets;
+  A.Wn = (const T *)(w + P.off_Wn); A.Wt = (const T *)(w + P.off_Wt);
+  A.F = (T *)(w + P.off_F); A.G = (T *)(w + P.off_G);
+  A.exps = (int *)(w + P.off_exps); A.esum = (int *)(w + P.off_esum);
+  A.y = (T *)(w + P.off_y); A.dy = (T *)(w + P.off_dy);
+  A.loss = nullptr; A.loss_sum = nullptr; A.out = nullptr; A.out_exp = nullptr;
+  A.stash = 0; A.KT = P.KT; A.TN = P.TN; A.loss_scale = T(1);
+}
+
+template <typename T, int NG> static int set_smem_attrs() {
+  // 200 KB opt-in ceiling for the dynamic-smem kernels; done once per instantiation.
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [] {
+    cudaError_t e = cudaFuncSetAttribute(mps_sweep_kernel<T, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(mps_class_kernel<T, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    err = e;
+  });
+  if (err != cudaSuccess) return fail("cudaFuncSetAttribute: %s", cudaGetErrorString(err));
+  return 0;
+}
+
+template <typename T, int NG>
+static int mps_forward_t(const tnb_problem *p, const MpsPlan &P, long long B, const void *x, const void *targets,
+                         const void *params, void *loss, double *loss_sum, void *out, int32_t *out_exp,
+                         int keep_stash, void *ws, cudaStream_t st) {
+  if (set_smem_attrs<T, NG>()) return 1;
+  if (P.smem_class > 200 * 1024) return fail("shared-memory plan too large (%zu B)", P.smem_class);
+  MpsArgs<T> A;
+  fill_mps_args<T>(p, P, B, x, targets, ws, A);
+  A.stash = keep_stash ? 1 : 0;
+  A.loss = (T *)loss; A.loss_sum = loss_sum; A.out = (T *)out; A.out_exp = out_exp;
+  size_t welems = (size_t)P.chip * p->d * P.chip * P.nslab;
+  int pblocks = (int)((welems + 255) / 256);
+  if (pblocks > 148 * 16) pblocks = 148 * 16;
+  mps_prep_kernel<T><<<pblocks, 256, 0, st>>>((const T *)params, (T *)A.Wn, (T *)A.Wt, p->L, p->chi, P.chip, p->d,
+                                              p->n_out, p->out_site);
+  TNB_LAUNCH_CHECK("mps_prep_kernel");
+  int tiles = (int)((B + P.BT - 1) / P.BT);
+  mps_sweep_kernel<T, NG><<<dim3(tiles, 2), P.NT, P.smem_sweep, st>>>(A, 0);
+  TNB_LAUNCH_CHECK("mps_sweep_kernel(fwd)");
+  mps_class_kernel<T, NG><<<tiles, P.NT, P.smem_class, st>>>(A);
+  TNB_LAUNCH_CHECK("mps_class_kernel");
+  return 0;
+}
+
+template <typename T, int NG>
+static int mps_backward_t(const tnb_problem *p, const MpsPlan &P, long long B, const void *x, const void *targets,
+                          double loss_scale, void *grads, int accumulate, void *ws, cudaStream_t st) {
+  if (set_smem_attrs<T, NG>()) return 1;
+  MpsArgs<T> A;
+  fill_mps_args<T>(p, P, B, x, targets, ws, A);
+  A.stash = 1;
+  A.loss_scale = (T)loss_scale;
+  if (!accumulate) TNB_CUDA(cudaMemsetAsync(grads, 0, (size_t)tnb_param_count(p) * sizeof(T), st));
+  int tiles = (int)((B + P.BT - 1) / P.BT);
+  mps_sweep_kernel<T, NG><<<dim3(tiles, 2), P.NT, P.smem_sweep, st>>>(A, 1);
+  TNB_LAUNCH_CHECK("mps_sweep_kernel(adj)");
+  DaArgs<T> Dg;
+  Dg.M = A;
+  Dg.grads = (T *)grads;
+  Dg.tiles_a = (P.chip + 63) / 64;
+  Dg.tiles_r = (P.chip + 63) / 64;
+  long long work = (long long)Dg.tiles_a * Dg.tiles_r * p->L * p->d;
+  long long ns = (148LL * 4 + work - 1) / work;
+  long long maxsplit = (B + 255) / 256;
+  if (ns > maxsplit) ns = maxsplit;
+  if (ns < 1) ns = 1;
+  Dg.nsplit = (int)ns;
+  Dg.bchunk = (B + ns - 1) / ns;
+  Dg.bchunk = (Dg.bchunk + 15) / 16 * 16;
+  Dg.only_site = -1;
+  dim3 grid(Dg.tiles_a * Dg.tiles_r * Dg.nsplit, p->L, p->d);
+  mps_da_kernel<T><<<grid, 256, 0, st>>>(Dg);
+  TNB_LAUNCH_CHECK("mps_da_kernel");
+  // class site: one GEMM per (s, class)
+  Dg.only_site = p->out_site;
+  work = (long long)Dg.tiles_a * Dg.tiles_r * p->d * p->n_out;
+  ns = (148LL * 2 + work - 1) / work;
+  if (ns > maxsplit) ns = maxsplit;
+  if (ns < 1) ns = 1;
+  Dg.nsplit = (int)ns;
+  Dg.bchunk = ((B + ns - 1) / ns + 15) / 16 * 16;
+  dim3 gridc(Dg.tiles_a * Dg.tiles_r * Dg.nsplit, 1, p->d * p->n_out);
+  mps_da_kernel<T><<<gridc, 256, 0, st>>>(Dg);
+  TNB_LAUNCH_CHECK("mps_da_kernel(class)");
+  return 0;
+}
+
+#define TNB_DISPATCH_MPS(fn, ...)                                                   \
+  do {                                                                              \
+    if (p->dtype == TNB_F64) {                                                      \
+      if (P.NG == 1) return fn<double, 1>(__VA_ARGS__);                             \
+      if (P.NG == 2) return fn<double, 2>(__VA_ARGS__);                             \
+      return fn<double, 4>(__VA_ARGS__);                                            \
+    } else {                                                                        \
+      if (P.NG == 1) return fn<float, 1>(__VA_ARGS__);                              \
+      if (P.NG == 2) return fn<float, 2>(__VA_ARGS__);                              \
+      return fn<float, 4>(__VA_ARGS__);                                             \
+    }                                                                               \
+  } while (0)
+
+}  // namespace tnb
+
+using namespace tnb;
+
+extern "C" {
+
+const char *tnb_version(void) { return "tn4ml_b200 0.1.0 (sm_100a)"; }
+const char *tnb_last_error(void) { return g_err; }
+int64_t tnb_launch_count(void) { return g_launches.load(); }
+
+int32_t tnb_site_nout(const tnb_problem *p, int32_t site) {
+  if (!p || site < 0 || site >= p->L) return 0;
+  if (p->kind == TNB_KIND_MPS) return site == p->out_site ? p->n_out : 1;
+  return site % p->spacing == 0 ? p->n_out : 1;
+}
+
+int64_t tnb_site_offset(const tnb_problem *p, int32_t site) {
+  if (!p || site < 0 || site > p->L) return -1;
+  int64_t per = (int64_t)p->chi * p->chi * p->d;
+  int64_t nwith;
+  if (p->kind == TNB_KIND_MPS) nwith = site > p->out_site ? 1 : 0;
+  else nwith = (site + p->spacing - 1) / p->spacing;  // output sites among [0, site)
+  return per * (site - nwith) + per * p->n_out * nwith;
+}
+
+int64_t tnb_param_count(const tnb_problem *p) { return p ? tnb_site_offset(p, p->L) : -1; }
+
+int64_t tnb_workspace_bytes(const tnb_problem *p, int64_t batch, int32_t need_grad) {
+  if (validate(p)) return -1;
+  if (batch < 1) { fail("batch must be >= 1"); return -1; }
+  if (p->kind == TNB_KIND_MPS) return (int64_t)plan_mps(p, batch, need_grad).total;
+  return (int64_t)plan_smpo(p, batch, need_grad).total;
+}
+
+int tnb_forward(const tnb_problem *p, int64_t batch, const void *x, const void *targets, const void *params,
+                void *loss, double *loss_sum, void *out, int32_t *out_exp, int32_t keep_stash, void *workspace,
+                int64_t workspace_bytes, void *stream) {
+  if (validate(p)) return 1;
+  if (batch < 1) return fail("batch must be >= 1");
+  if (!x || !params || !workspace) return fail("null device pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->kind == TNB_KIND_MPS) {
+    if (p->head != TNB_HEAD_NLL && !targets) return fail("classifier heads need targets");
+    MpsPlan P = plan_mps(p, batch, keep_stash);
+    if ((int64_t)P.total > workspace_bytes)
+      return fail("workspace too small: need %zu bytes, got %lld", P.total, (long long)workspace_bytes);
+    TNB_DISPATCH_MPS(mps_forward_t, p, P, batch, x, targets, params, loss, loss_sum, out, out_exp, keep_stash,
+                     workspace, st);
+  }
+  SmpoPlan P = plan_smpo(p, batch, keep_stash);
+  if ((int64_t)P.total > workspace_bytes)
+    return fail("workspace too small: need %zu bytes, got %lld", P.total, (long long)workspace_bytes);
+  int rc;
+  const char *what = "";
+  if (p->dtype == TNB_F64)
+    rc = smpo_forward_t<double>(p, P, batch, x, params, loss, loss_sum, out, out_exp, keep_stash, workspace, st, &what);
+  else
+    rc = smpo_forward_t<float>(p, P, batch, x, params, loss, loss_sum, out, out_exp, keep_stash, workspace, st, &what);
+  g_launches.fetch_add(P.launches_fwd, std::memory_order_relaxed);
+  if (rc) return fail("%s", what);
+  return 0;
+}
+
+int tnb_backward(const tnb_problem *p, int64_t batch, const void *x, const void *targets, const void *params,
+                 double loss_scale, void *grads, int32_t accumulate, void *workspace, int64_t workspace_bytes,
+                 void *stream) {
+  if (validate(p)) return 1;
+  if (batch < 1) return fail("batch must be >= 1");
+  if (!x || !params || !workspace || !grads) return fail("null device pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->kind == TNB_KIND_MPS) {
+    MpsPlan P = plan_mps(p, batch, 1);
+    if ((int64_t)P.total > workspace_bytes)
+      return fail("workspace too small: need %zu bytes, got %lld", P.total, (long long)workspace_bytes);
+    TNB_DISPATCH_MPS(mps_backward_t, p, P, batch, x, targets, loss_scale, grads, accumulate, workspace, st);
+  }
+  SmpoPlan P = plan_smpo(p, batch, 1);
+  if ((int64_t)P.total > workspace_bytes)
+    return fail("workspace too small: need %zu bytes, got %lld", P.total, (long long)workspace_bytes);
+  int rc;
+  const char *what = "";
+  if (p->dtype == TNB_F64)
+    rc = smpo_backward_t<double>(p, P, batch, x, params, loss_scale, grads, accumulate, workspace, st, &what);
+  else
+    rc = smpo_backward_t<float>(p, P, batch, x, params, loss_scale, grads, accumulate, workspace, st, &what);
+  g_launches.fetch_add(P.launches_bwd, std::memory_order_relaxed);
+  if (rc) return fail("%s", what);
+  return 0;
+}
+
+int tnb_embed(const tnb_embedding *emb, int32_t dtype, int64_t n, const void *x, void *phi, void *stream) {
+  if (!emb || !x || !phi) return fail("null pointer");
+  int d = emb_dim(*emb);
+  if (d < 1 || d > TNB_MAX_PHYS) return fail("embedding dimension %d out of range", d);
+  if (n < 1) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  int blocks = (int)((n + 255) / 256);
+  if (dtype == TNB_F64) {
+    EmbParams<double> e;
+    fill_emb<double>(*emb, e, d);
+    embed_kernel<double><<<blocks, 256, 0, st>>>(e, n, (const double *)x, (double *)phi);
+  } else if (dtype == TNB_F32) {
+    EmbParams<float> e;
+    fill_emb<float>(*emb, e, d);
+    embed_kernel<float><<<blocks, 256, 0, st>>>(e, n, (const float *)x, (float *)phi);
+  } else {
+    return fail("bad dtype");
+  }
+  TNB_LAUNCH_CHECK("embed_kernel");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,507 @@
+// K1/K3/K4 (SIMT family): MPS environment sweeps, class site + heads, VJP.
+//
+// Generic in bond dimension (<= 512), physical dimension (<= 16) and dtype (f32/f64).
+// It is the fp64 path of every config and the fp32 path below the tensor-core threshold.
+//
+//   recurrence (what XLA runs for metrics.py:47 and :473-476):
+//     F[j+1][b,r] = 2^-delta_j[b] * sum_{a,s} F[j][b,a] * phi_j[b,s] * A_j[a,r,s]      (left half)
+//     F[j][b,a]   = 2^-delta_j[b] * sum_{r,s} A_j[a,r,s] * phi_j[b,s] * F[j+1][b,r]    (right half)
+//   delta_j[b] is the binary exponent of the row maximum: the environment is carried as
+//   (mantissa vector, integer exponent) so that no chain length or bond dimension can
+//   leave the floating-point range; powers of two are exact, so fp64 results
+//   equal the reference's unscaled arithmetic to rounding.
+#pragma once
+#include "common.cuh"
+
+namespace tnb {
+
+template <typename T> struct MpsArgs {
+  int L, chi, chip, D, C, c, head;
+  long long B;
+  EmbParams<T> emb;
+  T cw[kMaxOut];
+  const T *x;
+  const T *targets;
+  const T *Wn;  // kernel-layout weights [slab][k=a][s][n=r]
+  const T *Wt;  // transposed           [slab][k=r][s][n=a]
+  T *F;         // forward environments  [slot][B][chip]
+  T *G;         // adjoint environments  [bond][B][chip]
+  int *exps;    // delta_j[b]            [L][B]
+  int *esum;    // sum of deltas         [2][B]  (left half, right half)
+  T *y;         // rescaled outputs y'   [B][C]
+  T *dy;        // dLoss/dy' * loss_scale [B][C]
+  T *loss;      // per-sample loss [B] (may be null)
+  double *loss_sum;
+  T *out;       // [B][C] copy of y' for the caller (may be null)
+  int *out_exp; // [B]
+  int stash;    // 1: every bond of F is stored (needed by backward)
+  int KT, TN;
+  T loss_scale;
+};
+
+template <typename T> __device__ __forceinline__ int mps_slab(const MpsArgs<T> &A, int site) {
+  return site <= A.c ? site : site + A.C - 1;
+}
+template <typename T> __device__ __forceinline__ T *mps_fenv(const MpsArgs<T> &A, int bond) {
+  int slot = A.stash ? bond : (bond == A.c ? 0 : (bond == A.c + 1 ? 1 : -1));
+  return slot < 0 ? nullptr : A.F + (size_t)slot * A.B * A.chip;
+}
+
+template <typename T, int RN> __device__ __forceinline__ void lds_vec(const T *p, T (&w)[RN]);
+template <> __device__ __forceinline__ void lds_vec<float, 4>(const float *p, float (&w)[4]) {
+  float4 v = *reinterpret_cast<const float4 *>(p);
+  w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+}
+template <> __device__ __forceinline__ void lds_vec<double, 4>(const double *p, double (&w)[4]) {
+  double2 v0 = *reinterpret_cast<const double2 *>(p);
+  double2 v1 = *reinterpret_cast<const double2 *>(p + 2);
+  w[0] = v0.x; w[1] = v0.y; w[2] = v1.x; w[3] = v1.y;
+}
+
+constexpr int kRB = 4, kRN = 4;
+
+// acc[g][rb][rn] += sum_{k<K, s<D} v[row][k] * phi[row][s] * rs[row] * W[k][s][n]
+// W streamed from global through a double-buffered cp.async ring of KT k-rows.
+template <typename T, int NG>
+__device__ __forceinline__ void step_gemm(const T *__restrict__ Wg, int K, int D, int chip, int KT,
+                                          const T *v_s, const T *phi_s, const T *rs_s, int rs_stride,
+                                          T *W_s, T (&acc)[NG][kRB][kRN], int tb, int tn, int TN) {
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const int row_elems = D * chip;
+  const int nchunks = (K + KT - 1) / KT;
+  auto issue = [&](int ch) {
+    int k0 = ch * KT;
+    int kt = min(KT, K - k0);
+    int n16 = (int)((size_t)kt * row_elems * sizeof(T) / 16);
+    const char *src = reinterpret_cast<const char *>(Wg + (size_t)k0 * row_elems);
+    char *dst = reinterpret_cast<char *>(W_s + (size_t)(ch & 1) * KT * row_elems);
+    for (int i = tid; i < n16; i += NT) cp_async16(dst + (size_t)i * 16, src + (size_t)i * 16);
+    cp_async_commit();
+  };
+  T rs[kRB];
+#pragma unroll
+  for (int rb = 0; rb < kRB; ++rb) rs[rb] = rs_s ? rs_s[(tb * kRB + rb) * rs_stride] : T(1);
+  issue(0);
+  for (int ch = 0; ch < nchunks; ++ch) {
+    if (ch + 1 < nchunks) {
+      issue(ch + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const int k0 = ch * KT;
+    const int kt = min(KT, K - k0);
+    const T *Wb = W_s + (size_t)(ch & 1) * KT * row_elems;
+    for (int kk = 0; kk < kt; ++kk) {
+      T vv[kRB];
+#pragma unroll
+      for (int rb = 0; rb < kRB; ++rb) vv[rb] = v_s[(tb * kRB + rb) * chip + k0 + kk] * rs[rb];
+      for (int s = 0; s < D; ++s) {
+        T a[kRB];
+#pragma unroll
+        for (int rb = 0; rb < kRB; ++rb) a[rb] = vv[rb] * phi_s[(tb * kRB + rb) * D + s];
+        const T *wrow = Wb + (size_t)(kk * D + s) * chip;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          int n0 = (g * TN + tn) * kRN;
+          if (n0 < chip) {
+            T w[kRN];
+            lds_vec<T, kRN>(wrow + n0, w);
+#pragma unroll
+            for (int rb = 0; rb < kRB; ++rb)
+#pragma unroll
+              for (int rn = 0; rn < kRN; ++rn) acc[g][rb][rn] = fma(a[rb], w[rn], acc[g][rb][rn]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T, int NG> __device__ __forceinline__ void zero_acc(T (&acc)[NG][kRB][kRN]) {
+#pragma unroll
+  for (int g = 0; g < NG; ++g)
+#pragma unroll
+    for (int rb = 0; rb < kRB; ++rb)
+#pragma unroll
+      for (int rn = 0; rn < kRN; ++rn) acc[g][rb][rn] = T(0);
+}
+
+// phi_s[row][s] for the CTA's rows at one site
+template <typename T>
+__device__ __forceinline__ void load_phi(const MpsArgs<T> &A, long long b0, int BT, int site, T *phi_s) {
+  for (int r = threadIdx.x; r < BT; r += blockDim.x) {
+    long long b = b0 + r;
+    T xv = b < A.B ? A.x[(size_t)b * A.L + site] : T(0.5);
+    T ph[kMaxPhys];
+    embed_site(A.emb, xv, ph);
+    for (int s = 0; s < A.D; ++s) phi_s[r * A.D + s] = ph[s];
+  }
+}
+
+// copy rows [b0, b0+BT) of an environment into smem (zero beyond the batch)
+template <typename T>
+__device__ __forceinline__ void load_env(const T *env, long long b0, long long B, int BT, int chip, T *dst) {
+  for (int i = threadIdx.x; i < BT * chip; i += blockDim.x) {
+    int r = i / chip;
+    long long b = b0 + r;
+    dst[i] = b < B ? env[(size_t)b * chip + (i - r * chip)] : T(0);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Environment sweep.  grid = (sample tiles, 2 halves).  adjoint = 0: forward environments
+// F (left half: bonds 0..c, right half: bonds L..c+1).  adjoint = 1: seeds G[c] / G[c+1]
+// through the class site from dLoss/dy', then the adjoint chains towards the boundaries,
+// reusing the forward exponents delta_j.
+// ---------------------------------------------------------------------------------------
+template <typename T, int NG>
+__global__ void __launch_bounds__(256) mps_sweep_kernel(MpsArgs<T> A, int adjoint) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int TN = A.TN, TB = blockDim.x / TN, BT = TB * kRB;
+  const int chip = A.chip, D = A.D, C = A.C, c = A.c, L = A.L;
+  T *v_s = reinterpret_cast<T *>(smem_raw);
+  T *W_s = v_s + (size_t)BT * chip;
+  T *phi_s = W_s + (size_t)2 * A.KT * D * chip;
+  T *dy_s = phi_s + (size_t)BT * D;
+  const int tid = threadIdx.x;
+  const int tn = tid % TN, tb = tid / TN;
+  const int half = blockIdx.y;
+  const long long b0 = (long long)blockIdx.x * BT;
+
+  int site0, nsites, dir;
+  bool transposed;
+  if (!adjoint) {
+    if (half == 0) { site0 = 0; nsites = c; dir = 1; transposed = false; }
+    else { site0 = L - 1; nsites = L - 1 - c; dir = -1; transposed = true; }
+  } else {
+    if (half == 0) { if (c == 0) return; site0 = c - 1; nsites = c - 1; dir = -1; transposed = true; }
+    else { if (c == L - 1) return; site0 = c + 1; nsites = L - 2 - c; dir = 1; transposed = false; }
+  }
+
+  T acc[NG][kRB][kRN];
+  int esum_r[kRB] = {0, 0, 0, 0};
+
+  auto store_env = [&](T *env, const T(&sc)[kRB]) {
+    // acc * sc -> v_s and (optionally) global env
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      int n0 = (g * TN + tn) * kRN;
+      if (n0 < chip) {
+#pragma unroll
+        for (int rb = 0; rb < kRB; ++rb) {
+          int r = tb * kRB + rb;
+          long long b = b0 + r;
+#pragma unroll
+          for (int rn = 0; rn < kRN; ++rn) {
+            T val = acc[g][rb][rn] * sc[rb];
+            v_s[r * chip + n0 + rn] = val;
+            if (env && b < A.B) env[(size_t)b * chip + n0 + rn] = val;
+          }
+        }
+      }
+    }
+  };
+
+  if (!adjoint) {
+    // boundary vector e_0 (bond dimension 1 zero-padded to chip)
+    T *env = mps_fenv(A, half == 0 ? 0 : L);
+    for (int i = tid; i < BT * chip; i += blockDim.x) {
+      int r = i / chip, n = i - r * chip;
+      T val = n == 0 ? T(1) : T(0);
+      v_s[i] = val;
+      long long b = b0 + r;
+      if (env && b < A.B) env[(size_t)b * chip + n] = val;
+    }
+  } else {
+    // seed through the class site:  G[c] = sum_k dy_k M_c^k F[c+1]   /   G[c+1] = sum_k dy_k F[c] M_c^k
+    for (int r = tid; r < BT; r += blockDim.x) {
+      long long b = b0 + r;
+      T dyl[kMaxOut];
+      if (b < A.B) {
+        T yl[kMaxOut], tl[kMaxOut];
+        for (int k = 0; k < C; ++k) {
+          yl[k] = A.y[(size_t)b * C + k];
+          tl[k] = A.targets ? A.targets[(size_t)b * C + k] : T(0);
+        }
+        int E = A.esum[b] + A.esum[A.B + b];
+        mps_head(A.head, C, yl, E, tl, A.cw, dyl);
+        for (int k = 0; k < C; ++k) {
+          dyl[k] *= A.loss_scale;
+          A.dy[(size_t)b * C + k] = dyl[k];
+        }
+      } else {
+        for (int k = 0; k < C; ++k) dyl[k] = T(0);
+      }
+      for (int k = 0; k < C; ++k) dy_s[r * C + k] = dyl[k];
+    }
+    load_env(mps_fenv(A, half == 0 ? c + 1 : c), b0, A.B, BT, chip, v_s);
+    load_phi(A, b0, BT, c, phi_s);
+    __syncthreads();
+    zero_acc<T, NG>(acc);
+    const T *Wc = (half == 0 ? A.Wt : A.Wn) + (size_t)c * chip * D * chip;
+    for (int k = 0; k < C; ++k)
+      step_gemm<T, NG>(Wc + (size_t)k * chip * D * chip, chip, D, chip, A.KT, v_s, phi_s, dy_s + k, C, W_s,
+                       acc, tb, tn, TN);
+    const T one[kRB] = {T(1), T(1), T(1), T(1)};
+    store_env(A.G + (size_t)(half == 0 ? c : c + 1) * A.B * chip, one);
+  }
+  __syncthreads();
+
+  for (int step = 0; step < nsites; ++step) {
+    const int site = site0 + step * dir;
+    const int bond_out = transposed ? site : site + 1;
+    load_phi(A, b0, BT, site, phi_s);
+    __syncthreads();
+    zero_acc<T, NG>(acc);
+    const T *W = (transposed ? A.Wt : A.Wn) + (size_t)mps_slab(A, site) * chip * D * chip;
+    step_gemm<T, NG>(W, chip, D, chip, A.KT, v_s, phi_s, (const T *)nullptr, 0, W_s, acc, tb, tn, TN);
+    T sc[kRB];
+    if (!adjoint) {
+      T m[kRB];
+#pragma unroll
+      for (int rb = 0; rb < kRB; ++rb) {
+        m[rb] = T(0);
+#pragma unroll
+        for (int g = 0; g < NG; ++g)
+#pragma unroll
+          for (int rn = 0; rn < kRN; ++rn) m[rb] = Num<T>::max(m[rb], Num<T>::abs(acc[g][rb][rn]));
+        for (int off = TN >> 1; off > 0; off >>= 1)
+          m[rb] = Num<T>::max(m[rb], __shfl_xor_sync(0xffffffffu, m[rb], off));
+        int e = 0;
+        if (m[rb] > T(0)) Num<T>::frexp(m[rb], &e);
+        sc[rb] = Num<T>::ldexp(T(1), -e);
+        esum_r[rb] += e;
+        long long b = b0 + tb * kRB + rb;
+        if (tn == 0 && b < A.B) A.exps[(size_t)site * A.B + b] = e;
+      }
+      store_env(mps_fenv(A, bond_out), sc);
+    } else {
+#pragma unroll
+      for (int rb = 0; rb < kRB; ++rb) {
+        long long b = b0 + tb * kRB + rb;
+        int e = b < A.B ? A.exps[(size_t)site * A.B + b] : 0;
+        sc[rb] = Num<T>::ldexp(T(1), -e);
+      }
+      store_env(A.G + (size_t)bond_out * A.B * chip, sc);
+    }
+    __syncthreads();
+  }
+  if (!adjoint && tn == 0) {
+#pragma unroll
+    for (int rb = 0; rb < kRB; ++rb) {
+      long long b = b0 + tb * kRB + rb;
+      if (b < A.B) A.esum[(size_t)half * A.B + b] = esum_r[rb];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Class site + head:  y'[b,k] = F[c][b,:] . M_c^k[b] . F[c+1][b,:]   then the loss head.
+// ---------------------------------------------------------------------------------------
+template <typename T, int NG>
+__global__ void __launch_bounds__(256) mps_class_kernel(MpsArgs<T> A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int TN = A.TN, TB = blockDim.x / TN, BT = TB * kRB;
+  const int chip = A.chip, D = A.D, C = A.C, c = A.c;
+  T *v_s = reinterpret_cast<T *>(smem_raw);
+  T *W_s = v_s + (size_t)BT * chip;
+  T *phi_s = W_s + (size_t)2 * A.KT * D * chip;
+  T *y_s = phi_s + (size_t)BT * D;
+  T *fr_s = y_s + (size_t)BT * C;
+  __shared__ double red_s[8];
+  const int tid = threadIdx.x;
+  const int tn = tid % TN, tb = tid / TN;
+  const long long b0 = (long long)blockIdx.x * BT;
+
+  load_env(mps_fenv(A, c), b0, A.B, BT, chip, v_s);
+  load_env(mps_fenv(A, c + 1), b0, A.B, BT, chip, fr_s);
+  load_phi(A, b0, BT, c, phi_s);
+  __syncthreads();
+  T acc[NG][kRB][kRN];
+  const T *Wc = A.Wn + (size_t)c * chip * D * chip;
+  for (int k = 0; k < C; ++k) {
+    zero_acc<T, NG>(acc);
+    step_gemm<T, NG>(Wc + (size_t)k * chip * D * chip, chip, D, chip, A.KT, v_s, phi_s, (const T *)nullptr, 0,
+                     W_s, acc, tb, tn, TN);
+#pragma unroll
+    for (int rb = 0; rb < kRB; ++rb) {
+      int r = tb * kRB + rb;
+      T part = T(0);
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        int n0 = (g * TN + tn) * kRN;
+        if (n0 < chip) {
+#pragma unroll
+          for (int rn = 0; rn < kRN; ++rn) part = fma(acc[g][rb][rn], fr_s[r * chip + n0 + rn], part);
+        }
+      }
+      for (int off = TN >> 1; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+      if (tn == 0) y_s[r * C + k] = part;
+    }
+  }
+  __syncthreads();
+  double lsum = 0.0;
+  for (int r = tid; r < BT; r += blockDim.x) {
+    long long b = b0 + r;
+    if (b < A.B) {
+      T yl[kMaxOut], tl[kMaxOut];
+      for (int k = 0; k < C; ++k) {
+        yl[k] = y_s[r * C + k];
+        tl[k] = A.targets ? A.targets[(size_t)b * C + k] : T(0);
+        A.y[(size_t)b * C + k] = yl[k];
+        if (A.out) A.out[(size_t)b * C + k] = yl[k];
+      }
+      int E = A.esum[b] + A.esum[A.B + b];
+      if (A.out_exp) A.out_exp[b] = E;
+      T l = mps_head(A.head, C, yl, E, tl, A.cw, (T *)nullptr);
+      if (A.loss) A.loss[b] = l;
+      lsum += (double)l;
+    }
+  }
+  if (A.loss_sum) {
+    for (int off = 16; off > 0; off >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
+    if ((tid & 31) == 0) red_s[tid >> 5] = lsum;
+    __syncthreads();
+    if (tid == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) tot += red_s[w];
+      atomicAdd(A.loss_sum, tot);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Weight gradients (K4):  dA_j[a,r,s(,k)] += sum_b w[b] U[b,a] phi_j[b,s] V[b,r]
+//   j < c : U = F[j],  V = G[j+1], w = 2^-delta_j        j > c : U = G[j], V = F[j+1], w = 2^-delta_j
+//   j = c : U = F[c],  V = F[c+1], w = dy'[b,k]
+// grid = (tiles * splits, L, D * n_j); 16x16 threads, 4x4 micro-tile, 64x64 output tile.
+// ---------------------------------------------------------------------------------------
+template <typename T> struct DaArgs {
+  MpsArgs<T> M;
+  T *grads;  // packed layout, chi (unpadded) strides
+  int tiles_a, tiles_r, nsplit;
+  long long bchunk;  // samples per split
+  int only_site;     // >= 0: this site only (the class site); < 0: site = blockIdx.y, class site skipped
+};
+
+template <typename T> __global__ void __launch_bounds__(256) mps_da_kernel(DaArgs<T> P) {
+  const MpsArgs<T> &A = P.M;
+  constexpr int TA = 64, TR = 64, BK = 16;
+  __shared__ __align__(16) T U_s[BK][TA];
+  __shared__ __align__(16) T V_s[BK][TR];
+  __shared__ T w_s[BK];
+  const int site = P.only_site >= 0 ? P.only_site : (int)blockIdx.y;
+  const int c = A.c, chip = A.chip, chi = A.chi, D = A.D, C = A.C;
+  if (P.only_site < 0 && site == c) return;
+  const int nj = site == c ? C : 1;
+  const int z = blockIdx.z;
+  const int s = z / nj, kcls = z - s * nj;
+  int bx = blockIdx.x;
+  const int split = bx % P.nsplit;
+  bx /= P.nsplit;
+  const int tr = bx % P.tiles_r, ta = bx / P.tiles_r;
+  const int a0 = ta * TA, r0 = tr * TR;
+  const T *U = site <= c ? mps_fenv(A, site) : A.G + (size_t)site * A.B * chip;
+  const T *V = site < c ? A.G + (size_t)(site + 1) * A.B * chip : mps_fenv(A, site + 1);
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  T acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+  const long long bbeg = (long long)split * P.bchunk;
+  const long long bend = min(A.B, bbeg + P.bchunk);
+  for (long long bb = bbeg; bb < bend; bb += BK) {
+    if (tid < BK) {
+      long long b = bb + tid;
+      T w = T(0);
+      if (b < bend) {
+        T ph[kMaxPhys];
+        embed_site(A.emb, A.x[(size_t)b * A.L + site], ph);
+        w = ph[s];
+        if (site == c) w *= A.dy[(size_t)b * C + kcls];
+        else w *= Num<T>::ldexp(T(1), -A.exps[(size_t)site * A.B + b]);
+      }
+      w_s[tid] = w;
+    }
+    __syncthreads();
+    for (int i = tid; i < BK * TA; i += 256) {
+      int kk = i / TA, col = i - kk * TA;
+      long long b = bb + kk;
+      bool ok = b < bend;
+      U_s[kk][col] = (ok && a0 + col < chip) ? U[(size_t)b * chip + a0 + col] * w_s[kk] : T(0);
+      V_s[kk][col] = (ok && r0 + col < chip) ? V[(size_t)b * chip + r0 + col] : T(0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      T u[4], v[4];
+      lds_vec<T, 4>(&U_s[kk][ty * 4], u);
+      lds_vec<T, 4>(&V_s[kk][tx * 4], v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(u[i], v[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  // scatter into the packed layout [a][r][s][k]
+  const size_t site_off = (size_t)site * chi * chi * D + (site > c ? (size_t)chi * chi * D * (C - 1) : 0);
+  T *g = P.grads + site_off;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int a = a0 + ty * 4 + i;
+    if (a >= chi) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int r = r0 + tx * 4 + j;
+      if (r >= chi) continue;
+      atomicAdd(&g[(((size_t)a * chi + r) * D + s) * nj + kcls], acc[i][j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Weight re-layout (once per step; parameters are tiny next to the batch work):
+//   packed A_j[a][r][s][o]  ->  Wn[slab][k=a][s][n=r] and Wt[slab][k=r][s][n=a], zero padded to chip.
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void mps_prep_kernel(const T *__restrict__ params, T *__restrict__ Wn, T *__restrict__ Wt, int L,
+                                int chi, int chip, int D, int C, int c) {
+  const int nslab = L - 1 + C;
+  const size_t slab_elems = (size_t)chip * D * chip;
+  const size_t total = slab_elems * nslab;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int slab = (int)(i / slab_elems);
+    size_t rem = i - (size_t)slab * slab_elems;
+    int k = (int)(rem / ((size_t)D * chip));
+    int s = (int)((rem / chip) % D);
+    int n = (int)(rem % chip);
+    int site, o, nj;
+    if (slab < c) { site = slab; o = 0; nj = 1; }
+    else if (slab < c + C) { site = c; o = slab - c; nj = C; }
+    else { site = slab - C + 1; o = 0; nj = 1; }
+    const size_t site_off = (size_t)site * chi * chi * D + (site > c ? (size_t)chi * chi * D * (C - 1) : 0);
+    T vn = T(0), vt = T(0);
+    if (k < chi && n < chi) {
+      vn = params[site_off + (((size_t)k * chi + n) * D + s) * nj + o];
+      vt = params[site_off + (((size_t)n * chi + k) * D + s) * nj + o];
+    }
+    Wn[i] = vn;
+    Wt[i] = vt;
+  }
+}
+
+template <typename T>
+__global__ void embed_kernel(EmbParams<T> e, long long n, const T *__restrict__ x, T *__restrict__ phi) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  T ph[kMaxPhys];
+  feature_map(e, x[i], ph);
+  for (int s = 0; s < e.d; ++s) phi[i * e.d + s] = ph[s];
+}
+
+}  // namespace tnb

@@ -1,0 +1,156 @@
+"""Host side of the drop-in seam: ``loss_fn`` / ``value_and_grad`` on the C-ABI.
+
+Replaces, for one (model, embedding, loss) triple,
+    loss_fn(data, targets, *params)            tn4ml/models/model.py:723-751
+    value_and_grad(params, data, targets)      tn4ml/models/model.py:554-566
+    evaluate()'s per-sample closure            tn4ml/models/model.py:1048-1076
+    predict()/forward()                        tn4ml/models/model.py:278-368
+PyTorch is used for device memory and streams only; every number is produced by the
+kernels in ``csrc/`` through ``tnb_forward`` / ``tnb_backward``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .embeddings import Embedding, spec_of
+from .metrics import LossExpr
+
+
+def _dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float64:
+        return _lib.F64
+    if dt == torch.float32:
+        return _lib.F32
+    raise TypeError(f"dtype {dt} is not supported (float32 / float64)")
+
+
+class Engine:
+    """One contraction problem bound to a CUDA device."""
+
+    def __init__(self, *, kind: int, L: int, chi: int, d: int, n_out: int, out_site: int, spacing: int,
+                 embedding: Embedding, loss: LossExpr | None, dtype: torch.dtype, device: torch.device,
+                 precision: int = _lib.PREC_SIMT, max_microbatch: int | None = None):
+        if device.type != "cuda":
+            raise RuntimeError("tn4ml_b200 runs on CUDA devices only (no CPU fallback)")
+        self.lib = _lib.lib()
+        self.dtype, self.device = dtype, device
+        p = _lib.TnbProblem()
+        p.kind, p.dtype, p.precision = kind, _dtype_code(dtype), precision
+        p.L, p.chi, p.d, p.n_out, p.out_site, p.spacing = L, chi, d, n_out, out_site, max(spacing, 1)
+        head = loss.head if loss is not None else (_lib.HEAD_TSN if kind == _lib.KIND_SMPO else
+                                                   (_lib.HEAD_NLL if n_out == 1 else _lib.HEAD_SOFTMAX_XENT))
+        p.head = head
+        p.emb = spec_of(embedding)
+        if loss is not None and loss.class_weights is not None:
+            for i, v in enumerate(loss.class_weights):
+                p.class_weights[i] = v
+        self.prob = p
+        self.n_params = int(self.lib.tnb_param_count(C.byref(p)))
+        if self.lib.tnb_workspace_bytes(C.byref(p), 1, 0) < 0:
+            msg = self.lib.tnb_last_error().decode()
+            if "physical dimension" in msg:
+                raise AssertionError(msg)  # metrics.py:34
+            raise ValueError("tn4ml_b200: " + msg)
+        self.max_microbatch = max_microbatch
+        self._ws = {}
+        self._loss_sum = torch.zeros(1, dtype=torch.float64, device=device)
+
+    # -- workspace ----------------------------------------------------------------
+    def _workspace(self, batch: int, need_grad: bool) -> torch.Tensor:
+        key = (batch, need_grad)
+        ws = self._ws.get(key)
+        if ws is None:
+            nbytes = self.lib.tnb_workspace_bytes(C.byref(self.prob), batch, int(need_grad))
+            if nbytes < 0:
+                raise RuntimeError("tn4ml_b200: " + self.lib.tnb_last_error().decode())
+            self._ws.clear()  # keep one workspace alive at a time
+            ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            self._ws[key] = ws
+        return ws
+
+    def microbatch(self, batch: int, need_grad: bool) -> int:
+        """Largest micro-batch whose workspace stays under ~60% of free HBM."""
+        if self.max_microbatch:
+            return min(batch, self.max_microbatch)
+        free, _ = torch.cuda.mem_get_info(self.device)
+        mb = batch
+        while mb > 1024:
+            nbytes = self.lib.tnb_workspace_bytes(C.byref(self.prob), mb, int(need_grad))
+            if nbytes <= 0.6 * free:
+                break
+            mb = (mb + 1) // 2
+        return mb
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _prep(self, x, targets):
+        x = torch.as_tensor(x)
+        if x.device != self.device or x.dtype != self.dtype:
+            x = x.to(self.device, self.dtype, non_blocking=True)
+        x = x.contiguous()
+        if x.ndim != 2 or x.shape[1] < self.prob.L:
+            raise ValueError(f"Input data must have at least {self.prob.L} elements!")  # model.py:306-307
+        if x.shape[1] != self.prob.L:
+            raise NotImplementedError("len(model) < len(data) is not on the fused path")
+        if targets is not None:
+            targets = torch.as_tensor(targets)
+            if targets.device != self.device or targets.dtype != self.dtype:
+                targets = targets.to(self.device, self.dtype, non_blocking=True)
+            targets = targets.contiguous().reshape(x.shape[0], -1)
+            if targets.shape[1] != self.prob.n_out:
+                raise ValueError(f"targets must have {self.prob.n_out} columns, got {targets.shape[1]}")
+        return x, targets
+
+    # -- forward only -------------------------------------------------------------
+    def forward(self, params: torch.Tensor, x, targets=None, want_loss=True):
+        """Per-sample losses [B], output mantissas [B, n_out] (or [B]) and exponents [B]."""
+        x, targets = self._prep(x, targets)
+        B = x.shape[0]
+        smpo = self.prob.kind == _lib.KIND_SMPO
+        loss = torch.empty(B, dtype=self.dtype, device=self.device)
+        out = torch.empty((B,) if smpo else (B, self.prob.n_out), dtype=self.dtype, device=self.device)
+        oexp = torch.empty(B, dtype=torch.int32, device=self.device)
+        if want_loss and not smpo and self.prob.head != _lib.HEAD_NLL and targets is None:
+            raise ValueError("supervised heads need targets")
+        if not want_loss and targets is None and not smpo and self.prob.head != _lib.HEAD_NLL:
+            targets = torch.zeros(B, self.prob.n_out, dtype=self.dtype, device=self.device)
+            targets[:, 0] = 1
+        mb = self.microbatch(B, False)
+        with torch.cuda.device(self.device):
+            for s in range(0, B, mb):
+                e = min(B, s + mb)
+                ws = self._workspace(e - s, False)
+                t_ptr = targets[s:e].data_ptr() if targets is not None else None
+                _lib.check(self.lib.tnb_forward(
+                    C.byref(self.prob), e - s, x[s:e].data_ptr(), t_ptr, params.data_ptr(), loss[s:e].data_ptr(),
+                    None, out[s:e].data_ptr(), oexp[s:e].data_ptr(), 0, ws.data_ptr(), ws.numel(), self._stream()))
+        return loss, out, oexp
+
+    # -- forward + backward -------------------------------------------------------
+    def value_and_grad(self, params: torch.Tensor, x, targets=None, *, denom: int | None = None,
+                       grads: torch.Tensor | None = None, accumulate: bool = False):
+        """(sum_b loss_b as a device float64 scalar, packed gradients of sum_b loss_b / denom)."""
+        x, targets = self._prep(x, targets)
+        B = x.shape[0]
+        denom = B if denom is None else denom
+        if grads is None:
+            grads = torch.empty(self.n_params, dtype=self.dtype, device=self.device)
+            accumulate = False
+        self._loss_sum.zero_()
+        mb = self.microbatch(B, True)
+        with torch.cuda.device(self.device):
+            for s in range(0, B, mb):
+                e = min(B, s + mb)
+                ws = self._workspace(e - s, True)
+                t_ptr = targets[s:e].data_ptr() if targets is not None else None
+                _lib.check(self.lib.tnb_forward(
+                    C.byref(self.prob), e - s, x[s:e].data_ptr(), t_ptr, params.data_ptr(), None,
+                    self._loss_sum.data_ptr(), None, None, 1, ws.data_ptr(), ws.numel(), self._stream()))
+                _lib.check(self.lib.tnb_backward(
+                    C.byref(self.prob), e - s, x[s:e].data_ptr(), t_ptr, params.data_ptr(), 1.0 / denom,
+                    grads.data_ptr(), int(accumulate or s > 0), ws.data_ptr(), ws.numel(), self._stream()))
+        return self._loss_sum, grads

@@ -1,0 +1,530 @@
+"""``Model``: the training seam of tn4ml (tn4ml/models/model.py) on the B200-native kernels.
+
+Same public surface as the reference for the data-parallel path: ``configure``, ``train``,
+``evaluate``, ``predict``, ``forward``, ``accuracy``, ``update_tensors``, ``arrays``,
+``tensors``, ``norm``, ``normalize``, ``nparams``, ``save`` / ``load_model``.  The site
+tensors are views of one packed device buffer (layout in ``include/tn4ml_b200.h``); the
+``loss_fn -> value_and_grad`` step runs in ``csrc/`` through :class:`tn4ml_b200.engine.Engine`.
+"""
+from __future__ import annotations
+
+import copy as _copy
+import logging
+import pickle
+from time import time
+from typing import Any, Callable, Sequence
+
+import numpy as np
+import torch
+
+from .. import _lib, optim
+from ..embeddings import Embedding, TrigonometricEmbedding
+from ..engine import Engine
+from ..metrics import LossExpr, resolve
+from ..util import EarlyStopping, TrainingType
+
+logger = logging.getLogger(__name__)
+
+
+def _torch_dtype(dtype) -> torch.dtype:
+    if isinstance(dtype, torch.dtype):
+        return dtype
+    return torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+
+
+class SiteTensor:
+    """Minimal stand-in for ``quimb.tensor.Tensor``: ``.data``, ``.shape``, ``.modify(data=)``."""
+
+    def __init__(self, model: "Model", i: int):
+        self._m, self._i = model, i
+
+    @property
+    def data(self) -> torch.Tensor:
+        return self._m.arrays[self._i]
+
+    @property
+    def shape(self):
+        return tuple(self._m._shapes[self._i])
+
+    def modify(self, data=None):
+        if data is not None:
+            self._m.arrays[self._i].copy_(torch.as_tensor(data).to(self._m._packed))
+
+
+class Model:
+    """Trainable tensor network whose site tensors live in one packed device buffer."""
+
+    kind = _lib.KIND_MPS
+
+    def __init__(self, arrays: Sequence[Any], *, n_out: int = 1, out_site: int | None = None, spacing: int = 0,
+                 dtype=None, device: Any = None):
+        arrays = [torch.as_tensor(np.asarray(a) if not torch.is_tensor(a) else a) for a in arrays]
+        if dtype is None:
+            dtype = arrays[0].dtype if arrays[0].dtype in (torch.float32, torch.float64) else torch.float64
+        self.dtype = _torch_dtype(dtype)
+        self.L = len(arrays)
+        self.n_out, self.spacing = n_out, spacing
+        self.out_site = out_site if out_site is not None else self.L - 1
+        self._shapes = [tuple(a.shape) for a in arrays]
+        self._canon = [self._canon_index(i, s) for i, s in enumerate(self._shapes)]
+        self.chi = max(max(c[0], c[1]) for c in self._canon)
+        self.phys_dim = self._canon[0][2]
+        self.loss: Callable | None = None
+        self.strategy: Any = "global"
+        self.optimizer: Any = optim.adam
+        self.learning_rate = 1e-3
+        self.train_type = TrainingType.UNSUPERVISED
+        self.gradient_transforms = None
+        self.device = ("gpu", 0)
+        self._engine_cache: dict = {}
+        self.precision = _lib.PREC_SIMT
+        self.process_group = None  # torch.distributed group for data-parallel training
+        if device is None:  # CPU tensors are storage only (layout tests); every compute call needs CUDA
+            device = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+        self._build_packed(arrays, torch.device(device))
+
+    # ---- layout -----------------------------------------------------------------
+    def _site_nout(self, i: int) -> int:
+        if self.kind == _lib.KIND_SMPO:
+            return self.n_out if i % self.spacing == 0 else 1
+        return self.n_out if (i == self.out_site and self.n_out > 1) else 1
+
+    def _canon_index(self, i: int, shape):
+        """(chi_l, chi_r, d, n_i, index) : how the reference-shaped site maps into its slab."""
+        raise NotImplementedError
+
+    def _site_offsets(self):
+        per = self.chi * self.chi * self.phys_dim
+        offs, o = [], 0
+        for i in range(self.L):
+            offs.append(o)
+            o += per * self._site_nout(i)
+        return offs, o
+
+    def _views(self, packed: torch.Tensor):
+        offs, _ = self._site_offsets()
+        out = []
+        for i in range(self.L):
+            cl, cr, d, nj, idx = self._canon[i]
+            slab = packed[offs[i]: offs[i] + self.chi * self.chi * d * nj].view(self.chi, self.chi, d, nj)
+            out.append(slab[idx])
+        return tuple(out)
+
+    def _build_packed(self, arrays, dev: torch.device):
+        _, total = self._site_offsets()
+        self._packed = torch.zeros(total, dtype=self.dtype, device=dev)
+        self._arrays = self._views(self._packed)
+        for v, a in zip(self._arrays, arrays):
+            if tuple(v.shape) != tuple(a.shape):
+                raise ValueError(f"site shape {tuple(a.shape)} does not fit the layout {tuple(v.shape)}")
+            v.copy_(a.to(dev, self.dtype))
+
+    # ---- reference surface --------------------------------------------------------
+    @property
+    def arrays(self):
+        return self._arrays
+
+    @property
+    def tensors(self):
+        return [SiteTensor(self, i) for i in range(self.L)]
+
+    def nparams(self) -> int:
+        return int(sum(int(np.prod(s)) for s in self._shapes))  # model.py:146-153
+
+    def update_tensors(self, params):  # model.py:467-490
+        for v, a in zip(self._arrays, params):
+            if v.data_ptr() != torch.as_tensor(a).data_ptr():
+                v.copy_(torch.as_tensor(a).to(v))
+
+    def copy(self, virtual: bool = False, deep: bool = False):
+        new = _copy.copy(self)
+        new._engine_cache = {}
+        if not virtual:
+            new._packed = self._packed.clone()
+            new._arrays = new._views(new._packed)
+        if deep and hasattr(self, "history"):
+            new.history = _copy.deepcopy(self.history)
+        return new
+
+    def to(self, device):
+        dev = torch.device(device)
+        self._packed = self._packed.to(dev)
+        self._arrays = self._views(self._packed)
+        self._engine_cache = {}
+        return self
+
+    def save(self, model_name, dir_name="~", tn=False):  # model.py:105-144 (pickle of the model)
+        import os
+        path = os.path.join(os.path.expanduser(dir_name), f"{model_name}.pkl")
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        state = self.__dict__.copy()
+        state["_packed"] = self._packed.cpu()
+        for k in ("_arrays", "_engine_cache", "step", "opt_state", "loss_func", "process_group"):
+            state.pop(k, None)
+        with open(path, "wb") as f:
+            pickle.dump((self.__class__, state), f)
+
+    # ---- model-only operations (plain device tensor algebra) -----
+    def _canon4(self, i: int) -> torch.Tensor:
+        offs, _ = self._site_offsets()
+        cl, cr, d, nj, _ = self._canon[i]
+        return self._packed[offs[i]: offs[i] + self.chi * self.chi * d * nj].view(self.chi, self.chi, d, nj)[:cl, :cr]
+
+    def norm(self, **_opts) -> torch.Tensor:
+        """sqrt(<A|A>) by a transfer-matrix sweep (tn.py:66-80, smpo.py:234-248)."""
+        E = torch.ones(1, 1, dtype=self.dtype, device=self._packed.device)
+        logscale = 0.0
+        for i in range(self.L):
+            A = self._canon4(i)
+            E = torch.einsum("lm,lrsk,mnsk->rn", E, A, A)
+            s = E.abs().max()
+            E = E / s
+            logscale = logscale + torch.log(s)
+        return torch.exp(0.5 * (torch.log(E[0, 0]) + logscale))
+
+    def normalize(self, insert=None):
+        """tn.py:82-113 / mps.py:34-51 / smpo.py:208-232.  L > 200 uses the reference's
+        site-by-site scheme in its norm-only form (each site divided by its Frobenius norm)."""
+        if self.L > 200:
+            for v in self._arrays:
+                v.div_(torch.linalg.norm(v))
+            return
+        nrm = self.norm()
+        if insert is None:
+            self._packed.div_(nrm ** (1.0 / self.L))
+        else:
+            self._arrays[insert].div_(nrm)
+
+    # ---- configure (model.py:155-276) ---------------------------------------------
+    def configure(self, **kwargs):
+        for key, value in kwargs.items():
+            if key == "strategy":
+                if value in ["global", "sgd", "gd", "gradient_descent"]:
+                    self.strategy = "global"
+                elif value in ["sweeps", "local", "dmrg", "dmrg-like", "sweeps-one-way",
+                               "sweeps-one-way-per-site", "sweeps-per-site"]:
+                    raise NotImplementedError("the Sweeps strategy is outside the data-parallel hot path")
+                else:
+                    raise ValueError(f'Strategy "{value}" not found')
+            elif key in ["optimizer", "loss", "train_type", "learning_rate", "gradient_transforms", "device",
+                         "precision", "process_group"]:
+                setattr(self, key, value)
+            else:
+                raise AttributeError(f"Attribute {key} not found")
+        if self.train_type not in [TrainingType.UNSUPERVISED, TrainingType.SUPERVISED, TrainingType.TARGET_TN]:
+            raise AttributeError("Specify type of training: UNSUPERVISED, SUPERVISED, or TARGET_TN!")
+        if self.train_type == TrainingType.TARGET_TN:
+            raise NotImplementedError("TARGET_TN has no batched contraction; it stays on the reference path")
+        if self.gradient_transforms:
+            self._opt = optim.chain(*self.gradient_transforms)
+        elif callable(self.optimizer) and not isinstance(self.optimizer, optim.GradientTransformation):
+            self._opt = self.optimizer(learning_rate=self.learning_rate)
+        elif isinstance(self.optimizer, optim.GradientTransformation):
+            self._opt = self.optimizer
+        else:
+            self._opt = optim.adam(learning_rate=self.learning_rate)
+        if isinstance(self.device, str):  # README form: device='gpu'  
+            self.device = (self.device, 0)
+        if len(self.device) != 2 or not isinstance(self.device, tuple):
+            raise AttributeError("Device must be a tuple of (str, int)!")
+        if self.device[0] not in ["cpu", "gpu"]:
+            raise AttributeError("Device must be 'cpu' or 'gpu'!")
+        if self.device[0] == "cpu":
+            raise RuntimeError("Device 'cpu' was requested but tn4ml_b200 has no CPU path; use ('gpu', i).")
+        if not torch.cuda.is_available() or self.device[1] >= torch.cuda.device_count():
+            raise RuntimeError(f"Device '{self.device[0]}' was requested but no such device is available.")
+        self.to(torch.device("cuda", self.device[1]))
+        logger.info("backend=tn4ml_b200 | requested=%s:%s", self.device[0], self.device[1])
+
+    # ---- engine -------------------------------------------------------------------
+    def _engine(self, embedding: Embedding, loss_fn, supervised: bool, dtype) -> tuple[Engine, LossExpr | None]:
+        dt = _torch_dtype(dtype) if dtype is not None else self.dtype
+        if dt != self.dtype:
+            self._packed = self._packed.to(dt)
+            self.dtype = dt
+            self._arrays = self._views(self._packed)
+            self._engine_cache = {}
+        expr = None
+        if loss_fn is not None:
+            expr = resolve(loss_fn, self, self.L, embedding.dim, supervised)
+        key = (id(embedding), None if expr is None else (expr.head, expr.class_weights), dt, self.precision)
+        eng = self._engine_cache.get(key)
+        if eng is None:
+            eng = Engine(kind=self.kind, L=self.L, chi=self.chi, d=self.phys_dim, n_out=self.n_out,
+                         out_site=self.out_site, spacing=self.spacing, embedding=embedding, loss=expr, dtype=dt,
+                         device=self._packed.device, precision=self.precision)
+            self._engine_cache[key] = eng
+        return eng, expr
+
+    def _reg_value_and_grad(self, expr: LossExpr):
+        """Model-only regularisers (metrics.py:89-168): value and packed gradient by autograd
+        over the transfer-matrix norm.  Batch independent; not part of the fused kernels."""
+        if not expr or not expr.regs:
+            return None, None
+        p = self._packed.detach().clone().requires_grad_(True)
+        saved = self._packed
+        self._packed = p
+        try:
+            nrm = self.norm()
+        finally:
+            self._packed = saved
+        total = 0.0
+        for r in expr.regs:
+            ln = torch.log(nrm)
+            v = {"log_frob": ln, "log_pow_frob": 2 * ln, "log_relu_frob": torch.clamp(ln, min=0.0),
+                 "quad_frob": (ln - 1.0) ** 2}[r.kind]
+            total = total + r.coef * v
+        (g,) = torch.autograd.grad(total, p)
+        return total.detach(), g
+
+    def create_train_step(self, params=None, loss_func=None, *, embedding=None, dtype=None):
+        """model.py:529-618: returns (train_step, opt_state).  ``train_step(params, opt_state, data,
+        grad_clip_threshold)`` -> (params, opt_state, loss) with the fused value-and-grad inside."""
+        supervised = self.train_type == TrainingType.SUPERVISED
+        eng, expr = self._engine(embedding or TrigonometricEmbedding(), self.loss, supervised, dtype)
+        opt_state = self._opt.init(self._packed)
+        grads = torch.zeros_like(self._packed)
+        group = self.process_group
+
+        def train_step(params, opt_state, data=None, grad_clip_threshold=None):
+            if isinstance(data, tuple) and len(data) == 2:
+                x, t = data
+            else:
+                x, t = data, None
+            n_local = x.shape[0]
+            n_global = n_local
+            if group is not None:
+                import torch.distributed as dist
+                n_global = n_local * dist.get_world_size(group)
+            loss_sum, g = eng.value_and_grad(self._packed, x, t, denom=n_global, grads=grads)
+            loss = loss_sum / n_global
+            if group is not None:
+                import torch.distributed as dist
+                dist.all_reduce(g, group=group)  # K6: sum of the per-site gradients over the batch shards
+                dist.all_reduce(loss, group=group)
+            rv, rg = self._reg_value_and_grad(expr)
+            if rv is not None:
+                loss = loss + rv
+                g = g + rg
+            if grad_clip_threshold:  # util.gradient_clip (util.py:131-155): global-norm clipping
+                gn = torch.linalg.norm(g)
+                g = g * torch.clamp(grad_clip_threshold / (gn + 1e-16), max=1.0)
+            updates, opt_state = self._opt.update(g, opt_state, self._packed)
+            optim.apply_updates(self._packed, updates.to(self._packed.dtype))
+            return self.arrays, opt_state, loss
+
+        return train_step, opt_state
+
+    # ---- train (model.py:620-976) ----------------------------------------------------
+    def train(self, inputs=None, val_inputs=None, targets=None, val_targets=None, tn_target=None, batch_size=None,
+              epochs=1, embedding=None, normalize=False, canonize=(False, None), time_limit=None, earlystop=None,
+              gradient_clip_threshold=None, val_batch_size=None, eval_metric=None, display_val_acc=False,
+              accuracy_fn=None, dtype=None, shuffle=False, seed=42, alternate_flip=False):
+        if embedding is None:
+            embedding = TrigonometricEmbedding()
+        if self.strategy != "global":
+            raise ValueError("Only Global Gradient Descent and DMRG Sweeping strategy is supported for now!")
+        if canonize and canonize[0]:
+            raise NotImplementedError("canonize=(True, c) is a model-only QR sweep outside the fused path")
+        if not hasattr(self, "_opt"):
+            raise AttributeError("Provide 'optimizer' or sequence of 'gradient_transforms'! ")
+        inputs = np.asarray(inputs)
+        if batch_size is None:
+            batch_size = len(inputs)
+        num_batches = max(1, len(inputs) // batch_size)
+        if targets is not None:
+            targets = np.asarray(targets)
+            if targets.ndim == 1:
+                targets = np.expand_dims(targets, axis=-1)
+        if val_inputs is not None and eval_metric is None:
+            eval_metric = self.loss
+        self.batch_size = batch_size
+        n_batches = max(1, len(inputs) // self.batch_size)
+        if not hasattr(self, "history"):
+            self.history = {"loss": [], "epoch_time": [], "unfinished": False}
+            if val_inputs is not None:
+                if val_batch_size is None:
+                    raise ValueError("Validation batch size must be provided!")
+                self.history["val_loss"] = []
+                if display_val_acc:
+                    self.history["val_acc"] = []
+        return_value = 0
+        if earlystop:
+            earlystop.on_begin_train(self.history, self)
+        self.step, self.opt_state = self.create_train_step(embedding=embedding, dtype=dtype)
+        start_train = time()
+        for epoch in range(epochs):
+            time_epoch = time()
+            loss_batch = torch.zeros((), dtype=torch.float64, device=self._packed.device)
+            for batch_data in _batch_iterator(inputs, targets, batch_size, dtype=self.dtype, shuffle=shuffle,
+                                              seed=seed, alternate_flip=alternate_flip):
+                dev = self._packed.device
+                if isinstance(batch_data, tuple):
+                    batch_data = tuple(_to_device(b, dev, self.dtype) for b in batch_data)
+                else:
+                    batch_data = _to_device(batch_data, dev, self.dtype)
+                _, self.opt_state, loss_curr = self.step(self.arrays, self.opt_state, batch_data,
+                                                         grad_clip_threshold=gradient_clip_threshold)
+                loss_batch = loss_batch + loss_curr.reshape(())
+                if normalize:
+                    self.normalize()
+            loss_epoch = float((loss_batch / n_batches).item())  # the one D2H sync per epoch (model.py:887)
+            self.history["loss"].append(loss_epoch)
+            self.history["epoch_time"].append(time() - time_epoch)
+            if time_limit is not None and (time() - start_train + np.mean(self.history["epoch_time"]) >= time_limit):
+                self.history["unfinished"] = True
+                return self.history
+            if val_inputs is not None:
+                loss_val = self.evaluate(val_inputs, val_targets, batch_size=val_batch_size, embedding=embedding,
+                                         evaluate_type=self.train_type, metric=eval_metric, dtype=dtype,
+                                         shuffle=shuffle, seed=seed, alternate_flip=alternate_flip)
+                self.history["val_loss"].append(loss_val)
+                if display_val_acc:
+                    self.history["val_acc"].append(self.accuracy(
+                        val_inputs, val_targets, batch_size=val_batch_size, embedding=embedding, shuffle=shuffle,
+                        accuracy_fn=accuracy_fn, dtype=dtype, seed=seed, alternate_flip=alternate_flip))
+                if earlystop and earlystop.monitor == "val_loss":
+                    return_value = earlystop.on_end_epoch(loss_val, epoch, self)
+            elif earlystop:
+                current = loss_epoch if earlystop.monitor == "loss" else \
+                    sum(self.history[earlystop.monitor][-num_batches:]) / num_batches
+                return_value = earlystop.on_end_epoch(current, epoch, self)
+            if earlystop and return_value == 1:
+                return earlystop.memory["best_model"].history
+        return self.history
+
+    # ---- evaluate (model.py:978-1151) --------------------------------------------------
+    def evaluate(self, inputs=None, targets=None, tn_target=None, batch_size=None, embedding=None,
+                 evaluate_type: int = TrainingType.UNSUPERVISED, return_list=False, metric=None, dtype=None,
+                 shuffle=False, seed=42, alternate_flip=False):
+        if embedding is None:
+            embedding = TrigonometricEmbedding()
+        if evaluate_type not in [TrainingType.UNSUPERVISED, TrainingType.SUPERVISED, TrainingType.TARGET_TN]:
+            raise ValueError("Specify type of evaluation: UNSUPERVISED, SUPERVISED, or TARGET_TN!")
+        if evaluate_type == TrainingType.TARGET_TN:
+            raise NotImplementedError("TARGET_TN has no batched contraction; it stays on the reference path")
+        if hasattr(self, "batch_size") and batch_size is None:
+            batch_size = self.batch_size
+        if not hasattr(self, "batch_size"):
+            self.batch_size = batch_size
+        supervised = evaluate_type == TrainingType.SUPERVISED
+        eng, expr = self._engine(embedding, metric or self.loss, supervised, dtype)
+        inputs = np.asarray(inputs)
+        if batch_size is None:
+            batch_size = len(inputs)
+        if targets is not None:
+            targets = np.asarray(targets)
+            if targets.ndim == 1:
+                targets = np.expand_dims(targets, axis=-1)
+        losses, loss_value, nb = [], 0.0, 0
+        for batch_data in _batch_iterator(inputs, targets if supervised else None, batch_size, dtype=self.dtype,
+                                          shuffle=shuffle, seed=seed, alternate_flip=alternate_flip):
+            x, y = batch_data if isinstance(batch_data, tuple) else (batch_data, None)
+            per, _, _ = eng.forward(self._packed, x, y)
+            losses.append(per)
+            nb += 1
+        if nb == 0:
+            raise ValueError("No evaluation batches were produced.")
+        rv, _ = self._reg_value_and_grad(expr)
+        if return_list:
+            out = torch.cat(losses)
+            if rv is not None:
+                out = out + rv.to(out.dtype)
+            return out.cpu().numpy()
+        loss_value = sum(float(l.mean().item()) for l in losses) / nb  # mean of batch means (model.py:1128-1141)
+        if rv is not None:
+            loss_value += float(rv)
+        return float(loss_value)
+
+    # ---- predict / forward / accuracy (model.py:278-465) ------------------------------
+    def forward(self, data, embedding=None, batch_size=64, normalize=False, dtype=None, seed=42,
+                alternate_flip=False):
+        """Raw model outputs for a batch -> CUDA tensor [N, n_out] (or [N])."""
+        if embedding is None:
+            embedding = TrigonometricEmbedding()
+        eng, _ = self._engine(embedding, None, False, dtype)
+        data = np.asarray(data) if not torch.is_tensor(data) else data
+        if data.ndim == 1:
+            data = data.reshape(1, -1)
+        outs = []
+        for x in _batch_iterator(data, None, batch_size, dtype=self.dtype, shuffle=False, seed=seed,
+                                 alternate_flip=alternate_flip):
+            _, out, oexp = eng.forward(self._packed, x, None, want_loss=False)
+            if normalize and out.ndim == 2:
+                out = out / torch.linalg.norm(out, dim=-1, keepdim=True)  # scale-free: exponent cancels
+            elif out.ndim == 2:
+                out = torch.ldexp(out, oexp[:, None])
+            else:
+                out = torch.ldexp(out, oexp)
+            outs.append(out.squeeze(-1) if out.ndim == 2 and out.shape[1] == 1 else out)
+        return torch.cat(outs, dim=0)
+
+    def predict(self, sample, embedding=None, return_tn=False, normalize=False):
+        if return_tn:
+            raise NotImplementedError("return_tn needs a quimb tensor network; not part of the fused path")
+        sample = np.asarray(sample)
+        if len(sample.flatten()) < self.L:
+            raise ValueError(f"Input data must have at least {self.L} elements!")
+        return self.forward(sample.reshape(1, -1), embedding=embedding, batch_size=1, normalize=normalize)[0]
+
+    def accuracy(self, data, y_true=None, embedding=None, batch_size=64, shuffle=False, normalize=False,
+                 accuracy_fn=None, dtype=None, seed=42, alternate_flip=False) -> float:
+        if y_true is None:
+            raise ValueError("For unsupervised learning you must provide target data!")
+        y_pred = self.forward(data, embedding=embedding, batch_size=batch_size, normalize=normalize, dtype=dtype,
+                              seed=seed, alternate_flip=alternate_flip)
+        if accuracy_fn is not None:
+            y_pred = accuracy_fn(y_pred)
+        y = torch.as_tensor(np.asarray(y_true)).to(y_pred.device)
+        return float((_as_class_labels(y_pred) == _as_class_labels(y)).sum().item()) / len(y)
+
+
+def _as_class_labels(a: torch.Tensor) -> torch.Tensor:
+    if a.ndim >= 2 and a.shape[-1] > 1:
+        return a.argmax(dim=-1)
+    return a.reshape(-1).round().long() if a.is_floating_point() else a.reshape(-1)
+
+
+def _to_device(a, dev, dtype):
+    t = torch.as_tensor(a)
+    if t.device.type == "cpu":
+        t = t.to(dtype).pin_memory()
+    return t.to(dev, dtype, non_blocking=True)
+
+
+def load_model(model_name, dir_name=None):
+    """model.py:1167-1183."""
+    import os
+    path = f"{model_name}.pkl" if dir_name is None else os.path.join(os.path.expanduser(dir_name), f"{model_name}.pkl")
+    with open(path, "rb") as f:
+        cls, state = pickle.load(f)
+    obj = cls.__new__(cls)
+    obj.__dict__.update(state)
+    obj._engine_cache = {}
+    obj.process_group = None
+    dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+    obj._packed = obj._packed.to(dev)
+    obj._arrays = obj._views(obj._packed)
+    return obj
+
+
+def _batch_iterator(x, y=None, batch_size=2, dtype=torch.float64, shuffle=True, seed=0, alternate_flip=False):
+    """model.py:1201-1277: optional shuffle, fixed-size chunks (last one may be smaller),
+    optional flip of every odd batch along the feature axis."""
+    xt = torch.as_tensor(x)
+    yt = None if y is None else torch.as_tensor(y)
+    n = len(xt)
+    if shuffle:
+        g = torch.Generator().manual_seed(int(seed))
+        perm = torch.randperm(n, generator=g)
+        xt = xt[perm.to(xt.device)]
+        if yt is not None:
+            yt = yt[perm.to(yt.device)]
+    for bi, s in enumerate(range(0, n, batch_size)):
+        xc = xt[s: s + batch_size]
+        if alternate_flip and bi % 2 == 1:
+            xc = torch.flip(xc, dims=[1])
+        if yt is not None:
+            yield xc, yt[s: s + batch_size]
+        else:
+            yield xc
