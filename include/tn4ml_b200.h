@@ -126,6 +126,13 @@ int tnb_backward(const tnb_problem *prob, int64_t batch, const void *x, const vo
 int tnb_embed(const tnb_embedding *emb, int32_t dtype, int64_t n, const void *x, void *phi,
               void *stream);
 
+/* Measurement aid (bench.py's roofline leg).  tnb_profile(1) starts bracketing every kernel
+ * launch with CUDA events on its stream; tnb_profile(0) stops and drops the records.
+ * tnb_profile_read synchronises on the recorded events and returns up to max_records
+ * (name[48], milliseconds) pairs in launch order.  Not for use on the hot path. */
+int tnb_profile(int32_t enable);
+int32_t tnb_profile_read(char *names, float *ms, int32_t max_records);
+
 /* Number of kernel launches issued by this library since load (all threads). */
 int64_t tnb_launch_count(void);
 

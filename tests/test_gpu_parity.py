@@ -40,20 +40,25 @@ def _emb(spec):
 
 def _check(model, prob, loss_fn, x, arrays, t, dtype, scale_tol=1.0):
     tol = TOL[dtype] * scale_tol
-    arr64 = [a.double() for a in arrays]
-    loss_ref, grads_ref = O.value_and_grad(prob, x.double(), arr64, None if t is None else t.double())
-    per_ref = O.per_sample_loss(prob, x.double(), arr64, None if t is None else t.double())
+    # identical inputs on both sides: round to the kernel dtype first, then run the oracle in float64
+    arr64 = [a.to(dtype).double() for a in arrays]
+    x = x.to(dtype).double()
+    loss_ref, grads_ref = O.value_and_grad(prob, x, arr64, None if t is None else t.double())
+    per_ref = O.per_sample_loss(prob, x, arr64, None if t is None else t.double())
     eng, _ = model._engine(_emb(prob.emb), loss_fn, t is not None, dtype)
     B = x.shape[0]
     loss_sum, g = eng.value_and_grad(model._packed, x.to(dtype), None if t is None else t.to(dtype))
     loss = float(loss_sum.item()) / B
     assert abs(loss - float(loss_ref)) <= tol * max(1.0, abs(float(loss_ref))), (loss, float(loss_ref))
+    gmax = max(float(q.abs().max()) for q in grads_ref)
+    gfro = max(float(q.norm()) for q in grads_ref)
     for i, (a, b) in enumerate(zip(model._views(g), grads_ref)):
         assert a.shape == b.shape
-        err = float((a.double().cpu() - b).abs().max())
-        ref = float(b.abs().max())
-        gmax = max(float(q.abs().max()) for q in grads_ref)
-        assert err <= tol * max(ref, 1e-3 * gmax), f"site {i}: err {err:.3e} ref {ref:.3e}"
+        diff = a.double().cpu() - b
+        # ||g - g_ref|| / ||g_ref|| per site, and max-elementwise scaled by ||g_ref||_inf
+        # (sites whose gradient is < 1e-3 of the largest are measured against that floor)
+        assert float(diff.norm()) <= tol * max(float(b.norm()), 1e-3 * gfro), f"site {i} (fro)"
+        assert float(diff.abs().max()) <= tol * max(float(b.abs().max()), 1e-3 * gmax), f"site {i} (max)"
     per, out, oexp = eng.forward(model._packed, x.to(dtype), None if t is None else t.to(dtype))
     assert torch.allclose(per.double().cpu(), per_ref, rtol=tol * 10, atol=tol * 10)
     return loss

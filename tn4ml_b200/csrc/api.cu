@@ -4,6 +4,7 @@
 #include <cstring>
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 #include "mps_simt.cuh"
@@ -28,8 +29,29 @@ static int fail(const char *fmt, ...) {
     if (_e != cudaSuccess) return fail("%s failed: %s", #expr, cudaGetErrorString(_e));  \
   } while (0)
 
+// Optional per-launch timing (bench.py's roofline leg): when enabled, every kernel launch
+// is bracketed by CUDA events on the launching stream.  Off by default; not thread-safe
+// by design (a measurement aid, enabled by one thread around one timed region).
+struct ProfRec { const char *name; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static inline void prof_begin(cudaStream_t st) {
+  if (!g_prof_on) return;
+  ProfRec r{"?", nullptr, nullptr};
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, st);
+  g_prof.push_back(r);
+}
+static inline void prof_end(const char *name, cudaStream_t st) {
+  if (!g_prof_on || g_prof.empty()) return;
+  g_prof.back().name = name;
+  cudaEventRecord(g_prof.back().b, st);
+}
+
 #define TNB_LAUNCH_CHECK(name)                                                           \
   do {                                                                                   \
+    prof_end(name, st);                                                                  \
     g_launches.fetch_add(1, std::memory_order_relaxed);                                  \
     cudaError_t _e = cudaGetLastError();                                                 \
     if (_e != cudaSuccess) return fail("launch %s failed: %s", name, cudaGetErrorString(_e)); \
@@ -173,12 +195,15 @@ static int mps_forward_t(const tnb_problem *p, const MpsPlan &P, long long B, co
   size_t welems = (size_t)P.chip * p->d * P.chip * P.nslab;
   int pblocks = (int)((welems + 255) / 256);
   if (pblocks > 148 * 16) pblocks = 148 * 16;
+  prof_begin(st);
   mps_prep_kernel<T><<<pblocks, 256, 0, st>>>((const T *)params, (T *)A.Wn, (T *)A.Wt, p->L, p->chi, P.chip, p->d,
                                               p->n_out, p->out_site);
   TNB_LAUNCH_CHECK("mps_prep_kernel");
   int tiles = (int)((B + P.BT - 1) / P.BT);
+  prof_begin(st);
   mps_sweep_kernel<T, NG><<<dim3(tiles, 2), P.NT, P.smem_sweep, st>>>(A, 0);
   TNB_LAUNCH_CHECK("mps_sweep_kernel(fwd)");
+  prof_begin(st);
   mps_class_kernel<T, NG><<<tiles, P.NT, P.smem_class, st>>>(A);
   TNB_LAUNCH_CHECK("mps_class_kernel");
   return 0;
@@ -194,6 +219,7 @@ static int mps_backward_t(const tnb_problem *p, const MpsPlan &P, long long B, c
   A.loss_scale = (T)loss_scale;
   if (!accumulate) TNB_CUDA(cudaMemsetAsync(grads, 0, (size_t)tnb_param_count(p) * sizeof(T), st));
   int tiles = (int)((B + P.BT - 1) / P.BT);
+  prof_begin(st);
   mps_sweep_kernel<T, NG><<<dim3(tiles, 2), P.NT, P.smem_sweep, st>>>(A, 1);
   TNB_LAUNCH_CHECK("mps_sweep_kernel(adj)");
   DaArgs<T> Dg;
@@ -211,6 +237,7 @@ static int mps_backward_t(const tnb_problem *p, const MpsPlan &P, long long B, c
   Dg.bchunk = (Dg.bchunk + 15) / 16 * 16;
   Dg.only_site = -1;
   dim3 grid(Dg.tiles_a * Dg.tiles_r * Dg.nsplit, p->L, p->d);
+  prof_begin(st);
   mps_da_kernel<T><<<grid, 256, 0, st>>>(Dg);
   TNB_LAUNCH_CHECK("mps_da_kernel");
   // class site: one GEMM per (s, class)
@@ -222,6 +249,7 @@ static int mps_backward_t(const tnb_problem *p, const MpsPlan &P, long long B, c
   Dg.nsplit = (int)ns;
   Dg.bchunk = ((B + ns - 1) / ns + 15) / 16 * 16;
   dim3 gridc(Dg.tiles_a * Dg.tiles_r * Dg.nsplit, 1, p->d * p->n_out);
+  prof_begin(st);
   mps_da_kernel<T><<<gridc, 256, 0, st>>>(Dg);
   TNB_LAUNCH_CHECK("mps_da_kernel(class)");
   return 0;
@@ -294,10 +322,12 @@ int tnb_forward(const tnb_problem *p, int64_t batch, const void *x, const void *
     return fail("workspace too small: need %zu bytes, got %lld", P.total, (long long)workspace_bytes);
   int rc;
   const char *what = "";
+  prof_begin(st);
   if (p->dtype == TNB_F64)
     rc = smpo_forward_t<double>(p, P, batch, x, params, loss, loss_sum, out, out_exp, keep_stash, workspace, st, &what);
   else
     rc = smpo_forward_t<float>(p, P, batch, x, params, loss, loss_sum, out, out_exp, keep_stash, workspace, st, &what);
+  prof_end("smpo_fwd_kernel", st);
   g_launches.fetch_add(P.launches_fwd, std::memory_order_relaxed);
   if (rc) return fail("%s", what);
   return 0;
@@ -321,13 +351,36 @@ int tnb_backward(const tnb_problem *p, int64_t batch, const void *x, const void 
     return fail("workspace too small: need %zu bytes, got %lld", P.total, (long long)workspace_bytes);
   int rc;
   const char *what = "";
+  prof_begin(st);
   if (p->dtype == TNB_F64)
     rc = smpo_backward_t<double>(p, P, batch, x, params, loss_scale, grads, accumulate, workspace, st, &what);
   else
     rc = smpo_backward_t<float>(p, P, batch, x, params, loss_scale, grads, accumulate, workspace, st, &what);
+  prof_end("smpo_bwd_kernel", st);
   g_launches.fetch_add(P.launches_bwd, std::memory_order_relaxed);
   if (rc) return fail("%s", what);
   return 0;
+}
+
+int tnb_profile(int32_t enable) {
+  for (auto &r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.clear();
+  g_prof_on = enable != 0;
+  return 0;
+}
+
+int32_t tnb_profile_read(char *names, float *ms, int32_t max_records) {
+  int32_t n = 0;
+  for (auto &r : g_prof) {
+    if (n >= max_records) break;
+    if (cudaEventSynchronize(r.b) != cudaSuccess) break;
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    ms[n] = t;
+    snprintf(names + (size_t)n * 48, 48, "%s", r.name);
+    ++n;
+  }
+  return n;
 }
 
 int tnb_embed(const tnb_embedding *emb, int32_t dtype, int64_t n, const void *x, void *phi, void *stream) {
@@ -340,10 +393,12 @@ int tnb_embed(const tnb_embedding *emb, int32_t dtype, int64_t n, const void *x,
   if (dtype == TNB_F64) {
     EmbParams<double> e;
     fill_emb<double>(*emb, e, d);
+    prof_begin(st);
     embed_kernel<double><<<blocks, 256, 0, st>>>(e, n, (const double *)x, (double *)phi);
   } else if (dtype == TNB_F32) {
     EmbParams<float> e;
     fill_emb<float>(*emb, e, d);
+    prof_begin(st);
     embed_kernel<float><<<blocks, 256, 0, st>>>(e, n, (const float *)x, (float *)phi);
   } else {
     return fail("bad dtype");

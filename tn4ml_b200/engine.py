@@ -56,6 +56,7 @@ class Engine:
             raise ValueError("tn4ml_b200: " + msg)
         self.max_microbatch = max_microbatch
         self._ws = {}
+        self._mb = {}
         self._loss_sum = torch.zeros(1, dtype=torch.float64, device=device)
 
     # -- workspace ----------------------------------------------------------------
@@ -75,6 +76,10 @@ class Engine:
         """Largest micro-batch whose workspace stays under ~60% of free HBM."""
         if self.max_microbatch:
             return min(batch, self.max_microbatch)
+        key = (batch, need_grad)
+        if key in self._mb:
+            return self._mb[key]
+        self._ws.clear()
         free, _ = torch.cuda.mem_get_info(self.device)
         mb = batch
         while mb > 1024:
@@ -82,6 +87,7 @@ class Engine:
             if nbytes <= 0.6 * free:
                 break
             mb = (mb + 1) // 2
+        self._mb[key] = mb
         return mb
 
     def _stream(self):
