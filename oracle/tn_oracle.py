@@ -204,6 +204,23 @@ def mps_outputs(phi: torch.Tensor, arrays: Sequence[torch.Tensor], order: str = 
     return torch.einsum("bl,blrk,br->bk", lv, Mc, rv)
 
 
+def mps_nll_logspace(phi: torch.Tensor, arrays: Sequence[torch.Tensor]) -> torch.Tensor:
+    """-log(<A|phi>^2) with the chain renormalised at every site (plain MPS only).  Same
+    quantity as head_loss(mps_outputs(...), "nll") wherever that does not under/overflow."""
+    sites, cls = canon_mps_sites(arrays)
+    assert cls < 0
+    B = phi.shape[0]
+    v = torch.ones(B, 1, dtype=phi.dtype)
+    logs = torch.zeros(B, dtype=phi.dtype)
+    for i, A in enumerate(sites):
+        M = torch.einsum("lrs,bs->blr", A[..., 0], phi[:, i])
+        v = torch.bmm(v.unsqueeze(1), M).squeeze(1)
+        n = v.abs().amax(dim=1)
+        v = v / n[:, None]
+        logs = logs + torch.log(n)
+    return -2.0 * (torch.log(v[:, 0].abs()) + logs)
+
+
 # ----------------------------------------------------------------------------
 # SMPO / MPO contraction  (smpo.py:269-404 ; metrics.py:56-81)
 # ----------------------------------------------------------------------------
@@ -455,7 +472,7 @@ def smpo_dense_sqnorm(phi: torch.Tensor, arrays: Sequence[torch.Tensor], spacing
 
 
 def make_mps_arrays(L, chi, d, class_site=None, C=None, std=1e-2, seed=42, dtype=torch.float64,
-                    squeeze_ends=False, shape_method="even"):
+                    squeeze_ends=False, shape_method="even", identity_all=False):
     """A_i = I delta_{s,0} + std N(0,1) (mps.py:348-355 add_identity), then a global
     division by norm^(1/L) as Model.normalize does (tn.py:103-107)."""
     g = torch.Generator().manual_seed(seed)
@@ -476,7 +493,10 @@ def make_mps_arrays(L, chi, d, class_site=None, C=None, std=1e-2, seed=42, dtype
         a = std * torch.randn(shape, generator=g, dtype=torch.float64)
         eye = torch.eye(cl, cr, dtype=torch.float64)
         if a.ndim == 3:
-            a[:, :, 0] += eye
+            if identity_all:
+                a += eye.unsqueeze(-1)
+            else:
+                a[:, :, 0] += eye
         else:
             a[:, :, 0, :] += eye.unsqueeze(-1)
         arrays.append(a)

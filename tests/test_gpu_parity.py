@@ -58,7 +58,7 @@ def _check(model, prob, loss_fn, x, arrays, t, dtype, scale_tol=1.0):
         # ||g - g_ref|| / ||g_ref|| per site, and max-elementwise scaled by ||g_ref||_inf
         # (sites whose gradient is < 1e-3 of the largest are measured against that floor)
         assert float(diff.norm()) <= tol * max(float(b.norm()), 1e-3 * gfro), f"site {i} (fro)"
-        assert float(diff.abs().max()) <= tol * max(float(b.abs().max()), 1e-3 * gmax), f"site {i} (max)"
+        assert float(diff.abs().max()) <= tol * gmax, f"site {i} (max)"
     per, out, oexp = eng.forward(model._packed, x.to(dtype), None if t is None else t.to(dtype))
     assert torch.allclose(per.double().cpu(), per_ref, rtol=tol * 10, atol=tol * 10)
     return loss
@@ -109,8 +109,10 @@ def test_cfg1_mnist_shaped_classifier(dtype):
 ], ids=["fourier16", "cfg4", "noteven"])
 def test_mps_nll_parity(case, dtype):
     import tn4ml_b200 as T
+    # identity on every physical component keeps <A|phi> away from 0 (where -log s^2 is singular
+    # and its gradient arbitrarily ill-conditioned)
     arrays = O.make_mps_arrays(case["L"], case["chi"], case["d"], std=0.05, seed=4, squeeze_ends=True,
-                               shape_method=case.get("shape_method", "even"))
+                               shape_method=case.get("shape_method", "even"), identity_all=True)
     x = O.make_inputs(case["B"], case["L"], seed=6)
     prob = O.Problem("mps", case["emb"], "nll")
     model = T.MatrixProductState(arrays, dtype=dtype, device="cuda:0")
@@ -138,18 +140,21 @@ def test_smpo_parity(case, dtype):
 
 
 def test_long_chain_does_not_leave_fp32_range():
-    """H2: a 784-site chain whose raw product underflows float32 is carried by the exponent."""
+    """H2: a 784-site chain whose raw product (~0.05^784) underflows float32 AND float64 is
+    carried by the per-sample exponent; checked against the oracle evaluated in log space."""
     import tn4ml_b200 as T
     L = 784
-    arrays = [0.05 * a for a in O.make_mps_arrays(L, 8, 2, std=0.05, seed=2, squeeze_ends=True)]
-    x = O.make_inputs(16, L, seed=3)
-    prob = O.Problem("mps", O.EmbSpec("trig"), "nll")
-    per_ref = O.per_sample_loss(prob, x, arrays)
+    base = O.make_mps_arrays(L, 8, 2, std=0.05, seed=2, squeeze_ends=True, identity_all=True)
+    arrays = [(0.05 * a).float() for a in base]
+    x = O.make_inputs(16, L, seed=3).float()
+    per_ref = O.mps_nll_logspace(O.embed_batch(x.double(), O.EmbSpec("trig")), [a.double() for a in arrays])
+    assert not torch.isfinite(O.per_sample_loss(O.Problem("mps", O.EmbSpec("trig"), "nll"), x.double(),
+                                                [a.double() for a in arrays])).any()
     model = T.MatrixProductState(arrays, dtype=torch.float32, device="cuda:0")
     eng, _ = model._engine(T.TrigonometricEmbedding(), _heads()["nll"], False, torch.float32)
-    per, out, oexp = eng.forward(model._packed, x.float())
+    per, out, oexp = eng.forward(model._packed, x)
     assert torch.isfinite(per).all()
-    assert torch.allclose(per.double().cpu(), per_ref, rtol=1e-4)
+    assert torch.allclose(per.double().cpu(), per_ref, rtol=1e-5)
 
 
 def test_embedding_call_matches_oracle():
