@@ -1,0 +1,59 @@
+"""Parity of the tcgen05 (fp16x3) sweep against the CPU oracle: float32 tolerance 1e-4."""
+import pytest
+import torch
+
+from oracle import tn_oracle as O
+from tests.test_gpu_parity import _check, _heads
+
+pytestmark = pytest.mark.gpu
+
+
+def _tensor_model(cls, arrays):
+    import tn4ml_b200 as T
+    from tn4ml_b200 import _lib
+    model = cls(arrays, dtype=torch.float32, device="cuda:0")
+    model.precision = _lib.PREC_TENSOR
+    return model
+
+
+@pytest.mark.parametrize("case", [
+    dict(L=6, chi=64, d=2, cls=3, C=3, B=128),
+    dict(L=12, chi=64, d=2, cls=5, C=4, B=200),       # ragged last tile
+    dict(L=9, chi=128, d=2, cls=0, C=3, B=130),       # class site on the left boundary
+    dict(L=9, chi=32, d=4, cls=8, C=2, B=64),         # class site on the right boundary, d=4
+    dict(L=8, chi=256, d=2, cls=4, C=10, B=256),      # cfg 5 bond dimension
+    dict(L=10, chi=128, d=3, cls=4, C=2, B=90),       # N = 384 -> two MMA halves of 192
+], ids=["chi64", "chi64_ragged", "chi128_cls0", "chi32_d4_clsL", "chi256", "chi128_d3"])
+def test_tensor_path_classifier(case):
+    import tn4ml_b200 as T
+    from tn4ml_b200 import _lib
+    arrays = O.make_mps_arrays(case["L"], case["chi"], case["d"], class_site=case["cls"], C=case["C"], std=0.05, seed=3)
+    x = O.make_inputs(case["B"], case["L"], seed=5)
+    t = O.make_labels(case["B"], case["C"])
+    emb = {2: O.EmbSpec("trig"), 3: O.EmbSpec("poly", degree=2, include_bias=True), 4: O.EmbSpec("trig", k=2)}[case["d"]]
+    prob = O.Problem("mps", emb, "softmax_xent")
+    model = _tensor_model(T.TensorNetwork, arrays)
+    l0 = _lib.lib().tnb_launch_count()
+    _check(model, prob, _heads()["softmax_xent"], x, arrays, t, torch.float32)
+    assert _lib.lib().tnb_launch_count() > l0
+
+
+def test_tensor_path_cfg4_nll():
+    """BASELINE config 4 shape: L=16, Fourier d=8, chi=64, NLL."""
+    import tn4ml_b200 as T
+    arrays = O.make_mps_arrays(16, 64, 8, std=0.05, seed=4, squeeze_ends=True, identity_all=True)
+    x = O.make_inputs(300, 16, seed=6)
+    prob = O.Problem("mps", O.EmbSpec("fourier", p=8), "nll")
+    model = _tensor_model(T.MatrixProductState, arrays)
+    _check(model, prob, _heads()["nll"], x, arrays, None, torch.float32)
+
+
+def test_tensor_path_long_chain():
+    """L=196 at chi=64: the accuracy budget of the fp16x3 split over the full cfg-5 chain length."""
+    import tn4ml_b200 as T
+    arrays = O.make_mps_arrays(196, 64, 2, class_site=97, C=10, std=1e-2, seed=42)
+    x = O.make_inputs(256, 196, seed=1)
+    t = O.make_labels(256, 10)
+    prob = O.Problem("mps", O.EmbSpec("trig"), "softmax_xent")
+    model = _tensor_model(T.TensorNetwork, arrays)
+    _check(model, prob, _heads()["softmax_xent"], x, arrays, t, torch.float32)

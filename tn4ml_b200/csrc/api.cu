@@ -5,9 +5,11 @@
 #include <atomic>
 #include <mutex>
 #include <vector>
+#include <type_traits>
 
 #include "common.cuh"
 #include "mps_simt.cuh"
+#include "mps_tc.cuh"
 #include "smpo_simt.cuh"
 
 namespace tnb {
@@ -107,7 +109,23 @@ struct MpsPlan {
   int chip, nslab, TN, NG, NT, BT, KT;
   size_t off_Wn, off_Wt, off_F, off_G, off_exps, off_esum, off_y, off_dy, total;
   size_t smem_sweep, smem_class;
+  // tensor-core sweep (f32, TNB_PREC_TENSOR)
+  int tc, tc_N, tc_NH, tc_NMMA, tc_nstage, tc_cols;
+  uint32_t tc_stage_bytes;
+  size_t tc_site_img, off_img_n, off_img_t, off_kW, tc_smem;
 };
+
+// The tcgen05 sweep covers: float32, chi a multiple of 16 in [32, 256], D*chi <= 512 TMEM columns.
+static bool tc_supported(const tnb_problem *p) {
+  if (p->kind != TNB_KIND_MPS || p->dtype != TNB_F32 || p->precision != TNB_PREC_TENSOR) return false;
+  if (p->chi % 16 != 0 || p->chi < 32 || p->chi > 256) return false;
+  const int N = p->d * p->chi;
+  if (N > 512) return false;
+  if (!(p->d == 2 || p->d == 3 || p->d == 4 || p->d == 6 || p->d == 8)) return false;
+  const int NH = (N + 255) / 256;
+  if (N % NH != 0 || (N / NH) % 16 != 0) return false;
+  return true;
+}
 
 static MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
   MpsPlan P{};
@@ -143,6 +161,26 @@ static MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
   P.off_esum = take((size_t)2 * B * sizeof(int));
   P.off_y = take((size_t)B * p->n_out * w);
   P.off_dy = need_grad ? take((size_t)B * p->n_out * w) : 0;
+  P.tc = tc_supported(p) ? 1 : 0;
+  if (P.tc) {
+    P.tc_N = p->d * p->chi;
+    P.tc_NH = (P.tc_N + 255) / 256;
+    P.tc_NMMA = P.tc_N / P.tc_NH;
+    P.tc_stage_bytes = 64u * P.tc_N;
+    P.tc_site_img = (size_t)(p->chi / 16) * P.tc_stage_bytes;
+    P.tc_cols = 32;
+    while (P.tc_cols < P.tc_N) P.tc_cols <<= 1;
+    const size_t a_bytes = (size_t)2 * kTcRows * p->chi * 2;
+    long ns = (long)((232448 - 1024 - (long)a_bytes) / (long)P.tc_stage_bytes);
+    P.tc_nstage = ns > 8 ? 8 : (int)ns;
+    P.tc_smem = a_bytes + (size_t)P.tc_nstage * P.tc_stage_bytes + 1024;
+    if (P.tc_nstage < 2) P.tc = 0;
+  }
+  if (P.tc) {
+    P.off_img_n = take(P.tc_site_img * P.nslab);
+    P.off_img_t = take(P.tc_site_img * P.nslab);
+    P.off_kW = take((size_t)P.nslab * sizeof(int));
+  }
   P.total = o;
   size_t base = ((size_t)P.BT * P.chip + (size_t)2 * P.KT * p->d * P.chip + (size_t)P.BT * p->d +
                  (size_t)P.BT * p->n_out) * w;
@@ -165,7 +203,47 @@ static void fill_mps_args(const tnb_problem *p, const MpsPlan &P, long long B, c
   A.exps = (int *)(w + P.off_exps); A.esum = (int *)(w + P.off_esum);
   A.y = (T *)(w + P.off_y); A.dy = (T *)(w + P.off_dy);
   A.loss = nullptr; A.loss_sum = nullptr; A.out = nullptr; A.out_exp = nullptr;
-  A.stash = 0; A.KT = P.KT; A.TN = P.TN; A.loss_scale = T(1);
+  A.stash = 0; A.KT = P.KT; A.TN = P.TN; A.loss_scale = T(1); A.seed_only = 0;
+}
+
+static void fill_tc_args(const MpsPlan &P, void *ws, const MpsArgs<float> &M, TcArgs &T) {
+  char *w = (char *)ws;
+  T.M = M;
+  T.img_n = (const uint8_t *)(w + P.off_img_n);
+  T.img_t = (const uint8_t *)(w + P.off_img_t);
+  T.kW = (const int *)(w + P.off_kW);
+  T.N = P.tc_N; T.NH = P.tc_NH; T.NMMA = P.tc_NMMA; T.nstage = P.tc_nstage; T.tmem_cols = P.tc_cols;
+  T.stage_bytes = P.tc_stage_bytes; T.site_img_bytes = P.tc_site_img;
+}
+
+template <int D> static cudaError_t tc_set_attr() {
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [] {
+    err = cudaFuncSetAttribute(tc_sweep_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  });
+  return err;
+}
+
+// launch the tcgen05 sweep (forward environments or adjoint chains)
+static int tc_launch_sweep(const tnb_problem *p, const MpsPlan &P, const TcArgs &T, long long B, int adjoint,
+                           cudaStream_t st) {
+  dim3 grid((unsigned)((B + kTcRows - 1) / kTcRows), 2);
+  cudaError_t e = cudaSuccess;
+#define TNB_TC_CASE(DD)                                                                     \
+  case DD:                                                                                   \
+    e = tc_set_attr<DD>();                                                                   \
+    if (e == cudaSuccess) tc_sweep_kernel<DD><<<grid, kTcThreads, P.tc_smem, st>>>(T, adjoint); \
+    break;
+  prof_begin(st);
+  switch (p->d) {
+    TNB_TC_CASE(2) TNB_TC_CASE(3) TNB_TC_CASE(4) TNB_TC_CASE(6) TNB_TC_CASE(8)
+    default: return fail("tensor path: unsupported physical dimension %d", p->d);
+  }
+#undef TNB_TC_CASE
+  if (e != cudaSuccess) return fail("cudaFuncSetAttribute(tc_sweep): %s", cudaGetErrorString(e));
+  TNB_LAUNCH_CHECK(adjoint ? "tc_sweep_kernel(adj)" : "tc_sweep_kernel(fwd)");
+  return 0;
 }
 
 template <typename T, int NG> static int set_smem_attrs() {
@@ -200,9 +278,29 @@ static int mps_forward_t(const tnb_problem *p, const MpsPlan &P, long long B, co
                                               p->n_out, p->out_site);
   TNB_LAUNCH_CHECK("mps_prep_kernel");
   int tiles = (int)((B + P.BT - 1) / P.BT);
-  prof_begin(st);
-  mps_sweep_kernel<T, NG><<<dim3(tiles, 2), P.NT, P.smem_sweep, st>>>(A, 0);
-  TNB_LAUNCH_CHECK("mps_sweep_kernel(fwd)");
+  if constexpr (std::is_same<T, float>::value) {
+    if (P.tc) {
+      TcArgs Tc;
+      fill_tc_args(P, ws, A, Tc);
+      prof_begin(st);
+      tc_sitemax_kernel<<<P.nslab, 256, 0, st>>>((const float *)params, (int *)Tc.kW, p->L, p->chi, p->d, p->n_out,
+                                                 p->out_site);
+      TNB_LAUNCH_CHECK("tc_sitemax_kernel");
+      size_t items = (size_t)P.tc_N * (p->chi / 8) * P.nslab;
+      int ib = (int)((items + 255) / 256);
+      if (ib > 148 * 32) ib = 148 * 32;
+      prof_begin(st);
+      tc_image_kernel<<<ib, 256, 0, st>>>((const float *)params, Tc.kW, (uint8_t *)Tc.img_n, (uint8_t *)Tc.img_t, p->L,
+                                          p->chi, p->d, p->n_out, p->out_site);
+      TNB_LAUNCH_CHECK("tc_image_kernel");
+      if (tc_launch_sweep(p, P, Tc, B, 0, st)) return 1;
+    }
+  }
+  if (!P.tc) {
+    prof_begin(st);
+    mps_sweep_kernel<T, NG><<<dim3(tiles, 2), P.NT, P.smem_sweep, st>>>(A, 0);
+    TNB_LAUNCH_CHECK("mps_sweep_kernel(fwd)");
+  }
   prof_begin(st);
   mps_class_kernel<T, NG><<<tiles, P.NT, P.smem_class, st>>>(A);
   TNB_LAUNCH_CHECK("mps_class_kernel");
@@ -219,9 +317,17 @@ static int mps_backward_t(const tnb_problem *p, const MpsPlan &P, long long B, c
   A.loss_scale = (T)loss_scale;
   if (!accumulate) TNB_CUDA(cudaMemsetAsync(grads, 0, (size_t)tnb_param_count(p) * sizeof(T), st));
   int tiles = (int)((B + P.BT - 1) / P.BT);
+  A.seed_only = P.tc ? 1 : 0;
   prof_begin(st);
   mps_sweep_kernel<T, NG><<<dim3(tiles, 2), P.NT, P.smem_sweep, st>>>(A, 1);
-  TNB_LAUNCH_CHECK("mps_sweep_kernel(adj)");
+  TNB_LAUNCH_CHECK(P.tc ? "mps_sweep_kernel(seed)" : "mps_sweep_kernel(adj)");
+  if constexpr (std::is_same<T, float>::value) {
+    if (P.tc) {
+      TcArgs Tc;
+      fill_tc_args(P, ws, A, Tc);
+      if (tc_launch_sweep(p, P, Tc, B, 1, st)) return 1;
+    }
+  }
   DaArgs<T> Dg;
   Dg.M = A;
   Dg.grads = (T *)grads;

@@ -37,6 +37,7 @@ template <typename T> struct MpsArgs {
   int stash;    // 1: every bond of F is stored (needed by backward)
   int KT, TN;
   T loss_scale;
+  int seed_only;  // adjoint launch: write the seeds G[c], G[c+1] (and dy) only; the chains run elsewhere
 };
 
 template <typename T> __device__ __forceinline__ int mps_slab(const MpsArgs<T> &A, int site) {
@@ -179,6 +180,7 @@ __global__ void __launch_bounds__(256) mps_sweep_kernel(MpsArgs<T> A, int adjoin
   } else {
     if (half == 0) { if (c == 0) return; site0 = c - 1; nsites = c - 1; dir = -1; transposed = true; }
     else { if (c == L - 1) return; site0 = c + 1; nsites = L - 2 - c; dir = 1; transposed = false; }
+    if (A.seed_only) nsites = 0;
   }
 
   T acc[NG][kRB][kRN];
