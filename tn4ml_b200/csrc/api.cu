@@ -112,7 +112,7 @@ struct MpsPlan {
   // tensor-core sweep (f32, TNB_PREC_TENSOR)
   int tc, tc_N, tc_NH, tc_NMMA, tc_nstage, tc_cols;
   uint32_t tc_stage_bytes;
-  size_t tc_site_img, off_img_n, off_img_t, off_kW, tc_smem;
+  size_t tc_site_img, off_img_n, off_img_t, off_kW, off_wq, off_qmax, tc_smem;
 };
 
 // The tcgen05 sweep covers: float32, chi a multiple of 16 in [32, 256], D*chi <= 512 TMEM columns.
@@ -124,6 +124,7 @@ static bool tc_supported(const tnb_problem *p) {
   if (!(p->d == 2 || p->d == 3 || p->d == 4 || p->d == 6 || p->d == 8)) return false;
   const int NH = (N + 255) / 256;
   if (N % NH != 0 || (N / NH) % 16 != 0) return false;
+  if (N % 128 != 0) return false;  // dA GEMM: M tiles of 128 rows over (s, a)
   return true;
 }
 
@@ -180,6 +181,10 @@ static MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
     P.off_img_n = take(P.tc_site_img * P.nslab);
     P.off_img_t = take(P.tc_site_img * P.nslab);
     P.off_kW = take((size_t)P.nslab * sizeof(int));
+    if (need_grad) {
+      P.off_wq = take((size_t)p->L * p->d * B * sizeof(float));
+      P.off_qmax = take((size_t)p->L * sizeof(int));
+    }
   }
   P.total = o;
   size_t base = ((size_t)P.BT * P.chip + (size_t)2 * P.KT * p->d * P.chip + (size_t)P.BT * p->d +
@@ -212,6 +217,8 @@ static void fill_tc_args(const MpsPlan &P, void *ws, const MpsArgs<float> &M, Tc
   T.img_n = (const uint8_t *)(w + P.off_img_n);
   T.img_t = (const uint8_t *)(w + P.off_img_t);
   T.kW = (const int *)(w + P.off_kW);
+  T.wq = (float *)(w + P.off_wq);
+  T.qmax = (int *)(w + P.off_qmax);
   T.N = P.tc_N; T.NH = P.tc_NH; T.NMMA = P.tc_NMMA; T.nstage = P.tc_nstage; T.tmem_cols = P.tc_cols;
   T.stage_bytes = P.tc_stage_bytes; T.site_img_bytes = P.tc_site_img;
 }
@@ -325,7 +332,34 @@ static int mps_backward_t(const tnb_problem *p, const MpsPlan &P, long long B, c
     if (P.tc) {
       TcArgs Tc;
       fill_tc_args(P, ws, A, Tc);
+      TNB_CUDA(cudaMemsetAsync(Tc.qmax, 0x80, (size_t)p->L * sizeof(int), st));
       if (tc_launch_sweep(p, P, Tc, B, 1, st)) return 1;
+      static std::once_flag once;
+      static cudaError_t aerr = cudaSuccess;
+      std::call_once(once, [] {
+        aerr = cudaFuncSetAttribute(tc_da_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 2048);
+      });
+      if (aerr != cudaSuccess) return fail("cudaFuncSetAttribute(tc_da): %s", cudaGetErrorString(aerr));
+      TcDaArgs Da;
+      Da.M = A;
+      Da.wq = Tc.wq;
+      Da.qmax = Tc.qmax;
+      Da.grads = (float *)grads;
+      Da.mgroups = (P.tc_N + 255) / 256;
+      Da.nstage = 3;
+      Da.tmem_cols = 32;
+      while (Da.tmem_cols < 2 * p->chi) Da.tmem_cols <<= 1;
+      long long ctas = (long long)p->L * Da.mgroups;
+      long long nsp = (148LL * 4 + ctas - 1) / ctas;
+      long long maxsp = (B + 2047) / 2048;
+      if (nsp > maxsp) nsp = maxsp;
+      if (nsp < 1) nsp = 1;
+      Da.nsplit = (int)nsp;
+      Da.bchunk = ((B + nsp - 1) / nsp + kDaKC - 1) / kDaKC * kDaKC;
+      dim3 gda((unsigned)(Da.mgroups * Da.nsplit), (unsigned)p->L);
+      prof_begin(st);
+      tc_da_kernel<<<gda, kDaThreads, (size_t)Da.nstage * kDaStage + 1024, st>>>(Da);
+      TNB_LAUNCH_CHECK("tc_da_kernel");
     }
   }
   DaArgs<T> Dg;
@@ -342,10 +376,12 @@ static int mps_backward_t(const tnb_problem *p, const MpsPlan &P, long long B, c
   Dg.bchunk = (B + ns - 1) / ns;
   Dg.bchunk = (Dg.bchunk + 15) / 16 * 16;
   Dg.only_site = -1;
-  dim3 grid(Dg.tiles_a * Dg.tiles_r * Dg.nsplit, p->L, p->d);
-  prof_begin(st);
-  mps_da_kernel<T><<<grid, 256, 0, st>>>(Dg);
-  TNB_LAUNCH_CHECK("mps_da_kernel");
+  if (!P.tc) {
+    dim3 grid(Dg.tiles_a * Dg.tiles_r * Dg.nsplit, p->L, p->d);
+    prof_begin(st);
+    mps_da_kernel<T><<<grid, 256, 0, st>>>(Dg);
+    TNB_LAUNCH_CHECK("mps_da_kernel");
+  }
   // class site: one GEMM per (s, class)
   Dg.only_site = p->out_site;
   work = (long long)Dg.tiles_a * Dg.tiles_r * p->d * p->n_out;

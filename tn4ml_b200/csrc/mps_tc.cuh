@@ -20,6 +20,7 @@
 // warp 4 bulk-copy producer, warp 5 TMEM owner + MMA issuer.
 #pragma once
 #include <cuda_fp16.h>
+#include <limits.h>
 
 #include "mps_simt.cuh"
 #include "ptx_sm100.cuh"
@@ -35,6 +36,8 @@ struct TcArgs {
   const uint8_t *img_n;  // stage images, normal direction      [slab][chi/16][2 planes][N*32 B]
   const uint8_t *img_t;  // stage images, transposed direction
   const int *kW;         // per-slab weight pre-scale exponent
+  float *wq;             // adjoint: phi_s[b] * 2^q[b] per (site, s, b): per-sample weight of the dA GEMM
+  int *qmax;             // adjoint: max_b q[site][b]
   int N, NH, NMMA, nstage, tmem_cols;
   uint32_t stage_bytes;
   size_t site_img_bytes;
@@ -138,6 +141,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_sweep_kernel(TcArgs A, int a
   } else {
     if (half == 0) { if (c == 0) return; site0 = c - 1; nsites = c - 1; dir = -1; transposed = true; }
     else { if (c == L - 1) return; site0 = c + 1; nsites = L - 2 - c; dir = 1; transposed = false; }
+  }
+  if (nsites <= 0 && adjoint) {
+    // the half is a single boundary site: normalise the seed in place and record its dA weights
+    const int bond = half == 0 ? c : c + 1, jb = half == 0 ? 0 : L - 1;
+    for (int r = tid; r < kTcRows; r += blockDim.x) {
+      const long long b = b0 + r;
+      if (b >= M.B) continue;
+      float *seed = M.G + (size_t)bond * M.B * chi + (size_t)b * chi;
+      float m = 0.f;
+      for (int n = 0; n < chi; ++n) m = fmaxf(m, fabsf(seed[n]));
+      int e = 0;
+      if (m > 0.f) frexpf(m, &e);
+      const float sc = ldexpf(1.f, -e);
+      for (int n = 0; n < chi; ++n) seed[n] *= sc;
+      const int q = e - M.exps[(size_t)jb * M.B + b];
+      float ph[kMaxPhys];
+      embed_site(M.emb, M.x[(size_t)b * L + jb], ph);
+      for (int s = 0; s < D; ++s) A.wq[((size_t)jb * D + s) * M.B + b] = ph[s] * ldexpf(1.f, q);
+      atomicMax(&A.qmax[jb], q);
+    }
+    return;
   }
   if (nsites <= 0) {
     if (!adjoint) {  // boundary vector only (class site sits on the boundary)
@@ -263,9 +287,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_sweep_kernel(TcArgs A, int a
       if (m > 0.f) frexpf(m, &e);
       esum = e;
       const float sc = valid ? ldexpf(1.f, kTcKA - e) : 0.f;
+      const float nrm = ldexpf(1.f, -e);
+      float *seed_w = M.G + (size_t)(half == 0 ? c : c + 1) * M.B * chi + (size_t)(valid ? b : 0) * chi;
       for (int kc = 0; kc < chi / 8; ++kc) {
         float w[8];
         float4 v0 = *reinterpret_cast<const float4 *>(seed + kc * 8), v1 = *reinterpret_cast<const float4 *>(seed + kc * 8 + 4);
+        if (valid) {  // the stash keeps the normalised adjoint; its scale lives in q
+          *reinterpret_cast<float4 *>(seed_w + kc * 8) = make_float4(v0.x * nrm, v0.y * nrm, v0.z * nrm, v0.w * nrm);
+          *reinterpret_cast<float4 *>(seed_w + kc * 8 + 4) = make_float4(v1.x * nrm, v1.y * nrm, v1.z * nrm, v1.w * nrm);
+        }
         w[0] = v0.x * sc; w[1] = v0.y * sc; w[2] = v0.z * sc; w[3] = v0.w * sc;
         w[4] = v1.x * sc; w[5] = v1.y * sc; w[6] = v1.z * sc; w[7] = v1.w * sc;
         uint4 hi, lo;
@@ -310,8 +340,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_sweep_kernel(TcArgs A, int a
         if (valid && M.exps) M.exps[(size_t)site * M.B + b] = dtrue;
         out_scale = 1.f;
       } else {
+        // dA_site = sum_b 2^q (F x phi x G) with q = h_in - delta_site ; h_in is the exponent of the input adjoint
+        const int q = esum - dsite;
+        if (valid) {
+#pragma unroll
+          for (int s = 0; s < D; ++s) A.wq[((size_t)site * D + s) * M.B + b] = ph[s] * ldexpf(1.f, q);
+        }
+        int qm = valid ? q : INT_MIN;
+        for (int off = 16; off > 0; off >>= 1) qm = max(qm, __shfl_xor_sync(0xffffffffu, qm, off));
+        if (lane == 0 && qm != INT_MIN) atomicMax(&A.qmax[site], qm);
         esum += dtrue - dsite;
-        out_scale = ldexpf(1.f, esum);
+        out_scale = 1.f;
       }
       const float nsc = valid ? ldexpf(1.f, -e) : 0.f;
       float *env = adjoint ? M.G + (size_t)bond_out * M.B * chi : mps_fenv(M, bond_out);
@@ -356,12 +395,187 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_sweep_kernel(TcArgs A, int a
       ptx::mbar_arrive(a_ready);
     }
     if (!adjoint && valid) M.esum[(size_t)half * M.B + b] = esum;
+    if (adjoint) {
+      const int jb = half == 0 ? 0 : L - 1;  // the boundary site: no chain step, but it has a gradient
+      int qm = INT_MIN;
+      if (valid) {
+        const int q = esum - M.exps[(size_t)jb * M.B + b];
+        float ph[kMaxPhys];
+        embed_site(M.emb, M.x[(size_t)b * L + jb], ph);
+#pragma unroll
+        for (int s = 0; s < D; ++s) A.wq[((size_t)jb * D + s) * M.B + b] = ph[s] * ldexpf(1.f, q);
+        qm = q;
+      }
+      for (int off = 16; off > 0; off >>= 1) qm = max(qm, __shfl_xor_sync(0xffffffffu, qm, off));
+      if (lane == 0 && qm != INT_MIN) atomicMax(&A.qmax[jb], qm);
+    }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   if (warp == 5) ptx::tmem_dealloc(tmem_base, (uint32_t)A.tmem_cols);
+}
+
+
+// ---------------------------------------------------------------------------------------
+// K4 (tensor-core family): weight gradients as a batch-reduction GEMM on tcgen05.
+//   dA_site[a, r, s] = 2^qmax * sum_b (U[b,a] * wq[site][s][b] * 2^-qmax) * V[b,r]
+//   rows m = s*chi + a (M tiles of 128, two per CTA), columns r (N = chi), K = samples.
+// Both operands are produced in-kernel from the fp32 environment stashes: 8 producer warps
+// read U / V coalesced, apply the per-sample weight, split to fp16 hi/lo and write the
+// canonical K-major shared-memory layout; warp 8 issues the MMAs; warps 0-3 drain TMEM once
+// at the end and reduce into the packed gradient with fp32 atomics (split-K across CTAs).
+// ---------------------------------------------------------------------------------------
+struct TcDaArgs {
+  MpsArgs<float> M;
+  const float *wq;
+  const int *qmax;
+  float *grads;
+  int mgroups, nsplit, nstage, tmem_cols;
+  long long bchunk;  // samples per split (multiple of 32)
+};
+
+constexpr int kDaKC = 32;                         // samples per pipeline stage
+constexpr int kDaProducers = 256;                 // threads
+constexpr int kDaThreads = kDaProducers + 32;
+constexpr uint32_t kDaPlane = 256u * kDaKC * 2u;  // one operand plane: 256 rows x 32 samples fp16 = 16 KB
+constexpr uint32_t kDaStage = 4u * kDaPlane;      // A_hi, A_lo, B_hi, B_lo
+
+__global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const MpsArgs<float> &M = A.M;
+  const int chi = M.chip, D = M.D, c = M.c, L = M.L;
+  const int site = blockIdx.y;
+  if (site == c) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int group = blockIdx.x % A.mgroups, split = blockIdx.x / A.mgroups;
+  const int Mtot = D * chi;
+  const int m0 = group * 256;
+  const int ntile = min(2, (Mtot - m0) / 128);
+  const long long kbeg = (long long)split * A.bchunk;
+  const long long kend = min(M.B, kbeg + A.bchunk);
+  if (kbeg >= kend) return;
+  const int nchunks = (int)((kend - kbeg + kDaKC - 1) / kDaKC);
+  const float *U = site < c ? mps_fenv(M, site) : M.G + (size_t)site * M.B * chi;
+  const float *V = site < c ? M.G + (size_t)(site + 1) * M.B * chi : mps_fenv(M, site + 1);
+
+  uint8_t *stages = smem;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(stages + (size_t)A.nstage * kDaStage);
+  uint64_t *full = bars, *empty = bars + A.nstage, *done = bars + 2 * A.nstage;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done + 1);
+  if (tid == 0) {
+    for (int i = 0; i < A.nstage; ++i) {
+      ptx::mbar_init(&full[i], kDaProducers);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    ptx::mbar_init(done, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 8) {
+    ptx::tmem_alloc(tmem_slot, (uint32_t)A.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int qmax = A.qmax[site];
+
+  if (warp == 8) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::idesc_f16_f32(128, chi);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        ptx::mbar_wait(&full[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t st = ptx::smem_u32(stages + (size_t)stage * kDaStage);
+        for (int t = 0; t < ntile; ++t) {
+#pragma unroll
+          for (int ks = 0; ks < kDaKC / 16; ++ks) {
+            const uint64_t da_hi = ptx::smem_desc_kmajor(st + t * 8192 + ks * 256, 128, 512);
+            const uint64_t da_lo = ptx::smem_desc_kmajor(st + kDaPlane + t * 8192 + ks * 256, 128, 512);
+            const uint64_t db_hi = ptx::smem_desc_kmajor(st + 2 * kDaPlane + ks * 256, 128, 512);
+            const uint64_t db_lo = ptx::smem_desc_kmajor(st + 3 * kDaPlane + ks * 256, 128, 512);
+            const uint32_t d = tmem_base + (uint32_t)t * chi;
+            ptx::mma_f16(d, da_hi, db_hi, idesc, (ch > 0 || ks > 0) ? 1u : 0u);
+            ptx::mma_f16(d, da_lo, db_hi, idesc, 1u);
+            ptx::mma_f16(d, da_hi, db_lo, idesc, 1u);
+          }
+        }
+        ptx::mma_commit(&empty[stage]);
+        if (++stage == A.nstage) { stage = 0; phase ^= 1; }
+      }
+      ptx::mma_commit(done);
+    }
+  } else {
+    // ===== producers =====
+    const int R = ntile * 128 + chi;  // operand rows per stage: A rows then B rows
+    const float qs = ldexpf(1.f, kTcKA - qmax);
+    const float ka = 16384.f;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int ch = 0; ch < nchunks; ++ch) {
+      ptx::mbar_wait(&empty[stage], phase ^ 1);
+      uint8_t *st = stages + (size_t)stage * kDaStage;
+      const long long bbase = kbeg + (long long)ch * kDaKC;
+      for (int item = tid; item < R * (kDaKC / 8); item += kDaProducers) {
+        const int oct = item / R, rowi = item - oct * R;
+        const long long bo = bbase + oct * 8;
+        float w[8];
+        uint8_t *dst;
+        if (rowi < ntile * 128) {
+          const int m = m0 + rowi, s = m / chi, a = m - s * chi;
+          const float *wsrc = A.wq + ((size_t)site * D + s) * M.B;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const long long b = bo + j;
+            w[j] = b < kend ? U[(size_t)b * chi + a] * (wsrc[b] * qs) : 0.f;
+          }
+          dst = st + (rowi >> 3) * 512 + oct * 128 + (rowi & 7) * 16;
+        } else {
+          const int n = rowi - ntile * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const long long b = bo + j;
+            w[j] = b < kend ? V[(size_t)b * chi + n] * ka : 0.f;
+          }
+          dst = st + 2 * kDaPlane + (n >> 3) * 512 + oct * 128 + (n & 7) * 16;
+        }
+        uint4 hi, lo;
+        split8(w, hi, lo);
+        *reinterpret_cast<uint4 *>(dst) = hi;
+        *reinterpret_cast<uint4 *>(dst + kDaPlane) = lo;
+      }
+      ptx::fence_proxy_async();
+      ptx::mbar_arrive(&full[stage]);
+      if (++stage == A.nstage) { stage = 0; phase ^= 1; }
+    }
+    // ===== epilogue (warps 0-3): TMEM -> packed gradient =====
+    if (warp < 4) {
+      ptx::mbar_wait(done, 0);
+      ptx::tc_fence_after();
+      const float sc = ldexpf(1.f, qmax - 2 * kTcKA);
+      const size_t site_off = (size_t)site * chi * chi * D + (site > c ? (size_t)chi * chi * D * (M.C - 1) : 0);
+      float *g = A.grads + site_off;
+      for (int t = 0; t < ntile; ++t) {
+        const int m = m0 + t * 128 + tid, s = m / chi, a = m - s * chi;
+        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)t * chi;
+        for (int n0 = 0; n0 < chi; n0 += 16) {
+          float v[16];
+          ptx::tmem_ld16(trow + n0, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) atomicAdd(&g[((size_t)a * chi + n0 + j) * D + s], v[j] * sc);
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (warp == 8) ptx::tmem_dealloc(tmem_base, (uint32_t)A.tmem_cols);
 }
 
 }  // namespace tnb
