@@ -423,8 +423,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_sweep_kernel(TcArgs A, int a
 //   dA_site[a, r, s] = 2^qmax * sum_b (U[b,a] * wq[site][s][b] * 2^-qmax) * V[b,r]
 //   rows m = s*chi + a (M tiles of 128, two per CTA), columns r (N = chi), K = samples.
 // Both operands are produced in-kernel from the fp32 environment stashes: 8 producer warps
-// read U / V coalesced, apply the per-sample weight, split to fp16 hi/lo and write the
-// canonical K-major shared-memory layout; warp 8 issues the MMAs; warps 0-3 drain TMEM once
+// (lane == sample) read 32-byte pieces of their stash rows, apply the per-sample weight, split
+// to fp16 hi/lo and write the canonical MN-major shared-memory layout; warp 8 issues the MMAs; warps 0-3 drain TMEM once
 // at the end and reduce into the packed gradient with fp32 atomics (split-K across CTAs).
 // ---------------------------------------------------------------------------------------
 struct TcDaArgs {
@@ -445,7 +445,7 @@ constexpr uint32_t kDaStage = 4u * kDaPlane;      // A_hi, A_lo, B_hi, B_lo
 __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const MpsArgs<float> &M = A.M;
-  const int chi = M.chip, D = M.D, c = M.c, L = M.L;
+  const int chi = M.chip, D = M.D, c = M.c;
   const int site = blockIdx.y;
   if (site == c) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
 
   if (warp == 8) {
     if (lane == 0) {
-      const uint32_t idesc = ptx::idesc_f16_f32(128, chi);
+      const uint32_t idesc = ptx::idesc_f16_f32(128, chi) | (1u << 15) | (1u << 16);  // A and B MN-major
       int stage = 0;
       uint32_t phase = 0;
       for (int ch = 0; ch < nchunks; ++ch) {
@@ -510,39 +510,44 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
       ptx::mma_commit(done);
     }
   } else {
-    // ===== producers =====
-    const int R = ntile * 128 + chi;  // operand rows per stage: A rows then B rows
+    // ===== producers: lane == sample, warp == row octet (MN-major operand tiles) =====
+    // Shared-memory operand layout (MN-major, no swizzle): 8 consecutive rows of one sample are one
+    // 16-byte unit; 8 samples form a 128-byte core matrix; sample blocks at LBO = 128 B, row octets
+    // at SBO = 512 B.  Each lane streams 32 contiguous bytes of its own stash row per item.
+    const int RO = (ntile * 128 + chi) / 8;  // row octets per stage: A octets then B octets
     const float qs = ldexpf(1.f, kTcKA - qmax);
     const float ka = 16384.f;
+    const uint32_t lane_off = (uint32_t)(lane >> 3) * 128 + (uint32_t)(lane & 7) * 16;
     int stage = 0;
     uint32_t phase = 0;
     for (int ch = 0; ch < nchunks; ++ch) {
+      const long long b = kbeg + (long long)ch * kDaKC + lane;
+      const bool ok = b < kend;
+      const float *urow = U + (size_t)(ok ? b : kbeg) * chi;
+      const float *vrow = V + (size_t)(ok ? b : kbeg) * chi;
+      float wsv[kMaxPhys];
+      for (int s = 0; s < D; ++s) wsv[s] = ok ? A.wq[((size_t)site * D + s) * M.B + b] * qs : 0.f;
       ptx::mbar_wait(&empty[stage], phase ^ 1);
       uint8_t *st = stages + (size_t)stage * kDaStage;
-      const long long bbase = kbeg + (long long)ch * kDaKC;
-      for (int item = tid; item < R * (kDaKC / 8); item += kDaProducers) {
-        const int oct = item / R, rowi = item - oct * R;
-        const long long bo = bbase + oct * 8;
-        float w[8];
+#pragma unroll 4
+      for (int ro = warp; ro < RO; ro += kDaProducers / 32) {
+        float4 v0, v1;
+        float sc;
         uint8_t *dst;
-        if (rowi < ntile * 128) {
-          const int m = m0 + rowi, s = m / chi, a = m - s * chi;
-          const float *wsrc = A.wq + ((size_t)site * D + s) * M.B;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const long long b = bo + j;
-            w[j] = b < kend ? U[(size_t)b * chi + a] * (wsrc[b] * qs) : 0.f;
-          }
-          dst = st + (rowi >> 3) * 512 + oct * 128 + (rowi & 7) * 16;
+        if (ro < ntile * 16) {
+          const int m = m0 + ro * 8, s = m / chi, a = m - s * chi;
+          v0 = *reinterpret_cast<const float4 *>(urow + a);
+          v1 = *reinterpret_cast<const float4 *>(urow + a + 4);
+          sc = wsv[s];
+          dst = st + (uint32_t)ro * 512 + lane_off;
         } else {
-          const int n = rowi - ntile * 128;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const long long b = bo + j;
-            w[j] = b < kend ? V[(size_t)b * chi + n] * ka : 0.f;
-          }
-          dst = st + 2 * kDaPlane + (n >> 3) * 512 + oct * 128 + (n & 7) * 16;
+          const int n = (ro - ntile * 16) * 8;
+          v0 = *reinterpret_cast<const float4 *>(vrow + n);
+          v1 = *reinterpret_cast<const float4 *>(vrow + n + 4);
+          sc = ok ? ka : 0.f;
+          dst = st + 2 * kDaPlane + (uint32_t)(ro - ntile * 16) * 512 + lane_off;
         }
+        float w[8] = {v0.x * sc, v0.y * sc, v0.z * sc, v0.w * sc, v1.x * sc, v1.y * sc, v1.z * sc, v1.w * sc};
         uint4 hi, lo;
         split8(w, hi, lo);
         *reinterpret_cast<uint4 *>(dst) = hi;
