@@ -525,33 +525,49 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
       const bool ok = b < kend;
       const float *urow = U + (size_t)(ok ? b : kbeg) * chi;
       const float *vrow = V + (size_t)(ok ? b : kbeg) * chi;
+      // phase 1: issue every global load of this stage (read-only path) before waiting for the slot
+      constexpr int kItems = 8;  // row octets per warp and stage: (2*128 + 256) / 8 / 8 warps
+      float4 r0[kItems], r1[kItems];
       float wsv[kMaxPhys];
-      for (int s = 0; s < D; ++s) wsv[s] = ok ? A.wq[((size_t)site * D + s) * M.B + b] * qs : 0.f;
+      for (int s = 0; s < D; ++s) wsv[s] = ok ? __ldg(&A.wq[((size_t)site * D + s) * M.B + b]) * qs : 0.f;
+#pragma unroll
+      for (int i = 0; i < kItems; ++i) {
+        const int ro = warp + i * (kDaProducers / 32);
+        if (ro < RO) {
+          const float *src;
+          if (ro < ntile * 16) {
+            const int m = m0 + ro * 8, s = m / chi;
+            src = urow + (m - s * chi);
+          } else {
+            src = vrow + (ro - ntile * 16) * 8;
+          }
+          r0[i] = __ldg(reinterpret_cast<const float4 *>(src));
+          r1[i] = __ldg(reinterpret_cast<const float4 *>(src + 4));
+        }
+      }
       ptx::mbar_wait(&empty[stage], phase ^ 1);
       uint8_t *st = stages + (size_t)stage * kDaStage;
-#pragma unroll 4
-      for (int ro = warp; ro < RO; ro += kDaProducers / 32) {
-        float4 v0, v1;
-        float sc;
-        uint8_t *dst;
-        if (ro < ntile * 16) {
-          const int m = m0 + ro * 8, s = m / chi, a = m - s * chi;
-          v0 = *reinterpret_cast<const float4 *>(urow + a);
-          v1 = *reinterpret_cast<const float4 *>(urow + a + 4);
-          sc = wsv[s];
-          dst = st + (uint32_t)ro * 512 + lane_off;
-        } else {
-          const int n = (ro - ntile * 16) * 8;
-          v0 = *reinterpret_cast<const float4 *>(vrow + n);
-          v1 = *reinterpret_cast<const float4 *>(vrow + n + 4);
-          sc = ok ? ka : 0.f;
-          dst = st + 2 * kDaPlane + (uint32_t)(ro - ntile * 16) * 512 + lane_off;
+      // phase 2: weight, split to fp16 hi/lo, write the operand tiles
+#pragma unroll
+      for (int i = 0; i < kItems; ++i) {
+        const int ro = warp + i * (kDaProducers / 32);
+        if (ro < RO) {
+          float sc;
+          uint8_t *dst;
+          if (ro < ntile * 16) {
+            sc = wsv[(m0 + ro * 8) / chi];
+            dst = st + (uint32_t)ro * 512 + lane_off;
+          } else {
+            sc = ok ? ka : 0.f;
+            dst = st + 2 * kDaPlane + (uint32_t)(ro - ntile * 16) * 512 + lane_off;
+          }
+          float w[8] = {r0[i].x * sc, r0[i].y * sc, r0[i].z * sc, r0[i].w * sc,
+                        r1[i].x * sc, r1[i].y * sc, r1[i].z * sc, r1[i].w * sc};
+          uint4 hi, lo;
+          split8(w, hi, lo);
+          *reinterpret_cast<uint4 *>(dst) = hi;
+          *reinterpret_cast<uint4 *>(dst + kDaPlane) = lo;
         }
-        float w[8] = {v0.x * sc, v0.y * sc, v0.z * sc, v0.w * sc, v1.x * sc, v1.y * sc, v1.z * sc, v1.w * sc};
-        uint4 hi, lo;
-        split8(w, hi, lo);
-        *reinterpret_cast<uint4 *>(dst) = hi;
-        *reinterpret_cast<uint4 *>(dst + kDaPlane) = lo;
       }
       ptx::fence_proxy_async();
       ptx::mbar_arrive(&full[stage]);
