@@ -437,7 +437,7 @@ struct TcDaArgs {
 };
 
 constexpr int kDaKC = 32;                         // samples per pipeline stage
-constexpr int kDaProducers = 256;                 // threads
+constexpr int kDaProducers = 512;                 // threads (16 warps)
 constexpr int kDaThreads = kDaProducers + 32;
 constexpr uint32_t kDaPlane = 256u * kDaKC * 2u;  // one operand plane: 256 rows x 32 samples fp16 = 16 KB
 constexpr uint32_t kDaStage = 4u * kDaPlane;      // A_hi, A_lo, B_hi, B_lo
@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
     ptx::mbar_init(done, 1);
     ptx::fence_mbar_init();
   }
-  if (warp == 8) {
+  if (warp == kDaProducers / 32) {
     ptx::tmem_alloc(tmem_slot, (uint32_t)A.tmem_cols);
     ptx::tmem_relinquish();
   }
@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
   const uint32_t tmem_base = *tmem_slot;
   const int qmax = A.qmax[site];
 
-  if (warp == 8) {
+  if (warp == kDaProducers / 32) {
     if (lane == 0) {
       const uint32_t idesc = ptx::idesc_f16_f32(128, chi) | (1u << 15) | (1u << 16);  // A and B MN-major
       int stage = 0;
@@ -518,60 +518,77 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
     const float qs = ldexpf(1.f, kTcKA - qmax);
     const float ka = 16384.f;
     const uint32_t lane_off = (uint32_t)(lane >> 3) * 128 + (uint32_t)(lane & 7) * 16;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int ch = 0; ch < nchunks; ++ch) {
+    constexpr int kItems = 4;  // row octets per warp and stage: (2*128 + 256) / 8 / 16 warps
+    // per-item constants (independent of the sample chunk)
+    int src_off[kItems], s_of[kItems];
+    uint32_t dst_off[kItems];
+#pragma unroll
+    for (int i = 0; i < kItems; ++i) {
+      const int ro = warp + i * (kDaProducers / 32);
+      src_off[i] = -1; s_of[i] = -1; dst_off[i] = 0;
+      if (ro < RO) {
+        if (ro < ntile * 16) {
+          const int m = m0 + ro * 8, sidx = m / chi;
+          s_of[i] = sidx;
+          src_off[i] = m - sidx * chi;
+          dst_off[i] = (uint32_t)ro * 512 + lane_off;
+        } else {
+          src_off[i] = (ro - ntile * 16) * 8;
+          dst_off[i] = 2 * kDaPlane + (uint32_t)(ro - ntile * 16) * 512 + lane_off;
+        }
+      }
+    }
+    const float *wq_site = A.wq + (size_t)site * D * M.B;
+    // issue every global load of one stage (read-only path); two stages are kept in flight
+    auto issue = [&](int ch, float4(&r0)[kItems], float4(&r1)[kItems], float(&sc)[kItems]) {
       const long long b = kbeg + (long long)ch * kDaKC + lane;
       const bool ok = b < kend;
-      const float *urow = U + (size_t)(ok ? b : kbeg) * chi;
-      const float *vrow = V + (size_t)(ok ? b : kbeg) * chi;
-      // phase 1: issue every global load of this stage (read-only path) before waiting for the slot
-      constexpr int kItems = 8;  // row octets per warp and stage: (2*128 + 256) / 8 / 8 warps
-      float4 r0[kItems], r1[kItems];
-      float wsv[kMaxPhys];
-      for (int s = 0; s < D; ++s) wsv[s] = ok ? __ldg(&A.wq[((size_t)site * D + s) * M.B + b]) * qs : 0.f;
+      const size_t row = (size_t)(ok ? b : kbeg) * chi;
 #pragma unroll
       for (int i = 0; i < kItems; ++i) {
-        const int ro = warp + i * (kDaProducers / 32);
-        if (ro < RO) {
-          const float *src;
-          if (ro < ntile * 16) {
-            const int m = m0 + ro * 8, s = m / chi;
-            src = urow + (m - s * chi);
-          } else {
-            src = vrow + (ro - ntile * 16) * 8;
-          }
+        sc[i] = 0.f;
+        if (src_off[i] >= 0) {
+          const float *src = (s_of[i] >= 0 ? U : V) + row + src_off[i];
           r0[i] = __ldg(reinterpret_cast<const float4 *>(src));
           r1[i] = __ldg(reinterpret_cast<const float4 *>(src + 4));
+          if (ok) sc[i] = s_of[i] >= 0 ? __ldg(wq_site + (size_t)s_of[i] * M.B + b) * qs : ka;
         }
       }
-      ptx::mbar_wait(&empty[stage], phase ^ 1);
-      uint8_t *st = stages + (size_t)stage * kDaStage;
-      // phase 2: weight, split to fp16 hi/lo, write the operand tiles
+    };
+    auto convert = [&](uint8_t *st, const float4(&r0)[kItems], const float4(&r1)[kItems], const float(&sc)[kItems]) {
 #pragma unroll
       for (int i = 0; i < kItems; ++i) {
-        const int ro = warp + i * (kDaProducers / 32);
-        if (ro < RO) {
-          float sc;
-          uint8_t *dst;
-          if (ro < ntile * 16) {
-            sc = wsv[(m0 + ro * 8) / chi];
-            dst = st + (uint32_t)ro * 512 + lane_off;
-          } else {
-            sc = ok ? ka : 0.f;
-            dst = st + 2 * kDaPlane + (uint32_t)(ro - ntile * 16) * 512 + lane_off;
-          }
-          float w[8] = {r0[i].x * sc, r0[i].y * sc, r0[i].z * sc, r0[i].w * sc,
-                        r1[i].x * sc, r1[i].y * sc, r1[i].z * sc, r1[i].w * sc};
+        if (src_off[i] >= 0) {
+          const float f = sc[i];
+          float w[8] = {r0[i].x * f, r0[i].y * f, r0[i].z * f, r0[i].w * f,
+                        r1[i].x * f, r1[i].y * f, r1[i].z * f, r1[i].w * f};
           uint4 hi, lo;
           split8(w, hi, lo);
-          *reinterpret_cast<uint4 *>(dst) = hi;
-          *reinterpret_cast<uint4 *>(dst + kDaPlane) = lo;
+          *reinterpret_cast<uint4 *>(st + dst_off[i]) = hi;
+          *reinterpret_cast<uint4 *>(st + dst_off[i] + kDaPlane) = lo;
         }
       }
+    };
+    float4 ra0[kItems], ra1[kItems], rb0[kItems], rb1[kItems];
+    float sa[kItems], sb[kItems];
+    int stage = 0;
+    uint32_t phase = 0;
+    issue(0, ra0, ra1, sa);
+    for (int ch = 0; ch < nchunks; ch += 2) {
+      if (ch + 1 < nchunks) issue(ch + 1, rb0, rb1, sb);
+      ptx::mbar_wait(&empty[stage], phase ^ 1);
+      convert(stages + (size_t)stage * kDaStage, ra0, ra1, sa);
       ptx::fence_proxy_async();
       ptx::mbar_arrive(&full[stage]);
       if (++stage == A.nstage) { stage = 0; phase ^= 1; }
+      if (ch + 1 < nchunks) {
+        if (ch + 2 < nchunks) issue(ch + 2, ra0, ra1, sa);
+        ptx::mbar_wait(&empty[stage], phase ^ 1);
+        convert(stages + (size_t)stage * kDaStage, rb0, rb1, sb);
+        ptx::fence_proxy_async();
+        ptx::mbar_arrive(&full[stage]);
+        if (++stage == A.nstage) { stage = 0; phase ^= 1; }
+      }
     }
     // ===== epilogue (warps 0-3): TMEM -> packed gradient =====
     if (warp < 4) {
@@ -596,7 +613,7 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  if (warp == 8) ptx::tmem_dealloc(tmem_base, (uint32_t)A.tmem_cols);
+  if (warp == kDaProducers / 32) ptx::tmem_dealloc(tmem_base, (uint32_t)A.tmem_cols);
 }
 
 }  // namespace tnb
