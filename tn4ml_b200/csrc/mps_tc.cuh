@@ -439,7 +439,8 @@ struct TcDaArgs {
 constexpr int kDaKC = 32;                         // samples per pipeline stage
 constexpr int kDaProducers = 512;                 // threads (16 warps)
 constexpr int kDaThreads = kDaProducers + 32;
-constexpr uint32_t kDaPlane = 256u * kDaKC * 2u;  // one operand plane: 256 rows x 32 samples fp16 = 16 KB
+constexpr uint32_t kDaSBO = 528u;                 // row-octet stride: 4 sample blocks x 128 B + 16 B skew (bank spread)
+constexpr uint32_t kDaPlane = 32u * kDaSBO;       // one operand plane: 32 row octets x 32 samples fp16
 constexpr uint32_t kDaStage = 4u * kDaPlane;      // A_hi, A_lo, B_hi, B_lo
 
 __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
@@ -494,10 +495,10 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
         for (int t = 0; t < ntile; ++t) {
 #pragma unroll
           for (int ks = 0; ks < kDaKC / 16; ++ks) {
-            const uint64_t da_hi = ptx::smem_desc_kmajor(st + t * 8192 + ks * 256, 128, 512);
-            const uint64_t da_lo = ptx::smem_desc_kmajor(st + kDaPlane + t * 8192 + ks * 256, 128, 512);
-            const uint64_t db_hi = ptx::smem_desc_kmajor(st + 2 * kDaPlane + ks * 256, 128, 512);
-            const uint64_t db_lo = ptx::smem_desc_kmajor(st + 3 * kDaPlane + ks * 256, 128, 512);
+            const uint64_t da_hi = ptx::smem_desc_kmajor(st + t * 16 * kDaSBO + ks * 256, 128, kDaSBO);
+            const uint64_t da_lo = ptx::smem_desc_kmajor(st + kDaPlane + t * 16 * kDaSBO + ks * 256, 128, kDaSBO);
+            const uint64_t db_hi = ptx::smem_desc_kmajor(st + 2 * kDaPlane + ks * 256, 128, kDaSBO);
+            const uint64_t db_lo = ptx::smem_desc_kmajor(st + 3 * kDaPlane + ks * 256, 128, kDaSBO);
             const uint32_t d = tmem_base + (uint32_t)t * chi;
             ptx::mma_f16(d, da_hi, db_hi, idesc, (ch > 0 || ks > 0) ? 1u : 0u);
             ptx::mma_f16(d, da_lo, db_hi, idesc, 1u);
@@ -510,81 +511,89 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
       ptx::mma_commit(done);
     }
   } else {
-    // ===== producers: lane == sample, warp == row octet (MN-major operand tiles) =====
+    // ===== producers: warp == (sample, 128-row block), lane == 4 consecutive rows =====
     // Shared-memory operand layout (MN-major, no swizzle): 8 consecutive rows of one sample are one
     // 16-byte unit; 8 samples form a 128-byte core matrix; sample blocks at LBO = 128 B, row octets
-    // at SBO = 512 B.  Each lane streams 32 contiguous bytes of its own stash row per item.
-    const int RO = (ntile * 128 + chi) / 8;  // row octets per stage: A octets then B octets
+    // at SBO = 528 B (the 16-byte skew spreads a warp's 16 octets over all banks).  A warp reads 512
+    // contiguous bytes of ONE stash row per load, so L1 sees 4 lines per request instead of 32.
+    const int nb = (chi + 127) / 128;       // 128-column blocks of the B operand
+    const int IPS = ntile + nb;             // warp-items per sample
+    const int nitems = kDaKC * IPS;         // warp-items per stage (<= 128)
     const float qs = ldexpf(1.f, kTcKA - qmax);
     const float ka = 16384.f;
-    const uint32_t lane_off = (uint32_t)(lane >> 3) * 128 + (uint32_t)(lane & 7) * 16;
-    constexpr int kItems = 4;  // row octets per warp and stage: (2*128 + 256) / 8 / 16 warps
+    constexpr int kItems = 8;               // warp-items per warp and stage: 128 / 16 warps
+    constexpr int kWarps = kDaProducers / 32;
     // per-item constants (independent of the sample chunk)
-    int src_off[kItems], s_of[kItems];
+    int k_of[kItems], src_off[kItems], s_of[kItems];
     uint32_t dst_off[kItems];
 #pragma unroll
     for (int i = 0; i < kItems; ++i) {
-      const int ro = warp + i * (kDaProducers / 32);
-      src_off[i] = -1; s_of[i] = -1; dst_off[i] = 0;
-      if (ro < RO) {
-        if (ro < ntile * 16) {
-          const int m = m0 + ro * 8, sidx = m / chi;
-          s_of[i] = sidx;
-          src_off[i] = m - sidx * chi;
-          dst_off[i] = (uint32_t)ro * 512 + lane_off;
-        } else {
-          src_off[i] = (ro - ntile * 16) * 8;
-          dst_off[i] = 2 * kDaPlane + (uint32_t)(ro - ntile * 16) * 512 + lane_off;
+      const int it = warp + i * kWarps;
+      k_of[i] = -1; src_off[i] = 0; s_of[i] = -1; dst_off[i] = 0;
+      if (it < nitems) {
+        const int k = it / IPS, sub = it - k * IPS;
+        if (sub < ntile) {  // A operand: rows m0 + 128*sub + 4*lane .. +3
+          const int m = m0 + sub * 128 + 4 * lane, sidx = m / chi;
+          k_of[i] = k; s_of[i] = sidx; src_off[i] = m - sidx * chi;
+          dst_off[i] = (uint32_t)(sub * 16 + (lane >> 1)) * kDaSBO + (uint32_t)(k >> 3) * 128 + (uint32_t)(k & 7) * 16 +
+                       (uint32_t)(lane & 1) * 8;
+        } else {            // B operand: columns 128*(sub - ntile) + 4*lane .. +3
+          const int n = (sub - ntile) * 128 + 4 * lane;
+          if (n < chi) {
+            k_of[i] = k; src_off[i] = n;
+            dst_off[i] = 2 * kDaPlane + (uint32_t)(n >> 3) * kDaSBO + (uint32_t)(k >> 3) * 128 + (uint32_t)(k & 7) * 16 +
+                         (uint32_t)(lane & 1) * 8;
+          }
         }
       }
     }
     const float *wq_site = A.wq + (size_t)site * D * M.B;
     // issue every global load of one stage (read-only path); two stages are kept in flight
-    auto issue = [&](int ch, float4(&r0)[kItems], float4(&r1)[kItems], float(&sc)[kItems]) {
-      const long long b = kbeg + (long long)ch * kDaKC + lane;
-      const bool ok = b < kend;
-      const size_t row = (size_t)(ok ? b : kbeg) * chi;
+    auto issue = [&](int ch, float4(&r)[kItems], float(&sc)[kItems]) {
+      const long long bbase = kbeg + (long long)ch * kDaKC;
 #pragma unroll
       for (int i = 0; i < kItems; ++i) {
         sc[i] = 0.f;
-        if (src_off[i] >= 0) {
-          const float *src = (s_of[i] >= 0 ? U : V) + row + src_off[i];
-          r0[i] = __ldg(reinterpret_cast<const float4 *>(src));
-          r1[i] = __ldg(reinterpret_cast<const float4 *>(src + 4));
+        if (k_of[i] >= 0) {
+          const long long b = bbase + k_of[i];
+          const bool ok = b < kend;
+          const float *src = (s_of[i] >= 0 ? U : V) + (size_t)(ok ? b : kbeg) * chi + src_off[i];
+          r[i] = __ldg(reinterpret_cast<const float4 *>(src));
           if (ok) sc[i] = s_of[i] >= 0 ? __ldg(wq_site + (size_t)s_of[i] * M.B + b) * qs : ka;
         }
       }
     };
-    auto convert = [&](uint8_t *st, const float4(&r0)[kItems], const float4(&r1)[kItems], const float(&sc)[kItems]) {
+    auto convert = [&](uint8_t *st, const float4(&r)[kItems], const float(&sc)[kItems]) {
 #pragma unroll
       for (int i = 0; i < kItems; ++i) {
-        if (src_off[i] >= 0) {
+        if (k_of[i] >= 0) {
           const float f = sc[i];
-          float w[8] = {r0[i].x * f, r0[i].y * f, r0[i].z * f, r0[i].w * f,
-                        r1[i].x * f, r1[i].y * f, r1[i].z * f, r1[i].w * f};
-          uint4 hi, lo;
-          split8(w, hi, lo);
-          *reinterpret_cast<uint4 *>(st + dst_off[i]) = hi;
-          *reinterpret_cast<uint4 *>(st + dst_off[i] + kDaPlane) = lo;
+          const float w0 = r[i].x * f, w1 = r[i].y * f, w2 = r[i].z * f, w3 = r[i].w * f;
+          const __half h0 = __float2half_rn(w0), h1 = __float2half_rn(w1), h2 = __float2half_rn(w2), h3 = __float2half_rn(w3);
+          __half2 hi[2] = {__halves2half2(h0, h1), __halves2half2(h2, h3)};
+          __half2 lo[2] = {__floats2half2_rn(w0 - __half2float(h0), w1 - __half2float(h1)),
+                           __floats2half2_rn(w2 - __half2float(h2), w3 - __half2float(h3))};
+          *reinterpret_cast<uint2 *>(st + dst_off[i]) = *reinterpret_cast<uint2 *>(hi);
+          *reinterpret_cast<uint2 *>(st + dst_off[i] + kDaPlane) = *reinterpret_cast<uint2 *>(lo);
         }
       }
     };
-    float4 ra0[kItems], ra1[kItems], rb0[kItems], rb1[kItems];
+    float4 ra[kItems], rb[kItems];
     float sa[kItems], sb[kItems];
     int stage = 0;
     uint32_t phase = 0;
-    issue(0, ra0, ra1, sa);
+    issue(0, ra, sa);
     for (int ch = 0; ch < nchunks; ch += 2) {
-      if (ch + 1 < nchunks) issue(ch + 1, rb0, rb1, sb);
+      if (ch + 1 < nchunks) issue(ch + 1, rb, sb);
       ptx::mbar_wait(&empty[stage], phase ^ 1);
-      convert(stages + (size_t)stage * kDaStage, ra0, ra1, sa);
+      convert(stages + (size_t)stage * kDaStage, ra, sa);
       ptx::fence_proxy_async();
       ptx::mbar_arrive(&full[stage]);
       if (++stage == A.nstage) { stage = 0; phase ^= 1; }
       if (ch + 1 < nchunks) {
-        if (ch + 2 < nchunks) issue(ch + 2, ra0, ra1, sa);
+        if (ch + 2 < nchunks) issue(ch + 2, ra, sa);
         ptx::mbar_wait(&empty[stage], phase ^ 1);
-        convert(stages + (size_t)stage * kDaStage, rb0, rb1, sb);
+        convert(stages + (size_t)stage * kDaStage, rb, sb);
         ptx::fence_proxy_async();
         ptx::mbar_arrive(&full[stage]);
         if (++stage == A.nstage) { stage = 0; phase ^= 1; }
