@@ -517,88 +517,92 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
     // at SBO = 528 B (the 16-byte skew spreads a warp's 16 octets over all banks).  A warp reads 512
     // contiguous bytes of ONE stash row per load, so L1 sees 4 lines per request instead of 32.
     const int nb = (chi + 127) / 128;       // 128-column blocks of the B operand
-    const int IPS = ntile + nb;             // warp-items per sample
-    const int nitems = kDaKC * IPS;         // warp-items per stage (<= 128)
+    const int IPS = ntile + nb;             // 128-row blocks per sample: A tiles then B blocks (2..4)
+    constexpr int kWarps = kDaProducers / 32;
+    constexpr int kItems = 8;               // samples per warp and stage (32 samples * IPS / 16 warps, IPS <= 4)
+    // every warp owns ONE 128-row block `sub` and a strided subset of the stage's 32 samples, so all
+    // per-lane addressing is loop invariant
+    const int sub = warp % IPS;
+    const int cnt = (kWarps - sub + IPS - 1) / IPS;  // warps sharing this block
+    const int j0 = warp / IPS;                       // this warp's rank among them: samples j0, j0+cnt, ...
+    const bool isA = sub < ntile;
+    bool lane_on = true;
+    int sidx = 0, src_off;
+    uint32_t dst_base;
+    if (isA) {
+      const int m = m0 + sub * 128 + 4 * lane;
+      sidx = m / chi;
+      src_off = m - sidx * chi;
+      dst_base = (uint32_t)(sub * 16 + (lane >> 1)) * kDaSBO + (uint32_t)(lane & 1) * 8;
+    } else {
+      const int n = (sub - ntile) * 128 + 4 * lane;
+      lane_on = n < chi;
+      src_off = lane_on ? n : 0;
+      dst_base = 2 * kDaPlane + (uint32_t)(n >> 3) * kDaSBO + (uint32_t)(lane & 1) * 8;
+    }
+    const float *src_base = (isA ? U : V) + src_off;
+    const float *wq_row = A.wq + ((size_t)site * D + sidx) * M.B;
     const float qs = ldexpf(1.f, kTcKA - qmax);
     const float ka = 16384.f;
-    constexpr int kItems = 8;               // warp-items per warp and stage: 128 / 16 warps
-    constexpr int kWarps = kDaProducers / 32;
-    // per-item constants (independent of the sample chunk)
-    int k_of[kItems], src_off[kItems], s_of[kItems];
-    uint32_t dst_off[kItems];
-#pragma unroll
-    for (int i = 0; i < kItems; ++i) {
-      const int it = warp + i * kWarps;
-      k_of[i] = -1; src_off[i] = 0; s_of[i] = -1; dst_off[i] = 0;
-      if (it < nitems) {
-        const int k = it / IPS, sub = it - k * IPS;
-        if (sub < ntile) {  // A operand: rows m0 + 128*sub + 4*lane .. +3
-          const int m = m0 + sub * 128 + 4 * lane, sidx = m / chi;
-          k_of[i] = k; s_of[i] = sidx; src_off[i] = m - sidx * chi;
-          dst_off[i] = (uint32_t)(sub * 16 + (lane >> 1)) * kDaSBO + (uint32_t)(k >> 3) * 128 + (uint32_t)(k & 7) * 16 +
-                       (uint32_t)(lane & 1) * 8;
-        } else {            // B operand: columns 128*(sub - ntile) + 4*lane .. +3
-          const int n = (sub - ntile) * 128 + 4 * lane;
-          if (n < chi) {
-            k_of[i] = k; src_off[i] = n;
-            dst_off[i] = 2 * kDaPlane + (uint32_t)(n >> 3) * kDaSBO + (uint32_t)(k >> 3) * 128 + (uint32_t)(k & 7) * 16 +
-                         (uint32_t)(lane & 1) * 8;
-          }
-        }
-      }
-    }
-    const float *wq_site = A.wq + (size_t)site * D * M.B;
-    // issue every global load of one stage (read-only path); two stages are kept in flight
-    auto issue = [&](int ch, float4(&r)[kItems], float(&sc)[kItems]) {
-      const long long bbase = kbeg + (long long)ch * kDaKC;
-#pragma unroll
-      for (int i = 0; i < kItems; ++i) {
-        sc[i] = 0.f;
-        if (k_of[i] >= 0) {
-          const long long b = bbase + k_of[i];
-          const bool ok = b < kend;
-          const float *src = (s_of[i] >= 0 ? U : V) + (size_t)(ok ? b : kbeg) * chi + src_off[i];
-          r[i] = __ldg(reinterpret_cast<const float4 *>(src));
-          if (ok) sc[i] = s_of[i] >= 0 ? __ldg(wq_site + (size_t)s_of[i] * M.B + b) * qs : ka;
-        }
-      }
-    };
-    auto convert = [&](uint8_t *st, const float4(&r)[kItems], const float(&sc)[kItems]) {
-#pragma unroll
-      for (int i = 0; i < kItems; ++i) {
-        if (k_of[i] >= 0) {
-          const float f = sc[i];
-          const float w0 = r[i].x * f, w1 = r[i].y * f, w2 = r[i].z * f, w3 = r[i].w * f;
-          const __half h0 = __float2half_rn(w0), h1 = __float2half_rn(w1), h2 = __float2half_rn(w2), h3 = __float2half_rn(w3);
-          __half2 hi[2] = {__halves2half2(h0, h1), __halves2half2(h2, h3)};
-          __half2 lo[2] = {__floats2half2_rn(w0 - __half2float(h0), w1 - __half2float(h1)),
-                           __floats2half2_rn(w2 - __half2float(h2), w3 - __half2float(h3))};
-          *reinterpret_cast<uint2 *>(st + dst_off[i]) = *reinterpret_cast<uint2 *>(hi);
-          *reinterpret_cast<uint2 *>(st + dst_off[i] + kDaPlane) = *reinterpret_cast<uint2 *>(lo);
-        }
-      }
-    };
+
+#define TNB_DA_ISSUE(CH, R, SC)                                                                      \
+  {                                                                                                   \
+    const long long bbase_ = kbeg + (long long)(CH)*kDaKC;                                            \
+    _Pragma("unroll") for (int i = 0; i < kItems; ++i) {                                              \
+      const int k_ = j0 + i * cnt;                                                                    \
+      SC[i] = 0.f;                                                                                    \
+      R[i] = make_float4(0.f, 0.f, 0.f, 0.f);                                                         \
+      if (k_ < kDaKC && lane_on) {                                                                    \
+        const long long b_ = bbase_ + k_;                                                             \
+        if (b_ < kend) {                                                                              \
+          R[i] = __ldg(reinterpret_cast<const float4 *>(src_base + (size_t)b_ * chi));                \
+          SC[i] = isA ? __ldg(wq_row + b_) * qs : ka;                                                 \
+        }                                                                                             \
+      }                                                                                               \
+    }                                                                                                 \
+  }
+#define TNB_DA_CONVERT(ST, R, SC)                                                                     \
+  {                                                                                                   \
+    _Pragma("unroll") for (int i = 0; i < kItems; ++i) {                                              \
+      const int k_ = j0 + i * cnt;                                                                    \
+      if (k_ < kDaKC && lane_on) {                                                                    \
+        const float f_ = SC[i];                                                                       \
+        const float w0 = R[i].x * f_, w1 = R[i].y * f_, w2 = R[i].z * f_, w3 = R[i].w * f_;           \
+        const __half2 hA = __floats2half2_rn(w0, w1), hB = __floats2half2_rn(w2, w3);                 \
+        const float2 fA = __half22float2(hA), fB = __half22float2(hB);                                \
+        const __half2 lA = __floats2half2_rn(w0 - fA.x, w1 - fA.y), lB = __floats2half2_rn(w2 - fB.x, w3 - fB.y); \
+        uint8_t *d_ = (ST) + dst_base + (uint32_t)(k_ >> 3) * 128 + (uint32_t)(k_ & 7) * 16;           \
+        uint2 hv, lv;                                                                                 \
+        hv.x = *reinterpret_cast<const uint32_t *>(&hA); hv.y = *reinterpret_cast<const uint32_t *>(&hB); \
+        lv.x = *reinterpret_cast<const uint32_t *>(&lA); lv.y = *reinterpret_cast<const uint32_t *>(&lB); \
+        *reinterpret_cast<uint2 *>(d_) = hv;                                                          \
+        *reinterpret_cast<uint2 *>(d_ + kDaPlane) = lv;                                               \
+      }                                                                                               \
+    }                                                                                                 \
+  }
     float4 ra[kItems], rb[kItems];
     float sa[kItems], sb[kItems];
     int stage = 0;
     uint32_t phase = 0;
-    issue(0, ra, sa);
+    TNB_DA_ISSUE(0, ra, sa)
     for (int ch = 0; ch < nchunks; ch += 2) {
-      if (ch + 1 < nchunks) issue(ch + 1, rb, sb);
+      if (ch + 1 < nchunks) TNB_DA_ISSUE(ch + 1, rb, sb)
       ptx::mbar_wait(&empty[stage], phase ^ 1);
-      convert(stages + (size_t)stage * kDaStage, ra, sa);
+      TNB_DA_CONVERT(stages + (size_t)stage * kDaStage, ra, sa)
       ptx::fence_proxy_async();
       ptx::mbar_arrive(&full[stage]);
       if (++stage == A.nstage) { stage = 0; phase ^= 1; }
       if (ch + 1 < nchunks) {
-        if (ch + 2 < nchunks) issue(ch + 2, ra, sa);
+        if (ch + 2 < nchunks) TNB_DA_ISSUE(ch + 2, ra, sa)
         ptx::mbar_wait(&empty[stage], phase ^ 1);
-        convert(stages + (size_t)stage * kDaStage, rb, sb);
+        TNB_DA_CONVERT(stages + (size_t)stage * kDaStage, rb, sb)
         ptx::fence_proxy_async();
         ptx::mbar_arrive(&full[stage]);
         if (++stage == A.nstage) { stage = 0; phase ^= 1; }
       }
     }
+#undef TNB_DA_ISSUE
+#undef TNB_DA_CONVERT
     // ===== epilogue (warps 0-3): TMEM -> packed gradient =====
     if (warp < 4) {
       ptx::mbar_wait(done, 0);
