@@ -541,32 +541,30 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
       dst_base = 2 * kDaPlane + (uint32_t)(n >> 3) * kDaSBO + (uint32_t)(lane & 1) * 8;
     }
     const float *src_base = (isA ? U : V) + src_off;
-    const float *wq_row = A.wq + ((size_t)site * D + sidx) * M.B;
+    const float *wq_row = A.wq + ((size_t)site * D + sidx) * M.B;  // (B blocks read it too, unused)
     const float qs = ldexpf(1.f, kTcKA - qmax);
     const float ka = 16384.f;
 
+    // Issue phase: loads only (no instruction may consume a loaded value here, or the in-order
+    // warp would stall on the first one and serialise the rest).  Out-of-range samples are
+    // clamped to a valid row and zeroed by their weight in the convert phase.
 #define TNB_DA_ISSUE(CH, R, SC)                                                                      \
   {                                                                                                   \
     const long long bbase_ = kbeg + (long long)(CH)*kDaKC;                                            \
     _Pragma("unroll") for (int i = 0; i < kItems; ++i) {                                              \
-      const int k_ = j0 + i * cnt;                                                                    \
-      SC[i] = 0.f;                                                                                    \
-      R[i] = make_float4(0.f, 0.f, 0.f, 0.f);                                                         \
-      if (k_ < kDaKC && lane_on) {                                                                    \
-        const long long b_ = bbase_ + k_;                                                             \
-        if (b_ < kend) {                                                                              \
-          R[i] = __ldg(reinterpret_cast<const float4 *>(src_base + (size_t)b_ * chi));                \
-          SC[i] = isA ? __ldg(wq_row + b_) * qs : ka;                                                 \
-        }                                                                                             \
-      }                                                                                               \
+      const int k_ = min(j0 + i * cnt, kDaKC - 1);                                                    \
+      const long long b_ = min(bbase_ + k_, kend - 1);                                                \
+      R[i] = __ldg(reinterpret_cast<const float4 *>(src_base + (size_t)b_ * chi));                    \
+      SC[i] = __ldg(wq_row + b_);                                                                     \
     }                                                                                                 \
   }
-#define TNB_DA_CONVERT(ST, R, SC)                                                                     \
+#define TNB_DA_CONVERT(CH, ST, R, SC)                                                                 \
   {                                                                                                   \
+    const long long bbase_ = kbeg + (long long)(CH)*kDaKC;                                            \
     _Pragma("unroll") for (int i = 0; i < kItems; ++i) {                                              \
       const int k_ = j0 + i * cnt;                                                                    \
       if (k_ < kDaKC && lane_on) {                                                                    \
-        const float f_ = SC[i];                                                                       \
+        const float f_ = (bbase_ + k_ < kend) ? (isA ? SC[i] * qs : ka) : 0.f;                        \
         const float w0 = R[i].x * f_, w1 = R[i].y * f_, w2 = R[i].z * f_, w3 = R[i].w * f_;           \
         const __half2 hA = __floats2half2_rn(w0, w1), hB = __floats2half2_rn(w2, w3);                 \
         const float2 fA = __half22float2(hA), fB = __half22float2(hB);                                \
@@ -588,14 +586,14 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
     for (int ch = 0; ch < nchunks; ch += 2) {
       if (ch + 1 < nchunks) TNB_DA_ISSUE(ch + 1, rb, sb)
       ptx::mbar_wait(&empty[stage], phase ^ 1);
-      TNB_DA_CONVERT(stages + (size_t)stage * kDaStage, ra, sa)
+      TNB_DA_CONVERT(ch, stages + (size_t)stage * kDaStage, ra, sa)
       ptx::fence_proxy_async();
       ptx::mbar_arrive(&full[stage]);
       if (++stage == A.nstage) { stage = 0; phase ^= 1; }
       if (ch + 1 < nchunks) {
         if (ch + 2 < nchunks) TNB_DA_ISSUE(ch + 2, ra, sa)
         ptx::mbar_wait(&empty[stage], phase ^ 1);
-        TNB_DA_CONVERT(stages + (size_t)stage * kDaStage, rb, sb)
+        TNB_DA_CONVERT(ch + 1, stages + (size_t)stage * kDaStage, rb, sb)
         ptx::fence_proxy_async();
         ptx::mbar_arrive(&full[stage]);
         if (++stage == A.nstage) { stage = 0; phase ^= 1; }
