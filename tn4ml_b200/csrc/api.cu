@@ -112,7 +112,7 @@ struct MpsPlan {
   // tensor-core sweep (f32, TNB_PREC_TENSOR)
   int tc, tc_N, tc_NH, tc_NMMA, tc_nstage, tc_cols;
   uint32_t tc_stage_bytes;
-  size_t tc_site_img, off_img_n, off_img_t, off_kW, off_wq, off_qmax, tc_smem;
+  size_t tc_site_img, off_img_n, off_img_t, off_kW, off_wq, off_qmax, off_wqc, tc_smem;
 };
 
 // The tcgen05 sweep covers: float32, chi a multiple of 16 in [32, 256], D*chi <= 512 TMEM columns.
@@ -183,7 +183,8 @@ static MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
     P.off_kW = take((size_t)P.nslab * sizeof(int));
     if (need_grad) {
       P.off_wq = take((size_t)p->L * p->d * B * sizeof(float));
-      P.off_qmax = take((size_t)p->L * sizeof(int));
+      P.off_qmax = take(((size_t)p->L + 1) * sizeof(int));  // [L] chain sites + [1] class site
+      P.off_wqc = take((size_t)p->d * p->n_out * B * sizeof(float));
     }
   }
   P.total = o;
@@ -219,6 +220,8 @@ static void fill_tc_args(const MpsPlan &P, void *ws, const MpsArgs<float> &M, Tc
   T.kW = (const int *)(w + P.off_kW);
   T.wq = (float *)(w + P.off_wq);
   T.qmax = (int *)(w + P.off_qmax);
+  T.wqc = (float *)(w + P.off_wqc);
+  T.qmaxc = T.qmax + M.L;
   T.N = P.tc_N; T.NH = P.tc_NH; T.NMMA = P.tc_NMMA; T.nstage = P.tc_nstage; T.tmem_cols = P.tc_cols;
   T.stage_bytes = P.tc_stage_bytes; T.site_img_bytes = P.tc_site_img;
 }
@@ -227,7 +230,7 @@ template <int D> static cudaError_t tc_set_attr() {
   static std::once_flag once;
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [] {
-    err = cudaFuncSetAttribute(tc_sweep_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    err = cudaFuncSetAttribute(tc_chain_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   });
   return err;
 }
@@ -235,12 +238,12 @@ template <int D> static cudaError_t tc_set_attr() {
 // launch the tcgen05 sweep (forward environments or adjoint chains)
 static int tc_launch_sweep(const tnb_problem *p, const MpsPlan &P, const TcArgs &T, long long B, int adjoint,
                            cudaStream_t st) {
-  dim3 grid((unsigned)((B + kTcRows - 1) / kTcRows), 2);
+  dim3 grid((unsigned)((B + kTcRows - 1) / kTcRows), adjoint ? 2 : 1);
   cudaError_t e = cudaSuccess;
 #define TNB_TC_CASE(DD)                                                                     \
   case DD:                                                                                   \
     e = tc_set_attr<DD>();                                                                   \
-    if (e == cudaSuccess) tc_sweep_kernel<DD><<<grid, kTcThreads, P.tc_smem, st>>>(T, adjoint); \
+    if (e == cudaSuccess) tc_chain_kernel<DD><<<grid, kTcThreads, P.tc_smem, st>>>(T, adjoint); \
     break;
   prof_begin(st);
   switch (p->d) {
@@ -248,8 +251,8 @@ static int tc_launch_sweep(const tnb_problem *p, const MpsPlan &P, const TcArgs 
     default: return fail("tensor path: unsupported physical dimension %d", p->d);
   }
 #undef TNB_TC_CASE
-  if (e != cudaSuccess) return fail("cudaFuncSetAttribute(tc_sweep): %s", cudaGetErrorString(e));
-  TNB_LAUNCH_CHECK(adjoint ? "tc_sweep_kernel(adj)" : "tc_sweep_kernel(fwd)");
+  if (e != cudaSuccess) return fail("cudaFuncSetAttribute(tc_chain): %s", cudaGetErrorString(e));
+  TNB_LAUNCH_CHECK(adjoint ? "tc_chain_kernel(adj)" : "tc_chain_kernel(fwd)");
   return 0;
 }
 
@@ -277,16 +280,9 @@ static int mps_forward_t(const tnb_problem *p, const MpsPlan &P, long long B, co
   fill_mps_args<T>(p, P, B, x, targets, ws, A);
   A.stash = keep_stash ? 1 : 0;
   A.loss = (T *)loss; A.loss_sum = loss_sum; A.out = (T *)out; A.out_exp = out_exp;
-  size_t welems = (size_t)P.chip * p->d * P.chip * P.nslab;
-  int pblocks = (int)((welems + 255) / 256);
-  if (pblocks > 148 * 16) pblocks = 148 * 16;
-  prof_begin(st);
-  mps_prep_kernel<T><<<pblocks, 256, 0, st>>>((const T *)params, (T *)A.Wn, (T *)A.Wt, p->L, p->chi, P.chip, p->d,
-                                              p->n_out, p->out_site);
-  TNB_LAUNCH_CHECK("mps_prep_kernel");
-  int tiles = (int)((B + P.BT - 1) / P.BT);
   if constexpr (std::is_same<T, float>::value) {
     if (P.tc) {
+      // tensor path: weight images, then ONE kernel for both chains, the class site and the head
       TcArgs Tc;
       fill_tc_args(P, ws, A, Tc);
       prof_begin(st);
@@ -300,14 +296,20 @@ static int mps_forward_t(const tnb_problem *p, const MpsPlan &P, long long B, co
       tc_image_kernel<<<ib, 256, 0, st>>>((const float *)params, Tc.kW, (uint8_t *)Tc.img_n, (uint8_t *)Tc.img_t, p->L,
                                           p->chi, p->d, p->n_out, p->out_site);
       TNB_LAUNCH_CHECK("tc_image_kernel");
-      if (tc_launch_sweep(p, P, Tc, B, 0, st)) return 1;
+      return tc_launch_sweep(p, P, Tc, B, 0, st);
     }
   }
-  if (!P.tc) {
-    prof_begin(st);
-    mps_sweep_kernel<T, NG><<<dim3(tiles, 2), P.NT, P.smem_sweep, st>>>(A, 0);
-    TNB_LAUNCH_CHECK("mps_sweep_kernel(fwd)");
-  }
+  size_t welems = (size_t)P.chip * p->d * P.chip * P.nslab;
+  int pblocks = (int)((welems + 255) / 256);
+  if (pblocks > 148 * 16) pblocks = 148 * 16;
+  prof_begin(st);
+  mps_prep_kernel<T><<<pblocks, 256, 0, st>>>((const T *)params, (T *)A.Wn, (T *)A.Wt, p->L, p->chi, P.chip, p->d,
+                                              p->n_out, p->out_site);
+  TNB_LAUNCH_CHECK("mps_prep_kernel");
+  int tiles = (int)((B + P.BT - 1) / P.BT);
+  prof_begin(st);
+  mps_sweep_kernel<T, NG><<<dim3(tiles, 2), P.NT, P.smem_sweep, st>>>(A, 0);
+  TNB_LAUNCH_CHECK("mps_sweep_kernel(fwd)");
   prof_begin(st);
   mps_class_kernel<T, NG><<<tiles, P.NT, P.smem_class, st>>>(A);
   TNB_LAUNCH_CHECK("mps_class_kernel");
@@ -323,17 +325,12 @@ static int mps_backward_t(const tnb_problem *p, const MpsPlan &P, long long B, c
   A.stash = 1;
   A.loss_scale = (T)loss_scale;
   if (!accumulate) TNB_CUDA(cudaMemsetAsync(grads, 0, (size_t)tnb_param_count(p) * sizeof(T), st));
-  int tiles = (int)((B + P.BT - 1) / P.BT);
-  A.seed_only = P.tc ? 1 : 0;
-  prof_begin(st);
-  mps_sweep_kernel<T, NG><<<dim3(tiles, 2), P.NT, P.smem_sweep, st>>>(A, 1);
-  TNB_LAUNCH_CHECK(P.tc ? "mps_sweep_kernel(seed)" : "mps_sweep_kernel(adj)");
   if constexpr (std::is_same<T, float>::value) {
     if (P.tc) {
       TcArgs Tc;
       fill_tc_args(P, ws, A, Tc);
-      TNB_CUDA(cudaMemsetAsync(Tc.qmax, 0x80, (size_t)p->L * sizeof(int), st));
-      if (tc_launch_sweep(p, P, Tc, B, 1, st)) return 1;
+      TNB_CUDA(cudaMemsetAsync(Tc.qmax, 0x80, ((size_t)p->L + 1) * sizeof(int), st));
+      if (tc_launch_sweep(p, P, Tc, B, 1, st)) return 1;  // seeds through the class site + adjoint chains
       static std::once_flag once;
       static cudaError_t aerr = cudaSuccess;
       std::call_once(once, [] {
@@ -342,26 +339,36 @@ static int mps_backward_t(const tnb_problem *p, const MpsPlan &P, long long B, c
       if (aerr != cudaSuccess) return fail("cudaFuncSetAttribute(tc_da): %s", cudaGetErrorString(aerr));
       TcDaArgs Da;
       Da.M = A;
-      Da.wq = Tc.wq;
-      Da.qmax = Tc.qmax;
       Da.grads = (float *)grads;
-      Da.mgroups = (P.tc_N + 255) / 256;
       Da.nstage = 3;
       Da.tmem_cols = 32;
       while (Da.tmem_cols < 2 * p->chi) Da.tmem_cols <<= 1;
-      long long ctas = (long long)p->L * Da.mgroups;
-      long long nsp = (148LL * 4 + ctas - 1) / ctas;
-      long long maxsp = (B + 2047) / 2048;
-      if (nsp > maxsp) nsp = maxsp;
-      if (nsp < 1) nsp = 1;
-      Da.nsplit = (int)nsp;
-      Da.bchunk = ((B + nsp - 1) / nsp + kDaKC - 1) / kDaKC * kDaKC;
-      dim3 gda((unsigned)(Da.mgroups * Da.nsplit), (unsigned)p->L);
-      prof_begin(st);
-      tc_da_kernel<<<gda, kDaThreads, (size_t)Da.nstage * kDaStage + 1024, st>>>(Da);
-      TNB_LAUNCH_CHECK("tc_da_kernel");
+      const long long maxsp = (B + 2047) / 2048;
+      for (int pass = 0; pass < 2; ++pass) {
+        // pass 0: every chain site (rows (s, a));  pass 1: the class site (rows ((s, k), a))
+        Da.Dv = pass == 0 ? p->d : p->d * p->n_out;
+        Da.only_site = pass == 0 ? -1 : p->out_site;
+        Da.wq = pass == 0 ? Tc.wq : Tc.wqc;
+        Da.qmax = pass == 0 ? Tc.qmax : Tc.qmaxc;
+        Da.mgroups = (Da.Dv * p->chi + 255) / 256;
+        long long ctas = (long long)(pass == 0 ? p->L : 1) * Da.mgroups;
+        long long nsp = (148LL * 4 + ctas - 1) / ctas;
+        if (nsp > maxsp) nsp = maxsp;
+        if (nsp < 1) nsp = 1;
+        Da.nsplit = (int)nsp;
+        Da.bchunk = ((B + nsp - 1) / nsp + kDaKC - 1) / kDaKC * kDaKC;
+        dim3 gda((unsigned)(Da.mgroups * Da.nsplit), (unsigned)(pass == 0 ? p->L : 1));
+        prof_begin(st);
+        tc_da_kernel<<<gda, kDaThreads, (size_t)Da.nstage * kDaStage + 1024, st>>>(Da);
+        TNB_LAUNCH_CHECK(pass == 0 ? "tc_da_kernel" : "tc_da_kernel(class)");
+      }
+      return 0;
     }
   }
+  int tiles = (int)((B + P.BT - 1) / P.BT);
+  prof_begin(st);
+  mps_sweep_kernel<T, NG><<<dim3(tiles, 2), P.NT, P.smem_sweep, st>>>(A, 1);
+  TNB_LAUNCH_CHECK("mps_sweep_kernel(adj)");
   DaArgs<T> Dg;
   Dg.M = A;
   Dg.grads = (T *)grads;
@@ -376,12 +383,10 @@ static int mps_backward_t(const tnb_problem *p, const MpsPlan &P, long long B, c
   Dg.bchunk = (B + ns - 1) / ns;
   Dg.bchunk = (Dg.bchunk + 15) / 16 * 16;
   Dg.only_site = -1;
-  if (!P.tc) {
-    dim3 grid(Dg.tiles_a * Dg.tiles_r * Dg.nsplit, p->L, p->d);
-    prof_begin(st);
-    mps_da_kernel<T><<<grid, 256, 0, st>>>(Dg);
-    TNB_LAUNCH_CHECK("mps_da_kernel");
-  }
+  dim3 grid(Dg.tiles_a * Dg.tiles_r * Dg.nsplit, p->L, p->d);
+  prof_begin(st);
+  mps_da_kernel<T><<<grid, 256, 0, st>>>(Dg);
+  TNB_LAUNCH_CHECK("mps_da_kernel");
   // class site: one GEMM per (s, class)
   Dg.only_site = p->out_site;
   work = (long long)Dg.tiles_a * Dg.tiles_r * p->d * p->n_out;

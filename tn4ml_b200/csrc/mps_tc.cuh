@@ -38,6 +38,8 @@ struct TcArgs {
   const int *kW;         // per-slab weight pre-scale exponent
   float *wq;             // adjoint: phi_s[b] * 2^q[b] per (site, s, b): per-sample weight of the dA GEMM
   int *qmax;             // adjoint: max_b q[site][b]
+  float *wqc;            // adjoint: phi_s[b] * dLoss/dy'_k[b] per ((s,k), b): weights of the class-site dA GEMM
+  int *qmaxc;            // adjoint: max exponent of wqc
   int N, NH, NMMA, nstage, tmem_cols;
   uint32_t stage_bytes;
   size_t site_img_bytes;
@@ -48,14 +50,15 @@ struct TcArgs {
 __global__ void tc_sitemax_kernel(const float *__restrict__ params, int *__restrict__ kW, int L, int chi, int D, int C,
                                   int c) {
   const int slab = blockIdx.x;
-  int site, o, nj;
-  if (slab < c) { site = slab; o = 0; nj = 1; }
-  else if (slab < c + C) { site = c; o = slab - c; nj = C; }
-  else { site = slab - C + 1; o = 0; nj = 1; }
+  int site, nj;
+  if (slab < c) { site = slab; nj = 1; }
+  else if (slab < c + C) { site = c; nj = C; }
+  else { site = slab - C + 1; nj = 1; }
   const size_t site_off = (size_t)site * chi * chi * D + (site > c ? (size_t)chi * chi * D * (C - 1) : 0);
   float m = 0.f;
-  const int n = chi * chi * D;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(params[site_off + (size_t)i * nj + o]));
+  // class slabs share one scale: the seed phase accumulates all of them into one TMEM tile
+  const int n = chi * chi * D * nj;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(params[site_off + i]));
   __shared__ float red[32];
   for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
@@ -124,299 +127,9 @@ __device__ __forceinline__ void split8(const float *w, uint4 &hi, uint4 &lo) {
   lo = *reinterpret_cast<uint4 *>(l);
 }
 
-template <int D>
-__global__ void __launch_bounds__(kTcThreads, 1) tc_sweep_kernel(TcArgs A, int adjoint) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const MpsArgs<float> &M = A.M;
-  const int chi = M.chip, L = M.L, c = M.c;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int half = blockIdx.y;
-  const long long b0 = (long long)blockIdx.x * kTcRows;
-
-  int site0, nsites, dir;
-  bool transposed;
-  if (!adjoint) {
-    if (half == 0) { site0 = 0; nsites = c; dir = 1; transposed = false; }
-    else { site0 = L - 1; nsites = L - 1 - c; dir = -1; transposed = true; }
-  } else {
-    if (half == 0) { if (c == 0) return; site0 = c - 1; nsites = c - 1; dir = -1; transposed = true; }
-    else { if (c == L - 1) return; site0 = c + 1; nsites = L - 2 - c; dir = 1; transposed = false; }
-  }
-  if (nsites <= 0 && adjoint) {
-    // the half is a single boundary site: normalise the seed in place and record its dA weights
-    const int bond = half == 0 ? c : c + 1, jb = half == 0 ? 0 : L - 1;
-    for (int r = tid; r < kTcRows; r += blockDim.x) {
-      const long long b = b0 + r;
-      if (b >= M.B) continue;
-      float *seed = M.G + (size_t)bond * M.B * chi + (size_t)b * chi;
-      float m = 0.f;
-      for (int n = 0; n < chi; ++n) m = fmaxf(m, fabsf(seed[n]));
-      int e = 0;
-      if (m > 0.f) frexpf(m, &e);
-      const float sc = ldexpf(1.f, -e);
-      for (int n = 0; n < chi; ++n) seed[n] *= sc;
-      const int q = e - M.exps[(size_t)jb * M.B + b];
-      float ph[kMaxPhys];
-      embed_site(M.emb, M.x[(size_t)b * L + jb], ph);
-      for (int s = 0; s < D; ++s) A.wq[((size_t)jb * D + s) * M.B + b] = ph[s] * ldexpf(1.f, q);
-      atomicMax(&A.qmax[jb], q);
-    }
-    return;
-  }
-  if (nsites <= 0) {
-    if (!adjoint) {  // boundary vector only (class site sits on the boundary)
-      float *env = mps_fenv(M, half == 0 ? 0 : L);
-      for (int i = tid; i < kTcRows * chi; i += blockDim.x) {
-        int r = i / chi, n = i - r * chi;
-        long long b = b0 + r;
-        if (env && b < M.B) env[(size_t)b * chi + n] = n == 0 ? 1.f : 0.f;
-      }
-      for (int r = tid; r < kTcRows; r += blockDim.x)
-        if (b0 + r < M.B) M.esum[(size_t)half * M.B + b0 + r] = 0;
-    }
-    return;
-  }
-
-  const uint32_t a_plane = (uint32_t)kTcRows * chi * 2;
-  uint8_t *a_hi = smem;
-  uint8_t *a_lo = smem + a_plane;
-  uint8_t *stages = smem + 2 * a_plane;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(stages + (size_t)A.nstage * A.stage_bytes);
-  uint64_t *full = bars, *empty = bars + A.nstage, *acc_full = bars + 2 * A.nstage, *a_ready = acc_full + 1;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_ready + 1);
-
-  if (tid == 0) {
-    for (int i = 0; i < A.nstage; ++i) {
-      ptx::mbar_init(&full[i], 1);
-      ptx::mbar_init(&empty[i], 1);
-    }
-    ptx::mbar_init(acc_full, 1);
-    ptx::mbar_init(a_ready, kTcRows);
-    ptx::fence_mbar_init();
-  }
-  if (warp == 5) {
-    ptx::tmem_alloc(tmem_slot, (uint32_t)A.tmem_cols);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int KS = chi / 16;
-
-  if (warp == 4) {
-    // ===== producer: one bulk async copy per pipeline stage =====
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int step = 0; step < nsites; ++step) {
-        const int site = site0 + step * dir;
-        const uint8_t *img = (transposed ? A.img_t : A.img_n) + (size_t)mps_slab(M, site) * A.site_img_bytes;
-        for (int ks = 0; ks < KS; ++ks) {
-          ptx::mbar_wait(&empty[stage], phase ^ 1);
-          ptx::mbar_expect_tx(&full[stage], A.stage_bytes);
-          ptx::bulk_g2s(stages + (size_t)stage * A.stage_bytes, img + (size_t)ks * A.stage_bytes, A.stage_bytes,
-                        &full[stage]);
-          if (++stage == A.nstage) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 5) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc = ptx::idesc_f16_f32(kTcRows, A.NMMA);
-      const uint32_t a_hi_s = ptx::smem_u32(a_hi), a_lo_s = ptx::smem_u32(a_lo);
-      const uint32_t sbo_a = (uint32_t)chi * 16;
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int step = 0; step < nsites; ++step) {
-        ptx::mbar_wait(a_ready, step & 1);
-        ptx::tc_fence_after();
-        for (int ks = 0; ks < KS; ++ks) {
-          ptx::mbar_wait(&full[stage], phase);
-          ptx::tc_fence_after();
-          const uint64_t da_hi = ptx::smem_desc_kmajor(a_hi_s + ks * 256, 128, sbo_a);
-          const uint64_t da_lo = ptx::smem_desc_kmajor(a_lo_s + ks * 256, 128, sbo_a);
-          const uint32_t st = ptx::smem_u32(stages + (size_t)stage * A.stage_bytes);
-          for (int h = 0; h < A.NH; ++h) {
-            const uint32_t boff = (uint32_t)h * (A.NMMA / 8) * 256;
-            const uint64_t db_hi = ptx::smem_desc_kmajor(st + boff, 128, 256);
-            const uint64_t db_lo = ptx::smem_desc_kmajor(st + (uint32_t)A.N * 32 + boff, 128, 256);
-            const uint32_t d = tmem_base + (uint32_t)h * A.NMMA;
-            ptx::mma_f16(d, da_hi, db_hi, idesc, ks > 0 ? 1u : 0u);
-            ptx::mma_f16(d, da_lo, db_hi, idesc, 1u);
-            ptx::mma_f16(d, da_hi, db_lo, idesc, 1u);
-          }
-          ptx::mma_commit(&empty[stage]);  // stage smem reusable once these MMAs retire
-          if (++stage == A.nstage) { stage = 0; phase ^= 1; }
-        }
-        ptx::mma_commit(acc_full);
-      }
-    }
-  } else {
-    // ===== epilogue: thread == sample row == TMEM lane =====
-    const int row = tid;
-    const long long b = b0 + row;
-    const bool valid = b < M.B;
-    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const uint32_t row_off = (uint32_t)(row >> 3) * (uint32_t)chi * 16 + (uint32_t)(row & 7) * 16;
-    int esum = 0;   // forward: sum of delta ; adjoint: running exponent h of G = v * 2^h
-    // --- initial A operand ---
-    if (!adjoint) {
-      float *env = mps_fenv(M, half == 0 ? 0 : L);
-      for (int kc = 0; kc < chi / 8; ++kc) {
-        uint4 z = make_uint4(0, 0, 0, 0), zh = z;
-        if (kc == 0) zh.x = 0x00007400u;  // fp16(2^14) in element 0
-        *reinterpret_cast<uint4 *>(a_hi + row_off + kc * 128) = zh;
-        *reinterpret_cast<uint4 *>(a_lo + row_off + kc * 128) = z;
-        if (env && valid) {
-          float4 e0 = make_float4(kc == 0 ? 1.f : 0.f, 0.f, 0.f, 0.f), z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          *reinterpret_cast<float4 *>(env + (size_t)b * chi + kc * 8) = e0;
-          *reinterpret_cast<float4 *>(env + (size_t)b * chi + kc * 8 + 4) = z4;
-        }
-      }
-    } else {
-      const float *seed = M.G + (size_t)(half == 0 ? c : c + 1) * M.B * chi + (size_t)(valid ? b : 0) * chi;
-      float m = 0.f;
-      for (int n = 0; n < chi; n += 4) {
-        float4 v = *reinterpret_cast<const float4 *>(seed + n);
-        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
-      }
-      if (!valid) m = 0.f;
-      int e = 0;
-      if (m > 0.f) frexpf(m, &e);
-      esum = e;
-      const float sc = valid ? ldexpf(1.f, kTcKA - e) : 0.f;
-      const float nrm = ldexpf(1.f, -e);
-      float *seed_w = M.G + (size_t)(half == 0 ? c : c + 1) * M.B * chi + (size_t)(valid ? b : 0) * chi;
-      for (int kc = 0; kc < chi / 8; ++kc) {
-        float w[8];
-        float4 v0 = *reinterpret_cast<const float4 *>(seed + kc * 8), v1 = *reinterpret_cast<const float4 *>(seed + kc * 8 + 4);
-        if (valid) {  // the stash keeps the normalised adjoint; its scale lives in q
-          *reinterpret_cast<float4 *>(seed_w + kc * 8) = make_float4(v0.x * nrm, v0.y * nrm, v0.z * nrm, v0.w * nrm);
-          *reinterpret_cast<float4 *>(seed_w + kc * 8 + 4) = make_float4(v1.x * nrm, v1.y * nrm, v1.z * nrm, v1.w * nrm);
-        }
-        w[0] = v0.x * sc; w[1] = v0.y * sc; w[2] = v0.z * sc; w[3] = v0.w * sc;
-        w[4] = v1.x * sc; w[5] = v1.y * sc; w[6] = v1.z * sc; w[7] = v1.w * sc;
-        uint4 hi, lo;
-        split8(w, hi, lo);
-        *reinterpret_cast<uint4 *>(a_hi + row_off + kc * 128) = hi;
-        *reinterpret_cast<uint4 *>(a_lo + row_off + kc * 128) = lo;
-      }
-    }
-    ptx::fence_proxy_async();
-    ptx::mbar_arrive(a_ready);
-
-    for (int step = 0; step < nsites; ++step) {
-      const int site = site0 + step * dir;
-      const int bond_out = transposed ? site : site + 1;
-      float ph[kMaxPhys];
-      embed_site(M.emb, valid ? M.x[(size_t)b * L + site] : 0.5f, ph);
-      const int dsite = (adjoint && valid) ? M.exps[(size_t)site * M.B + b] : 0;
-      const int kw = A.kW[mps_slab(M, site)];
-      ptx::mbar_wait(acc_full, step & 1);
-      ptx::tc_fence_after();
-      // pass 1: row maximum of the new environment
-      float m = 0.f;
-      for (int n0 = 0; n0 < chi; n0 += 16) {
-        float t[D][16];
-#pragma unroll
-        for (int s = 0; s < D; ++s) ptx::tmem_ld16(trow + (uint32_t)(s * chi + n0), t[s]);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float o = ph[0] * t[0][j];
-#pragma unroll
-          for (int s = 1; s < D; ++s) o = fmaf(ph[s], t[s][j], o);
-          m = fmaxf(m, fabsf(o));
-        }
-      }
-      int e = 0;
-      if (m > 0.f && valid) frexpf(m, &e);
-      const int dtrue = (m > 0.f && valid) ? e - kTcKA - kw : 0;  // exponent in units of the true recurrence
-      float out_scale;  // applied to the normalised value for the HBM stash
-      if (!adjoint) {
-        esum += dtrue;
-        if (valid && M.exps) M.exps[(size_t)site * M.B + b] = dtrue;
-        out_scale = 1.f;
-      } else {
-        // dA_site = sum_b 2^q (F x phi x G) with q = h_in - delta_site ; h_in is the exponent of the input adjoint
-        const int q = esum - dsite;
-        if (valid) {
-#pragma unroll
-          for (int s = 0; s < D; ++s) A.wq[((size_t)site * D + s) * M.B + b] = ph[s] * ldexpf(1.f, q);
-        }
-        int qm = valid ? q : INT_MIN;
-        for (int off = 16; off > 0; off >>= 1) qm = max(qm, __shfl_xor_sync(0xffffffffu, qm, off));
-        if (lane == 0 && qm != INT_MIN) atomicMax(&A.qmax[site], qm);
-        esum += dtrue - dsite;
-        out_scale = 1.f;
-      }
-      const float nsc = valid ? ldexpf(1.f, -e) : 0.f;
-      float *env = adjoint ? M.G + (size_t)bond_out * M.B * chi : mps_fenv(M, bond_out);
-      const bool last = step == nsites - 1;
-      // pass 2: normalise, stash, and write the next A operand (fp16 hi/lo)
-      for (int n0 = 0; n0 < chi; n0 += 16) {
-        float t[D][16];
-#pragma unroll
-        for (int s = 0; s < D; ++s) ptx::tmem_ld16(trow + (uint32_t)(s * chi + n0), t[s]);
-        ptx::tmem_ld_wait();
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float o = ph[0] * t[0][j];
-#pragma unroll
-          for (int s = 1; s < D; ++s) o = fmaf(ph[s], t[s][j], o);
-          v[j] = o * nsc;
-        }
-        if (env && valid) {
-          float *dst = env + (size_t)b * chi + n0;
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<float4 *>(dst + 4 * q) =
-                make_float4(v[4 * q] * out_scale, v[4 * q + 1] * out_scale, v[4 * q + 2] * out_scale, v[4 * q + 3] * out_scale);
-        }
-        if (!last) {
-          const float ka = 16384.f;  // 2^kTcKA
-          float w[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) w[j] = v[j] * ka;
-          uint4 hi, lo;
-          split8(w, hi, lo);
-          *reinterpret_cast<uint4 *>(a_hi + row_off + (n0 / 8) * 128) = hi;
-          *reinterpret_cast<uint4 *>(a_lo + row_off + (n0 / 8) * 128) = lo;
-          split8(w + 8, hi, lo);
-          *reinterpret_cast<uint4 *>(a_hi + row_off + (n0 / 8 + 1) * 128) = hi;
-          *reinterpret_cast<uint4 *>(a_lo + row_off + (n0 / 8 + 1) * 128) = lo;
-        }
-      }
-      ptx::tc_fence_before();
-      ptx::fence_proxy_async();
-      ptx::mbar_arrive(a_ready);
-    }
-    if (!adjoint && valid) M.esum[(size_t)half * M.B + b] = esum;
-    if (adjoint) {
-      const int jb = half == 0 ? 0 : L - 1;  // the boundary site: no chain step, but it has a gradient
-      int qm = INT_MIN;
-      if (valid) {
-        const int q = esum - M.exps[(size_t)jb * M.B + b];
-        float ph[kMaxPhys];
-        embed_site(M.emb, M.x[(size_t)b * L + jb], ph);
-#pragma unroll
-        for (int s = 0; s < D; ++s) A.wq[((size_t)jb * D + s) * M.B + b] = ph[s] * ldexpf(1.f, q);
-        qm = q;
-      }
-      for (int off = 16; off > 0; off >>= 1) qm = max(qm, __shfl_xor_sync(0xffffffffu, qm, off));
-      if (lane == 0 && qm != INT_MIN) atomicMax(&A.qmax[jb], qm);
-    }
-  }
-
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  if (warp == 5) ptx::tmem_dealloc(tmem_base, (uint32_t)A.tmem_cols);
-}
-
+}  // namespace tnb
+#include "mps_tc_chain.cuh"  // tc_chain_kernel: chains, class site, head and adjoint seeds
+namespace tnb {
 
 // ---------------------------------------------------------------------------------------
 // K4 (tensor-core family): weight gradients as a batch-reduction GEMM on tcgen05.
@@ -434,6 +147,8 @@ struct TcDaArgs {
   float *grads;
   int mgroups, nsplit, nstage, tmem_cols;
   long long bchunk;  // samples per split (multiple of 32)
+  int Dv;            // rows m = sigma*chi + a with sigma < Dv: D for chain sites, D*C for the class site
+  int only_site;     // >= 0: this site only (the class site; wq/qmax point at its own tables)
 };
 
 constexpr int kDaKC = 32;                         // samples per pipeline stage
@@ -446,9 +161,9 @@ constexpr uint32_t kDaStage = 4u * kDaPlane;      // A_hi, A_lo, B_hi, B_lo
 __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const MpsArgs<float> &M = A.M;
-  const int chi = M.chip, D = M.D, c = M.c;
-  const int site = blockIdx.y;
-  if (site == c) return;
+  const int chi = M.chip, D = A.Dv, c = M.c;
+  const int site = A.only_site >= 0 ? A.only_site : (int)blockIdx.y;
+  if (A.only_site < 0 && site == c) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int group = blockIdx.x % A.mgroups, split = blockIdx.x / A.mgroups;
   const int Mtot = D * chi;
@@ -481,7 +196,7 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int qmax = A.qmax[site];
+  const int qmax = A.only_site >= 0 ? A.qmax[0] : A.qmax[site];
 
   if (warp == kDaProducers / 32) {
     if (lane == 0) {
@@ -541,7 +256,7 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
       dst_base = 2 * kDaPlane + (uint32_t)(n >> 3) * kDaSBO + (uint32_t)(lane & 1) * 8;
     }
     const float *src_base = (isA ? U : V) + src_off;
-    const float *wq_row = A.wq + ((size_t)site * D + sidx) * M.B;  // (B blocks read it too, unused)
+    const float *wq_row = A.wq + ((size_t)(A.only_site >= 0 ? 0 : site) * D + sidx) * M.B;  // (B blocks read it too, unused)
     const float qs = ldexpf(1.f, kTcKA - qmax);
     const float ka = 16384.f;
 
@@ -606,7 +321,7 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
       ptx::mbar_wait(done, 0);
       ptx::tc_fence_after();
       const float sc = ldexpf(1.f, qmax - 2 * kTcKA);
-      const size_t site_off = (size_t)site * chi * chi * D + (site > c ? (size_t)chi * chi * D * (M.C - 1) : 0);
+      const size_t site_off = (size_t)site * chi * chi * M.D + (site > c ? (size_t)chi * chi * M.D * (M.C - 1) : 0);
       float *g = A.grads + site_off;
       for (int t = 0; t < ntile; ++t) {
         const int m = m0 + t * 128 + tid, s = m / chi, a = m - s * chi;

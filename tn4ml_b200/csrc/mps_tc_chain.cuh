@@ -1,0 +1,475 @@
+// K2 + K3 (tensor-core family): the whole per-sample chain on tcgen05 / TMEM.
+//
+// One CTA owns 128 samples (thread == sample row == TMEM lane in the epilogue warps) and runs a
+// "program" of MMA steps; every step is one GEMM  acc[128, D*chi] = operand[128, chi] x W[chi, D*chi]
+// whose B operand is a pre-split weight image streamed by 1-D bulk copies, followed by an epilogue
+// that turns the accumulator into the next A operand without leaving the SM.
+//
+//   forward (grid.y == 1):   right chain  (sites L-1 .. c+1, transposed images)
+//                            left chain   (sites 0 .. c-1)
+//                            class steps  (slabs c+k, k < C):  y'_k = <F[c] M_c^k , F[c+1]>
+//                            head         (loss, out)                         -- K3
+//   adjoint (grid.y == 2):   seed steps   (k < C, accumulating in TMEM):
+//                                G[c]   = sum_k dy'_k M_c^k F[c+1]   (half 0)
+//                                G[c+1] = sum_k dy'_k F[c] M_c^k     (half 1)
+//                            adjoint chain towards the boundary, recording the per-sample weights
+//                            wq / qmax of the dA GEMM (mps_tc.cuh, tc_da_kernel).
+//
+// Environments are carried as (mantissa row, integer exponent): every epilogue renormalises the
+// row to max-abs in [0.5, 1) by an exact power of two, which is also what keeps the fp16 hi/lo
+// operand split inside the fp16 range (see mps_tc.cuh for the fp16x3 arithmetic).
+#pragma once
+#include "mps_tc.cuh"
+
+namespace tnb {
+
+template <int D>
+__global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int adjoint) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const MpsArgs<float> &M = A.M;
+  const int chi = M.chip, L = M.L, c = M.c, C = M.C;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = blockIdx.y;
+  const long long b0 = (long long)blockIdx.x * kTcRows;
+  const int nR = L - 1 - c, nL = c;
+
+  // ---- the step program (identical in every warp role) ----
+  int nseed, nchain, total;
+  if (!adjoint) {
+    nseed = 0; nchain = nR + nL; total = nchain + C;
+  } else {
+    if (half == 0 && c == 0) return;
+    if (half == 1 && c == L - 1) return;
+    nseed = C;
+    nchain = half == 0 ? c - 1 : L - 2 - c;
+    total = nseed + nchain;
+  }
+  // step -> weight image
+  auto step_image = [&](int step) -> const uint8_t * {
+    int slab;
+    bool tr;
+    if (!adjoint) {
+      if (step < nR) { slab = mps_slab(M, L - 1 - step); tr = true; }
+      else if (step < nR + nL) { slab = mps_slab(M, step - nR); tr = false; }
+      else { slab = c + (step - nR - nL); tr = false; }
+    } else {
+      if (step < nseed) { slab = c + step; tr = half == 0; }
+      else if (half == 0) { slab = mps_slab(M, c - 1 - (step - nseed)); tr = true; }
+      else { slab = mps_slab(M, c + 1 + (step - nseed)); tr = false; }
+    }
+    return (tr ? A.img_t : A.img_n) + (size_t)slab * A.site_img_bytes;
+  };
+
+  const uint32_t a_plane = (uint32_t)kTcRows * chi * 2;
+  uint8_t *a_hi = smem;
+  uint8_t *a_lo = smem + a_plane;
+  uint8_t *stages = smem + 2 * a_plane;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(stages + (size_t)A.nstage * A.stage_bytes);
+  uint64_t *full = bars, *empty = bars + A.nstage, *acc_full = bars + 2 * A.nstage, *a_ready = acc_full + 1;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_ready + 1);
+
+  if (tid == 0) {
+    for (int i = 0; i < A.nstage; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    ptx::mbar_init(acc_full, 1);
+    ptx::mbar_init(a_ready, kTcRows);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 5) {
+    ptx::tmem_alloc(tmem_slot, (uint32_t)A.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int KS = chi / 16;
+
+  if (warp == 4) {
+    // ===== producer: one bulk async copy per pipeline stage =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int step = 0; step < total; ++step) {
+        const uint8_t *img = step_image(step);
+        for (int ks = 0; ks < KS; ++ks) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1);
+          ptx::mbar_expect_tx(&full[stage], A.stage_bytes);
+          ptx::bulk_g2s(stages + (size_t)stage * A.stage_bytes, img + (size_t)ks * A.stage_bytes, A.stage_bytes,
+                        &full[stage]);
+          if (++stage == A.nstage) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = ptx::idesc_f16_f32(kTcRows, A.NMMA);
+      const uint32_t a_hi_s = ptx::smem_u32(a_hi), a_lo_s = ptx::smem_u32(a_lo);
+      const uint32_t sbo_a = (uint32_t)chi * 16;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int step = 0; step < total; ++step) {
+        const bool accum_step = adjoint && step > 0 && step < nseed;  // seed steps accumulate over k
+        ptx::mbar_wait(a_ready, step & 1);
+        ptx::tc_fence_after();
+        for (int ks = 0; ks < KS; ++ks) {
+          ptx::mbar_wait(&full[stage], phase);
+          ptx::tc_fence_after();
+          const uint64_t da_hi = ptx::smem_desc_kmajor(a_hi_s + ks * 256, 128, sbo_a);
+          const uint64_t da_lo = ptx::smem_desc_kmajor(a_lo_s + ks * 256, 128, sbo_a);
+          const uint32_t st = ptx::smem_u32(stages + (size_t)stage * A.stage_bytes);
+          for (int h = 0; h < A.NH; ++h) {
+            const uint32_t boff = (uint32_t)h * (A.NMMA / 8) * 256;
+            const uint64_t db_hi = ptx::smem_desc_kmajor(st + boff, 128, 256);
+            const uint64_t db_lo = ptx::smem_desc_kmajor(st + (uint32_t)A.N * 32 + boff, 128, 256);
+            const uint32_t d = tmem_base + (uint32_t)h * A.NMMA;
+            ptx::mma_f16(d, da_hi, db_hi, idesc, (ks > 0 || accum_step) ? 1u : 0u);
+            ptx::mma_f16(d, da_lo, db_hi, idesc, 1u);
+            ptx::mma_f16(d, da_hi, db_lo, idesc, 1u);
+          }
+          ptx::mma_commit(&empty[stage]);
+          if (++stage == A.nstage) { stage = 0; phase ^= 1; }
+        }
+        ptx::mma_commit(acc_full);
+      }
+    }
+  } else {
+    // ===== epilogue: thread == sample row == TMEM lane =====
+    const int row = tid;
+    const long long b = b0 + row;
+    const bool valid = b < M.B;
+    const size_t bs = (size_t)(valid ? b : 0);
+    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t row_off = (uint32_t)(row >> 3) * (uint32_t)chi * 16 + (uint32_t)(row & 7) * 16;
+    const float ka = 16384.f;  // 2^kTcKA
+    int step = 0;
+
+    auto store_op16 = [&](int n0, const float(&w)[16]) {
+      uint4 hi, lo;
+      split8(w, hi, lo);
+      *reinterpret_cast<uint4 *>(a_hi + row_off + (n0 / 8) * 128) = hi;
+      *reinterpret_cast<uint4 *>(a_lo + row_off + (n0 / 8) * 128) = lo;
+      split8(w + 8, hi, lo);
+      *reinterpret_cast<uint4 *>(a_hi + row_off + (n0 / 8 + 1) * 128) = hi;
+      *reinterpret_cast<uint4 *>(a_lo + row_off + (n0 / 8 + 1) * 128) = lo;
+    };
+    auto write_e0_operand = [&]() {
+      for (int kc = 0; kc < chi / 8; ++kc) {
+        uint4 z = make_uint4(0, 0, 0, 0), zh = z;
+        if (kc == 0) zh.x = 0x00007400u;  // fp16(2^14) in element 0
+        *reinterpret_cast<uint4 *>(a_hi + row_off + kc * 128) = zh;
+        *reinterpret_cast<uint4 *>(a_lo + row_off + kc * 128) = z;
+      }
+    };
+    auto write_e0_env = [&](float *env) {
+      if (!env || !valid) return;
+      for (int n = 0; n < chi; n += 4)
+        *reinterpret_cast<float4 *>(env + (size_t)b * chi + n) = make_float4(n == 0 ? 1.f : 0.f, 0.f, 0.f, 0.f);
+    };
+    auto write_operand_from_row = [&](const float *rowp, float scale) {
+      for (int n0 = 0; n0 < chi; n0 += 16) {
+        float w[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 v = *reinterpret_cast<const float4 *>(rowp + n0 + 4 * q);
+          w[4 * q] = v.x * scale; w[4 * q + 1] = v.y * scale; w[4 * q + 2] = v.z * scale; w[4 * q + 3] = v.w * scale;
+        }
+        store_op16(n0, w);
+      }
+    };
+    auto publish = [&]() {  // operand (and TMEM reads) done -> the MMA warp may start the next step
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async();
+      ptx::mbar_arrive(a_ready);
+    };
+    // One chain step.  mode 0: forward (records delta, stashes F)   mode 1: adjoint (records wq/qmax, stashes G)
+    // `hexp` is the forward exponent sum (mode 0) or the running exponent h of the adjoint (mode 1).
+    // next_op: 0 = none, 1 = the normalised vector, 2 = the boundary vector e0.
+    auto chain_step = [&](int site, int kw, const float *ph_in, float *env, int mode, int &hexp, int next_op) {
+      float ph[D];  // registers (static indexing only)
+#pragma unroll
+      for (int s = 0; s < D; ++s) ph[s] = ph_in[s];
+      const int dsite = (mode == 1 && valid) ? M.exps[(size_t)site * M.B + b] : 0;
+      ptx::mbar_wait(acc_full, step & 1);
+      ptx::tc_fence_after();
+      float m = 0.f;
+      for (int n0 = 0; n0 < chi; n0 += 16) {
+        float t[D][16];
+#pragma unroll
+        for (int s = 0; s < D; ++s) ptx::tmem_ld16(trow + (uint32_t)(s * chi + n0), t[s]);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float o = ph[0] * t[0][j];
+#pragma unroll
+          for (int s = 1; s < D; ++s) o = fmaf(ph[s], t[s][j], o);
+          m = fmaxf(m, fabsf(o));
+        }
+      }
+      int e = 0;
+      const bool nz = m > 0.f && valid;
+      if (nz) frexpf(m, &e);
+      const int dtrue = nz ? e - kTcKA - kw : 0;  // exponent in units of the true recurrence
+      if (mode == 0) {
+        hexp += dtrue;
+        if (valid && M.exps) M.exps[(size_t)site * M.B + b] = dtrue;
+      } else {
+        // dA_site = sum_b 2^q (F x phi x G), q = h_in - delta_site, h_in = exponent of the input adjoint
+        const int q = hexp - dsite;
+        if (valid) {
+#pragma unroll
+          for (int s = 0; s < D; ++s) A.wq[((size_t)site * D + s) * M.B + b] = ph[s] * ldexpf(1.f, q);
+        }
+        int qm = valid ? q : INT_MIN;
+        for (int off = 16; off > 0; off >>= 1) qm = max(qm, __shfl_xor_sync(0xffffffffu, qm, off));
+        if (lane == 0 && qm != INT_MIN) atomicMax(&A.qmax[site], qm);
+        hexp += dtrue - dsite;
+      }
+      const float nsc = valid ? ldexpf(1.f, -e) : 0.f;
+      for (int n0 = 0; n0 < chi; n0 += 16) {
+        float t[D][16];
+#pragma unroll
+        for (int s = 0; s < D; ++s) ptx::tmem_ld16(trow + (uint32_t)(s * chi + n0), t[s]);
+        ptx::tmem_ld_wait();
+        float w[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float o = ph[0] * t[0][j];
+#pragma unroll
+          for (int s = 1; s < D; ++s) o = fmaf(ph[s], t[s][j], o);
+          w[j] = o * nsc;
+        }
+        if (env && valid) {
+          float *dst = env + (size_t)b * chi + n0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4 *>(dst + 4 * q) = make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+        }
+        if (next_op == 1) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) w[j] *= ka;
+          store_op16(n0, w);
+        }
+      }
+      if (next_op == 2) write_e0_operand();
+      publish();
+      ++step;
+    };
+
+    if (!adjoint) {
+      // ---------------- forward program ----------------
+      int esumR = 0, esumL = 0;
+      write_e0_operand();
+      write_e0_env(mps_fenv(M, L));
+      write_e0_env(mps_fenv(M, 0));
+      publish();
+      for (int i = 0; i < nR; ++i) {
+        const int site = L - 1 - i;
+        float ph[kMaxPhys];
+        embed_site(M.emb, valid ? M.x[bs * L + site] : 0.5f, ph);
+        chain_step(site, A.kW[mps_slab(M, site)], ph, mps_fenv(M, site), 0, esumR, i == nR - 1 ? 2 : 1);
+      }
+      for (int i = 0; i < nL; ++i) {
+        const int site = i;
+        float ph[kMaxPhys];
+        embed_site(M.emb, valid ? M.x[bs * L + site] : 0.5f, ph);
+        chain_step(site, A.kW[mps_slab(M, site)], ph, mps_fenv(M, site + 1), 0, esumL, 1);
+      }
+      // ---------------- class site + head ----------------
+      float phc[D];
+      {
+        float phl[kMaxPhys];
+        embed_site(M.emb, valid ? M.x[bs * L + c] : 0.5f, phl);
+#pragma unroll
+        for (int s = 0; s < D; ++s) phc[s] = phl[s];
+      }
+      const float *fr = mps_fenv(M, c + 1) + bs * chi;  // this thread wrote that row itself
+      const float ysc = ldexpf(1.f, -(kTcKA + A.kW[c]));
+      float y[kMaxOut];
+      for (int k = 0; k < C; ++k) {
+        ptx::mbar_wait(acc_full, step & 1);
+        ptx::tc_fence_after();
+        float acc = 0.f;
+        for (int n0 = 0; n0 < chi; n0 += 16) {
+          float t[D][16];
+#pragma unroll
+          for (int s = 0; s < D; ++s) ptx::tmem_ld16(trow + (uint32_t)(s * chi + n0), t[s]);
+          float f[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 v = *reinterpret_cast<const float4 *>(fr + n0 + 4 * q);
+            f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w;
+          }
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float o = phc[0] * t[0][j];
+#pragma unroll
+            for (int s = 1; s < D; ++s) o = fmaf(phc[s], t[s][j], o);
+            acc = fmaf(o, f[j], acc);
+          }
+        }
+        y[k] = acc * ysc;
+        publish();
+        ++step;
+      }
+      float lval = 0.f;
+      if (valid) {
+        M.esum[b] = esumL;
+        M.esum[M.B + b] = esumR;
+        float tl[kMaxOut];
+        for (int k = 0; k < C; ++k) {
+          tl[k] = M.targets ? M.targets[(size_t)b * C + k] : 0.f;
+          M.y[(size_t)b * C + k] = y[k];
+          if (M.out) M.out[(size_t)b * C + k] = y[k];
+        }
+        const int E = esumL + esumR;
+        if (M.out_exp) M.out_exp[b] = E;
+        lval = mps_head<float>(M.head, C, y, E, tl, M.cw, (float *)nullptr);
+        if (M.loss) M.loss[b] = lval;
+      }
+      if (M.loss_sum) {  // one atomic per warp
+        double ls = (double)lval;
+        for (int off = 16; off > 0; off >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, off);
+        if (lane == 0) atomicAdd(M.loss_sum, ls);
+      }
+    } else {
+      // ---------------- adjoint program ----------------
+      // head derivative dLoss/dy' (times loss_scale) for this sample
+      float dy[kMaxOut];
+      {
+        float yl[kMaxOut], tl[kMaxOut];
+        for (int k = 0; k < C; ++k) {
+          yl[k] = valid ? M.y[(size_t)b * C + k] : 1.f;
+          tl[k] = (valid && M.targets) ? M.targets[(size_t)b * C + k] : (k == 0 ? 1.f : 0.f);
+        }
+        const int E = valid ? M.esum[b] + M.esum[M.B + b] : 0;
+        mps_head<float>(M.head, C, yl, E, tl, M.cw, dy);
+        for (int k = 0; k < C; ++k) dy[k] = valid ? dy[k] * M.loss_scale : 0.f;
+      }
+      float phc[D];
+      {
+        float phl[kMaxPhys];
+        embed_site(M.emb, valid ? M.x[bs * L + c] : 0.5f, phl);
+#pragma unroll
+        for (int s = 0; s < D; ++s) phc[s] = phl[s];
+      }
+      float dmax = 0.f;
+      for (int k = 0; k < C; ++k) dmax = fmaxf(dmax, fabsf(dy[k]));
+      int ed = 0;
+      if (dmax > 0.f) frexpf(dmax, &ed);
+      if (valid) {
+        // class-site dA weights: wqc[(s,k)][b] = phi_s * dy'_k ; both halves write identical values
+        int qm = INT_MIN;
+        for (int s = 0; s < D; ++s)
+          for (int k = 0; k < C; ++k) {
+            const float w = phc[s] * dy[k];
+            A.wqc[((size_t)s * C + k) * M.B + b] = w;
+            if (w != 0.f) { int ew; frexpf(w, &ew); qm = max(qm, ew); }
+          }
+        for (int k = 0; k < C; ++k) M.dy[(size_t)b * C + k] = dy[k];
+        if (qm != INT_MIN) atomicMax(A.qmaxc, qm);
+      }
+      const float *vrow = mps_fenv(M, half == 0 ? c + 1 : c) + bs * chi;
+      const float dsc = valid ? ldexpf(1.f, kTcKA - ed) : 0.f;  // |dy_k * dsc| < 2^14 and the row is normalised
+      write_operand_from_row(vrow, dy[0] * dsc);
+      publish();
+      int h = 0;
+      const int jb = half == 0 ? 0 : L - 1;  // the boundary site: no chain step, but it has a gradient
+      for (int k = 0; k < C; ++k) {
+        if (k < C - 1) {
+          ptx::mbar_wait(acc_full, step & 1);  // MMAs of step k have finished reading the operand
+          ptx::tc_fence_after();
+          write_operand_from_row(vrow, dy[k + 1] * dsc);
+          publish();
+          ++step;
+        } else {
+          // all C slabs accumulated: normalise -> seed G[c] / G[c+1]
+          int hs = 0;
+          float *genv = M.G + (size_t)(half == 0 ? c : c + 1) * M.B * chi;
+          // reuse the forward-mode bookkeeping of chain_step: hs receives (e - 14 - kWc)
+          ptx::mbar_wait(acc_full, step & 1);
+          ptx::tc_fence_after();
+          float m = 0.f;
+          for (int n0 = 0; n0 < chi; n0 += 16) {
+            float t[D][16];
+#pragma unroll
+            for (int s = 0; s < D; ++s) ptx::tmem_ld16(trow + (uint32_t)(s * chi + n0), t[s]);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float o = phc[0] * t[0][j];
+#pragma unroll
+              for (int s = 1; s < D; ++s) o = fmaf(phc[s], t[s][j], o);
+              m = fmaxf(m, fabsf(o));
+            }
+          }
+          int e = 0;
+          const bool nz = m > 0.f && valid;
+          if (nz) frexpf(m, &e);
+          hs = nz ? e - kTcKA - A.kW[c] : 0;
+          h = hs + ed;  // G = normalised row * 2^h   (the operand carried dy * 2^-ed)
+          const float nsc = valid ? ldexpf(1.f, -e) : 0.f;
+          for (int n0 = 0; n0 < chi; n0 += 16) {
+            float t[D][16];
+#pragma unroll
+            for (int s = 0; s < D; ++s) ptx::tmem_ld16(trow + (uint32_t)(s * chi + n0), t[s]);
+            ptx::tmem_ld_wait();
+            float w[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float o = phc[0] * t[0][j];
+#pragma unroll
+              for (int s = 1; s < D; ++s) o = fmaf(phc[s], t[s][j], o);
+              w[j] = o * nsc;
+            }
+            if (valid) {
+              float *dst = genv + (size_t)b * chi + n0;
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4 *>(dst + 4 * q) = make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+            }
+            if (nchain > 0) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) w[j] *= ka;
+              store_op16(n0, w);
+            }
+          }
+          publish();
+          ++step;
+        }
+      }
+      for (int i = 0; i < nchain; ++i) {
+        const int site = half == 0 ? c - 1 - i : c + 1 + i;
+        const int bond_out = half == 0 ? site : site + 1;
+        float ph[kMaxPhys];
+        embed_site(M.emb, valid ? M.x[bs * L + site] : 0.5f, ph);
+        chain_step(site, A.kW[mps_slab(M, site)], ph, M.G + (size_t)bond_out * M.B * chi, 1, h, i == nchain - 1 ? 0 : 1);
+      }
+      // boundary site weights
+      {
+        int qm = INT_MIN;
+        if (valid) {
+          const int q = h - M.exps[(size_t)jb * M.B + b];
+          float ph[kMaxPhys];
+          embed_site(M.emb, M.x[(size_t)b * L + jb], ph);
+#pragma unroll
+          for (int s = 0; s < D; ++s) A.wq[((size_t)jb * D + s) * M.B + b] = ph[s] * ldexpf(1.f, q);
+          qm = q;
+        }
+        for (int off = 16; off > 0; off >>= 1) qm = max(qm, __shfl_xor_sync(0xffffffffu, qm, off));
+        if (lane == 0 && qm != INT_MIN) atomicMax(&A.qmax[jb], qm);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (warp == 5) ptx::tmem_dealloc(tmem_base, (uint32_t)A.tmem_cols);
+}
+
+}  // namespace tnb
