@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
   const long long kend = min(M.B, kbeg + A.bchunk);
   if (kbeg >= kend) return;
   const int nchunks = (int)((kend - kbeg + kDaKC - 1) / kDaKC);
-  const float *U = site < c ? mps_fenv(M, site) : M.G + (size_t)site * M.B * chi;
+  const float *U = site <= c ? mps_fenv(M, site) : M.G + (size_t)site * M.B * chi;
   const float *V = site < c ? M.G + (size_t)(site + 1) * M.B * chi : mps_fenv(M, site + 1);
 
   uint8_t *stages = smem;
