@@ -183,8 +183,7 @@ def run_native(args):
     model = T.TensorNetwork(arrays, dtype=dtype, device=dev)
     precision = {"auto": None, "simt": _lib.PREC_SIMT, "tensor": _lib.PREC_TENSOR}[args.precision]
     if precision is None:
-        precision = _lib.PREC_TENSOR if (dtype == torch.float32 and hasattr(T, "TENSOR_PATH") and
-                                         args.chi in getattr(T, "TENSOR_PATH")) else _lib.PREC_SIMT
+        precision = _lib.PREC_TENSOR if dtype == torch.float32 else _lib.PREC_SIMT
     loss_fn = lambda *a, **k: metrics.OptaxWrapper(metrics.softmax_cross_entropy)(*a, **k).mean()  # noqa: E731
     model.configure(optimizer=T.optim.adam, learning_rate=1e-4, loss=loss_fn, train_type=T.TrainingType.SUPERVISED,
                     device=("gpu", local), precision=precision,
@@ -261,7 +260,8 @@ def run_native(args):
     top = max(per, key=lambda k: sum(per[k])) if per else "none"
     fps = flops_per_sample(args.L, args.chi, 2, args.classes, c)
     # share of the step's algorithmic flops carried by each kernel family (fwd sweep 1/3, adjoint 1/3, dA 1/3)
-    share = {"mps_sweep_kernel(fwd)": 1 / 3, "mps_sweep_kernel(adj)": 1 / 3, "mps_da_kernel": 1 / 3}
+    share = {"mps_sweep_kernel(fwd)": 1 / 3, "mps_sweep_kernel(adj)": 1 / 3, "mps_da_kernel": 1 / 3,
+             "tc_chain_kernel(fwd)": 1 / 3, "tc_chain_kernel(adj)": 1 / 3, "tc_da_kernel": 1 / 3}
     mb_launches = len(per.get(top, [1]))
     top_ms = float(np.mean(per[top])) if per else float("nan")
     peaks = {}

@@ -1,0 +1,103 @@
+"""The drop-in surface on a GPU: configure -> train -> evaluate / forward / accuracy / predict,
+for the model kinds of the BASELINE configs (reference: tests/test_model.py:468-613 checks that
+train() returns a finite history of the right length; here values are also checked against the oracle)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import tn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def test_train_unsupervised_nll_history_and_descent():
+    import tn4ml_b200 as T
+    from tn4ml_b200.initializers import randn
+    model = T.MPS_initialize(8, initializer=randn(0.3), key=7, bond_dim=6, phys_dim=2, device="cuda:0")
+    model.configure(optimizer=T.optim.adam, strategy="global", loss=T.metrics.NegLogLikelihood,
+                    train_type=T.TrainingType.UNSUPERVISED, learning_rate=5e-2, device=("gpu", 0))
+    x = np.random.default_rng(0).random((40, 8))
+    hist = model.train(x, batch_size=16, epochs=6, embedding=T.TrigonometricEmbedding(), normalize=True,
+                       dtype=np.float64)
+    assert len(hist["loss"]) == 6 and len(hist["epoch_time"]) == 6 and np.all(np.isfinite(hist["loss"]))
+    assert hist["loss"][-1] < hist["loss"][0]
+    assert abs(float(model.norm()) - 1.0) < 1e-9              # normalize=True keeps <A|A> = 1
+    scores = model.evaluate(x, batch_size=16, embedding=T.TrigonometricEmbedding(), return_list=True,
+                            metric=T.metrics.NegLogLikelihood, dtype=np.float64)
+    assert scores.shape == (40,) and np.all(scores >= 0)       # tests/test_metrics.py:40-113
+    ref = O.per_sample_loss(O.Problem("mps", O.EmbSpec("trig"), "nll"), torch.tensor(x),
+                            [a.detach().cpu().double() for a in model.arrays])
+    assert np.allclose(scores, ref.numpy(), rtol=1e-10)
+
+
+def test_train_supervised_classifier_first_step_matches_oracle_adam():
+    import tn4ml_b200 as T
+    arrays = O.make_mps_arrays(10, 5, 3, class_site=4, C=3, std=0.2, seed=5)
+    x, t = O.make_inputs(24, 10, seed=1), O.make_labels(24, 3)
+    model = T.TensorNetwork(arrays, device="cuda:0")
+
+    def loss(*a, **k):
+        return T.metrics.OptaxWrapper(T.metrics.softmax_cross_entropy)(*a, **k).mean()
+
+    model.configure(optimizer=T.optim.adam, loss=loss, train_type=T.TrainingType.SUPERVISED, learning_rate=1e-2,
+                    device=("gpu", 0))
+    emb = T.PolynomialEmbedding(degree=2, n=1, include_bias=True)
+    hist = model.train(x.numpy(), targets=t.numpy(), batch_size=24, epochs=1, embedding=emb, dtype=np.float64)
+    prob = O.Problem("mps", O.EmbSpec("poly", degree=2, include_bias=True), "softmax_xent")
+    lref, gref = O.value_and_grad(prob, x, arrays, t)
+    assert abs(hist["loss"][0] - float(lref)) < 1e-10
+    for a_new, a_old, g in zip(model.arrays, arrays, gref):    # first Adam step: -lr * g / (|g| + eps)
+        exp = a_old - 1e-2 * g / (g.abs() + 1e-8)
+        mask = g.abs() > 1e-6                                   # sign(g) is ill-defined where g ~ 0
+        assert torch.allclose(a_new.cpu()[mask], exp[mask], atol=1e-7)
+    acc = model.accuracy(x.numpy(), t.numpy(), embedding=emb, batch_size=7, dtype=np.float64)
+    assert 0.0 <= acc <= 1.0
+    y = model.forward(x.numpy(), embedding=emb, batch_size=9, dtype=np.float64)
+    yref = O.mps_outputs(O.embed_batch(x, prob.emb), [a.detach().cpu() for a in model.arrays])
+    assert torch.allclose(y.cpu(), yref, rtol=1e-9, atol=1e-300)
+    yn = model.predict(x[0].numpy(), embedding=emb, normalize=True)
+    assert torch.allclose(yn.cpu(), yref[0] / yref[0].norm(), rtol=1e-9)
+    with pytest.raises(ValueError):
+        model.predict(x[0, :5].numpy(), embedding=emb)         # model.py:306-307
+
+
+def test_train_smpo_combined_loss_with_regulariser():
+    import tn4ml_b200 as T
+    from tn4ml_b200.initializers import randn
+    model = T.SMPO_initialize(16, randn(0.5), 3, spacing=4, bond_dim=4, phys_dim=(2, 2), device="cuda:0")
+
+    def loss_combined(m, data, y_true=None, embedding=None):   # examples/unsupervised/mnist_ad.py:47-57
+        return T.metrics.CombinedLoss(m, data, y_true, error=T.metrics.LogQuadNorm,
+                                      reg=lambda P: 0.4 * T.metrics.LogReLUFrobNorm(P), embedding=embedding)
+
+    model.configure(optimizer=T.optim.adam, loss=loss_combined, train_type=T.TrainingType.UNSUPERVISED,
+                    learning_rate=1e-2, device=("gpu", 0))
+    x = np.random.default_rng(1).random((12, 16))
+    arrays0 = [a.detach().cpu().clone() for a in model.arrays]
+    hist = model.train(x, batch_size=12, epochs=3, embedding=T.TrigonometricEmbedding(), dtype=np.float64)
+    assert len(hist["loss"]) == 3 and np.all(np.isfinite(hist["loss"]))
+    prob = O.Problem("smpo", O.EmbSpec("trig"), "logquad", spacing=4)
+    l0 = float(O.loss_fn(prob, torch.tensor(x), arrays0))      # ||P|| = 1 after init, so the regulariser is 0
+    assert abs(hist["loss"][0] - l0) < 1e-9 * max(1.0, abs(l0))
+
+
+def test_float32_model_uses_tensor_path_by_default_and_trains():
+    import tn4ml_b200 as T
+    from tn4ml_b200 import _lib
+    arrays = O.make_mps_arrays(12, 64, 2, class_site=5, C=4, std=0.05, seed=2, dtype=torch.float32)
+    x, t = O.make_inputs(256, 12, seed=3), O.make_labels(256, 4)
+    model = T.TensorNetwork(arrays, dtype=torch.float32, device="cuda:0")
+    assert model.precision == _lib.PREC_TENSOR
+    model.configure(optimizer=T.optim.adam, loss=T.metrics.CrossEntropySoftmax, train_type=T.TrainingType.SUPERVISED,
+                    learning_rate=1e-3, device=("gpu", 0))
+    hist = model.train(x.numpy(), targets=t.numpy(), batch_size=128, epochs=4, embedding=T.TrigonometricEmbedding(),
+                       dtype=np.float32)
+    assert np.all(np.isfinite(hist["loss"])) and hist["loss"][-1] < hist["loss"][0]
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from tn4ml_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libtn4ml_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.lib()

@@ -38,7 +38,9 @@ def _emb(spec):
     return T.GaussianRBFEmbedding(centers=np.array(spec.centers), gamma=spec.gamma)
 
 
-def _check(model, prob, loss_fn, x, arrays, t, dtype, scale_tol=1.0):
+def _check(model, prob, loss_fn, x, arrays, t, dtype, scale_tol=1.0, precision=0):
+    model.precision = precision  # 0 = SIMT kernels, 1 = tcgen05 kernels where the shape allows
+    model._engine_cache = {}
     tol = TOL[dtype] * scale_tol
     # identical inputs on both sides: round to the kernel dtype first, then run the oracle in float64
     arr64 = [a.to(dtype).double() for a in arrays]

@@ -34,7 +34,7 @@ def test_tensor_path_classifier(case):
     prob = O.Problem("mps", emb, "softmax_xent")
     model = _tensor_model(T.TensorNetwork, arrays)
     l0 = _lib.lib().tnb_launch_count()
-    _check(model, prob, _heads()["softmax_xent"], x, arrays, t, torch.float32)
+    _check(model, prob, _heads()["softmax_xent"], x, arrays, t, torch.float32, precision=1)
     assert _lib.lib().tnb_launch_count() > l0
 
 
@@ -45,7 +45,7 @@ def test_tensor_path_cfg4_nll():
     x = O.make_inputs(300, 16, seed=6)
     prob = O.Problem("mps", O.EmbSpec("fourier", p=8), "nll")
     model = _tensor_model(T.MatrixProductState, arrays)
-    _check(model, prob, _heads()["nll"], x, arrays, None, torch.float32)
+    _check(model, prob, _heads()["nll"], x, arrays, None, torch.float32, precision=1)
 
 
 def test_tensor_path_long_chain():
@@ -56,4 +56,4 @@ def test_tensor_path_long_chain():
     t = O.make_labels(256, 10)
     prob = O.Problem("mps", O.EmbSpec("trig"), "softmax_xent")
     model = _tensor_model(T.TensorNetwork, arrays)
-    _check(model, prob, _heads()["softmax_xent"], x, arrays, t, torch.float32)
+    _check(model, prob, _heads()["softmax_xent"], x, arrays, t, torch.float32, precision=1)

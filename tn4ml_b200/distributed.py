@@ -1,0 +1,35 @@
+"""Data parallelism of the hot path: one process per GPU, the (already ordered)
+batch is split into contiguous shards, site tensors are replicated, and the only exchange is ONE
+all-reduce (sum) of the packed gradient buffer plus the scalar loss per step -- K6.
+
+The reference has no multi-device code at all (tn4ml/models/model.py picks one jax device), so
+this module is new; it keeps ``train_step`` semantics: every rank ends the step with identical
+parameters because it applies the same optimizer update to the same summed gradient.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Rows [lo, hi) of an n-row batch owned by `rank`: contiguous, sizes differ by at most one."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_batch(x, targets=None, group=None):
+    """This rank's contiguous shard of a batch (and of its targets)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, hi = shard_bounds(len(x), rank, world)
+    return (x[lo:hi], None if targets is None else targets[lo:hi])
+
+
+def allreduce_step(loss_sum: torch.Tensor, grads: torch.Tensor, group=None):
+    """Sum the local loss sum and the packed gradient over the batch shards (in place)."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(grads, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(loss_sum, op=dist.ReduceOp.SUM, group=group)
+    return loss_sum, grads

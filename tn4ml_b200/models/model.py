@@ -77,7 +77,9 @@ class Model:
         self.gradient_transforms = None
         self.device = ("gpu", 0)
         self._engine_cache: dict = {}
-        self.precision = _lib.PREC_SIMT
+        # float32 chains run on the tcgen05 kernels wherever the shape allows (the library falls back to
+        # the SIMT family otherwise); float64 always runs on the SIMT/FP64 family
+        self.precision = _lib.PREC_TENSOR
         self.process_group = None  # torch.distributed group for data-parallel training
         if device is None:  # CPU tensors are storage only (layout tests); every compute call needs CUDA
             device = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
@@ -297,11 +299,10 @@ class Model:
                 import torch.distributed as dist
                 n_global = n_local * dist.get_world_size(group)
             loss_sum, g = eng.value_and_grad(self._packed, x, t, denom=n_global, grads=grads)
+            if group is not None:  # K6: sum of the packed per-site gradients (and the loss) over the batch shards
+                from ..distributed import allreduce_step
+                loss_sum, g = allreduce_step(loss_sum, g, group)
             loss = loss_sum / n_global
-            if group is not None:
-                import torch.distributed as dist
-                dist.all_reduce(g, group=group)  # K6: sum of the per-site gradients over the batch shards
-                dist.all_reduce(loss, group=group)
             rv, rg = self._reg_value_and_grad(expr)
             if rv is not None:
                 loss = loss + rv
