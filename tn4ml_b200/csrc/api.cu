@@ -112,7 +112,7 @@ struct MpsPlan {
   // tensor-core sweep (f32, TNB_PREC_TENSOR)
   int tc, tc_N, tc_NH, tc_NMMA, tc_nstage, tc_cols;
   uint32_t tc_stage_bytes;
-  size_t tc_site_img, off_img_n, off_img_t, off_kW, off_wq, off_qmax, off_wqc, tc_smem;
+  size_t tc_site_img, off_img_n, off_img_t, off_kW, off_wq, off_qmax, off_wqc, off_vimg, tc_smem, vimg_bond_bytes;
 };
 
 // The tcgen05 sweep covers: float32, chi a multiple of 16 in [32, 256], D*chi <= 512 TMEM columns.
@@ -185,6 +185,8 @@ static MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
       P.off_wq = take((size_t)p->L * p->d * B * sizeof(float));
       P.off_qmax = take(((size_t)p->L + 1) * sizeof(int));  // [L] chain sites + [1] class site
       P.off_wqc = take((size_t)p->d * p->n_out * B * sizeof(float));
+      P.vimg_bond_bytes = (size_t)((B + 31) / 32 * 32) * p->chi * 4;
+      P.off_vimg = take(((size_t)p->L + 1) * P.vimg_bond_bytes);
     }
   }
   P.total = o;
@@ -221,6 +223,8 @@ static void fill_tc_args(const MpsPlan &P, void *ws, const MpsArgs<float> &M, Tc
   T.wq = (float *)(w + P.off_wq);
   T.qmax = (int *)(w + P.off_qmax);
   T.wqc = (float *)(w + P.off_wqc);
+  T.vimg = M.stash ? (uint8_t *)(w + P.off_vimg) : nullptr;
+  T.vimg_bond_bytes = P.vimg_bond_bytes;
   T.qmaxc = T.qmax + M.L;
   T.N = P.tc_N; T.NH = P.tc_NH; T.NMMA = P.tc_NMMA; T.nstage = P.tc_nstage; T.tmem_cols = P.tc_cols;
   T.stage_bytes = P.tc_stage_bytes; T.site_img_bytes = P.tc_site_img;
@@ -289,6 +293,11 @@ static int mps_forward_t(const tnb_problem *p, const MpsPlan &P, long long B, co
       tc_sitemax_kernel<<<P.nslab, 256, 0, st>>>((const float *)params, (int *)Tc.kW, p->L, p->chi, p->d, p->n_out,
                                                  p->out_site);
       TNB_LAUNCH_CHECK("tc_sitemax_kernel");
+      if (p->n_out > 1) {
+        prof_begin(st);
+        tc_classmin_kernel<<<1, 32, 0, st>>>((int *)Tc.kW, p->out_site, p->n_out);
+        TNB_LAUNCH_CHECK("tc_classmin_kernel");
+      }
       size_t items = (size_t)P.tc_N * (p->chi / 8) * P.nslab;
       int ib = (int)((items + 255) / 256);
       if (ib > 148 * 32) ib = 148 * 32;
@@ -340,6 +349,8 @@ static int mps_backward_t(const tnb_problem *p, const MpsPlan &P, long long B, c
       TcDaArgs Da;
       Da.M = A;
       Da.grads = (float *)grads;
+      Da.vimg = Tc.vimg;
+      Da.vimg_bond_bytes = Tc.vimg_bond_bytes;
       Da.nstage = 3;
       Da.tmem_cols = 32;
       while (Da.tmem_cols < 2 * p->chi) Da.tmem_cols <<= 1;

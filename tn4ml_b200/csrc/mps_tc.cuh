@@ -38,6 +38,8 @@ struct TcArgs {
   const int *kW;         // per-slab weight pre-scale exponent
   float *wq;             // adjoint: phi_s[b] * 2^q[b] per (site, s, b): per-sample weight of the dA GEMM
   int *qmax;             // adjoint: max_b q[site][b]
+  uint8_t *vimg;         // fp16 hi/lo images of the dA GEMM's V operand, per bond: [bond][B/32][2 planes][chi/8][512 B]
+  size_t vimg_bond_bytes;
   float *wqc;            // adjoint: phi_s[b] * dLoss/dy'_k[b] per ((s,k), b): weights of the class-site dA GEMM
   int *qmaxc;            // adjoint: max exponent of wqc
   int N, NH, NMMA, nstage, tmem_cols;
@@ -56,9 +58,9 @@ __global__ void tc_sitemax_kernel(const float *__restrict__ params, int *__restr
   else { site = slab - C + 1; nj = 1; }
   const size_t site_off = (size_t)site * chi * chi * D + (site > c ? (size_t)chi * chi * D * (C - 1) : 0);
   float m = 0.f;
-  // class slabs share one scale: the seed phase accumulates all of them into one TMEM tile
-  const int n = chi * chi * D * nj;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(params[site_off + i]));
+  const int o = slab - site - (site > c ? C - 1 : 0);  // class slabs: o = slab - c ; otherwise 0
+  const int n = chi * chi * D;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(params[site_off + (size_t)i * nj + o]));
   __shared__ float red[32];
   for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
@@ -69,6 +71,14 @@ __global__ void tc_sitemax_kernel(const float *__restrict__ params, int *__restr
     if (m > 0.f) frexpf(m, &e);
     kW[slab] = kTcKA - e;
   }
+}
+
+// class slabs share one scale (the seed phase accumulates all of them into one TMEM tile): kW <- min over the C slabs
+__global__ void tc_classmin_kernel(int *__restrict__ kW, int c, int C) {
+  int m = INT_MAX;
+  for (int k = threadIdx.x; k < C; k += 32) m = min(m, kW[c + k]);
+  for (int off = 16; off > 0; off >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, off));
+  for (int k = threadIdx.x; k < C; k += 32) kW[c + k] = m;
 }
 
 // one thread per (slab, n', k-octet): 8 weights -> 16 B of hi and 16 B of lo, both directions
@@ -135,10 +145,12 @@ namespace tnb {
 // K4 (tensor-core family): weight gradients as a batch-reduction GEMM on tcgen05.
 //   dA_site[a, r, s] = 2^qmax * sum_b (U[b,a] * wq[site][s][b] * 2^-qmax) * V[b,r]
 //   rows m = s*chi + a (M tiles of 128, two per CTA), columns r (N = chi), K = samples.
-// Both operands are produced in-kernel from the fp32 environment stashes: 8 producer warps
-// (lane == sample) read 32-byte pieces of their stash rows, apply the per-sample weight, split
-// to fp16 hi/lo and write the canonical MN-major shared-memory layout; warp 8 issues the MMAs; warps 0-3 drain TMEM once
-// at the end and reduce into the packed gradient with fp32 atomics (split-K across CTAs).
+// The V operand needs no per-sample weight, so the chain kernels write it once as fp16 hi/lo
+// images in exactly the MN-major shared-memory layout and one bulk async copy per stage brings
+// it in.  The U operand carries the per-sample weight: 16 producer warps read 512 contiguous
+// bytes of a stash row per load, apply the weight, split to fp16 hi/lo and write the operand
+// tiles.  One warp issues the MMAs; warps 0-3 drain TMEM once at the end and reduce into the
+// packed gradient with fp32 atomics (split-K across CTAs).
 // ---------------------------------------------------------------------------------------
 struct TcDaArgs {
   MpsArgs<float> M;
@@ -147,16 +159,19 @@ struct TcDaArgs {
   float *grads;
   int mgroups, nsplit, nstage, tmem_cols;
   long long bchunk;  // samples per split (multiple of 32)
+  const uint8_t *vimg;
+  size_t vimg_bond_bytes;
   int Dv;            // rows m = sigma*chi + a with sigma < Dv: D for chain sites, D*C for the class site
   int only_site;     // >= 0: this site only (the class site; wq/qmax point at its own tables)
 };
 
 constexpr int kDaKC = 32;                         // samples per pipeline stage
 constexpr int kDaProducers = 512;                 // threads (16 warps)
-constexpr int kDaThreads = kDaProducers + 32;
+constexpr int kDaThreads = kDaProducers + 64;      // + MMA warp + bulk-copy warp
 constexpr uint32_t kDaSBO = 528u;                 // row-octet stride: 4 sample blocks x 128 B + 16 B skew (bank spread)
 constexpr uint32_t kDaPlane = 32u * kDaSBO;       // one operand plane: 32 row octets x 32 samples fp16
-constexpr uint32_t kDaStage = 4u * kDaPlane;      // A_hi, A_lo, B_hi, B_lo
+constexpr uint32_t kDaBMax = 256u * 128u;         // B region: chi * 128 B (hi plane then lo plane, SBO 512)
+constexpr uint32_t kDaStage = 2u * kDaPlane + kDaBMax;  // A_hi, A_lo (transformed in-kernel), B (bulk-copied image)
 
 __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -174,21 +189,24 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
   if (kbeg >= kend) return;
   const int nchunks = (int)((kend - kbeg + kDaKC - 1) / kDaKC);
   const float *U = site <= c ? mps_fenv(M, site) : M.G + (size_t)site * M.B * chi;
-  const float *V = site < c ? M.G + (size_t)(site + 1) * M.B * chi : mps_fenv(M, site + 1);
+  // V operand: pre-split image of bond site+1 (G for the left half, F for the right half and the class site)
+  const uint8_t *Vimg = A.vimg + (size_t)(site + 1) * A.vimg_bond_bytes + (size_t)(kbeg / kDaKC) * chi * 128;
+  const uint32_t b_bytes = (uint32_t)chi * 128;
 
+  constexpr int kMmaWarp = kDaProducers / 32, kCopyWarp = kMmaWarp + 1;
   uint8_t *stages = smem;
   uint64_t *bars = reinterpret_cast<uint64_t *>(stages + (size_t)A.nstage * kDaStage);
   uint64_t *full = bars, *empty = bars + A.nstage, *done = bars + 2 * A.nstage;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done + 1);
   if (tid == 0) {
     for (int i = 0; i < A.nstage; ++i) {
-      ptx::mbar_init(&full[i], kDaProducers);
+      ptx::mbar_init(&full[i], kDaProducers + 1);  // 512 transform arrivals + the bulk copy's expect_tx arrival
       ptx::mbar_init(&empty[i], 1);
     }
     ptx::mbar_init(done, 1);
     ptx::fence_mbar_init();
   }
-  if (warp == kDaProducers / 32) {
+  if (warp == kMmaWarp) {
     ptx::tmem_alloc(tmem_slot, (uint32_t)A.tmem_cols);
     ptx::tmem_relinquish();
   }
@@ -198,7 +216,7 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
   const uint32_t tmem_base = *tmem_slot;
   const int qmax = A.only_site >= 0 ? A.qmax[0] : A.qmax[site];
 
-  if (warp == kDaProducers / 32) {
+  if (warp == kMmaWarp) {
     if (lane == 0) {
       const uint32_t idesc = ptx::idesc_f16_f32(128, chi) | (1u << 15) | (1u << 16);  // A and B MN-major
       int stage = 0;
@@ -212,8 +230,8 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
           for (int ks = 0; ks < kDaKC / 16; ++ks) {
             const uint64_t da_hi = ptx::smem_desc_kmajor(st + t * 16 * kDaSBO + ks * 256, 128, kDaSBO);
             const uint64_t da_lo = ptx::smem_desc_kmajor(st + kDaPlane + t * 16 * kDaSBO + ks * 256, 128, kDaSBO);
-            const uint64_t db_hi = ptx::smem_desc_kmajor(st + 2 * kDaPlane + ks * 256, 128, kDaSBO);
-            const uint64_t db_lo = ptx::smem_desc_kmajor(st + 3 * kDaPlane + ks * 256, 128, kDaSBO);
+            const uint64_t db_hi = ptx::smem_desc_kmajor(st + 2 * kDaPlane + ks * 256, 128, 512);
+            const uint64_t db_lo = ptx::smem_desc_kmajor(st + 2 * kDaPlane + (uint32_t)chi * 64 + ks * 256, 128, 512);
             const uint32_t d = tmem_base + (uint32_t)t * chi;
             ptx::mma_f16(d, da_hi, db_hi, idesc, (ch > 0 || ks > 0) ? 1u : 0u);
             ptx::mma_f16(d, da_lo, db_hi, idesc, 1u);
@@ -225,44 +243,39 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
       }
       ptx::mma_commit(done);
     }
-  } else {
-    // ===== producers: warp == (sample, 128-row block), lane == 4 consecutive rows =====
-    // Shared-memory operand layout (MN-major, no swizzle): 8 consecutive rows of one sample are one
-    // 16-byte unit; 8 samples form a 128-byte core matrix; sample blocks at LBO = 128 B, row octets
-    // at SBO = 528 B (the 16-byte skew spreads a warp's 16 octets over all banks).  A warp reads 512
-    // contiguous bytes of ONE stash row per load, so L1 sees 4 lines per request instead of 32.
-    const int nb = (chi + 127) / 128;       // 128-column blocks of the B operand
-    const int IPS = ntile + nb;             // 128-row blocks per sample: A tiles then B blocks (2..4)
-    constexpr int kWarps = kDaProducers / 32;
-    constexpr int kItems = 8;               // samples per warp and stage (32 samples * IPS / 16 warps, IPS <= 4)
-    // every warp owns ONE 128-row block `sub` and a strided subset of the stage's 32 samples, so all
-    // per-lane addressing is loop invariant
-    const int sub = warp % IPS;
-    const int cnt = (kWarps - sub + IPS - 1) / IPS;  // warps sharing this block
-    const int j0 = warp / IPS;                       // this warp's rank among them: samples j0, j0+cnt, ...
-    const bool isA = sub < ntile;
-    bool lane_on = true;
-    int sidx = 0, src_off;
-    uint32_t dst_base;
-    if (isA) {
-      const int m = m0 + sub * 128 + 4 * lane;
-      sidx = m / chi;
-      src_off = m - sidx * chi;
-      dst_base = (uint32_t)(sub * 16 + (lane >> 1)) * kDaSBO + (uint32_t)(lane & 1) * 8;
-    } else {
-      const int n = (sub - ntile) * 128 + 4 * lane;
-      lane_on = n < chi;
-      src_off = lane_on ? n : 0;
-      dst_base = 2 * kDaPlane + (uint32_t)(n >> 3) * kDaSBO + (uint32_t)(lane & 1) * 8;
+  } else if (warp == kCopyWarp) {
+    // ===== V operand: one bulk async copy of the pre-split image per stage =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        ptx::mbar_wait(&empty[stage], phase ^ 1);
+        ptx::mbar_expect_tx(&full[stage], b_bytes);
+        ptx::bulk_g2s(stages + (size_t)stage * kDaStage + 2 * kDaPlane, Vimg + (size_t)ch * b_bytes, b_bytes, &full[stage]);
+        if (++stage == A.nstage) { stage = 0; phase ^= 1; }
+      }
     }
-    const float *src_base = (isA ? U : V) + src_off;
-    const float *wq_row = A.wq + ((size_t)(A.only_site >= 0 ? 0 : site) * D + sidx) * M.B;  // (B blocks read it too, unused)
+  } else {
+    // ===== U operand producers: warp == (sample subset, 128-row block), lane == 4 consecutive rows =====
+    // Shared-memory layout (MN-major, no swizzle): 8 consecutive rows of one sample are one 16-byte unit;
+    // 8 samples form a 128-byte core matrix; sample blocks at LBO = 128 B, row octets at SBO = 528 B
+    // (the 16-byte skew spreads a warp's 16 octets over all banks).  A warp reads 512 contiguous bytes
+    // of ONE stash row per load.
+    constexpr int kWarps = kDaProducers / 32;
+    constexpr int kItems = 4;               // samples per warp and stage: 32 samples * 2 blocks / 16 warps
+    const int sub = warp % ntile;                        // this warp's 128-row block
+    const int cnt = (kWarps - sub + ntile - 1) / ntile;  // warps sharing it
+    const int j0 = warp / ntile;                         // samples j0, j0 + cnt, ...
+    const int m = m0 + sub * 128 + 4 * lane;
+    const int sidx = m / chi;
+    const float *src_base = U + (m - sidx * chi);
+    const uint32_t dst_base = (uint32_t)(sub * 16 + (lane >> 1)) * kDaSBO + (uint32_t)(lane & 1) * 8;
+    const float *wq_row = A.wq + ((size_t)(A.only_site >= 0 ? 0 : site) * D + sidx) * M.B;
     const float qs = ldexpf(1.f, kTcKA - qmax);
-    const float ka = 16384.f;
 
-    // Issue phase: loads only (no instruction may consume a loaded value here, or the in-order
-    // warp would stall on the first one and serialise the rest).  Out-of-range samples are
-    // clamped to a valid row and zeroed by their weight in the convert phase.
+    // Issue phase: loads only (no instruction may consume a loaded value here, or the in-order warp
+    // would stall on the first one and serialise the rest).  Out-of-range samples are clamped to a
+    // valid row and zeroed by their weight in the convert phase.
 #define TNB_DA_ISSUE(CH, R, SC)                                                                      \
   {                                                                                                   \
     const long long bbase_ = kbeg + (long long)(CH)*kDaKC;                                            \
@@ -278,8 +291,8 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
     const long long bbase_ = kbeg + (long long)(CH)*kDaKC;                                            \
     _Pragma("unroll") for (int i = 0; i < kItems; ++i) {                                              \
       const int k_ = j0 + i * cnt;                                                                    \
-      if (k_ < kDaKC && lane_on) {                                                                    \
-        const float f_ = (bbase_ + k_ < kend) ? (isA ? SC[i] * qs : ka) : 0.f;                        \
+      if (k_ < kDaKC) {                                                                               \
+        const float f_ = (bbase_ + k_ < kend) ? SC[i] * qs : 0.f;                                     \
         const float w0 = R[i].x * f_, w1 = R[i].y * f_, w2 = R[i].z * f_, w3 = R[i].w * f_;           \
         const __half2 hA = __floats2half2_rn(w0, w1), hB = __floats2half2_rn(w2, w3);                 \
         const float2 fA = __half22float2(hA), fB = __half22float2(hB);                                \
@@ -324,7 +337,7 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
       const size_t site_off = (size_t)site * chi * chi * M.D + (site > c ? (size_t)chi * chi * M.D * (M.C - 1) : 0);
       float *g = A.grads + site_off;
       for (int t = 0; t < ntile; ++t) {
-        const int m = m0 + t * 128 + tid, s = m / chi, a = m - s * chi;
+        const int mm = m0 + t * 128 + tid, s = mm / chi, a = mm - s * chi;
         const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)t * chi;
         for (int n0 = 0; n0 < chi; n0 += 16) {
           float v[16];
@@ -339,7 +352,7 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  if (warp == kDaProducers / 32) ptx::tmem_dealloc(tmem_base, (uint32_t)A.tmem_cols);
+  if (warp == kMmaWarp) ptx::tmem_dealloc(tmem_base, (uint32_t)A.tmem_cols);
 }
 
 }  // namespace tnb

@@ -147,14 +147,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
     const float ka = 16384.f;  // 2^kTcKA
     int step = 0;
 
-    auto store_op16 = [&](int n0, const float(&w)[16]) {
+    // w (already scaled by 2^14) -> fp16 hi/lo octets -> next A operand (smem) and/or the dA V image (global)
+    auto store_op16 = [&](int n0, const float(&w)[16], bool to_smem = true, uint8_t *vrow = nullptr) {
       uint4 hi, lo;
-      split8(w, hi, lo);
-      *reinterpret_cast<uint4 *>(a_hi + row_off + (n0 / 8) * 128) = hi;
-      *reinterpret_cast<uint4 *>(a_lo + row_off + (n0 / 8) * 128) = lo;
-      split8(w + 8, hi, lo);
-      *reinterpret_cast<uint4 *>(a_hi + row_off + (n0 / 8 + 1) * 128) = hi;
-      *reinterpret_cast<uint4 *>(a_lo + row_off + (n0 / 8 + 1) * 128) = lo;
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        split8(w + 8 * o, hi, lo);
+        if (to_smem) {
+          *reinterpret_cast<uint4 *>(a_hi + row_off + (n0 / 8 + o) * 128) = hi;
+          *reinterpret_cast<uint4 *>(a_lo + row_off + (n0 / 8 + o) * 128) = lo;
+        }
+        if (vrow) {
+          *reinterpret_cast<uint4 *>(vrow + (size_t)(n0 / 8 + o) * 512) = hi;
+          *reinterpret_cast<uint4 *>(vrow + (size_t)chi * 64 + (size_t)(n0 / 8 + o) * 512) = lo;
+        }
+      }
+    };
+    // this sample's slot inside the V image of `bond`: [bond][b/32][plane][n/8][(b%32)/8][b%8][8 halves]
+    const bool img_ok = A.vimg != nullptr && (b0 + row) < (M.B + 31) / 32 * 32;
+    auto vimg_row = [&](int bond) -> uint8_t * {
+      if (!img_ok) return nullptr;
+      const long long bb = b0 + row;
+      return A.vimg + (size_t)bond * A.vimg_bond_bytes + (size_t)(bb >> 5) * chi * 128 + (size_t)((bb & 31) >> 3) * 128 +
+             (size_t)(bb & 7) * 16;
     };
     auto write_e0_operand = [&]() {
       for (int kc = 0; kc < chi / 8; ++kc) {
@@ -188,7 +203,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
     // One chain step.  mode 0: forward (records delta, stashes F)   mode 1: adjoint (records wq/qmax, stashes G)
     // `hexp` is the forward exponent sum (mode 0) or the running exponent h of the adjoint (mode 1).
     // next_op: 0 = none, 1 = the normalised vector, 2 = the boundary vector e0.
-    auto chain_step = [&](int site, int kw, const float *ph_in, float *env, int mode, int &hexp, int next_op) {
+    auto chain_step = [&](int site, int kw, const float *ph_in, float *env, int mode, int &hexp, int next_op,
+                          uint8_t *vrow) {
       float ph[D];  // registers (static indexing only)
 #pragma unroll
       for (int s = 0; s < D; ++s) ph[s] = ph_in[s];
@@ -248,10 +264,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
           for (int q = 0; q < 4; ++q)
             *reinterpret_cast<float4 *>(dst + 4 * q) = make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
         }
-        if (next_op == 1) {
+        if (next_op == 1 || vrow) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) w[j] *= ka;
-          store_op16(n0, w);
+          store_op16(n0, w, next_op == 1, vrow);
         }
       }
       if (next_op == 2) write_e0_operand();
@@ -265,18 +281,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       write_e0_operand();
       write_e0_env(mps_fenv(M, L));
       write_e0_env(mps_fenv(M, 0));
+      if (uint8_t *vr = vimg_row(L)) {  // V image of the boundary vector (dA of site L-1 / of a class site at L-1)
+        for (int o = 0; o < chi / 8; ++o) {
+          uint4 z = make_uint4(0, 0, 0, 0), zh = z;
+          if (o == 0 && valid) zh.x = 0x00007400u;
+          *reinterpret_cast<uint4 *>(vr + (size_t)o * 512) = zh;
+          *reinterpret_cast<uint4 *>(vr + (size_t)chi * 64 + (size_t)o * 512) = z;
+        }
+      }
       publish();
       for (int i = 0; i < nR; ++i) {
         const int site = L - 1 - i;
         float ph[kMaxPhys];
         embed_site(M.emb, valid ? M.x[bs * L + site] : 0.5f, ph);
-        chain_step(site, A.kW[mps_slab(M, site)], ph, mps_fenv(M, site), 0, esumR, i == nR - 1 ? 2 : 1);
+        chain_step(site, A.kW[mps_slab(M, site)], ph, mps_fenv(M, site), 0, esumR, i == nR - 1 ? 2 : 1, vimg_row(site));
       }
       for (int i = 0; i < nL; ++i) {
         const int site = i;
         float ph[kMaxPhys];
         embed_site(M.emb, valid ? M.x[bs * L + site] : 0.5f, ph);
-        chain_step(site, A.kW[mps_slab(M, site)], ph, mps_fenv(M, site + 1), 0, esumL, 1);
+        chain_step(site, A.kW[mps_slab(M, site)], ph, mps_fenv(M, site + 1), 0, esumL, 1, nullptr);
       }
       // ---------------- class site + head ----------------
       float phc[D];
@@ -432,10 +456,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
               for (int q = 0; q < 4; ++q)
                 *reinterpret_cast<float4 *>(dst + 4 * q) = make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
             }
-            if (nchain > 0) {
+            uint8_t *vr = half == 0 ? vimg_row(c) : nullptr;
+            if (nchain > 0 || vr) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) w[j] *= ka;
-              store_op16(n0, w);
+              store_op16(n0, w, nchain > 0, vr);
             }
           }
           publish();
@@ -447,7 +472,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
         const int bond_out = half == 0 ? site : site + 1;
         float ph[kMaxPhys];
         embed_site(M.emb, valid ? M.x[bs * L + site] : 0.5f, ph);
-        chain_step(site, A.kW[mps_slab(M, site)], ph, M.G + (size_t)bond_out * M.B * chi, 1, h, i == nchain - 1 ? 0 : 1);
+        chain_step(site, A.kW[mps_slab(M, site)], ph, M.G + (size_t)bond_out * M.B * chi, 1, h, i == nchain - 1 ? 0 : 1,
+                   half == 0 ? vimg_row(bond_out) : nullptr);
       }
       // boundary site weights
       {
