@@ -124,7 +124,6 @@ static bool tc_supported(const tnb_problem *p) {
   if (!(p->d == 2 || p->d == 3 || p->d == 4 || p->d == 6 || p->d == 8)) return false;
   const int NH = (N + 255) / 256;
   if (N % NH != 0 || (N / NH) % 16 != 0) return false;
-  if (N % 128 != 0) return false;  // dA GEMM: M tiles of 128 rows over (s, a)
   return true;
 }
 

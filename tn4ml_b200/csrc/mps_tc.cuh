@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
   const int group = blockIdx.x % A.mgroups, split = blockIdx.x / A.mgroups;
   const int Mtot = D * chi;
   const int m0 = group * 256;
-  const int ntile = min(2, (Mtot - m0) / 128);
+  const int ntile = min(2, (Mtot - m0 + 127) / 128);  // the last tile may be partial: rows >= Mtot stay zero
   const long long kbeg = (long long)split * A.bchunk;
   const long long kend = min(M.B, kbeg + A.bchunk);
   if (kbeg >= kend) return;
@@ -209,6 +209,12 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
   if (warp == kMmaWarp) {
     ptx::tmem_alloc(tmem_slot, (uint32_t)A.tmem_cols);
     ptx::tmem_relinquish();
+  }
+  if (m0 + ntile * 128 > Mtot) {  // partial tile: its unused operand rows must read as zero
+    for (int st = 0; st < A.nstage; ++st)
+      for (uint32_t i = tid * 16u; i < 2u * kDaPlane; i += kDaThreads * 16u)
+        *reinterpret_cast<uint4 *>(stages + (size_t)st * kDaStage + i) = make_uint4(0, 0, 0, 0);
+    ptx::fence_proxy_async();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -267,8 +273,9 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
     const int cnt = (kWarps - sub + ntile - 1) / ntile;  // warps sharing it
     const int j0 = warp / ntile;                         // samples j0, j0 + cnt, ...
     const int m = m0 + sub * 128 + 4 * lane;
-    const int sidx = m / chi;
-    const float *src_base = U + (m - sidx * chi);
+    const bool row_on = m < Mtot;  // (Mtot is a multiple of 4)
+    const int sidx = row_on ? m / chi : 0;
+    const float *src_base = U + (row_on ? m - sidx * chi : 0);
     const uint32_t dst_base = (uint32_t)(sub * 16 + (lane >> 1)) * kDaSBO + (uint32_t)(lane & 1) * 8;
     const float *wq_row = A.wq + ((size_t)(A.only_site >= 0 ? 0 : site) * D + sidx) * M.B;
     const float qs = ldexpf(1.f, kTcKA - qmax);
@@ -291,7 +298,7 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
     const long long bbase_ = kbeg + (long long)(CH)*kDaKC;                                            \
     _Pragma("unroll") for (int i = 0; i < kItems; ++i) {                                              \
       const int k_ = j0 + i * cnt;                                                                    \
-      if (k_ < kDaKC) {                                                                               \
+      if (k_ < kDaKC && row_on) {                                                                     \
         const float f_ = (bbase_ + k_ < kend) ? SC[i] * qs : 0.f;                                     \
         const float w0 = R[i].x * f_, w1 = R[i].y * f_, w2 = R[i].z * f_, w3 = R[i].w * f_;           \
         const __half2 hA = __floats2half2_rn(w0, w1), hB = __floats2half2_rn(w2, w3);                 \
@@ -338,6 +345,7 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
       float *g = A.grads + site_off;
       for (int t = 0; t < ntile; ++t) {
         const int mm = m0 + t * 128 + tid, s = mm / chi, a = mm - s * chi;
+        if (mm >= Mtot) continue;
         const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)t * chi;
         for (int n0 = 0; n0 < chi; n0 += 16) {
           float v[16];
