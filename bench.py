@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--microbatch", type=int, default=0)
     ap.add_argument("--cpu-batch", type=int, default=0, help="samples per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-chi-sweep", action="store_true", help="skip the chi=32/128 side measurements")
     return ap.parse_args()
 
 
@@ -161,6 +162,39 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def quick_point(args, chi, dtype, dev, steps=2):
+    """Device-resident fwd+bwd throughput at another bond dimension (the metric's chi = 32 / 128 points)."""
+    import copy
+    import tn4ml_b200 as T
+    from tn4ml_b200 import metrics
+    a2 = copy.copy(args)
+    a2.chi = chi
+    arrays, c = make_problem(a2, dtype)
+    model = T.TensorNetwork(arrays, dtype=dtype, device=dev)
+    loss_fn = lambda *a, **k: metrics.OptaxWrapper(metrics.softmax_cross_entropy)(*a, **k).mean()  # noqa: E731
+    eng, _ = model._engine(T.TrigonometricEmbedding(), loss_fn, True, dtype)
+    rng = np.random.default_rng(7)
+    B = args.batch
+    x = torch.from_numpy((1.0 - rng.random((B, args.L))).astype(np.float32 if dtype == torch.float32 else np.float64)).to(dev)
+    t = torch.nn.functional.one_hot(torch.from_numpy(rng.integers(0, args.classes, size=B)), args.classes).to(dev, dtype)
+    g = torch.zeros(eng.n_params, dtype=dtype, device=dev)
+    for _ in range(3):
+        eng.value_and_grad(model._packed, x, t, grads=g)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        eng.value_and_grad(model._packed, x, t, grads=g)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    fl = flops_per_sample(args.L, chi, 2, args.classes, c) * B
+    out = {"samples_per_s": B / ms * 1e3, "ms_per_step": ms, "tflops": fl / ms / 1e9}
+    del eng, model, g, x, t
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_native(args):
@@ -301,6 +335,20 @@ def run_native(args):
     e2e_value = B * world / (float(ems.item()) / args.steps * 1e-3)
     h2d = x_host.numel() * x_host.element_size() + t_host.numel() * t_host.element_size()
 
+    sweep = None
+    if rank == 0 and world == 1 and not args.no_chi_sweep:
+        del x_dev, t_dev, grads
+        eng._ws.clear()
+        torch.cuda.empty_cache()
+        sweep = {str(args.chi): {"samples_per_s": value, "ms_per_step": ms_per_step,
+                                 "tflops": fps * B / (ms_per_step * 1e-3) / 1e12}}
+        for chi2 in (128, 32):
+            if chi2 != args.chi:
+                try:
+                    sweep[str(chi2)] = quick_point(args, chi2, dtype, dev)
+                except Exception as exc:  # pragma: no cover
+                    sweep[str(chi2)] = {"error": str(exc)[:200]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -324,6 +372,7 @@ def run_native(args):
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                     "includes": "H2D of x and targets from pinned memory, value_and_grad, all-reduce, Adam update, loss D2H"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "chi_sweep": sweep,
             "loss": lval,
         }
         print(json.dumps(line), flush=True)
