@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -112,7 +113,7 @@ struct MpsPlan {
   // tensor-core sweep (f32, TNB_PREC_TENSOR)
   int tc, tc_N, tc_NH, tc_NMMA, tc_nstage, tc_cols;
   uint32_t tc_stage_bytes;
-  size_t tc_site_img, off_img_n, off_img_t, off_kW, off_wq, off_qmax, off_wqc, off_vimg, tc_smem, vimg_bond_bytes;
+  size_t tc_site_img, off_img_n, off_img_t, off_kW, off_wq, off_qmax, off_wqc, off_fimg, off_gimg, tc_smem, img_bond_bytes;
 };
 
 // The tcgen05 sweep covers: float32, chi a multiple of 16 in [32, 256], D*chi <= 512 TMEM columns.
@@ -154,9 +155,10 @@ static MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
   P.off_Wn = take(slab * P.nslab);
   P.off_Wt = take(slab * P.nslab);
+  const bool tc_mode = tc_supported(p);
   size_t fslots = need_grad ? (size_t)p->L + 1 : 2;
-  P.off_F = take(fslots * B * P.chip * w);
-  P.off_G = need_grad ? take(((size_t)p->L + 1) * B * P.chip * w) : 0;
+  P.off_F = tc_mode ? 0 : take(fslots * B * P.chip * w);
+  P.off_G = (need_grad && !tc_mode) ? take(((size_t)p->L + 1) * B * P.chip * w) : 0;
   P.off_exps = take((size_t)p->L * B * sizeof(int));
   P.off_esum = take((size_t)2 * B * sizeof(int));
   P.off_y = take((size_t)B * p->n_out * w);
@@ -177,6 +179,9 @@ static MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
     if (P.tc_nstage < 2) P.tc = 0;
   }
   if (P.tc) {
+    // the tensor path keeps its environments as fp16 hi/lo bond images instead of F / G
+    P.img_bond_bytes = (size_t)((B + 31) / 32 * 32) * p->chi * 4;
+    P.off_fimg = take((need_grad ? (size_t)p->L + 1 : 1) * P.img_bond_bytes);
     P.off_img_n = take(P.tc_site_img * P.nslab);
     P.off_img_t = take(P.tc_site_img * P.nslab);
     P.off_kW = take((size_t)P.nslab * sizeof(int));
@@ -184,8 +189,7 @@ static MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
       P.off_wq = take((size_t)p->L * p->d * B * sizeof(float));
       P.off_qmax = take(((size_t)p->L + 1) * sizeof(int));  // [L] chain sites + [1] class site
       P.off_wqc = take((size_t)p->d * p->n_out * B * sizeof(float));
-      P.vimg_bond_bytes = (size_t)((B + 31) / 32 * 32) * p->chi * 4;
-      P.off_vimg = take(((size_t)p->L + 1) * P.vimg_bond_bytes);
+      P.off_gimg = take(((size_t)p->L + 1) * P.img_bond_bytes);
     }
   }
   P.total = o;
@@ -222,9 +226,12 @@ static void fill_tc_args(const MpsPlan &P, void *ws, const MpsArgs<float> &M, Tc
   T.wq = (float *)(w + P.off_wq);
   T.qmax = (int *)(w + P.off_qmax);
   T.wqc = (float *)(w + P.off_wqc);
-  T.vimg = M.stash ? (uint8_t *)(w + P.off_vimg) : nullptr;
-  T.vimg_bond_bytes = P.vimg_bond_bytes;
+  T.fimg = (uint8_t *)(w + P.off_fimg);
+  T.gimg = M.stash ? (uint8_t *)(w + P.off_gimg) : nullptr;
+  T.img_bond_bytes = P.img_bond_bytes;
+  T.img_stash = M.stash;
   T.qmaxc = T.qmax + M.L;
+  { const char *dbg = getenv("TNB_DEBUG"); T.dbg = dbg ? atoi(dbg) : 0; }
   T.N = P.tc_N; T.NH = P.tc_NH; T.NMMA = P.tc_NMMA; T.nstage = P.tc_nstage; T.tmem_cols = P.tc_cols;
   T.stage_bytes = P.tc_stage_bytes; T.site_img_bytes = P.tc_site_img;
 }
@@ -348,8 +355,9 @@ static int mps_backward_t(const tnb_problem *p, const MpsPlan &P, long long B, c
       TcDaArgs Da;
       Da.M = A;
       Da.grads = (float *)grads;
-      Da.vimg = Tc.vimg;
-      Da.vimg_bond_bytes = Tc.vimg_bond_bytes;
+      Da.fimg = Tc.fimg;
+      Da.gimg = Tc.gimg;
+      Da.img_bond_bytes = Tc.img_bond_bytes;
       Da.nstage = 3;
       Da.tmem_cols = 32;
       while (Da.tmem_cols < 2 * p->chi) Da.tmem_cols <<= 1;

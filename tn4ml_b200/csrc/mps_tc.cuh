@@ -38,11 +38,16 @@ struct TcArgs {
   const int *kW;         // per-slab weight pre-scale exponent
   float *wq;             // adjoint: phi_s[b] * 2^q[b] per (site, s, b): per-sample weight of the dA GEMM
   int *qmax;             // adjoint: max_b q[site][b]
-  uint8_t *vimg;         // fp16 hi/lo images of the dA GEMM's V operand, per bond: [bond][B/32][2 planes][chi/8][512 B]
-  size_t vimg_bond_bytes;
+  // Environment stash of the tensor path: fp16 hi/lo images (value * 2^14, rows normalised), one per bond,
+  // laid out [slot][B/32][plane hi|lo][chi/8][4 sample blocks][8 samples][8 halves] = exactly the MN-major
+  // operand tile of the dA GEMM for a chunk of 32 samples.  fimg: forward environments, gimg: adjoints.
+  uint8_t *fimg, *gimg;
+  size_t img_bond_bytes;
+  int img_stash;         // 1: every bond has a slot; 0: forward-only, a single slot for bond c+1
   float *wqc;            // adjoint: phi_s[b] * dLoss/dy'_k[b] per ((s,k), b): weights of the class-site dA GEMM
   int *qmaxc;            // adjoint: max exponent of wqc
   int N, NH, NMMA, nstage, tmem_cols;
+  int dbg;               // measurement switches (TNB_DEBUG env): 1 = no fp32 stash stores, 2 = no V images, 4 = skip max pass
   uint32_t stage_bytes;
   size_t site_img_bytes;
 };
@@ -145,11 +150,10 @@ namespace tnb {
 // K4 (tensor-core family): weight gradients as a batch-reduction GEMM on tcgen05.
 //   dA_site[a, r, s] = 2^qmax * sum_b (U[b,a] * wq[site][s][b] * 2^-qmax) * V[b,r]
 //   rows m = s*chi + a (M tiles of 128, two per CTA), columns r (N = chi), K = samples.
-// The V operand needs no per-sample weight, so the chain kernels write it once as fp16 hi/lo
-// images in exactly the MN-major shared-memory layout and one bulk async copy per stage brings
-// it in.  The U operand carries the per-sample weight: 16 producer warps read 512 contiguous
-// bytes of a stash row per load, apply the weight, split to fp16 hi/lo and write the operand
-// tiles.  One warp issues the MMAs; warps 0-3 drain TMEM once at the end and reduce into the
+// Both operands come from the fp16 hi/lo bond images the chain kernels write, which already are
+// the MN-major shared-memory tile layout.  V needs no per-sample weight: one bulk async copy per
+// stage brings it in.  U carries the per-sample weight: 16 producer warps (lane == sample) read
+// hi/lo units, rebuild fp32, apply the weight, re-split and write the operand tiles.  One warp issues the MMAs; warps 0-3 drain TMEM once at the end and reduce into the
 // packed gradient with fp32 atomics (split-K across CTAs).
 // ---------------------------------------------------------------------------------------
 struct TcDaArgs {
@@ -159,8 +163,8 @@ struct TcDaArgs {
   float *grads;
   int mgroups, nsplit, nstage, tmem_cols;
   long long bchunk;  // samples per split (multiple of 32)
-  const uint8_t *vimg;
-  size_t vimg_bond_bytes;
+  const uint8_t *fimg, *gimg;
+  size_t img_bond_bytes;
   int Dv;            // rows m = sigma*chi + a with sigma < Dv: D for chain sites, D*C for the class site
   int only_site;     // >= 0: this site only (the class site; wq/qmax point at its own tables)
 };
@@ -168,7 +172,7 @@ struct TcDaArgs {
 constexpr int kDaKC = 32;                         // samples per pipeline stage
 constexpr int kDaProducers = 512;                 // threads (16 warps)
 constexpr int kDaThreads = kDaProducers + 64;      // + MMA warp + bulk-copy warp
-constexpr uint32_t kDaSBO = 528u;                 // row-octet stride: 4 sample blocks x 128 B + 16 B skew (bank spread)
+constexpr uint32_t kDaSBO = 512u;                 // row-octet stride: 4 sample blocks x 128 B
 constexpr uint32_t kDaPlane = 32u * kDaSBO;       // one operand plane: 32 row octets x 32 samples fp16
 constexpr uint32_t kDaBMax = 256u * 128u;         // B region: chi * 128 B (hi plane then lo plane, SBO 512)
 constexpr uint32_t kDaStage = 2u * kDaPlane + kDaBMax;  // A_hi, A_lo (transformed in-kernel), B (bulk-copied image)
@@ -188,9 +192,12 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
   const long long kend = min(M.B, kbeg + A.bchunk);
   if (kbeg >= kend) return;
   const int nchunks = (int)((kend - kbeg + kDaKC - 1) / kDaKC);
-  const float *U = site <= c ? mps_fenv(M, site) : M.G + (size_t)site * M.B * chi;
-  // V operand: pre-split image of bond site+1 (G for the left half, F for the right half and the class site)
-  const uint8_t *Vimg = A.vimg + (size_t)(site + 1) * A.vimg_bond_bytes + (size_t)(kbeg / kDaKC) * chi * 128;
+  // both operands come from the bond images written by the chain kernels:
+  //   U = F[site] (left half, class site) or G[site] (right half): re-weighted per sample in-kernel
+  //   V = G[site+1] (left half) or F[site+1] (right half, class site): bulk-copied as is
+  const size_t chunk0 = (size_t)(kbeg / kDaKC) * chi * 128;
+  const uint8_t *Uimg = (site <= c ? A.fimg : A.gimg) + (size_t)site * A.img_bond_bytes + chunk0;
+  const uint8_t *Vimg = (site < c ? A.gimg : A.fimg) + (size_t)(site + 1) * A.img_bond_bytes + chunk0;
   const uint32_t b_bytes = (uint32_t)chi * 128;
 
   constexpr int kMmaWarp = kDaProducers / 32, kCopyWarp = kMmaWarp + 1;
@@ -262,73 +269,81 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
       }
     }
   } else {
-    // ===== U operand producers: warp == (sample subset, 128-row block), lane == 4 consecutive rows =====
-    // Shared-memory layout (MN-major, no swizzle): 8 consecutive rows of one sample are one 16-byte unit;
-    // 8 samples form a 128-byte core matrix; sample blocks at LBO = 128 B, row octets at SBO = 528 B
-    // (the 16-byte skew spreads a warp's 16 octets over all banks).  A warp reads 512 contiguous bytes
-    // of ONE stash row per load.
+    // ===== U operand producers: lane == sample, warp == row octet =====
+    // The bond image already is the MN-major tile layout (8 rows of one sample = one 16-byte unit,
+    // consecutive samples = consecutive units), so a warp reads 512 contiguous bytes per plane and
+    // writes 512 contiguous bytes per plane: hi + lo -> fp32 -> * per-sample weight -> hi/lo.
     constexpr int kWarps = kDaProducers / 32;
-    constexpr int kItems = 4;               // samples per warp and stage: 32 samples * 2 blocks / 16 warps
-    const int sub = warp % ntile;                        // this warp's 128-row block
-    const int cnt = (kWarps - sub + ntile - 1) / ntile;  // warps sharing it
-    const int j0 = warp / ntile;                         // samples j0, j0 + cnt, ...
-    const int m = m0 + sub * 128 + 4 * lane;
-    const bool row_on = m < Mtot;  // (Mtot is a multiple of 4)
-    const int sidx = row_on ? m / chi : 0;
-    const float *src_base = U + (row_on ? m - sidx * chi : 0);
-    const uint32_t dst_base = (uint32_t)(sub * 16 + (lane >> 1)) * kDaSBO + (uint32_t)(lane & 1) * 8;
-    const float *wq_row = A.wq + ((size_t)(A.only_site >= 0 ? 0 : site) * D + sidx) * M.B;
-    const float qs = ldexpf(1.f, kTcKA - qmax);
+    constexpr int kItems = 2;  // row octets per warp and stage: 2 tiles * 16 octets / 16 warps
+    const uint32_t lane_off = (uint32_t)(lane >> 3) * 128 + (uint32_t)(lane & 7) * 16;
+    uint32_t src_off[kItems], dst_off[kItems];
+    const float *wq_row[kItems];
+    bool on[kItems];
+#pragma unroll
+    for (int i = 0; i < kItems; ++i) {
+      const int ro = warp + i * kWarps;
+      const int m = m0 + ro * 8;
+      on[i] = ro < ntile * 16 && m < Mtot;
+      const int sidx = on[i] ? m / chi : 0;
+      const int a0 = on[i] ? m - sidx * chi : 0;
+      src_off[i] = (uint32_t)(a0 >> 3) * 512 + lane_off;
+      dst_off[i] = (uint32_t)ro * kDaSBO + lane_off;
+      wq_row[i] = A.wq + ((size_t)(A.only_site >= 0 ? 0 : site) * D + sidx) * M.B;
+    }
+    const float qs = ldexpf(1.f, -qmax);  // (the image already carries the 2^14 operand scale)
+    const uint32_t lo_off = (uint32_t)chi * 64;
 
     // Issue phase: loads only (no instruction may consume a loaded value here, or the in-order warp
-    // would stall on the first one and serialise the rest).  Out-of-range samples are clamped to a
-    // valid row and zeroed by their weight in the convert phase.
-#define TNB_DA_ISSUE(CH, R, SC)                                                                      \
+    // would stall on the first one and serialise the rest).
+#define TNB_DA_ISSUE(CH, RH, RL, SC)                                                                  \
   {                                                                                                   \
-    const long long bbase_ = kbeg + (long long)(CH)*kDaKC;                                            \
+    const uint8_t *cb_ = Uimg + (size_t)(CH)*chi * 128;                                               \
+    const long long b_ = min(kbeg + (long long)(CH)*kDaKC + lane, kend - 1);                          \
     _Pragma("unroll") for (int i = 0; i < kItems; ++i) {                                              \
-      const int k_ = min(j0 + i * cnt, kDaKC - 1);                                                    \
-      const long long b_ = min(bbase_ + k_, kend - 1);                                                \
-      R[i] = __ldg(reinterpret_cast<const float4 *>(src_base + (size_t)b_ * chi));                    \
-      SC[i] = __ldg(wq_row + b_);                                                                     \
-    }                                                                                                 \
-  }
-#define TNB_DA_CONVERT(CH, ST, R, SC)                                                                 \
-  {                                                                                                   \
-    const long long bbase_ = kbeg + (long long)(CH)*kDaKC;                                            \
-    _Pragma("unroll") for (int i = 0; i < kItems; ++i) {                                              \
-      const int k_ = j0 + i * cnt;                                                                    \
-      if (k_ < kDaKC && row_on) {                                                                     \
-        const float f_ = (bbase_ + k_ < kend) ? SC[i] * qs : 0.f;                                     \
-        const float w0 = R[i].x * f_, w1 = R[i].y * f_, w2 = R[i].z * f_, w3 = R[i].w * f_;           \
-        const __half2 hA = __floats2half2_rn(w0, w1), hB = __floats2half2_rn(w2, w3);                 \
-        const float2 fA = __half22float2(hA), fB = __half22float2(hB);                                \
-        const __half2 lA = __floats2half2_rn(w0 - fA.x, w1 - fA.y), lB = __floats2half2_rn(w2 - fB.x, w3 - fB.y); \
-        uint8_t *d_ = (ST) + dst_base + (uint32_t)(k_ >> 3) * 128 + (uint32_t)(k_ & 7) * 16;           \
-        uint2 hv, lv;                                                                                 \
-        hv.x = *reinterpret_cast<const uint32_t *>(&hA); hv.y = *reinterpret_cast<const uint32_t *>(&hB); \
-        lv.x = *reinterpret_cast<const uint32_t *>(&lA); lv.y = *reinterpret_cast<const uint32_t *>(&lB); \
-        *reinterpret_cast<uint2 *>(d_) = hv;                                                          \
-        *reinterpret_cast<uint2 *>(d_ + kDaPlane) = lv;                                               \
+      if (on[i]) {                                                                                    \
+        RH[i] = __ldg(reinterpret_cast<const uint4 *>(cb_ + src_off[i]));                             \
+        RL[i] = __ldg(reinterpret_cast<const uint4 *>(cb_ + lo_off + src_off[i]));                    \
+        SC[i] = __ldg(wq_row[i] + b_);                                                                \
       }                                                                                               \
     }                                                                                                 \
   }
-    float4 ra[kItems], rb[kItems];
+#define TNB_DA_CONVERT(CH, ST, RH, RL, SC)                                                            \
+  {                                                                                                   \
+    const bool ok_ = kbeg + (long long)(CH)*kDaKC + lane < kend;                                      \
+    _Pragma("unroll") for (int i = 0; i < kItems; ++i) {                                              \
+      if (on[i]) {                                                                                    \
+        const float f_ = ok_ ? SC[i] * qs : 0.f;                                                      \
+        const __half2 *h_ = reinterpret_cast<const __half2 *>(&RH[i]);                                \
+        const __half2 *l_ = reinterpret_cast<const __half2 *>(&RL[i]);                                \
+        float w_[8];                                                                                  \
+        _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                               \
+          const float2 fh = __half22float2(h_[j]), fl = __half22float2(l_[j]);                        \
+          w_[2 * j] = (fh.x + fl.x) * f_;                                                             \
+          w_[2 * j + 1] = (fh.y + fl.y) * f_;                                                         \
+        }                                                                                             \
+        uint4 hv, lv;                                                                                 \
+        split8(w_, hv, lv);                                                                           \
+        *reinterpret_cast<uint4 *>((ST) + dst_off[i]) = hv;                                           \
+        *reinterpret_cast<uint4 *>((ST) + kDaPlane + dst_off[i]) = lv;                                \
+      }                                                                                               \
+    }                                                                                                 \
+  }
+    uint4 rah[kItems], ral[kItems], rbh[kItems], rbl[kItems];
     float sa[kItems], sb[kItems];
     int stage = 0;
     uint32_t phase = 0;
-    TNB_DA_ISSUE(0, ra, sa)
+    TNB_DA_ISSUE(0, rah, ral, sa)
     for (int ch = 0; ch < nchunks; ch += 2) {
-      if (ch + 1 < nchunks) TNB_DA_ISSUE(ch + 1, rb, sb)
+      if (ch + 1 < nchunks) TNB_DA_ISSUE(ch + 1, rbh, rbl, sb)
       ptx::mbar_wait(&empty[stage], phase ^ 1);
-      TNB_DA_CONVERT(ch, stages + (size_t)stage * kDaStage, ra, sa)
+      TNB_DA_CONVERT(ch, stages + (size_t)stage * kDaStage, rah, ral, sa)
       ptx::fence_proxy_async();
       ptx::mbar_arrive(&full[stage]);
       if (++stage == A.nstage) { stage = 0; phase ^= 1; }
       if (ch + 1 < nchunks) {
-        if (ch + 2 < nchunks) TNB_DA_ISSUE(ch + 2, ra, sa)
+        if (ch + 2 < nchunks) TNB_DA_ISSUE(ch + 2, rah, ral, sa)
         ptx::mbar_wait(&empty[stage], phase ^ 1);
-        TNB_DA_CONVERT(ch + 1, stages + (size_t)stage * kDaStage, rb, sb)
+        TNB_DA_CONVERT(ch + 1, stages + (size_t)stage * kDaStage, rbh, rbl, sb)
         ptx::fence_proxy_async();
         ptx::mbar_arrive(&full[stage]);
         if (++stage == A.nstage) { stage = 0; phase ^= 1; }

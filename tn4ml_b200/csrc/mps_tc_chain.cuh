@@ -144,11 +144,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
     const size_t bs = (size_t)(valid ? b : 0);
     const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
     const uint32_t row_off = (uint32_t)(row >> 3) * (uint32_t)chi * 16 + (uint32_t)(row & 7) * 16;
-    const float ka = 16384.f;  // 2^kTcKA
     int step = 0;
 
-    // w (already scaled by 2^14) -> fp16 hi/lo octets -> next A operand (smem) and/or the dA V image (global)
-    auto store_op16 = [&](int n0, const float(&w)[16], bool to_smem = true, uint8_t *vrow = nullptr) {
+    // this sample's 16-byte slot inside the image of `bond` (see TcArgs): consecutive samples of a warp
+    // are consecutive 16-byte units, so every warp-wide image store/load is 512 contiguous bytes
+    const bool img_ok = b < (M.B + 31) / 32 * 32;
+    auto img_row = [&](uint8_t *base, int bond) -> uint8_t * {
+      const int slot = A.img_stash ? bond : (bond == c + 1 ? 0 : -1);
+      if (!img_ok || slot < 0 || base == nullptr) return nullptr;
+      return base + (size_t)slot * A.img_bond_bytes + (size_t)(b >> 5) * chi * 128 + (size_t)((b & 31) >> 3) * 128 +
+             (size_t)(b & 7) * 16;
+    };
+    // w (already scaled by 2^14) -> fp16 hi/lo octets -> next A operand (smem) and/or the bond image (global)
+    auto store_op16 = [&](int n0, const float(&w)[16], bool to_smem, uint8_t *irow) {
       uint4 hi, lo;
 #pragma unroll
       for (int o = 0; o < 2; ++o) {
@@ -157,19 +165,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
           *reinterpret_cast<uint4 *>(a_hi + row_off + (n0 / 8 + o) * 128) = hi;
           *reinterpret_cast<uint4 *>(a_lo + row_off + (n0 / 8 + o) * 128) = lo;
         }
-        if (vrow) {
-          *reinterpret_cast<uint4 *>(vrow + (size_t)(n0 / 8 + o) * 512) = hi;
-          *reinterpret_cast<uint4 *>(vrow + (size_t)chi * 64 + (size_t)(n0 / 8 + o) * 512) = lo;
+        if (irow) {
+          *reinterpret_cast<uint4 *>(irow + (size_t)(n0 / 8 + o) * 512) = hi;
+          *reinterpret_cast<uint4 *>(irow + (size_t)chi * 64 + (size_t)(n0 / 8 + o) * 512) = lo;
         }
       }
     };
-    // this sample's slot inside the V image of `bond`: [bond][b/32][plane][n/8][(b%32)/8][b%8][8 halves]
-    const bool img_ok = A.vimg != nullptr && (b0 + row) < (M.B + 31) / 32 * 32;
-    auto vimg_row = [&](int bond) -> uint8_t * {
-      if (!img_ok) return nullptr;
-      const long long bb = b0 + row;
-      return A.vimg + (size_t)bond * A.vimg_bond_bytes + (size_t)(bb >> 5) * chi * 128 + (size_t)((bb & 31) >> 3) * 128 +
-             (size_t)(bb & 7) * 16;
+    // 16 values of an image row: hi + lo (exact in fp32), still carrying the 2^14 image scale
+    auto load_img16 = [&](const uint8_t *irow, int n0, float(&v)[16]) {
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        const uint4 hi = *reinterpret_cast<const uint4 *>(irow + (size_t)(n0 / 8 + o) * 512);
+        const uint4 lo = *reinterpret_cast<const uint4 *>(irow + (size_t)chi * 64 + (size_t)(n0 / 8 + o) * 512);
+        const __half2 *h = reinterpret_cast<const __half2 *>(&hi), *l = reinterpret_cast<const __half2 *>(&lo);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 fh = __half22float2(h[j]), fl = __half22float2(l[j]);
+          v[8 * o + 2 * j] = fh.x + fl.x;
+          v[8 * o + 2 * j + 1] = fh.y + fl.y;
+        }
+      }
     };
     auto write_e0_operand = [&]() {
       for (int kc = 0; kc < chi / 8; ++kc) {
@@ -179,20 +194,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
         *reinterpret_cast<uint4 *>(a_lo + row_off + kc * 128) = z;
       }
     };
-    auto write_e0_env = [&](float *env) {
-      if (!env || !valid) return;
-      for (int n = 0; n < chi; n += 4)
-        *reinterpret_cast<float4 *>(env + (size_t)b * chi + n) = make_float4(n == 0 ? 1.f : 0.f, 0.f, 0.f, 0.f);
+    auto write_e0_image = [&](uint8_t *irow) {
+      if (!irow) return;
+      for (int o = 0; o < chi / 8; ++o) {
+        uint4 z = make_uint4(0, 0, 0, 0), zh = z;
+        if (o == 0 && valid) zh.x = 0x00007400u;
+        *reinterpret_cast<uint4 *>(irow + (size_t)o * 512) = zh;
+        *reinterpret_cast<uint4 *>(irow + (size_t)chi * 64 + (size_t)o * 512) = z;
+      }
     };
-    auto write_operand_from_row = [&](const float *rowp, float scale) {
+    auto write_operand_from_image = [&](const uint8_t *irow, float scale) {
       for (int n0 = 0; n0 < chi; n0 += 16) {
         float w[16];
+        if (irow) load_img16(irow, n0, w);
+        else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 v = *reinterpret_cast<const float4 *>(rowp + n0 + 4 * q);
-          w[4 * q] = v.x * scale; w[4 * q + 1] = v.y * scale; w[4 * q + 2] = v.z * scale; w[4 * q + 3] = v.w * scale;
+          for (int j = 0; j < 16; ++j) w[j] = 0.f;
         }
-        store_op16(n0, w);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w[j] *= scale;
+        store_op16(n0, w, true, nullptr);
       }
     };
     auto publish = [&]() {  // operand (and TMEM reads) done -> the MMA warp may start the next step
@@ -200,11 +221,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       ptx::fence_proxy_async();
       ptx::mbar_arrive(a_ready);
     };
-    // One chain step.  mode 0: forward (records delta, stashes F)   mode 1: adjoint (records wq/qmax, stashes G)
+    // One chain step.  mode 0: forward (records delta)   mode 1: adjoint (records wq/qmax).
     // `hexp` is the forward exponent sum (mode 0) or the running exponent h of the adjoint (mode 1).
-    // next_op: 0 = none, 1 = the normalised vector, 2 = the boundary vector e0.
-    auto chain_step = [&](int site, int kw, const float *ph_in, float *env, int mode, int &hexp, int next_op,
-                          uint8_t *vrow) {
+    // next_op: 0 = none, 1 = the normalised vector, 2 = the boundary vector e0.  irow: image slot of the output bond.
+    auto chain_step = [&](int site, int kw, const float *ph_in, int mode, int &hexp, int next_op, uint8_t *irow) {
       float ph[D];  // registers (static indexing only)
 #pragma unroll
       for (int s = 0; s < D; ++s) ph[s] = ph_in[s];
@@ -212,6 +232,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       ptx::mbar_wait(acc_full, step & 1);
       ptx::tc_fence_after();
       float m = 0.f;
+      if (A.dbg & 4) m = 16384.f;
+      else
       for (int n0 = 0; n0 < chi; n0 += 16) {
         float t[D][16];
 #pragma unroll
@@ -229,6 +251,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       const bool nz = m > 0.f && valid;
       if (nz) frexpf(m, &e);
       const int dtrue = nz ? e - kTcKA - kw : 0;  // exponent in units of the true recurrence
+      if (A.dbg & 2) irow = nullptr;
       if (mode == 0) {
         hexp += dtrue;
         if (valid && M.exps) M.exps[(size_t)site * M.B + b] = dtrue;
@@ -244,30 +267,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
         if (lane == 0 && qm != INT_MIN) atomicMax(&A.qmax[site], qm);
         hexp += dtrue - dsite;
       }
-      const float nsc = valid ? ldexpf(1.f, -e) : 0.f;
-      for (int n0 = 0; n0 < chi; n0 += 16) {
-        float t[D][16];
+      const float nsc = valid ? ldexpf(1.f, kTcKA - e) : 0.f;  // normalise and apply the 2^14 operand/image scale
+      if (next_op == 1 || irow) {
+        for (int n0 = 0; n0 < chi; n0 += 16) {
+          float t[D][16];
 #pragma unroll
-        for (int s = 0; s < D; ++s) ptx::tmem_ld16(trow + (uint32_t)(s * chi + n0), t[s]);
-        ptx::tmem_ld_wait();
-        float w[16];
+          for (int s = 0; s < D; ++s) ptx::tmem_ld16(trow + (uint32_t)(s * chi + n0), t[s]);
+          ptx::tmem_ld_wait();
+          float w[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float o = ph[0] * t[0][j];
+          for (int j = 0; j < 16; ++j) {
+            float o = ph[0] * t[0][j];
 #pragma unroll
-          for (int s = 1; s < D; ++s) o = fmaf(ph[s], t[s][j], o);
-          w[j] = o * nsc;
-        }
-        if (env && valid) {
-          float *dst = env + (size_t)b * chi + n0;
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<float4 *>(dst + 4 * q) = make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-        }
-        if (next_op == 1 || vrow) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) w[j] *= ka;
-          store_op16(n0, w, next_op == 1, vrow);
+            for (int s = 1; s < D; ++s) o = fmaf(ph[s], t[s][j], o);
+            w[j] = o * nsc;
+          }
+          store_op16(n0, w, next_op == 1, irow);
         }
       }
       if (next_op == 2) write_e0_operand();
@@ -279,28 +294,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       // ---------------- forward program ----------------
       int esumR = 0, esumL = 0;
       write_e0_operand();
-      write_e0_env(mps_fenv(M, L));
-      write_e0_env(mps_fenv(M, 0));
-      if (uint8_t *vr = vimg_row(L)) {  // V image of the boundary vector (dA of site L-1 / of a class site at L-1)
-        for (int o = 0; o < chi / 8; ++o) {
-          uint4 z = make_uint4(0, 0, 0, 0), zh = z;
-          if (o == 0 && valid) zh.x = 0x00007400u;
-          *reinterpret_cast<uint4 *>(vr + (size_t)o * 512) = zh;
-          *reinterpret_cast<uint4 *>(vr + (size_t)chi * 64 + (size_t)o * 512) = z;
-        }
-      }
+      write_e0_image(img_row(A.fimg, L));
+      write_e0_image(img_row(A.fimg, 0));
       publish();
       for (int i = 0; i < nR; ++i) {
         const int site = L - 1 - i;
         float ph[kMaxPhys];
         embed_site(M.emb, valid ? M.x[bs * L + site] : 0.5f, ph);
-        chain_step(site, A.kW[mps_slab(M, site)], ph, mps_fenv(M, site), 0, esumR, i == nR - 1 ? 2 : 1, vimg_row(site));
+        chain_step(site, A.kW[mps_slab(M, site)], ph, 0, esumR, i == nR - 1 ? 2 : 1, img_row(A.fimg, site));
       }
       for (int i = 0; i < nL; ++i) {
         const int site = i;
         float ph[kMaxPhys];
         embed_site(M.emb, valid ? M.x[bs * L + site] : 0.5f, ph);
-        chain_step(site, A.kW[mps_slab(M, site)], ph, mps_fenv(M, site + 1), 0, esumL, 1, nullptr);
+        chain_step(site, A.kW[mps_slab(M, site)], ph, 0, esumL, 1, img_row(A.fimg, site + 1));
       }
       // ---------------- class site + head ----------------
       float phc[D];
@@ -310,8 +317,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
 #pragma unroll
         for (int s = 0; s < D; ++s) phc[s] = phl[s];
       }
-      const float *fr = mps_fenv(M, c + 1) + bs * chi;  // this thread wrote that row itself
-      const float ysc = ldexpf(1.f, -(kTcKA + A.kW[c]));
+      const uint8_t *fr = img_row(A.fimg, c + 1);  // this thread wrote that row itself (image scale 2^14)
+      const float ysc = ldexpf(1.f, -(2 * kTcKA + A.kW[c]));
       float y[kMaxOut];
       for (int k = 0; k < C; ++k) {
         ptx::mbar_wait(acc_full, step & 1);
@@ -322,10 +329,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
 #pragma unroll
           for (int s = 0; s < D; ++s) ptx::tmem_ld16(trow + (uint32_t)(s * chi + n0), t[s]);
           float f[16];
+          if (fr) load_img16(fr, n0, f);
+          else {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 v = *reinterpret_cast<const float4 *>(fr + n0 + 4 * q);
-            f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w;
+            for (int j = 0; j < 16; ++j) f[j] = 0.f;
           }
           ptx::tmem_ld_wait();
 #pragma unroll
@@ -397,9 +404,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
         for (int k = 0; k < C; ++k) M.dy[(size_t)b * C + k] = dy[k];
         if (qm != INT_MIN) atomicMax(A.qmaxc, qm);
       }
-      const float *vrow = mps_fenv(M, half == 0 ? c + 1 : c) + bs * chi;
-      const float dsc = valid ? ldexpf(1.f, kTcKA - ed) : 0.f;  // |dy_k * dsc| < 2^14 and the row is normalised
-      write_operand_from_row(vrow, dy[0] * dsc);
+      const uint8_t *vrow = img_row(A.fimg, half == 0 ? c + 1 : c);  // normalised row * 2^14
+      const float dsc = valid ? ldexpf(1.f, -ed) : 0.f;              // |dy_k * dsc| < 1
+      write_operand_from_image(vrow, dy[0] * dsc);
       publish();
       int h = 0;
       const int jb = half == 0 ? 0 : L - 1;  // the boundary site: no chain step, but it has a gradient
@@ -407,14 +414,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
         if (k < C - 1) {
           ptx::mbar_wait(acc_full, step & 1);  // MMAs of step k have finished reading the operand
           ptx::tc_fence_after();
-          write_operand_from_row(vrow, dy[k + 1] * dsc);
+          write_operand_from_image(vrow, dy[k + 1] * dsc);
           publish();
           ++step;
         } else {
           // all C slabs accumulated: normalise -> seed G[c] / G[c+1]
-          int hs = 0;
-          float *genv = M.G + (size_t)(half == 0 ? c : c + 1) * M.B * chi;
-          // reuse the forward-mode bookkeeping of chain_step: hs receives (e - 14 - kWc)
+          uint8_t *girow = img_row(A.gimg, half == 0 ? c : c + 1);
           ptx::mbar_wait(acc_full, step & 1);
           ptx::tc_fence_after();
           float m = 0.f;
@@ -434,9 +439,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
           int e = 0;
           const bool nz = m > 0.f && valid;
           if (nz) frexpf(m, &e);
-          hs = nz ? e - kTcKA - A.kW[c] : 0;
-          h = hs + ed;  // G = normalised row * 2^h   (the operand carried dy * 2^-ed)
-          const float nsc = valid ? ldexpf(1.f, -e) : 0.f;
+          h = (nz ? e - kTcKA - A.kW[c] : 0) + ed;  // G = normalised row * 2^h (the operand carried dy * 2^-ed)
+          const float nsc = valid ? ldexpf(1.f, kTcKA - e) : 0.f;
           for (int n0 = 0; n0 < chi; n0 += 16) {
             float t[D][16];
 #pragma unroll
@@ -450,18 +454,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
               for (int s = 1; s < D; ++s) o = fmaf(phc[s], t[s][j], o);
               w[j] = o * nsc;
             }
-            if (valid) {
-              float *dst = genv + (size_t)b * chi + n0;
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<float4 *>(dst + 4 * q) = make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-            }
-            uint8_t *vr = half == 0 ? vimg_row(c) : nullptr;
-            if (nchain > 0 || vr) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) w[j] *= ka;
-              store_op16(n0, w, nchain > 0, vr);
-            }
+            store_op16(n0, w, nchain > 0, girow);
           }
           publish();
           ++step;
@@ -472,8 +465,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
         const int bond_out = half == 0 ? site : site + 1;
         float ph[kMaxPhys];
         embed_site(M.emb, valid ? M.x[bs * L + site] : 0.5f, ph);
-        chain_step(site, A.kW[mps_slab(M, site)], ph, M.G + (size_t)bond_out * M.B * chi, 1, h, i == nchain - 1 ? 0 : 1,
-                   half == 0 ? vimg_row(bond_out) : nullptr);
+        chain_step(site, A.kW[mps_slab(M, site)], ph, 1, h, i == nchain - 1 ? 0 : 1, img_row(A.gimg, bond_out));
       }
       // boundary site weights
       {
