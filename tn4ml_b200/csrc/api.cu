@@ -120,12 +120,23 @@ struct MpsPlan {
 static bool tc_supported(const tnb_problem *p) {
   if (p->kind != TNB_KIND_MPS || p->dtype != TNB_F32 || p->precision != TNB_PREC_TENSOR) return false;
   if (p->chi % 16 != 0 || p->chi < 32 || p->chi > 256) return false;
-  const int N = p->d * p->chi;
-  if (N > 512) return false;
+  if (p->d * p->chi > 512) return false;
   if (!(p->d == 2 || p->d == 3 || p->d == 4 || p->d == 6 || p->d == 8)) return false;
-  const int NH = (N + 255) / 256;
-  if (N % NH != 0 || (N / NH) % 16 != 0) return false;
   return true;
+}
+
+// Column chunks per chain step: the smallest NH dividing chi/16 whose chunk (D*chi/NH columns) fits one MMA (N <= 256).
+// TNB_TC_NH (environment) forces another legal split (measurement aid).
+static int tc_pick_nh(const tnb_problem *p) {
+  const int groups = p->chi / 16;
+  auto legal = [&](int nh) { return nh >= 1 && nh <= kTcMaxNH && groups % nh == 0 && p->d * p->chi / nh <= 256; };
+  if (const char *e = getenv("TNB_TC_NH")) {
+    const int nh = atoi(e);
+    if (legal(nh)) return nh;
+  }
+  for (int nh = 1; nh <= groups; ++nh)
+    if (legal(nh)) return nh;
+  return groups;
 }
 
 static MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
@@ -166,16 +177,17 @@ static MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
   P.tc = tc_supported(p) ? 1 : 0;
   if (P.tc) {
     P.tc_N = p->d * p->chi;
-    P.tc_NH = (P.tc_N + 255) / 256;
+    P.tc_NH = tc_pick_nh(p);
     P.tc_NMMA = P.tc_N / P.tc_NH;
-    P.tc_stage_bytes = 64u * P.tc_N;
-    P.tc_site_img = (size_t)(p->chi / 16) * P.tc_stage_bytes;
+    P.tc_stage_bytes = 64u * P.tc_NMMA;  // one K-slab (16 rows) of one column chunk, hi and lo planes
+    P.tc_site_img = (size_t)P.tc_NH * (p->chi / 16) * P.tc_stage_bytes;
     P.tc_cols = 32;
     while (P.tc_cols < P.tc_N) P.tc_cols <<= 1;
     const size_t a_bytes = (size_t)2 * kTcRows * p->chi * 2;
-    long ns = (long)((232448 - 1024 - (long)a_bytes) / (long)P.tc_stage_bytes);
-    P.tc_nstage = ns > 8 ? 8 : (int)ns;
-    P.tc_smem = a_bytes + (size_t)P.tc_nstage * P.tc_stage_bytes + 1024;
+    const size_t fixed = 4096 /* row exchange */ + 1024 /* barriers */;
+    long ns = (long)((232448 - (long)fixed - (long)a_bytes) / (long)P.tc_stage_bytes);
+    P.tc_nstage = ns > 12 ? 12 : (int)ns;
+    P.tc_smem = a_bytes + (size_t)P.tc_nstage * P.tc_stage_bytes + fixed;
     if (P.tc_nstage < 2) P.tc = 0;
   }
   if (P.tc) {
@@ -231,18 +243,24 @@ static void fill_tc_args(const MpsPlan &P, void *ws, const MpsArgs<float> &M, Tc
   T.img_bond_bytes = P.img_bond_bytes;
   T.img_stash = M.stash;
   T.qmaxc = T.qmax + M.L;
-  { const char *dbg = getenv("TNB_DEBUG"); T.dbg = dbg ? atoi(dbg) : 0; }
   T.N = P.tc_N; T.NH = P.tc_NH; T.NMMA = P.tc_NMMA; T.nstage = P.tc_nstage; T.tmem_cols = P.tc_cols;
   T.stage_bytes = P.tc_stage_bytes; T.site_img_bytes = P.tc_site_img;
 }
 
-template <int D> static cudaError_t tc_set_attr() {
+template <int D, int SLOTS, int KEEP> static cudaError_t tc_set_attr() {
   static std::once_flag once;
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [] {
-    err = cudaFuncSetAttribute(tc_chain_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    err = cudaFuncSetAttribute(tc_chain_kernel<D, SLOTS, KEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   });
   return err;
+}
+
+template <int D, int SLOTS, int KEEP>
+static cudaError_t tc_launch_one(dim3 grid, size_t smem, const TcArgs &T, int adjoint, cudaStream_t st) {
+  cudaError_t e = tc_set_attr<D, SLOTS, KEEP>();
+  if (e == cudaSuccess) tc_chain_kernel<D, SLOTS, KEEP><<<grid, kTcThreads, smem, st>>>(T, adjoint);
+  return e;
 }
 
 // launch the tcgen05 sweep (forward environments or adjoint chains)
@@ -250,17 +268,16 @@ static int tc_launch_sweep(const tnb_problem *p, const MpsPlan &P, const TcArgs 
                            cudaStream_t st) {
   dim3 grid((unsigned)((B + kTcRows - 1) / kTcRows), adjoint ? 2 : 1);
   cudaError_t e = cudaSuccess;
-#define TNB_TC_CASE(DD)                                                                     \
-  case DD:                                                                                   \
-    e = tc_set_attr<DD>();                                                                   \
-    if (e == cudaSuccess) tc_chain_kernel<DD><<<grid, kTcThreads, P.tc_smem, st>>>(T, adjoint); \
-    break;
+  const bool wide = p->chi > 128;  // 16-column groups per epilogue thread: 4 (chi <= 256) or 2 (chi <= 128)
   prof_begin(st);
   switch (p->d) {
-    TNB_TC_CASE(2) TNB_TC_CASE(3) TNB_TC_CASE(4) TNB_TC_CASE(6) TNB_TC_CASE(8)
+    case 2: e = wide ? tc_launch_one<2, 4, 3>(grid, P.tc_smem, T, adjoint, st) : tc_launch_one<2, 2, 2>(grid, P.tc_smem, T, adjoint, st); break;
+    case 3: e = wide ? tc_launch_one<3, 4, 3>(grid, P.tc_smem, T, adjoint, st) : tc_launch_one<3, 2, 2>(grid, P.tc_smem, T, adjoint, st); break;
+    case 4: e = tc_launch_one<4, 2, 2>(grid, P.tc_smem, T, adjoint, st); break;
+    case 6: e = tc_launch_one<6, 2, 2>(grid, P.tc_smem, T, adjoint, st); break;
+    case 8: e = tc_launch_one<8, 2, 2>(grid, P.tc_smem, T, adjoint, st); break;
     default: return fail("tensor path: unsupported physical dimension %d", p->d);
   }
-#undef TNB_TC_CASE
   if (e != cudaSuccess) return fail("cudaFuncSetAttribute(tc_chain): %s", cudaGetErrorString(e));
   TNB_LAUNCH_CHECK(adjoint ? "tc_chain_kernel(adj)" : "tc_chain_kernel(fwd)");
   return 0;
@@ -309,7 +326,7 @@ static int mps_forward_t(const tnb_problem *p, const MpsPlan &P, long long B, co
       if (ib > 148 * 32) ib = 148 * 32;
       prof_begin(st);
       tc_image_kernel<<<ib, 256, 0, st>>>((const float *)params, Tc.kW, (uint8_t *)Tc.img_n, (uint8_t *)Tc.img_t, p->L,
-                                          p->chi, p->d, p->n_out, p->out_site);
+                                          p->chi, p->d, p->n_out, p->out_site, P.tc_NH);
       TNB_LAUNCH_CHECK("tc_image_kernel");
       return tc_launch_sweep(p, P, Tc, B, 0, st);
     }

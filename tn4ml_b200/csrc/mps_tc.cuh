@@ -16,8 +16,8 @@
 // shared-memory operand layout (canonical K-major, no swizzle), so one 1-D bulk async copy
 // (TMA engine) moves a whole pipeline stage and completes on an mbarrier.
 //
-// Warp roles (192 threads): warps 0-3 epilogue (thread == sample row == TMEM lane),
-// warp 4 bulk-copy producer, warp 5 TMEM owner + MMA issuer.
+// Warp roles of the chain kernel (576 threads; mps_tc_chain.cuh): warps 0-15 epilogue (four threads per
+// sample row == TMEM lane), warp 16 TMEM owner + MMA issuer, warp 17 bulk-copy producer.
 #pragma once
 #include <cuda_fp16.h>
 #include <limits.h>
@@ -29,11 +29,14 @@ namespace tnb {
 
 constexpr int kTcRows = 128;   // samples per CTA == TMEM lanes
 constexpr int kTcKA = 14;      // A operand pre-scale: |v| < 1  ->  |v * 2^14| < 2^14 (fp16 max 65504)
-constexpr int kTcThreads = 192;
+constexpr int kTcEpiWarps = 16;                      // 4 lane quarters x 4 column groups
+constexpr int kTcMmaWarp = kTcEpiWarps;              // + 1: the bulk-copy producer warp
+constexpr int kTcThreads = (kTcEpiWarps + 2) * 32;
+constexpr int kTcMaxNH = 16;                         // column chunks per step (chi / 16 at most)
 
 struct TcArgs {
   MpsArgs<float> M;
-  const uint8_t *img_n;  // stage images, normal direction      [slab][chi/16][2 planes][N*32 B]
+  const uint8_t *img_n;  // stage images, normal direction      [slab][NH chunks][chi/16][2 planes][NMMA*32 B]
   const uint8_t *img_t;  // stage images, transposed direction
   const int *kW;         // per-slab weight pre-scale exponent
   float *wq;             // adjoint: phi_s[b] * 2^q[b] per (site, s, b): per-sample weight of the dA GEMM
@@ -46,8 +49,7 @@ struct TcArgs {
   int img_stash;         // 1: every bond has a slot; 0: forward-only, a single slot for bond c+1
   float *wqc;            // adjoint: phi_s[b] * dLoss/dy'_k[b] per ((s,k), b): weights of the class-site dA GEMM
   int *qmaxc;            // adjoint: max exponent of wqc
-  int N, NH, NMMA, nstage, tmem_cols;
-  int dbg;               // measurement switches (TNB_DEBUG env): 1 = no fp32 stash stores, 2 = no V images, 4 = skip max pass
+  int N, NH, NMMA, nstage, tmem_cols;  // N = D*chi accumulator columns = NH chunks of NMMA (n in [h*chi/NH, ..) x all s)
   uint32_t stage_bytes;
   size_t site_img_bytes;
 };
@@ -86,21 +88,24 @@ __global__ void tc_classmin_kernel(int *__restrict__ kW, int c, int C) {
   for (int k = threadIdx.x; k < C; k += 32) kW[c + k] = m;
 }
 
-// one thread per (slab, n', k-octet): 8 weights -> 16 B of hi and 16 B of lo, both directions
+// one thread per (slab, n', k-octet): 8 weights -> 16 B of hi and 16 B of lo, both directions.
+// Stage (h, ks) of a slab holds the K-slab ks of column chunk h: columns n'' = s*chi_h + (n - h*chi_h).
 __global__ void tc_image_kernel(const float *__restrict__ params, const int *__restrict__ kW, uint8_t *__restrict__ img_n,
-                                uint8_t *__restrict__ img_t, int L, int chi, int D, int C, int c) {
+                                uint8_t *__restrict__ img_t, int L, int chi, int D, int C, int c, int NH) {
   const int nslab = L - 1 + C;
-  const int N = D * chi, KO = chi / 8;
+  const int N = D * chi, KO = chi / 8, KS = chi / 16;
+  const int chi_h = chi / NH, NMMA = N / NH;
   const size_t per_slab = (size_t)N * KO;
   const size_t total = per_slab * nslab;
-  const uint32_t stage_bytes = 64u * N;
-  const size_t site_img_bytes = (size_t)(chi / 16) * stage_bytes;
+  const uint32_t stage_bytes = 64u * NMMA;
+  const size_t site_img_bytes = (size_t)NH * KS * stage_bytes;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int slab = (int)(i / per_slab);
     const size_t rem = i - (size_t)slab * per_slab;
     const int ko = (int)(rem / N);       // k octet: k = ko*8 .. ko*8+7
     const int np = (int)(rem % N);       // n' = s*chi + n
     const int s = np / chi, n = np - s * chi;
+    const int h = n / chi_h, npp = s * chi_h + (n - h * chi_h);
     int site, o, nj;
     if (slab < c) { site = slab; o = 0; nj = 1; }
     else if (slab < c + C) { site = c; o = slab - c; nj = C; }
@@ -108,8 +113,8 @@ __global__ void tc_image_kernel(const float *__restrict__ params, const int *__r
     const size_t site_off = (size_t)site * chi * chi * D + (site > c ? (size_t)chi * chi * D * (C - 1) : 0);
     const float sc = ldexpf(1.f, kW[slab]);
     const int ks = ko / 2, kc = ko & 1;
-    const size_t off = (size_t)slab * site_img_bytes + (size_t)ks * stage_bytes + (size_t)(np / 8) * 256 + kc * 128 +
-                       (np % 8) * 16;
+    const size_t off = (size_t)slab * site_img_bytes + ((size_t)h * KS + ks) * stage_bytes + (size_t)(npp / 8) * 256 +
+                       kc * 128 + (npp % 8) * 16;
 #pragma unroll
     for (int dir = 0; dir < 2; ++dir) {
       __half hi[8], lo[8];
@@ -123,7 +128,7 @@ __global__ void tc_image_kernel(const float *__restrict__ params, const int *__r
       }
       uint8_t *base = (dir == 0 ? img_n : img_t) + off;
       *reinterpret_cast<uint4 *>(base) = *reinterpret_cast<const uint4 *>(hi);
-      *reinterpret_cast<uint4 *>(base + (size_t)N * 32) = *reinterpret_cast<const uint4 *>(lo);
+      *reinterpret_cast<uint4 *>(base + (size_t)NMMA * 32) = *reinterpret_cast<const uint4 *>(lo);
     }
   }
 }

@@ -1,9 +1,9 @@
 // K2 + K3 (tensor-core family): the whole per-sample chain on tcgen05 / TMEM.
 //
-// One CTA owns 128 samples (thread == sample row == TMEM lane in the epilogue warps) and runs a
-// "program" of MMA steps; every step is one GEMM  acc[128, D*chi] = operand[128, chi] x W[chi, D*chi]
-// whose B operand is a pre-split weight image streamed by 1-D bulk copies, followed by an epilogue
-// that turns the accumulator into the next A operand without leaving the SM.
+// One CTA owns 128 samples (sample row == TMEM lane) and runs a "program" of MMA steps; every step
+// is one GEMM  acc[128, D*chi] = operand[128, chi] x W[chi, D*chi]  whose B operand is a pre-split
+// weight image streamed by 1-D bulk copies, followed by an epilogue that turns the accumulator into
+// the next A operand without leaving the SM.
 //
 //   forward (grid.y == 1):   right chain  (sites L-1 .. c+1, transposed images)
 //                            left chain   (sites 0 .. c-1)
@@ -15,6 +15,21 @@
 //                            adjoint chain towards the boundary, recording the per-sample weights
 //                            wq / qmax of the dA GEMM (mps_tc.cuh, tc_da_kernel).
 //
+// The N = D*chi accumulator columns are issued as NH column chunks of NMMA = D*chi/NH columns;
+// chunk h holds the outputs n in [h*chi/NH, (h+1)*chi/NH) for every physical index s
+// (TMEM column h*NMMA + s*chi/NH + n - h*chi/NH) and has its own commit barrier, so the epilogue
+// of chunk h runs underneath the MMAs of chunk h+1.
+//
+// Warp roles (576 threads): warps 0-15 epilogue, warp 16 TMEM owner + MMA issuer, warp 17 bulk-copy
+// producer.  A TMEM lane quarter is only visible to warps with warp % 4 == quarter, so the four
+// warps {q, q+4, q+8, q+12} share the 32 sample rows of quarter q and split a row's 16-column
+// groups between them (group j belongs to warp group j % 4).  Every thread keeps its <= 64 outputs
+// in registers: ONE pass over TMEM produces the phi-contracted row, the row maximum is combined
+// through a 4 KB shared-memory exchange and a 128-thread named barrier per lane quarter, and the
+// normalised fp16 hi/lo operand is written straight from registers.  (With one epilogue warp per
+// scheduler and two TMEM passes the kernel was bound by the TMEM load latency: ncu 14 % issue
+// active, tensor pipe 43 %.)
+//
 // Environments are carried as (mantissa row, integer exponent): every epilogue renormalises the
 // row to max-abs in [0.5, 1) by an exact power of two, which is also what keeps the fp16 hi/lo
 // operand split inside the fp16 range (see mps_tc.cuh for the fp16x3 arithmetic).
@@ -23,7 +38,34 @@
 
 namespace tnb {
 
+// acc columns -> o[j] = sum_s ph[s] * acc[col + s*cstride + j], j < 16   (one 16-column group).
+// The s = 0 slice is loaded straight into o (registers are the scarce resource here: 64 outputs per thread stay live).
 template <int D>
+__device__ __forceinline__ void tc_combine16(uint32_t col, uint32_t cstride, const float (&ph)[D], float (&o)[16]) {
+  ptx::tmem_ld16(col, o);
+  if constexpr (D == 1) {
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] *= ph[0];
+  } else {
+    float t[16];
+    ptx::tmem_ld16(col + cstride, t);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] = fmaf(ph[1], t[j], ph[0] * o[j]);
+#pragma unroll
+    for (int s = 2; s < D; ++s) {
+      ptx::tmem_ld16(col + (uint32_t)s * cstride, t);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = fmaf(ph[s], t[j], o[j]);
+    }
+  }
+}
+
+// SLOTS: 16-column groups per epilogue thread; the first KEEP of them stay in registers between the maximum and the
+// normalisation, the others are read from TMEM a second time (576 threads leave 96 registers per thread).
+template <int D, int SLOTS, int KEEP>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int adjoint) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const MpsArgs<float> &M = A.M;
@@ -32,6 +74,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
   const int half = blockIdx.y;
   const long long b0 = (long long)blockIdx.x * kTcRows;
   const int nR = L - 1 - c, nL = c;
+  const int NH = A.NH, chi_h = chi / NH;
 
   // ---- the step program (identical in every warp role) ----
   int nseed, nchain, total;
@@ -64,8 +107,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
   uint8_t *a_hi = smem;
   uint8_t *a_lo = smem + a_plane;
   uint8_t *stages = smem + 2 * a_plane;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(stages + (size_t)A.nstage * A.stage_bytes);
-  uint64_t *full = bars, *empty = bars + A.nstage, *acc_full = bars + 2 * A.nstage, *a_ready = acc_full + 1;
+  float *xch = reinterpret_cast<float *>(stages + (size_t)A.nstage * A.stage_bytes);  // [2][4][128]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(xch + 2 * 4 * kTcRows);
+  uint64_t *full = bars, *empty = bars + A.nstage, *acc_full = bars + 2 * A.nstage, *a_ready = acc_full + kTcMaxNH;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_ready + 1);
 
   if (tid == 0) {
@@ -73,11 +117,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       ptx::mbar_init(&full[i], 1);
       ptx::mbar_init(&empty[i], 1);
     }
-    ptx::mbar_init(acc_full, 1);
-    ptx::mbar_init(a_ready, kTcRows);
+    for (int h = 0; h < NH; ++h) ptx::mbar_init(&acc_full[h], 1);
+    ptx::mbar_init(a_ready, kTcEpiWarps);
     ptx::fence_mbar_init();
   }
-  if (warp == 5) {
+  if (warp == kTcMmaWarp) {
     ptx::tmem_alloc(tmem_slot, (uint32_t)A.tmem_cols);
     ptx::tmem_relinquish();
   }
@@ -87,64 +131,81 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
   const uint32_t tmem_base = *tmem_slot;
   const int KS = chi / 16;
 
-  if (warp == 4) {
-    // ===== producer: one bulk async copy per pipeline stage =====
+  if (warp == kTcMmaWarp + 1) {
+    // ===== producer: one bulk async copy per pipeline stage (= one K-slab of one column chunk) =====
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      const int per_step = NH * KS;
       for (int step = 0; step < total; ++step) {
         const uint8_t *img = step_image(step);
-        for (int ks = 0; ks < KS; ++ks) {
+        for (int hk = 0; hk < per_step; ++hk) {
           ptx::mbar_wait(&empty[stage], phase ^ 1);
           ptx::mbar_expect_tx(&full[stage], A.stage_bytes);
-          ptx::bulk_g2s(stages + (size_t)stage * A.stage_bytes, img + (size_t)ks * A.stage_bytes, A.stage_bytes,
+          ptx::bulk_g2s(stages + (size_t)stage * A.stage_bytes, img + (size_t)hk * A.stage_bytes, A.stage_bytes,
                         &full[stage]);
           if (++stage == A.nstage) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kTcMmaWarp) {
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = ptx::idesc_f16_f32(kTcRows, A.NMMA);
       const uint32_t a_hi_s = ptx::smem_u32(a_hi), a_lo_s = ptx::smem_u32(a_lo);
       const uint32_t sbo_a = (uint32_t)chi * 16;
+      const uint32_t lo_plane = (uint32_t)A.NMMA * 32;
       int stage = 0;
       uint32_t phase = 0;
       for (int step = 0; step < total; ++step) {
         const bool accum_step = adjoint && step > 0 && step < nseed;  // seed steps accumulate over k
         ptx::mbar_wait(a_ready, step & 1);
         ptx::tc_fence_after();
-        for (int ks = 0; ks < KS; ++ks) {
-          ptx::mbar_wait(&full[stage], phase);
-          ptx::tc_fence_after();
-          const uint64_t da_hi = ptx::smem_desc_kmajor(a_hi_s + ks * 256, 128, sbo_a);
-          const uint64_t da_lo = ptx::smem_desc_kmajor(a_lo_s + ks * 256, 128, sbo_a);
-          const uint32_t st = ptx::smem_u32(stages + (size_t)stage * A.stage_bytes);
-          for (int h = 0; h < A.NH; ++h) {
-            const uint32_t boff = (uint32_t)h * (A.NMMA / 8) * 256;
-            const uint64_t db_hi = ptx::smem_desc_kmajor(st + boff, 128, 256);
-            const uint64_t db_lo = ptx::smem_desc_kmajor(st + (uint32_t)A.N * 32 + boff, 128, 256);
-            const uint32_t d = tmem_base + (uint32_t)h * A.NMMA;
+        for (int h = 0; h < NH; ++h) {
+          const uint32_t d = tmem_base + (uint32_t)h * A.NMMA;
+          for (int ks = 0; ks < KS; ++ks) {
+            ptx::mbar_wait(&full[stage], phase);
+            ptx::tc_fence_after();
+            const uint64_t da_hi = ptx::smem_desc_kmajor(a_hi_s + ks * 256, 128, sbo_a);
+            const uint64_t da_lo = ptx::smem_desc_kmajor(a_lo_s + ks * 256, 128, sbo_a);
+            const uint32_t st = ptx::smem_u32(stages + (size_t)stage * A.stage_bytes);
+            const uint64_t db_hi = ptx::smem_desc_kmajor(st, 128, 256);
+            const uint64_t db_lo = ptx::smem_desc_kmajor(st + lo_plane, 128, 256);
             ptx::mma_f16(d, da_hi, db_hi, idesc, (ks > 0 || accum_step) ? 1u : 0u);
             ptx::mma_f16(d, da_lo, db_hi, idesc, 1u);
             ptx::mma_f16(d, da_hi, db_lo, idesc, 1u);
+            ptx::mma_commit(&empty[stage]);
+            if (++stage == A.nstage) { stage = 0; phase ^= 1; }
           }
-          ptx::mma_commit(&empty[stage]);
-          if (++stage == A.nstage) { stage = 0; phase ^= 1; }
+          ptx::mma_commit(&acc_full[h]);
         }
-        ptx::mma_commit(acc_full);
       }
     }
   } else {
-    // ===== epilogue: thread == sample row == TMEM lane =====
-    const int row = tid;
+    // ===== epilogue: 4 threads per sample row (one per warp group), each owning every 4th 16-column group =====
+    const int lq = warp & 3, grp = warp >> 2;
+    const int row = lq * 32 + lane;
     const long long b = b0 + row;
     const bool valid = b < M.B;
+    const bool lead = grp == 0;  // the thread of the row that does the per-sample bookkeeping
     const size_t bs = (size_t)(valid ? b : 0);
-    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t trow = tmem_base + ((uint32_t)(lq * 32) << 16);
     const uint32_t row_off = (uint32_t)(row >> 3) * (uint32_t)chi * 16 + (uint32_t)(row & 7) * 16;
+    const int nch = chi / 16;
     int step = 0;
+
+    // my 16-column groups: j = 4*i + grp (i < SLOTS); chunk index and first TMEM column of each
+    bool son[SLOTS];
+    int sh[SLOTS];
+    uint32_t scol[SLOTS];
+#pragma unroll
+    for (int i = 0; i < SLOTS; ++i) {
+      const int j = 4 * i + grp;
+      son[i] = j < nch;
+      const int n0 = 16 * j;
+      sh[i] = son[i] ? n0 / chi_h : 0;
+      scol[i] = trow + (uint32_t)(sh[i] * A.NMMA + (n0 - sh[i] * chi_h));
+    }
 
     // this sample's 16-byte slot inside the image of `bond` (see TcArgs): consecutive samples of a warp
     // are consecutive 16-byte units, so every warp-wide image store/load is 512 contiguous bytes
@@ -156,136 +217,170 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
              (size_t)(b & 7) * 16;
     };
     // w (already scaled by 2^14) -> fp16 hi/lo octets -> next A operand (smem) and/or the bond image (global)
-    auto store_op16 = [&](int n0, const float(&w)[16], bool to_smem, uint8_t *irow) {
+    auto store_op16 = [&](int j, const float(&w)[16], bool to_smem, uint8_t *irow) {
       uint4 hi, lo;
 #pragma unroll
       for (int o = 0; o < 2; ++o) {
         split8(w + 8 * o, hi, lo);
         if (to_smem) {
-          *reinterpret_cast<uint4 *>(a_hi + row_off + (n0 / 8 + o) * 128) = hi;
-          *reinterpret_cast<uint4 *>(a_lo + row_off + (n0 / 8 + o) * 128) = lo;
+          *reinterpret_cast<uint4 *>(a_hi + row_off + (2 * j + o) * 128) = hi;
+          *reinterpret_cast<uint4 *>(a_lo + row_off + (2 * j + o) * 128) = lo;
         }
         if (irow) {
-          *reinterpret_cast<uint4 *>(irow + (size_t)(n0 / 8 + o) * 512) = hi;
-          *reinterpret_cast<uint4 *>(irow + (size_t)chi * 64 + (size_t)(n0 / 8 + o) * 512) = lo;
+          *reinterpret_cast<uint4 *>(irow + (size_t)(2 * j + o) * 512) = hi;
+          *reinterpret_cast<uint4 *>(irow + (size_t)chi * 64 + (size_t)(2 * j + o) * 512) = lo;
         }
       }
     };
     // 16 values of an image row: hi + lo (exact in fp32), still carrying the 2^14 image scale
-    auto load_img16 = [&](const uint8_t *irow, int n0, float(&v)[16]) {
+    auto load_img16 = [&](const uint8_t *irow, int j, float(&v)[16]) {
 #pragma unroll
       for (int o = 0; o < 2; ++o) {
-        const uint4 hi = *reinterpret_cast<const uint4 *>(irow + (size_t)(n0 / 8 + o) * 512);
-        const uint4 lo = *reinterpret_cast<const uint4 *>(irow + (size_t)chi * 64 + (size_t)(n0 / 8 + o) * 512);
+        const uint4 hi = *reinterpret_cast<const uint4 *>(irow + (size_t)(2 * j + o) * 512);
+        const uint4 lo = *reinterpret_cast<const uint4 *>(irow + (size_t)chi * 64 + (size_t)(2 * j + o) * 512);
         const __half2 *h = reinterpret_cast<const __half2 *>(&hi), *l = reinterpret_cast<const __half2 *>(&lo);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 fh = __half22float2(h[j]), fl = __half22float2(l[j]);
-          v[8 * o + 2 * j] = fh.x + fl.x;
-          v[8 * o + 2 * j + 1] = fh.y + fl.y;
+        for (int q = 0; q < 4; ++q) {
+          const float2 fh = __half22float2(h[q]), fl = __half22float2(l[q]);
+          v[8 * o + 2 * q] = fh.x + fl.x;
+          v[8 * o + 2 * q + 1] = fh.y + fl.y;
         }
       }
     };
-    auto write_e0_operand = [&]() {
-      for (int kc = 0; kc < chi / 8; ++kc) {
-        uint4 z = make_uint4(0, 0, 0, 0), zh = z;
-        if (kc == 0) zh.x = 0x00007400u;  // fp16(2^14) in element 0
-        *reinterpret_cast<uint4 *>(a_hi + row_off + kc * 128) = zh;
-        *reinterpret_cast<uint4 *>(a_lo + row_off + kc * 128) = z;
-      }
-    };
-    auto write_e0_image = [&](uint8_t *irow) {
-      if (!irow) return;
-      for (int o = 0; o < chi / 8; ++o) {
-        uint4 z = make_uint4(0, 0, 0, 0), zh = z;
-        if (o == 0 && valid) zh.x = 0x00007400u;
-        *reinterpret_cast<uint4 *>(irow + (size_t)o * 512) = zh;
-        *reinterpret_cast<uint4 *>(irow + (size_t)chi * 64 + (size_t)o * 512) = z;
+    // boundary vector e0 * 2^14 as the A operand / as a bond image (my column groups only)
+    auto write_e0 = [&](bool to_smem, uint8_t *irow) {
+#pragma unroll
+      for (int i = 0; i < SLOTS; ++i) {
+        if (!son[i]) continue;
+        const int j = 4 * i + grp;
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          uint4 z = make_uint4(0, 0, 0, 0), zh = z;
+          if (2 * j + o == 0) zh.x = 0x00007400u;  // fp16(2^14) in element 0
+          if (to_smem) {
+            *reinterpret_cast<uint4 *>(a_hi + row_off + (2 * j + o) * 128) = zh;
+            *reinterpret_cast<uint4 *>(a_lo + row_off + (2 * j + o) * 128) = z;
+          }
+          if (irow) {
+            *reinterpret_cast<uint4 *>(irow + (size_t)(2 * j + o) * 512) = valid ? zh : z;
+            *reinterpret_cast<uint4 *>(irow + (size_t)chi * 64 + (size_t)(2 * j + o) * 512) = z;
+          }
+        }
       }
     };
     auto write_operand_from_image = [&](const uint8_t *irow, float scale) {
-      for (int n0 = 0; n0 < chi; n0 += 16) {
+#pragma unroll
+      for (int i = 0; i < SLOTS; ++i) {
+        if (!son[i]) continue;
+        const int j = 4 * i + grp;
         float w[16];
-        if (irow) load_img16(irow, n0, w);
+        if (irow) load_img16(irow, j, w);
         else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) w[j] = 0.f;
+          for (int q = 0; q < 16; ++q) w[q] = 0.f;
         }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) w[j] *= scale;
-        store_op16(n0, w, true, nullptr);
+        for (int q = 0; q < 16; ++q) w[q] *= scale;
+        store_op16(j, w, true, nullptr);
       }
     };
     auto publish = [&]() {  // operand (and TMEM reads) done -> the MMA warp may start the next step
       ptx::tc_fence_before();
       ptx::fence_proxy_async();
-      ptx::mbar_arrive(a_ready);
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(a_ready);
+    };
+    // combine one float per thread across the 4 threads of a row (through smem, fixed order)
+    auto row_exchange = [&](float v) -> const float * {
+      float *x = xch + (step & 1) * (4 * kTcRows);
+      x[grp * kTcRows + row] = v;
+      ptx::named_bar_sync(1 + lq, 4 * 32);
+      return x + row;
+    };
+    // wait for the column chunks holding my groups and contract them with phi: vals[i][*] (i < KEEP), row max of my part
+    auto gather = [&](const float(&ph)[D], float(&vals)[KEEP][16]) -> float {
+      float m = 0.f;
+      int hprev = -1;
+#pragma unroll
+      for (int i = 0; i < SLOTS; ++i) {
+        if (!son[i]) continue;
+        if (sh[i] != hprev) {
+          ptx::mbar_wait(&acc_full[sh[i]], step & 1);
+          ptx::tc_fence_after();
+          hprev = sh[i];
+        }
+        if (i < KEEP) {
+          tc_combine16<D>(scol[i], (uint32_t)chi_h, ph, vals[i < KEEP ? i : 0]);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) m = fmaxf(m, fabsf(vals[i < KEEP ? i : 0][q]));
+        } else {
+          float o[16];
+          tc_combine16<D>(scol[i], (uint32_t)chi_h, ph, o);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) m = fmaxf(m, fabsf(o[q]));
+        }
+      }
+      if (hprev != NH - 1) {  // every thread has seen the whole step complete before it publishes
+        ptx::mbar_wait(&acc_full[NH - 1], step & 1);
+        ptx::tc_fence_after();
+      }
+      return m;
+    };
+    auto normalise_store = [&](const float(&ph)[D], float(&vals)[KEEP][16], float nsc, bool to_smem, uint8_t *irow) {
+#pragma unroll
+      for (int i = 0; i < SLOTS; ++i) {
+        if (!son[i]) continue;
+        if (i < KEEP) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) vals[i < KEEP ? i : 0][q] *= nsc;
+          store_op16(4 * i + grp, vals[i < KEEP ? i : 0], to_smem, irow);
+        } else {
+          float o[16];
+          tc_combine16<D>(scol[i], (uint32_t)chi_h, ph, o);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) o[q] *= nsc;
+          store_op16(4 * i + grp, o, to_smem, irow);
+        }
+      }
     };
     // One chain step.  mode 0: forward (records delta)   mode 1: adjoint (records wq/qmax).
-    // `hexp` is the forward exponent sum (mode 0) or the running exponent h of the adjoint (mode 1).
+    // `hexp` is the forward exponent sum (mode 0) or the running exponent h of the adjoint (mode 1); lead thread only.
     // next_op: 0 = none, 1 = the normalised vector, 2 = the boundary vector e0.  irow: image slot of the output bond.
     auto chain_step = [&](int site, int kw, const float *ph_in, int mode, int &hexp, int next_op, uint8_t *irow) {
       float ph[D];  // registers (static indexing only)
 #pragma unroll
       for (int s = 0; s < D; ++s) ph[s] = ph_in[s];
-      const int dsite = (mode == 1 && valid) ? M.exps[(size_t)site * M.B + b] : 0;
-      ptx::mbar_wait(acc_full, step & 1);
-      ptx::tc_fence_after();
-      float m = 0.f;
-      if (A.dbg & 4) m = 16384.f;
-      else
-      for (int n0 = 0; n0 < chi; n0 += 16) {
-        float t[D][16];
-#pragma unroll
-        for (int s = 0; s < D; ++s) ptx::tmem_ld16(trow + (uint32_t)(s * chi + n0), t[s]);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float o = ph[0] * t[0][j];
-#pragma unroll
-          for (int s = 1; s < D; ++s) o = fmaf(ph[s], t[s][j], o);
-          m = fmaxf(m, fabsf(o));
-        }
+      const int dsite = (mode == 1 && valid && lead) ? M.exps[(size_t)site * M.B + b] : 0;
+      float vals[KEEP][16];
+      float m = gather(ph, vals);
+      {
+        const float *x = row_exchange(m);
+        m = fmaxf(fmaxf(x[0], x[kTcRows]), fmaxf(x[2 * kTcRows], x[3 * kTcRows]));
       }
       int e = 0;
       const bool nz = m > 0.f && valid;
       if (nz) frexpf(m, &e);
-      const int dtrue = nz ? e - kTcKA - kw : 0;  // exponent in units of the true recurrence
-      if (A.dbg & 2) irow = nullptr;
-      if (mode == 0) {
-        hexp += dtrue;
-        if (valid && M.exps) M.exps[(size_t)site * M.B + b] = dtrue;
-      } else {
-        // dA_site = sum_b 2^q (F x phi x G), q = h_in - delta_site, h_in = exponent of the input adjoint
-        const int q = hexp - dsite;
-        if (valid) {
+      if (lead) {
+        const int dtrue = nz ? e - kTcKA - kw : 0;  // exponent in units of the true recurrence
+        if (mode == 0) {
+          hexp += dtrue;
+          if (valid && M.exps) M.exps[(size_t)site * M.B + b] = dtrue;
+        } else {
+          // dA_site = sum_b 2^q (F x phi x G), q = h_in - delta_site, h_in = exponent of the input adjoint
+          const int q = hexp - dsite;
+          if (valid) {
 #pragma unroll
-          for (int s = 0; s < D; ++s) A.wq[((size_t)site * D + s) * M.B + b] = ph[s] * ldexpf(1.f, q);
+            for (int s = 0; s < D; ++s) A.wq[((size_t)site * D + s) * M.B + b] = ph[s] * ldexpf(1.f, q);
+          }
+          int qm = valid ? q : INT_MIN;
+          for (int off = 16; off > 0; off >>= 1) qm = max(qm, __shfl_xor_sync(0xffffffffu, qm, off));
+          if (lane == 0 && qm != INT_MIN) atomicMax(&A.qmax[site], qm);
+          hexp += dtrue - dsite;
         }
-        int qm = valid ? q : INT_MIN;
-        for (int off = 16; off > 0; off >>= 1) qm = max(qm, __shfl_xor_sync(0xffffffffu, qm, off));
-        if (lane == 0 && qm != INT_MIN) atomicMax(&A.qmax[site], qm);
-        hexp += dtrue - dsite;
       }
       const float nsc = valid ? ldexpf(1.f, kTcKA - e) : 0.f;  // normalise and apply the 2^14 operand/image scale
-      if (next_op == 1 || irow) {
-        for (int n0 = 0; n0 < chi; n0 += 16) {
-          float t[D][16];
-#pragma unroll
-          for (int s = 0; s < D; ++s) ptx::tmem_ld16(trow + (uint32_t)(s * chi + n0), t[s]);
-          ptx::tmem_ld_wait();
-          float w[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float o = ph[0] * t[0][j];
-#pragma unroll
-            for (int s = 1; s < D; ++s) o = fmaf(ph[s], t[s][j], o);
-            w[j] = o * nsc;
-          }
-          store_op16(n0, w, next_op == 1, irow);
-        }
-      }
-      if (next_op == 2) write_e0_operand();
+      if (next_op == 1 || irow) normalise_store(ph, vals, nsc, next_op == 1, irow);
+      if (next_op == 2) write_e0(true, nullptr);
       publish();
       ++step;
     };
@@ -293,9 +388,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
     if (!adjoint) {
       // ---------------- forward program ----------------
       int esumR = 0, esumL = 0;
-      write_e0_operand();
-      write_e0_image(img_row(A.fimg, L));
-      write_e0_image(img_row(A.fimg, 0));
+      write_e0(true, img_row(A.fimg, L));
+      write_e0(false, img_row(A.fimg, 0));
       publish();
       for (int i = 0; i < nR; ++i) {
         const int site = L - 1 - i;
@@ -317,55 +411,61 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
 #pragma unroll
         for (int s = 0; s < D; ++s) phc[s] = phl[s];
       }
-      const uint8_t *fr = img_row(A.fimg, c + 1);  // this thread wrote that row itself (image scale 2^14)
+      const uint8_t *fr = img_row(A.fimg, c + 1);  // each thread wrote its own column groups of that row (scale 2^14)
       const float ysc = ldexpf(1.f, -(2 * kTcKA + A.kW[c]));
       float y[kMaxOut];
       for (int k = 0; k < C; ++k) {
-        ptx::mbar_wait(acc_full, step & 1);
-        ptx::tc_fence_after();
         float acc = 0.f;
-        for (int n0 = 0; n0 < chi; n0 += 16) {
-          float t[D][16];
+        int hprev = -1;
 #pragma unroll
-          for (int s = 0; s < D; ++s) ptx::tmem_ld16(trow + (uint32_t)(s * chi + n0), t[s]);
+        for (int i = 0; i < SLOTS; ++i) {
+          if (!son[i]) continue;
           float f[16];
-          if (fr) load_img16(fr, n0, f);
+          if (fr) load_img16(fr, 4 * i + grp, f);
           else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = 0.f;
+            for (int q = 0; q < 16; ++q) f[q] = 0.f;
           }
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float o = phc[0] * t[0][j];
-#pragma unroll
-            for (int s = 1; s < D; ++s) o = fmaf(phc[s], t[s][j], o);
-            acc = fmaf(o, f[j], acc);
+          if (sh[i] != hprev) {
+            ptx::mbar_wait(&acc_full[sh[i]], step & 1);
+            ptx::tc_fence_after();
+            hprev = sh[i];
           }
+          float o[16];
+          tc_combine16<D>(scol[i], (uint32_t)chi_h, phc, o);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) acc = fmaf(o[q], f[q], acc);
         }
-        y[k] = acc * ysc;
+        if (hprev != NH - 1) {
+          ptx::mbar_wait(&acc_full[NH - 1], step & 1);
+          ptx::tc_fence_after();
+        }
+        const float *x = row_exchange(acc);
+        y[k] = ((x[0] + x[kTcRows]) + (x[2 * kTcRows] + x[3 * kTcRows])) * ysc;
         publish();
         ++step;
       }
-      float lval = 0.f;
-      if (valid) {
-        M.esum[b] = esumL;
-        M.esum[M.B + b] = esumR;
-        float tl[kMaxOut];
-        for (int k = 0; k < C; ++k) {
-          tl[k] = M.targets ? M.targets[(size_t)b * C + k] : 0.f;
-          M.y[(size_t)b * C + k] = y[k];
-          if (M.out) M.out[(size_t)b * C + k] = y[k];
+      if (lead) {
+        float lval = 0.f;
+        if (valid) {
+          M.esum[b] = esumL;
+          M.esum[M.B + b] = esumR;
+          float tl[kMaxOut];
+          for (int k = 0; k < C; ++k) {
+            tl[k] = M.targets ? M.targets[(size_t)b * C + k] : 0.f;
+            M.y[(size_t)b * C + k] = y[k];
+            if (M.out) M.out[(size_t)b * C + k] = y[k];
+          }
+          const int E = esumL + esumR;
+          if (M.out_exp) M.out_exp[b] = E;
+          lval = mps_head<float>(M.head, C, y, E, tl, M.cw, (float *)nullptr);
+          if (M.loss) M.loss[b] = lval;
         }
-        const int E = esumL + esumR;
-        if (M.out_exp) M.out_exp[b] = E;
-        lval = mps_head<float>(M.head, C, y, E, tl, M.cw, (float *)nullptr);
-        if (M.loss) M.loss[b] = lval;
-      }
-      if (M.loss_sum) {  // one atomic per warp
-        double ls = (double)lval;
-        for (int off = 16; off > 0; off >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, off);
-        if (lane == 0) atomicAdd(M.loss_sum, ls);
+        if (M.loss_sum) {  // one atomic per warp
+          double ls = (double)lval;
+          for (int off = 16; off > 0; off >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, off);
+          if (lane == 0) atomicAdd(M.loss_sum, ls);
+        }
       }
     } else {
       // ---------------- adjoint program ----------------
@@ -392,7 +492,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       for (int k = 0; k < C; ++k) dmax = fmaxf(dmax, fabsf(dy[k]));
       int ed = 0;
       if (dmax > 0.f) frexpf(dmax, &ed);
-      if (valid) {
+      if (valid && lead) {
         // class-site dA weights: wqc[(s,k)][b] = phi_s * dy'_k ; both halves write identical values
         int qm = INT_MIN;
         for (int s = 0; s < D; ++s)
@@ -412,7 +512,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       const int jb = half == 0 ? 0 : L - 1;  // the boundary site: no chain step, but it has a gradient
       for (int k = 0; k < C; ++k) {
         if (k < C - 1) {
-          ptx::mbar_wait(acc_full, step & 1);  // MMAs of step k have finished reading the operand
+          ptx::mbar_wait(&acc_full[NH - 1], step & 1);  // MMAs of step k have finished reading the operand
           ptx::tc_fence_after();
           write_operand_from_image(vrow, dy[k + 1] * dsc);
           publish();
@@ -420,42 +520,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
         } else {
           // all C slabs accumulated: normalise -> seed G[c] / G[c+1]
           uint8_t *girow = img_row(A.gimg, half == 0 ? c : c + 1);
-          ptx::mbar_wait(acc_full, step & 1);
-          ptx::tc_fence_after();
-          float m = 0.f;
-          for (int n0 = 0; n0 < chi; n0 += 16) {
-            float t[D][16];
-#pragma unroll
-            for (int s = 0; s < D; ++s) ptx::tmem_ld16(trow + (uint32_t)(s * chi + n0), t[s]);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float o = phc[0] * t[0][j];
-#pragma unroll
-              for (int s = 1; s < D; ++s) o = fmaf(phc[s], t[s][j], o);
-              m = fmaxf(m, fabsf(o));
-            }
+          float vals[KEEP][16];
+          float m = gather(phc, vals);
+          {
+            const float *x = row_exchange(m);
+            m = fmaxf(fmaxf(x[0], x[kTcRows]), fmaxf(x[2 * kTcRows], x[3 * kTcRows]));
           }
           int e = 0;
           const bool nz = m > 0.f && valid;
           if (nz) frexpf(m, &e);
           h = (nz ? e - kTcKA - A.kW[c] : 0) + ed;  // G = normalised row * 2^h (the operand carried dy * 2^-ed)
           const float nsc = valid ? ldexpf(1.f, kTcKA - e) : 0.f;
-          for (int n0 = 0; n0 < chi; n0 += 16) {
-            float t[D][16];
-#pragma unroll
-            for (int s = 0; s < D; ++s) ptx::tmem_ld16(trow + (uint32_t)(s * chi + n0), t[s]);
-            ptx::tmem_ld_wait();
-            float w[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float o = phc[0] * t[0][j];
-#pragma unroll
-              for (int s = 1; s < D; ++s) o = fmaf(phc[s], t[s][j], o);
-              w[j] = o * nsc;
-            }
-            store_op16(n0, w, nchain > 0, girow);
-          }
+          normalise_store(phc, vals, nsc, nchain > 0, girow);
           publish();
           ++step;
         }
@@ -468,7 +544,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
         chain_step(site, A.kW[mps_slab(M, site)], ph, 1, h, i == nchain - 1 ? 0 : 1, img_row(A.gimg, bond_out));
       }
       // boundary site weights
-      {
+      if (lead) {
         int qm = INT_MIN;
         if (valid) {
           const int q = h - M.exps[(size_t)jb * M.B + b];
@@ -487,7 +563,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  if (warp == 5) ptx::tmem_dealloc(tmem_base, (uint32_t)A.tmem_cols);
+  if (warp == kTcMmaWarp) ptx::tmem_dealloc(tmem_base, (uint32_t)A.tmem_cols);
 }
 
 }  // namespace tnb

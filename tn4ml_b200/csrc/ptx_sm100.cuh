@@ -49,6 +49,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       : "memory");
 }
 
+// named barrier: `nthreads` threads (a multiple of 32) of the CTA meet at barrier `id` (1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ---- bulk async copy global -> shared (completes on an mbarrier) --------------------------
 __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
