@@ -279,8 +279,12 @@ def run_native(args):
 
     # per-kernel timing for the roofline of the dominant kernel (separate pass, events on the launch stream)
     lib.tnb_profile(1)
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
     step_resident()
+    pe1.record()
     torch.cuda.synchronize(dev)
+    profile_step_ms = pe0.elapsed_time(pe1)
     nmax = 8192
     names = C.create_string_buffer(48 * nmax)
     msbuf = (C.c_float * nmax)()
@@ -315,7 +319,8 @@ def run_native(args):
                 "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_note,
                 "kernel_ms_avg": top_ms, "kernel_share_of_step": sum(per.get(top, [0])) / tot,
                 "step_tflops": fps * B / (ms_per_step * 1e-3) / 1e12,
-                "kernel_ms": {k: float(np.sum(v)) for k, v in per.items()}}
+                "kernel_ms": {k: float(np.sum(v)) for k, v in per.items()},
+                "profiled_step_ms": profile_step_ms, "profiled_kernel_sum_ms": float(tot)}
 
     # end to end through the public train step: pinned host inputs -> H2D -> step -> loss D2H
     state = opt_state

@@ -192,7 +192,7 @@ static MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
   }
   if (P.tc) {
     // the tensor path keeps its environments as fp16 hi/lo bond images instead of F / G
-    P.img_bond_bytes = (size_t)((B + 31) / 32 * 32) * p->chi * 4;
+    P.img_bond_bytes = (size_t)((B + kTcRows - 1) / kTcRows * kTcRows) * p->chi * 4;  // whole 128-sample tiles
     P.off_fimg = take((need_grad ? (size_t)p->L + 1 : 1) * P.img_bond_bytes);
     P.off_img_n = take(P.tc_site_img * P.nslab);
     P.off_img_t = take(P.tc_site_img * P.nslab);
@@ -564,6 +564,15 @@ int32_t tnb_profile_read(char *names, float *ms, int32_t max_records) {
   }
   return n;
 }
+
+#ifdef TNB_TC_TRACE
+/* measurement build only: copy the in-kernel timeline of the chain kernel (mps_tc_chain.cuh) to the host */
+int tnb_debug_trace_read(long long *host, int32_t n) {
+  if (n > 64 * 32) n = 64 * 32;
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(host, tnb::g_tc_trace, (size_t)n * sizeof(long long)) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 int tnb_embed(const tnb_embedding *emb, int32_t dtype, int64_t n, const void *x, void *phi, void *stream) {
   if (!emb || !x || !phi) return fail("null pointer");

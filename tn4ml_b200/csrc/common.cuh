@@ -118,6 +118,60 @@ __device__ __forceinline__ void embed_site(const EmbParams<T> &e, T x, T *out) {
   for (int s = 0; s < e.d; ++s) out[s] *= inv;
 }
 
+// Same map with the physical dimension as a compile-time constant: every loop unrolls and phi stays in
+// registers (the tensor-core chain kernel evaluates it once per site and sample inside its epilogue warps).
+template <int D, typename T>
+__device__ __forceinline__ void embed_site_d(const EmbParams<T> &e, T x, T (&out)[D]) {
+  using N = Num<T>;
+  if (e.kind == TNB_EMB_TRIG) {
+    constexpr int K = D / 2 > 0 ? D / 2 : 1;
+    const T inv = T(1) / N::sqrt(T(K));
+    T scale = T(0.5);
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      out[i] = N::cospi(x * scale) * inv;
+      if (K + i < D) out[K + i] = N::sinpi(x * scale) * inv;
+      scale *= T(0.5);
+    }
+  } else if (e.kind == TNB_EMB_FOURIER) {
+    const T pinv = T(1) / T(D);
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      const T y = T(D - 1) * x - T(j);
+      const T den = N::sinpi(y * pinv);
+      const T num = N::sinpi(y);
+      T v;
+      if (N::abs(den) < T(1e-6)) {
+        T re = 0, im = 0;
+        for (int kk = 0; kk < D; ++kk) {
+          re += N::cospi(T(2 * kk) * y * pinv);
+          im += N::sinpi(T(2 * kk) * y * pinv);
+        }
+        v = N::sqrt(re * re + im * im) * pinv;
+      } else {
+        v = N::abs(num / den) * pinv;
+      }
+      out[j] = v;
+    }
+  } else if (e.kind == TNB_EMB_POLY) {
+    T pw = e.include_bias ? T(1) : x;
+#pragma unroll
+    for (int s = 0; s < D; ++s) {
+      out[s] = pw;
+      pw *= x;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < D; ++j) out[j] = N::exp(-e.gamma * (x - e.centers[j]));
+  }
+  T n2 = 0;
+#pragma unroll
+  for (int s = 0; s < D; ++s) n2 += out[s] * out[s];
+  const T inv = T(1) / N::sqrt(n2);
+#pragma unroll
+  for (int s = 0; s < D; ++s) out[s] *= inv;
+}
+
 // ---------------------------------------------------------------------------------------
 // Classifier / NLL heads on the rescaled output y' = y * 2^-E (E = esum).  Returns the
 // per-sample loss; if dy != nullptr writes dLoss/dy' (unscaled by loss_scale).

@@ -16,8 +16,9 @@
 // shared-memory operand layout (canonical K-major, no swizzle), so one 1-D bulk async copy
 // (TMA engine) moves a whole pipeline stage and completes on an mbarrier.
 //
-// Warp roles of the chain kernel (576 threads; mps_tc_chain.cuh): warps 0-15 epilogue (four threads per
-// sample row == TMEM lane), warp 16 TMEM owner + MMA issuer, warp 17 bulk-copy producer.
+// Warp roles of the chain kernel (608 threads; mps_tc_chain.cuh): warps 0-15 epilogue (four threads per
+// sample row == TMEM lane), warp 16 TMEM owner + MMA issuer, warp 17 bulk-copy producer (weights in),
+// warp 18 bulk-copy image writer (environments out).
 #pragma once
 #include <cuda_fp16.h>
 #include <limits.h>
@@ -30,8 +31,8 @@ namespace tnb {
 constexpr int kTcRows = 128;   // samples per CTA == TMEM lanes
 constexpr int kTcKA = 14;      // A operand pre-scale: |v| < 1  ->  |v * 2^14| < 2^14 (fp16 max 65504)
 constexpr int kTcEpiWarps = 16;                      // 4 lane quarters x 4 column groups
-constexpr int kTcMmaWarp = kTcEpiWarps;              // + 1: the bulk-copy producer warp
-constexpr int kTcThreads = (kTcEpiWarps + 2) * 32;
+constexpr int kTcMmaWarp = kTcEpiWarps;              // + 1: weight producer warp, + 2: image writer warp
+constexpr int kTcThreads = (kTcEpiWarps + 3) * 32;
 constexpr int kTcMaxNH = 16;                         // column chunks per step (chi / 16 at most)
 
 struct TcArgs {
@@ -41,9 +42,11 @@ struct TcArgs {
   const int *kW;         // per-slab weight pre-scale exponent
   float *wq;             // adjoint: phi_s[b] * 2^q[b] per (site, s, b): per-sample weight of the dA GEMM
   int *qmax;             // adjoint: max_b q[site][b]
-  // Environment stash of the tensor path: fp16 hi/lo images (value * 2^14, rows normalised), one per bond,
-  // laid out [slot][B/32][plane hi|lo][chi/8][4 sample blocks][8 samples][8 halves] = exactly the MN-major
-  // operand tile of the dA GEMM for a chunk of 32 samples.  fimg: forward environments, gimg: adjoints.
+  // Environment stash of the tensor path: fp16 hi/lo images (value * 2^14, rows normalised), one per bond, laid out
+  // [slot][sample block of 8][plane hi|lo][chi/8 octets][8 samples][8 halves]: the 16-byte unit is 8 consecutive bond
+  // indices of one sample.  A tile of 128 samples is byte-identical to the chain kernel's shared-memory A operand
+  // (K-major, LBO 128, SBO chi*32), so it leaves the SM as one bulk copy; a run of 32 samples is an MN-major operand
+  // tile of the dA GEMM (K-block stride chi*32, octet stride 128).  fimg: forward environments, gimg: adjoints.
   uint8_t *fimg, *gimg;
   size_t img_bond_bytes;
   int img_stash;         // 1: every bond has a slot; 0: forward-only, a single slot for bond c+1
@@ -132,6 +135,9 @@ __global__ void tc_image_kernel(const float *__restrict__ params, const int *__r
     }
   }
 }
+
+// byte offset of sample b's 16-byte units inside a bond image (add plane * chi*16 + octet * 128)
+__device__ __forceinline__ size_t tc_img_row(long long b, int chi) { return (size_t)(b >> 3) * chi * 32 + (size_t)(b & 7) * 16; }
 
 // pack 8 floats (already scaled) into fp16 hi / lo octets
 __device__ __forceinline__ void split8(const float *w, uint4 &hi, uint4 &lo) {
@@ -237,6 +243,8 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
   if (warp == kMmaWarp) {
     if (lane == 0) {
       const uint32_t idesc = ptx::idesc_f16_f32(128, chi) | (1u << 15) | (1u << 16);  // A and B MN-major
+      // V tile = 32 samples of a bond image: sample-block (K) stride chi*32, lo plane at chi*16, 16 samples = 2 blocks
+      const uint32_t vlbo = (uint32_t)chi * 32, vlo = (uint32_t)chi * 16, vks = (uint32_t)chi * 64;
       int stage = 0;
       uint32_t phase = 0;
       for (int ch = 0; ch < nchunks; ++ch) {
@@ -248,8 +256,8 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
           for (int ks = 0; ks < kDaKC / 16; ++ks) {
             const uint64_t da_hi = ptx::smem_desc_kmajor(st + t * 16 * kDaSBO + ks * 256, 128, kDaSBO);
             const uint64_t da_lo = ptx::smem_desc_kmajor(st + kDaPlane + t * 16 * kDaSBO + ks * 256, 128, kDaSBO);
-            const uint64_t db_hi = ptx::smem_desc_kmajor(st + 2 * kDaPlane + ks * 256, 128, 512);
-            const uint64_t db_lo = ptx::smem_desc_kmajor(st + 2 * kDaPlane + (uint32_t)chi * 64 + ks * 256, 128, 512);
+            const uint64_t db_hi = ptx::smem_desc_kmajor(st + 2 * kDaPlane + ks * vks, vlbo, 128);
+            const uint64_t db_lo = ptx::smem_desc_kmajor(st + 2 * kDaPlane + vlo + ks * vks, vlbo, 128);
             const uint32_t d = tmem_base + (uint32_t)t * chi;
             ptx::mma_f16(d, da_hi, db_hi, idesc, (ch > 0 || ks > 0) ? 1u : 0u);
             ptx::mma_f16(d, da_lo, db_hi, idesc, 1u);
@@ -275,12 +283,13 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
     }
   } else {
     // ===== U operand producers: lane == sample, warp == row octet =====
-    // The bond image already is the MN-major tile layout (8 rows of one sample = one 16-byte unit,
-    // consecutive samples = consecutive units), so a warp reads 512 contiguous bytes per plane and
-    // writes 512 contiguous bytes per plane: hi + lo -> fp32 -> * per-sample weight -> hi/lo.
+    // The unit of a bond image is 8 rows of one sample (16 bytes); the 8 samples of a block are consecutive
+    // units, so a warp reads 4 x 128 contiguous bytes per plane and writes 512 contiguous bytes per plane:
+    // hi + lo -> fp32 -> * per-sample weight -> hi/lo.
     constexpr int kWarps = kDaProducers / 32;
     constexpr int kItems = 2;  // row octets per warp and stage: 2 tiles * 16 octets / 16 warps
-    const uint32_t lane_off = (uint32_t)(lane >> 3) * 128 + (uint32_t)(lane & 7) * 16;
+    const uint32_t lane_off = (uint32_t)(lane >> 3) * 128 + (uint32_t)(lane & 7) * 16;            // operand tile
+    const uint32_t lane_src = (uint32_t)(lane >> 3) * (uint32_t)chi * 32 + (uint32_t)(lane & 7) * 16;  // bond image
     uint32_t src_off[kItems], dst_off[kItems];
     const float *wq_row[kItems];
     bool on[kItems];
@@ -291,12 +300,12 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
       on[i] = ro < ntile * 16 && m < Mtot;
       const int sidx = on[i] ? m / chi : 0;
       const int a0 = on[i] ? m - sidx * chi : 0;
-      src_off[i] = (uint32_t)(a0 >> 3) * 512 + lane_off;
+      src_off[i] = (uint32_t)(a0 >> 3) * 128 + lane_src;
       dst_off[i] = (uint32_t)ro * kDaSBO + lane_off;
       wq_row[i] = A.wq + ((size_t)(A.only_site >= 0 ? 0 : site) * D + sidx) * M.B;
     }
     const float qs = ldexpf(1.f, -qmax);  // (the image already carries the 2^14 operand scale)
-    const uint32_t lo_off = (uint32_t)chi * 64;
+    const uint32_t lo_off = (uint32_t)chi * 16;
 
     // Issue phase: loads only (no instruction may consume a loaded value here, or the in-order warp
     // would stall on the first one and serialise the rest).

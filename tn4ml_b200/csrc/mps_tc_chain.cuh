@@ -20,15 +20,19 @@
 // (TMEM column h*NMMA + s*chi/NH + n - h*chi/NH) and has its own commit barrier, so the epilogue
 // of chunk h runs underneath the MMAs of chunk h+1.
 //
-// Warp roles (576 threads): warps 0-15 epilogue, warp 16 TMEM owner + MMA issuer, warp 17 bulk-copy
-// producer.  A TMEM lane quarter is only visible to warps with warp % 4 == quarter, so the four
-// warps {q, q+4, q+8, q+12} share the 32 sample rows of quarter q and split a row's 16-column
-// groups between them (group j belongs to warp group j % 4).  Every thread keeps its <= 64 outputs
-// in registers: ONE pass over TMEM produces the phi-contracted row, the row maximum is combined
-// through a 4 KB shared-memory exchange and a 128-thread named barrier per lane quarter, and the
-// normalised fp16 hi/lo operand is written straight from registers.  (With one epilogue warp per
-// scheduler and two TMEM passes the kernel was bound by the TMEM load latency: ncu 14 % issue
-// active, tensor pipe 43 %.)
+// Warp roles (608 threads):
+//   warps 0-15  epilogue.  A TMEM lane quarter is only visible to warps with warp % 4 == quarter, so the four
+//               warps {q, q+4, q+8, q+12} share the 32 sample rows of quarter q and split a row's 16-column
+//               groups between them (group j belongs to warp group j % 4).  Every thread keeps its outputs in
+//               registers: ONE pass over TMEM produces the phi-contracted row, the row maximum is combined
+//               through a 4 KB shared-memory exchange and a 128-thread named barrier per lane quarter, and the
+//               normalised fp16 hi/lo operand is written straight from registers to shared memory.
+//   warp 16     TMEM owner + MMA issuer.
+//   warp 17     weight producer: one bulk copy global -> shared per pipeline stage.
+//   warp 18     image writer: the new A operand IS the bond image of these 128 samples (same bytes), so it goes to
+//               the HBM stash as one bulk copy shared -> global while the next step's MMAs run.  (Written with
+//               per-thread stores from the epilogue, those 128 KB per step sat on the critical path: measured
+//               4.5 k of 22 k cycles per step, the per-SM store bandwidth.)
 //
 // Environments are carried as (mantissa row, integer exponent): every epilogue renormalises the
 // row to max-abs in [0.5, 1) by an exact power of two, which is also what keeps the fp16 hi/lo
@@ -37,6 +41,19 @@
 #include "mps_tc.cuh"
 
 namespace tnb {
+
+// Optional in-kernel timeline (built only with -DTNB_TC_TRACE, tools/trace_chain.py): CTA (0,0) records clock64() at
+// fixed points of a few steady-state steps; read back with tnb_debug_trace_read.
+#ifdef TNB_TC_TRACE
+__device__ long long g_tc_trace[64 * 32];
+#define TNB_TRACE(who, step_, ev)                                                                              \
+  do {                                                                                                         \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && (step_) >= 20 && (step_) < 52 && (threadIdx.x & 31) == 0 && (who) < 4) \
+      g_tc_trace[((step_)-20) * 64 + (who)*16 + (ev)] = clock64();                                              \
+  } while (0)
+#else
+#define TNB_TRACE(who, step_, ev) do { } while (0)
+#endif
 
 // acc columns -> o[j] = sum_s ph[s] * acc[col + s*cstride + j], j < 16   (one 16-column group).
 // The s = 0 slice is loaded straight into o (registers are the scarce resource here: 64 outputs per thread stay live).
@@ -64,7 +81,7 @@ __device__ __forceinline__ void tc_combine16(uint32_t col, uint32_t cstride, con
 }
 
 // SLOTS: 16-column groups per epilogue thread; the first KEEP of them stay in registers between the maximum and the
-// normalisation, the others are read from TMEM a second time (576 threads leave 96 registers per thread).
+// normalisation, the others are read from TMEM a second time (640 allocated threads leave 96 registers per thread).
 template <int D, int SLOTS, int KEEP>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int adjoint) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -102,15 +119,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
     }
     return (tr ? A.img_t : A.img_n) + (size_t)slab * A.site_img_bytes;
   };
+  // step -> bond whose image is the operand this step's epilogue leaves in shared memory (-1: none / not stashed).
+  // (The last right-chain step of the forward program replaces the operand by e0: its image is stored by the
+  // epilogue threads themselves.)
+  auto step_out_bond = [&](int step) -> int {
+    if (!adjoint) {
+      if (!A.img_stash) return -1;
+      if (step < nR) return step == nR - 1 ? -1 : L - 1 - step;
+      if (step < nR + nL) return step - nR + 1;
+      return -1;
+    }
+    if (step < nseed - 1) return -1;
+    if (step == nseed - 1) return half == 0 ? c : c + 1;
+    const int i = step - nseed;
+    return half == 0 ? c - 1 - i : c + 2 + i;
+  };
 
-  const uint32_t a_plane = (uint32_t)kTcRows * chi * 2;
-  uint8_t *a_hi = smem;
-  uint8_t *a_lo = smem + a_plane;
-  uint8_t *stages = smem + 2 * a_plane;
+  // A operand = bond image of this CTA's 128 rows: unit (row, octet o, plane p) at (row/8)*chi*32 + p*chi*16 + o*128 + (row%8)*16
+  const uint32_t a_bytes = (uint32_t)kTcRows * chi * 4;
+  uint8_t *a_op = smem;
+  uint8_t *stages = smem + a_bytes;
   float *xch = reinterpret_cast<float *>(stages + (size_t)A.nstage * A.stage_bytes);  // [2][4][128]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(xch + 2 * 4 * kTcRows);
+  uint32_t *gcol = reinterpret_cast<uint32_t *>(xch + 2 * 4 * kTcRows);               // [16] group -> TMEM column
+  uint32_t *gchunk = gcol + 16;                                                       // [16] group -> column chunk
+  uint64_t *bars = reinterpret_cast<uint64_t *>(gchunk + 16);
   uint64_t *full = bars, *empty = bars + A.nstage, *acc_full = bars + 2 * A.nstage, *a_ready = acc_full + kTcMaxNH;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_ready + 1);
+  uint64_t *img_done = a_ready + 1;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(img_done + 1);
 
   if (tid == 0) {
     for (int i = 0; i < A.nstage; ++i) {
@@ -119,7 +154,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
     }
     for (int h = 0; h < NH; ++h) ptx::mbar_init(&acc_full[h], 1);
     ptx::mbar_init(a_ready, kTcEpiWarps);
+    ptx::mbar_init(img_done, 1);
     ptx::fence_mbar_init();
+  }
+  if (tid < 16) {
+    const int n0 = 16 * tid;
+    const int h = n0 < chi ? n0 / chi_h : 0;
+    gchunk[tid] = (uint32_t)h;
+    gcol[tid] = (uint32_t)(h * A.NMMA + (n0 - h * chi_h));
   }
   if (warp == kTcMmaWarp) {
     ptx::tmem_alloc(tmem_slot, (uint32_t)A.tmem_cols);
@@ -131,8 +173,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
   const uint32_t tmem_base = *tmem_slot;
   const int KS = chi / 16;
 
-  if (warp == kTcMmaWarp + 1) {
-    // ===== producer: one bulk async copy per pipeline stage (= one K-slab of one column chunk) =====
+  if (warp == kTcMmaWarp + 2) {
+    // ===== image writer: operand generation g (published as phase g of a_ready) -> HBM stash =====
+    if (lane == 0) {
+      uint8_t *base = adjoint ? A.gimg : A.fimg;
+      const size_t tile_off = (size_t)(b0 >> 3) * chi * 32;
+      for (int g = 0; g <= total; ++g) {
+        ptx::mbar_wait(a_ready, g & 1);
+        const int bond = g > 0 ? step_out_bond(g - 1) : -1;
+        if (bond >= 0 && base) {
+          ptx::bulk_s2g(base + (size_t)bond * A.img_bond_bytes + tile_off, a_op, a_bytes);
+          ptx::bulk_commit();
+          ptx::bulk_wait_read0();
+        }
+        ptx::mbar_arrive(img_done);  // the operand may be overwritten
+      }
+      ptx::bulk_wait0();
+    }
+  } else if (warp == kTcMmaWarp + 1) {
+    // ===== weight producer: one bulk async copy per pipeline stage (= one K-slab of one column chunk) =====
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -152,8 +211,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = ptx::idesc_f16_f32(kTcRows, A.NMMA);
-      const uint32_t a_hi_s = ptx::smem_u32(a_hi), a_lo_s = ptx::smem_u32(a_lo);
-      const uint32_t sbo_a = (uint32_t)chi * 16;
+      const uint32_t a_hi_s = ptx::smem_u32(a_op), a_lo_s = a_hi_s + (uint32_t)chi * 16;
+      const uint32_t sbo_a = (uint32_t)chi * 32;
       const uint32_t lo_plane = (uint32_t)A.NMMA * 32;
       int stage = 0;
       uint32_t phase = 0;
@@ -161,6 +220,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
         const bool accum_step = adjoint && step > 0 && step < nseed;  // seed steps accumulate over k
         ptx::mbar_wait(a_ready, step & 1);
         ptx::tc_fence_after();
+        TNB_TRACE(3, step, 0);
         for (int h = 0; h < NH; ++h) {
           const uint32_t d = tmem_base + (uint32_t)h * A.NMMA;
           for (int ks = 0; ks < KS; ++ks) {
@@ -178,6 +238,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
             if (++stage == A.nstage) { stage = 0; phase ^= 1; }
           }
           ptx::mma_commit(&acc_full[h]);
+          TNB_TRACE(3, step, 1 + h);
         }
       }
     }
@@ -190,54 +251,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
     const bool lead = grp == 0;  // the thread of the row that does the per-sample bookkeeping
     const size_t bs = (size_t)(valid ? b : 0);
     const uint32_t trow = tmem_base + ((uint32_t)(lq * 32) << 16);
-    const uint32_t row_off = (uint32_t)(row >> 3) * (uint32_t)chi * 16 + (uint32_t)(row & 7) * 16;
-    const int nch = chi / 16;
+    uint8_t *a_row = a_op + (uint32_t)(row >> 3) * (uint32_t)chi * 32 + (uint32_t)(row & 7) * 16;
+    const uint32_t lo_off = (uint32_t)chi * 16;  // lo plane of a unit, in the operand and in the bond images
+    const int nmine = (chi / 16 - grp + 3) >> 2;  // my 16-column groups: j = 4*i + grp, i < nmine (<= SLOTS)
     int step = 0;
+#ifdef TNB_TC_TRACE
+    const int tw = warp == 0 ? 0 : (warp == 15 ? 1 : (warp == 6 ? 2 : 63));  // traced epilogue warps (63: not recorded)
+#endif
 
-    // my 16-column groups: j = 4*i + grp (i < SLOTS); chunk index and first TMEM column of each
-    bool son[SLOTS];
-    int sh[SLOTS];
-    uint32_t scol[SLOTS];
-#pragma unroll
-    for (int i = 0; i < SLOTS; ++i) {
-      const int j = 4 * i + grp;
-      son[i] = j < nch;
-      const int n0 = 16 * j;
-      sh[i] = son[i] ? n0 / chi_h : 0;
-      scol[i] = trow + (uint32_t)(sh[i] * A.NMMA + (n0 - sh[i] * chi_h));
-    }
-
-    // this sample's 16-byte slot inside the image of `bond` (see TcArgs): consecutive samples of a warp
-    // are consecutive 16-byte units, so every warp-wide image store/load is 512 contiguous bytes
-    const bool img_ok = b < (M.B + 31) / 32 * 32;
+    // this sample's 16-byte units inside the image of `bond` (see TcArgs)
     auto img_row = [&](uint8_t *base, int bond) -> uint8_t * {
       const int slot = A.img_stash ? bond : (bond == c + 1 ? 0 : -1);
-      if (!img_ok || slot < 0 || base == nullptr) return nullptr;
-      return base + (size_t)slot * A.img_bond_bytes + (size_t)(b >> 5) * chi * 128 + (size_t)((b & 31) >> 3) * 128 +
-             (size_t)(b & 7) * 16;
+      if (slot < 0 || base == nullptr) return nullptr;
+      return base + (size_t)slot * A.img_bond_bytes + tc_img_row(b, chi);
     };
-    // w (already scaled by 2^14) -> fp16 hi/lo octets -> next A operand (smem) and/or the bond image (global)
-    auto store_op16 = [&](int j, const float(&w)[16], bool to_smem, uint8_t *irow) {
+    // w (already scaled by 2^14) -> fp16 hi/lo octets -> the unit row `dst` (operand row in smem or image row in HBM)
+    auto store_op16 = [&](int j, const float(&w)[16], uint8_t *dst) {
       uint4 hi, lo;
 #pragma unroll
       for (int o = 0; o < 2; ++o) {
         split8(w + 8 * o, hi, lo);
-        if (to_smem) {
-          *reinterpret_cast<uint4 *>(a_hi + row_off + (2 * j + o) * 128) = hi;
-          *reinterpret_cast<uint4 *>(a_lo + row_off + (2 * j + o) * 128) = lo;
-        }
-        if (irow) {
-          *reinterpret_cast<uint4 *>(irow + (size_t)(2 * j + o) * 512) = hi;
-          *reinterpret_cast<uint4 *>(irow + (size_t)chi * 64 + (size_t)(2 * j + o) * 512) = lo;
-        }
+        *reinterpret_cast<uint4 *>(dst + (2 * j + o) * 128) = hi;
+        *reinterpret_cast<uint4 *>(dst + lo_off + (2 * j + o) * 128) = lo;
       }
     };
     // 16 values of an image row: hi + lo (exact in fp32), still carrying the 2^14 image scale
     auto load_img16 = [&](const uint8_t *irow, int j, float(&v)[16]) {
 #pragma unroll
       for (int o = 0; o < 2; ++o) {
-        const uint4 hi = *reinterpret_cast<const uint4 *>(irow + (size_t)(2 * j + o) * 512);
-        const uint4 lo = *reinterpret_cast<const uint4 *>(irow + (size_t)chi * 64 + (size_t)(2 * j + o) * 512);
+        const uint4 hi = *reinterpret_cast<const uint4 *>(irow + (2 * j + o) * 128);
+        const uint4 lo = *reinterpret_cast<const uint4 *>(irow + lo_off + (2 * j + o) * 128);
         const __half2 *h = reinterpret_cast<const __half2 *>(&hi), *l = reinterpret_cast<const __half2 *>(&lo);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -247,31 +290,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
         }
       }
     };
-    // boundary vector e0 * 2^14 as the A operand / as a bond image (my column groups only)
-    auto write_e0 = [&](bool to_smem, uint8_t *irow) {
+    // boundary vector e0 * 2^14 into a unit row (my column groups only); `one` = false writes zeros
+    auto write_e0 = [&](uint8_t *dst, bool one) {
+      if (!dst) return;
 #pragma unroll
       for (int i = 0; i < SLOTS; ++i) {
-        if (!son[i]) continue;
+        if (i >= nmine) continue;
         const int j = 4 * i + grp;
 #pragma unroll
         for (int o = 0; o < 2; ++o) {
           uint4 z = make_uint4(0, 0, 0, 0), zh = z;
-          if (2 * j + o == 0) zh.x = 0x00007400u;  // fp16(2^14) in element 0
-          if (to_smem) {
-            *reinterpret_cast<uint4 *>(a_hi + row_off + (2 * j + o) * 128) = zh;
-            *reinterpret_cast<uint4 *>(a_lo + row_off + (2 * j + o) * 128) = z;
-          }
-          if (irow) {
-            *reinterpret_cast<uint4 *>(irow + (size_t)(2 * j + o) * 512) = valid ? zh : z;
-            *reinterpret_cast<uint4 *>(irow + (size_t)chi * 64 + (size_t)(2 * j + o) * 512) = z;
-          }
+          if (2 * j + o == 0 && one) zh.x = 0x00007400u;  // fp16(2^14) in element 0
+          *reinterpret_cast<uint4 *>(dst + (2 * j + o) * 128) = zh;
+          *reinterpret_cast<uint4 *>(dst + lo_off + (2 * j + o) * 128) = z;
         }
       }
     };
     auto write_operand_from_image = [&](const uint8_t *irow, float scale) {
 #pragma unroll
       for (int i = 0; i < SLOTS; ++i) {
-        if (!son[i]) continue;
+        if (i >= nmine) continue;
         const int j = 4 * i + grp;
         float w[16];
         if (irow) load_img16(irow, j, w);
@@ -281,7 +319,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
         }
 #pragma unroll
         for (int q = 0; q < 16; ++q) w[q] *= scale;
-        store_op16(j, w, true, nullptr);
+        store_op16(j, w, a_row);
       }
     };
     auto publish = [&]() {  // operand (and TMEM reads) done -> the MMA warp may start the next step
@@ -290,6 +328,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(a_ready);
     };
+    // the image writer has finished reading the operand of this step (it may be overwritten)
+    auto operand_free = [&]() { ptx::mbar_wait(img_done, step & 1); };
     // combine one float per thread across the 4 threads of a row (through smem, fixed order)
     auto row_exchange = [&](float v) -> const float * {
       float *x = xch + (step & 1) * (4 * kTcRows);
@@ -303,19 +343,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       int hprev = -1;
 #pragma unroll
       for (int i = 0; i < SLOTS; ++i) {
-        if (!son[i]) continue;
-        if (sh[i] != hprev) {
-          ptx::mbar_wait(&acc_full[sh[i]], step & 1);
+        if (i >= nmine) continue;
+        const int j = 4 * i + grp;
+        const int h = (int)gchunk[j];
+        if (h != hprev) {
+          ptx::mbar_wait(&acc_full[h], step & 1);
           ptx::tc_fence_after();
-          hprev = sh[i];
+          hprev = h;
+          TNB_TRACE(tw, step, h);
         }
         if (i < KEEP) {
-          tc_combine16<D>(scol[i], (uint32_t)chi_h, ph, vals[i < KEEP ? i : 0]);
+          tc_combine16<D>(trow + gcol[j], (uint32_t)chi_h, ph, vals[i < KEEP ? i : 0]);
 #pragma unroll
           for (int q = 0; q < 16; ++q) m = fmaxf(m, fabsf(vals[i < KEEP ? i : 0][q]));
         } else {
           float o[16];
-          tc_combine16<D>(scol[i], (uint32_t)chi_h, ph, o);
+          tc_combine16<D>(trow + gcol[j], (uint32_t)chi_h, ph, o);
 #pragma unroll
           for (int q = 0; q < 16; ++q) m = fmaxf(m, fabsf(o[q]));
         }
@@ -326,40 +369,54 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       }
       return m;
     };
-    auto normalise_store = [&](const float(&ph)[D], float(&vals)[KEEP][16], float nsc, bool to_smem, uint8_t *irow) {
+    auto normalise_store = [&](const float(&ph)[D], float(&vals)[KEEP][16], float nsc, uint8_t *dst) {
 #pragma unroll
       for (int i = 0; i < SLOTS; ++i) {
-        if (!son[i]) continue;
+        if (i >= nmine) continue;
+        const int j = 4 * i + grp;
         if (i < KEEP) {
 #pragma unroll
           for (int q = 0; q < 16; ++q) vals[i < KEEP ? i : 0][q] *= nsc;
-          store_op16(4 * i + grp, vals[i < KEEP ? i : 0], to_smem, irow);
+          store_op16(j, vals[i < KEEP ? i : 0], dst);
         } else {
           float o[16];
-          tc_combine16<D>(scol[i], (uint32_t)chi_h, ph, o);
+          tc_combine16<D>(trow + gcol[j], (uint32_t)chi_h, ph, o);
 #pragma unroll
           for (int q = 0; q < 16; ++q) o[q] *= nsc;
-          store_op16(4 * i + grp, o, to_smem, irow);
+          store_op16(j, o, dst);
         }
       }
     };
     // One chain step.  mode 0: forward (records delta)   mode 1: adjoint (records wq/qmax).
     // `hexp` is the forward exponent sum (mode 0) or the running exponent h of the adjoint (mode 1); lead thread only.
-    // next_op: 0 = none, 1 = the normalised vector, 2 = the boundary vector e0.  irow: image slot of the output bond.
-    auto chain_step = [&](int site, int kw, const float *ph_in, int mode, int &hexp, int next_op, uint8_t *irow) {
-      float ph[D];  // registers (static indexing only)
-#pragma unroll
-      for (int s = 0; s < D; ++s) ph[s] = ph_in[s];
+    // to_e0: the next operand is the boundary vector e0 and the normalised row goes to its image `irow` directly
+    // (end of the right chain); otherwise the row becomes the next operand and the image writer stashes it.
+    auto chain_step = [&](int site, int kw, const float(&ph)[D], int mode, int &hexp, bool to_e0, uint8_t *irow) {
       const int dsite = (mode == 1 && valid && lead) ? M.exps[(size_t)site * M.B + b] : 0;
       float vals[KEEP][16];
       float m = gather(ph, vals);
+      TNB_TRACE(tw, step, 8);
       {
         const float *x = row_exchange(m);
         m = fmaxf(fmaxf(x[0], x[kTcRows]), fmaxf(x[2 * kTcRows], x[3 * kTcRows]));
       }
+      TNB_TRACE(tw, step, 9);
       int e = 0;
       const bool nz = m > 0.f && valid;
       if (nz) frexpf(m, &e);
+      const float nsc = valid ? ldexpf(1.f, kTcKA - e) : 0.f;  // normalise and apply the 2^14 operand/image scale
+      operand_free();
+      TNB_TRACE(tw, step, 10);
+      if (to_e0) {
+        if (irow) normalise_store(ph, vals, nsc, irow);
+        write_e0(a_row, true);
+      } else {
+        normalise_store(ph, vals, nsc, a_row);
+      }
+      TNB_TRACE(tw, step, 11);
+      publish();
+      TNB_TRACE(tw, step, 12);
+      // per-sample bookkeeping, off the critical path (the next step's MMAs are running)
       if (lead) {
         const int dtrue = nz ? e - kTcKA - kw : 0;  // exponent in units of the true recurrence
         if (mode == 0) {
@@ -378,39 +435,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
           hexp += dtrue - dsite;
         }
       }
-      const float nsc = valid ? ldexpf(1.f, kTcKA - e) : 0.f;  // normalise and apply the 2^14 operand/image scale
-      if (next_op == 1 || irow) normalise_store(ph, vals, nsc, next_op == 1, irow);
-      if (next_op == 2) write_e0(true, nullptr);
-      publish();
       ++step;
     };
 
     if (!adjoint) {
       // ---------------- forward program ----------------
       int esumR = 0, esumL = 0;
-      write_e0(true, img_row(A.fimg, L));
-      write_e0(false, img_row(A.fimg, 0));
+      write_e0(a_row, true);
+      write_e0(img_row(A.fimg, L), valid);
+      write_e0(img_row(A.fimg, 0), valid);
       publish();
       for (int i = 0; i < nR; ++i) {
         const int site = L - 1 - i;
-        float ph[kMaxPhys];
-        embed_site(M.emb, valid ? M.x[bs * L + site] : 0.5f, ph);
-        chain_step(site, A.kW[mps_slab(M, site)], ph, 0, esumR, i == nR - 1 ? 2 : 1, img_row(A.fimg, site));
+        float ph[D];
+        embed_site_d<D>(M.emb, valid ? M.x[bs * L + site] : 0.5f, ph);
+        const bool last = i == nR - 1;
+        chain_step(site, A.kW[mps_slab(M, site)], ph, 0, esumR, last, last ? img_row(A.fimg, site) : nullptr);
       }
       for (int i = 0; i < nL; ++i) {
         const int site = i;
-        float ph[kMaxPhys];
-        embed_site(M.emb, valid ? M.x[bs * L + site] : 0.5f, ph);
-        chain_step(site, A.kW[mps_slab(M, site)], ph, 0, esumL, 1, img_row(A.fimg, site + 1));
+        float ph[D];
+        embed_site_d<D>(M.emb, valid ? M.x[bs * L + site] : 0.5f, ph);
+        chain_step(site, A.kW[mps_slab(M, site)], ph, 0, esumL, false, nullptr);
       }
       // ---------------- class site + head ----------------
       float phc[D];
-      {
-        float phl[kMaxPhys];
-        embed_site(M.emb, valid ? M.x[bs * L + c] : 0.5f, phl);
-#pragma unroll
-        for (int s = 0; s < D; ++s) phc[s] = phl[s];
-      }
+      embed_site_d<D>(M.emb, valid ? M.x[bs * L + c] : 0.5f, phc);
       const uint8_t *fr = img_row(A.fimg, c + 1);  // each thread wrote its own column groups of that row (scale 2^14)
       const float ysc = ldexpf(1.f, -(2 * kTcKA + A.kW[c]));
       float y[kMaxOut];
@@ -419,20 +469,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
         int hprev = -1;
 #pragma unroll
         for (int i = 0; i < SLOTS; ++i) {
-          if (!son[i]) continue;
+          if (i >= nmine) continue;
+          const int j = 4 * i + grp;
           float f[16];
-          if (fr) load_img16(fr, 4 * i + grp, f);
+          if (fr) load_img16(fr, j, f);
           else {
 #pragma unroll
             for (int q = 0; q < 16; ++q) f[q] = 0.f;
           }
-          if (sh[i] != hprev) {
-            ptx::mbar_wait(&acc_full[sh[i]], step & 1);
+          const int h = (int)gchunk[j];
+          if (h != hprev) {
+            ptx::mbar_wait(&acc_full[h], step & 1);
             ptx::tc_fence_after();
-            hprev = sh[i];
+            hprev = h;
           }
           float o[16];
-          tc_combine16<D>(scol[i], (uint32_t)chi_h, phc, o);
+          tc_combine16<D>(trow + gcol[j], (uint32_t)chi_h, phc, o);
 #pragma unroll
           for (int q = 0; q < 16; ++q) acc = fmaf(o[q], f[q], acc);
         }
@@ -482,12 +534,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
         for (int k = 0; k < C; ++k) dy[k] = valid ? dy[k] * M.loss_scale : 0.f;
       }
       float phc[D];
-      {
-        float phl[kMaxPhys];
-        embed_site(M.emb, valid ? M.x[bs * L + c] : 0.5f, phl);
-#pragma unroll
-        for (int s = 0; s < D; ++s) phc[s] = phl[s];
-      }
+      embed_site_d<D>(M.emb, valid ? M.x[bs * L + c] : 0.5f, phc);
       float dmax = 0.f;
       for (int k = 0; k < C; ++k) dmax = fmaxf(dmax, fabsf(dy[k]));
       int ed = 0;
@@ -495,6 +542,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       if (valid && lead) {
         // class-site dA weights: wqc[(s,k)][b] = phi_s * dy'_k ; both halves write identical values
         int qm = INT_MIN;
+#pragma unroll
         for (int s = 0; s < D; ++s)
           for (int k = 0; k < C; ++k) {
             const float w = phc[s] * dy[k];
@@ -514,12 +562,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
         if (k < C - 1) {
           ptx::mbar_wait(&acc_full[NH - 1], step & 1);  // MMAs of step k have finished reading the operand
           ptx::tc_fence_after();
+          operand_free();
           write_operand_from_image(vrow, dy[k + 1] * dsc);
           publish();
           ++step;
         } else {
-          // all C slabs accumulated: normalise -> seed G[c] / G[c+1]
-          uint8_t *girow = img_row(A.gimg, half == 0 ? c : c + 1);
+          // all C slabs accumulated: normalise -> seed G[c] / G[c+1] (the next operand; the image writer stashes it)
           float vals[KEEP][16];
           float m = gather(phc, vals);
           {
@@ -531,25 +579,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
           if (nz) frexpf(m, &e);
           h = (nz ? e - kTcKA - A.kW[c] : 0) + ed;  // G = normalised row * 2^h (the operand carried dy * 2^-ed)
           const float nsc = valid ? ldexpf(1.f, kTcKA - e) : 0.f;
-          normalise_store(phc, vals, nsc, nchain > 0, girow);
+          operand_free();
+          normalise_store(phc, vals, nsc, a_row);
           publish();
           ++step;
         }
       }
       for (int i = 0; i < nchain; ++i) {
         const int site = half == 0 ? c - 1 - i : c + 1 + i;
-        const int bond_out = half == 0 ? site : site + 1;
-        float ph[kMaxPhys];
-        embed_site(M.emb, valid ? M.x[bs * L + site] : 0.5f, ph);
-        chain_step(site, A.kW[mps_slab(M, site)], ph, 1, h, i == nchain - 1 ? 0 : 1, img_row(A.gimg, bond_out));
+        float ph[D];
+        embed_site_d<D>(M.emb, valid ? M.x[bs * L + site] : 0.5f, ph);
+        chain_step(site, A.kW[mps_slab(M, site)], ph, 1, h, false, nullptr);
       }
       // boundary site weights
       if (lead) {
         int qm = INT_MIN;
         if (valid) {
           const int q = h - M.exps[(size_t)jb * M.B + b];
-          float ph[kMaxPhys];
-          embed_site(M.emb, M.x[(size_t)b * L + jb], ph);
+          float ph[D];
+          embed_site_d<D>(M.emb, M.x[(size_t)b * L + jb], ph);
 #pragma unroll
           for (int s = 0; s < D; ++s) A.wq[((size_t)jb * D + s) * M.B + b] = ph[s] * ldexpf(1.f, q);
           qm = q;

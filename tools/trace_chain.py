@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""In-kernel timeline of the tcgen05 chain kernel (measurement aid).
+
+Builds a second copy of the library with -DTNB_TC_TRACE (tools/libtn4ml_b200_trace.so), runs one forward+backward of
+cfg 5 at a small batch and prints, for CTA (0,0) of the LAST chain launch (the adjoint), clock64() deltas per step:
+    mma: a_ready seen -> chunk commits issued;  epilogue warps 0 / 15 / 6: chunk h seen, gather done, exchange done,
+    bookkeeping done, stores done, published.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+SO = os.path.join(ROOT, "tools", "libtn4ml_b200_trace.so")
+
+
+def build():
+    cmd = ["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+           "-Xcompiler", "-fPIC", "-shared", "-DTNB_TC_TRACE", os.path.join(ROOT, "tn4ml_b200/csrc/api.cu"), "-o", SO, "-lcuda"]
+    subprocess.run(cmd, check=True)
+
+
+if __name__ == "__main__":
+    if "--build" in sys.argv:
+        build()
+        sys.exit(0)
+    import torch
+    from tn4ml_b200 import _lib
+    _lib.LIB_PATH = SO
+    from tools.bench_configs import CONFIGS, run
+    cfg = dict(CONFIGS["cfg5"])
+    cfg["B"] = int(os.environ.get("TRACE_B", "18944"))
+    fwd_only = "--fwd" in sys.argv
+    run("cfg5", cfg, torch.float32, steps=1, warmup=1)
+    lib = _lib.lib()
+    lib.tnb_debug_trace_read.restype = C.c_int
+    n = 64 * 32
+    buf = (C.c_longlong * n)()
+    assert lib.tnb_debug_trace_read(buf, n) == 0
+    prev_pub = None
+    for st in range(32):
+        row = buf[st * 64:(st + 1) * 64]
+        mma = row[48:64]
+        t0 = mma[0]
+        if t0 == 0:
+            continue
+        def rel(v):
+            return "-" if v == 0 else str(v - t0)
+        line = f"step {20 + st:3d} mma: aready=0 commits=" + ",".join(rel(v) for v in mma[1:5])
+        for w, name in ((0, "w0"), (1, "w15"), (2, "w6")):
+            e = row[w * 16:(w + 1) * 16]
+            line += f" | {name}: seen=" + ",".join(rel(v) for v in e[0:4]) + \
+                    f" gath={rel(e[8])} exch={rel(e[9])} book={rel(e[10])} store={rel(e[11])} pub={rel(e[12])}"
+        if prev_pub:
+            line += f" | step_len={t0 - prev_pub}"
+        prev_pub = t0
+        print(line)
