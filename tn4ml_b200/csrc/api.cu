@@ -247,19 +247,19 @@ static void fill_tc_args(const MpsPlan &P, void *ws, const MpsArgs<float> &M, Tc
   T.stage_bytes = P.tc_stage_bytes; T.site_img_bytes = P.tc_site_img;
 }
 
-template <int D, int SLOTS, int KEEP> static cudaError_t tc_set_attr() {
+template <int D, int SLOTS> static cudaError_t tc_set_attr() {
   static std::once_flag once;
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [] {
-    err = cudaFuncSetAttribute(tc_chain_kernel<D, SLOTS, KEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    err = cudaFuncSetAttribute(tc_chain_kernel<D, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   });
   return err;
 }
 
-template <int D, int SLOTS, int KEEP>
+template <int D, int SLOTS>
 static cudaError_t tc_launch_one(dim3 grid, size_t smem, const TcArgs &T, int adjoint, cudaStream_t st) {
-  cudaError_t e = tc_set_attr<D, SLOTS, KEEP>();
-  if (e == cudaSuccess) tc_chain_kernel<D, SLOTS, KEEP><<<grid, kTcThreads, smem, st>>>(T, adjoint);
+  cudaError_t e = tc_set_attr<D, SLOTS>();
+  if (e == cudaSuccess) tc_chain_kernel<D, SLOTS><<<grid, kTcThreads, smem, st>>>(T, adjoint);
   return e;
 }
 
@@ -271,11 +271,11 @@ static int tc_launch_sweep(const tnb_problem *p, const MpsPlan &P, const TcArgs 
   const bool wide = p->chi > 128;  // 16-column groups per epilogue thread: 4 (chi <= 256) or 2 (chi <= 128)
   prof_begin(st);
   switch (p->d) {
-    case 2: e = wide ? tc_launch_one<2, 4, 3>(grid, P.tc_smem, T, adjoint, st) : tc_launch_one<2, 2, 2>(grid, P.tc_smem, T, adjoint, st); break;
-    case 3: e = wide ? tc_launch_one<3, 4, 3>(grid, P.tc_smem, T, adjoint, st) : tc_launch_one<3, 2, 2>(grid, P.tc_smem, T, adjoint, st); break;
-    case 4: e = tc_launch_one<4, 2, 2>(grid, P.tc_smem, T, adjoint, st); break;
-    case 6: e = tc_launch_one<6, 2, 2>(grid, P.tc_smem, T, adjoint, st); break;
-    case 8: e = tc_launch_one<8, 2, 2>(grid, P.tc_smem, T, adjoint, st); break;
+    case 2: e = wide ? tc_launch_one<2, 4>(grid, P.tc_smem, T, adjoint, st) : tc_launch_one<2, 2>(grid, P.tc_smem, T, adjoint, st); break;
+    case 3: e = wide ? tc_launch_one<3, 4>(grid, P.tc_smem, T, adjoint, st) : tc_launch_one<3, 2>(grid, P.tc_smem, T, adjoint, st); break;
+    case 4: e = tc_launch_one<4, 2>(grid, P.tc_smem, T, adjoint, st); break;
+    case 6: e = tc_launch_one<6, 2>(grid, P.tc_smem, T, adjoint, st); break;
+    case 8: e = tc_launch_one<8, 2>(grid, P.tc_smem, T, adjoint, st); break;
     default: return fail("tensor path: unsupported physical dimension %d", p->d);
   }
   if (e != cudaSuccess) return fail("cudaFuncSetAttribute(tc_chain): %s", cudaGetErrorString(e));

@@ -16,9 +16,8 @@
 // shared-memory operand layout (canonical K-major, no swizzle), so one 1-D bulk async copy
 // (TMA engine) moves a whole pipeline stage and completes on an mbarrier.
 //
-// Warp roles of the chain kernel (608 threads; mps_tc_chain.cuh): warps 0-15 epilogue (four threads per
-// sample row == TMEM lane), warp 16 TMEM owner + MMA issuer, warp 17 bulk-copy producer (weights in),
-// warp 18 bulk-copy image writer (environments out).
+// Warp roles of the chain kernel (576 threads; mps_tc_chain.cuh): warps 0-15 epilogue (four threads per
+// sample row == TMEM lane), warp 16 TMEM owner + MMA issuer, warp 17 bulk-copy producer.
 #pragma once
 #include <cuda_fp16.h>
 #include <limits.h>
@@ -31,8 +30,8 @@ namespace tnb {
 constexpr int kTcRows = 128;   // samples per CTA == TMEM lanes
 constexpr int kTcKA = 14;      // A operand pre-scale: |v| < 1  ->  |v * 2^14| < 2^14 (fp16 max 65504)
 constexpr int kTcEpiWarps = 16;                      // 4 lane quarters x 4 column groups
-constexpr int kTcMmaWarp = kTcEpiWarps;              // + 1: weight producer warp, + 2: image writer warp
-constexpr int kTcThreads = (kTcEpiWarps + 3) * 32;
+constexpr int kTcMmaWarp = kTcEpiWarps;              // + 1: the bulk-copy producer warp
+constexpr int kTcThreads = (kTcEpiWarps + 2) * 32;
 constexpr int kTcMaxNH = 16;                         // column chunks per step (chi / 16 at most)
 
 struct TcArgs {
@@ -45,7 +44,7 @@ struct TcArgs {
   // Environment stash of the tensor path: fp16 hi/lo images (value * 2^14, rows normalised), one per bond, laid out
   // [slot][sample block of 8][plane hi|lo][chi/8 octets][8 samples][8 halves]: the 16-byte unit is 8 consecutive bond
   // indices of one sample.  A tile of 128 samples is byte-identical to the chain kernel's shared-memory A operand
-  // (K-major, LBO 128, SBO chi*32), so it leaves the SM as one bulk copy; a run of 32 samples is an MN-major operand
+  // (K-major, LBO 128, SBO chi*32); a run of 32 samples is an MN-major operand
   // tile of the dA GEMM (K-block stride chi*32, octet stride 128).  fimg: forward environments, gimg: adjoints.
   uint8_t *fimg, *gimg;
   size_t img_bond_bytes;

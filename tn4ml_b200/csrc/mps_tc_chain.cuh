@@ -20,19 +20,24 @@
 // (TMEM column h*NMMA + s*chi/NH + n - h*chi/NH) and has its own commit barrier, so the epilogue
 // of chunk h runs underneath the MMAs of chunk h+1.
 //
-// Warp roles (608 threads):
+// Warp roles (576 threads):
 //   warps 0-15  epilogue.  A TMEM lane quarter is only visible to warps with warp % 4 == quarter, so the four
 //               warps {q, q+4, q+8, q+12} share the 32 sample rows of quarter q and split a row's 16-column
-//               groups between them (group j belongs to warp group j % 4).  Every thread keeps its outputs in
-//               registers: ONE pass over TMEM produces the phi-contracted row, the row maximum is combined
-//               through a 4 KB shared-memory exchange and a 128-thread named barrier per lane quarter, and the
-//               normalised fp16 hi/lo operand is written straight from registers to shared memory.
+//               groups between them (group j belongs to warp group j % 4).  ONE pass over TMEM: a group is
+//               phi-contracted, scaled by ITS OWN power of two and split into fp16 hi/lo at once (the expensive
+//               part, done under the MMAs of the following chunks); the packed halves are parked in the TMEM
+//               columns they came from (tcgen05.st; only their own thread ever reads those columns), so no
+//               thread carries more than one group in registers.  When the last chunk is in, the row maximum is
+//               combined through a 4 KB shared-memory exchange and a 128-thread named barrier per lane quarter,
+//               each group is brought back, moved to the row's common exponent by one exact half2 multiply per
+//               register, and written to shared memory as the next operand.  After the next step's MMAs have
+//               been released the operand row is copied to the HBM stash (shared -> global, off the critical path).
 //   warp 16     TMEM owner + MMA issuer.
 //   warp 17     weight producer: one bulk copy global -> shared per pipeline stage.
-//   warp 18     image writer: the new A operand IS the bond image of these 128 samples (same bytes), so it goes to
-//               the HBM stash as one bulk copy shared -> global while the next step's MMAs run.  (Written with
-//               per-thread stores from the epilogue, those 128 KB per step sat on the critical path: measured
-//               4.5 k of 22 k cycles per step, the per-SM store bandwidth.)
+//
+// Measured steps of this design (in-kernel clock64 trace, tools/trace_chain.py, cfg 5): two TMEM passes with
+// 4 epilogue warps: MMA 7 us + epilogue 8.5 us per step; 16 warps, one pass, stores on the critical path:
+// 13.4 k + 8.4 k cycles; (this version) see DESIGN.md.
 //
 // Environments are carried as (mantissa row, integer exponent): every epilogue renormalises the
 // row to max-abs in [0.5, 1) by an exact power of two, which is also what keeps the fp16 hi/lo
@@ -80,9 +85,39 @@ __device__ __forceinline__ void tc_combine16(uint32_t col, uint32_t cstride, con
   }
 }
 
-// SLOTS: 16-column groups per epilogue thread; the first KEEP of them stay in registers between the maximum and the
-// normalisation, the others are read from TMEM a second time (640 allocated threads leave 96 registers per thread).
-template <int D, int SLOTS, int KEEP>
+// 16 fp32 values -> scaled by 2^(14 - e) with e = frexp exponent of their own max-abs -> fp16 hi/lo octets.
+// pk[2*o + plane]: octet o (values 8o..8o+7), plane 0 = hi, 1 = lo.  Returns the max-abs; *ex = e (0 if the group is zero
+// or `on` is false, in which case the packed group is zero).
+__device__ __forceinline__ float tc_pack16(const float (&v)[16], bool on, uint4 (&pk)[4], int *ex) {
+  float m = 0.f;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) m = fmaxf(m, fabsf(v[q]));
+  const int ef = (int)((__float_as_uint(m) >> 23) & 0xffu);  // biased exponent; m = f * 2^(ef - 126), f in [0.5, 1)
+  const bool ok = on && ef >= 16;                            // (smaller than 2^-110: flushed, never seen in practice)
+  const float sc = ok ? __uint_as_float((uint32_t)(127 + 126 + kTcKA - ef) << 23) : 0.f;
+  *ex = ok ? ef - 126 : 0;
+  float w[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) w[q] = v[q] * sc;
+  split8(w, pk[0], pk[1]);
+  split8(w + 8, pk[2], pk[3]);
+  return ok ? m : 0.f;
+}
+
+// multiply the 8 halves of each register by 2^k (k <= 0; exact unless the result is subnormal)
+__device__ __forceinline__ void tc_rescale(uint4 (&pk)[4], int k) {
+  if (k == 0) return;
+  const __half2 f = __float2half2_rn(k < -40 ? 0.f : __uint_as_float((uint32_t)(127 + k) << 23));
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    __half2 *h = reinterpret_cast<__half2 *>(&pk[r]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) h[q] = __hmul2(h[q], f);
+  }
+}
+
+// SLOTS: the largest number of 16-column groups an epilogue thread owns (chi / 64).
+template <int D, int SLOTS>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int adjoint) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const MpsArgs<float> &M = A.M;
@@ -119,23 +154,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
     }
     return (tr ? A.img_t : A.img_n) + (size_t)slab * A.site_img_bytes;
   };
-  // step -> bond whose image is the operand this step's epilogue leaves in shared memory (-1: none / not stashed).
-  // (The last right-chain step of the forward program replaces the operand by e0: its image is stored by the
-  // epilogue threads themselves.)
-  auto step_out_bond = [&](int step) -> int {
-    if (!adjoint) {
-      if (!A.img_stash) return -1;
-      if (step < nR) return step == nR - 1 ? -1 : L - 1 - step;
-      if (step < nR + nL) return step - nR + 1;
-      return -1;
-    }
-    if (step < nseed - 1) return -1;
-    if (step == nseed - 1) return half == 0 ? c : c + 1;
-    const int i = step - nseed;
-    return half == 0 ? c - 1 - i : c + 2 + i;
-  };
 
-  // A operand = bond image of this CTA's 128 rows: unit (row, octet o, plane p) at (row/8)*chi*32 + p*chi*16 + o*128 + (row%8)*16
+  // A operand, in the layout of a bond image: unit (row, octet o, plane p) at (row/8)*chi*32 + p*chi*16 + o*128 + (row%8)*16
   const uint32_t a_bytes = (uint32_t)kTcRows * chi * 4;
   uint8_t *a_op = smem;
   uint8_t *stages = smem + a_bytes;
@@ -144,8 +164,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
   uint32_t *gchunk = gcol + 16;                                                       // [16] group -> column chunk
   uint64_t *bars = reinterpret_cast<uint64_t *>(gchunk + 16);
   uint64_t *full = bars, *empty = bars + A.nstage, *acc_full = bars + 2 * A.nstage, *a_ready = acc_full + kTcMaxNH;
-  uint64_t *img_done = a_ready + 1;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(img_done + 1);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_ready + 1);
 
   if (tid == 0) {
     for (int i = 0; i < A.nstage; ++i) {
@@ -154,7 +173,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
     }
     for (int h = 0; h < NH; ++h) ptx::mbar_init(&acc_full[h], 1);
     ptx::mbar_init(a_ready, kTcEpiWarps);
-    ptx::mbar_init(img_done, 1);
     ptx::fence_mbar_init();
   }
   if (tid < 16) {
@@ -173,24 +191,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
   const uint32_t tmem_base = *tmem_slot;
   const int KS = chi / 16;
 
-  if (warp == kTcMmaWarp + 2) {
-    // ===== image writer: operand generation g (published as phase g of a_ready) -> HBM stash =====
-    if (lane == 0) {
-      uint8_t *base = adjoint ? A.gimg : A.fimg;
-      const size_t tile_off = (size_t)(b0 >> 3) * chi * 32;
-      for (int g = 0; g <= total; ++g) {
-        ptx::mbar_wait(a_ready, g & 1);
-        const int bond = g > 0 ? step_out_bond(g - 1) : -1;
-        if (bond >= 0 && base) {
-          ptx::bulk_s2g(base + (size_t)bond * A.img_bond_bytes + tile_off, a_op, a_bytes);
-          ptx::bulk_commit();
-          ptx::bulk_wait_read0();
-        }
-        ptx::mbar_arrive(img_done);  // the operand may be overwritten
-      }
-      ptx::bulk_wait0();
-    }
-  } else if (warp == kTcMmaWarp + 1) {
+  if (warp == kTcMmaWarp + 1) {
     // ===== weight producer: one bulk async copy per pipeline stage (= one K-slab of one column chunk) =====
     if (lane == 0) {
       int stage = 0;
@@ -265,14 +266,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       if (slot < 0 || base == nullptr) return nullptr;
       return base + (size_t)slot * A.img_bond_bytes + tc_img_row(b, chi);
     };
-    // w (already scaled by 2^14) -> fp16 hi/lo octets -> the unit row `dst` (operand row in smem or image row in HBM)
-    auto store_op16 = [&](int j, const float(&w)[16], uint8_t *dst) {
-      uint4 hi, lo;
+    // packed group j -> the unit row `dst` (operand row in smem or image row in HBM)
+    auto store_pk = [&](int j, const uint4(&pk)[4], uint8_t *dst) {
 #pragma unroll
       for (int o = 0; o < 2; ++o) {
-        split8(w + 8 * o, hi, lo);
-        *reinterpret_cast<uint4 *>(dst + (2 * j + o) * 128) = hi;
-        *reinterpret_cast<uint4 *>(dst + lo_off + (2 * j + o) * 128) = lo;
+        *reinterpret_cast<uint4 *>(dst + (2 * j + o) * 128) = pk[2 * o];
+        *reinterpret_cast<uint4 *>(dst + lo_off + (2 * j + o) * 128) = pk[2 * o + 1];
+      }
+    };
+    // my groups of the operand row (shared memory) -> image row in the HBM stash
+    auto stash_row = [&](uint8_t *irow) {
+      if (!irow) return;
+#pragma unroll
+      for (int i = 0; i < SLOTS; ++i) {
+        if (i >= nmine) continue;
+        const int j = 4 * i + grp;
+        uint4 pk[4];
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          pk[2 * o] = *reinterpret_cast<const uint4 *>(a_row + (2 * j + o) * 128);
+          pk[2 * o + 1] = *reinterpret_cast<const uint4 *>(a_row + lo_off + (2 * j + o) * 128);
+        }
+        store_pk(j, pk, irow);
       }
     };
     // 16 values of an image row: hi + lo (exact in fp32), still carrying the 2^14 image scale
@@ -319,7 +334,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
         }
 #pragma unroll
         for (int q = 0; q < 16; ++q) w[q] *= scale;
-        store_op16(j, w, a_row);
+        uint4 pk[4];
+        split8(w, pk[0], pk[1]);
+        split8(w + 8, pk[2], pk[3]);
+        store_pk(j, pk, a_row);
       }
     };
     auto publish = [&]() {  // operand (and TMEM reads) done -> the MMA warp may start the next step
@@ -328,8 +346,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(a_ready);
     };
-    // the image writer has finished reading the operand of this step (it may be overwritten)
-    auto operand_free = [&]() { ptx::mbar_wait(img_done, step & 1); };
     // combine one float per thread across the 4 threads of a row (through smem, fixed order)
     auto row_exchange = [&](float v) -> const float * {
       float *x = xch + (step & 1) * (4 * kTcRows);
@@ -337,12 +353,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       ptx::named_bar_sync(1 + lq, 4 * 32);
       return x + row;
     };
-    // wait for the column chunks holding my groups and contract them with phi: vals[i][*] (i < KEEP), row max of my part
-    auto gather = [&](const float(&ph)[D], float(&vals)[KEEP][16]) -> float {
+    // Wait for the column chunks holding my groups, contract them with phi and pack each group at its own exponent
+    // (parked in TMEM, except my last group); then bring the row to its common exponent and write it to `dst`
+    // (operand row in smem, image row in HBM, or null).  Returns the row's frexp exponent e (0 for a zero / invalid row).
+    auto gather_pack = [&](const float(&ph)[D], uint8_t *dst, bool *nonzero) -> int {
       float m = 0.f;
       int hprev = -1;
+      int ex[SLOTS];
+      uint4 pkl[4];
 #pragma unroll
       for (int i = 0; i < SLOTS; ++i) {
+        ex[i] = 0;
         if (i >= nmine) continue;
         const int j = 4 * i + grp;
         const int h = (int)gchunk[j];
@@ -352,71 +373,65 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
           hprev = h;
           TNB_TRACE(tw, step, h);
         }
-        if (i < KEEP) {
-          tc_combine16<D>(trow + gcol[j], (uint32_t)chi_h, ph, vals[i < KEEP ? i : 0]);
+        float o[16];
+        tc_combine16<D>(trow + gcol[j], (uint32_t)chi_h, ph, o);
+        uint4 pk[4];
+        m = fmaxf(m, tc_pack16(o, valid, pk, &ex[i]));
+        if (i == nmine - 1) {
 #pragma unroll
-          for (int q = 0; q < 16; ++q) m = fmaxf(m, fabsf(vals[i < KEEP ? i : 0][q]));
+          for (int r = 0; r < 4; ++r) pkl[r] = pk[r];
         } else {
-          float o[16];
-          tc_combine16<D>(trow + gcol[j], (uint32_t)chi_h, ph, o);
-#pragma unroll
-          for (int q = 0; q < 16; ++q) m = fmaxf(m, fabsf(o[q]));
+          ptx::tmem_st16(trow + gcol[j], *reinterpret_cast<const uint32_t(*)[16]>(&pk[0]));
         }
       }
+      ptx::tmem_st_wait();
       if (hprev != NH - 1) {  // every thread has seen the whole step complete before it publishes
         ptx::mbar_wait(&acc_full[NH - 1], step & 1);
         ptx::tc_fence_after();
       }
-      return m;
-    };
-    auto normalise_store = [&](const float(&ph)[D], float(&vals)[KEEP][16], float nsc, uint8_t *dst) {
-#pragma unroll
-      for (int i = 0; i < SLOTS; ++i) {
-        if (i >= nmine) continue;
-        const int j = 4 * i + grp;
-        if (i < KEEP) {
-#pragma unroll
-          for (int q = 0; q < 16; ++q) vals[i < KEEP ? i : 0][q] *= nsc;
-          store_op16(j, vals[i < KEEP ? i : 0], dst);
-        } else {
-          float o[16];
-          tc_combine16<D>(trow + gcol[j], (uint32_t)chi_h, ph, o);
-#pragma unroll
-          for (int q = 0; q < 16; ++q) o[q] *= nsc;
-          store_op16(j, o, dst);
-        }
-      }
-    };
-    // One chain step.  mode 0: forward (records delta)   mode 1: adjoint (records wq/qmax).
-    // `hexp` is the forward exponent sum (mode 0) or the running exponent h of the adjoint (mode 1); lead thread only.
-    // to_e0: the next operand is the boundary vector e0 and the normalised row goes to its image `irow` directly
-    // (end of the right chain); otherwise the row becomes the next operand and the image writer stashes it.
-    auto chain_step = [&](int site, int kw, const float(&ph)[D], int mode, int &hexp, bool to_e0, uint8_t *irow) {
-      const int dsite = (mode == 1 && valid && lead) ? M.exps[(size_t)site * M.B + b] : 0;
-      float vals[KEEP][16];
-      float m = gather(ph, vals);
       TNB_TRACE(tw, step, 8);
       {
         const float *x = row_exchange(m);
         m = fmaxf(fmaxf(x[0], x[kTcRows]), fmaxf(x[2 * kTcRows], x[3 * kTcRows]));
       }
       TNB_TRACE(tw, step, 9);
-      int e = 0;
-      const bool nz = m > 0.f && valid;
-      if (nz) frexpf(m, &e);
-      const float nsc = valid ? ldexpf(1.f, kTcKA - e) : 0.f;  // normalise and apply the 2^14 operand/image scale
-      operand_free();
-      TNB_TRACE(tw, step, 10);
-      if (to_e0) {
-        if (irow) normalise_store(ph, vals, nsc, irow);
-        write_e0(a_row, true);
-      } else {
-        normalise_store(ph, vals, nsc, a_row);
+      const bool nz = m > 0.f;
+      const int e = nz ? (int)((__float_as_uint(m) >> 23) & 0xffu) - 126 : 0;
+      if (dst) {
+#pragma unroll
+        for (int i = 0; i < SLOTS; ++i) {
+          if (i >= nmine) continue;
+          const int j = 4 * i + grp;
+          if (i == nmine - 1) {
+            tc_rescale(pkl, nz ? ex[i] - e : 0);
+            store_pk(j, pkl, dst);
+          } else {
+            uint4 pk[4];
+            ptx::tmem_ld16u(trow + gcol[j], *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
+            ptx::tmem_ld_wait();
+            tc_rescale(pk, nz ? ex[i] - e : 0);
+            store_pk(j, pk, dst);
+          }
+        }
       }
+      *nonzero = nz;
+      return e;
+    };
+    // One chain step.  mode 0: forward (records delta)   mode 1: adjoint (records wq/qmax).
+    // `hexp` is the forward exponent sum (mode 0) or the running exponent h of the adjoint (mode 1); lead thread only.
+    // next_op: 1 = the normalised row becomes the next operand, 2 = the boundary vector e0 does (the row only goes to
+    // its image).  irow: image row of the output bond in the HBM stash (or null).
+    auto chain_step = [&](int site, int kw, const float(&ph)[D], int mode, int &hexp, int next_op, uint8_t *irow) {
+      const int dsite = (mode == 1 && valid && lead) ? M.exps[(size_t)site * M.B + b] : 0;
+      bool nz;
+      const int e = gather_pack(ph, next_op == 2 ? irow : a_row, &nz);
+      TNB_TRACE(tw, step, 10);
+      if (next_op == 2) write_e0(a_row, true);
       TNB_TRACE(tw, step, 11);
       publish();
       TNB_TRACE(tw, step, 12);
-      // per-sample bookkeeping, off the critical path (the next step's MMAs are running)
+      // off the critical path (the next step's MMAs are running): the stash copy and the per-sample bookkeeping
+      if (next_op != 2) stash_row(irow);
       if (lead) {
         const int dtrue = nz ? e - kTcKA - kw : 0;  // exponent in units of the true recurrence
         if (mode == 0) {
@@ -449,14 +464,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
         const int site = L - 1 - i;
         float ph[D];
         embed_site_d<D>(M.emb, valid ? M.x[bs * L + site] : 0.5f, ph);
-        const bool last = i == nR - 1;
-        chain_step(site, A.kW[mps_slab(M, site)], ph, 0, esumR, last, last ? img_row(A.fimg, site) : nullptr);
+        chain_step(site, A.kW[mps_slab(M, site)], ph, 0, esumR, i == nR - 1 ? 2 : 1, img_row(A.fimg, site));
       }
       for (int i = 0; i < nL; ++i) {
         const int site = i;
         float ph[D];
         embed_site_d<D>(M.emb, valid ? M.x[bs * L + site] : 0.5f, ph);
-        chain_step(site, A.kW[mps_slab(M, site)], ph, 0, esumL, false, nullptr);
+        chain_step(site, A.kW[mps_slab(M, site)], ph, 0, esumL, 1, img_row(A.fimg, site + 1));
       }
       // ---------------- class site + head ----------------
       float phc[D];
@@ -562,34 +576,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
         if (k < C - 1) {
           ptx::mbar_wait(&acc_full[NH - 1], step & 1);  // MMAs of step k have finished reading the operand
           ptx::tc_fence_after();
-          operand_free();
           write_operand_from_image(vrow, dy[k + 1] * dsc);
           publish();
           ++step;
         } else {
-          // all C slabs accumulated: normalise -> seed G[c] / G[c+1] (the next operand; the image writer stashes it)
-          float vals[KEEP][16];
-          float m = gather(phc, vals);
-          {
-            const float *x = row_exchange(m);
-            m = fmaxf(fmaxf(x[0], x[kTcRows]), fmaxf(x[2 * kTcRows], x[3 * kTcRows]));
-          }
-          int e = 0;
-          const bool nz = m > 0.f && valid;
-          if (nz) frexpf(m, &e);
+          // all C slabs accumulated: normalise -> seed G[c] / G[c+1] (operand of the first chain step, and its image)
+          bool nz;
+          const int e = gather_pack(phc, a_row, &nz);
           h = (nz ? e - kTcKA - A.kW[c] : 0) + ed;  // G = normalised row * 2^h (the operand carried dy * 2^-ed)
-          const float nsc = valid ? ldexpf(1.f, kTcKA - e) : 0.f;
-          operand_free();
-          normalise_store(phc, vals, nsc, a_row);
           publish();
+          stash_row(img_row(A.gimg, half == 0 ? c : c + 1));
           ++step;
         }
       }
       for (int i = 0; i < nchain; ++i) {
         const int site = half == 0 ? c - 1 - i : c + 1 + i;
+        const int bond_out = half == 0 ? site : site + 1;
         float ph[D];
         embed_site_d<D>(M.emb, valid ? M.x[bs * L + site] : 0.5f, ph);
-        chain_step(site, A.kW[mps_slab(M, site)], ph, 1, h, false, nullptr);
+        chain_step(site, A.kW[mps_slab(M, site)], ph, 1, h, 1, img_row(A.gimg, bond_out));
       }
       // boundary site weights
       if (lead) {
