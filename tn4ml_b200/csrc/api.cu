@@ -113,7 +113,7 @@ struct MpsPlan {
   // tensor-core sweep (f32, TNB_PREC_TENSOR)
   int tc, tc_N, tc_NH, tc_NMMA, tc_nstage, tc_cols;
   uint32_t tc_stage_bytes;
-  size_t tc_site_img, off_img_n, off_img_t, off_kW, off_wq, off_qmax, off_wqc, off_fimg, off_gimg, tc_smem, img_bond_bytes;
+  size_t tc_site_img, off_img_n, off_img_t, off_kW, off_cs, off_wq, off_qmax, off_wqc, off_fimg, off_gimg, tc_smem, img_bond_bytes;
 };
 
 // The tcgen05 sweep covers: float32, chi a multiple of 16 in [32, 256], D*chi <= 512 TMEM columns.
@@ -197,6 +197,7 @@ static MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
     P.off_img_n = take(P.tc_site_img * P.nslab);
     P.off_img_t = take(P.tc_site_img * P.nslab);
     P.off_kW = take((size_t)P.nslab * sizeof(int));
+    P.off_cs = take((size_t)2 * P.nslab * sizeof(float));
     if (need_grad) {
       P.off_wq = take((size_t)p->L * p->d * B * sizeof(float));
       P.off_qmax = take(((size_t)p->L + 1) * sizeof(int));  // [L] chain sites + [1] class site
@@ -235,6 +236,8 @@ static void fill_tc_args(const MpsPlan &P, void *ws, const MpsArgs<float> &M, Tc
   T.img_n = (const uint8_t *)(w + P.off_img_n);
   T.img_t = (const uint8_t *)(w + P.off_img_t);
   T.kW = (const int *)(w + P.off_kW);
+  T.colsum = (const float *)(w + P.off_cs);
+  { const char *e = getenv("TNB_TC_PACE_NS"); T.pace_ns = e ? atoi(e) : P.tc_N / 5; }
   T.wq = (float *)(w + P.off_wq);
   T.qmax = (int *)(w + P.off_qmax);
   T.wqc = (float *)(w + P.off_wqc);
@@ -321,6 +324,10 @@ static int mps_forward_t(const tnb_problem *p, const MpsPlan &P, long long B, co
         tc_classmin_kernel<<<1, 32, 0, st>>>((int *)Tc.kW, p->out_site, p->n_out);
         TNB_LAUNCH_CHECK("tc_classmin_kernel");
       }
+      prof_begin(st);
+      tc_colsum_kernel<<<dim3(P.nslab, 2), 256, 0, st>>>((const float *)params, Tc.kW, (float *)Tc.colsum, p->L, p->chi,
+                                                         p->d, p->n_out, p->out_site);
+      TNB_LAUNCH_CHECK("tc_colsum_kernel");
       size_t items = (size_t)P.tc_N * (p->chi / 8) * P.nslab;
       int ib = (int)((items + 255) / 256);
       if (ib > 148 * 32) ib = 148 * 32;

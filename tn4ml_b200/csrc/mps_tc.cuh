@@ -16,8 +16,9 @@
 // shared-memory operand layout (canonical K-major, no swizzle), so one 1-D bulk async copy
 // (TMA engine) moves a whole pipeline stage and completes on an mbarrier.
 //
-// Warp roles of the chain kernel (576 threads; mps_tc_chain.cuh): warps 0-15 epilogue (four threads per
-// sample row == TMEM lane), warp 16 TMEM owner + MMA issuer, warp 17 bulk-copy producer.
+// Warp roles of the chain kernel (608 threads; mps_tc_chain.cuh): warps 0-15 epilogue (four threads per
+// sample row == TMEM lane), warp 16 TMEM owner + MMA issuer, warp 17 bulk-copy producer (weights in),
+// warp 18 bulk-copy image writer (environments out).
 #pragma once
 #include <cuda_fp16.h>
 #include <limits.h>
@@ -30,8 +31,8 @@ namespace tnb {
 constexpr int kTcRows = 128;   // samples per CTA == TMEM lanes
 constexpr int kTcKA = 14;      // A operand pre-scale: |v| < 1  ->  |v * 2^14| < 2^14 (fp16 max 65504)
 constexpr int kTcEpiWarps = 16;                      // 4 lane quarters x 4 column groups
-constexpr int kTcMmaWarp = kTcEpiWarps;              // + 1: the bulk-copy producer warp
-constexpr int kTcThreads = (kTcEpiWarps + 2) * 32;
+constexpr int kTcMmaWarp = kTcEpiWarps;              // + 1: weight producer warp, + 2: image writer warp
+constexpr int kTcThreads = (kTcEpiWarps + 3) * 32;
 constexpr int kTcMaxNH = 16;                         // column chunks per step (chi / 16 at most)
 
 struct TcArgs {
@@ -39,6 +40,8 @@ struct TcArgs {
   const uint8_t *img_n;  // stage images, normal direction      [slab][NH chunks][chi/16][2 planes][NMMA*32 B]
   const uint8_t *img_t;  // stage images, transposed direction
   const int *kW;         // per-slab weight pre-scale exponent
+  const float *colsum;   // [2 directions][slab]: max_n sum_{k,s} |W[k,s,n]| * 2^kW  (bound of one chain step, see chain kernel)
+  int pace_ns;           // image writer: pause between 4 KB pieces
   float *wq;             // adjoint: phi_s[b] * 2^q[b] per (site, s, b): per-sample weight of the dA GEMM
   int *qmax;             // adjoint: max_b q[site][b]
   // Environment stash of the tensor path: fp16 hi/lo images (value * 2^14, rows normalised), one per bond, laid out
@@ -88,6 +91,37 @@ __global__ void tc_classmin_kernel(int *__restrict__ kW, int c, int C) {
   for (int k = threadIdx.x; k < C; k += 32) m = min(m, kW[c + k]);
   for (int off = 16; off > 0; off >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, off));
   for (int k = threadIdx.x; k < C; k += 32) kW[c + k] = m;
+}
+
+// colsum[dir][slab] = max_n sum_{k,s} |W[k,s,n]| * 2^kW[slab]: with |phi_s| <= 1 and an operand row of max-abs m, every
+// output of the chain step through this slab is bounded by m * colsum, which fixes the step's power-of-two scale
+// BEFORE the step runs (no row maximum on the critical path).  One block per (slab, direction), thread = column n.
+__global__ void tc_colsum_kernel(const float *__restrict__ params, const int *__restrict__ kW, float *__restrict__ colsum,
+                                 int L, int chi, int D, int C, int c) {
+  const int slab = blockIdx.x, dir = blockIdx.y, nslab = L - 1 + C;
+  int site, o, nj;
+  if (slab < c) { site = slab; o = 0; nj = 1; }
+  else if (slab < c + C) { site = c; o = slab - c; nj = C; }
+  else { site = slab - C + 1; o = 0; nj = 1; }
+  const size_t site_off = (size_t)site * chi * chi * D + (site > c ? (size_t)chi * chi * D * (C - 1) : 0);
+  float best = 0.f;
+  for (int n = threadIdx.x; n < chi; n += blockDim.x) {
+    float acc = 0.f;
+    for (int k = 0; k < chi; ++k) {
+      const int a = dir == 0 ? k : n, r = dir == 0 ? n : k;
+      const float *w = params + site_off + (((size_t)a * chi + r) * D) * nj + o;
+      for (int s = 0; s < D; ++s) acc += fabsf(w[(size_t)s * nj]);
+    }
+    best = fmaxf(best, acc);
+  }
+  __shared__ float red[32];
+  for (int off = 16; off > 0; off >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, off));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x + 31) / 32; ++w) best = fmaxf(best, red[w]);
+    colsum[dir * nslab + slab] = ldexpf(best, kW[slab]) * 1.001f;  // margin for the fp16x3 rounding of the products
+  }
 }
 
 // one thread per (slab, n', k-octet): 8 weights -> 16 B of hi and 16 B of lo, both directions.

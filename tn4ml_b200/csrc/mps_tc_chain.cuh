@@ -20,24 +20,28 @@
 // (TMEM column h*NMMA + s*chi/NH + n - h*chi/NH) and has its own commit barrier, so the epilogue
 // of chunk h runs underneath the MMAs of chunk h+1.
 //
-// Warp roles (576 threads):
+// A-priori scaling.  The next operand must be a row of bounded magnitude (fp16 range) times an exact power of two.
+// Instead of the row maximum of the outputs (a reduction on the critical path) the scale comes from a bound known
+// before the step runs: |o[n]| <= m * colsum, m = max-abs of the operand row (found while the NEXT step's MMAs run),
+// colsum = max_n sum_{k,s} |W[k,s,n]| (tc_colsum_kernel; |phi_s| <= 1).  The row then peaks a few bits below 2^14
+// (the looseness of the bound, never accumulating because m is exact), which costs nothing in fp16 hi/lo.
+//
+// Warp roles (608 threads):
 //   warps 0-15  epilogue.  A TMEM lane quarter is only visible to warps with warp % 4 == quarter, so the four
 //               warps {q, q+4, q+8, q+12} share the 32 sample rows of quarter q and split a row's 16-column
 //               groups between them (group j belongs to warp group j % 4).  ONE pass over TMEM: a group is
-//               phi-contracted, scaled by ITS OWN power of two and split into fp16 hi/lo at once (the expensive
-//               part, done under the MMAs of the following chunks); the packed halves are parked in the TMEM
-//               columns they came from (tcgen05.st; only their own thread ever reads those columns), so no
-//               thread carries more than one group in registers.  When the last chunk is in, the row maximum is
-//               combined through a 4 KB shared-memory exchange and a 128-thread named barrier per lane quarter,
-//               each group is brought back, moved to the row's common exponent by one exact half2 multiply per
-//               register, and written to shared memory as the next operand.  After the next step's MMAs have
-//               been released the operand row is copied to the HBM stash (shared -> global, off the critical path).
+//               phi-contracted, scaled and split into fp16 hi/lo as soon as its column chunk is complete (under
+//               the MMAs of the following chunks) and parked in the TMEM columns it came from (tcgen05.st; only
+//               its own thread ever touches those columns), so no thread carries more than one group in registers.
+//               When the last chunk is in, its groups are packed and everything is written to shared memory as the
+//               next operand.  Row maximum (4 KB shared-memory exchange + a 128-thread named barrier per lane
+//               quarter) and per-sample bookkeeping follow after the next step's MMAs have been released.
 //   warp 16     TMEM owner + MMA issuer.
 //   warp 17     weight producer: one bulk copy global -> shared per pipeline stage.
-//
-// Measured steps of this design (in-kernel clock64 trace, tools/trace_chain.py, cfg 5): two TMEM passes with
-// 4 epilogue warps: MMA 7 us + epilogue 8.5 us per step; 16 warps, one pass, stores on the critical path:
-// 13.4 k + 8.4 k cycles; (this version) see DESIGN.md.
+//   warp 18     image writer: the A operand IS the bond image of these 128 samples (same bytes); it goes to the HBM
+//               stash as paced 4 KB bulk copies shared -> global while the step's MMAs run.  (Per-thread stores from
+//               the epilogue put 128 KB per step on the critical path, 4.5 k cycles; one unpaced 128 KB bulk copy
+//               starved the weight loads for as long.)
 //
 // Environments are carried as (mantissa row, integer exponent): every epilogue renormalises the
 // row to max-abs in [0.5, 1) by an exact power of two, which is also what keeps the fp16 hi/lo
@@ -85,35 +89,19 @@ __device__ __forceinline__ void tc_combine16(uint32_t col, uint32_t cstride, con
   }
 }
 
-// 16 fp32 values -> scaled by 2^(14 - e) with e = frexp exponent of their own max-abs -> fp16 hi/lo octets.
-// pk[2*o + plane]: octet o (values 8o..8o+7), plane 0 = hi, 1 = lo.  Returns the max-abs; *ex = e (0 if the group is zero
-// or `on` is false, in which case the packed group is zero).
-__device__ __forceinline__ float tc_pack16(const float (&v)[16], bool on, uint4 (&pk)[4], int *ex) {
+// 16 fp32 values * sc -> fp16 hi/lo octets.  pk[2*o + plane]: octet o (values 8o..8o+7), plane 0 = hi, 1 = lo.
+// Returns the max-abs of the scaled values.
+__device__ __forceinline__ float tc_pack16(const float (&v)[16], float sc, uint4 (&pk)[4]) {
+  float w[16];
   float m = 0.f;
 #pragma unroll
-  for (int q = 0; q < 16; ++q) m = fmaxf(m, fabsf(v[q]));
-  const int ef = (int)((__float_as_uint(m) >> 23) & 0xffu);  // biased exponent; m = f * 2^(ef - 126), f in [0.5, 1)
-  const bool ok = on && ef >= 16;                            // (smaller than 2^-110: flushed, never seen in practice)
-  const float sc = ok ? __uint_as_float((uint32_t)(127 + 126 + kTcKA - ef) << 23) : 0.f;
-  *ex = ok ? ef - 126 : 0;
-  float w[16];
-#pragma unroll
-  for (int q = 0; q < 16; ++q) w[q] = v[q] * sc;
+  for (int q = 0; q < 16; ++q) {
+    w[q] = v[q] * sc;
+    m = fmaxf(m, fabsf(w[q]));
+  }
   split8(w, pk[0], pk[1]);
   split8(w + 8, pk[2], pk[3]);
-  return ok ? m : 0.f;
-}
-
-// multiply the 8 halves of each register by 2^k (k <= 0; exact unless the result is subnormal)
-__device__ __forceinline__ void tc_rescale(uint4 (&pk)[4], int k) {
-  if (k == 0) return;
-  const __half2 f = __float2half2_rn(k < -40 ? 0.f : __uint_as_float((uint32_t)(127 + k) << 23));
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    __half2 *h = reinterpret_cast<__half2 *>(&pk[r]);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) h[q] = __hmul2(h[q], f);
-  }
+  return m;
 }
 
 // SLOTS: the largest number of 16-column groups an epilogue thread owns (chi / 64).
@@ -155,6 +143,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
     return (tr ? A.img_t : A.img_n) + (size_t)slab * A.site_img_bytes;
   };
 
+  // step -> bond whose image is the operand this step's epilogue leaves in shared memory (-1: none / not stashed).
+  // (The last right-chain step of the forward program replaces the operand by e0: its image is stored by the
+  // epilogue threads themselves.)
+  auto step_out_bond = [&](int step) -> int {
+    if (!adjoint) {
+      if (!A.img_stash) return -1;
+      if (step < nR) return step == nR - 1 ? -1 : L - 1 - step;
+      if (step < nR + nL) return step - nR + 1;
+      return -1;
+    }
+    if (step < nseed - 1) return -1;
+    if (step == nseed - 1) return half == 0 ? c : c + 1;
+    const int i = step - nseed;
+    return half == 0 ? c - 1 - i : c + 2 + i;
+  };
+
   // A operand, in the layout of a bond image: unit (row, octet o, plane p) at (row/8)*chi*32 + p*chi*16 + o*128 + (row%8)*16
   const uint32_t a_bytes = (uint32_t)kTcRows * chi * 4;
   uint8_t *a_op = smem;
@@ -164,7 +168,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
   uint32_t *gchunk = gcol + 16;                                                       // [16] group -> column chunk
   uint64_t *bars = reinterpret_cast<uint64_t *>(gchunk + 16);
   uint64_t *full = bars, *empty = bars + A.nstage, *acc_full = bars + 2 * A.nstage, *a_ready = acc_full + kTcMaxNH;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_ready + 1);
+  uint64_t *img_done = a_ready + 1;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(img_done + 1);
 
   if (tid == 0) {
     for (int i = 0; i < A.nstage; ++i) {
@@ -173,6 +178,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
     }
     for (int h = 0; h < NH; ++h) ptx::mbar_init(&acc_full[h], 1);
     ptx::mbar_init(a_ready, kTcEpiWarps);
+    ptx::mbar_init(img_done, 1);
     ptx::fence_mbar_init();
   }
   if (tid < 16) {
@@ -191,7 +197,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
   const uint32_t tmem_base = *tmem_slot;
   const int KS = chi / 16;
 
-  if (warp == kTcMmaWarp + 1) {
+  if (warp == kTcMmaWarp + 2) {
+    // ===== image writer: operand generation g (published as phase g of a_ready) -> HBM stash, in paced pieces =====
+    if (lane == 0) {
+      uint8_t *base = adjoint ? A.gimg : A.fimg;
+      const size_t tile_off = (size_t)(b0 >> 3) * chi * 32;
+      constexpr uint32_t kPiece = 4096;
+      for (int g = 0; g <= total; ++g) {
+        ptx::mbar_wait(a_ready, g & 1);
+        const int bond = g > 0 ? step_out_bond(g - 1) : -1;
+        if (bond >= 0 && base) {
+          uint8_t *dst = base + (size_t)bond * A.img_bond_bytes + tile_off;
+          for (uint32_t off = 0; off < a_bytes; off += kPiece) {
+            ptx::bulk_s2g(dst + off, a_op + off, kPiece);
+            ptx::bulk_commit();
+            if (A.pace_ns > 0) __nanosleep((unsigned)A.pace_ns);
+          }
+          ptx::bulk_wait_read0();
+        }
+        ptx::mbar_arrive(img_done);  // the operand may be overwritten
+      }
+      ptx::bulk_wait0();
+    }
+  } else if (warp == kTcMmaWarp + 1) {
     // ===== weight producer: one bulk async copy per pipeline stage (= one K-slab of one column chunk) =====
     if (lane == 0) {
       int stage = 0;
@@ -274,22 +302,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
         *reinterpret_cast<uint4 *>(dst + lo_off + (2 * j + o) * 128) = pk[2 * o + 1];
       }
     };
-    // my groups of the operand row (shared memory) -> image row in the HBM stash
-    auto stash_row = [&](uint8_t *irow) {
-      if (!irow) return;
-#pragma unroll
-      for (int i = 0; i < SLOTS; ++i) {
-        if (i >= nmine) continue;
-        const int j = 4 * i + grp;
-        uint4 pk[4];
-#pragma unroll
-        for (int o = 0; o < 2; ++o) {
-          pk[2 * o] = *reinterpret_cast<const uint4 *>(a_row + (2 * j + o) * 128);
-          pk[2 * o + 1] = *reinterpret_cast<const uint4 *>(a_row + lo_off + (2 * j + o) * 128);
-        }
-        store_pk(j, pk, irow);
-      }
-    };
     // 16 values of an image row: hi + lo (exact in fp32), still carrying the 2^14 image scale
     auto load_img16 = [&](const uint8_t *irow, int j, float(&v)[16]) {
 #pragma unroll
@@ -353,17 +365,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       ptx::named_bar_sync(1 + lq, 4 * 32);
       return x + row;
     };
-    // Wait for the column chunks holding my groups, contract them with phi and pack each group at its own exponent
-    // (parked in TMEM, except my last group); then bring the row to its common exponent and write it to `dst`
-    // (operand row in smem, image row in HBM, or null).  Returns the row's frexp exponent e (0 for a zero / invalid row).
-    auto gather_pack = [&](const float(&ph)[D], uint8_t *dst, bool *nonzero) -> int {
+    // the image writer has finished reading the operand of this step (it may be overwritten)
+    auto operand_free = [&]() { ptx::mbar_wait(img_done, step & 1); };
+    const int nslab = L - 1 + C;
+    // Scale of a step whose outputs are bounded by `bnd`: 2^(14 - e), bnd = f * 2^e, f in [0.5, 1).  *e_out = e.
+    auto bound_scale = [&](float bnd, int *e_out) -> float {
+      const int ef = (int)((__float_as_uint(bnd) >> 23) & 0xffu);
+      const bool ok = valid && ef >= 16 && ef < 255;  // (a zero row, or one below 2^-110: flushed)
+      *e_out = ok ? ef - 126 : 0;
+      return ok ? __uint_as_float((uint32_t)(127 + 126 + kTcKA - ef) << 23) : 0.f;
+    };
+    // Wait for the column chunks holding my groups, contract them with phi, scale by sc and split to fp16 hi/lo
+    // (parked in TMEM, except my last group); then write the row to `dst` (operand row in smem or image row in HBM).
+    // Returns the max-abs of my part of the scaled row.
+    auto gather_pack = [&](const float(&ph)[D], float sc, uint8_t *dst) -> float {
       float m = 0.f;
       int hprev = -1;
-      int ex[SLOTS];
       uint4 pkl[4];
 #pragma unroll
       for (int i = 0; i < SLOTS; ++i) {
-        ex[i] = 0;
         if (i >= nmine) continue;
         const int j = 4 * i + grp;
         const int h = (int)gchunk[j];
@@ -376,7 +396,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
         float o[16];
         tc_combine16<D>(trow + gcol[j], (uint32_t)chi_h, ph, o);
         uint4 pk[4];
-        m = fmaxf(m, tc_pack16(o, valid, pk, &ex[i]));
+        m = fmaxf(m, tc_pack16(o, sc, pk));
         if (i == nmine - 1) {
 #pragma unroll
           for (int r = 0; r < 4; ++r) pkl[r] = pk[r];
@@ -390,48 +410,51 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
         ptx::tc_fence_after();
       }
       TNB_TRACE(tw, step, 8);
-      {
-        const float *x = row_exchange(m);
-        m = fmaxf(fmaxf(x[0], x[kTcRows]), fmaxf(x[2 * kTcRows], x[3 * kTcRows]));
-      }
+      if (dst == a_row) operand_free();
       TNB_TRACE(tw, step, 9);
-      const bool nz = m > 0.f;
-      const int e = nz ? (int)((__float_as_uint(m) >> 23) & 0xffu) - 126 : 0;
-      if (dst) {
 #pragma unroll
-        for (int i = 0; i < SLOTS; ++i) {
-          if (i >= nmine) continue;
-          const int j = 4 * i + grp;
-          if (i == nmine - 1) {
-            tc_rescale(pkl, nz ? ex[i] - e : 0);
-            store_pk(j, pkl, dst);
-          } else {
-            uint4 pk[4];
-            ptx::tmem_ld16u(trow + gcol[j], *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
-            ptx::tmem_ld_wait();
-            tc_rescale(pk, nz ? ex[i] - e : 0);
-            store_pk(j, pk, dst);
-          }
+      for (int i = 0; i < SLOTS; ++i) {
+        if (i >= nmine) continue;
+        const int j = 4 * i + grp;
+        if (!dst) continue;
+        if (i == nmine - 1) {
+          store_pk(j, pkl, dst);
+        } else {
+          uint4 pk[4];
+          ptx::tmem_ld16u(trow + gcol[j], *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
+          ptx::tmem_ld_wait();
+          store_pk(j, pk, dst);
         }
       }
-      *nonzero = nz;
-      return e;
+      return m;
     };
+    float m_op = 16384.f;  // max-abs of the current operand row (operand units); the boundary vector is e0 * 2^14
     // One chain step.  mode 0: forward (records delta)   mode 1: adjoint (records wq/qmax).
     // `hexp` is the forward exponent sum (mode 0) or the running exponent h of the adjoint (mode 1); lead thread only.
-    // next_op: 1 = the normalised row becomes the next operand, 2 = the boundary vector e0 does (the row only goes to
-    // its image).  irow: image row of the output bond in the HBM stash (or null).
-    auto chain_step = [&](int site, int kw, const float(&ph)[D], int mode, int &hexp, int next_op, uint8_t *irow) {
+    // next_op: 1 = the scaled row becomes the next operand (the image writer stashes it), 2 = the boundary vector e0
+    // does and the row only goes to its image row `irow`, written here.
+    auto chain_step = [&](int site, int slab, int dir, const float(&ph)[D], int mode, int &hexp, int next_op, uint8_t *irow) {
       const int dsite = (mode == 1 && valid && lead) ? M.exps[(size_t)site * M.B + b] : 0;
-      bool nz;
-      const int e = gather_pack(ph, next_op == 2 ? irow : a_row, &nz);
+      const int kw = A.kW[slab];
+      int e;
+      const float sc = bound_scale(m_op * A.colsum[dir * nslab + slab], &e);
+      const bool nz = sc != 0.f;
+      float m = gather_pack(ph, sc, next_op == 2 ? irow : a_row);
       TNB_TRACE(tw, step, 10);
-      if (next_op == 2) write_e0(a_row, true);
+      if (next_op == 2) {
+        operand_free();
+        write_e0(a_row, true);
+      }
       TNB_TRACE(tw, step, 11);
       publish();
       TNB_TRACE(tw, step, 12);
-      // off the critical path (the next step's MMAs are running): the stash copy and the per-sample bookkeeping
-      if (next_op != 2) stash_row(irow);
+      // off the critical path (the next step's MMAs are running): row maximum of the new operand, bookkeeping
+      if (next_op == 2) {
+        m_op = 16384.f;
+      } else {
+        const float *x = row_exchange(m);
+        m_op = fmaxf(fmaxf(x[0], x[kTcRows]), fmaxf(x[2 * kTcRows], x[3 * kTcRows]));
+      }
       if (lead) {
         const int dtrue = nz ? e - kTcKA - kw : 0;  // exponent in units of the true recurrence
         if (mode == 0) {
@@ -464,13 +487,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
         const int site = L - 1 - i;
         float ph[D];
         embed_site_d<D>(M.emb, valid ? M.x[bs * L + site] : 0.5f, ph);
-        chain_step(site, A.kW[mps_slab(M, site)], ph, 0, esumR, i == nR - 1 ? 2 : 1, img_row(A.fimg, site));
+        chain_step(site, mps_slab(M, site), 1, ph, 0, esumR, i == nR - 1 ? 2 : 1, img_row(A.fimg, site));
       }
       for (int i = 0; i < nL; ++i) {
         const int site = i;
         float ph[D];
         embed_site_d<D>(M.emb, valid ? M.x[bs * L + site] : 0.5f, ph);
-        chain_step(site, A.kW[mps_slab(M, site)], ph, 0, esumL, 1, img_row(A.fimg, site + 1));
+        chain_step(site, mps_slab(M, site), 0, ph, 0, esumL, 1, nullptr);
       }
       // ---------------- class site + head ----------------
       float phc[D];
@@ -566,8 +589,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
         for (int k = 0; k < C; ++k) M.dy[(size_t)b * C + k] = dy[k];
         if (qm != INT_MIN) atomicMax(A.qmaxc, qm);
       }
-      const uint8_t *vrow = img_row(A.fimg, half == 0 ? c + 1 : c);  // normalised row * 2^14
+      const uint8_t *vrow = img_row(A.fimg, half == 0 ? c + 1 : c);  // forward environment row (operand units)
       const float dsc = valid ? ldexpf(1.f, -ed) : 0.f;              // |dy_k * dsc| < 1
+      // bound of the accumulated seed: sum_k |dy_k dsc| * max|row| * colsum(slab c+k)
+      float mrow = 0.f;
+      if (vrow) {
+#pragma unroll
+        for (int i = 0; i < SLOTS; ++i) {
+          if (i >= nmine) continue;
+          float w[16];
+          load_img16(vrow, 4 * i + grp, w);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) mrow = fmaxf(mrow, fabsf(w[q]));
+        }
+      }
+      {
+        const float *x = row_exchange(mrow);
+        mrow = fmaxf(fmaxf(x[0], x[kTcRows]), fmaxf(x[2 * kTcRows], x[3 * kTcRows]));
+      }
+      float bnd = 0.f;
+      for (int k = 0; k < C; ++k) bnd += fabsf(dy[k] * dsc) * A.colsum[(half == 0 ? nslab : 0) + c + k];
+      bnd *= mrow * 1.001f;
       write_operand_from_image(vrow, dy[0] * dsc);
       publish();
       int h = 0;
@@ -576,25 +618,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
         if (k < C - 1) {
           ptx::mbar_wait(&acc_full[NH - 1], step & 1);  // MMAs of step k have finished reading the operand
           ptx::tc_fence_after();
+          operand_free();
           write_operand_from_image(vrow, dy[k + 1] * dsc);
           publish();
           ++step;
         } else {
-          // all C slabs accumulated: normalise -> seed G[c] / G[c+1] (operand of the first chain step, and its image)
-          bool nz;
-          const int e = gather_pack(phc, a_row, &nz);
-          h = (nz ? e - kTcKA - A.kW[c] : 0) + ed;  // G = normalised row * 2^h (the operand carried dy * 2^-ed)
+          // all C slabs accumulated: scale -> seed G[c] / G[c+1] (operand of the first chain step; the writer stashes it)
+          int e;
+          const float sc = bound_scale(bnd, &e);
+          const float m = gather_pack(phc, sc, a_row);
+          h = (sc != 0.f ? e - kTcKA - A.kW[c] : 0) + ed;  // G = row * 2^h (the operand carried dy * 2^-ed)
           publish();
-          stash_row(img_row(A.gimg, half == 0 ? c : c + 1));
+          const float *x = row_exchange(m);
+          m_op = fmaxf(fmaxf(x[0], x[kTcRows]), fmaxf(x[2 * kTcRows], x[3 * kTcRows]));
           ++step;
         }
       }
       for (int i = 0; i < nchain; ++i) {
         const int site = half == 0 ? c - 1 - i : c + 1 + i;
-        const int bond_out = half == 0 ? site : site + 1;
         float ph[D];
         embed_site_d<D>(M.emb, valid ? M.x[bs * L + site] : 0.5f, ph);
-        chain_step(site, A.kW[mps_slab(M, site)], ph, 1, h, 1, img_row(A.gimg, bond_out));
+        chain_step(site, mps_slab(M, site), half == 0 ? 1 : 0, ph, 1, h, 1, nullptr);
       }
       // boundary site weights
       if (lead) {
