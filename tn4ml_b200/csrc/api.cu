@@ -237,7 +237,7 @@ static void fill_tc_args(const MpsPlan &P, void *ws, const MpsArgs<float> &M, Tc
   T.img_t = (const uint8_t *)(w + P.off_img_t);
   T.kW = (const int *)(w + P.off_kW);
   T.colsum = (const float *)(w + P.off_cs);
-  { const char *e = getenv("TNB_TC_PACE_NS"); T.pace_ns = e ? atoi(e) : P.tc_N / 5; }
+  { const char *e = getenv("TNB_TC_PACE_NS"); T.pace_ns = e ? atoi(e) : P.tc_N * 2 / 5; }
   T.wq = (float *)(w + P.off_wq);
   T.qmax = (int *)(w + P.off_qmax);
   T.wqc = (float *)(w + P.off_wqc);

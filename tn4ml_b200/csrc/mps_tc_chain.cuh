@@ -65,7 +65,7 @@ __device__ long long g_tc_trace[64 * 32];
 #endif
 
 // acc columns -> o[j] = sum_s ph[s] * acc[col + s*cstride + j], j < 16   (one 16-column group).
-// The s = 0 slice is loaded straight into o (registers are the scarce resource here: 64 outputs per thread stay live).
+// The s = 0 slice is loaded straight into o (registers are the scarce resource in the chain kernel).
 template <int D>
 __device__ __forceinline__ void tc_combine16(uint32_t col, uint32_t cstride, const float (&ph)[D], float (&o)[16]) {
   ptx::tmem_ld16(col, o);
@@ -89,18 +89,54 @@ __device__ __forceinline__ void tc_combine16(uint32_t col, uint32_t cstride, con
   }
 }
 
-// 16 fp32 values * sc -> fp16 hi/lo octets.  pk[2*o + plane]: octet o (values 8o..8o+7), plane 0 = hi, 1 = lo.
-// Returns the max-abs of the scaled values.
-__device__ __forceinline__ float tc_pack16(const float (&v)[16], float sc, uint4 (&pk)[4]) {
-  float w[16];
-  float m = 0.f;
+// Same contraction on packed fp32 pairs (phs = phi already multiplied by the step's power-of-two scale), followed by
+// the fp16 hi/lo split.  pk[2*o + plane]: octet o (values 8o..8o+7), plane 0 = hi, 1 = lo.  Returns the max-abs of
+// the 16 scaled values.
+template <int D>
+__device__ __forceinline__ float tc_combine_pack16(uint32_t col, uint32_t cstride, const float (&phs)[D], uint4 (&pk)[4]) {
+  float t0[16];
+  uint64_t w[8];
+  ptx::tmem_ld16(col, t0);
+  if constexpr (D == 1) {
+    ptx::tmem_ld_wait();
+    const uint64_t p0 = ptx::f2_pack(phs[0], phs[0]);
 #pragma unroll
-  for (int q = 0; q < 16; ++q) {
-    w[q] = v[q] * sc;
-    m = fmaxf(m, fabsf(w[q]));
+    for (int j = 0; j < 8; ++j) w[j] = ptx::f2_mul(p0, ptx::f2_pack(t0[2 * j], t0[2 * j + 1]));
+  } else {
+    float t1[16];
+    ptx::tmem_ld16(col + cstride, t1);
+    ptx::tmem_ld_wait();
+    const uint64_t p0 = ptx::f2_pack(phs[0], phs[0]), p1 = ptx::f2_pack(phs[1], phs[1]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      w[j] = ptx::f2_fma(p1, ptx::f2_pack(t1[2 * j], t1[2 * j + 1]), ptx::f2_mul(p0, ptx::f2_pack(t0[2 * j], t0[2 * j + 1])));
+#pragma unroll
+    for (int s = 2; s < D; ++s) {
+      ptx::tmem_ld16(col + (uint32_t)s * cstride, t1);
+      ptx::tmem_ld_wait();
+      const uint64_t ps = ptx::f2_pack(phs[s], phs[s]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = ptx::f2_fma(ps, ptx::f2_pack(t1[2 * j], t1[2 * j + 1]), w[j]);
+    }
   }
-  split8(w, pk[0], pk[1]);
-  split8(w + 8, pk[2], pk[3]);
+  float m = 0.f;
+  __half2 hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float a, b;
+    ptx::f2_unpack(w[j], a, b);
+    m = fmaxf(m, fmaxf(fabsf(a), fabsf(b)));
+    hi[j] = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(hi[j]);
+    float la, lb;
+    ptx::f2_unpack(ptx::f2_sub(w[j], ptx::f2_pack(hf.x, hf.y)), la, lb);
+    lo[j] = __floats2half2_rn(la, lb);
+  }
+  auto u = [](__half2 h) { return *reinterpret_cast<uint32_t *>(&h); };
+  pk[0] = make_uint4(u(hi[0]), u(hi[1]), u(hi[2]), u(hi[3]));
+  pk[1] = make_uint4(u(lo[0]), u(lo[1]), u(lo[2]), u(lo[3]));
+  pk[2] = make_uint4(u(hi[4]), u(hi[5]), u(hi[6]), u(hi[7]));
+  pk[3] = make_uint4(u(lo[4]), u(lo[5]), u(lo[6]), u(lo[7]));
   return m;
 }
 
@@ -375,13 +411,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       *e_out = ok ? ef - 126 : 0;
       return ok ? __uint_as_float((uint32_t)(127 + 126 + kTcKA - ef) << 23) : 0.f;
     };
-    // Wait for the column chunks holding my groups, contract them with phi, scale by sc and split to fp16 hi/lo
-    // (parked in TMEM, except my last group); then write the row to `dst` (operand row in smem or image row in HBM).
-    // Returns the max-abs of my part of the scaled row.
+    // Wait for the column chunks holding my groups, contract them with phi * sc and split to fp16 hi/lo (my last
+    // group stays in registers, earlier ones are parked in TMEM); then write the row to `dst` (operand row in smem,
+    // image row in HBM, or null).  Returns the max-abs of my part of the scaled row.
     auto gather_pack = [&](const float(&ph)[D], float sc, uint8_t *dst) -> float {
+      float phs[D];
+#pragma unroll
+      for (int s = 0; s < D; ++s) phs[s] = ph[s] * sc;
       float m = 0.f;
       int hprev = -1;
-      uint4 pkl[4];
+      uint4 pka[4];  // my last group
 #pragma unroll
       for (int i = 0; i < SLOTS; ++i) {
         if (i >= nmine) continue;
@@ -393,37 +432,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
           hprev = h;
           TNB_TRACE(tw, step, h);
         }
-        float o[16];
-        tc_combine16<D>(trow + gcol[j], (uint32_t)chi_h, ph, o);
         uint4 pk[4];
-        m = fmaxf(m, tc_pack16(o, sc, pk));
+        m = fmaxf(m, tc_combine_pack16<D>(trow + gcol[j], (uint32_t)chi_h, phs, pk));
         if (i == nmine - 1) {
 #pragma unroll
-          for (int r = 0; r < 4; ++r) pkl[r] = pk[r];
+          for (int r = 0; r < 4; ++r) pka[r] = pk[r];
         } else {
-          ptx::tmem_st16(trow + gcol[j], *reinterpret_cast<const uint32_t(*)[16]>(&pk[0]));
+          ptx::tmem_st16(trow + gcol[j], pk);
         }
       }
-      ptx::tmem_st_wait();
+      if (SLOTS > 1) ptx::tmem_st_wait();
       if (hprev != NH - 1) {  // every thread has seen the whole step complete before it publishes
         ptx::mbar_wait(&acc_full[NH - 1], step & 1);
         ptx::tc_fence_after();
       }
       TNB_TRACE(tw, step, 8);
+      if (!dst) return m;
       if (dst == a_row) operand_free();
       TNB_TRACE(tw, step, 9);
+      if (nmine >= 1) store_pk(4 * (nmine - 1) + grp, pka, dst);
 #pragma unroll
-      for (int i = 0; i < SLOTS; ++i) {
-        if (i >= nmine) continue;
-        const int j = 4 * i + grp;
-        if (!dst) continue;
-        if (i == nmine - 1) {
-          store_pk(j, pkl, dst);
-        } else {
-          uint4 pk[4];
-          ptx::tmem_ld16u(trow + gcol[j], *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
+      for (int i = 0; i + 1 < SLOTS; ++i) {
+        if (i + 1 < nmine) {
+          uint4 pkr[4];
+          ptx::tmem_ld16u(trow + gcol[4 * i + grp], pkr);
           ptx::tmem_ld_wait();
-          store_pk(j, pk, dst);
+          store_pk(4 * i + grp, pkr, dst);
         }
       }
       return m;

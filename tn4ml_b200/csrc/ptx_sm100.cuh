@@ -121,23 +121,48 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-// 16 registers per thread -> 32 lanes x 16 consecutive 32-bit columns (thread = TMEM lane)
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+// 16 registers per thread (four uint4) <-> 32 lanes x 16 consecutive 32-bit columns (thread = TMEM lane)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint4 (&p)[4]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      "r"(p[0].x), "r"(p[0].y), "r"(p[0].z), "r"(p[0].w), "r"(p[1].x), "r"(p[1].y), "r"(p[1].z), "r"(p[1].w), "r"(p[2].x),
+      "r"(p[2].y), "r"(p[2].z), "r"(p[2].w), "r"(p[3].x), "r"(p[3].y), "r"(p[3].z), "r"(p[3].w)
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld16u(uint32_t taddr, uint32_t (&r)[16]) {
+__device__ __forceinline__ void tmem_ld16u(uint32_t taddr, uint4 (&p)[4]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "=r"(p[0].x), "=r"(p[0].y), "=r"(p[0].z), "=r"(p[0].w), "=r"(p[1].x), "=r"(p[1].y), "=r"(p[1].z), "=r"(p[1].w),
+        "=r"(p[2].x), "=r"(p[2].y), "=r"(p[2].z), "=r"(p[2].w), "=r"(p[3].x), "=r"(p[3].y), "=r"(p[3].z), "=r"(p[3].w)
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
+// ---- packed fp32 pairs (sm_100: FMUL2 / FFMA2 / FADD2 issue one instruction for two floats) -------------------
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 
 // Shared-memory matrix descriptor, K-major, no swizzle ("interleave"):
 //   element (row, k) of a 16-bit operand lives at  start + (row/8)*SBO + (k/8)*LBO + (row%8)*16 + (k%8)*2
