@@ -204,8 +204,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
   uint32_t *gchunk = gcol + 16;                                                       // [16] group -> column chunk
   uint64_t *bars = reinterpret_cast<uint64_t *>(gchunk + 16);
   uint64_t *full = bars, *empty = bars + A.nstage, *acc_full = bars + 2 * A.nstage, *a_ready = acc_full + kTcMaxNH;
-  uint64_t *img_done = a_ready + 1;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(img_done + 1);
+  uint64_t *img_done = a_ready + 1, *img_half = a_ready + 2, *a_rel = a_ready + 3;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_rel + 1);
 
   if (tid == 0) {
     for (int i = 0; i < A.nstage; ++i) {
@@ -215,6 +215,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
     for (int h = 0; h < NH; ++h) ptx::mbar_init(&acc_full[h], 1);
     ptx::mbar_init(a_ready, kTcEpiWarps);
     ptx::mbar_init(img_done, 1);
+    ptx::mbar_init(img_half, 1);
+    ptx::mbar_init(a_rel, 1);
     ptx::fence_mbar_init();
   }
   if (tid < 16) {
@@ -232,26 +234,48 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int KS = chi / 16;
+  // Early release: once the last column chunk's MMAs have consumed the K-slabs [0, krel), the operand columns
+  // n < 16*krel (= the outputs of all earlier chunks) may be overwritten with the next operand.
+  const int krel = (NH - 1) * (KS / NH);
 
   if (warp == kTcMmaWarp + 2) {
     // ===== image writer: operand generation g (published as phase g of a_ready) -> HBM stash, in paced pieces =====
+    // Columns n < 16*krel first (they are overwritten early, see krel), then the rest.
     if (lane == 0) {
       uint8_t *base = adjoint ? A.gimg : A.fimg;
       const size_t tile_off = (size_t)(b0 >> 3) * chi * 32;
-      constexpr uint32_t kPiece = 4096;
+      const uint32_t lo_bytes = (uint32_t)krel * 256, hi_bytes = (uint32_t)(KS - krel) * 256;  // per (row block, plane)
+      const unsigned pace = (unsigned)(A.pace_ns > 0 ? (krel > 0 ? A.pace_ns / 2 : A.pace_ns) : 0);
       for (int g = 0; g <= total; ++g) {
         ptx::mbar_wait(a_ready, g & 1);
         const int bond = g > 0 ? step_out_bond(g - 1) : -1;
-        if (bond >= 0 && base) {
-          uint8_t *dst = base + (size_t)bond * A.img_bond_bytes + tile_off;
-          for (uint32_t off = 0; off < a_bytes; off += kPiece) {
-            ptx::bulk_s2g(dst + off, a_op + off, kPiece);
+        const bool on = bond >= 0 && base;
+        uint8_t *dst = on ? base + (size_t)bond * A.img_bond_bytes + tile_off : nullptr;
+        if (on && krel > 0) {
+          for (uint32_t blk = 0; blk < 2 * kTcRows / 8; ++blk) {
+            ptx::bulk_s2g(dst + (size_t)blk * chi * 16, a_op + (size_t)blk * chi * 16, lo_bytes);
             ptx::bulk_commit();
-            if (A.pace_ns > 0) __nanosleep((unsigned)A.pace_ns);
+            if (pace) __nanosleep(pace);
           }
           ptx::bulk_wait_read0();
         }
-        ptx::mbar_arrive(img_done);  // the operand may be overwritten
+        ptx::mbar_arrive(img_half);  // columns n < 16*krel may be overwritten
+        if (on && krel > 0) {
+          for (uint32_t blk = 0; blk < 2 * kTcRows / 8; ++blk) {
+            ptx::bulk_s2g(dst + (size_t)blk * chi * 16 + lo_bytes, a_op + (size_t)blk * chi * 16 + lo_bytes, hi_bytes);
+            ptx::bulk_commit();
+            if (pace) __nanosleep(pace);
+          }
+          ptx::bulk_wait_read0();
+        } else if (on) {  // one column chunk: the tile is one contiguous run
+          for (uint32_t off = 0; off < a_bytes; off += 4096) {
+            ptx::bulk_s2g(dst + off, a_op + off, 4096);
+            ptx::bulk_commit();
+            if (pace) __nanosleep(pace);
+          }
+          ptx::bulk_wait_read0();
+        }
+        ptx::mbar_arrive(img_done);  // the whole operand may be overwritten
       }
       ptx::bulk_wait0();
     }
@@ -300,6 +324,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
             ptx::mma_f16(d, da_lo, db_hi, idesc, 1u);
             ptx::mma_f16(d, da_hi, db_lo, idesc, 1u);
             ptx::mma_commit(&empty[stage]);
+            if (h == NH - 1 && ks == krel - 1) ptx::mma_commit(a_rel);
             if (++stage == A.nstage) { stage = 0; phase ^= 1; }
           }
           ptx::mma_commit(&acc_full[h]);
@@ -388,7 +413,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
         store_pk(j, pk, a_row);
       }
     };
-    auto publish = [&]() {  // operand (and TMEM reads) done -> the MMA warp may start the next step
+    // the image writer has finished reading the operand of this step (it may be overwritten)
+    auto operand_free = [&]() { ptx::mbar_wait(img_done, step & 1); };
+    // operand (and TMEM reads) done -> the MMA warp may start the next step.  Every warp first makes sure the image
+    // writer has passed this step, so that no barrier phase can run more than one step ahead of a waiter.
+    auto publish = [&](bool first = false) {
+      if (!first) operand_free();
       ptx::tc_fence_before();
       ptx::fence_proxy_async();
       __syncwarp();
@@ -401,8 +431,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       ptx::named_bar_sync(1 + lq, 4 * 32);
       return x + row;
     };
-    // the image writer has finished reading the operand of this step (it may be overwritten)
-    auto operand_free = [&]() { ptx::mbar_wait(img_done, step & 1); };
     const int nslab = L - 1 + C;
     // Scale of a step whose outputs are bounded by `bnd`: 2^(14 - e), bnd = f * 2^e, f in [0.5, 1).  *e_out = e.
     auto bound_scale = [&](float bnd, int *e_out) -> float {
@@ -411,55 +439,67 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       *e_out = ok ? ef - 126 : 0;
       return ok ? __uint_as_float((uint32_t)(127 + 126 + kTcKA - ef) << 23) : 0.f;
     };
-    // Wait for the column chunks holding my groups, contract them with phi * sc and split to fp16 hi/lo (my last
-    // group stays in registers, earlier ones are parked in TMEM); then write the row to `dst` (operand row in smem,
-    // image row in HBM, or null).  Returns the max-abs of my part of the scaled row.
+    // Wait for the column chunks holding my groups, contract them with phi * sc, split to fp16 hi/lo and write the row
+    // to `dst`: an image row in HBM (every group at once), or the next operand row in smem.  There a group of the last
+    // chunk is stored at once (all MMAs of the step are done), an earlier group is parked in the TMEM columns it came from
+    // and moved to smem as soon as the last chunk's MMAs have released those operand columns (a_rel) -- long before the
+    // last chunk itself is complete.  Returns the max-abs of my part of the scaled row.
     auto gather_pack = [&](const float(&ph)[D], float sc, uint8_t *dst) -> float {
       float phs[D];
 #pragma unroll
       for (int s = 0; s < D; ++s) phs[s] = ph[s] * sc;
+      const bool to_op = dst == a_row;
+      auto move_parked = [&]() {
+        ptx::tmem_st_wait();
+        ptx::mbar_wait(a_rel, step & 1);
+        ptx::mbar_wait(img_half, step & 1);
+#pragma unroll
+        for (int i = 0; i < SLOTS; ++i) {
+          if (i >= nmine) continue;
+          const int j = 4 * i + grp;
+          if ((int)gchunk[j] == NH - 1) continue;
+          uint4 pk[4];
+          ptx::tmem_ld16u(trow + gcol[j], pk);
+          ptx::tmem_ld_wait();
+          store_pk(j, pk, a_row);
+        }
+        TNB_TRACE(tw, step, 7);
+      };
       float m = 0.f;
       int hprev = -1;
-      uint4 pka[4];  // my last group
+      bool moved = !to_op || NH == 1;
 #pragma unroll
       for (int i = 0; i < SLOTS; ++i) {
         if (i >= nmine) continue;
         const int j = 4 * i + grp;
         const int h = (int)gchunk[j];
         if (h != hprev) {
+          if (h == NH - 1 && !moved) {
+            move_parked();
+            moved = true;
+          }
           ptx::mbar_wait(&acc_full[h], step & 1);
           ptx::tc_fence_after();
+          if (h == NH - 1 && to_op) operand_free();
           hprev = h;
           TNB_TRACE(tw, step, h);
         }
         uint4 pk[4];
         m = fmaxf(m, tc_combine_pack16<D>(trow + gcol[j], (uint32_t)chi_h, phs, pk));
-        if (i == nmine - 1) {
-#pragma unroll
-          for (int r = 0; r < 4; ++r) pka[r] = pk[r];
+        if (!to_op) {
+          if (dst) store_pk(j, pk, dst);
+        } else if (h == NH - 1) {
+          store_pk(j, pk, a_row);
         } else {
           ptx::tmem_st16(trow + gcol[j], pk);
         }
       }
-      if (SLOTS > 1) ptx::tmem_st_wait();
+      if (!moved) move_parked();
       if (hprev != NH - 1) {  // every thread has seen the whole step complete before it publishes
         ptx::mbar_wait(&acc_full[NH - 1], step & 1);
         ptx::tc_fence_after();
       }
       TNB_TRACE(tw, step, 8);
-      if (!dst) return m;
-      if (dst == a_row) operand_free();
-      TNB_TRACE(tw, step, 9);
-      if (nmine >= 1) store_pk(4 * (nmine - 1) + grp, pka, dst);
-#pragma unroll
-      for (int i = 0; i + 1 < SLOTS; ++i) {
-        if (i + 1 < nmine) {
-          uint4 pkr[4];
-          ptx::tmem_ld16u(trow + gcol[4 * i + grp], pkr);
-          ptx::tmem_ld_wait();
-          store_pk(4 * i + grp, pkr, dst);
-        }
-      }
       return m;
     };
     float m_op = 16384.f;  // max-abs of the current operand row (operand units); the boundary vector is e0 * 2^14
@@ -516,7 +556,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       write_e0(a_row, true);
       write_e0(img_row(A.fimg, L), valid);
       write_e0(img_row(A.fimg, 0), valid);
-      publish();
+      publish(true);
       for (int i = 0; i < nR; ++i) {
         const int site = L - 1 - i;
         float ph[D];
@@ -645,7 +685,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       for (int k = 0; k < C; ++k) bnd += fabsf(dy[k] * dsc) * A.colsum[(half == 0 ? nslab : 0) + c + k];
       bnd *= mrow * 1.001f;
       write_operand_from_image(vrow, dy[0] * dsc);
-      publish();
+      publish(true);
       int h = 0;
       const int jb = half == 0 ? 0 : L - 1;  // the boundary site: no chain step, but it has a gradient
       for (int k = 0; k < C; ++k) {

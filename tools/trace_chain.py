@@ -3,8 +3,8 @@
 
 Builds a second copy of the library with -DTNB_TC_TRACE (tools/libtn4ml_b200_trace.so), runs one forward+backward of
 cfg 5 at a small batch and prints, for CTA (0,0) of the LAST chain launch (the adjoint), clock64() deltas per step:
-    mma: a_ready seen -> chunk commits issued;  epilogue warps 0 / 15 / 6: chunk h seen, gather done, exchange done,
-    bookkeeping done, stores done, published.
+    mma: a_ready seen -> chunk commits issued;  epilogue warps 0 / 15 / 6: chunk h seen, parked groups moved to the
+    operand, gather done, published.
 """
 import ctypes as C
 import os
@@ -52,7 +52,7 @@ if __name__ == "__main__":
         for w, name in ((0, "w0"), (1, "w15"), (2, "w6")):
             e = row[w * 16:(w + 1) * 16]
             line += f" | {name}: seen=" + ",".join(rel(v) for v in e[0:4]) + \
-                    f" gath={rel(e[8])} exch={rel(e[9])} book={rel(e[10])} store={rel(e[11])} pub={rel(e[12])}"
+                    f" moved={rel(e[7])} gath={rel(e[8])} pub={rel(e[12])}"
         if prev_pub:
             line += f" | step_len={t0 - prev_pub}"
         prev_pub = t0
