@@ -386,19 +386,26 @@ static int mps_backward_t(const tnb_problem *p, const MpsPlan &P, long long B, c
       Da.tmem_cols = 32;
       while (Da.tmem_cols < 2 * p->chi) Da.tmem_cols <<= 1;
       const long long maxsp = (B + 2047) / 2048;
+      Da.cpg = 256 / p->chi < 1 ? 1 : 256 / p->chi;
       for (int pass = 0; pass < 2; ++pass) {
-        // pass 0: every chain site (rows (s, a));  pass 1: the class site (rows ((s, k), a))
+        // pass 0: every chain site (copies sigma = s);  pass 1: the class site (copies sigma = (s, k))
         Da.Dv = pass == 0 ? p->d : p->d * p->n_out;
         Da.only_site = pass == 0 ? -1 : p->out_site;
         Da.wq = pass == 0 ? Tc.wq : Tc.wqc;
         Da.qmax = pass == 0 ? Tc.qmax : Tc.qmaxc;
-        Da.mgroups = (Da.Dv * p->chi + 255) / 256;
-        long long ctas = (long long)(pass == 0 ? p->L : 1) * Da.mgroups;
-        long long nsp = (148LL * 4 + ctas - 1) / ctas;
-        if (nsp > maxsp) nsp = maxsp;
-        if (nsp < 1) nsp = 1;
-        Da.nsplit = (int)nsp;
-        Da.bchunk = ((B + nsp - 1) / nsp + kDaKC - 1) / kDaKC * kDaKC;
+        Da.mgroups = (Da.Dv + Da.cpg - 1) / Da.cpg;
+        // split K (the batch) so that the grid fills the 148 SMs about four times over with little wave quantisation
+        const long long ctas = (long long)(pass == 0 ? p->L - 1 : 1) * Da.mgroups;
+        long long best = 1;
+        double best_eff = 0.0;
+        for (long long nsp = 1; nsp <= maxsp && nsp <= 64; ++nsp) {
+          const long long n = ctas * nsp;
+          const double eff = (double)n / (double)((n + 147) / 148 * 148);
+          const double score = eff - (n < 148 * 3 ? 1.0 : 0.0) - 0.002 * (double)nsp;  // prefer >= 3 waves, fewer splits
+          if (nsp == 1 || score > best_eff) { best = nsp; best_eff = score; }
+        }
+        Da.nsplit = (int)best;
+        Da.bchunk = ((B + Da.nsplit - 1) / Da.nsplit + kDaKC - 1) / kDaKC * kDaKC;
         dim3 gda((unsigned)(Da.mgroups * Da.nsplit), (unsigned)(pass == 0 ? p->L : 1));
         prof_begin(st);
         tc_da_kernel<<<gda, kDaThreads, (size_t)Da.nstage * kDaStage + 1024, st>>>(Da);

@@ -192,12 +192,14 @@ namespace tnb {
 
 // ---------------------------------------------------------------------------------------
 // K4 (tensor-core family): weight gradients as a batch-reduction GEMM on tcgen05.
-//   dA_site[a, r, s] = 2^qmax * sum_b (U[b,a] * wq[site][s][b] * 2^-qmax) * V[b,r]
-//   rows m = s*chi + a (M tiles of 128, two per CTA), columns r (N = chi), K = samples.
-// Both operands come from the fp16 hi/lo bond images the chain kernels write, which already are
-// the MN-major shared-memory tile layout.  V needs no per-sample weight: one bulk async copy per
-// stage brings it in.  U carries the per-sample weight: 16 producer warps (lane == sample) read
-// hi/lo units, rebuild fp32, apply the weight, re-split and write the operand tiles.  One warp issues the MMAs; warps 0-3 drain TMEM once at the end and reduce into the
+//   dA_site[a, r, sigma] = 2^qmax * sum_b (U[b,a] * wq[site][sigma][b] * 2^-qmax) * V[b,r]
+//   rows m = sigma*chi + a, columns r (N = chi), K = samples.
+// Both operands are the fp16 hi/lo bond images the chain kernels write; a run of 32 samples of an image is an
+// MN-major operand tile as it stands, so both arrive by bulk async copies (deep prefetch, no load latency in any warp).
+// V is used as it is.  U carries the per-sample weight: one CTA owns `cpg` weighted copies sigma of the chi rows
+// (cpg*chi <= 256 rows, two M tiles); the raw chunk lands in the rows of the CTA's first copy, and 16 producer warps
+// (lane == sample, warp == row octet) rebuild fp32 from hi/lo, apply each copy's weight, re-split and write the copies
+// (the first one in place).  One warp issues the MMAs; warps 0-3 drain TMEM once at the end and reduce into the
 // packed gradient with fp32 atomics (split-K across CTAs).
 // ---------------------------------------------------------------------------------------
 struct TcDaArgs {
@@ -209,49 +211,56 @@ struct TcDaArgs {
   long long bchunk;  // samples per split (multiple of 32)
   const uint8_t *fimg, *gimg;
   size_t img_bond_bytes;
-  int Dv;            // rows m = sigma*chi + a with sigma < Dv: D for chain sites, D*C for the class site
+  int Dv;            // weighted copies sigma < Dv: D for chain sites, D*C for the class site
+  int cpg;           // copies per CTA: max(1, 256 / chi)
   int only_site;     // >= 0: this site only (the class site; wq/qmax point at its own tables)
 };
 
 constexpr int kDaKC = 32;                         // samples per pipeline stage
 constexpr int kDaProducers = 512;                 // threads (16 warps)
-constexpr int kDaThreads = kDaProducers + 64;      // + MMA warp + bulk-copy warp
-constexpr uint32_t kDaSBO = 512u;                 // row-octet stride: 4 sample blocks x 128 B
-constexpr uint32_t kDaPlane = 32u * kDaSBO;       // one operand plane: 32 row octets x 32 samples fp16
-constexpr uint32_t kDaBMax = 256u * 128u;         // B region: chi * 128 B (hi plane then lo plane, SBO 512)
-constexpr uint32_t kDaStage = 2u * kDaPlane + kDaBMax;  // A_hi, A_lo (transformed in-kernel), B (bulk-copied image)
+constexpr int kDaThreads = kDaProducers + 64;     // + MMA warp + bulk-copy warp
+constexpr int kDaMaxCpg = 8;                      // chi >= 32
+// U operand of a stage: a "virtual bond image" of 256 rows, [4 sample blocks][plane hi|lo][32 row octets][8 samples][16 B]
+constexpr uint32_t kDaUPlane = 32u * 128u;        // 4 KB
+constexpr uint32_t kDaUBlock = 2u * kDaUPlane;    // 8 KB: K-block (8 samples) stride
+constexpr uint32_t kDaU = 4u * kDaUBlock;         // 32 KB
+constexpr uint32_t kDaBMax = 256u * 128u;         // V region: chi * 128 B (a raw image chunk)
+constexpr uint32_t kDaStage = kDaU + kDaBMax;
 
 __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const MpsArgs<float> &M = A.M;
-  const int chi = M.chip, D = A.Dv, c = M.c;
+  const int chi = M.chip, Dv = A.Dv, c = M.c;
   const int site = A.only_site >= 0 ? A.only_site : (int)blockIdx.y;
   if (A.only_site < 0 && site == c) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int group = blockIdx.x % A.mgroups, split = blockIdx.x / A.mgroups;
-  const int Mtot = D * chi;
-  const int m0 = group * 256;
-  const int ntile = min(2, (Mtot - m0 + 127) / 128);  // the last tile may be partial: rows >= Mtot stay zero
+  const int sig0 = group * A.cpg;                       // first copy of this CTA
+  const int ncopy = min(A.cpg, Dv - sig0);              // copies of this CTA
+  const int nrows = ncopy * chi;                        // operand rows in use (<= 256)
+  const int ntile = (nrows + 127) / 128;
+  const int noct = chi / 8;                             // row octets of one copy
   const long long kbeg = (long long)split * A.bchunk;
   const long long kend = min(M.B, kbeg + A.bchunk);
   if (kbeg >= kend) return;
   const int nchunks = (int)((kend - kbeg + kDaKC - 1) / kDaKC);
   // both operands come from the bond images written by the chain kernels:
   //   U = F[site] (left half, class site) or G[site] (right half): re-weighted per sample in-kernel
-  //   V = G[site+1] (left half) or F[site+1] (right half, class site): bulk-copied as is
+  //   V = G[site+1] (left half) or F[site+1] (right half, class site): used as it is
   const size_t chunk0 = (size_t)(kbeg / kDaKC) * chi * 128;
   const uint8_t *Uimg = (site <= c ? A.fimg : A.gimg) + (size_t)site * A.img_bond_bytes + chunk0;
   const uint8_t *Vimg = (site < c ? A.gimg : A.fimg) + (size_t)(site + 1) * A.img_bond_bytes + chunk0;
-  const uint32_t b_bytes = (uint32_t)chi * 128;
+  const uint32_t b_bytes = (uint32_t)chi * 128;  // one chunk (32 samples) of an image
 
   constexpr int kMmaWarp = kDaProducers / 32, kCopyWarp = kMmaWarp + 1;
   uint8_t *stages = smem;
   uint64_t *bars = reinterpret_cast<uint64_t *>(stages + (size_t)A.nstage * kDaStage);
-  uint64_t *full = bars, *empty = bars + A.nstage, *done = bars + 2 * A.nstage;
+  uint64_t *loaded = bars, *ready = bars + A.nstage, *empty = bars + 2 * A.nstage, *done = bars + 3 * A.nstage;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done + 1);
   if (tid == 0) {
     for (int i = 0; i < A.nstage; ++i) {
-      ptx::mbar_init(&full[i], kDaProducers + 1);  // 512 transform arrivals + the bulk copy's expect_tx arrival
+      ptx::mbar_init(&loaded[i], 1);             // the bulk copies' expect_tx arrival
+      ptx::mbar_init(&ready[i], kDaProducers / 32);  // one arrival per producer warp
       ptx::mbar_init(&empty[i], 1);
     }
     ptx::mbar_init(done, 1);
@@ -261,12 +270,11 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
     ptx::tmem_alloc(tmem_slot, (uint32_t)A.tmem_cols);
     ptx::tmem_relinquish();
   }
-  if (m0 + ntile * 128 > Mtot) {  // partial tile: its unused operand rows must read as zero
-    for (int st = 0; st < A.nstage; ++st)
-      for (uint32_t i = tid * 16u; i < 2u * kDaPlane; i += kDaThreads * 16u)
-        *reinterpret_cast<uint4 *>(stages + (size_t)st * kDaStage + i) = make_uint4(0, 0, 0, 0);
-    ptx::fence_proxy_async();
-  }
+  // operand rows that no copy fills (partial last tile) must read as zero
+  for (int st = 0; st < A.nstage; ++st)
+    for (uint32_t i = tid * 16u; i < kDaU; i += kDaThreads * 16u)
+      *reinterpret_cast<uint4 *>(stages + (size_t)st * kDaStage + i) = make_uint4(0, 0, 0, 0);
+  ptx::fence_proxy_async();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -281,16 +289,16 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
       int stage = 0;
       uint32_t phase = 0;
       for (int ch = 0; ch < nchunks; ++ch) {
-        ptx::mbar_wait(&full[stage], phase);
+        ptx::mbar_wait(&ready[stage], phase);
         ptx::tc_fence_after();
         const uint32_t st = ptx::smem_u32(stages + (size_t)stage * kDaStage);
         for (int t = 0; t < ntile; ++t) {
 #pragma unroll
           for (int ks = 0; ks < kDaKC / 16; ++ks) {
-            const uint64_t da_hi = ptx::smem_desc_kmajor(st + t * 16 * kDaSBO + ks * 256, 128, kDaSBO);
-            const uint64_t da_lo = ptx::smem_desc_kmajor(st + kDaPlane + t * 16 * kDaSBO + ks * 256, 128, kDaSBO);
-            const uint64_t db_hi = ptx::smem_desc_kmajor(st + 2 * kDaPlane + ks * vks, vlbo, 128);
-            const uint64_t db_lo = ptx::smem_desc_kmajor(st + 2 * kDaPlane + vlo + ks * vks, vlbo, 128);
+            const uint64_t da_hi = ptx::smem_desc_kmajor(st + t * 16 * 128 + ks * 2 * kDaUBlock, kDaUBlock, 128);
+            const uint64_t da_lo = ptx::smem_desc_kmajor(st + kDaUPlane + t * 16 * 128 + ks * 2 * kDaUBlock, kDaUBlock, 128);
+            const uint64_t db_hi = ptx::smem_desc_kmajor(st + kDaU + ks * vks, vlbo, 128);
+            const uint64_t db_lo = ptx::smem_desc_kmajor(st + kDaU + vlo + ks * vks, vlbo, 128);
             const uint32_t d = tmem_base + (uint32_t)t * chi;
             ptx::mma_f16(d, da_hi, db_hi, idesc, (ch > 0 || ks > 0) ? 1u : 0u);
             ptx::mma_f16(d, da_lo, db_hi, idesc, 1u);
@@ -303,101 +311,77 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
       ptx::mma_commit(done);
     }
   } else if (warp == kCopyWarp) {
-    // ===== V operand: one bulk async copy of the pre-split image per stage =====
+    // ===== both operands: bulk async copies of one image chunk per stage (U: per sample block and plane, into the
+    //       rows of the CTA's first copy; V: the whole chunk) =====
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int ch = 0; ch < nchunks; ++ch) {
         ptx::mbar_wait(&empty[stage], phase ^ 1);
-        ptx::mbar_expect_tx(&full[stage], b_bytes);
-        ptx::bulk_g2s(stages + (size_t)stage * kDaStage + 2 * kDaPlane, Vimg + (size_t)ch * b_bytes, b_bytes, &full[stage]);
+        uint8_t *st = stages + (size_t)stage * kDaStage;
+        ptx::mbar_expect_tx(&loaded[stage], 2 * b_bytes);
+        const uint8_t *usrc = Uimg + (size_t)ch * b_bytes;
+#pragma unroll
+        for (int bp = 0; bp < 8; ++bp)  // (sample block, plane)
+          ptx::bulk_g2s(st + (uint32_t)bp * kDaUPlane, usrc + (size_t)bp * chi * 16, (uint32_t)chi * 16, &loaded[stage]);
+        ptx::bulk_g2s(st + kDaU, Vimg + (size_t)ch * b_bytes, b_bytes, &loaded[stage]);
         if (++stage == A.nstage) { stage = 0; phase ^= 1; }
       }
     }
   } else {
-    // ===== U operand producers: lane == sample, warp == row octet =====
-    // The unit of a bond image is 8 rows of one sample (16 bytes); the 8 samples of a block are consecutive
-    // units, so a warp reads 4 x 128 contiguous bytes per plane and writes 512 contiguous bytes per plane:
-    // hi + lo -> fp32 -> * per-sample weight -> hi/lo.
+    // ===== U operand producers: lane == sample, warp == row octet of a copy =====
+    // unit (sample block lane/8, plane, octet o, sample lane%8) of the raw chunk sits in the first copy's rows
     constexpr int kWarps = kDaProducers / 32;
-    constexpr int kItems = 2;  // row octets per warp and stage: 2 tiles * 16 octets / 16 warps
-    const uint32_t lane_off = (uint32_t)(lane >> 3) * 128 + (uint32_t)(lane & 7) * 16;            // operand tile
-    const uint32_t lane_src = (uint32_t)(lane >> 3) * (uint32_t)chi * 32 + (uint32_t)(lane & 7) * 16;  // bond image
-    uint32_t src_off[kItems], dst_off[kItems];
-    const float *wq_row[kItems];
-    bool on[kItems];
-#pragma unroll
-    for (int i = 0; i < kItems; ++i) {
-      const int ro = warp + i * kWarps;
-      const int m = m0 + ro * 8;
-      on[i] = ro < ntile * 16 && m < Mtot;
-      const int sidx = on[i] ? m / chi : 0;
-      const int a0 = on[i] ? m - sidx * chi : 0;
-      src_off[i] = (uint32_t)(a0 >> 3) * 128 + lane_src;
-      dst_off[i] = (uint32_t)ro * kDaSBO + lane_off;
-      wq_row[i] = A.wq + ((size_t)(A.only_site >= 0 ? 0 : site) * D + sidx) * M.B;
-    }
+    const uint32_t lane_off = (uint32_t)(lane >> 3) * kDaUBlock + (uint32_t)(lane & 7) * 16;
     const float qs = ldexpf(1.f, -qmax);  // (the image already carries the 2^14 operand scale)
-    const uint32_t lo_off = (uint32_t)chi * 16;
-
-    // Issue phase: loads only (no instruction may consume a loaded value here, or the in-order warp
-    // would stall on the first one and serialise the rest).
-#define TNB_DA_ISSUE(CH, RH, RL, SC)                                                                  \
-  {                                                                                                   \
-    const uint8_t *cb_ = Uimg + (size_t)(CH)*chi * 128;                                               \
-    const long long b_ = min(kbeg + (long long)(CH)*kDaKC + lane, kend - 1);                          \
-    _Pragma("unroll") for (int i = 0; i < kItems; ++i) {                                              \
-      if (on[i]) {                                                                                    \
-        RH[i] = __ldg(reinterpret_cast<const uint4 *>(cb_ + src_off[i]));                             \
-        RL[i] = __ldg(reinterpret_cast<const uint4 *>(cb_ + lo_off + src_off[i]));                    \
-        SC[i] = __ldg(wq_row[i] + b_);                                                                \
-      }                                                                                               \
-    }                                                                                                 \
-  }
-#define TNB_DA_CONVERT(CH, ST, RH, RL, SC)                                                            \
-  {                                                                                                   \
-    const bool ok_ = kbeg + (long long)(CH)*kDaKC + lane < kend;                                      \
-    _Pragma("unroll") for (int i = 0; i < kItems; ++i) {                                              \
-      if (on[i]) {                                                                                    \
-        const float f_ = ok_ ? SC[i] * qs : 0.f;                                                      \
-        const __half2 *h_ = reinterpret_cast<const __half2 *>(&RH[i]);                                \
-        const __half2 *l_ = reinterpret_cast<const __half2 *>(&RL[i]);                                \
-        float w_[8];                                                                                  \
-        _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                               \
-          const float2 fh = __half22float2(h_[j]), fl = __half22float2(l_[j]);                        \
-          w_[2 * j] = (fh.x + fl.x) * f_;                                                             \
-          w_[2 * j + 1] = (fh.y + fl.y) * f_;                                                         \
-        }                                                                                             \
-        uint4 hv, lv;                                                                                 \
-        split8(w_, hv, lv);                                                                           \
-        *reinterpret_cast<uint4 *>((ST) + dst_off[i]) = hv;                                           \
-        *reinterpret_cast<uint4 *>((ST) + kDaPlane + dst_off[i]) = lv;                                \
-      }                                                                                               \
-    }                                                                                                 \
-  }
-    uint4 rah[kItems], ral[kItems], rbh[kItems], rbl[kItems];
-    float sa[kItems], sb[kItems];
+    const float *wq0 = A.wq + ((size_t)(A.only_site >= 0 ? 0 : site) * Dv + sig0) * M.B;
+    float wn[kDaMaxCpg];  // weights of the next chunk, one per copy
+    auto load_w = [&](int ch) {
+      const long long b_ = kbeg + (long long)ch * kDaKC + lane;
+#pragma unroll
+      for (int s = 0; s < kDaMaxCpg; ++s)
+        wn[s] = (s < ncopy && b_ < kend) ? __ldg(wq0 + (size_t)s * M.B + b_) * qs : 0.f;
+    };
     int stage = 0;
     uint32_t phase = 0;
-    TNB_DA_ISSUE(0, rah, ral, sa)
-    for (int ch = 0; ch < nchunks; ch += 2) {
-      if (ch + 1 < nchunks) TNB_DA_ISSUE(ch + 1, rbh, rbl, sb)
-      ptx::mbar_wait(&empty[stage], phase ^ 1);
-      TNB_DA_CONVERT(ch, stages + (size_t)stage * kDaStage, rah, ral, sa)
-      ptx::fence_proxy_async();
-      ptx::mbar_arrive(&full[stage]);
-      if (++stage == A.nstage) { stage = 0; phase ^= 1; }
-      if (ch + 1 < nchunks) {
-        if (ch + 2 < nchunks) TNB_DA_ISSUE(ch + 2, rah, ral, sa)
-        ptx::mbar_wait(&empty[stage], phase ^ 1);
-        TNB_DA_CONVERT(ch + 1, stages + (size_t)stage * kDaStage, rbh, rbl, sb)
-        ptx::fence_proxy_async();
-        ptx::mbar_arrive(&full[stage]);
-        if (++stage == A.nstage) { stage = 0; phase ^= 1; }
+    load_w(0);
+    for (int ch = 0; ch < nchunks; ++ch) {
+      float wc[kDaMaxCpg];
+#pragma unroll
+      for (int s = 0; s < kDaMaxCpg; ++s) wc[s] = wn[s];
+      if (ch + 1 < nchunks) load_w(ch + 1);
+      ptx::mbar_wait(&loaded[stage], phase);
+      uint8_t *st = stages + (size_t)stage * kDaStage + lane_off;
+      for (int o = warp; o < noct; o += kWarps) {
+        const uint4 hv = *reinterpret_cast<const uint4 *>(st + o * 128);
+        const uint4 lv = *reinterpret_cast<const uint4 *>(st + kDaUPlane + o * 128);
+        const __half2 *h_ = reinterpret_cast<const __half2 *>(&hv);
+        const __half2 *l_ = reinterpret_cast<const __half2 *>(&lv);
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 fh = __half22float2(h_[j]), fl = __half22float2(l_[j]);
+          v[2 * j] = fh.x + fl.x;
+          v[2 * j + 1] = fh.y + fl.y;
+        }
+#pragma unroll
+        for (int s = 0; s < kDaMaxCpg; ++s) {
+          if (s < ncopy) {
+            float w_[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w_[j] = v[j] * wc[s];
+            uint4 ho, lo;
+            split8(w_, ho, lo);
+            *reinterpret_cast<uint4 *>(st + (s * noct + o) * 128) = ho;
+            *reinterpret_cast<uint4 *>(st + kDaUPlane + (s * noct + o) * 128) = lo;
+          }
+        }
       }
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&ready[stage]);
+      if (++stage == A.nstage) { stage = 0; phase ^= 1; }
     }
-#undef TNB_DA_ISSUE
-#undef TNB_DA_CONVERT
     // ===== epilogue (warps 0-3): TMEM -> packed gradient =====
     if (warp < 4) {
       ptx::mbar_wait(done, 0);
@@ -406,15 +390,19 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
       const size_t site_off = (size_t)site * chi * chi * M.D + (site > c ? (size_t)chi * chi * M.D * (M.C - 1) : 0);
       float *g = A.grads + site_off;
       for (int t = 0; t < ntile; ++t) {
-        const int mm = m0 + t * 128 + tid, s = mm / chi, a = mm - s * chi;
-        if (mm >= Mtot) continue;
+        if (t * 128 + warp * 32 >= nrows) continue;  // warp-uniform: tcgen05.ld is a warp-collective instruction
+        const int mm = t * 128 + tid;
+        const bool on = mm < nrows;
+        const int sl = on ? mm / chi : 0, a = on ? mm - sl * chi : 0, sg = sig0 + sl;
         const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)t * chi;
         for (int n0 = 0; n0 < chi; n0 += 16) {
           float v[16];
           ptx::tmem_ld16(trow + n0, v);
           ptx::tmem_ld_wait();
+          if (on) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(&g[((size_t)a * chi + n0 + j) * D + s], v[j] * sc);
+            for (int j = 0; j < 16; ++j) atomicAdd(&g[((size_t)a * chi + n0 + j) * Dv + sg], v[j] * sc);
+          }
         }
       }
     }
