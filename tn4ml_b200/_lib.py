@@ -37,7 +37,8 @@ class TnbProblem(C.Structure):
     ]
 
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtn4ml_b200.so")
+# TNB_LIB points at another build of the same library (measurement builds under tools/); default: the in-tree build
+LIB_PATH = os.environ.get("TNB_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtn4ml_b200.so")
 
 # every symbol include/tn4ml_b200.h declares: name -> (restype, argtypes)
 _P = C.POINTER

@@ -373,7 +373,11 @@ static int mps_backward_t(const tnb_problem *p, const MpsPlan &P, long long B, c
       static std::once_flag once;
       static cudaError_t aerr = cudaSuccess;
       std::call_once(once, [] {
-        aerr = cudaFuncSetAttribute(tc_da_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 2048);
+        aerr = cudaFuncSetAttribute(tc_da_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 2048);
+        if (aerr == cudaSuccess)
+          aerr = cudaFuncSetAttribute(tc_da_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 2048);
+        if (aerr == cudaSuccess)
+          aerr = cudaFuncSetAttribute(tc_da_kernel<kDaMaxCpg>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 2048);
       });
       if (aerr != cudaSuccess) return fail("cudaFuncSetAttribute(tc_da): %s", cudaGetErrorString(aerr));
       TcDaArgs Da;
@@ -382,7 +386,7 @@ static int mps_backward_t(const tnb_problem *p, const MpsPlan &P, long long B, c
       Da.fimg = Tc.fimg;
       Da.gimg = Tc.gimg;
       Da.img_bond_bytes = Tc.img_bond_bytes;
-      Da.nstage = 3;
+      Da.nstage = (int)((232448 - 2048 - 1024) / kDaStage);
       Da.tmem_cols = 32;
       while (Da.tmem_cols < 2 * p->chi) Da.tmem_cols <<= 1;
       const long long maxsp = (B + 2047) / 2048;
@@ -408,7 +412,10 @@ static int mps_backward_t(const tnb_problem *p, const MpsPlan &P, long long B, c
         Da.bchunk = ((B + Da.nsplit - 1) / Da.nsplit + kDaKC - 1) / kDaKC * kDaKC;
         dim3 gda((unsigned)(Da.mgroups * Da.nsplit), (unsigned)(pass == 0 ? p->L : 1));
         prof_begin(st);
-        tc_da_kernel<<<gda, kDaThreads, (size_t)Da.nstage * kDaStage + 1024, st>>>(Da);
+        const size_t da_smem = (size_t)Da.nstage * kDaStage + 1024;
+        if (Da.cpg == 1) tc_da_kernel<1><<<gda, kDaThreads, da_smem, st>>>(Da);
+        else if (Da.cpg == 2) tc_da_kernel<2><<<gda, kDaThreads, da_smem, st>>>(Da);
+        else tc_da_kernel<kDaMaxCpg><<<gda, kDaThreads, da_smem, st>>>(Da);
         TNB_LAUNCH_CHECK(pass == 0 ? "tc_da_kernel" : "tc_da_kernel(class)");
       }
       return 0;

@@ -216,17 +216,22 @@ struct TcDaArgs {
   int only_site;     // >= 0: this site only (the class site; wq/qmax point at its own tables)
 };
 
-constexpr int kDaKC = 32;                         // samples per pipeline stage
+#ifndef TNB_DA_KC
+#define TNB_DA_KC 32
+#endif
+constexpr int kDaKC = TNB_DA_KC;                  // samples per pipeline stage (a multiple of the MMA's K = 16)
 constexpr int kDaProducers = 512;                 // threads (16 warps)
 constexpr int kDaThreads = kDaProducers + 64;     // + MMA warp + bulk-copy warp
 constexpr int kDaMaxCpg = 8;                      // chi >= 32
-// U operand of a stage: a "virtual bond image" of 256 rows, [4 sample blocks][plane hi|lo][32 row octets][8 samples][16 B]
+// U operand of a stage: a "virtual bond image" of 256 rows, [kDaKC/8 sample blocks][plane hi|lo][32 row octets][8 samples][16 B]
 constexpr uint32_t kDaUPlane = 32u * 128u;        // 4 KB
 constexpr uint32_t kDaUBlock = 2u * kDaUPlane;    // 8 KB: K-block (8 samples) stride
-constexpr uint32_t kDaU = 4u * kDaUBlock;         // 32 KB
-constexpr uint32_t kDaBMax = 256u * 128u;         // V region: chi * 128 B (a raw image chunk)
-constexpr uint32_t kDaStage = kDaU + kDaBMax;
+constexpr uint32_t kDaU = (kDaKC / 8) * kDaUBlock;  // 16 KB
+constexpr uint32_t kDaBMax = 256u * 4u * kDaKC;   // V region: a raw image chunk of kDaKC samples
+constexpr uint32_t kDaStage = kDaU + kDaBMax;     // 64 KB (32 samples): 3 stages
 
+// CPG: upper bound of the copies per CTA (compile time, so that the producer loop is straight-line code)
+template <int CPG>
 __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const MpsArgs<float> &M = A.M;
@@ -236,7 +241,7 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int group = blockIdx.x % A.mgroups, split = blockIdx.x / A.mgroups;
   const int sig0 = group * A.cpg;                       // first copy of this CTA
-  const int ncopy = min(A.cpg, Dv - sig0);              // copies of this CTA
+  const int ncopy = min(A.cpg, Dv - sig0);              // copies of this CTA (<= CPG)
   const int nrows = ncopy * chi;                        // operand rows in use (<= 256)
   const int ntile = (nrows + 127) / 128;
   const int noct = chi / 8;                             // row octets of one copy
@@ -247,10 +252,10 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
   // both operands come from the bond images written by the chain kernels:
   //   U = F[site] (left half, class site) or G[site] (right half): re-weighted per sample in-kernel
   //   V = G[site+1] (left half) or F[site+1] (right half, class site): used as it is
-  const size_t chunk0 = (size_t)(kbeg / kDaKC) * chi * 128;
+  const size_t chunk0 = (size_t)(kbeg / 8) * chi * 32;
   const uint8_t *Uimg = (site <= c ? A.fimg : A.gimg) + (size_t)site * A.img_bond_bytes + chunk0;
   const uint8_t *Vimg = (site < c ? A.gimg : A.fimg) + (size_t)(site + 1) * A.img_bond_bytes + chunk0;
-  const uint32_t b_bytes = (uint32_t)chi * 128;  // one chunk (32 samples) of an image
+  const uint32_t b_bytes = (uint32_t)chi * 4 * kDaKC;  // one chunk (16 samples) of an image
 
   constexpr int kMmaWarp = kDaProducers / 32, kCopyWarp = kMmaWarp + 1;
   uint8_t *stages = smem;
@@ -259,7 +264,7 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done + 1);
   if (tid == 0) {
     for (int i = 0; i < A.nstage; ++i) {
-      ptx::mbar_init(&loaded[i], 1);             // the bulk copies' expect_tx arrival
+      ptx::mbar_init(&loaded[i], 1);                 // the bulk copies' expect_tx arrival
       ptx::mbar_init(&ready[i], kDaProducers / 32);  // one arrival per producer warp
       ptx::mbar_init(&empty[i], 1);
     }
@@ -284,8 +289,8 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
   if (warp == kMmaWarp) {
     if (lane == 0) {
       const uint32_t idesc = ptx::idesc_f16_f32(128, chi) | (1u << 15) | (1u << 16);  // A and B MN-major
-      // V tile = 32 samples of a bond image: sample-block (K) stride chi*32, lo plane at chi*16, 16 samples = 2 blocks
-      const uint32_t vlbo = (uint32_t)chi * 32, vlo = (uint32_t)chi * 16, vks = (uint32_t)chi * 64;
+      // V tile = kDaKC samples of a bond image: sample-block (K) stride chi*32, lo plane at chi*16
+      const uint32_t vlbo = (uint32_t)chi * 32, vlo = (uint32_t)chi * 16;
       int stage = 0;
       uint32_t phase = 0;
       for (int ch = 0; ch < nchunks; ++ch) {
@@ -297,8 +302,8 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
           for (int ks = 0; ks < kDaKC / 16; ++ks) {
             const uint64_t da_hi = ptx::smem_desc_kmajor(st + t * 16 * 128 + ks * 2 * kDaUBlock, kDaUBlock, 128);
             const uint64_t da_lo = ptx::smem_desc_kmajor(st + kDaUPlane + t * 16 * 128 + ks * 2 * kDaUBlock, kDaUBlock, 128);
-            const uint64_t db_hi = ptx::smem_desc_kmajor(st + kDaU + ks * vks, vlbo, 128);
-            const uint64_t db_lo = ptx::smem_desc_kmajor(st + kDaU + vlo + ks * vks, vlbo, 128);
+            const uint64_t db_hi = ptx::smem_desc_kmajor(st + kDaU + ks * 2 * vlbo, vlbo, 128);
+            const uint64_t db_lo = ptx::smem_desc_kmajor(st + kDaU + vlo + ks * 2 * vlbo, vlbo, 128);
             const uint32_t d = tmem_base + (uint32_t)t * chi;
             ptx::mma_f16(d, da_hi, db_hi, idesc, (ch > 0 || ks > 0) ? 1u : 0u);
             ptx::mma_f16(d, da_lo, db_hi, idesc, 1u);
@@ -322,58 +327,72 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
         ptx::mbar_expect_tx(&loaded[stage], 2 * b_bytes);
         const uint8_t *usrc = Uimg + (size_t)ch * b_bytes;
 #pragma unroll
-        for (int bp = 0; bp < 8; ++bp)  // (sample block, plane)
+        for (int bp = 0; bp < 2 * (kDaKC / 8); ++bp)  // (sample block, plane)
           ptx::bulk_g2s(st + (uint32_t)bp * kDaUPlane, usrc + (size_t)bp * chi * 16, (uint32_t)chi * 16, &loaded[stage]);
         ptx::bulk_g2s(st + kDaU, Vimg + (size_t)ch * b_bytes, b_bytes, &loaded[stage]);
         if (++stage == A.nstage) { stage = 0; phase ^= 1; }
       }
     }
   } else {
-    // ===== U operand producers: lane == sample, warp == row octet of a copy =====
-    // unit (sample block lane/8, plane, octet o, sample lane%8) of the raw chunk sits in the first copy's rows
-    constexpr int kWarps = kDaProducers / 32;
-    const uint32_t lane_off = (uint32_t)(lane >> 3) * kDaUBlock + (uint32_t)(lane & 7) * 16;
-    const float qs = ldexpf(1.f, -qmax);  // (the image already carries the 2^14 operand scale)
+    // ===== U operand producers: kDaKC lanes == the samples of the chunk, (warp, lane / kDaKC) == row octet of a copy =====
+    // unit (sample block, plane, octet o, sample % 8) of the raw chunk sits in the first copy's rows
+    constexpr int kOctPerWarp = 32 / kDaKC;
+    const int smp = lane & (kDaKC - 1);
+    const uint32_t lane_off = (uint32_t)(smp >> 3) * kDaUBlock + (uint32_t)(smp & 7) * 16;
+    const int o0 = kOctPerWarp * warp + lane / kDaKC;  // my octets: o0, o0 + 16 * kOctPerWarp, ...
+    const float qs = ldexpf(1.f, -qmax);          // (the image already carries the 2^14 operand scale)
     const float *wq0 = A.wq + ((size_t)(A.only_site >= 0 ? 0 : site) * Dv + sig0) * M.B;
-    float wn[kDaMaxCpg];  // weights of the next chunk, one per copy
+    // weights of the next chunk, one per copy: loaded one chunk ahead and not touched until then (an instruction
+    // that consumes a loaded value would stall this in-order warp for the whole memory latency)
+    float wn[CPG];
     auto load_w = [&](int ch) {
-      const long long b_ = kbeg + (long long)ch * kDaKC + lane;
+      const long long b_ = kbeg + (long long)ch * kDaKC + smp;
 #pragma unroll
-      for (int s = 0; s < kDaMaxCpg; ++s)
-        wn[s] = (s < ncopy && b_ < kend) ? __ldg(wq0 + (size_t)s * M.B + b_) * qs : 0.f;
+      for (int s = 0; s < CPG; ++s) {
+        wn[s] = 0.f;
+        if (s < ncopy && b_ < kend) wn[s] = __ldg(wq0 + (size_t)s * M.B + b_);
+      }
     };
     int stage = 0;
     uint32_t phase = 0;
     load_w(0);
     for (int ch = 0; ch < nchunks; ++ch) {
-      float wc[kDaMaxCpg];
+      uint64_t wc[CPG];
 #pragma unroll
-      for (int s = 0; s < kDaMaxCpg; ++s) wc[s] = wn[s];
+      for (int s = 0; s < CPG; ++s) wc[s] = ptx::f2_pack(wn[s] * qs, wn[s] * qs);
       if (ch + 1 < nchunks) load_w(ch + 1);
       ptx::mbar_wait(&loaded[stage], phase);
       uint8_t *st = stages + (size_t)stage * kDaStage + lane_off;
-      for (int o = warp; o < noct; o += kWarps) {
+      for (int o = o0; o < noct; o += kOctPerWarp * (kDaProducers / 32)) {
         const uint4 hv = *reinterpret_cast<const uint4 *>(st + o * 128);
         const uint4 lv = *reinterpret_cast<const uint4 *>(st + kDaUPlane + o * 128);
         const __half2 *h_ = reinterpret_cast<const __half2 *>(&hv);
         const __half2 *l_ = reinterpret_cast<const __half2 *>(&lv);
-        float v[8];
+        uint64_t v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 fh = __half22float2(h_[j]), fl = __half22float2(l_[j]);
-          v[2 * j] = fh.x + fl.x;
-          v[2 * j + 1] = fh.y + fl.y;
+          v[j] = ptx::f2_add(ptx::f2_pack(fh.x, fh.y), ptx::f2_pack(fl.x, fl.y));
         }
 #pragma unroll
-        for (int s = 0; s < kDaMaxCpg; ++s) {
+        for (int s = 0; s < CPG; ++s) {
           if (s < ncopy) {
-            float w_[8];
+            uint32_t ho[4], lo[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) w_[j] = v[j] * wc[s];
-            uint4 ho, lo;
-            split8(w_, ho, lo);
-            *reinterpret_cast<uint4 *>(st + (s * noct + o) * 128) = ho;
-            *reinterpret_cast<uint4 *>(st + kDaUPlane + (s * noct + o) * 128) = lo;
+            for (int j = 0; j < 4; ++j) {
+              const uint64_t w2 = ptx::f2_mul(v[j], wc[s]);
+              float wa, wb;
+              ptx::f2_unpack(w2, wa, wb);
+              const __half2 hh = __floats2half2_rn(wa, wb);
+              const float2 hf = __half22float2(hh);
+              float la, lb;
+              ptx::f2_unpack(ptx::f2_sub(w2, ptx::f2_pack(hf.x, hf.y)), la, lb);
+              const __half2 ll = __floats2half2_rn(la, lb);
+              ho[j] = *reinterpret_cast<const uint32_t *>(&hh);
+              lo[j] = *reinterpret_cast<const uint32_t *>(&ll);
+            }
+            *reinterpret_cast<uint4 *>(st + (s * noct + o) * 128) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
+            *reinterpret_cast<uint4 *>(st + kDaUPlane + (s * noct + o) * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
         }
       }
