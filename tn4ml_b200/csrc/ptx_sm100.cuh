@@ -34,21 +34,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// Blocking wait on a phase parity.  The suspend-time hint lets the hardware park the thread until the barrier flips
-// (or the hint expires) instead of spinning on try_wait: dozens of waiting warps per CTA otherwise burn issue slots
-// and power that the tensor pipe needs under the board's power cap.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   uint32_t addr = smem_u32(bar);
   asm volatile(
       "{\n\t"
       ".reg .pred P1;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
       "@P1 bra WAIT_DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t"
       "}\n" ::"r"(addr),
-      "r"(parity), "r"(0x989680u)
+      "r"(parity)
       : "memory");
 }
 
