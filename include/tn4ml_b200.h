@@ -122,6 +122,13 @@ int tnb_backward(const tnb_problem *prob, int64_t batch, const void *x, const vo
                  const void *params, double loss_scale, void *grads, int32_t accumulate,
                  void *workspace, int64_t workspace_bytes, void *stream);
 
+/* One optax.adam step on the packed buffers (the update side of train_step, tn4ml/models/model.py:591-614, where the
+ * reference runs eager optax over an L-leaf pytree):  mu, nu updated in place, params += -lr * mu_hat / (sqrt(nu_hat +
+ * eps_root) + eps) with the bias corrections of step `count` (1-based).  grad_scale multiplies the gradient first
+ * (global-norm clipping, util.py:131-155, passes its factor here; 1.0 otherwise).  All buffers: n elements of dtype. */
+int tnb_adam_update(int32_t dtype, int64_t n, void *params, const void *grads, void *mu, void *nu, double lr,
+                    double b1, double b2, double eps, double eps_root, int64_t count, double grad_scale, void *stream);
+
 /* Embedding.__call__ for n scalars: phi [n, d] (dtype), before embed()'s normaliser. */
 int tnb_embed(const tnb_embedding *emb, int32_t dtype, int64_t n, const void *x, void *phi,
               void *stream);

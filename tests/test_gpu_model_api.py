@@ -101,3 +101,23 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libtn4ml_b200.so")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         _lib.lib()
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+def test_fused_adam_matches_the_optax_rule(dtype):
+    """tnb_adam_update (one kernel on the packed buffer) against the same rule written with tensor ops."""
+    import tn4ml_b200 as T
+    g = torch.Generator(device="cpu").manual_seed(0)
+    p0 = torch.randn(10007, generator=g, dtype=dtype).cuda()
+    opt = T.optim.adam(T.optim.exponential_decay(3e-3, 2, 0.9), b1=0.8, b2=0.95, eps=1e-7, eps_root=1e-12)
+    pa, pb = p0.clone(), p0.clone()
+    sa, sb = opt.init(pa), opt.init(pb)
+    for step in range(5):
+        grad = torch.randn(10007, generator=g, dtype=dtype).cuda()
+        scale = 0.5 if step == 3 else 1.0
+        sa = opt.fused_step(pa, grad, sa, grad_scale=scale)
+        upd, sb = opt.update(grad * scale, sb, pb)
+        T.optim.apply_updates(pb, upd)
+    tol = 1e-12 if dtype == torch.float64 else 2e-6
+    assert torch.allclose(pa, pb, rtol=tol, atol=tol)
+    assert torch.allclose(sa["mu"], sb["mu"], rtol=tol, atol=tol) and torch.allclose(sa["nu"], sb["nu"], rtol=tol, atol=tol)

@@ -1,4 +1,5 @@
 // C-ABI of the tn4ml hot path (see include/tn4ml_b200.h for the contract).
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -473,6 +474,21 @@ static int mps_backward_t(const tnb_problem *p, const MpsPlan &P, long long B, c
 
 }  // namespace tnb
 
+namespace tnb {
+template <typename T>
+__global__ void adam_kernel(long long n, T *__restrict__ p, const T *__restrict__ g, T *__restrict__ mu, T *__restrict__ nu,
+                            T lr, T b1, T b2, T eps, T eps_root, T c1, T c2, T gs) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const T gi = g[i] * gs;
+    const T m = b1 * mu[i] + (T(1) - b1) * gi;
+    const T v = b2 * nu[i] + (T(1) - b2) * gi * gi;
+    mu[i] = m;
+    nu[i] = v;
+    p[i] -= lr * (m * c1) / (Num<T>::sqrt(v * c2 + eps_root) + eps);
+  }
+}
+}  // namespace tnb
+
 using namespace tnb;
 
 extern "C" {
@@ -594,6 +610,28 @@ int tnb_debug_trace_read(long long *host, int32_t n) {
   return cudaMemcpyFromSymbol(host, tnb::g_tc_trace, (size_t)n * sizeof(long long)) == cudaSuccess ? 0 : 1;
 }
 #endif
+
+int tnb_adam_update(int32_t dtype, int64_t n, void *params, const void *grads, void *mu, void *nu, double lr, double b1,
+                    double b2, double eps, double eps_root, int64_t count, double grad_scale, void *stream) {
+  if (!params || !grads || !mu || !nu) return fail("null device pointer");
+  if (n < 1 || count < 1) return fail("n and count must be >= 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  const double c1 = 1.0 / (1.0 - pow(b1, (double)count)), c2 = 1.0 / (1.0 - pow(b2, (double)count));
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  prof_begin(st);
+  if (dtype == TNB_F64)
+    adam_kernel<double><<<blocks, 256, 0, st>>>(n, (double *)params, (const double *)grads, (double *)mu, (double *)nu, lr,
+                                                 b1, b2, eps, eps_root, c1, c2, grad_scale);
+  else if (dtype == TNB_F32)
+    adam_kernel<float><<<blocks, 256, 0, st>>>(n, (float *)params, (const float *)grads, (float *)mu, (float *)nu,
+                                                (float)lr, (float)b1, (float)b2, (float)eps, (float)eps_root, (float)c1,
+                                                (float)c2, (float)grad_scale);
+  else
+    return fail("bad dtype");
+  TNB_LAUNCH_CHECK("adam_kernel");
+  return 0;
+}
 
 int tnb_embed(const tnb_embedding *emb, int32_t dtype, int64_t n, const void *x, void *phi, void *stream) {
   if (!emb || !x || !phi) return fail("null pointer");

@@ -307,9 +307,18 @@ class Model:
             if rv is not None:
                 loss = loss + rv
                 g = g + rg
+            fused = (isinstance(self._opt, optim._Adam) and g.is_cuda and g.dtype == self._packed.dtype
+                     and g.is_contiguous())
             if grad_clip_threshold:  # util.gradient_clip (util.py:131-155): global-norm clipping
                 gn = torch.linalg.norm(g)
-                g = g * torch.clamp(grad_clip_threshold / (gn + 1e-16), max=1.0)
+                scale = torch.clamp(grad_clip_threshold / (gn + 1e-16), max=1.0)
+                if fused:
+                    opt_state = self._opt.fused_step(self._packed, g, opt_state, grad_scale=float(scale))
+                    return self.arrays, opt_state, loss
+                g = g * scale
+            if fused:  # optimizer + update_tensors of train_step (model.py:591-614) as one kernel on the packed buffer
+                opt_state = self._opt.fused_step(self._packed, g, opt_state)
+                return self.arrays, opt_state, loss
             updates, opt_state = self._opt.update(g, opt_state, self._packed)
             optim.apply_updates(self._packed, updates.to(self._packed.dtype))
             return self.arrays, opt_state, loss

@@ -35,6 +35,20 @@ class _Adam(GradientTransformation):
         lr = self.lr(t - 1) if callable(self.lr) else self.lr
         return -lr * mu_hat / (torch.sqrt(nu_hat + self.eps_root) + self.eps), state
 
+    def fused_step(self, params, grads, state, grad_scale=1.0):
+        """update() + apply_updates() as ONE kernel over the packed CUDA buffers (tnb_adam_update)."""
+        from . import _lib
+        state["count"] += 1
+        t = state["count"]
+        lr = self.lr(t - 1) if callable(self.lr) else self.lr
+        code = _lib.F64 if params.dtype == torch.float64 else _lib.F32
+        with torch.cuda.device(params.device):
+            _lib.check(_lib.lib().tnb_adam_update(
+                code, params.numel(), params.data_ptr(), grads.data_ptr(), state["mu"].data_ptr(), state["nu"].data_ptr(),
+                float(lr), self.b1, self.b2, self.eps, self.eps_root, t, float(grad_scale),
+                torch.cuda.current_stream(params.device).cuda_stream))
+        return state
+
 
 class _Sgd(GradientTransformation):
     def __init__(self, learning_rate, momentum=None):

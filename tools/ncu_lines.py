@@ -28,13 +28,17 @@ def num(v):
         return 0
 
 
+def cell(r, i):
+    return r[i] if i < len(r) else ""
+
+
 agg = {}
 for f, r in out:
     key = (f, int(r[0]), r[1].strip()[:100])
     a = agg.setdefault(key, [0, {}])
-    a[0] += num(r[si])
+    a[0] += num(cell(r, si))
     for n in stalls:
-        v = num(r[idx[n]])
+        v = num(cell(r, idx[n]))
         if v:
             a[1][n] = a[1].get(n, 0) + v
 tot = sum(a[0] for a in agg.values())
