@@ -112,7 +112,7 @@ struct MpsPlan {
   size_t off_Wn, off_Wt, off_F, off_G, off_exps, off_esum, off_y, off_dy, total;
   size_t smem_sweep, smem_class;
   // tensor-core sweep (f32, TNB_PREC_TENSOR)
-  int tc, tc_N, tc_NH, tc_NMMA, tc_nstage, tc_cols;
+  int tc, tc_N, tc_NH, tc_NMMA, tc_nstage, tc_cols, tc_tiles;
   uint32_t tc_stage_bytes;
   size_t tc_site_img, off_img_n, off_img_t, off_kW, off_cs, off_wq, off_qmax, off_wqc, off_fimg, off_gimg, tc_smem, img_bond_bytes;
 };
@@ -182,13 +182,17 @@ static MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
     P.tc_NMMA = P.tc_N / P.tc_NH;
     P.tc_stage_bytes = 64u * P.tc_NMMA;  // one K-slab (16 rows) of one column chunk, hi and lo planes
     P.tc_site_img = (size_t)P.tc_NH * (p->chi / 16) * P.tc_stage_bytes;
-    P.tc_cols = 32;
-    while (P.tc_cols < P.tc_N) P.tc_cols <<= 1;
     const size_t a_bytes = (size_t)2 * kTcRows * p->chi * 2;
-    const size_t fixed = 4096 /* row exchange */ + 1024 /* barriers */;
-    long ns = (long)((232448 - (long)fixed - (long)a_bytes) / (long)P.tc_stage_bytes);
+    // two sample tiles per CTA when one column chunk covers the step (nothing else hides the epilogue); TNB_TC_TILES=1 forces one
+    // (pays when the step's MMA time is comparable to its exposed tail: N = 256; measured slower at N <= 128)
+    P.tc_tiles = (P.tc_NH == 1 && P.tc_N == 256) ? 2 : 1;
+    if (const char *e = getenv("TNB_TC_TILES")) { if (atoi(e) == 1) P.tc_tiles = 1; }
+    P.tc_cols = 32;
+    while (P.tc_cols < P.tc_tiles * P.tc_N) P.tc_cols <<= 1;
+    const size_t fixed = (size_t)P.tc_tiles * 4096 /* row exchange */ + 1024 /* tables, barriers */;
+    long ns = (long)((232448 - (long)fixed - (long)(P.tc_tiles * a_bytes)) / (long)P.tc_stage_bytes);
     P.tc_nstage = ns > 12 ? 12 : (int)ns;
-    P.tc_smem = a_bytes + (size_t)P.tc_nstage * P.tc_stage_bytes + fixed;
+    P.tc_smem = P.tc_tiles * a_bytes + (size_t)P.tc_nstage * P.tc_stage_bytes + fixed;
     if (P.tc_nstage < 2) P.tc = 0;
   }
   if (P.tc) {
@@ -237,6 +241,7 @@ static void fill_tc_args(const MpsPlan &P, void *ws, const MpsArgs<float> &M, Tc
   T.img_n = (const uint8_t *)(w + P.off_img_n);
   T.img_t = (const uint8_t *)(w + P.off_img_t);
   T.kW = (const int *)(w + P.off_kW);
+  T.tile0 = 0;
   T.colsum = (const float *)(w + P.off_cs);
   { const char *e = getenv("TNB_TC_PACE_NS"); T.pace_ns = e ? atoi(e) : P.tc_N * 2 / 5; }
   T.wq = (float *)(w + P.off_wq);
@@ -251,37 +256,55 @@ static void fill_tc_args(const MpsPlan &P, void *ws, const MpsArgs<float> &M, Tc
   T.stage_bytes = P.tc_stage_bytes; T.site_img_bytes = P.tc_site_img;
 }
 
-template <int D, int SLOTS> static cudaError_t tc_set_attr() {
+template <int D, int SLOTS, int TILES> static cudaError_t tc_set_attr() {
   static std::once_flag once;
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [] {
-    err = cudaFuncSetAttribute(tc_chain_kernel<D, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    err = cudaFuncSetAttribute(tc_chain_kernel<D, SLOTS, TILES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   });
   return err;
 }
 
-template <int D, int SLOTS>
-static cudaError_t tc_launch_one(dim3 grid, size_t smem, const TcArgs &T, int adjoint, cudaStream_t st) {
-  cudaError_t e = tc_set_attr<D, SLOTS>();
-  if (e == cudaSuccess) tc_chain_kernel<D, SLOTS><<<grid, kTcThreads, smem, st>>>(T, adjoint);
+template <int D, int SLOTS, int TILES>
+static cudaError_t tc_launch_one(long long ntiles, long long tile0, size_t smem, TcArgs T, int adjoint, cudaStream_t st) {
+  cudaError_t e = tc_set_attr<D, SLOTS, TILES>();
+  T.tile0 = tile0 * kTcRows;
+  dim3 grid((unsigned)(ntiles / TILES), adjoint ? 2 : 1);
+  if (e == cudaSuccess && ntiles > 0) tc_chain_kernel<D, SLOTS, TILES><<<grid, kTcThreads, smem, st>>>(T, adjoint);
   return e;
 }
 
 // launch the tcgen05 sweep (forward environments or adjoint chains)
 static int tc_launch_sweep(const tnb_problem *p, const MpsPlan &P, const TcArgs &T, long long B, int adjoint,
                            cudaStream_t st) {
-  dim3 grid((unsigned)((B + kTcRows - 1) / kTcRows), adjoint ? 2 : 1);
   cudaError_t e = cudaSuccess;
-  const bool wide = p->chi > 128;  // 16-column groups per epilogue thread: 4 (chi <= 256) or 2 (chi <= 128)
+  const bool wide = p->chi > 128;   // 16-column groups per epilogue thread: 4 (chi <= 256) or 2 (chi <= 128)
+  const long long ntiles = (B + kTcRows - 1) / kTcRows;
+  // Two-tile CTAs take whole rounds of 148 SMs (per half of the adjoint grid); the remaining tiles run as one-tile
+  // CTAs behind them, so that the last round is not half empty with double-length CTAs.
+  long long npair = 0;
+  if (P.tc_tiles == 2) {
+    const long long per_round = 2LL * 148 / (adjoint ? 2 : 1);
+    npair = ntiles / per_round * per_round;
+    if (ntiles - npair > per_round / 2) npair = ntiles / 2 * 2;  // the rest would need two more rounds anyway
+  }
+#define TNB_TC_GO(DD, SS)                                                                                     \
+  do {                                                                                                        \
+    if (npair > 0) e = tc_launch_one<DD, SS, 2>(npair, 0, P.tc_smem, T, adjoint, st);                         \
+    if (e == cudaSuccess && ntiles > npair) e = tc_launch_one<DD, SS, 1>(ntiles - npair, npair, P.tc_smem, T, adjoint, st); \
+  } while (0)
+#define TNB_TC_GO1(DD, SS) e = tc_launch_one<DD, SS, 1>(ntiles, 0, P.tc_smem, T, adjoint, st)
   prof_begin(st);
   switch (p->d) {
-    case 2: e = wide ? tc_launch_one<2, 4>(grid, P.tc_smem, T, adjoint, st) : tc_launch_one<2, 2>(grid, P.tc_smem, T, adjoint, st); break;
-    case 3: e = wide ? tc_launch_one<3, 4>(grid, P.tc_smem, T, adjoint, st) : tc_launch_one<3, 2>(grid, P.tc_smem, T, adjoint, st); break;
-    case 4: e = tc_launch_one<4, 2>(grid, P.tc_smem, T, adjoint, st); break;
-    case 6: e = tc_launch_one<6, 2>(grid, P.tc_smem, T, adjoint, st); break;
-    case 8: e = tc_launch_one<8, 2>(grid, P.tc_smem, T, adjoint, st); break;
+    case 2: if (wide) TNB_TC_GO1(2, 4); else TNB_TC_GO(2, 2); break;
+    case 3: if (wide) TNB_TC_GO1(3, 4); else TNB_TC_GO1(3, 2); break;
+    case 4: TNB_TC_GO(4, 2); break;
+    case 6: TNB_TC_GO1(6, 2); break;
+    case 8: TNB_TC_GO(8, 2); break;
     default: return fail("tensor path: unsupported physical dimension %d", p->d);
   }
+#undef TNB_TC_GO
+#undef TNB_TC_GO1
   if (e != cudaSuccess) return fail("cudaFuncSetAttribute(tc_chain): %s", cudaGetErrorString(e));
   TNB_LAUNCH_CHECK(adjoint ? "tc_chain_kernel(adj)" : "tc_chain_kernel(fwd)");
   return 0;

@@ -42,6 +42,7 @@ struct TcArgs {
   const int *kW;         // per-slab weight pre-scale exponent
   const float *colsum;   // [2 directions][slab]: max_n sum_{k,s} |W[k,s,n]| * 2^kW  (bound of one chain step, see chain kernel)
   int pace_ns;           // image writer: pause between 4 KB pieces
+  long long tile0;       // first sample of this launch (a sweep may be split into a two-tile and a one-tile launch)
   float *wq;             // adjoint: phi_s[b] * 2^q[b] per (site, s, b): per-sample weight of the dA GEMM
   int *qmax;             // adjoint: max_b q[site][b]
   // Environment stash of the tensor path: fp16 hi/lo images (value * 2^14, rows normalised), one per bond, laid out

@@ -141,14 +141,17 @@ __device__ __forceinline__ float tc_combine_pack16(uint32_t col, uint32_t cstrid
 }
 
 // SLOTS: the largest number of 16-column groups an epilogue thread owns (chi / 64).
-template <int D, int SLOTS>
+// TILES: sample tiles of 128 rows per CTA.  With one column chunk (chi <= 128) nothing hides a step's epilogue, so the
+// CTA carries two independent tiles (own operand, own TMEM columns, own barriers): the MMAs of one tile run under the
+// epilogue of the other.  At chi = 256 one tile fills TMEM and shared memory, and the column chunks do the hiding.
+template <int D, int SLOTS, int TILES>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int adjoint) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const MpsArgs<float> &M = A.M;
   const int chi = M.chip, L = M.L, c = M.c, C = M.C;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int half = blockIdx.y;
-  const long long b0 = (long long)blockIdx.x * kTcRows;
+  const long long b0 = A.tile0 + (long long)blockIdx.x * (kTcRows * TILES);
   const int nR = L - 1 - c, nL = c;
   const int NH = A.NH, chi_h = chi / NH;
 
@@ -195,28 +198,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
     return half == 0 ? c - 1 - i : c + 2 + i;
   };
 
-  // A operand, in the layout of a bond image: unit (row, octet o, plane p) at (row/8)*chi*32 + p*chi*16 + o*128 + (row%8)*16
+  // A operand of tile t, in the layout of a bond image: unit (row, octet o, plane p) at
+  // (row/8)*chi*32 + p*chi*16 + o*128 + (row%8)*16
   const uint32_t a_bytes = (uint32_t)kTcRows * chi * 4;
-  uint8_t *a_op = smem;
-  uint8_t *stages = smem + a_bytes;
-  float *xch = reinterpret_cast<float *>(stages + (size_t)A.nstage * A.stage_bytes);  // [2][4][128]
-  uint32_t *gcol = reinterpret_cast<uint32_t *>(xch + 2 * 4 * kTcRows);               // [16] group -> TMEM column
+  uint8_t *a_op = smem;  // [TILES][a_bytes]
+  uint8_t *stages = smem + (size_t)TILES * a_bytes;
+  float *xch = reinterpret_cast<float *>(stages + (size_t)A.nstage * A.stage_bytes);  // [TILES][2][4][128]
+  uint32_t *gcol = reinterpret_cast<uint32_t *>(xch + TILES * 2 * 4 * kTcRows);       // [16] group -> TMEM column
   uint32_t *gchunk = gcol + 16;                                                       // [16] group -> column chunk
   uint64_t *bars = reinterpret_cast<uint64_t *>(gchunk + 16);
-  uint64_t *full = bars, *empty = bars + A.nstage, *acc_full = bars + 2 * A.nstage, *a_ready = acc_full + kTcMaxNH;
-  uint64_t *img_done = a_ready + 1, *img_half = a_ready + 2, *a_rel = a_ready + 3;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_rel + 1);
+  uint64_t *full = bars, *empty = bars + A.nstage;
+  uint64_t *acc_full = bars + 2 * A.nstage;        // [TILES][kTcMaxNH]
+  uint64_t *a_ready = acc_full + TILES * kTcMaxNH;  // [TILES]
+  uint64_t *img_done = a_ready + TILES, *img_half = img_done + TILES, *a_rel = img_half + TILES;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_rel + TILES);
 
   if (tid == 0) {
     for (int i = 0; i < A.nstage; ++i) {
       ptx::mbar_init(&full[i], 1);
       ptx::mbar_init(&empty[i], 1);
     }
-    for (int h = 0; h < NH; ++h) ptx::mbar_init(&acc_full[h], 1);
-    ptx::mbar_init(a_ready, kTcEpiWarps);
-    ptx::mbar_init(img_done, 1);
-    ptx::mbar_init(img_half, 1);
-    ptx::mbar_init(a_rel, 1);
+    for (int t = 0; t < TILES; ++t) {
+      for (int h = 0; h < NH; ++h) ptx::mbar_init(&acc_full[t * kTcMaxNH + h], 1);
+      ptx::mbar_init(&a_ready[t], kTcEpiWarps);
+      ptx::mbar_init(&img_done[t], 1);
+      ptx::mbar_init(&img_half[t], 1);
+      ptx::mbar_init(&a_rel[t], 1);
+    }
     ptx::fence_mbar_init();
   }
   if (tid < 16) {
@@ -233,6 +241,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tile_cols = (uint32_t)A.tmem_cols / TILES;  // TMEM columns of one tile's accumulator
   const int KS = chi / 16;
   // Early release: once the last column chunk's MMAs have consumed the K-slabs [0, krel), the operand columns
   // n < 16*krel (= the outputs of all earlier chunks) may be overwritten with the next operand.
@@ -243,56 +252,62 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
     // Columns n < 16*krel first (they are overwritten early, see krel), then the rest.
     if (lane == 0) {
       uint8_t *base = adjoint ? A.gimg : A.fimg;
-      const size_t tile_off = (size_t)(b0 >> 3) * chi * 32;
       const uint32_t lo_bytes = (uint32_t)krel * 256, hi_bytes = (uint32_t)(KS - krel) * 256;  // per (row block, plane)
       const unsigned pace = (unsigned)(A.pace_ns > 0 ? (krel > 0 ? A.pace_ns / 2 : A.pace_ns) : 0);
       for (int g = 0; g <= total; ++g) {
-        ptx::mbar_wait(a_ready, g & 1);
         const int bond = g > 0 ? step_out_bond(g - 1) : -1;
         const bool on = bond >= 0 && base;
-        uint8_t *dst = on ? base + (size_t)bond * A.img_bond_bytes + tile_off : nullptr;
-        if (on && krel > 0) {
-          for (uint32_t blk = 0; blk < 2 * kTcRows / 8; ++blk) {
-            ptx::bulk_s2g(dst + (size_t)blk * chi * 16, a_op + (size_t)blk * chi * 16, lo_bytes);
-            ptx::bulk_commit();
-            if (pace) __nanosleep(pace);
+#pragma unroll
+        for (int t = 0; t < TILES; ++t) {
+          ptx::mbar_wait(&a_ready[t], g & 1);
+          const uint8_t *src = a_op + (size_t)t * a_bytes;
+          uint8_t *dst = on ? base + (size_t)bond * A.img_bond_bytes + (size_t)((b0 + t * kTcRows) >> 3) * chi * 32 : nullptr;
+          if (on && krel > 0) {
+            for (uint32_t blk = 0; blk < 2 * kTcRows / 8; ++blk) {
+              ptx::bulk_s2g(dst + (size_t)blk * chi * 16, src + (size_t)blk * chi * 16, lo_bytes);
+              ptx::bulk_commit();
+              if (pace) __nanosleep(pace);
+            }
+            ptx::bulk_wait_read0();
           }
-          ptx::bulk_wait_read0();
+          ptx::mbar_arrive(&img_half[t]);  // columns n < 16*krel may be overwritten
+          if (on && krel > 0) {
+            for (uint32_t blk = 0; blk < 2 * kTcRows / 8; ++blk) {
+              ptx::bulk_s2g(dst + (size_t)blk * chi * 16 + lo_bytes, src + (size_t)blk * chi * 16 + lo_bytes, hi_bytes);
+              ptx::bulk_commit();
+              if (pace) __nanosleep(pace);
+            }
+            ptx::bulk_wait_read0();
+          } else if (on) {  // one column chunk: the tile is one contiguous run
+            for (uint32_t off = 0; off < a_bytes; off += 4096) {
+              ptx::bulk_s2g(dst + off, src + off, 4096);
+              ptx::bulk_commit();
+              if (pace) __nanosleep(pace);
+            }
+            ptx::bulk_wait_read0();
+          }
+          ptx::mbar_arrive(&img_done[t]);  // the whole operand may be overwritten
         }
-        ptx::mbar_arrive(img_half);  // columns n < 16*krel may be overwritten
-        if (on && krel > 0) {
-          for (uint32_t blk = 0; blk < 2 * kTcRows / 8; ++blk) {
-            ptx::bulk_s2g(dst + (size_t)blk * chi * 16 + lo_bytes, a_op + (size_t)blk * chi * 16 + lo_bytes, hi_bytes);
-            ptx::bulk_commit();
-            if (pace) __nanosleep(pace);
-          }
-          ptx::bulk_wait_read0();
-        } else if (on) {  // one column chunk: the tile is one contiguous run
-          for (uint32_t off = 0; off < a_bytes; off += 4096) {
-            ptx::bulk_s2g(dst + off, a_op + off, 4096);
-            ptx::bulk_commit();
-            if (pace) __nanosleep(pace);
-          }
-          ptx::bulk_wait_read0();
-        }
-        ptx::mbar_arrive(img_done);  // the whole operand may be overwritten
       }
       ptx::bulk_wait0();
     }
   } else if (warp == kTcMmaWarp + 1) {
-    // ===== weight producer: one bulk async copy per pipeline stage (= one K-slab of one column chunk) =====
+    // ===== weight producer: one bulk async copy per pipeline stage (= one K-slab of one column chunk); the step's
+    //       image is streamed once per tile =====
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       const int per_step = NH * KS;
       for (int step = 0; step < total; ++step) {
         const uint8_t *img = step_image(step);
-        for (int hk = 0; hk < per_step; ++hk) {
-          ptx::mbar_wait(&empty[stage], phase ^ 1);
-          ptx::mbar_expect_tx(&full[stage], A.stage_bytes);
-          ptx::bulk_g2s(stages + (size_t)stage * A.stage_bytes, img + (size_t)hk * A.stage_bytes, A.stage_bytes,
-                        &full[stage]);
-          if (++stage == A.nstage) { stage = 0; phase ^= 1; }
+        for (int t = 0; t < TILES; ++t) {
+          for (int hk = 0; hk < per_step; ++hk) {
+            ptx::mbar_wait(&empty[stage], phase ^ 1);
+            ptx::mbar_expect_tx(&full[stage], A.stage_bytes);
+            ptx::bulk_g2s(stages + (size_t)stage * A.stage_bytes, img + (size_t)hk * A.stage_bytes, A.stage_bytes,
+                          &full[stage]);
+            if (++stage == A.nstage) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
@@ -300,35 +315,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = ptx::idesc_f16_f32(kTcRows, A.NMMA);
-      const uint32_t a_hi_s = ptx::smem_u32(a_op), a_lo_s = a_hi_s + (uint32_t)chi * 16;
       const uint32_t sbo_a = (uint32_t)chi * 32;
       const uint32_t lo_plane = (uint32_t)A.NMMA * 32;
       int stage = 0;
       uint32_t phase = 0;
       for (int step = 0; step < total; ++step) {
         const bool accum_step = adjoint && step > 0 && step < nseed;  // seed steps accumulate over k
-        ptx::mbar_wait(a_ready, step & 1);
-        ptx::tc_fence_after();
-        TNB_TRACE(3, step, 0);
-        for (int h = 0; h < NH; ++h) {
-          const uint32_t d = tmem_base + (uint32_t)h * A.NMMA;
-          for (int ks = 0; ks < KS; ++ks) {
-            ptx::mbar_wait(&full[stage], phase);
-            ptx::tc_fence_after();
-            const uint64_t da_hi = ptx::smem_desc_kmajor(a_hi_s + ks * 256, 128, sbo_a);
-            const uint64_t da_lo = ptx::smem_desc_kmajor(a_lo_s + ks * 256, 128, sbo_a);
-            const uint32_t st = ptx::smem_u32(stages + (size_t)stage * A.stage_bytes);
-            const uint64_t db_hi = ptx::smem_desc_kmajor(st, 128, 256);
-            const uint64_t db_lo = ptx::smem_desc_kmajor(st + lo_plane, 128, 256);
-            ptx::mma_f16(d, da_hi, db_hi, idesc, (ks > 0 || accum_step) ? 1u : 0u);
-            ptx::mma_f16(d, da_lo, db_hi, idesc, 1u);
-            ptx::mma_f16(d, da_hi, db_lo, idesc, 1u);
-            ptx::mma_commit(&empty[stage]);
-            if (h == NH - 1 && ks == krel - 1) ptx::mma_commit(a_rel);
-            if (++stage == A.nstage) { stage = 0; phase ^= 1; }
+#pragma unroll
+        for (int t = 0; t < TILES; ++t) {
+          const uint32_t a_hi_s = ptx::smem_u32(a_op + (size_t)t * a_bytes), a_lo_s = a_hi_s + (uint32_t)chi * 16;
+          ptx::mbar_wait(&a_ready[t], step & 1);
+          ptx::tc_fence_after();
+          if (t == 0) TNB_TRACE(3, step, 0);
+          for (int h = 0; h < NH; ++h) {
+            const uint32_t d = tmem_base + (uint32_t)t * tile_cols + (uint32_t)h * A.NMMA;
+            for (int ks = 0; ks < KS; ++ks) {
+              ptx::mbar_wait(&full[stage], phase);
+              ptx::tc_fence_after();
+              const uint64_t da_hi = ptx::smem_desc_kmajor(a_hi_s + ks * 256, 128, sbo_a);
+              const uint64_t da_lo = ptx::smem_desc_kmajor(a_lo_s + ks * 256, 128, sbo_a);
+              const uint32_t st = ptx::smem_u32(stages + (size_t)stage * A.stage_bytes);
+              const uint64_t db_hi = ptx::smem_desc_kmajor(st, 128, 256);
+              const uint64_t db_lo = ptx::smem_desc_kmajor(st + lo_plane, 128, 256);
+              ptx::mma_f16(d, da_hi, db_hi, idesc, (ks > 0 || accum_step) ? 1u : 0u);
+              ptx::mma_f16(d, da_lo, db_hi, idesc, 1u);
+              ptx::mma_f16(d, da_hi, db_lo, idesc, 1u);
+              ptx::mma_commit(&empty[stage]);
+              if (h == NH - 1 && ks == krel - 1) ptx::mma_commit(&a_rel[t]);
+              if (++stage == A.nstage) { stage = 0; phase ^= 1; }
+            }
+            ptx::mma_commit(&acc_full[t * kTcMaxNH + h]);
+            if (t == 0) TNB_TRACE(3, step, 1 + h);
           }
-          ptx::mma_commit(&acc_full[h]);
-          TNB_TRACE(3, step, 1 + h);
         }
       }
     }
@@ -336,21 +354,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
     // ===== epilogue: 4 threads per sample row (one per warp group), each owning every 4th 16-column group =====
     const int lq = warp & 3, grp = warp >> 2;
     const int row = lq * 32 + lane;
-    const long long b = b0 + row;
-    const bool valid = b < M.B;
     const bool lead = grp == 0;  // the thread of the row that does the per-sample bookkeeping
-    const size_t bs = (size_t)(valid ? b : 0);
-    const uint32_t trow = tmem_base + ((uint32_t)(lq * 32) << 16);
-    uint8_t *a_row = a_op + (uint32_t)(row >> 3) * (uint32_t)chi * 32 + (uint32_t)(row & 7) * 16;
     const uint32_t lo_off = (uint32_t)chi * 16;  // lo plane of a unit, in the operand and in the bond images
     const int nmine = (chi / 16 - grp + 3) >> 2;  // my 16-column groups: j = 4*i + grp, i < nmine (<= SLOTS)
+    const int nslab = L - 1 + C;
     int step = 0;
 #ifdef TNB_TC_TRACE
     const int tw = warp == 0 ? 0 : (warp == 15 ? 1 : (warp == 6 ? 2 : 63));  // traced epilogue warps (63: not recorded)
 #endif
+    // per-tile state of this thread (its row in each tile)
+    struct Tile {
+      long long b;
+      size_t bs;
+      bool valid;
+      uint32_t trow;
+      uint8_t *a_row;
+      float m_op;    // max-abs of the current operand row (operand units)
+      int ea, eb;    // forward: exponent sums of the left / right chain; adjoint: running exponent h (ea)
+    } T[TILES];
+#pragma unroll
+    for (int t = 0; t < TILES; ++t) {
+      T[t].b = b0 + t * kTcRows + row;
+      T[t].valid = T[t].b < M.B;
+      T[t].bs = (size_t)(T[t].valid ? T[t].b : 0);
+      T[t].trow = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)t * tile_cols;
+      T[t].a_row = a_op + (size_t)t * a_bytes + (uint32_t)(row >> 3) * (uint32_t)chi * 32 + (uint32_t)(row & 7) * 16;
+      T[t].m_op = 16384.f;  // the boundary vector is e0 * 2^14
+      T[t].ea = T[t].eb = 0;
+    }
 
-    // this sample's 16-byte units inside the image of `bond` (see TcArgs)
-    auto img_row = [&](uint8_t *base, int bond) -> uint8_t * {
+    // a sample's 16-byte units inside the image of `bond` (see TcArgs)
+    auto img_row = [&](uint8_t *base, int bond, long long b) -> uint8_t * {
       const int slot = A.img_stash ? bond : (bond == c + 1 ? 0 : -1);
       if (slot < 0 || base == nullptr) return nullptr;
       return base + (size_t)slot * A.img_bond_bytes + tc_img_row(b, chi);
@@ -394,7 +428,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
         }
       }
     };
-    auto write_operand_from_image = [&](const uint8_t *irow, float scale) {
+    auto write_operand_from_image = [&](const uint8_t *irow, float scale, uint8_t *a_row) {
 #pragma unroll
       for (int i = 0; i < SLOTS; ++i) {
         if (i >= nmine) continue;
@@ -413,46 +447,52 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
         store_pk(j, pk, a_row);
       }
     };
-    // the image writer has finished reading the operand of this step (it may be overwritten)
-    auto operand_free = [&]() { ptx::mbar_wait(img_done, step & 1); };
-    // operand (and TMEM reads) done -> the MMA warp may start the next step.  Every warp first makes sure the image
-    // writer has passed this step, so that no barrier phase can run more than one step ahead of a waiter.
-    auto publish = [&](bool first = false) {
-      if (!first) operand_free();
+    // the image writer has finished reading tile t's operand of this step (it may be overwritten)
+    auto operand_free = [&](int t) { ptx::mbar_wait(&img_done[t], step & 1); };
+    // operand (and TMEM reads) done -> the MMA warp may start the tile's next step.  Every warp first makes sure the
+    // image writer has passed this step, so that no barrier phase can run more than one step ahead of a waiter.
+    auto publish = [&](int t, bool first = false) {
+      if (!first) operand_free(t);
       ptx::tc_fence_before();
       ptx::fence_proxy_async();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(a_ready);
+      if (lane == 0) ptx::mbar_arrive(&a_ready[t]);
     };
     // combine one float per thread across the 4 threads of a row (through smem, fixed order)
-    auto row_exchange = [&](float v) -> const float * {
-      float *x = xch + (step & 1) * (4 * kTcRows);
+    auto row_exchange = [&](int t, float v) -> const float * {
+      float *x = xch + (t * 2 + (step & 1)) * (4 * kTcRows);
       x[grp * kTcRows + row] = v;
       ptx::named_bar_sync(1 + lq, 4 * 32);
       return x + row;
     };
-    const int nslab = L - 1 + C;
+    auto row_max = [&](int t, float v) -> float {
+      const float *x = row_exchange(t, v);
+      return fmaxf(fmaxf(x[0], x[kTcRows]), fmaxf(x[2 * kTcRows], x[3 * kTcRows]));
+    };
     // Scale of a step whose outputs are bounded by `bnd`: 2^(14 - e), bnd = f * 2^e, f in [0.5, 1).  *e_out = e.
-    auto bound_scale = [&](float bnd, int *e_out) -> float {
+    auto bound_scale = [&](float bnd, bool valid, int *e_out) -> float {
       const int ef = (int)((__float_as_uint(bnd) >> 23) & 0xffu);
       const bool ok = valid && ef >= 16 && ef < 255;  // (a zero row, or one below 2^-110: flushed)
       *e_out = ok ? ef - 126 : 0;
       return ok ? __uint_as_float((uint32_t)(127 + 126 + kTcKA - ef) << 23) : 0.f;
     };
-    // Wait for the column chunks holding my groups, contract them with phi * sc, split to fp16 hi/lo and write the row
-    // to `dst`: an image row in HBM (every group at once), or the next operand row in smem.  There a group of the last
-    // chunk is stored at once (all MMAs of the step are done), an earlier group is parked in the TMEM columns it came from
-    // and moved to smem as soon as the last chunk's MMAs have released those operand columns (a_rel) -- long before the
-    // last chunk itself is complete.  Returns the max-abs of my part of the scaled row.
-    auto gather_pack = [&](const float(&ph)[D], float sc, uint8_t *dst) -> float {
+    // Wait for the column chunks holding my groups of tile t, contract them with phi * sc, split to fp16 hi/lo and write
+    // the row to `dst`: an image row in HBM (every group at once), or the next operand row in smem.  There a group of
+    // the last chunk is stored at once (all MMAs of the step are done), an earlier group is parked in the TMEM columns
+    // it came from and moved to smem as soon as the last chunk's MMAs have released those operand columns (a_rel) --
+    // long before the last chunk itself is complete.  Returns the max-abs of my part of the scaled row.
+    auto gather_pack = [&](int t, const float(&ph)[D], float sc, uint8_t *dst) -> float {
       float phs[D];
 #pragma unroll
       for (int s = 0; s < D; ++s) phs[s] = ph[s] * sc;
+      uint8_t *a_row = T[t].a_row;
+      const uint32_t trow = T[t].trow;
       const bool to_op = dst == a_row;
+      uint64_t *accf = acc_full + t * kTcMaxNH;
       auto move_parked = [&]() {
         ptx::tmem_st_wait();
-        ptx::mbar_wait(a_rel, step & 1);
-        ptx::mbar_wait(img_half, step & 1);
+        ptx::mbar_wait(&a_rel[t], step & 1);
+        ptx::mbar_wait(&img_half[t], step & 1);
 #pragma unroll
         for (int i = 0; i < SLOTS; ++i) {
           if (i >= nmine) continue;
@@ -463,7 +503,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
           ptx::tmem_ld_wait();
           store_pk(j, pk, a_row);
         }
-        TNB_TRACE(tw, step, 7);
+        if (t == 0) TNB_TRACE(tw, step, 7);
       };
       float m = 0.f;
       int hprev = -1;
@@ -478,11 +518,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
             move_parked();
             moved = true;
           }
-          ptx::mbar_wait(&acc_full[h], step & 1);
+          ptx::mbar_wait(&accf[h], step & 1);
           ptx::tc_fence_after();
-          if (h == NH - 1 && to_op) operand_free();
+          if (h == NH - 1 && to_op) operand_free(t);
           hprev = h;
-          TNB_TRACE(tw, step, h);
+          if (t == 0) TNB_TRACE(tw, step, h);
         }
         uint4 pk[4];
         m = fmaxf(m, tc_combine_pack16<D>(trow + gcol[j], (uint32_t)chi_h, phs, pk));
@@ -496,39 +536,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       }
       if (!moved) move_parked();
       if (hprev != NH - 1) {  // every thread has seen the whole step complete before it publishes
-        ptx::mbar_wait(&acc_full[NH - 1], step & 1);
+        ptx::mbar_wait(&accf[NH - 1], step & 1);
         ptx::tc_fence_after();
       }
-      TNB_TRACE(tw, step, 8);
+      if (t == 0) TNB_TRACE(tw, step, 8);
       return m;
     };
-    float m_op = 16384.f;  // max-abs of the current operand row (operand units); the boundary vector is e0 * 2^14
-    // One chain step.  mode 0: forward (records delta)   mode 1: adjoint (records wq/qmax).
+    // One chain step of tile t.  mode 0: forward (records delta)   mode 1: adjoint (records wq/qmax).
     // `hexp` is the forward exponent sum (mode 0) or the running exponent h of the adjoint (mode 1); lead thread only.
     // next_op: 1 = the scaled row becomes the next operand (the image writer stashes it), 2 = the boundary vector e0
     // does and the row only goes to its image row `irow`, written here.
-    auto chain_step = [&](int site, int slab, int dir, const float(&ph)[D], int mode, int &hexp, int next_op, uint8_t *irow) {
+    auto chain_step = [&](int t, int site, int slab, int dir, int mode, int &hexp, int next_op, uint8_t *irow) {
+      const bool valid = T[t].valid;
+      const long long b = T[t].b;
+      float ph[D];
+      embed_site_d<D>(M.emb, valid ? M.x[T[t].bs * L + site] : 0.5f, ph);
       const int dsite = (mode == 1 && valid && lead) ? M.exps[(size_t)site * M.B + b] : 0;
       const int kw = A.kW[slab];
       int e;
-      const float sc = bound_scale(m_op * A.colsum[dir * nslab + slab], &e);
+      const float sc = bound_scale(T[t].m_op * A.colsum[dir * nslab + slab], valid, &e);
       const bool nz = sc != 0.f;
-      float m = gather_pack(ph, sc, next_op == 2 ? irow : a_row);
-      TNB_TRACE(tw, step, 10);
+      const float m = gather_pack(t, ph, sc, next_op == 2 ? irow : T[t].a_row);
       if (next_op == 2) {
-        operand_free();
-        write_e0(a_row, true);
+        operand_free(t);
+        write_e0(T[t].a_row, true);
       }
-      TNB_TRACE(tw, step, 11);
-      publish();
-      TNB_TRACE(tw, step, 12);
-      // off the critical path (the next step's MMAs are running): row maximum of the new operand, bookkeeping
-      if (next_op == 2) {
-        m_op = 16384.f;
-      } else {
-        const float *x = row_exchange(m);
-        m_op = fmaxf(fmaxf(x[0], x[kTcRows]), fmaxf(x[2 * kTcRows], x[3 * kTcRows]));
-      }
+      if (t == 0) TNB_TRACE(tw, step, 11);
+      publish(t);
+      if (t == 0) TNB_TRACE(tw, step, 12);
+      // off the critical path (the tile's next MMAs are running): row maximum of the new operand, bookkeeping
+      T[t].m_op = next_op == 2 ? 16384.f : row_max(t, m);
       if (lead) {
         const int dtrue = nz ? e - kTcKA - kw : 0;  // exponent in units of the true recurrence
         if (mode == 0) {
@@ -547,186 +584,205 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
           hexp += dtrue - dsite;
         }
       }
-      ++step;
     };
 
     if (!adjoint) {
       // ---------------- forward program ----------------
-      int esumR = 0, esumL = 0;
-      write_e0(a_row, true);
-      write_e0(img_row(A.fimg, L), valid);
-      write_e0(img_row(A.fimg, 0), valid);
-      publish(true);
+#pragma unroll
+      for (int t = 0; t < TILES; ++t) {
+        write_e0(T[t].a_row, true);
+        write_e0(img_row(A.fimg, L, T[t].b), T[t].valid);
+        write_e0(img_row(A.fimg, 0, T[t].b), T[t].valid);
+        publish(t, true);
+      }
       for (int i = 0; i < nR; ++i) {
         const int site = L - 1 - i;
-        float ph[D];
-        embed_site_d<D>(M.emb, valid ? M.x[bs * L + site] : 0.5f, ph);
-        chain_step(site, mps_slab(M, site), 1, ph, 0, esumR, i == nR - 1 ? 2 : 1, img_row(A.fimg, site));
+#pragma unroll
+        for (int t = 0; t < TILES; ++t)
+          chain_step(t, site, mps_slab(M, site), 1, 0, T[t].eb, i == nR - 1 ? 2 : 1, img_row(A.fimg, site, T[t].b));
+        ++step;
       }
       for (int i = 0; i < nL; ++i) {
-        const int site = i;
-        float ph[D];
-        embed_site_d<D>(M.emb, valid ? M.x[bs * L + site] : 0.5f, ph);
-        chain_step(site, mps_slab(M, site), 0, ph, 0, esumL, 1, nullptr);
+#pragma unroll
+        for (int t = 0; t < TILES; ++t) chain_step(t, i, mps_slab(M, i), 0, 0, T[t].ea, 1, nullptr);
+        ++step;
       }
       // ---------------- class site + head ----------------
-      float phc[D];
-      embed_site_d<D>(M.emb, valid ? M.x[bs * L + c] : 0.5f, phc);
-      const uint8_t *fr = img_row(A.fimg, c + 1);  // each thread wrote its own column groups of that row (scale 2^14)
       const float ysc = ldexpf(1.f, -(2 * kTcKA + A.kW[c]));
-      float y[kMaxOut];
+      float y[TILES][kMaxOut];
+      float phc[TILES][D];
+#pragma unroll
+      for (int t = 0; t < TILES; ++t) embed_site_d<D>(M.emb, T[t].valid ? M.x[T[t].bs * L + c] : 0.5f, phc[t]);
       for (int k = 0; k < C; ++k) {
-        float acc = 0.f;
-        int hprev = -1;
 #pragma unroll
-        for (int i = 0; i < SLOTS; ++i) {
-          if (i >= nmine) continue;
-          const int j = 4 * i + grp;
-          float f[16];
-          if (fr) load_img16(fr, j, f);
-          else {
+        for (int t = 0; t < TILES; ++t) {
+          const uint8_t *fr = img_row(A.fimg, c + 1, T[t].b);  // each thread wrote its own column groups of that row
+          uint64_t *accf = acc_full + t * kTcMaxNH;
+          float acc = 0.f;
+          int hprev = -1;
 #pragma unroll
-            for (int q = 0; q < 16; ++q) f[q] = 0.f;
+          for (int i = 0; i < SLOTS; ++i) {
+            if (i >= nmine) continue;
+            const int j = 4 * i + grp;
+            float f[16];
+            if (fr) load_img16(fr, j, f);
+            else {
+#pragma unroll
+              for (int q = 0; q < 16; ++q) f[q] = 0.f;
+            }
+            const int h = (int)gchunk[j];
+            if (h != hprev) {
+              ptx::mbar_wait(&accf[h], step & 1);
+              ptx::tc_fence_after();
+              hprev = h;
+            }
+            float o[16];
+            tc_combine16<D>(T[t].trow + gcol[j], (uint32_t)chi_h, phc[t], o);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) acc = fmaf(o[q], f[q], acc);
           }
-          const int h = (int)gchunk[j];
-          if (h != hprev) {
-            ptx::mbar_wait(&acc_full[h], step & 1);
+          if (hprev != NH - 1) {
+            ptx::mbar_wait(&accf[NH - 1], step & 1);
             ptx::tc_fence_after();
-            hprev = h;
           }
-          float o[16];
-          tc_combine16<D>(trow + gcol[j], (uint32_t)chi_h, phc, o);
-#pragma unroll
-          for (int q = 0; q < 16; ++q) acc = fmaf(o[q], f[q], acc);
+          const float *x = row_exchange(t, acc);
+          y[t][k] = ((x[0] + x[kTcRows]) + (x[2 * kTcRows] + x[3 * kTcRows])) * ysc;
+          publish(t);
         }
-        if (hprev != NH - 1) {
-          ptx::mbar_wait(&acc_full[NH - 1], step & 1);
-          ptx::tc_fence_after();
-        }
-        const float *x = row_exchange(acc);
-        y[k] = ((x[0] + x[kTcRows]) + (x[2 * kTcRows] + x[3 * kTcRows])) * ysc;
-        publish();
         ++step;
       }
       if (lead) {
-        float lval = 0.f;
-        if (valid) {
-          M.esum[b] = esumL;
-          M.esum[M.B + b] = esumR;
-          float tl[kMaxOut];
-          for (int k = 0; k < C; ++k) {
-            tl[k] = M.targets ? M.targets[(size_t)b * C + k] : 0.f;
-            M.y[(size_t)b * C + k] = y[k];
-            if (M.out) M.out[(size_t)b * C + k] = y[k];
+#pragma unroll
+        for (int t = 0; t < TILES; ++t) {
+          const long long b = T[t].b;
+          float lval = 0.f;
+          if (T[t].valid) {
+            M.esum[b] = T[t].ea;
+            M.esum[M.B + b] = T[t].eb;
+            float tl[kMaxOut];
+            for (int k = 0; k < C; ++k) {
+              tl[k] = M.targets ? M.targets[(size_t)b * C + k] : 0.f;
+              M.y[(size_t)b * C + k] = y[t][k];
+              if (M.out) M.out[(size_t)b * C + k] = y[t][k];
+            }
+            const int E = T[t].ea + T[t].eb;
+            if (M.out_exp) M.out_exp[b] = E;
+            lval = mps_head<float>(M.head, C, y[t], E, tl, M.cw, (float *)nullptr);
+            if (M.loss) M.loss[b] = lval;
           }
-          const int E = esumL + esumR;
-          if (M.out_exp) M.out_exp[b] = E;
-          lval = mps_head<float>(M.head, C, y, E, tl, M.cw, (float *)nullptr);
-          if (M.loss) M.loss[b] = lval;
-        }
-        if (M.loss_sum) {  // one atomic per warp
-          double ls = (double)lval;
-          for (int off = 16; off > 0; off >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, off);
-          if (lane == 0) atomicAdd(M.loss_sum, ls);
+          if (M.loss_sum) {  // one atomic per warp
+            double ls = (double)lval;
+            for (int off = 16; off > 0; off >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, off);
+            if (lane == 0) atomicAdd(M.loss_sum, ls);
+          }
         }
       }
     } else {
       // ---------------- adjoint program ----------------
-      // head derivative dLoss/dy' (times loss_scale) for this sample
-      float dy[kMaxOut];
-      {
-        float yl[kMaxOut], tl[kMaxOut];
-        for (int k = 0; k < C; ++k) {
-          yl[k] = valid ? M.y[(size_t)b * C + k] : 1.f;
-          tl[k] = (valid && M.targets) ? M.targets[(size_t)b * C + k] : (k == 0 ? 1.f : 0.f);
-        }
-        const int E = valid ? M.esum[b] + M.esum[M.B + b] : 0;
-        mps_head<float>(M.head, C, yl, E, tl, M.cw, dy);
-        for (int k = 0; k < C; ++k) dy[k] = valid ? dy[k] * M.loss_scale : 0.f;
-      }
-      float phc[D];
-      embed_site_d<D>(M.emb, valid ? M.x[bs * L + c] : 0.5f, phc);
-      float dmax = 0.f;
-      for (int k = 0; k < C; ++k) dmax = fmaxf(dmax, fabsf(dy[k]));
-      int ed = 0;
-      if (dmax > 0.f) frexpf(dmax, &ed);
-      if (valid && lead) {
-        // class-site dA weights: wqc[(s,k)][b] = phi_s * dy'_k ; both halves write identical values
-        int qm = INT_MIN;
+      float dy[TILES][kMaxOut];
+      float phc[TILES][D];
+      float bnd[TILES], dsc[TILES];
+      int ed[TILES];
+      const uint8_t *vrow[TILES];
 #pragma unroll
-        for (int s = 0; s < D; ++s)
+      for (int t = 0; t < TILES; ++t) {
+        const bool valid = T[t].valid;
+        const long long b = T[t].b;
+        // head derivative dLoss/dy' (times loss_scale) for this sample
+        {
+          float yl[kMaxOut], tl[kMaxOut];
           for (int k = 0; k < C; ++k) {
-            const float w = phc[s] * dy[k];
-            A.wqc[((size_t)s * C + k) * M.B + b] = w;
-            if (w != 0.f) { int ew; frexpf(w, &ew); qm = max(qm, ew); }
+            yl[k] = valid ? M.y[(size_t)b * C + k] : 1.f;
+            tl[k] = (valid && M.targets) ? M.targets[(size_t)b * C + k] : (k == 0 ? 1.f : 0.f);
           }
-        for (int k = 0; k < C; ++k) M.dy[(size_t)b * C + k] = dy[k];
-        if (qm != INT_MIN) atomicMax(A.qmaxc, qm);
-      }
-      const uint8_t *vrow = img_row(A.fimg, half == 0 ? c + 1 : c);  // forward environment row (operand units)
-      const float dsc = valid ? ldexpf(1.f, -ed) : 0.f;              // |dy_k * dsc| < 1
-      // bound of the accumulated seed: sum_k |dy_k dsc| * max|row| * colsum(slab c+k)
-      float mrow = 0.f;
-      if (vrow) {
-#pragma unroll
-        for (int i = 0; i < SLOTS; ++i) {
-          if (i >= nmine) continue;
-          float w[16];
-          load_img16(vrow, 4 * i + grp, w);
-#pragma unroll
-          for (int q = 0; q < 16; ++q) mrow = fmaxf(mrow, fabsf(w[q]));
+          const int E = valid ? M.esum[b] + M.esum[M.B + b] : 0;
+          mps_head<float>(M.head, C, yl, E, tl, M.cw, dy[t]);
+          for (int k = 0; k < C; ++k) dy[t][k] = valid ? dy[t][k] * M.loss_scale : 0.f;
         }
+        embed_site_d<D>(M.emb, valid ? M.x[T[t].bs * L + c] : 0.5f, phc[t]);
+        float dmax = 0.f;
+        for (int k = 0; k < C; ++k) dmax = fmaxf(dmax, fabsf(dy[t][k]));
+        ed[t] = 0;
+        if (dmax > 0.f) frexpf(dmax, &ed[t]);
+        if (valid && lead) {
+          // class-site dA weights: wqc[(s,k)][b] = phi_s * dy'_k ; both halves write identical values
+          int qm = INT_MIN;
+#pragma unroll
+          for (int s = 0; s < D; ++s)
+            for (int k = 0; k < C; ++k) {
+              const float w = phc[t][s] * dy[t][k];
+              A.wqc[((size_t)s * C + k) * M.B + b] = w;
+              if (w != 0.f) { int ew; frexpf(w, &ew); qm = max(qm, ew); }
+            }
+          for (int k = 0; k < C; ++k) M.dy[(size_t)b * C + k] = dy[t][k];
+          if (qm != INT_MIN) atomicMax(A.qmaxc, qm);
+        }
+        vrow[t] = img_row(A.fimg, half == 0 ? c + 1 : c, b);  // forward environment row (operand units)
+        dsc[t] = valid ? ldexpf(1.f, -ed[t]) : 0.f;           // |dy_k * dsc| < 1
+        // bound of the accumulated seed: sum_k |dy_k dsc| * max|row| * colsum(slab c+k)
+        float mrow = 0.f;
+        if (vrow[t]) {
+#pragma unroll
+          for (int i = 0; i < SLOTS; ++i) {
+            if (i >= nmine) continue;
+            float w[16];
+            load_img16(vrow[t], 4 * i + grp, w);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) mrow = fmaxf(mrow, fabsf(w[q]));
+          }
+        }
+        mrow = row_max(t, mrow);
+        float bs_ = 0.f;
+        for (int k = 0; k < C; ++k) bs_ += fabsf(dy[t][k] * dsc[t]) * A.colsum[(half == 0 ? nslab : 0) + c + k];
+        bnd[t] = bs_ * mrow * 1.001f;
+        write_operand_from_image(vrow[t], dy[t][0] * dsc[t], T[t].a_row);
+        publish(t, true);
       }
-      {
-        const float *x = row_exchange(mrow);
-        mrow = fmaxf(fmaxf(x[0], x[kTcRows]), fmaxf(x[2 * kTcRows], x[3 * kTcRows]));
-      }
-      float bnd = 0.f;
-      for (int k = 0; k < C; ++k) bnd += fabsf(dy[k] * dsc) * A.colsum[(half == 0 ? nslab : 0) + c + k];
-      bnd *= mrow * 1.001f;
-      write_operand_from_image(vrow, dy[0] * dsc);
-      publish(true);
-      int h = 0;
       const int jb = half == 0 ? 0 : L - 1;  // the boundary site: no chain step, but it has a gradient
       for (int k = 0; k < C; ++k) {
-        if (k < C - 1) {
-          ptx::mbar_wait(&acc_full[NH - 1], step & 1);  // MMAs of step k have finished reading the operand
-          ptx::tc_fence_after();
-          operand_free();
-          write_operand_from_image(vrow, dy[k + 1] * dsc);
-          publish();
-          ++step;
-        } else {
-          // all C slabs accumulated: scale -> seed G[c] / G[c+1] (operand of the first chain step; the writer stashes it)
-          int e;
-          const float sc = bound_scale(bnd, &e);
-          const float m = gather_pack(phc, sc, a_row);
-          h = (sc != 0.f ? e - kTcKA - A.kW[c] : 0) + ed;  // G = row * 2^h (the operand carried dy * 2^-ed)
-          publish();
-          const float *x = row_exchange(m);
-          m_op = fmaxf(fmaxf(x[0], x[kTcRows]), fmaxf(x[2 * kTcRows], x[3 * kTcRows]));
-          ++step;
+#pragma unroll
+        for (int t = 0; t < TILES; ++t) {
+          if (k < C - 1) {
+            ptx::mbar_wait(&acc_full[t * kTcMaxNH + NH - 1], step & 1);  // MMAs of step k have finished reading the operand
+            ptx::tc_fence_after();
+            operand_free(t);
+            write_operand_from_image(vrow[t], dy[t][k + 1] * dsc[t], T[t].a_row);
+            publish(t);
+          } else {
+            // all C slabs accumulated: scale -> seed G[c] / G[c+1] (operand of the first chain step; the writer stashes it)
+            int e;
+            const float sc = bound_scale(bnd[t], T[t].valid, &e);
+            const float m = gather_pack(t, phc[t], sc, T[t].a_row);
+            T[t].ea = (sc != 0.f ? e - kTcKA - A.kW[c] : 0) + ed[t];  // G = row * 2^h (the operand carried dy * 2^-ed)
+            publish(t);
+            T[t].m_op = row_max(t, m);
+          }
         }
+        ++step;
       }
       for (int i = 0; i < nchain; ++i) {
         const int site = half == 0 ? c - 1 - i : c + 1 + i;
-        float ph[D];
-        embed_site_d<D>(M.emb, valid ? M.x[bs * L + site] : 0.5f, ph);
-        chain_step(site, mps_slab(M, site), half == 0 ? 1 : 0, ph, 1, h, 1, nullptr);
+#pragma unroll
+        for (int t = 0; t < TILES; ++t) chain_step(t, site, mps_slab(M, site), half == 0 ? 1 : 0, 1, T[t].ea, 1, nullptr);
+        ++step;
       }
       // boundary site weights
       if (lead) {
-        int qm = INT_MIN;
-        if (valid) {
-          const int q = h - M.exps[(size_t)jb * M.B + b];
-          float ph[D];
-          embed_site_d<D>(M.emb, M.x[(size_t)b * L + jb], ph);
 #pragma unroll
-          for (int s = 0; s < D; ++s) A.wq[((size_t)jb * D + s) * M.B + b] = ph[s] * ldexpf(1.f, q);
-          qm = q;
+        for (int t = 0; t < TILES; ++t) {
+          int qm = INT_MIN;
+          if (T[t].valid) {
+            const long long b = T[t].b;
+            const int q = T[t].ea - M.exps[(size_t)jb * M.B + b];
+            float ph[D];
+            embed_site_d<D>(M.emb, M.x[(size_t)b * L + jb], ph);
+#pragma unroll
+            for (int s = 0; s < D; ++s) A.wq[((size_t)jb * D + s) * M.B + b] = ph[s] * ldexpf(1.f, q);
+            qm = q;
+          }
+          for (int off = 16; off > 0; off >>= 1) qm = max(qm, __shfl_xor_sync(0xffffffffu, qm, off));
+          if (lane == 0 && qm != INT_MIN) atomicMax(&A.qmax[jb], qm);
         }
-        for (int off = 16; off > 0; off >>= 1) qm = max(qm, __shfl_xor_sync(0xffffffffu, qm, off));
-        if (lane == 0 && qm != INT_MIN) atomicMax(&A.qmax[jb], qm);
       }
     }
   }

@@ -30,10 +30,11 @@ if __name__ == "__main__":
     from tn4ml_b200 import _lib
     _lib.LIB_PATH = SO
     from tools.bench_configs import CONFIGS, run
-    cfg = dict(CONFIGS["cfg5"])
+    name = os.environ.get("TRACE_CFG", "cfg5")
+    cfg = dict(CONFIGS[name])
     cfg["B"] = int(os.environ.get("TRACE_B", "18944"))
     fwd_only = "--fwd" in sys.argv
-    run("cfg5", cfg, torch.float32, steps=1, warmup=1)
+    run(name, cfg, torch.float32, steps=1, warmup=1)
     lib = _lib.lib()
     lib.tnb_debug_trace_read.restype = C.c_int
     n = 64 * 32
