@@ -60,3 +60,16 @@ def test_tensor_path_long_chain():
     prob = O.Problem("mps", O.EmbSpec("trig"), "softmax_xent")
     model = _tensor_model(T.TensorNetwork, arrays)
     _check(model, prob, _heads()["softmax_xent"], x, arrays, t, torch.float32, precision=1)
+
+
+def test_tensor_path_two_tile_rounds_and_remainder():
+    """chi = 128 (N = 256, one column chunk): a sweep over 297 sample tiles runs as two-tile CTAs for the whole rounds of
+    148 SMs and one-tile CTAs for the remainder (forward: 296 + 1 tiles; adjoint: 148-tile rounds per half)."""
+    import tn4ml_b200 as T
+    B = 297 * 128 - 5
+    arrays = O.make_mps_arrays(5, 128, 2, class_site=2, C=3, std=0.05, seed=3)
+    x = O.make_inputs(B, 5, seed=5)
+    t = O.make_labels(B, 3)
+    prob = O.Problem("mps", O.EmbSpec("trig"), "softmax_xent")
+    model = _tensor_model(T.TensorNetwork, arrays)
+    _check(model, prob, _heads()["softmax_xent"], x, arrays, t, torch.float32, precision=1)
