@@ -117,6 +117,20 @@ struct MpsPlan {
   size_t tc_site_img, off_img_n, off_img_t, off_kW, off_cs, off_wq, off_qmax, off_wqc, off_fimg, off_gimg, tc_smem, img_bond_bytes;
 };
 
+// Measurement knobs of the tensor path (environment, read once): TNB_TC_NH forces a legal column-chunk count,
+// TNB_TC_TILES=1 forces one sample tile per CTA, TNB_TC_PACE_NS sets the image writer's pause between pieces.
+struct TcKnobs { int nh = 0, tiles = 0, pace_ns = -1; };
+static const TcKnobs &tc_knobs() {
+  static TcKnobs k;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    if (const char *e = getenv("TNB_TC_NH")) k.nh = atoi(e);
+    if (const char *e = getenv("TNB_TC_TILES")) k.tiles = atoi(e);
+    if (const char *e = getenv("TNB_TC_PACE_NS")) k.pace_ns = atoi(e);
+  });
+  return k;
+}
+
 // The tcgen05 sweep covers: float32, chi a multiple of 16 in [32, 256], D*chi <= 512 TMEM columns.
 static bool tc_supported(const tnb_problem *p) {
   if (p->kind != TNB_KIND_MPS || p->dtype != TNB_F32 || p->precision != TNB_PREC_TENSOR) return false;
@@ -127,14 +141,10 @@ static bool tc_supported(const tnb_problem *p) {
 }
 
 // Column chunks per chain step: the smallest NH dividing chi/16 whose chunk (D*chi/NH columns) fits one MMA (N <= 256).
-// TNB_TC_NH (environment) forces another legal split (measurement aid).
 static int tc_pick_nh(const tnb_problem *p) {
   const int groups = p->chi / 16;
   auto legal = [&](int nh) { return nh >= 1 && nh <= kTcMaxNH && groups % nh == 0 && p->d * p->chi / nh <= 256; };
-  if (const char *e = getenv("TNB_TC_NH")) {
-    const int nh = atoi(e);
-    if (legal(nh)) return nh;
-  }
+  if (legal(tc_knobs().nh)) return tc_knobs().nh;
   for (int nh = 1; nh <= groups; ++nh)
     if (legal(nh)) return nh;
   return groups;
@@ -186,7 +196,7 @@ static MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
     // two sample tiles per CTA when one column chunk covers the step (nothing else hides the epilogue); TNB_TC_TILES=1 forces one
     // (pays when the step's MMA time is comparable to its exposed tail: N = 256; measured slower at N <= 128)
     P.tc_tiles = (P.tc_NH == 1 && P.tc_N == 256) ? 2 : 1;
-    if (const char *e = getenv("TNB_TC_TILES")) { if (atoi(e) == 1) P.tc_tiles = 1; }
+    if (tc_knobs().tiles == 1) P.tc_tiles = 1;
     P.tc_cols = 32;
     while (P.tc_cols < P.tc_tiles * P.tc_N) P.tc_cols <<= 1;
     const size_t fixed = (size_t)P.tc_tiles * 4096 /* row exchange */ + 1024 /* tables, barriers */;
@@ -243,7 +253,7 @@ static void fill_tc_args(const MpsPlan &P, void *ws, const MpsArgs<float> &M, Tc
   T.kW = (const int *)(w + P.off_kW);
   T.tile0 = 0;
   T.colsum = (const float *)(w + P.off_cs);
-  { const char *e = getenv("TNB_TC_PACE_NS"); T.pace_ns = e ? atoi(e) : P.tc_N * 2 / 5; }
+  T.pace_ns = tc_knobs().pace_ns >= 0 ? tc_knobs().pace_ns : P.tc_N * 2 / 5;
   T.wq = (float *)(w + P.off_wq);
   T.qmax = (int *)(w + P.off_qmax);
   T.wqc = (float *)(w + P.off_wqc);
