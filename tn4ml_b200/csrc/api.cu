@@ -407,9 +407,7 @@ static int mps_backward_t(const tnb_problem *p, const MpsPlan &P, long long B, c
       static std::once_flag once;
       static cudaError_t aerr = cudaSuccess;
       std::call_once(once, [] {
-        aerr = cudaFuncSetAttribute(tc_da_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 2048);
-        if (aerr == cudaSuccess)
-          aerr = cudaFuncSetAttribute(tc_da_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 2048);
+        aerr = cudaFuncSetAttribute(tc_da_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 2048);
         if (aerr == cudaSuccess)
           aerr = cudaFuncSetAttribute(tc_da_kernel<kDaMaxCpg>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 2048);
       });
@@ -424,14 +422,15 @@ static int mps_backward_t(const tnb_problem *p, const MpsPlan &P, long long B, c
       Da.tmem_cols = 32;
       while (Da.tmem_cols < 2 * p->chi) Da.tmem_cols <<= 1;
       const long long maxsp = (B + 2047) / 2048;
-      Da.cpg = 256 / p->chi < 1 ? 1 : 256 / p->chi;
+      Da.ra = p->chi < 128 ? p->chi : 128;
+      Da.cpg = 256 / Da.ra;
       for (int pass = 0; pass < 2; ++pass) {
         // pass 0: every chain site (copies sigma = s);  pass 1: the class site (copies sigma = (s, k))
         Da.Dv = pass == 0 ? p->d : p->d * p->n_out;
         Da.only_site = pass == 0 ? -1 : p->out_site;
         Da.wq = pass == 0 ? Tc.wq : Tc.wqc;
         Da.qmax = pass == 0 ? Tc.qmax : Tc.qmaxc;
-        Da.mgroups = (Da.Dv + Da.cpg - 1) / Da.cpg;
+        Da.mgroups = ((p->chi + Da.ra - 1) / Da.ra) * ((Da.Dv + Da.cpg - 1) / Da.cpg);
         // split K (the batch) so that the grid fills the 148 SMs about four times over with little wave quantisation
         const long long ctas = (long long)(pass == 0 ? p->L - 1 : 1) * Da.mgroups;
         long long best = 1;
@@ -447,8 +446,7 @@ static int mps_backward_t(const tnb_problem *p, const MpsPlan &P, long long B, c
         dim3 gda((unsigned)(Da.mgroups * Da.nsplit), (unsigned)(pass == 0 ? p->L : 1));
         prof_begin(st);
         const size_t da_smem = (size_t)Da.nstage * kDaStage + 1024;
-        if (Da.cpg == 1) tc_da_kernel<1><<<gda, kDaThreads, da_smem, st>>>(Da);
-        else if (Da.cpg == 2) tc_da_kernel<2><<<gda, kDaThreads, da_smem, st>>>(Da);
+        if (Da.cpg == 2) tc_da_kernel<2><<<gda, kDaThreads, da_smem, st>>>(Da);
         else tc_da_kernel<kDaMaxCpg><<<gda, kDaThreads, da_smem, st>>>(Da);
         TNB_LAUNCH_CHECK(pass == 0 ? "tc_da_kernel" : "tc_da_kernel(class)");
       }

@@ -197,11 +197,13 @@ namespace tnb {
 //   rows m = sigma*chi + a, columns r (N = chi), K = samples.
 // Both operands are the fp16 hi/lo bond images the chain kernels write; a run of 32 samples of an image is an
 // MN-major operand tile as it stands, so both arrive by bulk async copies (deep prefetch, no load latency in any warp).
-// V is used as it is.  U carries the per-sample weight: one CTA owns `cpg` weighted copies sigma of the chi rows
-// (cpg*chi <= 256 rows, two M tiles); the raw chunk lands in the rows of the CTA's first copy, and 16 producer warps
-// (lane == sample, warp == row octet) rebuild fp32 from hi/lo, apply each copy's weight, re-split and write the copies
-// (the first one in place).  One warp issues the MMAs; warps 0-3 drain TMEM once at the end and reduce into the
-// packed gradient with fp32 atomics (split-K across CTAs).
+// V is used as it is.  U carries the per-sample weight: one CTA owns `cpg` weighted copies sigma of `ra` bond rows
+// (ra = min(chi, 128), cpg*ra <= 256 rows, two M tiles); the raw rows land in the CTA's first copy, and 16 producer
+// warps (lane == sample, warp == row octet) rebuild fp32 from hi/lo, apply each copy's weight, re-split and write the
+// copies (the first one in place).  One warp issues the MMAs; warps 0-3 drain TMEM once at the end and reduce into the
+// packed gradient with fp32 atomics (split-K across CTAs).  With ra = 128 and two copies, tile t is copy t of the same
+// 128 rows: both values of a (row, column) go through a per-warp shared-memory transpose and leave as 128-byte runs of
+// the packed layout [a][r][sigma].
 // ---------------------------------------------------------------------------------------
 struct TcDaArgs {
   MpsArgs<float> M;
@@ -213,7 +215,8 @@ struct TcDaArgs {
   const uint8_t *fimg, *gimg;
   size_t img_bond_bytes;
   int Dv;            // weighted copies sigma < Dv: D for chain sites, D*C for the class site
-  int cpg;           // copies per CTA: max(1, 256 / chi)
+  int ra;            // bond rows per copy and CTA: min(chi, 128)
+  int cpg;           // copies per CTA: 256 / ra
   int only_site;     // >= 0: this site only (the class site; wq/qmax point at its own tables)
 };
 
@@ -241,11 +244,15 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
   if (A.only_site < 0 && site == c) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int group = blockIdx.x % A.mgroups, split = blockIdx.x / A.mgroups;
-  const int sig0 = group * A.cpg;                       // first copy of this CTA
+  const int nag = (chi + A.ra - 1) / A.ra;              // row groups
+  const int ag = group % nag, cg = group / nag;
+  const int a0 = ag * A.ra;                             // first bond row of this CTA
+  const int ra = A.ra, ra_eff = min(ra, chi - a0);      // rows per copy (stride) / rows in use
+  const int sig0 = cg * A.cpg;                          // first copy of this CTA
   const int ncopy = min(A.cpg, Dv - sig0);              // copies of this CTA (<= CPG)
-  const int nrows = ncopy * chi;                        // operand rows in use (<= 256)
+  const int nrows = ncopy * ra;                         // operand rows spanned (<= 256)
   const int ntile = (nrows + 127) / 128;
-  const int noct = chi / 8;                             // row octets of one copy
+  const int noct = ra_eff / 8;                          // row octets of one copy in use
   const long long kbeg = (long long)split * A.bchunk;
   const long long kend = min(M.B, kbeg + A.bchunk);
   if (kbeg >= kend) return;
@@ -325,11 +332,12 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
       for (int ch = 0; ch < nchunks; ++ch) {
         ptx::mbar_wait(&empty[stage], phase ^ 1);
         uint8_t *st = stages + (size_t)stage * kDaStage;
-        ptx::mbar_expect_tx(&loaded[stage], 2 * b_bytes);
-        const uint8_t *usrc = Uimg + (size_t)ch * b_bytes;
+        const uint32_t u_bytes = (uint32_t)noct * 128;  // the CTA's rows of one (sample block, plane)
+        ptx::mbar_expect_tx(&loaded[stage], 2 * (kDaKC / 8) * u_bytes + b_bytes);
+        const uint8_t *usrc = Uimg + (size_t)ch * b_bytes + (size_t)(a0 / 8) * 128;
 #pragma unroll
         for (int bp = 0; bp < 2 * (kDaKC / 8); ++bp)  // (sample block, plane)
-          ptx::bulk_g2s(st + (uint32_t)bp * kDaUPlane, usrc + (size_t)bp * chi * 16, (uint32_t)chi * 16, &loaded[stage]);
+          ptx::bulk_g2s(st + (uint32_t)bp * kDaUPlane, usrc + (size_t)bp * chi * 16, u_bytes, &loaded[stage]);
         ptx::bulk_g2s(st + kDaU, Vimg + (size_t)ch * b_bytes, b_bytes, &loaded[stage]);
         if (++stage == A.nstage) { stage = 0; phase ^= 1; }
       }
@@ -392,8 +400,8 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
               ho[j] = *reinterpret_cast<const uint32_t *>(&hh);
               lo[j] = *reinterpret_cast<const uint32_t *>(&ll);
             }
-            *reinterpret_cast<uint4 *>(st + (s * noct + o) * 128) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
-            *reinterpret_cast<uint4 *>(st + kDaUPlane + (s * noct + o) * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4 *>(st + (s * (ra / 8) + o) * 128) = make_uint4(ho[0], ho[1], ho[2], ho[3]);
+            *reinterpret_cast<uint4 *>(st + kDaUPlane + (s * (ra / 8) + o) * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
         }
       }
@@ -409,19 +417,46 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
       const float sc = ldexpf(1.f, qmax - 2 * kTcKA);
       const size_t site_off = (size_t)site * chi * chi * M.D + (site > c ? (size_t)chi * chi * M.D * (M.C - 1) : 0);
       float *g = A.grads + site_off;
-      for (int t = 0; t < ntile; ++t) {
-        if (t * 128 + warp * 32 >= nrows) continue;  // warp-uniform: tcgen05.ld is a warp-collective instruction
-        const int mm = t * 128 + tid;
-        const bool on = mm < nrows;
-        const int sl = on ? mm / chi : 0, a = on ? mm - sl * chi : 0, sg = sig0 + sl;
-        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)t * chi;
+      if (ra == 128 && ncopy == 2) {
+        // tile t == copy t of rows a0 .. a0+127: transpose 32 rows x (16 columns x 2 copies) through shared memory (the
+        // pipeline stages are idle now) so that a warp adds one 128-byte run of [a][r][sigma] per instruction
+        float *stg = reinterpret_cast<float *>(stages) + warp * (32 * 33);
+        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const int abase = a0 + warp * 32;
         for (int n0 = 0; n0 < chi; n0 += 16) {
-          float v[16];
-          ptx::tmem_ld16(trow + n0, v);
+          float v0[16], v1[16];
+          ptx::tmem_ld16(trow + n0, v0);
+          ptx::tmem_ld16(trow + chi + n0, v1);
           ptx::tmem_ld_wait();
-          if (on) {
+          __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) atomicAdd(&g[((size_t)a * chi + n0 + j) * Dv + sg], v[j] * sc);
+          for (int j = 0; j < 16; ++j) {
+            stg[lane * 33 + 2 * j] = v0[j] * sc;
+            stg[lane * 33 + 2 * j + 1] = v1[j] * sc;
+          }
+          __syncwarp();
+          for (int rr = 0; rr < 32; ++rr) {
+            const int a = abase + rr;
+            if (a >= a0 + ra_eff) break;
+            atomicAdd(&g[((size_t)a * chi + n0 + (lane >> 1)) * Dv + sig0 + (lane & 1)], stg[rr * 33 + lane]);
+          }
+        }
+      } else {
+        for (int t = 0; t < ntile; ++t) {
+          if (t * 128 + warp * 32 >= nrows) continue;  // warp-uniform: tcgen05.ld is a warp-collective instruction
+          const int mm = t * 128 + tid;
+          const int sl = mm / ra, al = mm - sl * ra;
+          const bool on = sl < ncopy && al < ra_eff;
+          const int a = a0 + al, sg = sig0 + sl;
+          const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)t * chi;
+          for (int n0 = 0; n0 < chi; n0 += 16) {
+            float v[16];
+            ptx::tmem_ld16(trow + n0, v);
+            ptx::tmem_ld_wait();
+            if (on) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) atomicAdd(&g[((size_t)a * chi + n0 + j) * Dv + sg], v[j] * sc);
+            }
           }
         }
       }

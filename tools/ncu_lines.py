@@ -1,20 +1,23 @@
 #!/usr/bin/env python
 """Aggregate the warp-stall samples of an ncu report by CUDA source line.
-   ncu -i rep.ncu-rep --page source --csv --print-source cuda,sass > src.csv ; python tools/ncu_lines.py src.csv [top]"""
+   ncu -i rep.ncu-rep --page source --csv --print-source cuda,sass > src.csv ; python tools/ncu_lines.py src.csv [top [kernel]]"""
 import csv
 import sys
 
 rows = list(csv.reader(open(sys.argv[1])))
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 50
-cur_file, hdr, out = None, None, []
+only = sys.argv[3] if len(sys.argv) > 3 else ""   # optional: restrict to kernels whose name contains this
+cur_file, cur_fn, hdr, out = None, "", None, []
 for r in rows:
     if not r:
         continue
     if r[0] == "File Path":
         cur_file = r[1].split('/')[-1]
+    elif r[0] == "Function Name":
+        cur_fn = r[1]
     elif r[0] == "Line No":
         hdr = r
-    elif r[0] not in ("", "Function Name") and hdr is not None and len(r) > 10 and r[0].isdigit():
+    elif r[0] != "" and hdr is not None and len(r) > 10 and r[0].isdigit() and only in cur_fn:
         out.append((cur_file, r))
 idx = {n: i for i, n in enumerate(hdr)}
 si = hdr.index("# Samples")
