@@ -118,8 +118,9 @@ struct MpsPlan {
 };
 
 // Measurement knobs of the tensor path (environment, read once): TNB_TC_NH forces a legal column-chunk count,
-// TNB_TC_TILES=1 forces one sample tile per CTA, TNB_TC_PACE_NS sets the image writer's pause between pieces.
-struct TcKnobs { int nh = 0, tiles = 0, pace_ns = -1; };
+// TNB_TC_TILES=1 forces one sample tile per CTA, TNB_TC_PACE_NS sets the image writer's pause between pieces,
+// TNB_DA_STAGES lowers the pipeline depth of the weight-gradient GEMM.
+struct TcKnobs { int nh = 0, tiles = 0, pace_ns = -1, da_stages = 0; };
 static const TcKnobs &tc_knobs() {
   static TcKnobs k;
   static std::once_flag once;
@@ -127,6 +128,7 @@ static const TcKnobs &tc_knobs() {
     if (const char *e = getenv("TNB_TC_NH")) k.nh = atoi(e);
     if (const char *e = getenv("TNB_TC_TILES")) k.tiles = atoi(e);
     if (const char *e = getenv("TNB_TC_PACE_NS")) k.pace_ns = atoi(e);
+    if (const char *e = getenv("TNB_DA_STAGES")) k.da_stages = atoi(e);
   });
   return k;
 }
@@ -419,6 +421,7 @@ static int mps_backward_t(const tnb_problem *p, const MpsPlan &P, long long B, c
       Da.gimg = Tc.gimg;
       Da.img_bond_bytes = Tc.img_bond_bytes;
       Da.nstage = (int)((232448 - 2048 - 1024) / kDaStage);
+      if (tc_knobs().da_stages >= 2 && tc_knobs().da_stages < Da.nstage) Da.nstage = tc_knobs().da_stages;
       Da.tmem_cols = 32;
       while (Da.tmem_cols < 2 * p->chi) Da.tmem_cols <<= 1;
       const long long maxsp = (B + 2047) / 2048;

@@ -234,6 +234,16 @@ constexpr uint32_t kDaU = (kDaKC / 8) * kDaUBlock;  // 16 KB
 constexpr uint32_t kDaBMax = 256u * 4u * kDaKC;   // V region: a raw image chunk of kDaKC samples
 constexpr uint32_t kDaStage = kDaU + kDaBMax;     // 64 KB (32 samples): 3 stages
 
+#ifdef TNB_TC_TRACE
+#define TNB_DA_TRACE(ch_, ev)                                                                              \
+  do {                                                                                                     \
+    if (blockIdx.x == 0 && blockIdx.y == 1 && (ch_) >= 200 && (ch_) < 232 && (threadIdx.x & 31) == 0)      \
+      g_tc_trace[((ch_)-200) * 64 + 32 + (ev)] = clock64();                                                \
+  } while (0)
+#else
+#define TNB_DA_TRACE(ch_, ev) do { } while (0)
+#endif
+
 // CPG: upper bound of the copies per CTA (compile time, so that the producer loop is straight-line code)
 template <int CPG>
 __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
@@ -304,6 +314,7 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
       for (int ch = 0; ch < nchunks; ++ch) {
         ptx::mbar_wait(&ready[stage], phase);
         ptx::tc_fence_after();
+        TNB_DA_TRACE(ch, 0);
         const uint32_t st = ptx::smem_u32(stages + (size_t)stage * kDaStage);
         for (int t = 0; t < ntile; ++t) {
 #pragma unroll
@@ -319,6 +330,7 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
           }
         }
         ptx::mma_commit(&empty[stage]);
+        TNB_DA_TRACE(ch, 1);
         if (++stage == A.nstage) { stage = 0; phase ^= 1; }
       }
       ptx::mma_commit(done);
@@ -329,8 +341,18 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      const int pf = A.nstage + 2;  // L2 prefetch distance (chunks): the stage ring alone does not cover the HBM latency
+      for (int ch = 0; ch < pf && ch < nchunks; ++ch) {
+        ptx::bulk_prefetch_l2(Uimg + (size_t)ch * b_bytes, b_bytes);
+        ptx::bulk_prefetch_l2(Vimg + (size_t)ch * b_bytes, b_bytes);
+      }
       for (int ch = 0; ch < nchunks; ++ch) {
+        if (ch + pf < nchunks) {
+          ptx::bulk_prefetch_l2(Uimg + (size_t)(ch + pf) * b_bytes, b_bytes);
+          ptx::bulk_prefetch_l2(Vimg + (size_t)(ch + pf) * b_bytes, b_bytes);
+        }
         ptx::mbar_wait(&empty[stage], phase ^ 1);
+        TNB_DA_TRACE(ch, 2);
         uint8_t *st = stages + (size_t)stage * kDaStage;
         const uint32_t u_bytes = (uint32_t)noct * 128;  // the CTA's rows of one (sample block, plane)
         ptx::mbar_expect_tx(&loaded[stage], 2 * (kDaKC / 8) * u_bytes + b_bytes);
@@ -371,6 +393,7 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
       for (int s = 0; s < CPG; ++s) wc[s] = ptx::f2_pack(wn[s] * qs, wn[s] * qs);
       if (ch + 1 < nchunks) load_w(ch + 1);
       ptx::mbar_wait(&loaded[stage], phase);
+      if (warp == 0) TNB_DA_TRACE(ch, 3);
       uint8_t *st = stages + (size_t)stage * kDaStage + lane_off;
       for (int o = o0; o < noct; o += kOctPerWarp * (kDaProducers / 32)) {
         const uint4 hv = *reinterpret_cast<const uint4 *>(st + o * 128);
@@ -408,6 +431,7 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
       ptx::fence_proxy_async();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&ready[stage]);
+      if (warp == 0) TNB_DA_TRACE(ch, 4);
       if (++stage == A.nstage) { stage = 0; phase ^= 1; }
     }
     // ===== epilogue (warps 0-3): TMEM -> packed gradient =====

@@ -74,6 +74,11 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 // ... have completed (writes performed)
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 
+// pull a contiguous global range towards L2 (no destination; a hint)
+__device__ __forceinline__ void bulk_prefetch_l2(const void *gmem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
+
 // generic-proxy smem writes -> visible to the async proxy (tensor core / TMA)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 

@@ -40,6 +40,19 @@ if __name__ == "__main__":
     n = 64 * 32
     buf = (C.c_longlong * n)()
     assert lib.tnb_debug_trace_read(buf, n) == 0
+    if "--da" in sys.argv:
+        # weight-gradient GEMM, CTA (0, site 1), chunks 200..231: mma = ready seen / MMAs issued; copy = stage free;
+        # prod = loaded seen / transformed (warp 0).  Cycles relative to the previous chunk's "ready seen".
+        prev = None
+        for st in range(32):
+            e = buf[st * 64 + 32:st * 64 + 40]
+            if e[0] == 0:
+                continue
+            if prev:
+                print(f"chunk {200 + st}: period={e[0] - prev} issue={e[1] - e[0]} stage_free={e[2] - e[0]} "
+                      f"loaded={e[3] - e[0]} transformed={e[4] - e[0]}")
+            prev = e[0]
+        sys.exit(0)
     prev_pub = None
     for st in range(32):
         row = buf[st * 64:(st + 1) * 64]
