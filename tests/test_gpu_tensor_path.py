@@ -73,3 +73,24 @@ def test_tensor_path_two_tile_rounds_and_remainder():
     prob = O.Problem("mps", O.EmbSpec("trig"), "softmax_xent")
     model = _tensor_model(T.TensorNetwork, arrays)
     _check(model, prob, _heads()["softmax_xent"], x, arrays, t, torch.float32, precision=1)
+
+
+@pytest.mark.parametrize("precision", [0, 1], ids=["simt", "tensor"])
+def test_micro_batched_step_equals_one_piece(precision):
+    """The host splits a step into micro-batches when the environment stash would not fit (cfg 5 at full size); the
+    gradient accumulates across tnb_backward calls (accumulate=1) and the loss sum across tnb_forward calls."""
+    import tn4ml_b200 as T
+    arrays = O.make_mps_arrays(9, 64, 2, class_site=4, C=3, std=0.05, seed=3)
+    x = O.make_inputs(300, 9, seed=5)
+    t = O.make_labels(300, 3)
+    model = _tensor_model(T.TensorNetwork, arrays)
+    model.precision = precision
+    model._engine_cache = {}
+    eng, _ = model._engine(T.TrigonometricEmbedding(), _heads()["softmax_xent"], True, torch.float32)
+    ls1, g1 = eng.value_and_grad(model._packed, x.float(), t.float())
+    ls1, g1 = float(ls1.item()), g1.clone()
+    eng.max_microbatch = 77                      # 300 = 77 + 77 + 77 + 69: ragged tiles in every piece
+    eng._ws.clear()
+    ls2, g2 = eng.value_and_grad(model._packed, x.float(), t.float())
+    assert abs(float(ls2.item()) - ls1) <= 1e-5 * abs(ls1)
+    assert float((g2 - g1).abs().max()) <= 2e-5 * float(g1.abs().max())
