@@ -112,15 +112,15 @@ struct MpsPlan {
   size_t off_Wn, off_Wt, off_F, off_G, off_exps, off_esum, off_y, off_dy, total;
   size_t smem_sweep, smem_class;
   // tensor-core sweep (f32, TNB_PREC_TENSOR)
-  int tc, tc_N, tc_NH, tc_NMMA, tc_nstage, tc_cols, tc_tiles;
+  int tc, tc_N, tc_NH, tc_NMMA, tc_nstage, tc_cols, tc_tiles, tc_cg;
   uint32_t tc_stage_bytes;
   size_t tc_site_img, off_img_n, off_img_t, off_kW, off_cs, off_wq, off_qmax, off_wqc, off_fimg, off_gimg, tc_smem, img_bond_bytes;
 };
 
 // Measurement knobs of the tensor path (environment, read once): TNB_TC_NH forces a legal column-chunk count,
 // TNB_TC_TILES=1 forces one sample tile per CTA, TNB_TC_PACE_NS sets the image writer's pause between pieces,
-// TNB_DA_STAGES lowers the pipeline depth of the weight-gradient GEMM.
-struct TcKnobs { int nh = 0, tiles = 0, pace_ns = -1, da_stages = 0; };
+// TNB_DA_STAGES lowers the pipeline depth of the weight-gradient GEMM, TNB_TC_CG=2 turns on the (experimental) CTA-pair chain kernel.
+struct TcKnobs { int nh = 0, tiles = 0, pace_ns = -1, da_stages = 0, cg = 0; };
 static const TcKnobs &tc_knobs() {
   static TcKnobs k;
   static std::once_flag once;
@@ -129,6 +129,7 @@ static const TcKnobs &tc_knobs() {
     if (const char *e = getenv("TNB_TC_TILES")) k.tiles = atoi(e);
     if (const char *e = getenv("TNB_TC_PACE_NS")) k.pace_ns = atoi(e);
     if (const char *e = getenv("TNB_DA_STAGES")) k.da_stages = atoi(e);
+    if (const char *e = getenv("TNB_TC_CG")) k.cg = atoi(e);
   });
   return k;
 }
@@ -193,12 +194,16 @@ static MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
     P.tc_NH = tc_pick_nh(p);
     P.tc_NMMA = P.tc_N / P.tc_NH;
     P.tc_stage_bytes = 64u * P.tc_NMMA;  // one K-slab (16 rows) of one column chunk, hi and lo planes
-    P.tc_site_img = (size_t)P.tc_NH * (p->chi / 16) * P.tc_stage_bytes;
+    P.tc_site_img = (size_t)P.tc_NH * (p->chi / 16) * P.tc_stage_bytes;  // (stage_bytes: still the whole stage here)
     const size_t a_bytes = (size_t)2 * kTcRows * p->chi * 2;
     // two sample tiles per CTA when one column chunk covers the step (nothing else hides the epilogue); TNB_TC_TILES=1 forces one
     // (pays when the step's MMA time is comparable to its exposed tail: N = 256; measured slower at N <= 128)
     P.tc_tiles = (P.tc_NH == 1 && P.tc_N == 256) ? 2 : 1;
     if (tc_knobs().tiles == 1) P.tc_tiles = 1;
+    // CTA pair (cta_group::2), opt-in: the wide-bond case (chi > 128, d = 2), where shared-memory bandwidth caps the MMA
+    // rate.  Parity-green but measured slower than the one-CTA kernel so far, hence not the default.
+    P.tc_cg = (p->chi > 128 && p->d == 2 && P.tc_tiles == 1 && tc_knobs().cg == 2) ? 2 : 1;
+    P.tc_stage_bytes /= (uint32_t)P.tc_cg;  // one CTA's half of a stage
     P.tc_cols = 32;
     while (P.tc_cols < P.tc_tiles * P.tc_N) P.tc_cols <<= 1;
     const size_t fixed = (size_t)P.tc_tiles * 4096 /* row exchange */ + 1024 /* tables, barriers */;
@@ -209,7 +214,8 @@ static MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
   }
   if (P.tc) {
     // the tensor path keeps its environments as fp16 hi/lo bond images instead of F / G
-    P.img_bond_bytes = (size_t)((B + kTcRows - 1) / kTcRows * kTcRows) * p->chi * 4;  // whole 128-sample tiles
+    const size_t span = (size_t)kTcRows * P.tc_cg;  // a CTA pair always writes both tiles
+    P.img_bond_bytes = (size_t)((B + span - 1) / span * span) * p->chi * 4;  // whole 128-sample tiles
     P.off_fimg = take((need_grad ? (size_t)p->L + 1 : 1) * P.img_bond_bytes);
     P.off_img_n = take(P.tc_site_img * P.nslab);
     P.off_img_t = take(P.tc_site_img * P.nslab);
@@ -254,6 +260,8 @@ static void fill_tc_args(const MpsPlan &P, void *ws, const MpsArgs<float> &M, Tc
   T.img_t = (const uint8_t *)(w + P.off_img_t);
   T.kW = (const int *)(w + P.off_kW);
   T.tile0 = 0;
+  T.cg = P.tc_cg;
+  { const char *e = getenv("TNB_TC_DBG"); T.dbg = e ? atoi(e) : 0; }
   T.colsum = (const float *)(w + P.off_cs);
   T.pace_ns = tc_knobs().pace_ns >= 0 ? tc_knobs().pace_ns : P.tc_N * 2 / 5;
   T.wq = (float *)(w + P.off_wq);
@@ -268,22 +276,39 @@ static void fill_tc_args(const MpsPlan &P, void *ws, const MpsArgs<float> &M, Tc
   T.stage_bytes = P.tc_stage_bytes; T.site_img_bytes = P.tc_site_img;
 }
 
-template <int D, int SLOTS, int TILES> static cudaError_t tc_set_attr() {
+template <int D, int SLOTS, int TILES, int CG> static cudaError_t tc_set_attr() {
   static std::once_flag once;
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [] {
-    err = cudaFuncSetAttribute(tc_chain_kernel<D, SLOTS, TILES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    err = cudaFuncSetAttribute(tc_chain_kernel<D, SLOTS, TILES, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   });
   return err;
 }
 
-template <int D, int SLOTS, int TILES>
+template <int D, int SLOTS, int TILES, int CG = 1>
 static cudaError_t tc_launch_one(long long ntiles, long long tile0, size_t smem, TcArgs T, int adjoint, cudaStream_t st) {
-  cudaError_t e = tc_set_attr<D, SLOTS, TILES>();
+  cudaError_t e = tc_set_attr<D, SLOTS, TILES, CG>();
+  if (e != cudaSuccess || ntiles <= 0) return e;
   T.tile0 = tile0 * kTcRows;
-  dim3 grid((unsigned)(ntiles / TILES), adjoint ? 2 : 1);
-  if (e == cudaSuccess && ntiles > 0) tc_chain_kernel<D, SLOTS, TILES><<<grid, kTcThreads, smem, st>>>(T, adjoint);
-  return e;
+  if (CG == 1) {
+    dim3 grid((unsigned)(ntiles / TILES), adjoint ? 2 : 1);
+    tc_chain_kernel<D, SLOTS, TILES, CG><<<grid, kTcThreads, smem, st>>>(T, adjoint);
+    return cudaSuccess;
+  }
+  // CTA pair: clusters of two CTAs along x (consecutive sample tiles); an odd tile count gets an all-padding tile
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((ntiles + 1) / 2 * 2), adjoint ? 2 : 1);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, tc_chain_kernel<D, SLOTS, TILES, CG>, T, adjoint);
 }
 
 // launch the tcgen05 sweep (forward environments or adjoint chains)
@@ -306,9 +331,14 @@ static int tc_launch_sweep(const tnb_problem *p, const MpsPlan &P, const TcArgs 
     if (e == cudaSuccess && ntiles > npair) e = tc_launch_one<DD, SS, 1>(ntiles - npair, npair, P.tc_smem, T, adjoint, st); \
   } while (0)
 #define TNB_TC_GO1(DD, SS) e = tc_launch_one<DD, SS, 1>(ntiles, 0, P.tc_smem, T, adjoint, st)
+#define TNB_TC_PAIR(DD, SS) e = tc_launch_one<DD, SS, 1, 2>(ntiles, 0, P.tc_smem, T, adjoint, st)
   prof_begin(st);
   switch (p->d) {
-    case 2: if (wide) TNB_TC_GO1(2, 4); else TNB_TC_GO(2, 2); break;
+    case 2:
+      if (wide && P.tc_cg == 2) TNB_TC_PAIR(2, 4);
+      else if (wide) TNB_TC_GO1(2, 4);
+      else TNB_TC_GO(2, 2);
+      break;
     case 3: if (wide) TNB_TC_GO1(3, 4); else TNB_TC_GO1(3, 2); break;
     case 4: TNB_TC_GO(4, 2); break;
     case 6: TNB_TC_GO1(6, 2); break;
@@ -317,6 +347,7 @@ static int tc_launch_sweep(const tnb_problem *p, const MpsPlan &P, const TcArgs 
   }
 #undef TNB_TC_GO
 #undef TNB_TC_GO1
+#undef TNB_TC_PAIR
   if (e != cudaSuccess) return fail("cudaFuncSetAttribute(tc_chain): %s", cudaGetErrorString(e));
   TNB_LAUNCH_CHECK(adjoint ? "tc_chain_kernel(adj)" : "tc_chain_kernel(fwd)");
   return 0;
@@ -369,7 +400,7 @@ static int mps_forward_t(const tnb_problem *p, const MpsPlan &P, long long B, co
       if (ib > 148 * 32) ib = 148 * 32;
       prof_begin(st);
       tc_image_kernel<<<ib, 256, 0, st>>>((const float *)params, Tc.kW, (uint8_t *)Tc.img_n, (uint8_t *)Tc.img_t, p->L,
-                                          p->chi, p->d, p->n_out, p->out_site, P.tc_NH);
+                                          p->chi, p->d, p->n_out, p->out_site, P.tc_NH, P.tc_cg);
       TNB_LAUNCH_CHECK("tc_image_kernel");
       return tc_launch_sweep(p, P, Tc, B, 0, st);
     }

@@ -42,6 +42,8 @@ struct TcArgs {
   const int *kW;         // per-slab weight pre-scale exponent
   const float *colsum;   // [2 directions][slab]: max_n sum_{k,s} |W[k,s,n]| * 2^kW  (bound of one chain step, see chain kernel)
   int pace_ns;           // image writer: pause between 4 KB pieces
+  int cg;                // CTAs per MMA: 1, or 2 (CTA pair; stage_bytes is then one CTA's half of a stage)
+  int dbg;               // measurement switches (trace builds only; TNB_TC_DBG)
   long long tile0;       // first sample of this launch (a sweep may be split into a two-tile and a one-tile launch)
   float *wq;             // adjoint: phi_s[b] * 2^q[b] per (site, s, b): per-sample weight of the dA GEMM
   int *qmax;             // adjoint: max_b q[site][b]
@@ -127,8 +129,9 @@ __global__ void tc_colsum_kernel(const float *__restrict__ params, const int *__
 
 // one thread per (slab, n', k-octet): 8 weights -> 16 B of hi and 16 B of lo, both directions.
 // Stage (h, ks) of a slab holds the K-slab ks of column chunk h: columns n'' = s*chi_h + (n - h*chi_h).
+// cg = 2 (CTA pair): a stage is [rank][plane hi|lo][NMMA / 2 columns], rank r holding the columns the r-th CTA supplies.
 __global__ void tc_image_kernel(const float *__restrict__ params, const int *__restrict__ kW, uint8_t *__restrict__ img_n,
-                                uint8_t *__restrict__ img_t, int L, int chi, int D, int C, int c, int NH) {
+                                uint8_t *__restrict__ img_t, int L, int chi, int D, int C, int c, int NH, int cg) {
   const int nslab = L - 1 + C;
   const int N = D * chi, KO = chi / 8, KS = chi / 16;
   const int chi_h = chi / NH, NMMA = N / NH;
@@ -150,8 +153,10 @@ __global__ void tc_image_kernel(const float *__restrict__ params, const int *__r
     const size_t site_off = (size_t)site * chi * chi * D + (site > c ? (size_t)chi * chi * D * (C - 1) : 0);
     const float sc = ldexpf(1.f, kW[slab]);
     const int ks = ko / 2, kc = ko & 1;
-    const size_t off = (size_t)slab * site_img_bytes + ((size_t)h * KS + ks) * stage_bytes + (size_t)(npp / 8) * 256 +
-                       kc * 128 + (npp % 8) * 16;
+    const int ncol = NMMA / cg;  // columns per CTA
+    const int rk = npp / ncol, nq = npp - rk * ncol;
+    const size_t off = (size_t)slab * site_img_bytes + ((size_t)h * KS + ks) * stage_bytes + (size_t)rk * ncol * 64 +
+                       (size_t)(nq / 8) * 256 + kc * 128 + (nq % 8) * 16;
 #pragma unroll
     for (int dir = 0; dir < 2; ++dir) {
       __half hi[8], lo[8];
@@ -165,7 +170,7 @@ __global__ void tc_image_kernel(const float *__restrict__ params, const int *__r
       }
       uint8_t *base = (dir == 0 ? img_n : img_t) + off;
       *reinterpret_cast<uint4 *>(base) = *reinterpret_cast<const uint4 *>(hi);
-      *reinterpret_cast<uint4 *>(base + (size_t)NMMA * 32) = *reinterpret_cast<const uint4 *>(lo);
+      *reinterpret_cast<uint4 *>(base + (size_t)ncol * 32) = *reinterpret_cast<const uint4 *>(lo);
     }
   }
 }
@@ -305,7 +310,8 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
   const int qmax = A.only_site >= 0 ? A.qmax[0] : A.qmax[site];
 
   if (warp == kMmaWarp) {
-    if (lane == 0) {
+    // the whole warp waits; the instructions go out under elect.sync (no per-instruction ELECT / BRA.U.ANY loop)
+    {
       const uint32_t idesc = ptx::idesc_f16_f32(128, chi) | (1u << 15) | (1u << 16);  // A and B MN-major
       // V tile = kDaKC samples of a bond image: sample-block (K) stride chi*32, lo plane at chi*16
       const uint32_t vlbo = (uint32_t)chi * 32, vlo = (uint32_t)chi * 16;
@@ -315,25 +321,28 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
         ptx::mbar_wait(&ready[stage], phase);
         ptx::tc_fence_after();
         TNB_DA_TRACE(ch, 0);
-        const uint32_t st = ptx::smem_u32(stages + (size_t)stage * kDaStage);
-        for (int t = 0; t < ntile; ++t) {
+        if (ptx::elect_one()) {
+          const uint32_t st = ptx::smem_u32(stages + (size_t)stage * kDaStage);
+          for (int t = 0; t < ntile; ++t) {
 #pragma unroll
-          for (int ks = 0; ks < kDaKC / 16; ++ks) {
-            const uint64_t da_hi = ptx::smem_desc_kmajor(st + t * 16 * 128 + ks * 2 * kDaUBlock, kDaUBlock, 128);
-            const uint64_t da_lo = ptx::smem_desc_kmajor(st + kDaUPlane + t * 16 * 128 + ks * 2 * kDaUBlock, kDaUBlock, 128);
-            const uint64_t db_hi = ptx::smem_desc_kmajor(st + kDaU + ks * 2 * vlbo, vlbo, 128);
-            const uint64_t db_lo = ptx::smem_desc_kmajor(st + kDaU + vlo + ks * 2 * vlbo, vlbo, 128);
-            const uint32_t d = tmem_base + (uint32_t)t * chi;
-            ptx::mma_f16(d, da_hi, db_hi, idesc, (ch > 0 || ks > 0) ? 1u : 0u);
-            ptx::mma_f16(d, da_lo, db_hi, idesc, 1u);
-            ptx::mma_f16(d, da_hi, db_lo, idesc, 1u);
+            for (int ks = 0; ks < kDaKC / 16; ++ks) {
+              const uint64_t da_hi = ptx::smem_desc_kmajor(st + t * 16 * 128 + ks * 2 * kDaUBlock, kDaUBlock, 128);
+              const uint64_t da_lo = ptx::smem_desc_kmajor(st + kDaUPlane + t * 16 * 128 + ks * 2 * kDaUBlock, kDaUBlock, 128);
+              const uint64_t db_hi = ptx::smem_desc_kmajor(st + kDaU + ks * 2 * vlbo, vlbo, 128);
+              const uint64_t db_lo = ptx::smem_desc_kmajor(st + kDaU + vlo + ks * 2 * vlbo, vlbo, 128);
+              const uint32_t d = tmem_base + (uint32_t)t * chi;
+              ptx::mma_f16(d, da_hi, db_hi, idesc, (ch > 0 || ks > 0) ? 1u : 0u);
+              ptx::mma_f16(d, da_lo, db_hi, idesc, 1u);
+              ptx::mma_f16(d, da_hi, db_lo, idesc, 1u);
+            }
           }
+          ptx::mma_commit(&empty[stage]);
         }
-        ptx::mma_commit(&empty[stage]);
+        __syncwarp();
         TNB_DA_TRACE(ch, 1);
         if (++stage == A.nstage) { stage = 0; phase ^= 1; }
       }
-      ptx::mma_commit(done);
+      if (ptx::elect_one()) ptx::mma_commit(done);
     }
   } else if (warp == kCopyWarp) {
     // ===== both operands: bulk async copies of one image chunk per stage (U: per sample block and plane, into the

@@ -60,8 +60,16 @@ __device__ long long g_tc_trace[64 * 32];
     if (blockIdx.x == 0 && blockIdx.y == 0 && (step_) >= 20 && (step_) < 52 && (threadIdx.x & 31) == 0 && (who) < 4) \
       g_tc_trace[((step_)-20) * 64 + (who)*16 + (ev)] = clock64();                                              \
   } while (0)
+#define TNB_TRACE_SET(who, step_, ev, val)                                                                      \
+  do {                                                                                                         \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && (step_) >= 20 && (step_) < 52 && (threadIdx.x & 31) == 0 && (who) < 4) \
+      g_tc_trace[((step_)-20) * 64 + (who)*16 + (ev)] = (val);                                                  \
+  } while (0)
+#define TNB_CLOCK() clock64()
 #else
 #define TNB_TRACE(who, step_, ev) do { } while (0)
+#define TNB_TRACE_SET(who, step_, ev, val) do { } while (0)
+#define TNB_CLOCK() 0ll
 #endif
 
 // acc columns -> o[j] = sum_s ph[s] * acc[col + s*cstride + j], j < 16   (one 16-column group).
@@ -144,8 +152,13 @@ __device__ __forceinline__ float tc_combine_pack16(uint32_t col, uint32_t cstrid
 // TILES: sample tiles of 128 rows per CTA.  With one column chunk (chi <= 128) nothing hides a step's epilogue, so the
 // CTA carries two independent tiles (own operand, own TMEM columns, own barriers): the MMAs of one tile run under the
 // epilogue of the other.  At chi = 256 one tile fills TMEM and shared memory, and the column chunks do the hiding.
-template <int D, int SLOTS, int TILES>
+// CG: 1 = every CTA multiplies its own tile; 2 = CTA pair (cluster of two CTAs on the two SMs of a TPC): the leader issues
+// `tcgen05.mma.cta_group::2` for both tiles (M = 256), each CTA holds -- and loads -- only its half of the B columns of a
+// weight stage, which takes the operand fetch of an MMA from 96 to 64 B/clk per SM (shared-memory bandwidth is what caps
+// the MMA rate of the one-CTA kernel).  Epilogue, operand, TMEM accumulator and stash writer stay per CTA.
+template <int D, int SLOTS, int TILES, int CG>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int adjoint) {
+  static_assert(CG == 1 || TILES == 1, "the CTA pair carries one tile per CTA");
   extern __shared__ __align__(1024) uint8_t smem[];
   const MpsArgs<float> &M = A.M;
   const int chi = M.chip, L = M.L, c = M.c, C = M.C;
@@ -154,6 +167,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
   const long long b0 = A.tile0 + (long long)blockIdx.x * (kTcRows * TILES);
   const int nR = L - 1 - c, nL = c;
   const int NH = A.NH, chi_h = chi / NH;
+  const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;  // 0: leader of the pair (issues the MMAs)
 
   // ---- the step program (identical in every warp role) ----
   int nseed, nchain, total;
@@ -211,7 +225,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
   uint64_t *acc_full = bars + 2 * A.nstage;        // [TILES][kTcMaxNH]
   uint64_t *a_ready = acc_full + TILES * kTcMaxNH;  // [TILES]
   uint64_t *img_done = a_ready + TILES, *img_half = img_done + TILES, *a_rel = img_half + TILES;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_rel + TILES);
+  uint64_t *a_mma = a_rel + TILES;  // CTA pair: both CTAs' operands are published (waited on by the leader's MMA warp)
+  uint64_t *pfull = a_mma + 1;      // CTA pair: [nstage] the follower's half of a weight stage has landed (relayed)
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(pfull + A.nstage);
 
   if (tid == 0) {
     for (int i = 0; i < A.nstage; ++i) {
@@ -225,6 +241,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       ptx::mbar_init(&img_half[t], 1);
       ptx::mbar_init(&a_rel[t], 1);
     }
+    ptx::mbar_init(a_mma, kTcEpiWarps * CG);
+    for (int i = 0; i < A.nstage; ++i) ptx::mbar_init(&pfull[i], 1);
     ptx::fence_mbar_init();
   }
   if (tid < 16) {
@@ -234,11 +252,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
     gcol[tid] = (uint32_t)(h * A.NMMA + (n0 - h * chi_h));
   }
   if (warp == kTcMmaWarp) {
-    ptx::tmem_alloc(tmem_slot, (uint32_t)A.tmem_cols);
-    ptx::tmem_relinquish();
+    if (CG == 2) {
+      ptx::tmem_alloc2(tmem_slot, (uint32_t)A.tmem_cols);
+      ptx::tmem_relinquish2();
+    } else {
+      ptx::tmem_alloc(tmem_slot, (uint32_t)A.tmem_cols);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CG == 2) ptx::cluster_sync();  // the peer's barriers are initialised before anything arrives on them remotely
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tile_cols = (uint32_t)A.tmem_cols / TILES;  // TMEM columns of one tile's accumulator
@@ -256,7 +280,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       const unsigned pace = (unsigned)(A.pace_ns > 0 ? (krel > 0 ? A.pace_ns / 2 : A.pace_ns) : 0);
       for (int g = 0; g <= total; ++g) {
         const int bond = g > 0 ? step_out_bond(g - 1) : -1;
-        const bool on = bond >= 0 && base;
+        const bool on = bond >= 0 && base && !(A.dbg & 2);
 #pragma unroll
         for (int t = 0; t < TILES; ++t) {
           ptx::mbar_wait(&a_ready[t], g & 1);
@@ -303,48 +327,92 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
         for (int t = 0; t < TILES; ++t) {
           for (int hk = 0; hk < per_step; ++hk) {
             ptx::mbar_wait(&empty[stage], phase ^ 1);
-            ptx::mbar_expect_tx(&full[stage], A.stage_bytes);
-            ptx::bulk_g2s(stages + (size_t)stage * A.stage_bytes, img + (size_t)hk * A.stage_bytes, A.stage_bytes,
-                          &full[stage]);
+            const uint32_t nbytes = (A.dbg & 16) ? 1024u : A.stage_bytes;  // (timing experiment: short loads, wrong results)
+            ptx::mbar_expect_tx(&full[stage], nbytes);
+            // (CTA pair: the stage image is [rank][plane][columns / 2]; each CTA fetches its own half)
+            ptx::bulk_g2s(stages + (size_t)stage * A.stage_bytes, img + ((size_t)hk * CG + rank) * A.stage_bytes,
+                          nbytes, &full[stage]);
             if (++stage == A.nstage) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == kTcMmaWarp) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc = ptx::idesc_f16_f32(kTcRows, A.NMMA);
-      const uint32_t sbo_a = (uint32_t)chi * 32;
-      const uint32_t lo_plane = (uint32_t)A.NMMA * 32;
+    // ===== MMA issuer (CTA pair: the leader issues for both CTAs; the follower relays its `full` barriers) =====
+    if (lane == 0 && rank != 0) {
       int stage = 0;
       uint32_t phase = 0;
+      for (int step = 0; step < total; ++step)
+        for (int hk = 0; hk < NH * KS; ++hk) {
+          ptx::mbar_wait(&full[stage], phase);
+          ptx::mbar_arrive_cluster(&pfull[stage], 0);
+          if (++stage == A.nstage) { stage = 0; phase ^= 1; }
+        }
+    } else if (CG == 1 || rank == 0) {
+      // The whole warp runs the loop and waits; the instructions are issued under `elect.sync` (with `lane == 0` the
+      // compiler wraps every tcgen05 instruction in an ELECT / BRA.U.ANY loop, which costs the issuer more than the
+      // waits do).
+      const uint32_t idesc = ptx::idesc_f16_f32(kTcRows * CG, A.NMMA);
+      const uint32_t sbo_a = (uint32_t)chi * 32;
+      const uint32_t lo_plane = (uint32_t)(A.NMMA / CG) * 32;  // B columns held by this CTA: NMMA / CG
+      int stage = 0;
+      uint32_t phase = 0;
+#ifdef TNB_TC_TRACE
+      long long tr_full = 0, tr_pfull = 0, tr_issue = 0;
+#endif
       for (int step = 0; step < total; ++step) {
         const bool accum_step = adjoint && step > 0 && step < nseed;  // seed steps accumulate over k
 #pragma unroll
         for (int t = 0; t < TILES; ++t) {
           const uint32_t a_hi_s = ptx::smem_u32(a_op + (size_t)t * a_bytes), a_lo_s = a_hi_s + (uint32_t)chi * 16;
-          ptx::mbar_wait(&a_ready[t], step & 1);
+          ptx::mbar_wait(CG == 2 ? a_mma : &a_ready[t], step & 1);
           ptx::tc_fence_after();
           if (t == 0) TNB_TRACE(3, step, 0);
           for (int h = 0; h < NH; ++h) {
             const uint32_t d = tmem_base + (uint32_t)t * tile_cols + (uint32_t)h * A.NMMA;
             for (int ks = 0; ks < KS; ++ks) {
+              const long long c0 = TNB_CLOCK();
               ptx::mbar_wait(&full[stage], phase);
+              const long long c1 = TNB_CLOCK();
+              if (CG == 2 && !(A.dbg & 4)) ptx::mbar_wait(&pfull[stage], phase);
+              const long long c2 = TNB_CLOCK();
               ptx::tc_fence_after();
-              const uint64_t da_hi = ptx::smem_desc_kmajor(a_hi_s + ks * 256, 128, sbo_a);
-              const uint64_t da_lo = ptx::smem_desc_kmajor(a_lo_s + ks * 256, 128, sbo_a);
-              const uint32_t st = ptx::smem_u32(stages + (size_t)stage * A.stage_bytes);
-              const uint64_t db_hi = ptx::smem_desc_kmajor(st, 128, 256);
-              const uint64_t db_lo = ptx::smem_desc_kmajor(st + lo_plane, 128, 256);
-              ptx::mma_f16(d, da_hi, db_hi, idesc, (ks > 0 || accum_step) ? 1u : 0u);
-              ptx::mma_f16(d, da_lo, db_hi, idesc, 1u);
-              ptx::mma_f16(d, da_hi, db_lo, idesc, 1u);
-              ptx::mma_commit(&empty[stage]);
-              if (h == NH - 1 && ks == krel - 1) ptx::mma_commit(&a_rel[t]);
+              if (ptx::elect_one()) {
+                const uint64_t da_hi = ptx::smem_desc_kmajor(a_hi_s + ks * 256, 128, sbo_a);
+                const uint64_t da_lo = ptx::smem_desc_kmajor(a_lo_s + ks * 256, 128, sbo_a);
+                const uint32_t st = ptx::smem_u32(stages + (size_t)stage * A.stage_bytes);
+                const uint64_t db_hi = ptx::smem_desc_kmajor(st, 128, 256);
+                const uint64_t db_lo = ptx::smem_desc_kmajor(st + lo_plane, 128, 256);
+                if (CG == 2) {
+                  ptx::mma_f16_pair(d, da_hi, db_hi, idesc, (ks > 0 || accum_step) ? 1u : 0u);
+                  ptx::mma_f16_pair(d, da_lo, db_hi, idesc, 1u);
+                  ptx::mma_f16_pair(d, da_hi, db_lo, idesc, 1u);
+                  ptx::mma_commit_pair(&empty[stage]);
+                  if (h == NH - 1 && ks == krel - 1) ptx::mma_commit_pair(&a_rel[t]);
+                  if (ks == KS - 1) ptx::mma_commit_pair(&acc_full[t * kTcMaxNH + h]);
+                } else {
+                  ptx::mma_f16(d, da_hi, db_hi, idesc, (ks > 0 || accum_step) ? 1u : 0u);
+                  ptx::mma_f16(d, da_lo, db_hi, idesc, 1u);
+                  ptx::mma_f16(d, da_hi, db_lo, idesc, 1u);
+                  ptx::mma_commit(&empty[stage]);
+                  if (h == NH - 1 && ks == krel - 1) ptx::mma_commit(&a_rel[t]);
+                  if (ks == KS - 1) ptx::mma_commit(&acc_full[t * kTcMaxNH + h]);
+                }
+              }
+              __syncwarp();
               if (++stage == A.nstage) { stage = 0; phase ^= 1; }
+#ifdef TNB_TC_TRACE
+              if (ks == 0) tr_full = tr_pfull = tr_issue = 0;
+              tr_full += c1 - c0; tr_pfull += c2 - c1; tr_issue += TNB_CLOCK() - c2;
+#endif
             }
-            ptx::mma_commit(&acc_full[t * kTcMaxNH + h]);
+#ifdef TNB_TC_TRACE
+            if (t == 0 && h < 2) {  // per column chunk: cycles waiting for the own stage / the peer's half / issuing
+              TNB_TRACE_SET(3, step, 4 + 3 * h, tr_full);
+              TNB_TRACE_SET(3, step, 5 + 3 * h, tr_pfull);
+              TNB_TRACE_SET(3, step, 6 + 3 * h, tr_issue);
+            }
+#endif
             if (t == 0) TNB_TRACE(3, step, 1 + h);
           }
         }
@@ -456,7 +524,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       ptx::tc_fence_before();
       ptx::fence_proxy_async();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&a_ready[t]);
+      if (lane == 0) {
+        ptx::mbar_arrive(&a_ready[t]);                       // this CTA's image writer (and, one CTA, its MMA warp)
+        if (CG == 2) ptx::mbar_arrive_cluster(a_mma, 0);     // the pair's MMA issuer
+      }
     };
     // combine one float per thread across the 4 threads of a row (through smem, fixed order)
     auto row_exchange = [&](int t, float v) -> const float * {
@@ -788,9 +859,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CG == 2) ptx::cluster_sync();  // both CTAs are done with each other's barriers and TMEM
+  else __syncthreads();
   ptx::tc_fence_after();
-  if (warp == kTcMmaWarp) ptx::tmem_dealloc(tmem_base, (uint32_t)A.tmem_cols);
+  if (warp == kTcMmaWarp) {
+    if (CG == 2) ptx::tmem_dealloc2(tmem_base, (uint32_t)A.tmem_cols);
+    else ptx::tmem_dealloc(tmem_base, (uint32_t)A.tmem_cols);
+  }
 }
 
 }  // namespace tnb

@@ -62,7 +62,10 @@ if __name__ == "__main__":
             continue
         def rel(v):
             return "-" if v == 0 else str(v - t0)
-        line = f"step {20 + st:3d} mma: aready=0 commits=" + ",".join(rel(v) for v in mma[1:5])
+        line = f"step {20 + st:3d} mma: aready=0 commits=" + ",".join(rel(v) for v in mma[1:4])
+        if "--stages" in sys.argv:  # per column chunk: cycles the issuer waited for its stage / the peer's half / spent issuing
+            line += " chunk[wait_full,wait_pfull,issue]=" + " ".join(
+                "(" + ",".join(str(mma[4 + 3 * k + j]) for j in range(3)) + ")" for k in range(2))
         for w, name in ((0, "w0"), (1, "w15"), (2, "w6")):
             e = row[w * 16:(w + 1) * 16]
             line += f" | {name}: seen=" + ",".join(rel(v) for v in e[0:4]) + \
