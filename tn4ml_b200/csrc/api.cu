@@ -109,8 +109,9 @@ template <typename T> static void fill_emb(const tnb_embedding &e, EmbParams<T> 
 // ------------------------------------------------------------------------------------
 struct MpsPlan {
   int chip, nslab, TN, NG, NT, BT, KT;
-  size_t off_Wn, off_Wt, off_F, off_G, off_exps, off_esum, off_y, off_dy, total;
+  size_t off_Wn, off_Wt, off_F, off_G, off_exps, off_esum, off_y, off_dy, off_wsimt, total;
   size_t smem_sweep, smem_class;
+  int RB;  // register-tile rows of the SIMT sweep / class kernels
   // tensor-core sweep (f32, TNB_PREC_TENSOR)
   int tc, tc_N, tc_NH, tc_NMMA, tc_nstage, tc_cols, tc_tiles, tc_cg;
   uint32_t tc_stage_bytes;
@@ -164,13 +165,21 @@ static MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
   int ng = (ngroups + P.TN - 1) / P.TN;
   P.NG = ng <= 1 ? 1 : (ng <= 2 ? 2 : 4);
   P.NT = 256;
+  // register-tile rows per thread: 4; TNB_SIMT_RB=8 selects 8 for float64 when the batch still fills the machine with
+  // 256-thread CTAs (twice the FMAs per operand load, but half the resident warps)
+  static const int rb_knob = [] { const char *e = getenv("TNB_SIMT_RB"); return e ? atoi(e) : 0; }();
+  P.RB = 4;
+  if (p->dtype == TNB_F64 && P.NG <= 2 && rb_knob == 8) {  // (measured slower at chi = 128: 204 registers, one CTA per SM)
+    const long long bt8 = (long long)(256 / P.TN) * 8;
+    if ((B + bt8 - 1) / bt8 >= 148) P.RB = 8;
+  }
   while (P.NT > 32) {
-    long long bt = (long long)(P.NT / P.TN) * kRB;
+    long long bt = (long long)(P.NT / P.TN) * P.RB;
     if ((B + bt - 1) / bt >= 148) break;
     P.NT >>= 1;
   }
   if (P.NT < P.TN) P.NT = P.TN < 32 ? 32 : P.TN;
-  P.BT = P.NT / P.TN * kRB;
+  P.BT = P.NT / P.TN * P.RB;
   size_t row = (size_t)p->d * P.chip * w;
   long kt = (long)(16384 / row);
   P.KT = kt < 1 ? 1 : (kt > 16 ? 16 : (int)kt);
@@ -188,6 +197,7 @@ static MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
   P.off_esum = take((size_t)2 * B * sizeof(int));
   P.off_y = take((size_t)B * p->n_out * w);
   P.off_dy = need_grad ? take((size_t)B * p->n_out * w) : 0;
+  P.off_wsimt = (need_grad && !tc_mode) ? take((size_t)p->L * p->d * B * w) : 0;  // per-sample dA weights of the SIMT family
   P.tc = tc_supported(p) ? 1 : 0;
   if (P.tc) {
     P.tc_N = p->d * p->chi;
@@ -200,6 +210,7 @@ static MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
     // (pays when the step's MMA time is comparable to its exposed tail: N = 256; measured slower at N <= 128)
     P.tc_tiles = (P.tc_NH == 1 && P.tc_N == 256) ? 2 : 1;
     if (tc_knobs().tiles == 1) P.tc_tiles = 1;
+    if (tc_knobs().tiles == 2 && P.tc_NH == 1 && (p->d == 2 || p->d == 4 || p->d == 8)) P.tc_tiles = 2;
     // CTA pair (cta_group::2), opt-in: the wide-bond case (chi > 128, d = 2), where shared-memory bandwidth caps the MMA
     // rate.  Parity-green but measured slower than the one-CTA kernel so far, hence not the default.
     P.tc_cg = (p->chi > 128 && p->d == 2 && P.tc_tiles == 1 && tc_knobs().cg == 2) ? 2 : 1;
@@ -249,6 +260,7 @@ static void fill_mps_args(const tnb_problem *p, const MpsPlan &P, long long B, c
   A.F = (T *)(w + P.off_F); A.G = (T *)(w + P.off_G);
   A.exps = (int *)(w + P.off_exps); A.esum = (int *)(w + P.off_esum);
   A.y = (T *)(w + P.off_y); A.dy = (T *)(w + P.off_dy);
+  A.wq = (T *)(w + P.off_wsimt);
   A.loss = nullptr; A.loss_sum = nullptr; A.out = nullptr; A.out_exp = nullptr;
   A.stash = 0; A.KT = P.KT; A.TN = P.TN; A.loss_scale = T(1); A.seed_only = 0;
 }
@@ -353,25 +365,25 @@ static int tc_launch_sweep(const tnb_problem *p, const MpsPlan &P, const TcArgs 
   return 0;
 }
 
-template <typename T, int NG> static int set_smem_attrs() {
+template <typename T, int NG, int RB> static int set_smem_attrs() {
   // 200 KB opt-in ceiling for the dynamic-smem kernels; done once per instantiation.
   static std::once_flag once;
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [] {
-    cudaError_t e = cudaFuncSetAttribute(mps_sweep_kernel<T, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(mps_sweep_kernel<T, NG, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(mps_class_kernel<T, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      e = cudaFuncSetAttribute(mps_class_kernel<T, NG, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     err = e;
   });
   if (err != cudaSuccess) return fail("cudaFuncSetAttribute: %s", cudaGetErrorString(err));
   return 0;
 }
 
-template <typename T, int NG>
+template <typename T, int NG, int RB>
 static int mps_forward_t(const tnb_problem *p, const MpsPlan &P, long long B, const void *x, const void *targets,
                          const void *params, void *loss, double *loss_sum, void *out, int32_t *out_exp,
                          int keep_stash, void *ws, cudaStream_t st) {
-  if (set_smem_attrs<T, NG>()) return 1;
+  if (set_smem_attrs<T, NG, RB>()) return 1;
   if (P.smem_class > 200 * 1024) return fail("shared-memory plan too large (%zu B)", P.smem_class);
   MpsArgs<T> A;
   fill_mps_args<T>(p, P, B, x, targets, ws, A);
@@ -414,18 +426,18 @@ static int mps_forward_t(const tnb_problem *p, const MpsPlan &P, long long B, co
   TNB_LAUNCH_CHECK("mps_prep_kernel");
   int tiles = (int)((B + P.BT - 1) / P.BT);
   prof_begin(st);
-  mps_sweep_kernel<T, NG><<<dim3(tiles, 2), P.NT, P.smem_sweep, st>>>(A, 0);
+  mps_sweep_kernel<T, NG, RB><<<dim3(tiles, 2), P.NT, P.smem_sweep, st>>>(A, 0);
   TNB_LAUNCH_CHECK("mps_sweep_kernel(fwd)");
   prof_begin(st);
-  mps_class_kernel<T, NG><<<tiles, P.NT, P.smem_class, st>>>(A);
+  mps_class_kernel<T, NG, RB><<<tiles, P.NT, P.smem_class, st>>>(A);
   TNB_LAUNCH_CHECK("mps_class_kernel");
   return 0;
 }
 
-template <typename T, int NG>
+template <typename T, int NG, int RB>
 static int mps_backward_t(const tnb_problem *p, const MpsPlan &P, long long B, const void *x, const void *targets,
                           double loss_scale, void *grads, int accumulate, void *ws, cudaStream_t st) {
-  if (set_smem_attrs<T, NG>()) return 1;
+  if (set_smem_attrs<T, NG, RB>()) return 1;
   MpsArgs<T> A;
   fill_mps_args<T>(p, P, B, x, targets, ws, A);
   A.stash = 1;
@@ -489,14 +501,24 @@ static int mps_backward_t(const tnb_problem *p, const MpsPlan &P, long long B, c
   }
   int tiles = (int)((B + P.BT - 1) / P.BT);
   prof_begin(st);
-  mps_sweep_kernel<T, NG><<<dim3(tiles, 2), P.NT, P.smem_sweep, st>>>(A, 1);
+  mps_sweep_kernel<T, NG, RB><<<dim3(tiles, 2), P.NT, P.smem_sweep, st>>>(A, 1);
   TNB_LAUNCH_CHECK("mps_sweep_kernel(adj)");
   DaArgs<T> Dg;
   Dg.M = A;
   Dg.grads = (T *)grads;
-  Dg.tiles_a = (P.chip + 63) / 64;
-  Dg.tiles_r = (P.chip + 63) / 64;
-  long long work = (long long)Dg.tiles_a * Dg.tiles_r * p->L * p->d;
+  {
+    const long long n = (long long)p->L * B;
+    prof_begin(st);
+    mps_wq_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A);
+    TNB_LAUNCH_CHECK("mps_wq_kernel");
+  }
+  // micro-tile rows: 8 (a 128 x 64 tile per CTA) when the flattened rows (s, a) fill it, else 4; TNB_DA_RM forces
+  static const int rm_knob = [] { const char *e = getenv("TNB_DA_RM"); return e ? atoi(e) : 0; }();
+  const int Mrows = p->d * p->chi;
+  const int RM = rm_knob == 4 || rm_knob == 8 ? rm_knob : (Mrows > 64 ? 8 : 4);
+  Dg.tiles_m = (Mrows + 16 * RM - 1) / (16 * RM);
+  Dg.tiles_r = (p->chi + 63) / 64;
+  long long work = (long long)Dg.tiles_m * Dg.tiles_r * p->L;
   long long ns = (148LL * 4 + work - 1) / work;
   long long maxsplit = (B + 255) / 256;
   if (ns > maxsplit) ns = maxsplit;
@@ -505,21 +527,23 @@ static int mps_backward_t(const tnb_problem *p, const MpsPlan &P, long long B, c
   Dg.bchunk = (B + ns - 1) / ns;
   Dg.bchunk = (Dg.bchunk + 15) / 16 * 16;
   Dg.only_site = -1;
-  dim3 grid(Dg.tiles_a * Dg.tiles_r * Dg.nsplit, p->L, p->d);
+  dim3 grid(Dg.tiles_m * Dg.tiles_r * Dg.nsplit, p->L, 1);
   prof_begin(st);
-  mps_da_kernel<T><<<grid, 256, 0, st>>>(Dg);
+  if (RM == 8) mps_da_kernel<T, 8><<<grid, 256, 0, st>>>(Dg);
+  else mps_da_kernel<T, 4><<<grid, 256, 0, st>>>(Dg);
   TNB_LAUNCH_CHECK("mps_da_kernel");
-  // class site: one GEMM per (s, class)
+  // class site: one GEMM per class
   Dg.only_site = p->out_site;
-  work = (long long)Dg.tiles_a * Dg.tiles_r * p->d * p->n_out;
+  work = (long long)Dg.tiles_m * Dg.tiles_r * p->n_out;
   ns = (148LL * 2 + work - 1) / work;
   if (ns > maxsplit) ns = maxsplit;
   if (ns < 1) ns = 1;
   Dg.nsplit = (int)ns;
   Dg.bchunk = ((B + ns - 1) / ns + 15) / 16 * 16;
-  dim3 gridc(Dg.tiles_a * Dg.tiles_r * Dg.nsplit, 1, p->d * p->n_out);
+  dim3 gridc(Dg.tiles_m * Dg.tiles_r * Dg.nsplit, 1, p->n_out);
   prof_begin(st);
-  mps_da_kernel<T><<<gridc, 256, 0, st>>>(Dg);
+  if (RM == 8) mps_da_kernel<T, 8><<<gridc, 256, 0, st>>>(Dg);
+  else mps_da_kernel<T, 4><<<gridc, 256, 0, st>>>(Dg);
   TNB_LAUNCH_CHECK("mps_da_kernel(class)");
   return 0;
 }
@@ -527,13 +551,15 @@ static int mps_backward_t(const tnb_problem *p, const MpsPlan &P, long long B, c
 #define TNB_DISPATCH_MPS(fn, ...)                                                   \
   do {                                                                              \
     if (p->dtype == TNB_F64) {                                                      \
-      if (P.NG == 1) return fn<double, 1>(__VA_ARGS__);                             \
-      if (P.NG == 2) return fn<double, 2>(__VA_ARGS__);                             \
-      return fn<double, 4>(__VA_ARGS__);                                            \
+      if (P.NG == 1 && P.RB == 8) return fn<double, 1, 8>(__VA_ARGS__);             \
+      if (P.NG == 2 && P.RB == 8) return fn<double, 2, 8>(__VA_ARGS__);             \
+      if (P.NG == 1) return fn<double, 1, 4>(__VA_ARGS__);                          \
+      if (P.NG == 2) return fn<double, 2, 4>(__VA_ARGS__);                          \
+      return fn<double, 4, 4>(__VA_ARGS__);                                         \
     } else {                                                                        \
-      if (P.NG == 1) return fn<float, 1>(__VA_ARGS__);                              \
-      if (P.NG == 2) return fn<float, 2>(__VA_ARGS__);                              \
-      return fn<float, 4>(__VA_ARGS__);                                             \
+      if (P.NG == 1) return fn<float, 1, 4>(__VA_ARGS__);                           \
+      if (P.NG == 2) return fn<float, 2, 4>(__VA_ARGS__);                           \
+      return fn<float, 4, 4>(__VA_ARGS__);                                          \
     }                                                                               \
   } while (0)
 

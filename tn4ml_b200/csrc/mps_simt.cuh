@@ -30,6 +30,7 @@ template <typename T> struct MpsArgs {
   int *esum;    // sum of deltas         [2][B]  (left half, right half)
   T *y;         // rescaled outputs y'   [B][C]
   T *dy;        // dLoss/dy' * loss_scale [B][C]
+  T *wq;        // SIMT dA weights [L][D][B]: phi_s[b] * 2^-delta_site[b] (class site: phi_s[b])
   T *loss;      // per-sample loss [B] (may be null)
   double *loss_sum;
   T *out;       // [B][C] copy of y' for the caller (may be null)
@@ -59,14 +60,14 @@ template <> __device__ __forceinline__ void lds_vec<double, 4>(const double *p, 
   w[0] = v0.x; w[1] = v0.y; w[2] = v1.x; w[3] = v1.y;
 }
 
-constexpr int kRB = 4, kRN = 4;
+constexpr int kRN = 4;  // register tile: RB rows (template parameter, 4 or 8) x kRN columns per thread
 
 // acc[g][rb][rn] += sum_{k<K, s<D} v[row][k] * phi[row][s] * rs[row] * W[k][s][n]
 // W streamed from global through a double-buffered cp.async ring of KT k-rows.
-template <typename T, int NG>
+template <typename T, int NG, int RB>
 __device__ __forceinline__ void step_gemm(const T *__restrict__ Wg, int K, int D, int chip, int KT,
                                           const T *v_s, const T *phi_s, const T *rs_s, int rs_stride,
-                                          T *W_s, T (&acc)[NG][kRB][kRN], int tb, int tn, int TN) {
+                                          T *W_s, T (&acc)[NG][RB][kRN], int tb, int tn, int TN) {
   const int tid = threadIdx.x, NT = blockDim.x;
   const int row_elems = D * chip;
   const int nchunks = (K + KT - 1) / KT;
@@ -79,9 +80,15 @@ __device__ __forceinline__ void step_gemm(const T *__restrict__ Wg, int K, int D
     for (int i = tid; i < n16; i += NT) cp_async16(dst + (size_t)i * 16, src + (size_t)i * 16);
     cp_async_commit();
   };
-  T rs[kRB];
+  T rs[RB];
 #pragma unroll
-  for (int rb = 0; rb < kRB; ++rb) rs[rb] = rs_s ? rs_s[(tb * kRB + rb) * rs_stride] : T(1);
+  for (int rb = 0; rb < RB; ++rb) rs[rb] = rs_s ? rs_s[(tb * RB + rb) * rs_stride] : T(1);
+  T rp0[RB], rp1[RB];
+#pragma unroll
+  for (int rb = 0; rb < RB; ++rb) {
+    rp0[rb] = D == 2 ? rs[rb] * phi_s[(tb * RB + rb) * 2] : T(0);
+    rp1[rb] = D == 2 ? rs[rb] * phi_s[(tb * RB + rb) * 2 + 1] : T(0);
+  }
   issue(0);
   for (int ch = 0; ch < nchunks; ++ch) {
     if (ch + 1 < nchunks) {
@@ -95,13 +102,18 @@ __device__ __forceinline__ void step_gemm(const T *__restrict__ Wg, int K, int D
     const int kt = min(KT, K - k0);
     const T *Wb = W_s + (size_t)(ch & 1) * KT * row_elems;
     for (int kk = 0; kk < kt; ++kk) {
-      T vv[kRB];
+      T vv[RB];
 #pragma unroll
-      for (int rb = 0; rb < kRB; ++rb) vv[rb] = v_s[(tb * kRB + rb) * chip + k0 + kk] * rs[rb];
+      for (int rb = 0; rb < RB; ++rb) vv[rb] = v_s[(tb * RB + rb) * chip + k0 + kk];
       for (int s = 0; s < D; ++s) {
-        T a[kRB];
+        T a[RB];
+        if (D == 2) {  // the common case keeps rs * phi in registers (one shared-memory load less per row and (k, s))
 #pragma unroll
-        for (int rb = 0; rb < kRB; ++rb) a[rb] = vv[rb] * phi_s[(tb * kRB + rb) * D + s];
+          for (int rb = 0; rb < RB; ++rb) a[rb] = vv[rb] * (s == 0 ? rp0[rb] : rp1[rb]);
+        } else {
+#pragma unroll
+          for (int rb = 0; rb < RB; ++rb) a[rb] = vv[rb] * rs[rb] * phi_s[(tb * RB + rb) * D + s];
+        }
         const T *wrow = Wb + (size_t)(kk * D + s) * chip;
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
@@ -110,7 +122,7 @@ __device__ __forceinline__ void step_gemm(const T *__restrict__ Wg, int K, int D
             T w[kRN];
             lds_vec<T, kRN>(wrow + n0, w);
 #pragma unroll
-            for (int rb = 0; rb < kRB; ++rb)
+            for (int rb = 0; rb < RB; ++rb)
 #pragma unroll
               for (int rn = 0; rn < kRN; ++rn) acc[g][rb][rn] = fma(a[rb], w[rn], acc[g][rb][rn]);
           }
@@ -121,11 +133,11 @@ __device__ __forceinline__ void step_gemm(const T *__restrict__ Wg, int K, int D
   }
 }
 
-template <typename T, int NG> __device__ __forceinline__ void zero_acc(T (&acc)[NG][kRB][kRN]) {
+template <typename T, int NG, int RB> __device__ __forceinline__ void zero_acc(T (&acc)[NG][RB][kRN]) {
 #pragma unroll
   for (int g = 0; g < NG; ++g)
 #pragma unroll
-    for (int rb = 0; rb < kRB; ++rb)
+    for (int rb = 0; rb < RB; ++rb)
 #pragma unroll
       for (int rn = 0; rn < kRN; ++rn) acc[g][rb][rn] = T(0);
 }
@@ -158,10 +170,10 @@ __device__ __forceinline__ void load_env(const T *env, long long b0, long long B
 // through the class site from dLoss/dy', then the adjoint chains towards the boundaries,
 // reusing the forward exponents delta_j.
 // ---------------------------------------------------------------------------------------
-template <typename T, int NG>
+template <typename T, int NG, int RB>
 __global__ void __launch_bounds__(256) mps_sweep_kernel(MpsArgs<T> A, int adjoint) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int TN = A.TN, TB = blockDim.x / TN, BT = TB * kRB;
+  const int TN = A.TN, TB = blockDim.x / TN, BT = TB * RB;
   const int chip = A.chip, D = A.D, C = A.C, c = A.c, L = A.L;
   T *v_s = reinterpret_cast<T *>(smem_raw);
   T *W_s = v_s + (size_t)BT * chip;
@@ -183,18 +195,20 @@ __global__ void __launch_bounds__(256) mps_sweep_kernel(MpsArgs<T> A, int adjoin
     if (A.seed_only) nsites = 0;
   }
 
-  T acc[NG][kRB][kRN];
-  int esum_r[kRB] = {0, 0, 0, 0};
+  T acc[NG][RB][kRN];
+  int esum_r[RB];
+#pragma unroll
+  for (int rb = 0; rb < RB; ++rb) esum_r[rb] = 0;
 
-  auto store_env = [&](T *env, const T(&sc)[kRB]) {
+  auto store_env = [&](T *env, const T(&sc)[RB]) {
     // acc * sc -> v_s and (optionally) global env
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
       int n0 = (g * TN + tn) * kRN;
       if (n0 < chip) {
 #pragma unroll
-        for (int rb = 0; rb < kRB; ++rb) {
-          int r = tb * kRB + rb;
+        for (int rb = 0; rb < RB; ++rb) {
+          int r = tb * RB + rb;
           long long b = b0 + r;
 #pragma unroll
           for (int rn = 0; rn < kRN; ++rn) {
@@ -242,12 +256,14 @@ __global__ void __launch_bounds__(256) mps_sweep_kernel(MpsArgs<T> A, int adjoin
     load_env(mps_fenv(A, half == 0 ? c + 1 : c), b0, A.B, BT, chip, v_s);
     load_phi(A, b0, BT, c, phi_s);
     __syncthreads();
-    zero_acc<T, NG>(acc);
+    zero_acc<T, NG, RB>(acc);
     const T *Wc = (half == 0 ? A.Wt : A.Wn) + (size_t)c * chip * D * chip;
     for (int k = 0; k < C; ++k)
-      step_gemm<T, NG>(Wc + (size_t)k * chip * D * chip, chip, D, chip, A.KT, v_s, phi_s, dy_s + k, C, W_s,
+      step_gemm<T, NG, RB>(Wc + (size_t)k * chip * D * chip, chip, D, chip, A.KT, v_s, phi_s, dy_s + k, C, W_s,
                        acc, tb, tn, TN);
-    const T one[kRB] = {T(1), T(1), T(1), T(1)};
+    T one[RB];
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb) one[rb] = T(1);
     store_env(A.G + (size_t)(half == 0 ? c : c + 1) * A.B * chip, one);
   }
   __syncthreads();
@@ -257,14 +273,14 @@ __global__ void __launch_bounds__(256) mps_sweep_kernel(MpsArgs<T> A, int adjoin
     const int bond_out = transposed ? site : site + 1;
     load_phi(A, b0, BT, site, phi_s);
     __syncthreads();
-    zero_acc<T, NG>(acc);
+    zero_acc<T, NG, RB>(acc);
     const T *W = (transposed ? A.Wt : A.Wn) + (size_t)mps_slab(A, site) * chip * D * chip;
-    step_gemm<T, NG>(W, chip, D, chip, A.KT, v_s, phi_s, (const T *)nullptr, 0, W_s, acc, tb, tn, TN);
-    T sc[kRB];
+    step_gemm<T, NG, RB>(W, chip, D, chip, A.KT, v_s, phi_s, (const T *)nullptr, 0, W_s, acc, tb, tn, TN);
+    T sc[RB];
     if (!adjoint) {
-      T m[kRB];
+      T m[RB];
 #pragma unroll
-      for (int rb = 0; rb < kRB; ++rb) {
+      for (int rb = 0; rb < RB; ++rb) {
         m[rb] = T(0);
 #pragma unroll
         for (int g = 0; g < NG; ++g)
@@ -276,14 +292,14 @@ __global__ void __launch_bounds__(256) mps_sweep_kernel(MpsArgs<T> A, int adjoin
         if (m[rb] > T(0)) Num<T>::frexp(m[rb], &e);
         sc[rb] = Num<T>::ldexp(T(1), -e);
         esum_r[rb] += e;
-        long long b = b0 + tb * kRB + rb;
+        long long b = b0 + tb * RB + rb;
         if (tn == 0 && b < A.B) A.exps[(size_t)site * A.B + b] = e;
       }
       store_env(mps_fenv(A, bond_out), sc);
     } else {
 #pragma unroll
-      for (int rb = 0; rb < kRB; ++rb) {
-        long long b = b0 + tb * kRB + rb;
+      for (int rb = 0; rb < RB; ++rb) {
+        long long b = b0 + tb * RB + rb;
         int e = b < A.B ? A.exps[(size_t)site * A.B + b] : 0;
         sc[rb] = Num<T>::ldexp(T(1), -e);
       }
@@ -293,8 +309,8 @@ __global__ void __launch_bounds__(256) mps_sweep_kernel(MpsArgs<T> A, int adjoin
   }
   if (!adjoint && tn == 0) {
 #pragma unroll
-    for (int rb = 0; rb < kRB; ++rb) {
-      long long b = b0 + tb * kRB + rb;
+    for (int rb = 0; rb < RB; ++rb) {
+      long long b = b0 + tb * RB + rb;
       if (b < A.B) A.esum[(size_t)half * A.B + b] = esum_r[rb];
     }
   }
@@ -303,10 +319,10 @@ __global__ void __launch_bounds__(256) mps_sweep_kernel(MpsArgs<T> A, int adjoin
 // ---------------------------------------------------------------------------------------
 // Class site + head:  y'[b,k] = F[c][b,:] . M_c^k[b] . F[c+1][b,:]   then the loss head.
 // ---------------------------------------------------------------------------------------
-template <typename T, int NG>
+template <typename T, int NG, int RB>
 __global__ void __launch_bounds__(256) mps_class_kernel(MpsArgs<T> A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int TN = A.TN, TB = blockDim.x / TN, BT = TB * kRB;
+  const int TN = A.TN, TB = blockDim.x / TN, BT = TB * RB;
   const int chip = A.chip, D = A.D, C = A.C, c = A.c;
   T *v_s = reinterpret_cast<T *>(smem_raw);
   T *W_s = v_s + (size_t)BT * chip;
@@ -322,15 +338,15 @@ __global__ void __launch_bounds__(256) mps_class_kernel(MpsArgs<T> A) {
   load_env(mps_fenv(A, c + 1), b0, A.B, BT, chip, fr_s);
   load_phi(A, b0, BT, c, phi_s);
   __syncthreads();
-  T acc[NG][kRB][kRN];
+  T acc[NG][RB][kRN];
   const T *Wc = A.Wn + (size_t)c * chip * D * chip;
   for (int k = 0; k < C; ++k) {
-    zero_acc<T, NG>(acc);
-    step_gemm<T, NG>(Wc + (size_t)k * chip * D * chip, chip, D, chip, A.KT, v_s, phi_s, (const T *)nullptr, 0,
+    zero_acc<T, NG, RB>(acc);
+    step_gemm<T, NG, RB>(Wc + (size_t)k * chip * D * chip, chip, D, chip, A.KT, v_s, phi_s, (const T *)nullptr, 0,
                      W_s, acc, tb, tn, TN);
 #pragma unroll
-    for (int rb = 0; rb < kRB; ++rb) {
-      int r = tb * kRB + rb;
+    for (int rb = 0; rb < RB; ++rb) {
+      int r = tb * RB + rb;
       T part = T(0);
 #pragma unroll
       for (int g = 0; g < NG; ++g) {
@@ -376,90 +392,129 @@ __global__ void __launch_bounds__(256) mps_class_kernel(MpsArgs<T> A) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Weight gradients (K4):  dA_j[a,r,s(,k)] += sum_b w[b] U[b,a] phi_j[b,s] V[b,r]
+// Weight gradients (K4):  dA_j[a,r,s(,k)] += sum_b w_s[b] U[b,a] V[b,r],   w_s[b] = phi_j[b,s] * w[b]
 //   j < c : U = F[j],  V = G[j+1], w = 2^-delta_j        j > c : U = G[j], V = F[j+1], w = 2^-delta_j
 //   j = c : U = F[c],  V = F[c+1], w = dy'[b,k]
-// grid = (tiles * splits, L, D * n_j); 16x16 threads, 4x4 micro-tile, 64x64 output tile.
+// One GEMM per site with the rows m = (s, a) flattened (M = D * chi), K = batch: the V tile is read once for all s and
+// no tile row is wasted at small bonds.  grid = (tiles_m * tiles_r * splits, L, n_j); 16x16 threads, RM x 4 micro-tile,
+// (16 RM) x 64 output tile.  The next 16 samples are fetched into registers while the current ones are multiplied
+// (the loads of the first version were synchronous, and its D copies re-read U and V).
 // ---------------------------------------------------------------------------------------
 template <typename T> struct DaArgs {
   MpsArgs<T> M;
   T *grads;  // packed layout, chi (unpadded) strides
-  int tiles_a, tiles_r, nsplit;
+  int tiles_m, tiles_r, nsplit;
   long long bchunk;  // samples per split
   int only_site;     // >= 0: this site only (the class site); < 0: site = blockIdx.y, class site skipped
 };
 
-template <typename T> __global__ void __launch_bounds__(256) mps_da_kernel(DaArgs<T> P) {
+// per-sample weights of the dA GEMM, one thread per (site, sample) (the embedding is evaluated once, not once per tile)
+template <typename T> __global__ void mps_wq_kernel(MpsArgs<T> A) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)A.L * A.B) return;
+  const int site = (int)(i / A.B);
+  const long long b = i - (long long)site * A.B;
+  T ph[kMaxPhys];
+  embed_site(A.emb, A.x[(size_t)b * A.L + site], ph);
+  const T f = site == A.c ? T(1) : Num<T>::ldexp(T(1), -A.exps[(size_t)site * A.B + b]);
+  for (int s = 0; s < A.D; ++s) A.wq[((size_t)site * A.D + s) * A.B + b] = ph[s] * f;
+}
+
+template <typename T, int RM> __global__ void __launch_bounds__(256) mps_da_kernel(DaArgs<T> P) {
   const MpsArgs<T> &A = P.M;
-  constexpr int TA = 64, TR = 64, BK = 16;
-  __shared__ __align__(16) T U_s[BK][TA];
+  constexpr int TM = 16 * RM, TR = 64, BK = 16;
+  constexpr int UE = BK * TM / 256, VE = BK * TR / 256;  // staged elements per thread and chunk
+  constexpr int UROWS = 256 / TM, VROWS = 256 / TR;      // samples covered by one pass of the CTA
+  __shared__ __align__(16) T U_s[BK][TM];
   __shared__ __align__(16) T V_s[BK][TR];
-  __shared__ T w_s[BK];
   const int site = P.only_site >= 0 ? P.only_site : (int)blockIdx.y;
   const int c = A.c, chip = A.chip, chi = A.chi, D = A.D, C = A.C;
   if (P.only_site < 0 && site == c) return;
-  const int nj = site == c ? C : 1;
-  const int z = blockIdx.z;
-  const int s = z / nj, kcls = z - s * nj;
+  const bool cls = site == c;
+  const int nj = cls ? C : 1;
+  const int kcls = blockIdx.z;
   int bx = blockIdx.x;
   const int split = bx % P.nsplit;
   bx /= P.nsplit;
-  const int tr = bx % P.tiles_r, ta = bx / P.tiles_r;
-  const int a0 = ta * TA, r0 = tr * TR;
+  const int tr = bx % P.tiles_r, tm = bx / P.tiles_r;
+  const int m0 = tm * TM, r0 = tr * TR, Mrows = D * chi;
   const T *U = site <= c ? mps_fenv(A, site) : A.G + (size_t)site * A.B * chip;
   const T *V = site < c ? A.G + (size_t)(site + 1) * A.B * chip : mps_fenv(A, site + 1);
   const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
-  T acc[4][4];
+  // staging coordinates: a thread always stages the same U row m = (s, a) and the same V column
+  const int ucol = tid % TM, ukk = tid / TM, vcol = tid % TR, vkk = tid / TR;
+  const int um = m0 + ucol;
+  const bool uok = um < Mrows, vok = r0 + vcol < chi;
+  const int us = uok ? um / chi : 0, ua = uok ? um - us * chi : 0;
+  const T *Wq = A.wq + ((size_t)site * D + us) * A.B;
+  T acc[RM][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < RM; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
   const long long bbeg = (long long)split * P.bchunk;
   const long long bend = min(A.B, bbeg + P.bchunk);
+  T ureg[UE], wreg[UE], vreg[VE];
+  auto fetch = [&](long long bb) {
+#pragma unroll
+    for (int e = 0; e < UE; ++e) {
+      const long long b = bb + e * UROWS + ukk;
+      const bool ok = uok && b < bend;
+      ureg[e] = ok ? U[(size_t)b * chip + ua] : T(0);
+      wreg[e] = ok ? Wq[b] : T(0);
+      if (cls && ok) wreg[e] *= A.dy[(size_t)b * C + kcls];
+    }
+#pragma unroll
+    for (int e = 0; e < VE; ++e) {
+      const long long b = bb + e * VROWS + vkk;
+      vreg[e] = (vok && b < bend) ? V[(size_t)b * chip + r0 + vcol] : T(0);
+    }
+  };
+  auto stage = [&]() {
+#pragma unroll
+    for (int e = 0; e < UE; ++e) U_s[e * UROWS + ukk][ucol] = ureg[e] * wreg[e];
+#pragma unroll
+    for (int e = 0; e < VE; ++e) V_s[e * VROWS + vkk][vcol] = vreg[e];
+  };
+  if (bbeg < bend) {
+    fetch(bbeg);
+    stage();
+    __syncthreads();
+  }
   for (long long bb = bbeg; bb < bend; bb += BK) {
-    if (tid < BK) {
-      long long b = bb + tid;
-      T w = T(0);
-      if (b < bend) {
-        T ph[kMaxPhys];
-        embed_site(A.emb, A.x[(size_t)b * A.L + site], ph);
-        w = ph[s];
-        if (site == c) w *= A.dy[(size_t)b * C + kcls];
-        else w *= Num<T>::ldexp(T(1), -A.exps[(size_t)site * A.B + b]);
-      }
-      w_s[tid] = w;
-    }
-    __syncthreads();
-    for (int i = tid; i < BK * TA; i += 256) {
-      int kk = i / TA, col = i - kk * TA;
-      long long b = bb + kk;
-      bool ok = b < bend;
-      U_s[kk][col] = (ok && a0 + col < chip) ? U[(size_t)b * chip + a0 + col] * w_s[kk] : T(0);
-      V_s[kk][col] = (ok && r0 + col < chip) ? V[(size_t)b * chip + r0 + col] : T(0);
-    }
-    __syncthreads();
+    const bool more = bb + BK < bend;
+    if (more) fetch(bb + BK);
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
-      T u[4], v[4];
-      lds_vec<T, 4>(&U_s[kk][ty * 4], u);
+      T u[RM], v[4];
+#pragma unroll
+      for (int i = 0; i < RM / 4; ++i) {
+        T t4[4];
+        lds_vec<T, 4>(&U_s[kk][ty * RM + 4 * i], t4);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) u[4 * i + q] = t4[q];
+      }
       lds_vec<T, 4>(&V_s[kk][tx * 4], v);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < RM; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fma(u[i], v[j], acc[i][j]);
     }
+    __syncthreads();
+    if (more) stage();
     __syncthreads();
   }
   // scatter into the packed layout [a][r][s][k]
   const size_t site_off = (size_t)site * chi * chi * D + (site > c ? (size_t)chi * chi * D * (C - 1) : 0);
   T *g = P.grads + site_off;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    int a = a0 + ty * 4 + i;
-    if (a >= chi) continue;
+  for (int i = 0; i < RM; ++i) {
+    const int m = m0 + ty * RM + i;
+    if (m >= Mrows) continue;
+    const int s = m / chi, a = m - s * chi;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      int r = r0 + tx * 4 + j;
+      const int r = r0 + tx * 4 + j;
       if (r >= chi) continue;
       atomicAdd(&g[(((size_t)a * chi + r) * D + s) * nj + kcls], acc[i][j]);
     }

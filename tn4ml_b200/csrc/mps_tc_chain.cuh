@@ -376,6 +376,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
               const long long c1 = TNB_CLOCK();
               if (CG == 2 && !(A.dbg & 4)) ptx::mbar_wait(&pfull[stage], phase);
               const long long c2 = TNB_CLOCK();
+              (void)c0; (void)c1; (void)c2;
               ptx::tc_fence_after();
               if (ptx::elect_one()) {
                 const uint64_t da_hi = ptx::smem_desc_kmajor(a_hi_s + ks * 256, 128, sbo_a);
