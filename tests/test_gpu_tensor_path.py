@@ -94,3 +94,23 @@ def test_micro_batched_step_equals_one_piece(precision):
     ls2, g2 = eng.value_and_grad(model._packed, x.float(), t.float())
     assert abs(float(ls2.item()) - ls1) <= 1e-5 * abs(ls1)
     assert float((g2 - g1).abs().max()) <= 2e-5 * float(g1.abs().max())
+
+
+def test_cta_pair_chain_kernel_opt_in():
+    """The opt-in CTA-pair chain kernel (TNB_TC_CG=2: cta_group::2 MMAs, each CTA of a cluster of two holding half of the
+    weight columns) against the oracle: chi = 256, an odd number of sample tiles (the pair's second tile is all padding).
+    The knob is read once per process, hence the subprocess (tools/pair_case.py prints the errors)."""
+    import os
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, TNB_TC_CG="2")
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "pair_case.py"), "300"], env=env, capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    m = re.search(r"loss ([0-9.eE+-]+) oracle ([0-9.eE+-]+)\s+max grad err / max\|g\| ([0-9.eE+-]+)", out.stdout)
+    assert m, out.stdout[-2000:]
+    loss, ref, err = (float(v) for v in m.groups())
+    assert abs(loss - ref) <= 1e-4 * abs(ref)
+    assert err <= 1e-4
