@@ -108,7 +108,7 @@ template <typename T> static void fill_emb(const tnb_embedding &e, EmbParams<T> 
 // MPS workspace plan
 // ------------------------------------------------------------------------------------
 struct MpsPlan {
-  int chip, nslab, TN, NG, NT, BT, KT;
+  int chip, nslab, TN, NG, NT, BT, KT, WS;
   size_t off_Wn, off_Wt, off_F, off_G, off_exps, off_esum, off_y, off_dy, off_wsimt, total;
   size_t smem_sweep, smem_class;
   int RB;  // register-tile rows of the SIMT sweep / class kernels
@@ -173,6 +173,8 @@ static MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
     const long long bt8 = (long long)(256 / P.TN) * 8;
     if ((B + bt8 - 1) / bt8 >= 148) P.RB = 8;
   }
+  static const int nt_knob = [] { const char *e = getenv("TNB_SIMT_NT"); return e ? atoi(e) : 0; }();
+  if (nt_knob == 128 || nt_knob == 64) P.NT = nt_knob;
   while (P.NT > 32) {
     long long bt = (long long)(P.NT / P.TN) * P.RB;
     if ((B + bt - 1) / bt >= 148) break;
@@ -182,9 +184,12 @@ static MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
   P.BT = P.NT / P.TN * P.RB;
   size_t row = (size_t)p->d * P.chip * w;
   long kt = (long)(16384 / row);
+  static const int kt_knob = [] { const char *e = getenv("TNB_SIMT_KT"); return e ? atoi(e) : 0; }();
+  if (kt_knob > 0) kt = kt_knob;
   P.KT = kt < 1 ? 1 : (kt > 16 ? 16 : (int)kt);
   if (P.KT > P.chip) P.KT = P.chip;
-  size_t slab = (size_t)P.chip * p->d * P.chip * w;
+  P.WS = p->dtype == TNB_F64 ? P.NG * P.TN * kRN : P.chip;  // row stride of the kernel-layout weights (mps_prep_kernel)
+  size_t slab = (size_t)P.chip * p->d * P.WS * w;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
   P.off_Wn = take(slab * P.nslab);
@@ -240,7 +245,7 @@ static MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
     }
   }
   P.total = o;
-  size_t base = ((size_t)P.BT * P.chip + (size_t)2 * P.KT * p->d * P.chip + (size_t)P.BT * p->d +
+  size_t base = ((size_t)P.BT * P.chip + (size_t)2 * P.KT * p->d * P.WS + (size_t)P.BT * p->d +
                  (size_t)P.BT * p->n_out) * w;
   P.smem_sweep = base;
   P.smem_class = base + (size_t)P.BT * P.chip * w;
@@ -262,7 +267,7 @@ static void fill_mps_args(const tnb_problem *p, const MpsPlan &P, long long B, c
   A.y = (T *)(w + P.off_y); A.dy = (T *)(w + P.off_dy);
   A.wq = (T *)(w + P.off_wsimt);
   A.loss = nullptr; A.loss_sum = nullptr; A.out = nullptr; A.out_exp = nullptr;
-  A.stash = 0; A.KT = P.KT; A.TN = P.TN; A.loss_scale = T(1); A.seed_only = 0;
+  A.stash = 0; A.KT = P.KT; A.TN = P.TN; A.WS = P.WS; A.loss_scale = T(1); A.seed_only = 0;
 }
 
 static void fill_tc_args(const MpsPlan &P, void *ws, const MpsArgs<float> &M, TcArgs &T) {
@@ -422,7 +427,7 @@ static int mps_forward_t(const tnb_problem *p, const MpsPlan &P, long long B, co
   if (pblocks > 148 * 16) pblocks = 148 * 16;
   prof_begin(st);
   mps_prep_kernel<T><<<pblocks, 256, 0, st>>>((const T *)params, (T *)A.Wn, (T *)A.Wt, p->L, p->chi, P.chip, p->d,
-                                              p->n_out, p->out_site);
+                                              p->n_out, p->out_site, P.WS, P.TN);
   TNB_LAUNCH_CHECK("mps_prep_kernel");
   int tiles = (int)((B + P.BT - 1) / P.BT);
   prof_begin(st);

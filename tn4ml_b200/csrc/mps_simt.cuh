@@ -37,6 +37,7 @@ template <typename T> struct MpsArgs {
   int *out_exp; // [B]
   int stash;    // 1: every bond of F is stored (needed by backward)
   int KT, TN;
+  int WS;        // shared-memory stride of one (k, s) weight row: chip, or NG*TN*4 for float64 (bank-conflict-free pair layout)
   T loss_scale;
   int seed_only;  // adjoint launch: write the seeds G[c], G[c+1] (and dy) only; the chains run elsewhere
 };
@@ -60,6 +61,13 @@ template <> __device__ __forceinline__ void lds_vec<double, 4>(const double *p, 
   w[0] = v0.x; w[1] = v0.y; w[2] = v1.x; w[3] = v1.y;
 }
 
+// two consecutive elements with one load (16 bytes for double; p is 16-byte aligned)
+template <typename T> __device__ __forceinline__ void lds_pair(const T *p, T &a, T &b) { a = p[0]; b = p[1]; }
+template <> __device__ __forceinline__ void lds_pair<double>(const double *p, double &a, double &b) {
+  const double2 v = *reinterpret_cast<const double2 *>(p);
+  a = v.x; b = v.y;
+}
+
 constexpr int kRN = 4;  // register tile: RB rows (template parameter, 4 or 8) x kRN columns per thread
 
 // acc[g][rb][rn] += sum_{k<K, s<D} v[row][k] * phi[row][s] * rs[row] * W[k][s][n]
@@ -67,9 +75,13 @@ constexpr int kRN = 4;  // register tile: RB rows (template parameter, 4 or 8) x
 template <typename T, int NG, int RB>
 __device__ __forceinline__ void step_gemm(const T *__restrict__ Wg, int K, int D, int chip, int KT,
                                           const T *v_s, const T *phi_s, const T *rs_s, int rs_stride,
-                                          T *W_s, T (&acc)[NG][RB][kRN], int tb, int tn, int TN) {
+                                          T *W_s, T (&acc)[NG][RB][kRN], int tb, int tn, int TN, int WS) {
   const int tid = threadIdx.x, NT = blockDim.x;
-  const int row_elems = D * chip;
+  const int row_elems = D * WS;  // one k-row, in global and in shared memory
+  // float64: a thread's four columns n0..n0+3 are two 16-byte loads; at the natural stride of 32 bytes per thread the
+  // lanes of a warp hit only half of the banks.  mps_prep_kernel therefore writes the rows as
+  // [group g][pair 0 | pair 1][tn][2] (WS = NG*TN*4 elements): lane tn reads 16 bytes at tn*16 for each pair.
+  constexpr bool kPairs = sizeof(T) == 8;
   const int nchunks = (K + KT - 1) / KT;
   auto issue = [&](int ch) {
     int k0 = ch * KT;
@@ -114,13 +126,19 @@ __device__ __forceinline__ void step_gemm(const T *__restrict__ Wg, int K, int D
 #pragma unroll
           for (int rb = 0; rb < RB; ++rb) a[rb] = vv[rb] * rs[rb] * phi_s[(tb * RB + rb) * D + s];
         }
-        const T *wrow = Wb + (size_t)(kk * D + s) * chip;
+        const T *wrow = Wb + (size_t)(kk * D + s) * WS;
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
           int n0 = (g * TN + tn) * kRN;
           if (n0 < chip) {
             T w[kRN];
-            lds_vec<T, kRN>(wrow + n0, w);
+            if (kPairs) {
+              const T *pg = wrow + g * TN * kRN + tn * 2;
+              lds_pair<T>(pg, w[0], w[1]);
+              lds_pair<T>(pg + TN * 2, w[2], w[3]);
+            } else {
+              lds_vec<T, kRN>(wrow + n0, w);
+            }
 #pragma unroll
             for (int rb = 0; rb < RB; ++rb)
 #pragma unroll
@@ -177,7 +195,7 @@ __global__ void __launch_bounds__(256) mps_sweep_kernel(MpsArgs<T> A, int adjoin
   const int chip = A.chip, D = A.D, C = A.C, c = A.c, L = A.L;
   T *v_s = reinterpret_cast<T *>(smem_raw);
   T *W_s = v_s + (size_t)BT * chip;
-  T *phi_s = W_s + (size_t)2 * A.KT * D * chip;
+  T *phi_s = W_s + (size_t)2 * A.KT * D * A.WS;
   T *dy_s = phi_s + (size_t)BT * D;
   const int tid = threadIdx.x;
   const int tn = tid % TN, tb = tid / TN;
@@ -257,10 +275,10 @@ __global__ void __launch_bounds__(256) mps_sweep_kernel(MpsArgs<T> A, int adjoin
     load_phi(A, b0, BT, c, phi_s);
     __syncthreads();
     zero_acc<T, NG, RB>(acc);
-    const T *Wc = (half == 0 ? A.Wt : A.Wn) + (size_t)c * chip * D * chip;
+    const T *Wc = (half == 0 ? A.Wt : A.Wn) + (size_t)c * chip * D * A.WS;
     for (int k = 0; k < C; ++k)
-      step_gemm<T, NG, RB>(Wc + (size_t)k * chip * D * chip, chip, D, chip, A.KT, v_s, phi_s, dy_s + k, C, W_s,
-                       acc, tb, tn, TN);
+      step_gemm<T, NG, RB>(Wc + (size_t)k * chip * D * A.WS, chip, D, chip, A.KT, v_s, phi_s, dy_s + k, C, W_s,
+                       acc, tb, tn, TN, A.WS);
     T one[RB];
 #pragma unroll
     for (int rb = 0; rb < RB; ++rb) one[rb] = T(1);
@@ -274,8 +292,8 @@ __global__ void __launch_bounds__(256) mps_sweep_kernel(MpsArgs<T> A, int adjoin
     load_phi(A, b0, BT, site, phi_s);
     __syncthreads();
     zero_acc<T, NG, RB>(acc);
-    const T *W = (transposed ? A.Wt : A.Wn) + (size_t)mps_slab(A, site) * chip * D * chip;
-    step_gemm<T, NG, RB>(W, chip, D, chip, A.KT, v_s, phi_s, (const T *)nullptr, 0, W_s, acc, tb, tn, TN);
+    const T *W = (transposed ? A.Wt : A.Wn) + (size_t)mps_slab(A, site) * chip * D * A.WS;
+    step_gemm<T, NG, RB>(W, chip, D, chip, A.KT, v_s, phi_s, (const T *)nullptr, 0, W_s, acc, tb, tn, TN, A.WS);
     T sc[RB];
     if (!adjoint) {
       T m[RB];
@@ -326,7 +344,7 @@ __global__ void __launch_bounds__(256) mps_class_kernel(MpsArgs<T> A) {
   const int chip = A.chip, D = A.D, C = A.C, c = A.c;
   T *v_s = reinterpret_cast<T *>(smem_raw);
   T *W_s = v_s + (size_t)BT * chip;
-  T *phi_s = W_s + (size_t)2 * A.KT * D * chip;
+  T *phi_s = W_s + (size_t)2 * A.KT * D * A.WS;
   T *y_s = phi_s + (size_t)BT * D;
   T *fr_s = y_s + (size_t)BT * C;
   __shared__ double red_s[8];
@@ -339,11 +357,11 @@ __global__ void __launch_bounds__(256) mps_class_kernel(MpsArgs<T> A) {
   load_phi(A, b0, BT, c, phi_s);
   __syncthreads();
   T acc[NG][RB][kRN];
-  const T *Wc = A.Wn + (size_t)c * chip * D * chip;
+  const T *Wc = A.Wn + (size_t)c * chip * D * A.WS;
   for (int k = 0; k < C; ++k) {
     zero_acc<T, NG, RB>(acc);
-    step_gemm<T, NG, RB>(Wc + (size_t)k * chip * D * chip, chip, D, chip, A.KT, v_s, phi_s, (const T *)nullptr, 0,
-                     W_s, acc, tb, tn, TN);
+    step_gemm<T, NG, RB>(Wc + (size_t)k * chip * D * A.WS, chip, D, chip, A.KT, v_s, phi_s, (const T *)nullptr, 0,
+                     W_s, acc, tb, tn, TN, A.WS);
 #pragma unroll
     for (int rb = 0; rb < RB; ++rb) {
       int r = tb * RB + rb;
@@ -446,6 +464,9 @@ template <typename T, int RM> __global__ void __launch_bounds__(256) mps_da_kern
   const int um = m0 + ucol;
   const bool uok = um < Mrows, vok = r0 + vcol < chi;
   const int us = uok ? um / chi : 0, ua = uok ? um - us * chi : 0;
+  // float64: a thread's four V columns are two 16-byte loads; stored as [pair 0 | pair 1][tx][2] the 16 lanes read
+  // consecutive 16-byte pieces (at the natural 32-byte stride they fall on half of the banks)
+  const int vpos = sizeof(T) == 8 ? ((vcol & 3) >> 1) * 32 + (vcol >> 2) * 2 + (vcol & 1) : vcol;
   const T *Wq = A.wq + ((size_t)site * D + us) * A.B;
   T acc[RM][4];
 #pragma unroll
@@ -474,7 +495,7 @@ template <typename T, int RM> __global__ void __launch_bounds__(256) mps_da_kern
 #pragma unroll
     for (int e = 0; e < UE; ++e) U_s[e * UROWS + ukk][ucol] = ureg[e] * wreg[e];
 #pragma unroll
-    for (int e = 0; e < VE; ++e) V_s[e * VROWS + vkk][vcol] = vreg[e];
+    for (int e = 0; e < VE; ++e) V_s[e * VROWS + vkk][vpos] = vreg[e];
   };
   if (bbeg < bend) {
     fetch(bbeg);
@@ -494,7 +515,12 @@ template <typename T, int RM> __global__ void __launch_bounds__(256) mps_da_kern
 #pragma unroll
         for (int q = 0; q < 4; ++q) u[4 * i + q] = t4[q];
       }
-      lds_vec<T, 4>(&V_s[kk][tx * 4], v);
+      if (sizeof(T) == 8) {
+        lds_pair<T>(&V_s[kk][tx * 2], v[0], v[1]);
+        lds_pair<T>(&V_s[kk][32 + tx * 2], v[2], v[3]);
+      } else {
+        lds_vec<T, 4>(&V_s[kk][tx * 4], v);
+      }
 #pragma unroll
       for (int i = 0; i < RM; ++i)
 #pragma unroll
@@ -527,7 +553,7 @@ template <typename T, int RM> __global__ void __launch_bounds__(256) mps_da_kern
 // ---------------------------------------------------------------------------------------
 template <typename T>
 __global__ void mps_prep_kernel(const T *__restrict__ params, T *__restrict__ Wn, T *__restrict__ Wt, int L,
-                                int chi, int chip, int D, int C, int c) {
+                                int chi, int chip, int D, int C, int c, int WS, int TN) {
   const int nslab = L - 1 + C;
   const size_t slab_elems = (size_t)chip * D * chip;
   const size_t total = slab_elems * nslab;
@@ -547,8 +573,15 @@ __global__ void mps_prep_kernel(const T *__restrict__ params, T *__restrict__ Wn
       vn = params[site_off + (((size_t)k * chi + n) * D + s) * nj + o];
       vt = params[site_off + (((size_t)n * chi + k) * D + s) * nj + o];
     }
-    Wn[i] = vn;
-    Wt[i] = vt;
+    // position of column n inside its row of WS elements (see step_gemm): natural, or the float64 pair layout
+    int pos = n;
+    if (sizeof(T) == 8) {
+      const int q4 = n >> 2, j = n & 3, g = q4 / TN, tn = q4 - g * TN;
+      pos = g * TN * 4 + (j >> 1) * TN * 2 + tn * 2 + (j & 1);
+    }
+    const size_t dst = (((size_t)slab * chip + k) * D + s) * WS + pos;
+    Wn[dst] = vn;
+    Wt[dst] = vt;
   }
 }
 
