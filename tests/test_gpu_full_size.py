@@ -1,0 +1,133 @@
+"""BASELINE.json's configurations at their FULL sizes, checked through size-independent properties (the oracle cannot run
+these sizes in seconds, so parity proper is tested at reduced sizes in test_gpu_parity.py / test_gpu_tensor_path.py):
+
+  * additivity over the batch: loss sum and gradient of a batch = those of its two halves added (exercises micro-batching,
+    split-K / atomic accumulation and ragged tiles at the real grid sizes);
+  * invariance under a permutation of the samples;
+  * power-of-two gauge: A_i * 2^k, A_{i+1} * 2^-k leaves every loss unchanged and scales the two gradients by 2^-k / 2^k
+    (exact in floating point up to the kernels' own exponent bookkeeping);
+  * the reference's own property tests at full size: 0 <= softmax cross-entropy of a unit-norm logit vector <= log C + 2,
+    TransformedSquaredNorm >= 0 (tn4ml tests/test_metrics.py:117-172), NegLogLikelihood >= 0 for a normalised model
+    (tests/test_metrics.py:40-113).
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tn_oracle as O  # synthetic-input generators only
+from tests.test_gpu_parity import _heads
+
+pytestmark = pytest.mark.gpu
+
+
+def _vg(eng, model, x, t):
+    ls, g = eng.value_and_grad(model._packed, x, t, denom=1)
+    out = float(ls.item()), g.clone()
+    eng._ws.clear()
+    torch.cuda.empty_cache()
+    return out
+
+
+def _inputs(B, L, C, dtype, seed=1234):
+    rng = np.random.default_rng(seed)
+    x = torch.from_numpy(1.0 - rng.random((B, L))).to("cuda:0", dtype)
+    t = None
+    if C:
+        t = torch.nn.functional.one_hot(torch.from_numpy(rng.integers(0, C, size=B)), C).to("cuda:0", dtype)
+    return x, t
+
+
+def _batch_properties(eng, model, x, t, tol, denom_scale):
+    B = x.shape[0]
+    ls, g = _vg(eng, model, x, t)
+    assert math.isfinite(ls) and bool(torch.isfinite(g).all())
+    gmax = float(g.abs().max())
+    assert gmax > 0
+    # additivity over the batch (odd split point: ragged tiles on both sides)
+    h = B // 2 + 37
+    la, ga = _vg(eng, model, x[:h], None if t is None else t[:h])
+    lb, gb = _vg(eng, model, x[h:], None if t is None else t[h:])
+    assert abs(la + lb - ls) <= tol * abs(ls)
+    assert float((ga + gb - g).abs().max()) <= tol * denom_scale * gmax
+    del ga, gb
+    # permutation of the samples
+    perm = torch.randperm(B, device=x.device, generator=torch.Generator(device=x.device).manual_seed(3))
+    lp, gp = _vg(eng, model, x[perm].contiguous(), None if t is None else t[perm].contiguous())
+    assert abs(lp - ls) <= tol * abs(ls)
+    assert float((gp - g).abs().max()) <= tol * denom_scale * gmax
+    return ls, g
+
+
+def test_cfg5_full_size_properties():
+    """MPS classifier L=196, chi=256, d=2, C=10 at site 97, B=131072, float32 on the tcgen05 family."""
+    import tn4ml_b200 as T
+    from tn4ml_b200 import _lib
+    L, chi, C, B = 196, 256, 10, 131072
+    arrays = O.make_mps_arrays(L, chi, 2, class_site=L // 2 - 1, C=C, std=1e-2, seed=42, dtype=torch.float32)
+    model = T.TensorNetwork(arrays, dtype=torch.float32, device="cuda:0")
+    assert model.precision == _lib.PREC_TENSOR
+    x, t = _inputs(B, L, C, torch.float32)
+    eng, _ = model._engine(T.TrigonometricEmbedding(), _heads()["softmax_xent"], True, torch.float32)
+    ls, g = _batch_properties(eng, model, x, t, tol=2e-5, denom_scale=5.0)
+    # per-sample head bounds on a slice (unit-norm logits: components in [-1, 1])
+    per, out, _ = eng.forward(model._packed, x[:8192], t[:8192])
+    assert float(per.min()) > 0.0 and float(per.max()) <= math.log(C) + 2.0
+    eng._ws.clear()
+    # power-of-two gauge on the bond between sites 40 and 41
+    views = model._views(model._packed)
+    views[40].mul_(8.0)
+    views[41].mul_(0.125)
+    ls2, g2 = _vg(eng, model, x, t)
+    assert abs(ls2 - ls) <= 2e-5 * abs(ls)
+    gv, gv2 = model._views(g), model._views(g2)
+    gmax = float(g.abs().max())
+    assert float((gv2[40] * 8.0 - gv[40]).abs().max()) <= 1e-4 * gmax
+    assert float((gv2[41] * 0.125 - gv[41]).abs().max()) <= 1e-4 * gmax
+    assert float((gv2[100] - gv[100]).abs().max()) <= 1e-4 * gmax
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+def test_cfg4_full_size_properties(dtype):
+    """MPS anomaly detection L=16, Fourier d=8, chi=64, B=65536 (float64: SIMT family; float32: tcgen05 family)."""
+    import tn4ml_b200 as T
+    L, chi, d, B = 16, 64, 8, 65536
+    arrays = O.make_mps_arrays(L, chi, d, std=1e-2, seed=42, dtype=dtype, squeeze_ends=True, identity_all=True)
+    model = T.MatrixProductState(arrays, dtype=dtype, device="cuda:0")
+    model.normalize()
+    assert abs(float(model.norm()) - 1.0) <= (1e-10 if dtype == torch.float64 else 1e-4)
+    x, _ = _inputs(B, L, 0, dtype)
+    eng, _ = model._engine(T.FourierEmbedding(p=8), _heads()["nll"], False, dtype)
+    tol = 1e-10 if dtype == torch.float64 else 2e-5
+    _batch_properties(eng, model, x, None, tol=tol, denom_scale=10.0)
+    # |<A|phi>| <= ||A|| ||phi|| = 1  =>  -log(s^2) >= 0
+    per, _, _ = eng.forward(model._packed, x)
+    assert float(per.min()) >= -(1e-9 if dtype == torch.float64 else 1e-3)
+
+
+def test_cfg3_full_size_properties():
+    """SMPO L=784, spacing 8, chi=32, d=d_o=2, B=4096, float64 (the reference example's dtype, mnist_ad.py:241)."""
+    import tn4ml_b200 as T
+    L, S, chi, B = 784, 8, 32, 4096
+    arrays = O.make_smpo_arrays(L, chi, 2, 2, S, std=1e-2, seed=42, dtype=torch.float64)
+    model = T.SpacedMatrixProductOperator(arrays, spacing=S, dtype=torch.float64, device="cuda:0")
+    x, _ = _inputs(B, L, 0, torch.float64)
+    eng, _ = model._engine(T.TrigonometricEmbedding(), _heads()["logquad"], False, torch.float64)
+    _batch_properties(eng, model, x, None, tol=1e-10, denom_scale=10.0)
+    eng_t, _ = model._engine(T.TrigonometricEmbedding(), _heads()["tsn"], False, torch.float64)
+    per, _, _ = eng_t.forward(model._packed, x)
+    assert bool(torch.isfinite(per).all()) and float(per.min()) >= 0.0
+
+
+def test_cfg2_full_size_properties():
+    """MPS classifier L=30, polynomial d=3, chi=32, C=2 at site 14, weighted cross-entropy, B=65536, float64."""
+    import tn4ml_b200 as T
+    from tn4ml_b200 import metrics as M
+    L, chi, C, B = 30, 32, 2, 65536
+    arrays = O.make_mps_arrays(L, chi, 3, class_site=14, C=C, std=1e-2, seed=42, dtype=torch.float64)
+    model = T.TensorNetwork(arrays, dtype=torch.float64, device="cuda:0")
+    x, t = _inputs(B, L, C, torch.float64)
+    eng, _ = model._engine(T.PolynomialEmbedding(degree=2, n=1, include_bias=True), M.CrossEntropyWeighted([0.7, 1.6]), True,
+                           torch.float64)
+    _batch_properties(eng, model, x, t, tol=1e-10, denom_scale=10.0)
