@@ -315,8 +315,18 @@ def run_native(args):
         peak, peak_note = 40.0, "FP64 nominal 40 TFLOP/s (no measured figure on file), of nominal"
     k_flops = fps * B * share.get(top, 1 / 3) / max(mb_launches, 1)
     achieved = k_flops / (top_ms * 1e-3) / 1e12 if top_ms == top_ms else None
+    # DRAM traffic of the dominant kernel per launch: from the ncu --set full capture of the same problem at 296 sample
+    # tiles (profiles/r01d_full_capture.csv: dram read + write of tc_chain_kernel), scaled to this launch's tile count.
+    # Only for the profiled configuration; null otherwise.
+    traffic, traffic_note = None, None
+    ncu_gb_per_296_tiles = {"tc_chain_kernel(fwd)": 0.378655 + 7.633898, "tc_chain_kernel(adj)": 0.445621 + 7.622838}
+    if (dtype == torch.float32 and args.chi == 256 and args.L == 196 and args.classes == 10 and top in ncu_gb_per_296_tiles):
+        tiles = (B // max(mb_launches, 1) + 127) // 128
+        traffic = ncu_gb_per_296_tiles[top] * 1e9 * tiles / 296.0
+        traffic_note = "bytes per launch; ncu dram__bytes_read+write.sum at 296 tiles (profiles/r01d_full_capture.csv) x tiles/296"
     roofline = {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_note,
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_note,
+                "peak_source": peak_note,
                 "kernel_ms_avg": top_ms, "kernel_share_of_step": sum(per.get(top, [0])) / tot,
                 "step_tflops": fps * B / (ms_per_step * 1e-3) / 1e12,
                 "kernel_ms": {k: float(np.sum(v)) for k, v in per.items()},
