@@ -60,9 +60,80 @@ template <> __device__ __forceinline__ void sts_vec4<double>(double *p, const do
 // C[i0..i0+3][j0..j0+3] (+)= alpha * op(A) op(B), all chip x chip in shared memory with row stride ld (rows 16-byte
 // aligned).  Four k at a time: every operand is fetched with 16-byte loads along its contiguous direction
 // (8 vector loads per 64 FMAs instead of 32 scalar ones -- the scalar version was bound by the LSU, not the FMA pipe).
+// float64 on the FP64 tensor pipe: the same product with `mma.sync.m8n8k4.f64` warp tiles.  A sample's (chip/4)^2 threads
+// are whole warps for chip = 32 (2 warps) and 64 (8 warps); every warp owns 8 of the 8x8 output tiles (chip 32: two tile
+// rows x four columns, chip 64: one tile row x eight columns).  Per k-step of 4 a lane loads one element per A / B tile
+// (RPW + NTI loads for 8 MMAs = 2048 FMAs of the warp); the FMA version issued 64 FMAs and 8 vector loads per thread for
+// the same k-step, i.e. 8x the math instructions.
+template <int CHIP, bool TA, bool TB>
+__device__ __forceinline__ void mm_dmma(double *Cs, const double *As, const double *Bs, int ld, int lt, double alpha,
+                                        bool accum) {
+  constexpr int NTI = CHIP / 8, RPW = 8 / NTI;
+  const int wi = lt >> 5, lane = lt & 31, g = lane >> 2, t = lane & 3;
+  double c[RPW][NTI][2];
+#pragma unroll
+  for (int r = 0; r < RPW; ++r)
+#pragma unroll
+    for (int cn = 0; cn < NTI; ++cn) c[r][cn][0] = c[r][cn][1] = 0.0;
+#pragma unroll 2
+  for (int k0 = 0; k0 < CHIP; k0 += 4) {
+    const int k = k0 + t;
+    double a[RPW], b[NTI];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const int i = (wi * RPW + r) * 8 + g;
+      a[r] = TA ? As[k * ld + i] : As[i * ld + k];
+    }
+#pragma unroll
+    for (int cn = 0; cn < NTI; ++cn) {
+      const int j = cn * 8 + g;
+      b[cn] = TB ? Bs[j * ld + k] : Bs[k * ld + j];
+    }
+#pragma unroll
+    for (int r = 0; r < RPW; ++r)
+#pragma unroll
+      for (int cn = 0; cn < NTI; ++cn)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
+                     : "+d"(c[r][cn][0]), "+d"(c[r][cn][1])
+                     : "d"(a[r]), "d"(b[cn]));
+  }
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    const int i = (wi * RPW + r) * 8 + g;
+#pragma unroll
+    for (int cn = 0; cn < NTI; ++cn) {
+      double2 *dst = reinterpret_cast<double2 *>(&Cs[i * ld + cn * 8 + 2 * t]);
+      double2 o;
+      if (accum) {
+        const double2 old = *dst;
+        o.x = fma(alpha, c[r][cn][0], old.x);
+        o.y = fma(alpha, c[r][cn][1], old.y);
+      } else {
+        o.x = alpha * c[r][cn][0];
+        o.y = alpha * c[r][cn][1];
+      }
+      *dst = o;
+    }
+  }
+}
+
+template <typename T, bool TA, bool TB> struct MmTensor {
+  static __device__ __forceinline__ bool run(T *, const T *, const T *, int, int, int, int, T, bool) { return false; }
+};
+template <bool TA, bool TB> struct MmTensor<double, TA, TB> {
+  static __device__ __forceinline__ bool run(double *Cs, const double *As, const double *Bs, int chip, int ld, int i0,
+                                             int j0, double alpha, bool accum) {
+    const int lt = (i0 >> 2) * (chip >> 2) + (j0 >> 2);  // thread index inside the sample
+    if (chip == 32) { mm_dmma<32, TA, TB>(Cs, As, Bs, ld, lt, alpha, accum); return true; }
+    if (chip == 64) { mm_dmma<64, TA, TB>(Cs, As, Bs, ld, lt, alpha, accum); return true; }
+    return false;
+  }
+};
+
 template <typename T, bool TA, bool TB>
 __device__ __forceinline__ void mm(T *Cs, const T *As, const T *Bs, int chip, int ld, int i0, int j0, T alpha,
                                    bool accum) {
+  if (MmTensor<T, TA, TB>::run(Cs, As, Bs, chip, ld, i0, j0, alpha, accum)) return;
   T acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -118,11 +189,50 @@ __device__ __forceinline__ void mm(T *Cs, const T *As, const T *Bs, int chip, in
   }
 }
 
+template <typename T> __device__ __forceinline__ void ldg_pair(const T *p, T &a, T &b);
+template <> __device__ __forceinline__ void ldg_pair<float>(const float *p, float &a, float &b) {
+  const float2 v = __ldg(reinterpret_cast<const float2 *>(p));
+  a = v.x; b = v.y;
+}
+template <> __device__ __forceinline__ void ldg_pair<double>(const double *p, double &a, double &b) {
+  const double2 v = __ldg(reinterpret_cast<const double2 *>(p));
+  a = v.x; b = v.y;
+}
+
 // M[a][r] = sum_s phi[s] * A_site[a][r][s][o]   (this thread's 4x4 block)
 template <typename T>
 __device__ __forceinline__ void form_m(const SmpoArgs<T> &A, int site, int o, const T *phi, T *Ms, int i0, int j0) {
   const int nj = (site % A.S == 0) ? A.DO : 1;
   const T *P = A.params + smpo_site_off(A.chi, A.D, A.DO, A.S, site);
+  // d = 2, full 4x4 block inside the bond: the block's weights are 4 runs of 8 (leg-less site) or 16 (output site, both
+  // output indices interleaved) consecutive values; all of them are requested before the first is used.  (The scalar
+  // loop below -- a dependent load per (a, r, s) behind bounds checks -- was 46 % of the backward kernel's stall samples.)
+  if (A.D == 2 && nj <= 2 && i0 + 4 <= A.chi && j0 + 4 <= A.chi) {
+    T w[4][4][2];  // [i][j][s]
+    if (nj == 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const T *q = P + ((size_t)(i0 + i) * A.chi + j0) * 2;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ldg_pair<T>(q + 2 * j, w[i][j][0], w[i][j][1]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const T *q = P + ((size_t)(i0 + i) * A.chi + j0) * 4 + o;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          w[i][j][0] = __ldg(q + 4 * j);
+          w[i][j][1] = __ldg(q + 4 * j + 2);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Ms[(i0 + i) * A.ld + j0 + j] = fma(phi[1], w[i][j][1], phi[0] * w[i][j][0]);
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     int a = i0 + i;
@@ -285,6 +395,18 @@ __device__ __forceinline__ void accum_grad(const SmpoArgs<T> &A, int site, int o
   const int nj = (site % A.S == 0) ? A.DO : 1;
   T *g = A.grads + smpo_site_off(A.chi, A.D, A.DO, A.S, site);
   const int total = A.chi * A.chi * A.D;
+  const int CD = A.chi * A.D;
+  if ((int)blockDim.x % CD == 0) {  // a thread keeps its (r, s) column and walks the rows: no divisions in the loop
+    const int cidx = threadIdx.x % CD, astep = blockDim.x / CD;
+    const int r = cidx / A.D, sidx = cidx - r * A.D;
+    for (int a = threadIdx.x / CD; a < A.chi; a += astep) {
+      T v = T(0);
+      for (int q = 0; q < A.SPC; ++q)
+        v = fma(phi_s[((size_t)q * A.S + k) * A.D + sidx], mats[sample_stride * q + slot_off + (size_t)a * A.ld + r], v);
+      atomicAdd(&g[((size_t)(a * A.chi + r) * A.D + sidx) * nj + o], v);
+    }
+    return;
+  }
   for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
     int s = idx % A.D;
     int ar = idx / A.D;
