@@ -117,8 +117,81 @@ __device__ __forceinline__ void mm_dmma(double *Cs, const double *As, const doub
   }
 }
 
+// float32 on the tensor cores with fp32 accuracy: 3xTF32 (x = big + small, both TF32; big*big + big*small + small*big
+// accumulated in fp32) on `mma.sync.m16n8k8.tf32` warp tiles.  A warp owns one 16-row tile and four 8-column tiles of the
+// sample's output (chip 32: 2 warps per sample, chip 64: 8); 12 MMAs per k-step of 8 replace 128 FMAs per thread.
+__device__ __forceinline__ void tf32_split(float x, uint32_t &big, uint32_t &small) {
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(big) : "f"(x));
+  const float rest = x - __uint_as_float(big);
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(small) : "f"(rest));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+template <int CHIP, bool TA, bool TB>
+__device__ __forceinline__ void mm_tf32x3(float *Cs, const float *As, const float *Bs, int ld, int lt, float alpha,
+                                          bool accum) {
+  constexpr int NW = CHIP / 32;  // warps per 16-row tile
+  const int wi = lt >> 5, lane = lt & 31, g = lane >> 2, t = lane & 3;
+  const int i_base = (wi / NW) * 16, j_base = (wi % NW) * 32;
+  float c[4][4];
+#pragma unroll
+  for (int n = 0; n < 4; ++n)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) c[n][q] = 0.f;
+#pragma unroll 2
+  for (int k0 = 0; k0 < CHIP; k0 += 8) {
+    uint32_t ab[4], as_[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = i_base + g + (q & 1) * 8, k = k0 + t + (q >> 1) * 4;
+      tf32_split(TA ? As[k * ld + i] : As[i * ld + k], ab[q], as_[q]);
+    }
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      uint32_t bb[2], bs[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int k = k0 + t + q * 4, j = j_base + n * 8 + g;
+        tf32_split(TB ? Bs[j * ld + k] : Bs[k * ld + j], bb[q], bs[q]);
+      }
+      mma_tf32(c[n], as_, bb);
+      mma_tf32(c[n], ab, bs);
+      mma_tf32(c[n], ab, bb);
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < 4; ++n)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float2 *dst = reinterpret_cast<float2 *>(&Cs[(i_base + g + h * 8) * ld + j_base + n * 8 + 2 * t]);
+      float2 o;
+      if (accum) {
+        const float2 old = *dst;
+        o.x = fmaf(alpha, c[n][2 * h], old.x);
+        o.y = fmaf(alpha, c[n][2 * h + 1], old.y);
+      } else {
+        o.x = alpha * c[n][2 * h];
+        o.y = alpha * c[n][2 * h + 1];
+      }
+      *dst = o;
+    }
+}
+
 template <typename T, bool TA, bool TB> struct MmTensor {
   static __device__ __forceinline__ bool run(T *, const T *, const T *, int, int, int, int, T, bool) { return false; }
+};
+template <bool TA, bool TB> struct MmTensor<float, TA, TB> {
+  static __device__ __forceinline__ bool run(float *Cs, const float *As, const float *Bs, int chip, int ld, int i0, int j0,
+                                             float alpha, bool accum) {
+    const int lt = (i0 >> 2) * (chip >> 2) + (j0 >> 2);  // thread index inside the sample
+    if (chip == 32) { mm_tf32x3<32, TA, TB>(Cs, As, Bs, ld, lt, alpha, accum); return true; }
+    if (chip == 64) { mm_tf32x3<64, TA, TB>(Cs, As, Bs, ld, lt, alpha, accum); return true; }
+    return false;
+  }
 };
 template <bool TA, bool TB> struct MmTensor<double, TA, TB> {
   static __device__ __forceinline__ bool run(double *Cs, const double *As, const double *Bs, int chip, int ld, int i0,
