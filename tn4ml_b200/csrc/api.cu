@@ -108,7 +108,7 @@ template <typename T> static void fill_emb(const tnb_embedding &e, EmbParams<T> 
 // MPS workspace plan
 // ------------------------------------------------------------------------------------
 struct MpsPlan {
-  int chip, nslab, TN, NG, NT, BT, KT, WS;
+  int chip, nslab, TN, NG, NT, BT, KT, WS, dmma_sweep, dmma_class;
   size_t off_Wn, off_Wt, off_F, off_G, off_exps, off_esum, off_y, off_dy, off_wsimt, total;
   size_t smem_sweep, smem_class;
   int RB;  // register-tile rows of the SIMT sweep / class kernels
@@ -188,6 +188,7 @@ static MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
   if (kt_knob > 0) kt = kt_knob;
   P.KT = kt < 1 ? 1 : (kt > 16 ? 16 : (int)kt);
   if (P.KT > P.chip) P.KT = P.chip;
+  if (P.KT >= 4) P.KT = P.KT / 4 * 4;  // (whole k-steps of the DMMA step GEMM)
   P.WS = p->dtype == TNB_F64 ? P.NG * P.TN * kRN : P.chip;  // row stride of the kernel-layout weights (mps_prep_kernel)
   size_t slab = (size_t)P.chip * p->d * P.WS * w;
   size_t o = 0;
@@ -249,6 +250,16 @@ static MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
                  (size_t)P.BT * p->n_out) * w;
   P.smem_sweep = base;
   P.smem_class = base + (size_t)P.BT * P.chip * w;
+  // float64, d = 2, one column group, full 256-thread CTAs: the step GEMM runs as DMMA warp tiles and needs one more
+  // [BT][chip] tile behind everything else (TNB_SIMT_DMMA=0 keeps the FMA loop)
+  static const int dmma_knob = [] { const char *e = getenv("TNB_SIMT_DMMA"); return e ? atoi(e) : 1; }();
+  P.dmma_sweep = P.dmma_class = 0;
+  if (p->dtype == TNB_F64 && p->d == 2 && P.NG == 1 && P.RB == 4 && P.TN >= 8 && P.NT == 256 && P.KT % 4 == 0 && dmma_knob) {
+    P.dmma_sweep = (int)align_up(P.smem_sweep, 16);
+    P.dmma_class = (int)align_up(P.smem_class, 16);
+    P.smem_sweep = P.dmma_sweep + (size_t)P.BT * P.chip * w;
+    P.smem_class = P.dmma_class + (size_t)P.BT * P.chip * w;
+  }
   return P;
 }
 
@@ -267,7 +278,7 @@ static void fill_mps_args(const tnb_problem *p, const MpsPlan &P, long long B, c
   A.y = (T *)(w + P.off_y); A.dy = (T *)(w + P.off_dy);
   A.wq = (T *)(w + P.off_wsimt);
   A.loss = nullptr; A.loss_sum = nullptr; A.out = nullptr; A.out_exp = nullptr;
-  A.stash = 0; A.KT = P.KT; A.TN = P.TN; A.WS = P.WS; A.loss_scale = T(1); A.seed_only = 0;
+  A.stash = 0; A.KT = P.KT; A.TN = P.TN; A.WS = P.WS; A.dmma_sweep = P.dmma_sweep; A.dmma_class = P.dmma_class; A.loss_scale = T(1); A.seed_only = 0;
 }
 
 static void fill_tc_args(const MpsPlan &P, void *ws, const MpsArgs<float> &M, TcArgs &T) {

@@ -37,6 +37,7 @@ template <typename T> struct MpsArgs {
   int *out_exp; // [B]
   int stash;    // 1: every bond of F is stored (needed by backward)
   int KT, TN;
+  int dmma_sweep, dmma_class;  // byte offsets of the DMMA output tile in the sweep / class kernels' shared memory (0: off)
   int WS;        // shared-memory stride of one (k, s) weight row: chip, or NG*TN*4 for float64 (bank-conflict-free pair layout)
   T loss_scale;
   int seed_only;  // adjoint launch: write the seeds G[c], G[c+1] (and dy) only; the chains run elsewhere
@@ -70,13 +71,129 @@ template <> __device__ __forceinline__ void lds_pair<double>(const double *p, do
 
 constexpr int kRN = 4;  // register tile: RB rows (template parameter, 4 or 8) x kRN columns per thread
 
+// float64, d = 2, one column group, 256 threads: the step GEMM on the FP64 tensor pipe (`mma.sync.m8n8k4.f64`).
+// out[BT, 2*WS] = v[BT, K] x W[K, 2*WS] as 8x8 tiles; a warp owns 4 row tiles x 2 position tiles x both physical indices
+// (16 MMAs per k-step of 4 for 4 + 4 operand loads; the FMA loop issued 128 FMAs and 32 loads per thread for the same
+// work).  Columns are the POSITIONS of the pair layout (see step_gemm); phi is applied when the tile is written to
+// `out_s` in natural column order, from where every thread picks up its (tb, tn) register tile as before.
+template <int RB, bool ZERO>
+__device__ __forceinline__ void step_gemm_dmma(const double *__restrict__ Wg, int K, int chip, int KT, const double *v_s,
+                                               const double *phi_s, const double *rs_s, int rs_stride, double *W_s,
+                                               double *out_s, double (&acc)[1][RB][kRN], int tb, int tn, int TN, int WS) {
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int ncg = TN >> 2, wc = warp % ncg, wr = warp / ncg;
+  const int R0 = wr * 32, P0 = wc * 16;
+  const int row_elems = 2 * WS;
+  const int nchunks = (K + KT - 1) / KT;
+  auto issue = [&](int ch) {
+    int k0 = ch * KT;
+    int kt = min(KT, K - k0);
+    int n16 = (int)((size_t)kt * row_elems * sizeof(double) / 16);
+    const char *src = reinterpret_cast<const char *>(Wg + (size_t)k0 * row_elems);
+    char *dst = reinterpret_cast<char *>(W_s + (size_t)(ch & 1) * KT * row_elems);
+    for (int i = tid; i < n16; i += NT) cp_async16(dst + (size_t)i * 16, src + (size_t)i * 16);
+    cp_async_commit();
+  };
+  double c[4][2][2][2];  // [row tile][position tile][s][2]
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int q = 0; q < 2; ++q) c[r][p][q][0] = c[r][p][q][1] = 0.0;
+  issue(0);
+  for (int ch = 0; ch < nchunks; ++ch) {
+    if (ch + 1 < nchunks) {
+      issue(ch + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const int k0 = ch * KT;
+    const int kt = min(KT, K - k0);
+    const double *Wb = W_s + (size_t)(ch & 1) * KT * row_elems + P0 + g;
+    const double *va = v_s + (size_t)(R0 + g) * chip + k0 + t;
+#pragma unroll 2
+    for (int kk = 0; kk < kt; kk += 4) {
+      double a[4], b[2][2];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) a[r] = va[(size_t)(8 * r) * chip + kk];
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int p = 0; p < 2; ++p) b[p][q] = Wb[(size_t)((kk + t) * 2 + q) * WS + 8 * p];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
+                         : "+d"(c[r][p][q][0]), "+d"(c[r][p][q][1])
+                         : "d"(a[r]), "d"(b[p][q]));
+    }
+    __syncthreads();
+  }
+  // phi-weighted combination of the two physical indices -> out_s[row][n]
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int row = R0 + 8 * r + g;
+    const double rsv = rs_s ? rs_s[row * rs_stride] : 1.0;
+    const double r0 = rsv * phi_s[row * 2], r1 = rsv * phi_s[row * 2 + 1];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      const int pos = P0 + 8 * p + 2 * t;  // even: the two values are columns n, n + 1
+      const int half = pos / (TN * 2), rem = pos - half * TN * 2;
+      const int n = 4 * (rem >> 1) + 2 * half;
+      if (n < chip) {
+        double2 o;
+        o.x = fma(r0, c[r][p][0][0], r1 * c[r][p][1][0]);
+        o.y = fma(r0, c[r][p][0][1], r1 * c[r][p][1][1]);
+        *reinterpret_cast<double2 *>(&out_s[(size_t)row * chip + n]) = o;
+      }
+    }
+  }
+  __syncthreads();
+  if (tn * kRN < chip) {
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb)
+#pragma unroll
+      for (int rn = 0; rn < kRN; ++rn) {
+        const double v = out_s[(size_t)(tb * RB + rb) * chip + tn * kRN + rn];
+        acc[0][rb][rn] = ZERO ? v : acc[0][rb][rn] + v;
+      }
+  }
+}
+
+template <typename T, int NG, int RB, bool ZERO> struct StepDmma {
+  template <typename... Args> static __device__ __forceinline__ void run(Args...) {}
+  static constexpr bool kAvail = false;
+};
+template <int RB, bool ZERO> struct StepDmma<double, 1, RB, ZERO> {
+  static constexpr bool kAvail = true;
+  static __device__ __forceinline__ void run(const double *Wg, int K, int chip, int KT, const double *v_s,
+                                             const double *phi_s, const double *rs_s, int rs_stride, double *W_s,
+                                             double *out_s, double (&acc)[1][RB][kRN], int tb, int tn, int TN, int WS) {
+    step_gemm_dmma<RB, ZERO>(Wg, K, chip, KT, v_s, phi_s, rs_s, rs_stride, W_s, out_s, acc, tb, tn, TN, WS);
+  }
+};
+
 // acc[g][rb][rn] += sum_{k<K, s<D} v[row][k] * phi[row][s] * rs[row] * W[k][s][n]
 // W streamed from global through a double-buffered cp.async ring of KT k-rows.
 // ZERO: acc is known to be zero on entry (lets the d = 2 fast path drop it from the live registers).
 template <typename T, int NG, int RB, bool ZERO = false>
 __device__ __forceinline__ void step_gemm(const T *__restrict__ Wg, int K, int D, int chip, int KT,
                                           const T *v_s, const T *phi_s, const T *rs_s, int rs_stride,
-                                          T *W_s, T (&acc)[NG][RB][kRN], int tb, int tn, int TN, int WS) {
+                                          T *W_s, T (&acc)[NG][RB][kRN], int tb, int tn, int TN, int WS,
+                                          T *out_s = nullptr) {
+  if constexpr (StepDmma<T, NG, RB, ZERO>::kAvail) {
+    if (out_s != nullptr && D == 2) {
+      StepDmma<T, NG, RB, ZERO>::run(Wg, K, chip, KT, v_s, phi_s, rs_s, rs_stride, W_s, out_s, acc, tb, tn, TN, WS);
+      return;
+    }
+  }
   const int tid = threadIdx.x, NT = blockDim.x;
   const int row_elems = D * WS;  // one k-row, in global and in shared memory
   // float64: a thread's four columns n0..n0+3 are two 16-byte loads; at the natural stride of 32 bytes per thread the
@@ -244,6 +361,7 @@ __global__ void __launch_bounds__(256, (NG == 1 && RB == 4) ? 2 : 1) mps_sweep_k
   T *W_s = v_s + (size_t)BT * chip;
   T *phi_s = W_s + (size_t)2 * A.KT * D * A.WS;
   T *dy_s = phi_s + (size_t)BT * D;
+  T *out_s = A.dmma_sweep ? reinterpret_cast<T *>(smem_raw + A.dmma_sweep) : nullptr;  // DMMA output tile (float64)
   const int tid = threadIdx.x;
   const int tn = tid % TN, tb = tid / TN;
   const int half = blockIdx.y;
@@ -325,7 +443,7 @@ __global__ void __launch_bounds__(256, (NG == 1 && RB == 4) ? 2 : 1) mps_sweep_k
     const T *Wc = (half == 0 ? A.Wt : A.Wn) + (size_t)c * chip * D * A.WS;
     for (int k = 0; k < C; ++k)
       step_gemm<T, NG, RB>(Wc + (size_t)k * chip * D * A.WS, chip, D, chip, A.KT, v_s, phi_s, dy_s + k, C, W_s,
-                       acc, tb, tn, TN, A.WS);
+                       acc, tb, tn, TN, A.WS, out_s);
     T one[RB];
 #pragma unroll
     for (int rb = 0; rb < RB; ++rb) one[rb] = T(1);
@@ -340,7 +458,7 @@ __global__ void __launch_bounds__(256, (NG == 1 && RB == 4) ? 2 : 1) mps_sweep_k
     __syncthreads();
     zero_acc<T, NG, RB>(acc);
     const T *W = (transposed ? A.Wt : A.Wn) + (size_t)mps_slab(A, site) * chip * D * A.WS;
-    step_gemm<T, NG, RB, true>(W, chip, D, chip, A.KT, v_s, phi_s, (const T *)nullptr, 0, W_s, acc, tb, tn, TN, A.WS);
+    step_gemm<T, NG, RB, true>(W, chip, D, chip, A.KT, v_s, phi_s, (const T *)nullptr, 0, W_s, acc, tb, tn, TN, A.WS, out_s);
     T sc[RB];
     if (!adjoint) {
       T m[RB];
@@ -394,6 +512,7 @@ __global__ void __launch_bounds__(256, (NG == 1 && RB == 4) ? 2 : 1) mps_class_k
   T *phi_s = W_s + (size_t)2 * A.KT * D * A.WS;
   T *y_s = phi_s + (size_t)BT * D;
   T *fr_s = y_s + (size_t)BT * C;
+  T *out_s = A.dmma_class ? reinterpret_cast<T *>(smem_raw + A.dmma_class) : nullptr;
   __shared__ double red_s[8];
   const int tid = threadIdx.x;
   const int tn = tid % TN, tb = tid / TN;
@@ -408,7 +527,7 @@ __global__ void __launch_bounds__(256, (NG == 1 && RB == 4) ? 2 : 1) mps_class_k
   for (int k = 0; k < C; ++k) {
     zero_acc<T, NG, RB>(acc);
     step_gemm<T, NG, RB, true>(Wc + (size_t)k * chip * D * A.WS, chip, D, chip, A.KT, v_s, phi_s, (const T *)nullptr, 0,
-                     W_s, acc, tb, tn, TN, A.WS);
+                     W_s, acc, tb, tn, TN, A.WS, out_s);
 #pragma unroll
     for (int rb = 0; rb < RB; ++rb) {
       int r = tb * RB + rb;
