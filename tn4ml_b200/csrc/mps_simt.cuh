@@ -632,7 +632,17 @@ template <typename T, int RM> __global__ void __launch_bounds__(256) mps_da_kern
   const int us = uok ? um / chi : 0, ua = uok ? um - us * chi : 0;
   // float64: a thread's four V columns are two 16-byte loads; stored as [pair 0 | pair 1][tx][2] the 16 lanes read
   // consecutive 16-byte pieces (at the natural 32-byte stride they fall on half of the banks)
-  const int vpos = sizeof(T) == 8 ? ((vcol & 3) >> 1) * 32 + (vcol >> 2) * 2 + (vcol & 1) : vcol;
+  // float64 with the 128 x 64 tile: the product runs as DMMA warp tiles (mma.sync.m8n8k4.f64, a warp owns 4 x 4 of the
+  // 8x8 output tiles: 16 MMAs per k-step of 4 for 8 operand loads) on the natural V layout
+  constexpr bool kDmma = sizeof(T) == 8 && RM == 8;
+  const int vpos = (sizeof(T) == 8 && !kDmma) ? ((vcol & 3) >> 1) * 32 + (vcol >> 2) * 2 + (vcol & 1) : vcol;
+  const int lane = tid & 31, wg = lane >> 2, wt = lane & 3;
+  const int M0 = ((tid >> 5) & 3) * 32, N0 = (tid >> 7) * 32;  // this warp's 32 x 32 part of the tile
+  double cd[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cd[i][j][0] = cd[i][j][1] = 0.0;
   const T *Wq = A.wq + ((size_t)site * D + us) * A.B;
   T acc[RM][4];
 #pragma unroll
@@ -671,6 +681,23 @@ template <typename T, int RM> __global__ void __launch_bounds__(256) mps_da_kern
   for (long long bb = bbeg; bb < bend; bb += BK) {
     const bool more = bb + BK < bend;
     if (more) fetch(bb + BK);
+    if constexpr (kDmma) {
+#pragma unroll
+      for (int kk = 0; kk < BK; kk += 4) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = (double)U_s[kk + wt][M0 + 8 * i + wg];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = (double)V_s[kk + wt][N0 + 8 * j + wg];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
+                         : "+d"(cd[i][j][0]), "+d"(cd[i][j][1])
+                         : "d"(a[i]), "d"(b[j]));
+      }
+    } else {
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       T u[RM], v[4];
@@ -692,6 +719,7 @@ template <typename T, int RM> __global__ void __launch_bounds__(256) mps_da_kern
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fma(u[i], v[j], acc[i][j]);
     }
+    }
     __syncthreads();
     if (more) stage();
     __syncthreads();
@@ -699,16 +727,32 @@ template <typename T, int RM> __global__ void __launch_bounds__(256) mps_da_kern
   // scatter into the packed layout [a][r][s][k]
   const size_t site_off = (size_t)site * chi * chi * D + (site > c ? (size_t)chi * chi * D * (C - 1) : 0);
   T *g = P.grads + site_off;
+  if constexpr (kDmma) {
 #pragma unroll
-  for (int i = 0; i < RM; ++i) {
-    const int m = m0 + ty * RM + i;
-    if (m >= Mrows) continue;
-    const int s = m / chi, a = m - s * chi;
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + M0 + 8 * i + wg;
+      if (m >= Mrows) continue;
+      const int s = m / chi, a = m - s * chi;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int r = r0 + tx * 4 + j;
-      if (r >= chi) continue;
-      atomicAdd(&g[(((size_t)a * chi + r) * D + s) * nj + kcls], acc[i][j]);
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int r = r0 + N0 + 8 * j + 2 * wt + e;
+          if (r < chi) atomicAdd(&g[(((size_t)a * chi + r) * D + s) * nj + kcls], (T)cd[i][j][e]);
+        }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < RM; ++i) {
+      const int m = m0 + ty * RM + i;
+      if (m >= Mrows) continue;
+      const int s = m / chi, a = m - s * chi;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = r0 + tx * 4 + j;
+        if (r >= chi) continue;
+        atomicAdd(&g[(((size_t)a * chi + r) * D + s) * nj + kcls], acc[i][j]);
+      }
     }
   }
 }
