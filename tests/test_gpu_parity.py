@@ -166,3 +166,22 @@ def test_embedding_call_matches_oracle():
                  O.EmbSpec("rbf", gamma=0.5, centers=(0.1, 0.9))]:
         phi = _emb(spec)(x.numpy())
         assert torch.allclose(phi.cpu(), O.feature_map(x, spec), atol=1e-12)
+
+
+@pytest.mark.parametrize("case", [
+    dict(L=5, chi=32, cls=2, C=3, B=19000),    # TN = 8: four row groups of warps
+    dict(L=5, chi=40, cls=1, C=2, B=9600),     # padded positions (WS = 64 > chi)
+    dict(L=4, chi=64, cls=0, C=3, B=9500),     # class site on the boundary
+    dict(L=4, chi=128, cls=2, C=2, B=4800),    # TN = 32, one column group
+    dict(L=4, chi=136, cls=1, C=2, B=4800),    # two column groups (chi > 128)
+], ids=["chi32", "chi40", "chi64", "chi128", "chi136"])
+def test_mps_classifier_parity_f64_tensor_pipe(case):
+    """float64, d = 2, batches large enough for full 256-thread CTAs: the step GEMM of the sweep / class kernels and the
+    128 x 64 dA tile run as DMMA (mma.sync.m8n8k4.f64) warp tiles -- same 1e-10 bar as the FMA loops."""
+    import tn4ml_b200 as T
+    arrays = O.make_mps_arrays(case["L"], case["chi"], 2, class_site=case["cls"], C=case["C"], std=0.1, seed=11)
+    x = O.make_inputs(case["B"], case["L"], seed=12)
+    t = O.make_labels(case["B"], case["C"])
+    prob = O.Problem("mps", O.EmbSpec("trig"), "softmax_xent")
+    model = T.TensorNetwork(arrays, dtype=torch.float64, device="cuda:0")
+    _check(model, prob, _heads()["softmax_xent"], x, arrays, t, torch.float64)

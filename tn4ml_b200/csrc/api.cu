@@ -254,11 +254,16 @@ static MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
   // [BT][chip] tile behind everything else (TNB_SIMT_DMMA=0 keeps the FMA loop)
   static const int dmma_knob = [] { const char *e = getenv("TNB_SIMT_DMMA"); return e ? atoi(e) : 1; }();
   P.dmma_sweep = P.dmma_class = 0;
-  if (p->dtype == TNB_F64 && p->d == 2 && P.NG == 1 && P.RB == 4 && P.TN >= 8 && P.NT == 256 && P.KT % 4 == 0 && dmma_knob) {
-    P.dmma_sweep = (int)align_up(P.smem_sweep, 16);
-    P.dmma_class = (int)align_up(P.smem_class, 16);
-    P.smem_sweep = P.dmma_sweep + (size_t)P.BT * P.chip * w;
-    P.smem_class = P.dmma_class + (size_t)P.BT * P.chip * w;
+  if (p->dtype == TNB_F64 && p->d == 2 && P.NG <= 2 && P.RB == 4 && P.TN >= 8 && P.NT == 256 && P.KT % 4 == 0 && dmma_knob) {
+    const size_t tile = (size_t)P.BT * P.chip * w, cap = 200 * 1024;  // (each kernel only if it still fits)
+    if (align_up(P.smem_sweep, 16) + tile <= cap) {
+      P.dmma_sweep = (int)align_up(P.smem_sweep, 16);
+      P.smem_sweep = P.dmma_sweep + tile;
+    }
+    if (align_up(P.smem_class, 16) + tile <= cap) {
+      P.dmma_class = (int)align_up(P.smem_class, 16);
+      P.smem_class = P.dmma_class + tile;
+    }
   }
   return P;
 }

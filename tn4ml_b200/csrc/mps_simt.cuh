@@ -76,94 +76,109 @@ constexpr int kRN = 4;  // register tile: RB rows (template parameter, 4 or 8) x
 // (16 MMAs per k-step of 4 for 4 + 4 operand loads; the FMA loop issued 128 FMAs and 32 loads per thread for the same
 // work).  Columns are the POSITIONS of the pair layout (see step_gemm); phi is applied when the tile is written to
 // `out_s` in natural column order, from where every thread picks up its (tb, tn) register tile as before.
-template <int RB, bool ZERO>
+template <int NG, int RB, bool ZERO>
 __device__ __forceinline__ void step_gemm_dmma(const double *__restrict__ Wg, int K, int chip, int KT, const double *v_s,
                                                const double *phi_s, const double *rs_s, int rs_stride, double *W_s,
-                                               double *out_s, double (&acc)[1][RB][kRN], int tb, int tn, int TN, int WS) {
+                                               double *out_s, double (&acc)[NG][RB][kRN], int tb, int tn, int TN, int WS) {
   const int tid = threadIdx.x, NT = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int ncg = TN >> 2, wc = warp % ncg, wr = warp / ncg;
   const int R0 = wr * 32, P0 = wc * 16;
-  const int row_elems = 2 * WS;
+  const int GW = TN * 4;          // positions of one column group
+  const int srow = 2 * GW;        // one k-row of one group in shared memory: [s][GW]
+  const int grow = 2 * WS;        // one k-row in global memory: [s][NG groups][GW]
   const int nchunks = (K + KT - 1) / KT;
-  auto issue = [&](int ch) {
-    int k0 = ch * KT;
-    int kt = min(KT, K - k0);
-    int n16 = (int)((size_t)kt * row_elems * sizeof(double) / 16);
-    const char *src = reinterpret_cast<const char *>(Wg + (size_t)k0 * row_elems);
-    char *dst = reinterpret_cast<char *>(W_s + (size_t)(ch & 1) * KT * row_elems);
-    for (int i = tid; i < n16; i += NT) cp_async16(dst + (size_t)i * 16, src + (size_t)i * 16);
-    cp_async_commit();
-  };
-  double c[4][2][2][2];  // [row tile][position tile][s][2]
+  const int pieces = GW / 2;      // 16-byte pieces of one (k, s) segment (a power of two: TN is)
+  const int pshift = __ffs(pieces) - 1;
+  // column groups one after the other (chi > 128 has two): each streams its own part of the weight rows
+  for (int grp = 0; grp < NG; ++grp) {
+    auto issue = [&](int ch) {
+      const int k0 = ch * KT;
+      const int kt = min(KT, K - k0);
+      const int n16 = kt * 2 * pieces;
+      const double *src = Wg + (size_t)k0 * grow + (size_t)grp * GW;
+      double *dst = W_s + (size_t)(ch & 1) * KT * srow;
+      for (int i = tid; i < n16; i += NT) {
+        const int seg = i >> pshift, q = i & (pieces - 1);  // seg = k * 2 + s
+        cp_async16(reinterpret_cast<char *>(dst + (size_t)seg * GW) + q * 16,
+                   reinterpret_cast<const char *>(src + (size_t)seg * WS) + q * 16);
+      }
+      cp_async_commit();
+    };
+    double c[4][2][2][2];  // [row tile][position tile][s][2]
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < 4; ++r)
 #pragma unroll
-    for (int p = 0; p < 2; ++p)
+      for (int p = 0; p < 2; ++p)
 #pragma unroll
-      for (int q = 0; q < 2; ++q) c[r][p][q][0] = c[r][p][q][1] = 0.0;
-  issue(0);
-  for (int ch = 0; ch < nchunks; ++ch) {
-    if (ch + 1 < nchunks) {
-      issue(ch + 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
-    const int k0 = ch * KT;
-    const int kt = min(KT, K - k0);
-    const double *Wb = W_s + (size_t)(ch & 1) * KT * row_elems + P0 + g;
-    const double *va = v_s + (size_t)(R0 + g) * chip + k0 + t;
+        for (int q = 0; q < 2; ++q) c[r][p][q][0] = c[r][p][q][1] = 0.0;
+    issue(0);
+    for (int ch = 0; ch < nchunks; ++ch) {
+      if (ch + 1 < nchunks) {
+        issue(ch + 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+      const int k0 = ch * KT;
+      const int kt = min(KT, K - k0);
+      const double *Wb = W_s + (size_t)(ch & 1) * KT * srow + P0 + g;
+      const double *va = v_s + (size_t)(R0 + g) * chip + k0 + t;
 #pragma unroll 2
-    for (int kk = 0; kk < kt; kk += 4) {
-      double a[4], b[2][2];
+      for (int kk = 0; kk < kt; kk += 4) {
+        double a[4], b[2][2];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) a[r] = va[(size_t)(8 * r) * chip + kk];
+        for (int r = 0; r < 4; ++r) a[r] = va[(size_t)(8 * r) * chip + kk];
 #pragma unroll
-      for (int q = 0; q < 2; ++q)
+        for (int q = 0; q < 2; ++q)
 #pragma unroll
-        for (int p = 0; p < 2; ++p) b[p][q] = Wb[(size_t)((kk + t) * 2 + q) * WS + 8 * p];
+          for (int p = 0; p < 2; ++p) b[p][q] = Wb[(size_t)((kk + t) * 2 + q) * GW + 8 * p];
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
+        for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int p = 0; p < 2; ++p)
+          for (int p = 0; p < 2; ++p)
 #pragma unroll
-          for (int q = 0; q < 2; ++q)
-            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
-                         : "+d"(c[r][p][q][0]), "+d"(c[r][p][q][1])
-                         : "d"(a[r]), "d"(b[p][q]));
+            for (int q = 0; q < 2; ++q)
+              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
+                           : "+d"(c[r][p][q][0]), "+d"(c[r][p][q][1])
+                           : "d"(a[r]), "d"(b[p][q]));
+      }
+      __syncthreads();
     }
-    __syncthreads();
-  }
-  // phi-weighted combination of the two physical indices -> out_s[row][n]
+    // phi-weighted combination of the two physical indices -> out_s[row][n]
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int row = R0 + 8 * r + g;
-    const double rsv = rs_s ? rs_s[row * rs_stride] : 1.0;
-    const double r0 = rsv * phi_s[row * 2], r1 = rsv * phi_s[row * 2 + 1];
+    for (int r = 0; r < 4; ++r) {
+      const int row = R0 + 8 * r + g;
+      const double rsv = rs_s ? rs_s[row * rs_stride] : 1.0;
+      const double r0 = rsv * phi_s[row * 2], r1 = rsv * phi_s[row * 2 + 1];
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
-      const int pos = P0 + 8 * p + 2 * t;  // even: the two values are columns n, n + 1
-      const int half = pos / (TN * 2), rem = pos - half * TN * 2;
-      const int n = 4 * (rem >> 1) + 2 * half;
-      if (n < chip) {
-        double2 o;
-        o.x = fma(r0, c[r][p][0][0], r1 * c[r][p][1][0]);
-        o.y = fma(r0, c[r][p][0][1], r1 * c[r][p][1][1]);
-        *reinterpret_cast<double2 *>(&out_s[(size_t)row * chip + n]) = o;
+      for (int p = 0; p < 2; ++p) {
+        const int pos = P0 + 8 * p + 2 * t;  // even: the two values are columns n, n + 1
+        const int half = pos / (TN * 2), rem = pos - half * TN * 2;
+        const int n = grp * GW + 4 * (rem >> 1) + 2 * half;
+        if (n < chip) {
+          double2 o;
+          o.x = fma(r0, c[r][p][0][0], r1 * c[r][p][1][0]);
+          o.y = fma(r0, c[r][p][0][1], r1 * c[r][p][1][1]);
+          *reinterpret_cast<double2 *>(&out_s[(size_t)row * chip + n]) = o;
+        }
       }
     }
   }
   __syncthreads();
-  if (tn * kRN < chip) {
 #pragma unroll
-    for (int rb = 0; rb < RB; ++rb)
+  for (int grp = 0; grp < NG; ++grp) {
+    const int n0 = (grp * TN + tn) * kRN;
+    if (n0 < chip) {
 #pragma unroll
-      for (int rn = 0; rn < kRN; ++rn) {
-        const double v = out_s[(size_t)(tb * RB + rb) * chip + tn * kRN + rn];
-        acc[0][rb][rn] = ZERO ? v : acc[0][rb][rn] + v;
-      }
+      for (int rb = 0; rb < RB; ++rb)
+#pragma unroll
+        for (int rn = 0; rn < kRN; ++rn) {
+          const double v = out_s[(size_t)(tb * RB + rb) * chip + n0 + rn];
+          acc[grp][rb][rn] = ZERO ? v : acc[grp][rb][rn] + v;
+        }
+    }
   }
 }
 
@@ -171,12 +186,12 @@ template <typename T, int NG, int RB, bool ZERO> struct StepDmma {
   template <typename... Args> static __device__ __forceinline__ void run(Args...) {}
   static constexpr bool kAvail = false;
 };
-template <int RB, bool ZERO> struct StepDmma<double, 1, RB, ZERO> {
-  static constexpr bool kAvail = true;
+template <int NG, int RB, bool ZERO> struct StepDmma<double, NG, RB, ZERO> {
+  static constexpr bool kAvail = NG <= 2;
   static __device__ __forceinline__ void run(const double *Wg, int K, int chip, int KT, const double *v_s,
                                              const double *phi_s, const double *rs_s, int rs_stride, double *W_s,
-                                             double *out_s, double (&acc)[1][RB][kRN], int tb, int tn, int TN, int WS) {
-    step_gemm_dmma<RB, ZERO>(Wg, K, chip, KT, v_s, phi_s, rs_s, rs_stride, W_s, out_s, acc, tb, tn, TN, WS);
+                                             double *out_s, double (&acc)[NG][RB][kRN], int tb, int tn, int TN, int WS) {
+    step_gemm_dmma<NG, RB, ZERO>(Wg, K, chip, KT, v_s, phi_s, rs_s, rs_stride, W_s, out_s, acc, tb, tn, TN, WS);
   }
 };
 
@@ -190,7 +205,8 @@ __device__ __forceinline__ void step_gemm(const T *__restrict__ Wg, int K, int D
                                           T *out_s = nullptr) {
   if constexpr (StepDmma<T, NG, RB, ZERO>::kAvail) {
     if (out_s != nullptr && D == 2) {
-      StepDmma<T, NG, RB, ZERO>::run(Wg, K, chip, KT, v_s, phi_s, rs_s, rs_stride, W_s, out_s, acc, tb, tn, TN, WS);
+      // (a group's rows are 1/NG of the full rows the buffers were sized for: NG times the k-rows per chunk)
+      StepDmma<T, NG, RB, ZERO>::run(Wg, K, chip, KT * NG, v_s, phi_s, rs_s, rs_stride, W_s, out_s, acc, tb, tn, TN, WS);
       return;
     }
   }
