@@ -16,7 +16,10 @@
  *   - `stream` is a cudaStream_t passed as void*;
  *   - every call returns 0 on success, non-zero otherwise; the message is read
  *     with tnb_last_error() (thread-local); no exceptions cross the boundary;
- *   - all calls are re-entrant and CUDA-graph capturable.
+ *   - tnb_init(device) sets every per-device kernel attribute; after it (or after the first call on that device,
+ *     which does the same under a lock) tnb_forward / tnb_backward / tnb_adam_update are re-entrant (no mutable
+ *     globals on the call path, no environment reads: measurement knobs are read once when the library is loaded)
+ *     and CUDA-graph capturable (tests/test_gpu_boundary.py captures and replays a step).
  */
 #ifndef TN4ML_B200_H
 #define TN4ML_B200_H
@@ -90,11 +93,24 @@ typedef struct tnb_problem {
 const char *tnb_version(void);
 const char *tnb_last_error(void);
 
+/* Per-device setup (opt-in shared-memory attributes of every kernel): call once per device before capturing a CUDA
+ * graph or calling from several threads.  Idempotent.  The XLA-FFI shim calls it from its `instantiate` stage. */
+int tnb_init(int32_t device);
+
 /* Number of elements of the packed parameter (and gradient) buffer. */
 int64_t tnb_param_count(const tnb_problem *prob);
 /* Element offset of site `site` inside the packed buffer, and its n_i. */
 int64_t tnb_site_offset(const tnb_problem *prob, int32_t site);
 int32_t tnb_site_nout(const tnb_problem *prob, int32_t site);
+
+/* Ragged reference-shaped site tensors <-> the packed layout.  sites[i] is a DEVICE pointer to site i,
+ * C-contiguous (chi_l[i], chi_r[i], d, n_i) -- tn4ml/models/mps.py:106-151 shapes with the squeezed boundary bonds
+ * given as 1; `packed` holds tnb_param_count elements.  pack zero-fills the padding; unpack reads the same region of
+ * a packed gradient back into reference-shaped buffers (value_and_grad returns one array per site, model.py:554-566). */
+int tnb_pack_params(const tnb_problem *prob, const void *const *sites, const int32_t *chi_l, const int32_t *chi_r,
+                    void *packed, void *stream);
+int tnb_unpack_grads(const tnb_problem *prob, const void *packed, void *const *sites, const int32_t *chi_l,
+                     const int32_t *chi_r, void *stream);
 
 /* Bytes of caller-provided device scratch for a batch of `batch` samples.
  * need_grad = 0: forward only (evaluate / predict); 1: forward + backward. */
@@ -142,6 +158,10 @@ int32_t tnb_profile_read(char *names, float *ms, int32_t max_records);
 
 /* Number of kernel launches issued by this library since load (all threads). */
 int64_t tnb_launch_count(void);
+
+/* 1 when the XLA-FFI handler symbols of csrc/xla_ffi_shim.cc (forward and backward) were compiled in (the build found
+ * xla/ffi/api/ffi.h), else 0.  See INTEGRATION.md. */
+int32_t tnb_ffi_available(void);
 
 #ifdef __cplusplus
 }

@@ -45,6 +45,10 @@ _P = C.POINTER
 SYMBOLS = {
     "tnb_version": (C.c_char_p, []),
     "tnb_last_error": (C.c_char_p, []),
+    "tnb_init": (C.c_int, [C.c_int32]),
+    "tnb_ffi_available": (C.c_int32, []),
+    "tnb_pack_params": (C.c_int, [_P(TnbProblem), _P(C.c_void_p), _P(C.c_int32), _P(C.c_int32), C.c_void_p, C.c_void_p]),
+    "tnb_unpack_grads": (C.c_int, [_P(TnbProblem), C.c_void_p, _P(C.c_void_p), _P(C.c_int32), _P(C.c_int32), C.c_void_p]),
     "tnb_param_count": (C.c_int64, [_P(TnbProblem)]),
     "tnb_site_offset": (C.c_int64, [_P(TnbProblem), C.c_int32]),
     "tnb_site_nout": (C.c_int32, [_P(TnbProblem), C.c_int32]),

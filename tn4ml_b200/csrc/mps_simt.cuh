@@ -12,6 +12,7 @@
 //   equal the reference's unscaled arithmetic to rounding.
 #pragma once
 #include "common.cuh"
+#include "consts.h"
 
 namespace tnb {
 
@@ -69,7 +70,7 @@ template <> __device__ __forceinline__ void lds_pair<double>(const double *p, do
   a = v.x; b = v.y;
 }
 
-constexpr int kRN = 4;  // register tile: RB rows (template parameter, 4 or 8) x kRN columns per thread
+// kRN (consts.h): register tile of RB rows (template parameter, 4 or 8) x kRN columns per thread
 
 // float64, d = 2, one column group, 256 threads: the step GEMM on the FP64 tensor pipe (`mma.sync.m8n8k4.f64`).
 // out[BT, 2*WS] = v[BT, K] x W[K, 2*WS] as 8x8 tiles; a warp owns 4 row tiles x 2 position tiles x both physical indices

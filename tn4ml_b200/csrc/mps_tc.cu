@@ -1,0 +1,220 @@
+// tcgen05 family of the MPS path (float32, TNB_PREC_TENSOR): host-side launch code.
+// Kernels: mps_tc.cuh (weight images, dA GEMM) and mps_tc_chain.cuh (chain kernel).  Entry points in host.h.
+#include "host.h"
+#include "mps_args.h"
+#include "mps_tc.cuh"
+
+namespace tnb {
+
+static void fill_tc_args(const MpsPlan &P, void *ws, const MpsArgs<float> &M, TcArgs &T) {
+  char *w = (char *)ws;
+  T.M = M;
+  T.img_n = (const uint8_t *)(w + P.off_img_n);
+  T.img_t = (const uint8_t *)(w + P.off_img_t);
+  T.kW = (const int *)(w + P.off_kW);
+  T.tile0 = 0;
+  T.cg = P.tc_cg;
+#ifdef TNB_TC_TRACE
+  T.dbg = knobs().tc_dbg;
+#endif
+  T.colsum = (const float *)(w + P.off_cs);
+  T.pace_ns = knobs().tc_pace_ns >= 0 ? knobs().tc_pace_ns : P.tc_N * 2 / 5;
+  T.wq = (float *)(w + P.off_wq);
+  T.qmax = (int *)(w + P.off_qmax);
+  T.wqc = (float *)(w + P.off_wqc);
+  T.fimg = (uint8_t *)(w + P.off_fimg);
+  T.gimg = M.stash ? (uint8_t *)(w + P.off_gimg) : nullptr;
+  T.img_bond_bytes = P.img_bond_bytes;
+  T.img_stash = M.stash;
+  T.qmaxc = T.qmax + M.L;
+  T.N = P.tc_N; T.NH = P.tc_NH; T.NMMA = P.tc_NMMA; T.nstage = P.tc_nstage; T.tmem_cols = P.tc_cols;
+  T.stage_bytes = P.tc_stage_bytes; T.site_img_bytes = P.tc_site_img;
+}
+
+template <int D, int SLOTS, int TILES, int CG> static cudaError_t tc_set_attr() {
+  return cudaFuncSetAttribute(tc_chain_kernel<D, SLOTS, TILES, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax);
+}
+
+// every instantiation tc_launch_sweep can reach + the dA GEMM, for the current device
+cudaError_t mps_tc_set_attrs() {
+  cudaError_t e = tc_set_attr<2, 4, 1, 2>();
+  if (e == cudaSuccess) e = tc_set_attr<2, 4, 1, 1>();
+  if (e == cudaSuccess) e = tc_set_attr<2, 2, 1, 1>();
+  if (e == cudaSuccess) e = tc_set_attr<2, 2, 2, 1>();
+  if (e == cudaSuccess) e = tc_set_attr<3, 4, 1, 1>();
+  if (e == cudaSuccess) e = tc_set_attr<3, 2, 1, 1>();
+  if (e == cudaSuccess) e = tc_set_attr<4, 2, 1, 1>();
+  if (e == cudaSuccess) e = tc_set_attr<4, 2, 2, 1>();
+  if (e == cudaSuccess) e = tc_set_attr<6, 2, 1, 1>();
+  if (e == cudaSuccess) e = tc_set_attr<8, 2, 1, 1>();
+  if (e == cudaSuccess) e = tc_set_attr<8, 2, 2, 1>();
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(tc_da_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax - 2048);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(tc_da_kernel<kDaMaxCpg>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax - 2048);
+  return e;
+}
+
+template <int D, int SLOTS, int TILES, int CG = 1>
+static cudaError_t tc_launch_one(long long ntiles, long long tile0, size_t smem, TcArgs T, int adjoint, cudaStream_t st) {
+  if (ntiles <= 0) return cudaSuccess;
+  T.tile0 = tile0 * kTcRows;
+  if (CG == 1) {
+    dim3 grid((unsigned)(ntiles / TILES), adjoint ? 2 : 1);
+    tc_chain_kernel<D, SLOTS, TILES, CG><<<grid, kTcThreads, smem, st>>>(T, adjoint);
+    return cudaSuccess;
+  }
+  // CTA pair: clusters of two CTAs along x (consecutive sample tiles); an odd tile count gets an all-padding tile
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((ntiles + 1) / 2 * 2), adjoint ? 2 : 1);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, tc_chain_kernel<D, SLOTS, TILES, CG>, T, adjoint);
+}
+
+// launch the tcgen05 sweep (forward environments or adjoint chains)
+static int tc_launch_sweep(const tnb_problem *p, const MpsPlan &P, const TcArgs &T, long long B, int adjoint,
+                           cudaStream_t st) {
+  cudaError_t e = cudaSuccess;
+  const bool wide = p->chi > 128;   // 16-column groups per epilogue thread: 4 (chi <= 256) or 2 (chi <= 128)
+  const long long ntiles = (B + kTcRows - 1) / kTcRows;
+  // Two-tile CTAs take whole rounds of 148 SMs (per half of the adjoint grid); the remaining tiles run as one-tile
+  // CTAs behind them, so that the last round is not half empty with double-length CTAs.
+  long long npair = 0;
+  if (P.tc_tiles == 2) {
+    const long long per_round = 2LL * 148 / (adjoint ? 2 : 1);
+    npair = ntiles / per_round * per_round;
+    if (ntiles - npair > per_round / 2) npair = ntiles / 2 * 2;  // the rest would need two more rounds anyway
+  }
+#define TNB_TC_GO(DD, SS)                                                                                     \
+  do {                                                                                                        \
+    if (npair > 0) e = tc_launch_one<DD, SS, 2>(npair, 0, P.tc_smem, T, adjoint, st);                         \
+    if (e == cudaSuccess && ntiles > npair) e = tc_launch_one<DD, SS, 1>(ntiles - npair, npair, P.tc_smem, T, adjoint, st); \
+  } while (0)
+#define TNB_TC_GO1(DD, SS) e = tc_launch_one<DD, SS, 1>(ntiles, 0, P.tc_smem, T, adjoint, st)
+#define TNB_TC_PAIR(DD, SS) e = tc_launch_one<DD, SS, 1, 2>(ntiles, 0, P.tc_smem, T, adjoint, st)
+  prof_begin(st);
+  switch (p->d) {
+    case 2:
+      if (wide && P.tc_cg == 2) TNB_TC_PAIR(2, 4);
+      else if (wide) TNB_TC_GO1(2, 4);
+      else TNB_TC_GO(2, 2);
+      break;
+    case 3: if (wide) TNB_TC_GO1(3, 4); else TNB_TC_GO1(3, 2); break;
+    case 4: TNB_TC_GO(4, 2); break;
+    case 6: TNB_TC_GO1(6, 2); break;
+    case 8: TNB_TC_GO(8, 2); break;
+    default: return fail("tensor path: unsupported physical dimension %d", p->d);
+  }
+#undef TNB_TC_GO
+#undef TNB_TC_GO1
+#undef TNB_TC_PAIR
+  if (e != cudaSuccess) return fail("tc_chain launch: %s", cudaGetErrorString(e));
+  TNB_LAUNCH_CHECK(adjoint ? "tc_chain_kernel(adj)" : "tc_chain_kernel(fwd)");
+  return 0;
+}
+
+int mps_tc_forward(const tnb_problem *p, const MpsPlan &P, long long B, const void *x, const void *targets,
+                   const void *params, void *loss, double *loss_sum, void *out, int32_t *out_exp, int keep_stash,
+                   void *ws, cudaStream_t st) {
+  MpsArgs<float> A;
+  fill_mps_args<float>(p, P, B, x, targets, ws, A);
+  A.stash = keep_stash ? 1 : 0;
+  A.loss = (float *)loss; A.loss_sum = loss_sum; A.out = (float *)out; A.out_exp = out_exp;
+  // weight images, then ONE kernel for both chains, the class site and the head
+  TcArgs Tc;
+  fill_tc_args(P, ws, A, Tc);
+  prof_begin(st);
+  tc_sitemax_kernel<<<P.nslab, 256, 0, st>>>((const float *)params, (int *)Tc.kW, p->L, p->chi, p->d, p->n_out,
+                                             p->out_site);
+  TNB_LAUNCH_CHECK("tc_sitemax_kernel");
+  if (p->n_out > 1) {
+    prof_begin(st);
+    tc_classmin_kernel<<<1, 32, 0, st>>>((int *)Tc.kW, p->out_site, p->n_out);
+    TNB_LAUNCH_CHECK("tc_classmin_kernel");
+  }
+  prof_begin(st);
+  tc_colsum_kernel<<<dim3(P.nslab, 2), 256, 0, st>>>((const float *)params, Tc.kW, (float *)Tc.colsum, p->L, p->chi,
+                                                     p->d, p->n_out, p->out_site);
+  TNB_LAUNCH_CHECK("tc_colsum_kernel");
+  size_t items = (size_t)P.tc_N * (p->chi / 8) * P.nslab;
+  int ib = (int)((items + 255) / 256);
+  if (ib > 148 * 32) ib = 148 * 32;
+  prof_begin(st);
+  tc_image_kernel<<<ib, 256, 0, st>>>((const float *)params, Tc.kW, (uint8_t *)Tc.img_n, (uint8_t *)Tc.img_t, p->L,
+                                      p->chi, p->d, p->n_out, p->out_site, P.tc_NH, P.tc_cg);
+  TNB_LAUNCH_CHECK("tc_image_kernel");
+  return tc_launch_sweep(p, P, Tc, B, 0, st);
+}
+
+int mps_tc_backward(const tnb_problem *p, const MpsPlan &P, long long B, const void *x, const void *targets,
+                    double loss_scale, void *grads, int accumulate, void *ws, cudaStream_t st) {
+  MpsArgs<float> A;
+  fill_mps_args<float>(p, P, B, x, targets, ws, A);
+  A.stash = 1;
+  A.loss_scale = (float)loss_scale;
+  if (!accumulate) TNB_CUDA(cudaMemsetAsync(grads, 0, (size_t)tnb_param_count(p) * sizeof(float), st));
+  TcArgs Tc;
+  fill_tc_args(P, ws, A, Tc);
+  TNB_CUDA(cudaMemsetAsync(Tc.qmax, 0x80, ((size_t)p->L + 1) * sizeof(int), st));
+  if (tc_launch_sweep(p, P, Tc, B, 1, st)) return 1;  // seeds through the class site + adjoint chains
+  TcDaArgs Da;
+  Da.M = A;
+  Da.grads = (float *)grads;
+  Da.fimg = Tc.fimg;
+  Da.gimg = Tc.gimg;
+  Da.img_bond_bytes = Tc.img_bond_bytes;
+  Da.nstage = (int)((kTcSmemMax - 2048 - 1024) / kDaStage);
+  if (knobs().da_stages >= 2 && knobs().da_stages < Da.nstage) Da.nstage = knobs().da_stages;
+  Da.tmem_cols = 32;
+  while (Da.tmem_cols < 2 * p->chi) Da.tmem_cols <<= 1;
+  const long long maxsp = (B + 2047) / 2048;
+  Da.ra = p->chi < 128 ? p->chi : 128;
+  Da.cpg = 256 / Da.ra;
+  for (int pass = 0; pass < 2; ++pass) {
+    // pass 0: every chain site (copies sigma = s);  pass 1: the class site (copies sigma = (s, k))
+    Da.Dv = pass == 0 ? p->d : p->d * p->n_out;
+    Da.only_site = pass == 0 ? -1 : p->out_site;
+    Da.wq = pass == 0 ? Tc.wq : Tc.wqc;
+    Da.qmax = pass == 0 ? Tc.qmax : Tc.qmaxc;
+    Da.mgroups = ((p->chi + Da.ra - 1) / Da.ra) * ((Da.Dv + Da.cpg - 1) / Da.cpg);
+    // split K (the batch) so that the grid fills the 148 SMs about four times over with little wave quantisation
+    const long long ctas = (long long)(pass == 0 ? p->L - 1 : 1) * Da.mgroups;
+    long long best = 1;
+    double best_eff = 0.0;
+    for (long long nsp = 1; nsp <= maxsp && nsp <= 64; ++nsp) {
+      const long long n = ctas * nsp;
+      const double eff = (double)n / (double)((n + 147) / 148 * 148);
+      const double score = eff - (n < 148 * 3 ? 1.0 : 0.0) - 0.002 * (double)nsp;  // prefer >= 3 waves, fewer splits
+      if (nsp == 1 || score > best_eff) { best = nsp; best_eff = score; }
+    }
+    Da.nsplit = (int)best;
+    Da.bchunk = ((B + Da.nsplit - 1) / Da.nsplit + kDaKC - 1) / kDaKC * kDaKC;
+    dim3 gda((unsigned)(Da.mgroups * Da.nsplit), (unsigned)(pass == 0 ? p->L : 1));
+    prof_begin(st);
+    const size_t da_smem = (size_t)Da.nstage * kDaStage + 1024;
+    if (Da.cpg == 2) tc_da_kernel<2><<<gda, kDaThreads, da_smem, st>>>(Da);
+    else tc_da_kernel<kDaMaxCpg><<<gda, kDaThreads, da_smem, st>>>(Da);
+    TNB_LAUNCH_CHECK(pass == 0 ? "tc_da_kernel" : "tc_da_kernel(class)");
+  }
+  return 0;
+}
+
+#ifdef TNB_TC_TRACE
+/* measurement build only: copy the in-kernel timeline of the chain kernel (mps_tc_chain.cuh) to the host */
+extern "C" int tnb_debug_trace_read(long long *host, int32_t n) {
+  if (n > 64 * 32) n = 64 * 32;
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(host, tnb::g_tc_trace, (size_t)n * sizeof(long long)) == cudaSuccess ? 0 : 1;
+}
+#endif
+
+}  // namespace tnb

@@ -28,12 +28,7 @@
 
 namespace tnb {
 
-constexpr int kTcRows = 128;   // samples per CTA == TMEM lanes
-constexpr int kTcKA = 14;      // A operand pre-scale: |v| < 1  ->  |v * 2^14| < 2^14 (fp16 max 65504)
-constexpr int kTcEpiWarps = 16;                      // 4 lane quarters x 4 column groups
-constexpr int kTcMmaWarp = kTcEpiWarps;              // + 1: weight producer warp, + 2: image writer warp
-constexpr int kTcThreads = (kTcEpiWarps + 3) * 32;
-constexpr int kTcMaxNH = 16;                         // column chunks per step (chi / 16 at most)
+// geometry constants (kTcRows, kTcKA, kTcEpiWarps, kTcMmaWarp, kTcThreads, kTcMaxNH): consts.h
 
 struct TcArgs {
   MpsArgs<float> M;
@@ -43,7 +38,9 @@ struct TcArgs {
   const float *colsum;   // [2 directions][slab]: max_n sum_{k,s} |W[k,s,n]| * 2^kW  (bound of one chain step, see chain kernel)
   int pace_ns;           // image writer: pause between 4 KB pieces
   int cg;                // CTAs per MMA: 1, or 2 (CTA pair; stage_bytes is then one CTA's half of a stage)
-  int dbg;               // measurement switches (trace builds only; TNB_TC_DBG)
+#ifdef TNB_TC_TRACE
+  int dbg;               // timing-experiment switches (TNB_TC_DBG): -DTNB_TC_TRACE builds only, absent from the release library
+#endif
   long long tile0;       // first sample of this launch (a sweep may be split into a two-tile and a one-tile launch)
   float *wq;             // adjoint: phi_s[b] * 2^q[b] per (site, s, b): per-sample weight of the dA GEMM
   int *qmax;             // adjoint: max_b q[site][b]
@@ -225,19 +222,7 @@ struct TcDaArgs {
   int only_site;     // >= 0: this site only (the class site; wq/qmax point at its own tables)
 };
 
-#ifndef TNB_DA_KC
-#define TNB_DA_KC 32
-#endif
-constexpr int kDaKC = TNB_DA_KC;                  // samples per pipeline stage (a multiple of the MMA's K = 16)
-constexpr int kDaProducers = 512;                 // threads (16 warps)
-constexpr int kDaThreads = kDaProducers + 64;     // + MMA warp + bulk-copy warp
-constexpr int kDaMaxCpg = 8;                      // chi >= 32
-// U operand of a stage: a "virtual bond image" of 256 rows, [kDaKC/8 sample blocks][plane hi|lo][32 row octets][8 samples][16 B]
-constexpr uint32_t kDaUPlane = 32u * 128u;        // 4 KB
-constexpr uint32_t kDaUBlock = 2u * kDaUPlane;    // 8 KB: K-block (8 samples) stride
-constexpr uint32_t kDaU = (kDaKC / 8) * kDaUBlock;  // 16 KB
-constexpr uint32_t kDaBMax = 256u * 4u * kDaKC;   // V region: a raw image chunk of kDaKC samples
-constexpr uint32_t kDaStage = kDaU + kDaBMax;     // 64 KB (32 samples): 3 stages
+// stage geometry of the dA GEMM (kDaKC, kDaProducers, kDaThreads, kDaMaxCpg, kDaU*, kDaStage): consts.h
 
 #ifdef TNB_TC_TRACE
 #define TNB_DA_TRACE(ch_, ev)                                                                              \

@@ -66,10 +66,12 @@ __device__ long long g_tc_trace[64 * 32];
       g_tc_trace[((step_)-20) * 64 + (who)*16 + (ev)] = (val);                                                  \
   } while (0)
 #define TNB_CLOCK() clock64()
+#define TNB_DBG(bit) (A.dbg & (bit))   // timing experiments of the trace build (TNB_TC_DBG); some give wrong results
 #else
 #define TNB_TRACE(who, step_, ev) do { } while (0)
 #define TNB_TRACE_SET(who, step_, ev, val) do { } while (0)
 #define TNB_CLOCK() 0ll
+#define TNB_DBG(bit) 0                 // release builds carry none of the experiment switches
 #endif
 
 // acc columns -> o[j] = sum_s ph[s] * acc[col + s*cstride + j], j < 16   (one 16-column group).
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       const unsigned pace = (unsigned)(A.pace_ns > 0 ? (krel > 0 ? A.pace_ns / 2 : A.pace_ns) : 0);
       for (int g = 0; g <= total; ++g) {
         const int bond = g > 0 ? step_out_bond(g - 1) : -1;
-        const bool on = bond >= 0 && base && !(A.dbg & 2);
+        const bool on = bond >= 0 && base && !TNB_DBG(2);
 #pragma unroll
         for (int t = 0; t < TILES; ++t) {
           ptx::mbar_wait(&a_ready[t], g & 1);
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
         for (int t = 0; t < TILES; ++t) {
           for (int hk = 0; hk < per_step; ++hk) {
             ptx::mbar_wait(&empty[stage], phase ^ 1);
-            const uint32_t nbytes = (A.dbg & 16) ? 1024u : A.stage_bytes;  // (timing experiment: short loads, wrong results)
+            const uint32_t nbytes = TNB_DBG(16) ? 1024u : A.stage_bytes;  // (trace-build experiment: short loads, wrong results)
             ptx::mbar_expect_tx(&full[stage], nbytes);
             // (CTA pair: the stage image is [rank][plane][columns / 2]; each CTA fetches its own half)
             ptx::bulk_g2s(stages + (size_t)stage * A.stage_bytes, img + ((size_t)hk * CG + rank) * A.stage_bytes,
@@ -374,7 +376,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
               const long long c0 = TNB_CLOCK();
               ptx::mbar_wait(&full[stage], phase);
               const long long c1 = TNB_CLOCK();
-              if (CG == 2 && !(A.dbg & 4)) ptx::mbar_wait(&pfull[stage], phase);
+              if (CG == 2 && !TNB_DBG(4)) ptx::mbar_wait(&pfull[stage], phase);
               const long long c2 = TNB_CLOCK();
               (void)c0; (void)c1; (void)c2;
               ptx::tc_fence_after();

@@ -12,6 +12,7 @@
 // SPC samples per CTA; every sample-local matrix lives in shared memory (row stride ld).
 #pragma once
 #include "common.cuh"
+#include "consts.h"
 #include "mps_simt.cuh"  // lds_vec
 
 namespace tnb {
@@ -650,17 +651,11 @@ static void fill_smpo_args(const tnb_problem *p, const SmpoPlan &P, long long B,
   A.loss_scale = T(1); A.stash = 0; A.SPC = P.SPC; A.TPS = P.TPS;
 }
 
-template <typename T> static int smpo_set_attrs(const char **what) {
-  static std::once_flag once;
-  static cudaError_t err = cudaSuccess;
-  std::call_once(once, [] {
-    cudaError_t e = cudaFuncSetAttribute(smpo_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(smpo_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
-    err = e;
-  });
-  if (err != cudaSuccess) { *what = cudaGetErrorString(err); return 1; }
-  return 0;
+template <typename T> static cudaError_t smpo_set_attrs_t() {
+  cudaError_t e = cudaFuncSetAttribute(smpo_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmpoSmemMax);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(smpo_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmpoSmemMax);
+  return e;
 }
 
 template <typename T>
@@ -668,7 +663,6 @@ static int smpo_forward_t(const tnb_problem *p, const SmpoPlan &P, long long B, 
                           void *loss, double *loss_sum, void *out, int32_t *out_exp, int keep_stash, void *ws,
                           cudaStream_t st, const char **what) {
   if (P.SPC < 1) { *what = "bond dimension too large for the SMPO shared-memory plan"; return 1; }
-  if (smpo_set_attrs<T>(what)) return 1;
   SmpoArgs<T> A;
   fill_smpo_args<T>(p, P, B, x, params, ws, A);
   A.stash = keep_stash ? 1 : 0;
@@ -684,7 +678,6 @@ static int smpo_backward_t(const tnb_problem *p, const SmpoPlan &P, long long B,
                            double loss_scale, void *grads, int accumulate, void *ws, cudaStream_t st,
                            const char **what) {
   if (P.SPC < 1) { *what = "bond dimension too large for the SMPO shared-memory plan"; return 1; }
-  if (smpo_set_attrs<T>(what)) return 1;
   SmpoArgs<T> A;
   fill_smpo_args<T>(p, P, B, x, params, ws, A);
   A.stash = 1;

@@ -37,6 +37,7 @@ class Engine:
             raise RuntimeError("tn4ml_b200 runs on CUDA devices only (no CPU fallback)")
         self.lib = _lib.lib()
         self.dtype, self.device = dtype, device
+        _lib.check(self.lib.tnb_init(device.index if device.index is not None else torch.cuda.current_device()))
         p = _lib.TnbProblem()
         p.kind, p.dtype, p.precision = kind, _dtype_code(dtype), precision
         p.L, p.chi, p.d, p.n_out, p.out_site, p.spacing = L, chi, d, n_out, out_site, max(spacing, 1)

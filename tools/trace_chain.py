@@ -17,9 +17,8 @@ SO = os.path.join(ROOT, "tools", "libtn4ml_b200_trace.so")
 
 
 def build():
-    cmd = ["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-DTNB_TC_TRACE", os.path.join(ROOT, "tn4ml_b200/csrc/api.cu"), "-o", SO, "-lcuda"]
-    subprocess.run(cmd, check=True)
+    import __graft_entry__ as G
+    G.build(extra_flags=("-DTNB_TC_TRACE",), target=SO)
 
 
 if __name__ == "__main__":
