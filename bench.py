@@ -10,14 +10,20 @@ One "step" = loss + all L site gradients for the whole batch (micro-batched insi
 plus the NCCL all-reduce of the packed gradient when N > 1.  Prints ONE JSON line.
 
   python bench.py [--gpus N --steps K --warmup W] [--chi 256] [--batch 131072] [--dtype f32|f64]
+                  [--scaling weak|strong]
   python bench.py --impl reference ...     # CPU restatement of the reference path on the host cores
+
+The product arm never imports oracle/: the synthetic-input generators live in tn4ml_b200/synthetic.py; the oracle is
+executed only by the `cpu_baseline` leg, the `parity` checker (after the timed regions) and `--impl reference`.
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
+import glob
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -33,19 +39,22 @@ import torch  # noqa: E402
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--chi", type=int, default=256)
     ap.add_argument("--L", type=int, default=196)
     ap.add_argument("--classes", type=int, default=10)
-    ap.add_argument("--batch", type=int, default=131072, help="samples per GPU per step (weak scaling)")
+    ap.add_argument("--batch", type=int, default=131072, help="samples per GPU per step (weak) / per step in total (strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--precision", default="auto", choices=["auto", "simt", "tensor"])
     ap.add_argument("--microbatch", type=int, default=0)
     ap.add_argument("--cpu-batch", type=int, default=0, help="samples per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-chi-sweep", action="store_true", help="skip the chi=32/128 side measurements")
+    ap.add_argument("--no-chi-sweep", action="store_true", help="skip the chi=32/128 and float64 side measurements")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="one trailing all-reduce instead of the overlapped one")
     return ap.parse_args()
 
 
@@ -91,45 +100,54 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        sm, mx, pw, reasons = [], None, [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
+                pw.append(float(r[2]))
                 for n, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_median": float(np.median(pw)) if pw else None}
 
 
-def make_problem(args, dtype):
-    from oracle import tn_oracle as O  # synthetic-input generators only (framework-neutral data)
+def make_problem(args, dtype, chi=None):
+    from tn4ml_b200 import synthetic as S  # data generators only (identity + noise site tensors)
     c = args.L // 2 - 1
-    arrays = O.make_mps_arrays(args.L, args.chi, 2, class_site=c, C=args.classes, std=1e-2, seed=42, dtype=dtype)
+    arrays = S.make_mps_arrays(args.L, chi or args.chi, 2, class_site=c, C=args.classes, std=1e-2, seed=42, dtype=dtype)
     return arrays, c
 
 
-def cpu_step_fn(args, arrays, B_cpu, dtype):
-    """The reference path restated on the CPU (oracle, gemm_order; the faster of the two orders)."""
+def make_batch(args, B, dtype, seed):
+    rng = np.random.default_rng(seed)
+    x = torch.from_numpy((1.0 - rng.random((B, args.L))).astype(np.float32 if dtype == torch.float32 else np.float64))
+    lab = rng.integers(0, args.classes, size=B)
+    t = torch.nn.functional.one_hot(torch.from_numpy(lab), args.classes).to(dtype)
+    return x, t
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU legs (the only places that execute oracle/)
+# --------------------------------------------------------------------------------------------------
+def time_cpu(args, arrays, dtype, steps, warmup, order):
+    """The reference path restated on the CPU (oracle): `order` = "gemm" (L_i @ A_i, then the phi-weighted sum) or
+    "ref" (what XLA receives from quimb: per-sample site matrices, then a batched vector-matrix chain)."""
     from oracle import tn_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    fps = flops_per_sample(args.L, args.chi, 2, args.classes, args.L // 2 - 1)
+    budget = 2.0e11 if order == "gemm" else 0.6e11  # ~ seconds of work per step on a few dozen cores
+    B_cpu = args.cpu_batch or max(32, min(4096, int(budget / fps)))
     prob = O.Problem("mps", O.EmbSpec("trig"), "softmax_xent")
-    x = O.make_inputs(B_cpu, args.L, seed=1239, dtype=dtype)
-    t = O.make_labels(B_cpu, args.classes, dtype=dtype)
+    x, t = make_batch(args, B_cpu, dtype, 1239)
 
     def step():
-        loss, grads = O.value_and_grad(prob, x, arrays, t, order="gemm")
+        loss, grads = O.value_and_grad(prob, x, arrays, t, order=order)
         return float(loss)
-    return step
-
-
-def time_cpu(args, arrays, dtype, steps, warmup):
-    torch.set_num_threads(os.cpu_count())
-    B_cpu = args.cpu_batch or max(64, min(4096, int(2.0e11 / flops_per_sample(args.L, args.chi, 2, args.classes, args.L // 2 - 1))))
-    step = cpu_step_fn(args, arrays, B_cpu, dtype)
     for _ in range(warmup):
         step()
     ts = []
@@ -141,44 +159,110 @@ def time_cpu(args, arrays, dtype, steps, warmup):
     return B_cpu / dt, dt, B_cpu
 
 
+def cpu_both_orders(args, arrays, dtype, steps, warmup):
+    """time both contraction orders, report the faster (labelled) with the other beside it."""
+    res = {}
+    for order in ("gemm", "ref"):
+        try:
+            sps, dt, B_cpu = time_cpu(args, arrays, dtype, steps, warmup, order)
+            res[order] = {"samples_per_s": sps, "s_per_step": dt, "batch": B_cpu}
+        except Exception as exc:  # pragma: no cover
+            res[order] = {"error": str(exc)[:200]}
+    ok = {k: v for k, v in res.items() if "samples_per_s" in v}
+    best = max(ok, key=lambda k: ok[k]["samples_per_s"]) if ok else None
+    return best, res
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     dtype = torch.float32 if args.dtype == "f32" else torch.float64
     arrays, c = make_problem(args, dtype)
-    sps, dt, B_cpu = time_cpu(args, arrays, dtype, max(1, args.steps), max(1, min(args.warmup, 2)))
+    best, res = cpu_both_orders(args, arrays, dtype, max(1, args.steps), max(1, min(args.warmup, 2)))
     cores = os.cpu_count()
+    r = res[best]
+    sps, dt, B_cpu = r["samples_per_s"], r["s_per_step"], r["batch"]
     line = {
         "impl": "reference", "metric": "train samples/sec (fwd+bwd)", "value": sps, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": f"MPS classifier L={args.L} chi={args.chi} d=2 C={args.classes} softmax-xent "
-                               f"(BASELINE configs[4]); CPU sample of {B_cpu} samples/step",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": f"MPS classifier L={args.L} chi={args.chi} d=2 C={args.classes} at site {c}, trig embedding, "
+                               f"softmax-xent (BASELINE configs[4]); CPU sample of {B_cpu} samples/step",
                    "batch_per_step": B_cpu},
         "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": f"{B_cpu} samples/step, torch-CPU {args.dtype}, gemm_order, {torch.get_num_threads()} threads"},
+                         "sample": f"{B_cpu} samples/step, torch-CPU {args.dtype}, {best}_order (the faster of the two "
+                                   f"orders), {torch.get_num_threads()} threads",
+                         "orders": res},
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def quick_point(args, chi, dtype, dev, steps=2):
-    """Device-resident fwd+bwd throughput at another bond dimension (the metric's chi = 32 / 128 points)."""
-    import copy
+# --------------------------------------------------------------------------------------------------
+# GPU legs
+# --------------------------------------------------------------------------------------------------
+def read_profile(lib):
+    nmax = 16384
+    names = C.create_string_buffer(48 * nmax)
+    msbuf = (C.c_float * nmax)()
+    n = lib.tnb_profile_read(names, msbuf, nmax)
+    per = {}
+    for i in range(n):
+        nm = names.raw[i * 48:(i + 1) * 48].split(b"\0")[0].decode()
+        per.setdefault(nm, []).append(msbuf[i])
+    return per
+
+
+def ncu_traffic(kernel: str, tiles: int):
+    """DRAM bytes per launch of `kernel` from the newest committed ncu --set full summary (profiles/*_full_capture.csv),
+    scaled from the capture's sample-tile count to this launch's.  None if no capture lists the kernel."""
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_full_capture.csv")))
+    want = kernel.split("(")[0]
+    adj = "(adj)" in kernel
+    for path in reversed(files):
+        try:
+            lines = open(path).read().splitlines()
+        except Exception:
+            continue
+        m = re.search(r"(\d+) sample tiles", lines[0]) if lines else None
+        if not m:
+            continue
+        cap_tiles = int(m.group(1))
+        hdr = next((ln for ln in lines if ln.startswith("kernel,")), None)
+        if not hdr:
+            continue
+        cols = hdr.split(",")
+        try:
+            ir, iw = cols.index("dram__bytes_read.sum"), cols.index("dram__bytes_write.sum")
+        except ValueError:
+            continue
+        rows = [ln for ln in lines if ln.startswith('"' + want)]
+        if want == "tc_chain_kernel" and len(rows) >= 2:
+            rows = [rows[1 if adj else 0]]  # first launch of the step = forward sweep, second = adjoint
+        if not rows:
+            continue
+        f = rows[0].rsplit('"', 1)[1].split(",")  # fields after the quoted kernel signature
+        gb = float(f[ir]) + float(f[iw])
+        return gb * 1e9 * tiles / cap_tiles, f"{os.path.basename(path)}: dram read+write at {cap_tiles} tiles x {tiles}/{cap_tiles}"
+    return None, None
+
+
+def quick_point(args, chi, dtype, dev, steps=10, batch=None, microbatch=0):
+    """Device-resident fwd+bwd throughput at another bond dimension / dtype (the metric's chi = 32 / 128 points and the
+    float64 variant), >= 10 timed steps."""
     import tn4ml_b200 as T
     from tn4ml_b200 import metrics
-    a2 = copy.copy(args)
-    a2.chi = chi
-    arrays, c = make_problem(a2, dtype)
+    arrays, c = make_problem(args, dtype, chi)
     model = T.TensorNetwork(arrays, dtype=dtype, device=dev)
     loss_fn = lambda *a, **k: metrics.OptaxWrapper(metrics.softmax_cross_entropy)(*a, **k).mean()  # noqa: E731
     eng, _ = model._engine(T.TrigonometricEmbedding(), loss_fn, True, dtype)
-    rng = np.random.default_rng(7)
-    B = args.batch
-    x = torch.from_numpy((1.0 - rng.random((B, args.L))).astype(np.float32 if dtype == torch.float32 else np.float64)).to(dev)
-    t = torch.nn.functional.one_hot(torch.from_numpy(rng.integers(0, args.classes, size=B)), args.classes).to(dev, dtype)
+    if microbatch:
+        eng.max_microbatch = microbatch
+    B = batch or args.batch
+    xh, th = make_batch(args, B, dtype, 7)
+    x, t = xh.to(dev), th.to(dev)
     g = torch.zeros(eng.n_params, dtype=dtype, device=dev)
     for _ in range(3):
         eng.value_and_grad(model._packed, x, t, grads=g)
@@ -191,16 +275,48 @@ def quick_point(args, chi, dtype, dev, steps=2):
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1) / steps
     fl = flops_per_sample(args.L, chi, 2, args.classes, c) * B
-    out = {"samples_per_s": B / ms * 1e3, "ms_per_step": ms, "tflops": fl / ms / 1e9}
+    out = {"samples_per_s": B / ms * 1e3, "ms_per_step": ms, "tflops": fl / ms / 1e9, "steps": steps, "batch": B}
     del eng, model, g, x, t
     torch.cuda.empty_cache()
     return out
+
+
+def parity_check(args, eng, model, x_dev, t_dev, dtype, n=256):
+    """Ties the perf line to correctness: the oracle (float64, CPU) on the first `n` samples of the timed batch against the
+    same kernels on the same samples -- per-sample losses and every site gradient.  Runs after the timed regions."""
+    from oracle import tn_oracle as O
+    n = min(n, x_dev.shape[0])
+    xs, ts = x_dev[:n].contiguous(), t_dev[:n].contiguous()
+    arrays = [a.detach().double().cpu() for a in model.arrays]
+    prob = O.Problem("mps", O.EmbSpec("trig"), "softmax_xent")
+    t0 = time.perf_counter()
+    loss_ref, grads_ref = O.value_and_grad(prob, xs.double().cpu(), arrays, ts.double().cpu())
+    per_ref = O.per_sample_loss(prob, xs.double().cpu(), arrays, ts.double().cpu())
+    t_oracle = time.perf_counter() - t0
+    ls, g = eng.value_and_grad(model._packed, xs, ts)
+    per, _, _ = eng.forward(model._packed, xs, ts)
+    loss = float(ls.item()) / n
+    gmax = max(float(q.abs().max()) for q in grads_ref)
+    gfro = max(float(q.norm()) for q in grads_ref)
+    worst_fro, worst_max = 0.0, 0.0
+    for a, b in zip(model._views(g), grads_ref):
+        diff = a.double().cpu() - b
+        worst_fro = max(worst_fro, float(diff.norm()) / max(float(b.norm()), 1e-3 * gfro))
+        worst_max = max(worst_max, float(diff.abs().max()) / gmax)
+    per_err = float(((per.double().cpu() - per_ref).abs() / per_ref.abs().clamp_min(1e-30)).max())
+    tol = 1e-4 if dtype == torch.float32 else 1e-10
+    err = max(abs(loss - float(loss_ref)) / abs(float(loss_ref)), worst_fro, worst_max)
+    return {"samples": n, "oracle": "oracle/tn_oracle.py float64 on the first samples of the timed batch",
+            "loss_rel_err": abs(loss - float(loss_ref)) / abs(float(loss_ref)), "per_sample_loss_max_rel_err": per_err,
+            "grad_site_fro_rel_err_max": worst_fro, "grad_max_abs_err_over_max": worst_max, "max_rel_err": err,
+            "tolerance": tol, "ok": bool(err <= tol), "oracle_seconds": t_oracle}
 
 
 def run_native(args):
     import torch.distributed as dist
     import tn4ml_b200 as T
     from tn4ml_b200 import _lib, metrics
+    from tn4ml_b200.distributed import OverlappedAllReduce
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -226,16 +342,18 @@ def run_native(args):
     eng, _ = model._engine(emb, loss_fn, True, dtype)
     if args.microbatch:
         eng.max_microbatch = args.microbatch
-    B = args.batch
-    rng = np.random.default_rng(1239 + rank)
-    x_host = torch.from_numpy((1.0 - rng.random((B, args.L))).astype(np.float32 if dtype == torch.float32 else np.float64)).pin_memory()
-    lab = rng.integers(0, args.classes, size=B)
-    t_host = torch.nn.functional.one_hot(torch.from_numpy(lab), args.classes).to(dtype).pin_memory()
+    # weak scaling: --batch samples per GPU; strong scaling: --batch samples per step in total, split over the ranks
+    B = args.batch if args.scaling == "weak" else args.batch // world
+    x_host, t_host = make_batch(args, B, dtype, 1239 + rank)
+    x_host, t_host = x_host.pin_memory(), t_host.pin_memory()
     x_dev, t_dev = x_host.to(dev), t_host.to(dev)
     grads = torch.zeros(eng.n_params, dtype=dtype, device=dev)
     denom = B * world
+    reducer = OverlappedAllReduce(dist.group.WORLD, dev) if (world > 1 and not args.no_overlap) else None
 
     def step_resident():
+        if reducer is not None:
+            return eng.value_and_grad(model._packed, x_dev, t_dev, denom=denom, grads=grads, reducer=reducer)[0]
         loss_sum, g = eng.value_and_grad(model._packed, x_dev, t_dev, denom=denom, grads=grads)
         if world > 1:
             dist.all_reduce(g)
@@ -243,12 +361,18 @@ def run_native(args):
         return loss_sum
 
     train_step, opt_state = model.create_train_step(embedding=emb, dtype=dtype)
+    copy_stream = torch.cuda.Stream(dev)
+    # double-buffered device inputs: the H2D of step i+1 runs on a copy stream under the kernels of step i
+    bufs = [(torch.empty_like(x_dev), torch.empty_like(t_dev)) for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    freed = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def step_e2e(state):
-        xb = x_host.to(dev, non_blocking=True)
-        tb = t_host.to(dev, non_blocking=True)
-        _, state, loss = train_step(model.arrays, state, (xb, tb))
-        return state, float(loss.item())
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[i % 2])
+            bufs[i % 2][0].copy_(x_host, non_blocking=True)
+            bufs[i % 2][1].copy_(t_host, non_blocking=True)
+            ready[i % 2].record(copy_stream)
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -256,7 +380,8 @@ def run_native(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step_resident()
     sync_all()
     sampler = ClockSampler(local)
@@ -268,39 +393,33 @@ def run_native(args):
     for _ in range(args.steps):
         step_resident()
     ev1.record()
-    sync_all()
     launches = int(lib.tnb_launch_count() - l0)
+    # The same K steps again, back to back with the timed ones (no host sync in between: the GPU never idles, so these run
+    # at the same sustained clocks), with CUDA events around every launch: the dominant kernel's STEADY-STATE duration.
+    lib.tnb_profile(1)
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
+    for _ in range(args.steps):
+        step_resident()
+    pe1.record()
+    sync_all()
     clocks = sampler.stop() if rank == 0 else None
+    per = read_profile(lib)
+    lib.tnb_profile(0)
+    profiled_ms_per_step = pe0.elapsed_time(pe1) / args.steps
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(ms.item()) / args.steps
     value = B * world / (ms_per_step * 1e-3)
 
-    # per-kernel timing for the roofline of the dominant kernel (separate pass, events on the launch stream)
-    lib.tnb_profile(1)
-    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    pe0.record()
-    step_resident()
-    pe1.record()
-    torch.cuda.synchronize(dev)
-    profile_step_ms = pe0.elapsed_time(pe1)
-    nmax = 8192
-    names = C.create_string_buffer(48 * nmax)
-    msbuf = (C.c_float * nmax)()
-    n = lib.tnb_profile_read(names, msbuf, nmax)
-    lib.tnb_profile(0)
-    per = {}
-    for i in range(n):
-        nm = names.raw[i * 48:(i + 1) * 48].split(b"\0")[0].decode()
-        per.setdefault(nm, []).append(msbuf[i])
     tot = sum(sum(v) for v in per.values()) or 1.0
     top = max(per, key=lambda k: sum(per[k])) if per else "none"
     fps = flops_per_sample(args.L, args.chi, 2, args.classes, c)
     # share of the step's algorithmic flops carried by each kernel family (fwd sweep 1/3, adjoint 1/3, dA 1/3)
     share = {"mps_sweep_kernel(fwd)": 1 / 3, "mps_sweep_kernel(adj)": 1 / 3, "mps_da_kernel": 1 / 3,
              "tc_chain_kernel(fwd)": 1 / 3, "tc_chain_kernel(adj)": 1 / 3, "tc_da_kernel": 1 / 3}
-    mb_launches = len(per.get(top, [1]))
+    launches_per_step = max(len(per.get(top, [1])) // max(args.steps, 1), 1)
     top_ms = float(np.mean(per[top])) if per else float("nan")
     peaks = {}
     try:
@@ -308,40 +427,57 @@ def run_native(args):
     except Exception:
         pass
     if dtype == torch.float32:
+        # timed inside a long back-to-back loop under the power cap -> the SUSTAINED measured figure
         peak = 0.5 * peaks.get("bf16_tflops_sustained", 1400.0)
-        peak_note = ("0.5 x measured sustained bf16 (TF32:BF16 nominal ratio), of measured" if peaks else
-                     "0.5 x 1.4 PFLOP/s, of fallback")
+        peak_note = ("0.5 x measured sustained bf16 (nominal TF32:BF16 ratio), kernel timed in the steady-state loop; of measured"
+                     if peaks else "0.5 x 1.4 PFLOP/s sustained, of fallback")
     else:
-        peak, peak_note = 40.0, "FP64 nominal 40 TFLOP/s (no measured figure on file), of nominal"
-    k_flops = fps * B * share.get(top, 1 / 3) / max(mb_launches, 1)
+        peak, peak_note = 40.0, "FP64 nominal 40 TFLOP/s, of nominal"
+        try:
+            dm = json.load(open(os.path.join(ROOT, "profiles", "r02_fp64_dmma_peak.json")))
+            peak = float(dm["fp64_dmma_tflops_sustained"])
+            peak_note = "measured sustained mma.sync.m8n8k4.f64 rate (tools/ubench/dmma_peak.cu, profiles/r02_fp64_dmma_peak.json); of measured"
+        except Exception:
+            pass
+    k_flops = fps * B * share.get(top, 1 / 3) / launches_per_step
     achieved = k_flops / (top_ms * 1e-3) / 1e12 if top_ms == top_ms else None
-    # DRAM traffic of the dominant kernel per launch: from the ncu --set full capture of the same problem at 296 sample
-    # tiles (profiles/r01d_full_capture.csv: dram read + write of tc_chain_kernel), scaled to this launch's tile count.
-    # Only for the profiled configuration; null otherwise.
-    traffic, traffic_note = None, None
-    ncu_gb_per_296_tiles = {"tc_chain_kernel(fwd)": 0.378655 + 7.633898, "tc_chain_kernel(adj)": 0.445621 + 7.622838}
-    if (dtype == torch.float32 and args.chi == 256 and args.L == 196 and args.classes == 10 and top in ncu_gb_per_296_tiles):
-        tiles = (B // max(mb_launches, 1) + 127) // 128
-        traffic = ncu_gb_per_296_tiles[top] * 1e9 * tiles / 296.0
-        traffic_note = "bytes per launch; ncu dram__bytes_read+write.sum at 296 tiles (profiles/r01d_full_capture.csv) x tiles/296"
+    tiles = (B // launches_per_step + 127) // 128
+    traffic, traffic_note = ncu_traffic(top, tiles) if dtype == torch.float32 and args.chi == 256 else (None, None)
     roofline = {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_note,
                 "peak_source": peak_note,
-                "kernel_ms_avg": top_ms, "kernel_share_of_step": sum(per.get(top, [0])) / tot,
+                "kernel_ms_avg": top_ms, "kernel_launches_timed": len(per.get(top, [])),
+                "kernel_share_of_step": sum(per.get(top, [0])) / tot,
                 "step_tflops": fps * B / (ms_per_step * 1e-3) / 1e12,
-                "kernel_ms": {k: float(np.sum(v)) for k, v in per.items()},
-                "profiled_step_ms": profile_step_ms, "profiled_kernel_sum_ms": float(tot)}
+                "step_frac": fps * B / (ms_per_step * 1e-3) / 1e12 / peak,
+                "kernel_ms_per_step": {k: float(np.sum(v)) / args.steps for k, v in per.items()},
+                "profiled_ms_per_step": profiled_ms_per_step}
 
-    # end to end through the public train step: pinned host inputs -> H2D -> step -> loss D2H
+    # end to end through the public train step: pinned host inputs -> H2D (prefetched on a copy stream) -> step -> loss D2H
     state = opt_state
+    for ev in freed:
+        ev.record()
+    prefetch(0)
+    lval = float("nan")
+
+    def step_e2e(i, state):
+        cur = i % 2
+        torch.cuda.current_stream(dev).wait_event(ready[cur])
+        prefetch(i + 1)
+        _, state, loss = train_step(model.arrays, state, bufs[cur])
+        freed[cur].record()
+        return state, float(loss.item())
+
+    k = 0
     for _ in range(2):
-        state, _ = step_e2e(state)
+        state, _ = step_e2e(k, state)
+        k += 1
     sync_all()
-    t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        state, lval = step_e2e(state)
+        state, lval = step_e2e(k, state)
+        k += 1
     e1.record()
     sync_all()
     ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -350,44 +486,63 @@ def run_native(args):
     e2e_value = B * world / (float(ems.item()) / args.steps * 1e-3)
     h2d = x_host.numel() * x_host.element_size() + t_host.numel() * t_host.element_size()
 
+    parity = None
+    if rank == 0 and not args.no_parity:
+        try:
+            # the e2e loop moved the parameters (Adam): the check uses the model as it is now, on the timed batch's samples
+            parity = parity_check(args, eng, model, x_dev, t_dev, dtype)
+        except Exception as exc:  # pragma: no cover
+            parity = {"error": str(exc)[:300]}
+
     sweep = None
     if rank == 0 and world == 1 and not args.no_chi_sweep:
-        del x_dev, t_dev, grads
+        del x_dev, t_dev, grads, bufs
         eng._ws.clear()
         torch.cuda.empty_cache()
         sweep = {str(args.chi): {"samples_per_s": value, "ms_per_step": ms_per_step,
-                                 "tflops": fps * B / (ms_per_step * 1e-3) / 1e12}}
+                                 "tflops": fps * B / (ms_per_step * 1e-3) / 1e12, "steps": args.steps, "batch": B}}
         for chi2 in (128, 32):
             if chi2 != args.chi:
                 try:
                     sweep[str(chi2)] = quick_point(args, chi2, dtype, dev)
                 except Exception as exc:  # pragma: no cover
                     sweep[str(chi2)] = {"error": str(exc)[:200]}
+        if dtype == torch.float32:
+            # the float64 variant configs[4] names: chi = 128 at the full batch (micro-batched) and chi = 256 at B = 16384
+            for chi2, b2, st in ((128, args.batch, 10), (256, 16384, 10)):
+                try:
+                    sweep[f"f64_chi{chi2}"] = quick_point(args, chi2, torch.float64, dev, steps=st, batch=b2)
+                except Exception as exc:  # pragma: no cover
+                    sweep[f"f64_chi{chi2}"] = {"error": str(exc)[:200]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            sps, dt, B_cpu = time_cpu(args, [a.cpu() for a in arrays], dtype, 3, 1)
-            cpu = {"value": sps, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
-                   "sample": f"{B_cpu} samples/step x 3 steps, torch-CPU {args.dtype}, gemm_order, "
-                             f"{torch.get_num_threads()} threads"}
+            best, res = cpu_both_orders(args, [a.cpu() for a in arrays], dtype, 3, 1)
+            r = res[best]
+            cpu = {"value": r["samples_per_s"], "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"{r['batch']} samples/step x 3 steps, torch-CPU {args.dtype}, {best}_order (the faster of the "
+                             f"two orders), {torch.get_num_threads()} threads",
+                   "orders": res}
         except Exception as exc:  # pragma: no cover
             cpu = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc}"}
 
     if rank == 0:
         line = {
             "metric": "train samples/sec (fwd+bwd)", "value": value, "unit": "samples/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"MPS classifier L={args.L} chi={args.chi} d=2 C={args.classes} at site {c}, "
                                    f"trig embedding, softmax-xent (BASELINE configs[4])",
                        "batch_per_gpu": B, "global_batch": B * world, "microbatch": eng.microbatch(B, True),
                        "precision": "tensor" if precision == _lib.PREC_TENSOR else "simt",
-                       "parallelism": f"dp{world}", "l2": "working set (env stash) >> L2"},
+                       "parallelism": f"dp{world}", "l2": "working set (env stash) >> L2",
+                       "allreduce": ("overlapped per site range" if reducer is not None else "one trailing ncclAllReduce") if world > 1 else None},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
-                    "includes": "H2D of x and targets from pinned memory, value_and_grad, all-reduce, Adam update, loss D2H"},
+                    "includes": "H2D of x and targets from pinned memory (double-buffered on a copy stream), value_and_grad, "
+                                "all-reduce, Adam update, loss D2H"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "chi_sweep": sweep,
+            "parity": parity, "chi_sweep": sweep,
             "loss": lval,
         }
         print(json.dumps(line), flush=True)

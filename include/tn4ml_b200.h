@@ -138,12 +138,36 @@ int tnb_backward(const tnb_problem *prob, int64_t batch, const void *x, const vo
                  const void *params, double loss_scale, void *grads, int32_t accumulate,
                  void *workspace, int64_t workspace_bytes, void *stream);
 
+/* The same backward pass in `nparts` site ranges, for overlapping the data-parallel gradient all-reduce with the
+ * rest of the weight-gradient work: part 0 runs the adjoint sweep and the gradients of the sites of range 0, part k > 0 the
+ * gradients of range k.  After part k returns (stream order) the gradient of every site in
+ * [site_begin, site_end) = tnb_part_sites(prob, k, nparts) is final: the caller records an event and all-reduces
+ * grads[tnb_site_offset(site_begin) : tnb_site_offset(site_end)] on another stream while part k+1 runs.  Parts must be
+ * issued in order 0 .. nparts-1 on the same stream.  tnb_backward == one part. */
+int tnb_backward_part(const tnb_problem *prob, int64_t batch, const void *x, const void *targets, const void *params,
+                      double loss_scale, void *grads, int32_t accumulate, void *workspace, int64_t workspace_bytes,
+                      void *stream, int32_t part, int32_t nparts);
+int32_t tnb_part_sites(const tnb_problem *prob, int32_t part, int32_t nparts, int32_t *site_begin, int32_t *site_end);
+
 /* One optax.adam step on the packed buffers (the update side of train_step, tn4ml/models/model.py:591-614, where the
  * reference runs eager optax over an L-leaf pytree):  mu, nu updated in place, params += -lr * mu_hat / (sqrt(nu_hat +
  * eps_root) + eps) with the bias corrections of step `count` (1-based).  grad_scale multiplies the gradient first
  * (global-norm clipping, util.py:131-155, passes its factor here; 1.0 otherwise).  All buffers: n elements of dtype. */
 int tnb_adam_update(int32_t dtype, int64_t n, void *params, const void *grads, void *mu, void *nu, double lr,
                     double b1, double b2, double eps, double eps_root, int64_t count, double grad_scale, void *stream);
+
+/* Same update with one more gradient factor read from DEVICE memory (grad_scale_dev: dtype[1], may be NULL): a factor
+ * computed on the device -- 1 / global batch after the all-reduce of the shard sizes, a global-norm clip -- reaches the
+ * update without a device-to-host round trip. */
+int tnb_adam_update_dev(int32_t dtype, int64_t n, void *params, const void *grads, void *mu, void *nu, double lr,
+                        double b1, double b2, double eps, double eps_root, int64_t count, double grad_scale,
+                        const void *grad_scale_dev, void *stream);
+
+/* util.gradient_clip (tn4ml/util.py:131-155) on the packed gradient, in place: the gradient of every SITE tensor is scaled by
+ * min(1, threshold / (||g_site||_2 + 1e-6)), after multiplying the whole buffer by pre_scale.  scratch: device memory of
+ * tnb_gradient_clip_scratch_bytes(prob) bytes; its tail holds the L squared site norms (float64) afterwards. */
+int64_t tnb_gradient_clip_scratch_bytes(const tnb_problem *prob);
+int tnb_gradient_clip(const tnb_problem *prob, void *grads, double threshold, double pre_scale, void *scratch, void *stream);
 
 /* Embedding.__call__ for n scalars: phi [n, d] (dtype), before embed()'s normaliser. */
 int tnb_embed(const tnb_embedding *emb, int32_t dtype, int64_t n, const void *x, void *phi,

@@ -5,7 +5,9 @@ import numpy as np
 import pytest
 import torch
 
+import tn4ml_b200 as T
 from oracle import tn_oracle as O
+from tn4ml_b200 import metrics as M
 
 pytestmark = pytest.mark.gpu
 
@@ -121,3 +123,44 @@ def test_fused_adam_matches_the_optax_rule(dtype):
     tol = 1e-12 if dtype == torch.float64 else 2e-6
     assert torch.allclose(pa, pb, rtol=tol, atol=tol)
     assert torch.allclose(sa["mu"], sb["mu"], rtol=tol, atol=tol) and torch.allclose(sa["nu"], sb["nu"], rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+def test_gradient_clip_is_per_site_like_the_reference(dtype):
+    """util.gradient_clip (tn4ml/util.py:131-155): every site tensor's gradient scaled by min(1, thr / (||g_site|| + 1e-6))
+    -- NOT one global-norm clip."""
+    arrays = O.make_mps_arrays(9, 12, 3, class_site=4, C=3, std=0.1, seed=1, shape_method="noteven")
+    model = T.TensorNetwork(arrays, dtype=dtype, device="cuda:0")
+    eng, _ = model._engine(T.PolynomialEmbedding(degree=2, n=1, include_bias=True),
+                           lambda *a, **k: M.OptaxWrapper(M.softmax_cross_entropy)(*a, **k).mean(), True, dtype)
+    g = torch.zeros(eng.n_params, dtype=dtype, device="cuda:0")
+    gen = torch.Generator().manual_seed(5)
+    scales = [0.01, 5.0, 0.3, 40.0, 1.0, 0.0, 2.0, 0.5, 7.0]  # some sites below, some above the threshold; one all-zero
+    for v, sc in zip(model._views(g), scales):
+        v.copy_((torch.randn(v.shape, generator=gen, dtype=torch.float64) * sc / max(v.numel(), 1) ** 0.5).to(dtype))
+    ref = []
+    for v in model._views(g):
+        n = float(torch.linalg.norm(v.double()))
+        ref.append(v.double().cpu() * min(1.0, 1.5 / (n + 1e-6)))
+    eng.gradient_clip(g, 1.5)
+    tol = 1e-12 if dtype == torch.float64 else 1e-6
+    for v, r in zip(model._views(g), ref):
+        assert float((v.double().cpu() - r).abs().max()) <= tol * max(1.0, float(r.abs().max()))
+    with pytest.raises(AssertionError):
+        eng.gradient_clip(g, 0.0)
+
+
+def test_engine_cache_is_keyed_on_the_embedding_contents():
+    """two temporaries with different parameters must not share an engine."""
+    arrays = O.make_mps_arrays(6, 4, 2, std=0.1, seed=1, squeeze_ends=True, identity_all=True)
+    model = T.MatrixProductState(arrays, dtype=torch.float64, device="cuda:0")
+    x = O.make_inputs(5, 6, seed=2)
+    import numpy as np
+    a = model.evaluate(x.numpy(), embedding=T.GaussianRBFEmbedding(centers=np.array([0.1, 0.9]), gamma=0.5), metric=M.NegLogLikelihood,
+                       return_list=True)
+    b = model.evaluate(x.numpy(), embedding=T.GaussianRBFEmbedding(centers=np.array([0.3, 0.6]), gamma=2.0), metric=M.NegLogLikelihood,
+                       return_list=True)
+    prob = O.Problem("mps", O.EmbSpec("rbf", gamma=2.0, centers=(0.3, 0.6)), "nll")
+    ref = O.per_sample_loss(prob, x, arrays)
+    assert not np.allclose(a, b)
+    assert np.allclose(b, ref.numpy(), rtol=1e-10)

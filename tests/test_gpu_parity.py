@@ -12,6 +12,7 @@ from oracle import tn_oracle as O
 pytestmark = pytest.mark.gpu
 
 TOL = {torch.float64: 1e-10, torch.float32: 1e-4}
+LAST = {}  # worst errors of the most recent _check (read by tools/parity_report.py)
 
 
 def _heads():
@@ -54,13 +55,24 @@ def _check(model, prob, loss_fn, x, arrays, t, dtype, scale_tol=1.0, precision=0
     assert abs(loss - float(loss_ref)) <= tol * max(1.0, abs(float(loss_ref))), (loss, float(loss_ref))
     gmax = max(float(q.abs().max()) for q in grads_ref)
     gfro = max(float(q.norm()) for q in grads_ref)
+    worst_fro, worst_max, worst_site = 0.0, 0.0, -1
     for i, (a, b) in enumerate(zip(model._views(g), grads_ref)):
         assert a.shape == b.shape
         diff = a.double().cpu() - b
         # ||g - g_ref|| / ||g_ref|| per site, and max-elementwise scaled by ||g_ref||_inf
         # (sites whose gradient is < 1e-3 of the largest are measured against that floor)
-        assert float(diff.norm()) <= tol * max(float(b.norm()), 1e-3 * gfro), f"site {i} (fro)"
-        assert float(diff.abs().max()) <= tol * gmax, f"site {i} (max)"
+        efro = float(diff.norm()) / max(float(b.norm()), 1e-3 * gfro)
+        emax = float(diff.abs().max()) / gmax
+        if efro > worst_fro:
+            worst_fro, worst_site = efro, i
+        worst_max = max(worst_max, emax)
+    # the margin is part of the record: pytest -s / -rP shows it, and tools/parity_report.py collects it
+    print(f"[parity] {dtype} B={B} L={len(arrays)}: loss rel err {abs(loss - float(loss_ref)) / max(1.0, abs(float(loss_ref))):.2e}, "
+          f"worst per-site rel Frobenius err {worst_fro:.2e} (site {worst_site}), worst max-abs err / max|g| {worst_max:.2e}, tol {tol:.0e}")
+    LAST["loss_rel"] = abs(loss - float(loss_ref)) / max(1.0, abs(float(loss_ref)))
+    LAST["site_fro"], LAST["site_max"], LAST["site"] = worst_fro, worst_max, worst_site
+    assert worst_fro <= tol, f"site {worst_site} (fro): {worst_fro:.3e} > {tol:.0e}"
+    assert worst_max <= tol, f"(max): {worst_max:.3e} > {tol:.0e}"
     per, out, oexp = eng.forward(model._packed, x.to(dtype), None if t is None else t.to(dtype))
     assert torch.allclose(per.double().cpu(), per_ref, rtol=tol * 10, atol=tol * 10)
     return loss
@@ -138,7 +150,7 @@ def test_smpo_parity(case, dtype):
     cls = T.MatrixProductOperator if case["S"] == 1 else T.SpacedMatrixProductOperator
     kw = {} if case["S"] == 1 else {"spacing": case["S"]}
     model = cls(arrays, dtype=dtype, device="cuda:0", **kw)
-    _check(model, prob, _heads()[case["head"]], x, arrays, None, dtype, scale_tol=10.0 if dtype == torch.float32 else 1.0)
+    _check(model, prob, _heads()[case["head"]], x, arrays, None, dtype)
 
 
 def test_long_chain_does_not_leave_fp32_range():

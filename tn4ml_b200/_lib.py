@@ -60,6 +60,14 @@ SYMBOLS = {
     "tnb_embed": (C.c_int, [_P(TnbEmbedding), C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tnb_adam_update": (C.c_int, [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                   C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_double, C.c_void_p]),
+    "tnb_adam_update_dev": (C.c_int, [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                      C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_double, C.c_void_p,
+                                      C.c_void_p]),
+    "tnb_gradient_clip_scratch_bytes": (C.c_int64, [_P(TnbProblem)]),
+    "tnb_gradient_clip": (C.c_int, [_P(TnbProblem), C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
+    "tnb_backward_part": (C.c_int, [_P(TnbProblem), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                    C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32]),
+    "tnb_part_sites": (C.c_int32, [_P(TnbProblem), C.c_int32, C.c_int32, _P(C.c_int32), _P(C.c_int32)]),
     "tnb_profile": (C.c_int, [C.c_int32]),
     "tnb_profile_read": (C.c_int32, [C.c_char_p, _P(C.c_float), C.c_int32]),
     "tnb_launch_count": (C.c_int64, []),

@@ -270,21 +270,6 @@ MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
 
 }  // namespace tnb
 
-namespace tnb {
-template <typename T>
-__global__ void adam_kernel(long long n, T *__restrict__ p, const T *__restrict__ g, T *__restrict__ mu, T *__restrict__ nu,
-                            T lr, T b1, T b2, T eps, T eps_root, T c1, T c2, T gs) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const T gi = g[i] * gs;
-    const T m = b1 * mu[i] + (T(1) - b1) * gi;
-    const T v = b2 * nu[i] + (T(1) - b2) * gi * gi;
-    mu[i] = m;
-    nu[i] = v;
-    p[i] -= lr * (m * c1) / (Num<T>::sqrt(v * c2 + eps_root) + eps);
-  }
-}
-}  // namespace tnb
-
 using namespace tnb;
 
 extern "C" {
@@ -346,22 +331,47 @@ int tnb_forward(const tnb_problem *p, int64_t batch, const void *x, const void *
   return smpo_forward(p, batch, x, params, loss, loss_sum, out, out_exp, keep_stash, workspace, workspace_bytes, st);
 }
 
-int tnb_backward(const tnb_problem *p, int64_t batch, const void *x, const void *targets, const void *params,
-                 double loss_scale, void *grads, int32_t accumulate, void *workspace, int64_t workspace_bytes,
-                 void *stream) {
+static int backward_impl(const tnb_problem *p, int64_t batch, const void *x, const void *targets, const void *params,
+                         double loss_scale, void *grads, int32_t accumulate, void *workspace, int64_t workspace_bytes,
+                         void *stream, int part, int nparts) {
   if (validate(p)) return 1;
   if (batch < 1) return fail("batch must be >= 1");
   if (!x || !params || !workspace || !grads) return fail("null device pointer");
+  if (nparts < 1 || part < 0 || part >= nparts) return fail("part %d of %d is out of range", part, nparts);
   if (ensure_device_ready()) return 1;
   cudaStream_t st = (cudaStream_t)stream;
   if (p->kind == TNB_KIND_MPS) {
     MpsPlan P = plan_mps(p, batch, 1);
     if ((int64_t)P.total > workspace_bytes)
       return fail("workspace too small: need %zu bytes, got %lld", P.total, (long long)workspace_bytes);
-    if (P.tc) return mps_tc_backward(p, P, batch, x, targets, loss_scale, grads, accumulate, workspace, st);
-    return mps_simt_backward(p, P, batch, x, targets, loss_scale, grads, accumulate, workspace, st);
+    if (P.tc) return mps_tc_backward(p, P, batch, x, targets, loss_scale, grads, accumulate, workspace, st, part, nparts);
+    return mps_simt_backward(p, P, batch, x, targets, loss_scale, grads, accumulate, workspace, st, part, nparts);
   }
+  if (part > 0) return 0;  // the double-layer VJP is one kernel over all sites: part 0 computes everything
   return smpo_backward(p, batch, x, params, loss_scale, grads, accumulate, workspace, workspace_bytes, st);
+}
+
+int tnb_backward(const tnb_problem *p, int64_t batch, const void *x, const void *targets, const void *params,
+                 double loss_scale, void *grads, int32_t accumulate, void *workspace, int64_t workspace_bytes,
+                 void *stream) {
+  return backward_impl(p, batch, x, targets, params, loss_scale, grads, accumulate, workspace, workspace_bytes, stream, 0, 1);
+}
+
+int tnb_backward_part(const tnb_problem *p, int64_t batch, const void *x, const void *targets, const void *params,
+                      double loss_scale, void *grads, int32_t accumulate, void *workspace, int64_t workspace_bytes,
+                      void *stream, int32_t part, int32_t nparts) {
+  return backward_impl(p, batch, x, targets, params, loss_scale, grads, accumulate, workspace, workspace_bytes, stream,
+                       part, nparts);
+}
+
+int32_t tnb_part_sites(const tnb_problem *p, int32_t part, int32_t nparts, int32_t *site_begin, int32_t *site_end) {
+  if (!p || !site_begin || !site_end || nparts < 1 || part < 0 || part >= nparts) return fail("bad arguments");
+  int s0, s1;
+  part_sites(p->L, part, nparts, &s0, &s1);
+  if (p->kind != TNB_KIND_MPS) { s0 = part == 0 ? 0 : p->L; s1 = p->L; }  // one part owns every site
+  *site_begin = s0;
+  *site_end = s1;
+  return 0;
 }
 
 // Ragged reference-shaped site tensors <-> the zero-padded packed layout: site i is C-contiguous
@@ -419,28 +429,6 @@ int32_t tnb_profile_read(char *names, float *ms, int32_t max_records) {
     ++n;
   }
   return n;
-}
-
-int tnb_adam_update(int32_t dtype, int64_t n, void *params, const void *grads, void *mu, void *nu, double lr, double b1,
-                    double b2, double eps, double eps_root, int64_t count, double grad_scale, void *stream) {
-  if (!params || !grads || !mu || !nu) return fail("null device pointer");
-  if (n < 1 || count < 1) return fail("n and count must be >= 1");
-  cudaStream_t st = (cudaStream_t)stream;
-  const double c1 = 1.0 / (1.0 - pow(b1, (double)count)), c2 = 1.0 / (1.0 - pow(b2, (double)count));
-  int blocks = (int)((n + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  prof_begin(st);
-  if (dtype == TNB_F64)
-    adam_kernel<double><<<blocks, 256, 0, st>>>(n, (double *)params, (const double *)grads, (double *)mu, (double *)nu, lr,
-                                                 b1, b2, eps, eps_root, c1, c2, grad_scale);
-  else if (dtype == TNB_F32)
-    adam_kernel<float><<<blocks, 256, 0, st>>>(n, (float *)params, (const float *)grads, (float *)mu, (float *)nu,
-                                                (float)lr, (float)b1, (float)b2, (float)eps, (float)eps_root, (float)c1,
-                                                (float)c2, (float)grad_scale);
-  else
-    return fail("bad dtype");
-  TNB_LAUNCH_CHECK("adam_kernel");
-  return 0;
 }
 
 int tnb_embed(const tnb_embedding *emb, int32_t dtype, int64_t n, const void *x, void *phi, void *stream) {

@@ -35,6 +35,12 @@ void count_launches(int n);
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline size_t esize(const tnb_problem *p) { return p->dtype == TNB_F64 ? 8 : 4; }
+// sites [s0, s1) of part `part` of `nparts` (contiguous, sizes differ by at most one)
+static inline void part_sites(int L, int part, int nparts, int *s0, int *s1) {
+  const int base = L / nparts, rem = L % nparts;
+  *s0 = part * base + (part < rem ? part : rem);
+  *s1 = *s0 + base + (part < rem ? 1 : 0);
+}
 
 // ---- measurement knobs: environment, read ONCE when the library is loaded (never on a call path) ----
 //   TNB_TC_NH forces a legal column-chunk count, TNB_TC_TILES=1|2 sample tiles per chain CTA, TNB_TC_PACE_NS the image
@@ -67,15 +73,16 @@ MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad);
 int mps_simt_forward(const tnb_problem *p, const MpsPlan &P, long long B, const void *x, const void *targets,
                      const void *params, void *loss, double *loss_sum, void *out, int32_t *out_exp, int keep_stash,
                      void *ws, cudaStream_t st);
+// part / nparts: the backward pass in site ranges (tnb_backward_part): part 0 also runs the adjoint sweep
 int mps_simt_backward(const tnb_problem *p, const MpsPlan &P, long long B, const void *x, const void *targets,
-                      double loss_scale, void *grads, int accumulate, void *ws, cudaStream_t st);
+                      double loss_scale, void *grads, int accumulate, void *ws, cudaStream_t st, int part, int nparts);
 cudaError_t mps_simt_set_attrs();
 // tcgen05 family (mps_tc.cu): float32, TNB_PREC_TENSOR
 int mps_tc_forward(const tnb_problem *p, const MpsPlan &P, long long B, const void *x, const void *targets,
                    const void *params, void *loss, double *loss_sum, void *out, int32_t *out_exp, int keep_stash,
                    void *ws, cudaStream_t st);
 int mps_tc_backward(const tnb_problem *p, const MpsPlan &P, long long B, const void *x, const void *targets,
-                    double loss_scale, void *grads, int accumulate, void *ws, cudaStream_t st);
+                    double loss_scale, void *grads, int accumulate, void *ws, cudaStream_t st, int part, int nparts);
 cudaError_t mps_tc_set_attrs();
 // SMPO / MPO double layer (smpo.cu)
 int64_t smpo_workspace_bytes(const tnb_problem *p, long long B, int need_grad);

@@ -56,32 +56,35 @@ static int mps_forward_t(const tnb_problem *p, const MpsPlan &P, long long B, co
 
 template <typename T, int NG, int RB>
 static int mps_backward_t(const tnb_problem *p, const MpsPlan &P, long long B, const void *x, const void *targets,
-                          double loss_scale, void *grads, int accumulate, void *ws, cudaStream_t st) {
+                          double loss_scale, void *grads, int accumulate, void *ws, cudaStream_t st, int part, int nparts) {
   MpsArgs<T> A;
   fill_mps_args<T>(p, P, B, x, targets, ws, A);
   A.stash = 1;
   A.loss_scale = (T)loss_scale;
-  if (!accumulate) TNB_CUDA(cudaMemsetAsync(grads, 0, (size_t)tnb_param_count(p) * sizeof(T), st));
-  int tiles = (int)((B + P.BT - 1) / P.BT);
-  prof_begin(st);
-  mps_sweep_kernel<T, NG, RB><<<dim3(tiles, 2), P.NT, P.smem_sweep, st>>>(A, 1);
-  TNB_LAUNCH_CHECK("mps_sweep_kernel(adj)");
   DaArgs<T> Dg;
   Dg.M = A;
   Dg.grads = (T *)grads;
-  {
+  if (part == 0) {
+    if (!accumulate) TNB_CUDA(cudaMemsetAsync(grads, 0, (size_t)tnb_param_count(p) * sizeof(T), st));
+    int tiles = (int)((B + P.BT - 1) / P.BT);
+    prof_begin(st);
+    mps_sweep_kernel<T, NG, RB><<<dim3(tiles, 2), P.NT, P.smem_sweep, st>>>(A, 1);
+    TNB_LAUNCH_CHECK("mps_sweep_kernel(adj)");
     const long long n = (long long)p->L * B;
     prof_begin(st);
     mps_wq_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A);
     TNB_LAUNCH_CHECK("mps_wq_kernel");
   }
+  int s0, s1;
+  part_sites(p->L, part, nparts, &s0, &s1);
+  if (s1 <= s0) return 0;
   // micro-tile rows: 8 (a 128 x 64 tile per CTA) when the flattened rows (s, a) fill it, else 4; TNB_DA_RM forces
   const int rm_knob = knobs().da_rm;
   const int Mrows = p->d * p->chi;
   const int RM = rm_knob == 4 || rm_knob == 8 ? rm_knob : (Mrows > 64 ? 8 : 4);
   Dg.tiles_m = (Mrows + 16 * RM - 1) / (16 * RM);
   Dg.tiles_r = (p->chi + 63) / 64;
-  long long work = (long long)Dg.tiles_m * Dg.tiles_r * p->L;
+  long long work = (long long)Dg.tiles_m * Dg.tiles_r * (s1 - s0);
   long long ns = (148LL * 4 + work - 1) / work;
   long long maxsplit = (B + 255) / 256;
   if (ns > maxsplit) ns = maxsplit;
@@ -90,12 +93,14 @@ static int mps_backward_t(const tnb_problem *p, const MpsPlan &P, long long B, c
   Dg.bchunk = (B + ns - 1) / ns;
   Dg.bchunk = (Dg.bchunk + 15) / 16 * 16;
   Dg.only_site = -1;
-  dim3 grid(Dg.tiles_m * Dg.tiles_r * Dg.nsplit, p->L, 1);
+  Dg.site0 = s0;
+  dim3 grid(Dg.tiles_m * Dg.tiles_r * Dg.nsplit, s1 - s0, 1);
   prof_begin(st);
   if (RM == 8) mps_da_kernel<T, 8><<<grid, 256, 0, st>>>(Dg);
   else mps_da_kernel<T, 4><<<grid, 256, 0, st>>>(Dg);
   TNB_LAUNCH_CHECK("mps_da_kernel");
-  // class site: one GEMM per class
+  // class site: one GEMM per class (in the part that owns it)
+  if (p->out_site < s0 || p->out_site >= s1) return 0;
   Dg.only_site = p->out_site;
   work = (long long)Dg.tiles_m * Dg.tiles_r * p->n_out;
   ns = (148LL * 2 + work - 1) / work;
@@ -133,8 +138,8 @@ int mps_simt_forward(const tnb_problem *p, const MpsPlan &P, long long B, const 
 }
 
 int mps_simt_backward(const tnb_problem *p, const MpsPlan &P, long long B, const void *x, const void *targets,
-                      double loss_scale, void *grads, int accumulate, void *ws, cudaStream_t st) {
-  TNB_DISPATCH_MPS(mps_backward_t, p, P, B, x, targets, loss_scale, grads, accumulate, ws, st);
+                      double loss_scale, void *grads, int accumulate, void *ws, cudaStream_t st, int part, int nparts) {
+  TNB_DISPATCH_MPS(mps_backward_t, p, P, B, x, targets, loss_scale, grads, accumulate, ws, st, part, nparts);
 }
 
 // Embedding.__call__ for n scalars (tnb_embed)

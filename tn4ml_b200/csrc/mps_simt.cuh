@@ -606,7 +606,8 @@ template <typename T> struct DaArgs {
   T *grads;  // packed layout, chi (unpadded) strides
   int tiles_m, tiles_r, nsplit;
   long long bchunk;  // samples per split
-  int only_site;     // >= 0: this site only (the class site); < 0: site = blockIdx.y, class site skipped
+  int only_site;     // >= 0: this site only (the class site); < 0: site = site0 + blockIdx.y, class site skipped
+  int site0;         // first site of this launch (the backward pass may run in site ranges)
 };
 
 // per-sample weights of the dA GEMM, one thread per (site, sample) (the embedding is evaluated once, not once per tile)
@@ -628,7 +629,7 @@ template <typename T, int RM> __global__ void __launch_bounds__(256) mps_da_kern
   constexpr int UROWS = 256 / TM, VROWS = 256 / TR;      // samples covered by one pass of the CTA
   __shared__ __align__(16) T U_s[BK][TM];
   __shared__ __align__(16) T V_s[BK][TR];
-  const int site = P.only_site >= 0 ? P.only_site : (int)blockIdx.y;
+  const int site = P.only_site >= 0 ? P.only_site : P.site0 + (int)blockIdx.y;
   const int c = A.c, chip = A.chip, chi = A.chi, D = A.D, C = A.C;
   if (P.only_site < 0 && site == c) return;
   const bool cls = site == c;

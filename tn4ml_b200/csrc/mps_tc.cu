@@ -156,16 +156,21 @@ int mps_tc_forward(const tnb_problem *p, const MpsPlan &P, long long B, const vo
 }
 
 int mps_tc_backward(const tnb_problem *p, const MpsPlan &P, long long B, const void *x, const void *targets,
-                    double loss_scale, void *grads, int accumulate, void *ws, cudaStream_t st) {
+                    double loss_scale, void *grads, int accumulate, void *ws, cudaStream_t st, int part, int nparts) {
   MpsArgs<float> A;
   fill_mps_args<float>(p, P, B, x, targets, ws, A);
   A.stash = 1;
   A.loss_scale = (float)loss_scale;
-  if (!accumulate) TNB_CUDA(cudaMemsetAsync(grads, 0, (size_t)tnb_param_count(p) * sizeof(float), st));
   TcArgs Tc;
   fill_tc_args(P, ws, A, Tc);
-  TNB_CUDA(cudaMemsetAsync(Tc.qmax, 0x80, ((size_t)p->L + 1) * sizeof(int), st));
-  if (tc_launch_sweep(p, P, Tc, B, 1, st)) return 1;  // seeds through the class site + adjoint chains
+  if (part == 0) {
+    if (!accumulate) TNB_CUDA(cudaMemsetAsync(grads, 0, (size_t)tnb_param_count(p) * sizeof(float), st));
+    TNB_CUDA(cudaMemsetAsync(Tc.qmax, 0x80, ((size_t)p->L + 1) * sizeof(int), st));
+    if (tc_launch_sweep(p, P, Tc, B, 1, st)) return 1;  // seeds through the class site + adjoint chains
+  }
+  int s0, s1;
+  part_sites(p->L, part, nparts, &s0, &s1);
+  if (s1 <= s0) return 0;
   TcDaArgs Da;
   Da.M = A;
   Da.grads = (float *)grads;
@@ -179,15 +184,18 @@ int mps_tc_backward(const tnb_problem *p, const MpsPlan &P, long long B, const v
   const long long maxsp = (B + 2047) / 2048;
   Da.ra = p->chi < 128 ? p->chi : 128;
   Da.cpg = 256 / Da.ra;
+  Da.site0 = s0;
   for (int pass = 0; pass < 2; ++pass) {
-    // pass 0: every chain site (copies sigma = s);  pass 1: the class site (copies sigma = (s, k))
+    // pass 0: every chain site of the range (copies sigma = s);  pass 1: the class site (copies sigma = (s, k))
+    if (pass == 1 && (p->out_site < s0 || p->out_site >= s1)) break;
+    if (pass == 0 && s1 - s0 == 1 && s0 == p->out_site) continue;
     Da.Dv = pass == 0 ? p->d : p->d * p->n_out;
     Da.only_site = pass == 0 ? -1 : p->out_site;
     Da.wq = pass == 0 ? Tc.wq : Tc.wqc;
     Da.qmax = pass == 0 ? Tc.qmax : Tc.qmaxc;
     Da.mgroups = ((p->chi + Da.ra - 1) / Da.ra) * ((Da.Dv + Da.cpg - 1) / Da.cpg);
     // split K (the batch) so that the grid fills the 148 SMs about four times over with little wave quantisation
-    const long long ctas = (long long)(pass == 0 ? p->L - 1 : 1) * Da.mgroups;
+    const long long ctas = (long long)(pass == 0 ? s1 - s0 : 1) * Da.mgroups;
     long long best = 1;
     double best_eff = 0.0;
     for (long long nsp = 1; nsp <= maxsp && nsp <= 64; ++nsp) {
@@ -198,7 +206,7 @@ int mps_tc_backward(const tnb_problem *p, const MpsPlan &P, long long B, const v
     }
     Da.nsplit = (int)best;
     Da.bchunk = ((B + Da.nsplit - 1) / Da.nsplit + kDaKC - 1) / kDaKC * kDaKC;
-    dim3 gda((unsigned)(Da.mgroups * Da.nsplit), (unsigned)(pass == 0 ? p->L : 1));
+    dim3 gda((unsigned)(Da.mgroups * Da.nsplit), (unsigned)(pass == 0 ? s1 - s0 : 1));
     prof_begin(st);
     const size_t da_smem = (size_t)Da.nstage * kDaStage + 1024;
     if (Da.cpg == 2) tc_da_kernel<2><<<gda, kDaThreads, da_smem, st>>>(Da);

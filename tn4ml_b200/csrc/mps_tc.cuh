@@ -220,6 +220,7 @@ struct TcDaArgs {
   int ra;            // bond rows per copy and CTA: min(chi, 128)
   int cpg;           // copies per CTA: 256 / ra
   int only_site;     // >= 0: this site only (the class site; wq/qmax point at its own tables)
+  int site0;         // first site of this launch (site = site0 + blockIdx.y): the backward pass may run in site ranges
 };
 
 // stage geometry of the dA GEMM (kDaKC, kDaProducers, kDaThreads, kDaMaxCpg, kDaU*, kDaStage): consts.h
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const MpsArgs<float> &M = A.M;
   const int chi = M.chip, Dv = A.Dv, c = M.c;
-  const int site = A.only_site >= 0 ? A.only_site : (int)blockIdx.y;
+  const int site = A.only_site >= 0 ? A.only_site : A.site0 + (int)blockIdx.y;
   if (A.only_site < 0 && site == c) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int group = blockIdx.x % A.mgroups, split = blockIdx.x / A.mgroups;

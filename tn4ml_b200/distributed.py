@@ -33,3 +33,31 @@ def allreduce_step(loss_sum: torch.Tensor, grads: torch.Tensor, group=None):
         dist.all_reduce(grads, op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(loss_sum, op=dist.ReduceOp.SUM, group=group)
     return loss_sum, grads
+
+
+class OverlappedAllReduce:
+    """The step's gradient all-reduce, issued per site range while the rest of the weight-gradient work is still running.
+
+    The backward pass runs in ``nparts`` site ranges (``tnb_backward_part``); after part k an event is recorded on the compute
+    stream, and the NCCL all-reduce of that range's slice of the packed gradient is issued on a communication stream that
+    waits for the event -- so the transfer of range k overlaps the GEMMs of range k+1 and only the last slice's collective
+    (1/nparts of the bytes) is exposed.  ``finish`` makes the compute stream wait for every collective of the step.
+    """
+
+    def __init__(self, group=None, device=None, nparts: int = 4):
+        self.group, self.nparts = group, nparts
+        self.stream = torch.cuda.Stream(device)
+        self._works = []
+
+    def reduce(self, tensor: torch.Tensor):
+        """All-reduce (sum, in place) ``tensor`` once everything issued so far on the current stream has finished."""
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ev)
+            self._works.append(dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self):
+        for w in self._works:
+            w.wait()  # stream-level: the current stream waits for the collective, the host does not block
+        self._works = []

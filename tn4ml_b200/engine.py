@@ -139,8 +139,13 @@ class Engine:
 
     # -- forward + backward -------------------------------------------------------
     def value_and_grad(self, params: torch.Tensor, x, targets=None, *, denom: int | None = None,
-                       grads: torch.Tensor | None = None, accumulate: bool = False):
-        """(sum_b loss_b as a device float64 scalar, packed gradients of sum_b loss_b / denom)."""
+                       grads: torch.Tensor | None = None, accumulate: bool = False, reducer=None):
+        """(sum_b loss_b as a device float64 scalar, packed gradients of sum_b loss_b / denom).
+
+        ``reducer`` (:class:`tn4ml_b200.distributed.OverlappedAllReduce`): data-parallel step -- the last micro-batch's
+        backward pass runs in site ranges and each range's slice of ``grads`` is all-reduced as soon as it is final, under
+        the GEMMs of the next range; the loss sum is all-reduced too.  On return both are the sums over all ranks
+        (in stream order)."""
         x, targets = self._prep(x, targets)
         B = x.shape[0]
         denom = B if denom is None else denom
@@ -157,7 +162,39 @@ class Engine:
                 _lib.check(self.lib.tnb_forward(
                     C.byref(self.prob), e - s, x[s:e].data_ptr(), t_ptr, params.data_ptr(), None,
                     self._loss_sum.data_ptr(), None, None, 1, ws.data_ptr(), ws.numel(), self._stream()))
-                _lib.check(self.lib.tnb_backward(
-                    C.byref(self.prob), e - s, x[s:e].data_ptr(), t_ptr, params.data_ptr(), 1.0 / denom,
-                    grads.data_ptr(), int(accumulate or s > 0), ws.data_ptr(), ws.numel(), self._stream()))
+                acc = int(accumulate or s > 0)
+                if reducer is None or e < B:
+                    _lib.check(self.lib.tnb_backward(
+                        C.byref(self.prob), e - s, x[s:e].data_ptr(), t_ptr, params.data_ptr(), 1.0 / denom,
+                        grads.data_ptr(), acc, ws.data_ptr(), ws.numel(), self._stream()))
+                    continue
+                reducer.reduce(self._loss_sum)  # (every micro-batch's forward has been issued)
+                nparts = reducer.nparts
+                for part in range(nparts):
+                    _lib.check(self.lib.tnb_backward_part(
+                        C.byref(self.prob), e - s, x[s:e].data_ptr(), t_ptr, params.data_ptr(), 1.0 / denom,
+                        grads.data_ptr(), acc, ws.data_ptr(), ws.numel(), self._stream(), part, nparts))
+                    lo, hi = self.part_range(part, nparts)
+                    if hi > lo:
+                        reducer.reduce(grads[lo:hi])
+                reducer.finish()
         return self._loss_sum, grads
+
+    def part_range(self, part: int, nparts: int) -> tuple[int, int]:
+        """Element range of the packed gradient that is final after part `part` of `nparts` (tnb_part_sites)."""
+        s0, s1 = C.c_int32(), C.c_int32()
+        _lib.check(self.lib.tnb_part_sites(C.byref(self.prob), part, nparts, C.byref(s0), C.byref(s1)))
+        return (int(self.lib.tnb_site_offset(C.byref(self.prob), s0.value)),
+                int(self.lib.tnb_site_offset(C.byref(self.prob), s1.value)))
+
+    def gradient_clip(self, grads: torch.Tensor, threshold: float, pre_scale: float = 1.0) -> torch.Tensor:
+        """util.gradient_clip (tn4ml/util.py:131-155) in place on the packed gradient: one factor per site tensor."""
+        if not threshold > 0:
+            raise AssertionError("Threshold must be positive.")
+        if getattr(self, "_clip_scratch", None) is None:
+            n = int(self.lib.tnb_gradient_clip_scratch_bytes(C.byref(self.prob)))
+            self._clip_scratch = torch.empty(n, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.tnb_gradient_clip(C.byref(self.prob), grads.data_ptr(), float(threshold), float(pre_scale),
+                                                  self._clip_scratch.data_ptr(), self._stream()))
+        return grads

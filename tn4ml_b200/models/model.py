@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from .. import _lib, optim
-from ..embeddings import Embedding, TrigonometricEmbedding
+from ..embeddings import Embedding, TrigonometricEmbedding, spec_of
 from ..engine import Engine
 from ..metrics import LossExpr, resolve
 from ..util import EarlyStopping, TrainingType
@@ -249,7 +249,8 @@ class Model:
         expr = None
         if loss_fn is not None:
             expr = resolve(loss_fn, self, self.L, embedding.dim, supervised)
-        key = (id(embedding), None if expr is None else (expr.head, expr.class_weights), dt, self.precision)
+        # keyed on the CONTENTS of the feature-map spec (id() of a temporary embedding is reused by CPython)
+        key = (bytes(spec_of(embedding)), None if expr is None else (expr.head, expr.class_weights), dt, self.precision)
         eng = self._engine_cache.get(key)
         if eng is None:
             eng = Engine(kind=self.kind, L=self.L, chi=self.chi, d=self.phys_dim, n_out=self.n_out,
@@ -288,36 +289,45 @@ class Model:
         grads = torch.zeros_like(self._packed)
         group = self.process_group
 
+        reducer = None
+        if group is not None:
+            from ..distributed import OverlappedAllReduce
+            reducer = OverlappedAllReduce(group, self._packed.device)
+        n_cnt = torch.zeros(1, dtype=torch.float64, device=self._packed.device)
+
         def train_step(params, opt_state, data=None, grad_clip_threshold=None):
             if isinstance(data, tuple) and len(data) == 2:
                 x, t = data
             else:
                 x, t = data, None
             n_local = x.shape[0]
-            n_global = n_local
-            if group is not None:
+            if group is None:
+                loss_sum, g = eng.value_and_grad(self._packed, x, t, denom=n_local, grads=grads)
+                loss = loss_sum / n_local
+                gscale = 1.0
+            else:
+                # K6: shards may differ in size (distributed.shard_bounds), so the gradient of the loss SUM is reduced and
+                # the division by the true global sample count happens on the device, after the all-reduce of the counts
                 import torch.distributed as dist
-                n_global = n_local * dist.get_world_size(group)
-            loss_sum, g = eng.value_and_grad(self._packed, x, t, denom=n_global, grads=grads)
-            if group is not None:  # K6: sum of the packed per-site gradients (and the loss) over the batch shards
-                from ..distributed import allreduce_step
-                loss_sum, g = allreduce_step(loss_sum, g, group)
-            loss = loss_sum / n_global
+                n_cnt.fill_(float(n_local))
+                dist.all_reduce(n_cnt, op=dist.ReduceOp.SUM, group=group)
+                loss_sum, g = eng.value_and_grad(self._packed, x, t, denom=1, grads=grads, reducer=reducer)
+                loss = loss_sum / n_cnt
+                gscale = (1.0 / n_cnt).to(self._packed.dtype)
             rv, rg = self._reg_value_and_grad(expr)
-            if rv is not None:
-                loss = loss + rv
-                g = g + rg
             fused = (isinstance(self._opt, optim._Adam) and g.is_cuda and g.dtype == self._packed.dtype
                      and g.is_contiguous())
-            if grad_clip_threshold:  # util.gradient_clip (util.py:131-155): global-norm clipping
-                gn = torch.linalg.norm(g)
-                scale = torch.clamp(grad_clip_threshold / (gn + 1e-16), max=1.0)
-                if fused:
-                    opt_state = self._opt.fused_step(self._packed, g, opt_state, grad_scale=float(scale))
-                    return self.arrays, opt_state, loss
-                g = g * scale
+            if rv is not None or grad_clip_threshold or not fused:
+                if torch.is_tensor(gscale):
+                    g.mul_(gscale)
+                    gscale = 1.0
+            if rv is not None:
+                loss = loss + rv
+                g = g.add_(rg)
+            if grad_clip_threshold:  # util.gradient_clip (util.py:131-155): one factor per SITE tensor, eps 1e-6
+                eng.gradient_clip(g, grad_clip_threshold)
             if fused:  # optimizer + update_tensors of train_step (model.py:591-614) as one kernel on the packed buffer
-                opt_state = self._opt.fused_step(self._packed, g, opt_state)
+                opt_state = self._opt.fused_step(self._packed, g, opt_state, grad_scale=gscale)
                 return self.arrays, opt_state, loss
             updates, opt_state = self._opt.update(g, opt_state, self._packed)
             optim.apply_updates(self._packed, updates.to(self._packed.dtype))

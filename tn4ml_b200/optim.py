@@ -36,17 +36,22 @@ class _Adam(GradientTransformation):
         return -lr * mu_hat / (torch.sqrt(nu_hat + self.eps_root) + self.eps), state
 
     def fused_step(self, params, grads, state, grad_scale=1.0):
-        """update() + apply_updates() as ONE kernel over the packed CUDA buffers (tnb_adam_update)."""
+        """update() + apply_updates() as ONE kernel over the packed CUDA buffers (tnb_adam_update).  ``grad_scale`` may be
+        a Python float or a one-element device tensor of the parameters' dtype (read by the kernel: no host round trip)."""
         from . import _lib
         state["count"] += 1
         t = state["count"]
         lr = self.lr(t - 1) if callable(self.lr) else self.lr
         code = _lib.F64 if params.dtype == torch.float64 else _lib.F32
+        gs_dev = None
+        if torch.is_tensor(grad_scale):
+            gs_dev = grad_scale.reshape(1).to(params.dtype)
+            grad_scale = 1.0
         with torch.cuda.device(params.device):
-            _lib.check(_lib.lib().tnb_adam_update(
+            _lib.check(_lib.lib().tnb_adam_update_dev(
                 code, params.numel(), params.data_ptr(), grads.data_ptr(), state["mu"].data_ptr(), state["nu"].data_ptr(),
                 float(lr), self.b1, self.b2, self.eps, self.eps_root, t, float(grad_scale),
-                torch.cuda.current_stream(params.device).cuda_stream))
+                None if gs_dev is None else gs_dev.data_ptr(), torch.cuda.current_stream(params.device).cuda_stream))
         return state
 
 

@@ -11,7 +11,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import tn4ml_b200 as T  # noqa: E402
-from oracle import tn_oracle as O  # noqa: E402  (synthetic-input generators only)
+from tn4ml_b200 import synthetic as O  # noqa: E402  (synthetic-input generators)
 from tn4ml_b200 import _lib, metrics as M  # noqa: E402
 
 
