@@ -1,0 +1,94 @@
+"""The oracle against golden vectors produced by EXECUTING THE REFERENCE'S OWN SOURCE (tools/make_reference_golden.py:
+/root/reference/tn4ml imported unmodified over stand-ins for its absent third-party stack, tools/ref_shim/README.md).
+
+This is what pins the oracle: feature maps, embed()'s normaliser on both branches, the axis / index conventions of
+plain and classifier MPS, every MPS loss head, and -- through central finite differences of the reference-executed mean loss --
+individual entries of value_and_grad.  CPU only; the GPU parity tests then compare the kernels with the oracle.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tn_oracle as O
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+SPECS = {
+    "trig_k1": O.EmbSpec("trig", k=1), "trig_k2": O.EmbSpec("trig", k=2),
+    "fourier_p4": O.EmbSpec("fourier", p=4), "fourier_p8": O.EmbSpec("fourier", p=8),
+    "poly_d2_bias": O.EmbSpec("poly", degree=2, include_bias=True), "poly_d3": O.EmbSpec("poly", degree=3),
+    "rbf": O.EmbSpec("rbf", gamma=0.8, centers=(0.1, 0.5, 0.9)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(SPECS))
+def test_feature_maps_match_the_reference_source(name):
+    z = np.load(os.path.join(G, "reference_embeddings.npz"))
+    phi = O.feature_map(torch.tensor(z["x"]), SPECS[name]).numpy()
+    assert phi.shape[1] == int(z[f"dim_{name}"]) == SPECS[name].dim
+    assert np.allclose(phi, z[f"phi_{name}"], rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("branch", ["short", "long"])
+@pytest.mark.parametrize("name", ["poly_d2_bias", "trig_k1", "rbf"])
+def test_embed_normaliser_matches_the_reference_source(branch, name):
+    """embed() (embeddings.py:1374-1387): L <= 200 divides by norm**(1/L); L > 200 normalises site by site between QRs, which
+    may move a sign from one site to the next -- the product state (what every contraction sees) is the same."""
+    z = np.load(os.path.join(G, "reference_embeddings.npz"))
+    x = torch.tensor(z[f"embed_{branch}_{name}_x"])
+    ref = z[f"embed_{branch}_{name}"]
+    assert abs(float(z[f"embed_{branch}_{name}_norm"]) - 1.0) < 1e-12
+    mine = O.embed_batch(x[None, :], SPECS[name])[0].numpy()
+    if branch == "short":
+        assert np.allclose(mine, ref, rtol=1e-12, atol=1e-14)
+        return
+    k = np.abs(ref).argmax(axis=1)
+    signs = np.sign(ref[np.arange(len(ref)), k]) * np.sign(mine[np.arange(len(ref)), k])
+    assert np.allclose(mine * signs[:, None], ref, rtol=1e-10, atol=1e-13)
+    assert np.prod(signs) == 1.0  # the signs the QRs move around cancel in the product state
+
+
+def _sites(z):
+    n = len([k for k in z.files if k.startswith("site")])
+    return [torch.tensor(z[f"site{i}"]) for i in range(n)]
+
+
+def _check_fd(prob, x, arrays, t, idx, fd):
+    _, grads = O.value_and_grad(prob, x, arrays, t)
+    for (s, k), g in zip(idx, fd):
+        mine = float(grads[int(s)].reshape(-1)[int(k)])
+        assert abs(mine - g) <= 1e-7 * max(1.0, abs(g)), (int(s), int(k), mine, g)
+
+
+def test_plain_mps_nll_matches_the_reference_source():
+    z = np.load(os.path.join(G, "reference_mps_nll.npz"))
+    arrays, x = _sites(z), torch.tensor(z["x"])
+    prob = O.Problem("mps", SPECS["poly_d2_bias"], "nll")
+    per = O.per_sample_loss(prob, x, arrays).numpy()
+    assert np.allclose(per, z["per_sample_loss"], rtol=1e-12)
+    _check_fd(prob, x, arrays, None, z["fd_index"], z["fd_grad"])
+
+
+@pytest.mark.parametrize("head", ["softmax_xent", "mse", "softmax_xent_weighted"])
+def test_classifier_heads_match_the_reference_source(head):
+    z = np.load(os.path.join(G, "reference_classifier.npz"))
+    arrays, x, y = _sites(z), torch.tensor(z["x"]), torch.tensor(z["y"])
+    cw = tuple(z["class_weights"]) if head == "softmax_xent_weighted" else None
+    prob = O.Problem("mps", SPECS["trig_k1"], head, class_weights=cw)
+    per = O.per_sample_loss(prob, x, arrays, y).numpy()
+    assert np.allclose(per, z[f"loss_{head}"], rtol=1e-12)
+    _check_fd(prob, x, arrays, y, z[f"fd_index_{head}"], z[f"fd_grad_{head}"])
+
+
+def test_classifier_outputs_match_the_reference_source():
+    """(model & data) ^ all with the class tensor built by the reference's MPS_initialize(arrays=..., class_index=...)."""
+    z = np.load(os.path.join(G, "reference_classifier.npz"))
+    arrays, x = _sites(z), torch.tensor(z["x"])
+    out = O.mps_outputs(O.embed_batch(x, SPECS["trig_k1"]), arrays).numpy()
+    # MPS_initialize normalises the model it builds (mps.py:470-490), so the raw outputs differ from those of the given arrays
+    # by ONE positive factor (the heads above are scale free): same direction, same signs, constant ratio
+    ratio = out / z["outputs"]
+    assert ratio.min() > 0 and np.allclose(ratio, ratio.mean(), rtol=1e-10)
+    assert int(z["class_site"]) == O.canon_mps_sites(arrays)[1]

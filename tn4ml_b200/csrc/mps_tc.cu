@@ -196,13 +196,17 @@ int mps_tc_backward(const tnb_problem *p, const MpsPlan &P, long long B, const v
     Da.mgroups = ((p->chi + Da.ra - 1) / Da.ra) * ((Da.Dv + Da.cpg - 1) / Da.cpg);
     // split K (the batch) so that the grid fills the 148 SMs about four times over with little wave quantisation
     const long long ctas = (long long)(pass == 0 ? s1 - s0 : 1) * Da.mgroups;
-    long long best = 1;
+    // ... and so that no TMEM accumulator takes more than ~3 k MMAs: tcgen05 accumulates with truncation, and a coherent
+    // sum of n terms loses about n / 4 ulp (1.2e-4 of the largest gradient entries at 43 k samples per split, measured
+    // against the SIMT family); 16 k samples per split keep that below 5e-5.
+    const long long nsp_min = (B + 16383) / 16384;
+    long long best = nsp_min;
     double best_eff = 0.0;
-    for (long long nsp = 1; nsp <= maxsp && nsp <= 64; ++nsp) {
+    for (long long nsp = nsp_min; nsp <= maxsp && nsp <= 64; ++nsp) {
       const long long n = ctas * nsp;
       const double eff = (double)n / (double)((n + 147) / 148 * 148);
       const double score = eff - (n < 148 * 3 ? 1.0 : 0.0) - 0.002 * (double)nsp;  // prefer >= 3 waves, fewer splits
-      if (nsp == 1 || score > best_eff) { best = nsp; best_eff = score; }
+      if (nsp == nsp_min || score > best_eff) { best = nsp; best_eff = score; }
     }
     Da.nsplit = (int)best;
     Da.bchunk = ((B + Da.nsplit - 1) / Da.nsplit + kDaKC - 1) / kDaKC * kDaKC;

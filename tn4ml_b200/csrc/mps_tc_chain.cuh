@@ -272,6 +272,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
   // Early release: once the last column chunk's MMAs have consumed the K-slabs [0, krel), the operand columns
   // n < 16*krel (= the outputs of all earlier chunks) may be overwritten with the next operand.
   const int krel = (NH - 1) * (KS / NH);
+  // K-slab order of a (step, chunk).  tcgen05 accumulates into TMEM with truncation (round toward zero): every MMA that adds
+  // to an accumulator already at its final magnitude shrinks it by about half an ulp.  With a fixed slab order and a
+  // near-identity site tensor (the reference's initialisation, mps.py:348-355) the SAME columns take the most truncations at
+  // every site, and the bias grows linearly along the chain (tools/parity_report.py: 1.1e-3 at L = 196, chi = 256).
+  // Rotating the order from step to step spreads the truncations evenly over the columns: a uniform relative shrink, which
+  // the per-sample normalisation cancels.  The last chunk keeps its low slabs [0, krel) first (early operand release).
+  // (one modulo per (step, chunk), outside the per-stage loops: the issuer warp is the critical path)
+  auto slab_rot = [&](int step, int h, int &r_lo, int &r_hi) {
+    const bool split = h == NH - 1 && krel > 0;
+    r_lo = (5 * step + 3 * h) % (split ? krel : KS);
+    r_hi = split ? (5 * step + 3 * h) % (KS - krel) : 0;
+  };
+  auto slab_of = [&](int h, int q, int r_lo, int r_hi) -> int {
+    if (h == NH - 1 && krel > 0) {
+      if (q < krel) { const int k = q + r_lo; return k >= krel ? k - krel : k; }
+      const int k = q + r_hi;
+      return k >= KS ? k - (KS - krel) : k;
+    }
+    const int k = q + r_lo;
+    return k >= KS ? k - KS : k;
+  };
 
   if (warp == kTcMmaWarp + 2) {
     // ===== image writer: operand generation g (published as phase g of a_ready) -> HBM stash, in paced pieces =====
@@ -323,18 +344,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const int per_step = NH * KS;
       for (int step = 0; step < total; ++step) {
         const uint8_t *img = step_image(step);
         for (int t = 0; t < TILES; ++t) {
-          for (int hk = 0; hk < per_step; ++hk) {
+          for (int h = 0, hk = 0; h < NH; ++h) {
+           int r_lo, r_hi;
+           slab_rot(step, h, r_lo, r_hi);
+           for (int q = 0; q < KS; ++q, ++hk) {
             ptx::mbar_wait(&empty[stage], phase ^ 1);
             const uint32_t nbytes = TNB_DBG(16) ? 1024u : A.stage_bytes;  // (trace-build experiment: short loads, wrong results)
             ptx::mbar_expect_tx(&full[stage], nbytes);
+            const int src = h * KS + slab_of(h, q, r_lo, r_hi);  // the q-th stage of chunk h holds K-slab slab_of(h, q)
             // (CTA pair: the stage image is [rank][plane][columns / 2]; each CTA fetches its own half)
-            ptx::bulk_g2s(stages + (size_t)stage * A.stage_bytes, img + ((size_t)hk * CG + rank) * A.stage_bytes,
+            ptx::bulk_g2s(stages + (size_t)stage * A.stage_bytes, img + ((size_t)src * CG + rank) * A.stage_bytes,
                           nbytes, &full[stage]);
             if (++stage == A.nstage) { stage = 0; phase ^= 1; }
+           }
           }
         }
       }
@@ -372,7 +397,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
           if (t == 0) TNB_TRACE(3, step, 0);
           for (int h = 0; h < NH; ++h) {
             const uint32_t d = tmem_base + (uint32_t)t * tile_cols + (uint32_t)h * A.NMMA;
-            for (int ks = 0; ks < KS; ++ks) {
+            int r_lo, r_hi;
+            slab_rot(step, h, r_lo, r_hi);
+            for (int q = 0; q < KS; ++q) {
+              const int ks = slab_of(h, q, r_lo, r_hi);  // operand K-slab of the q-th stage of this chunk
               const long long c0 = TNB_CLOCK();
               ptx::mbar_wait(&full[stage], phase);
               const long long c1 = TNB_CLOCK();
@@ -387,25 +415,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
                 const uint64_t db_hi = ptx::smem_desc_kmajor(st, 128, 256);
                 const uint64_t db_lo = ptx::smem_desc_kmajor(st + lo_plane, 128, 256);
                 if (CG == 2) {
-                  ptx::mma_f16_pair(d, da_hi, db_hi, idesc, (ks > 0 || accum_step) ? 1u : 0u);
+                  ptx::mma_f16_pair(d, da_hi, db_hi, idesc, (q > 0 || accum_step) ? 1u : 0u);
                   ptx::mma_f16_pair(d, da_lo, db_hi, idesc, 1u);
                   ptx::mma_f16_pair(d, da_hi, db_lo, idesc, 1u);
                   ptx::mma_commit_pair(&empty[stage]);
-                  if (h == NH - 1 && ks == krel - 1) ptx::mma_commit_pair(&a_rel[t]);
-                  if (ks == KS - 1) ptx::mma_commit_pair(&acc_full[t * kTcMaxNH + h]);
+                  if (h == NH - 1 && q == krel - 1) ptx::mma_commit_pair(&a_rel[t]);
+                  if (q == KS - 1) ptx::mma_commit_pair(&acc_full[t * kTcMaxNH + h]);
                 } else {
-                  ptx::mma_f16(d, da_hi, db_hi, idesc, (ks > 0 || accum_step) ? 1u : 0u);
+                  ptx::mma_f16(d, da_hi, db_hi, idesc, (q > 0 || accum_step) ? 1u : 0u);
                   ptx::mma_f16(d, da_lo, db_hi, idesc, 1u);
                   ptx::mma_f16(d, da_hi, db_lo, idesc, 1u);
                   ptx::mma_commit(&empty[stage]);
-                  if (h == NH - 1 && ks == krel - 1) ptx::mma_commit(&a_rel[t]);
-                  if (ks == KS - 1) ptx::mma_commit(&acc_full[t * kTcMaxNH + h]);
+                  if (h == NH - 1 && q == krel - 1) ptx::mma_commit(&a_rel[t]);
+                  if (q == KS - 1) ptx::mma_commit(&acc_full[t * kTcMaxNH + h]);
                 }
               }
               __syncwarp();
               if (++stage == A.nstage) { stage = 0; phase ^= 1; }
 #ifdef TNB_TC_TRACE
-              if (ks == 0) tr_full = tr_pfull = tr_issue = 0;
+              if (q == 0) tr_full = tr_pfull = tr_issue = 0;
               tr_full += c1 - c0; tr_pfull += c2 - c1; tr_issue += TNB_CLOCK() - c2;
 #endif
             }

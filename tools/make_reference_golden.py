@@ -1,0 +1,156 @@
+#!/usr/bin/env python
+"""Golden vectors produced by EXECUTING THE REFERENCE'S OWN SOURCE (run in this container; /root/reference is not on the
+GPU box, the committed .npz files are what travels).
+
+/root/reference/tn4ml is imported unmodified; its absent third-party stack (jax, optax, quimb, autoray, funcy) is replaced by
+the stand-ins in tools/ref_shim (numpy semantics; a generic named-index tensor network -- see tools/ref_shim/README.md).
+For every case the script stores the inputs and what the reference code returned:
+
+  reference_embeddings.npz   Embedding.__call__ of the four feature maps on the hot path (embeddings.py:327-351, 394-423,
+                             588-602, 680-717) and embed()'s normalised product state on both branches (:1374-1387)
+  reference_mps_nll.npz      tn4ml.metrics.NegLogLikelihood(model, embed(x)) per sample, model = tn4ml.models.mps.
+                             MatrixProductState(arrays) (plain MPS, squeezed boundaries) -- metrics.py:17-53
+  reference_classifier.npz   OptaxWrapper(optax.softmax_cross_entropy), CrossEntropySoftmax-style heads, MeanSquaredError,
+                             CrossEntropyWeighted on a classifier built by the reference's MPS_initialize(arrays=...,
+                             class_index=...) (mps.py:296-330 index naming) -- metrics.py:291-333, 336-396, 423-532
+  + central finite differences of the reference-executed mean loss with respect to a few site-tensor entries (the shim has no
+    autodiff), which pin value_and_grad (model.py:554-566) entry by entry.
+
+tests/test_reference_golden.py checks the oracle (CPU) against these files; the GPU parity tests check the kernels against the
+oracle.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference/tn4ml"
+sys.path.insert(0, os.path.join(ROOT, "tools", "ref_shim"))
+sys.path.insert(0, ROOT)
+pkg = types.ModuleType("tn4ml")  # the package WITHOUT its __init__ (which imports plotting / sklearn helpers)
+pkg.__path__ = [REF]
+sys.modules["tn4ml"] = pkg
+
+import optax  # noqa: E402  (stand-in)
+import tn4ml.embeddings as RE  # noqa: E402  (reference source)
+import tn4ml.metrics as RM  # noqa: E402
+import tn4ml.models.mps as RMPS  # noqa: E402
+
+from tn4ml_b200 import synthetic as S  # noqa: E402  (seeded data generators)
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def embeddings_file():
+    xs = np.linspace(0.013, 1.0, 23)
+    out = {"x": xs}
+    maps = {
+        "trig_k1": RE.TrigonometricEmbedding(k=1), "trig_k2": RE.TrigonometricEmbedding(k=2),
+        "fourier_p4": RE.FourierEmbedding(p=4), "fourier_p8": RE.FourierEmbedding(p=8),
+        "poly_d2_bias": RE.PolynomialEmbedding(degree=2, n=1, include_bias=True),
+        "poly_d3": RE.PolynomialEmbedding(degree=3, n=1, include_bias=False),
+        "rbf": RE.GaussianRBFEmbedding(centers=np.array([0.1, 0.5, 0.9]), gamma=0.8),
+    }
+    for name, phi in maps.items():
+        out[f"phi_{name}"] = np.stack([np.asarray(phi(np.asarray(x)), dtype=np.float64).reshape(-1) for x in xs])
+        out[f"dim_{name}"] = np.array(phi.dim)
+    # embed(): the normalised product state, L <= 200 branch and L > 200 branch
+    rng = np.random.default_rng(5)
+    for name, L in (("short", 7), ("long", 203)):
+        x = 1.0 - rng.random(L)
+        for mname in ("poly_d2_bias", "trig_k1", "rbf"):
+            mps = RE.embed(x, maps[mname])
+            arr = np.stack([np.asarray(t.data, dtype=np.float64).reshape(-1) for t in mps.tensors])
+            out[f"embed_{name}_{mname}_x"] = x
+            out[f"embed_{name}_{mname}"] = arr
+            out[f"embed_{name}_{mname}_norm"] = np.array(float(mps.norm()))
+    np.savez_compressed(os.path.join(OUT, "reference_embeddings.npz"), **out)
+    return out
+
+
+def mps_nll_file():
+    L, chi, d, B = 8, 5, 3, 6
+    arrays = [a.numpy() for a in S.make_mps_arrays(L, chi, d, std=0.2, seed=11, squeeze_ends=True, identity_all=True)]
+    x = S.make_inputs(B, L, seed=12).numpy()
+    phi = RE.PolynomialEmbedding(degree=2, n=1, include_bias=True)
+
+    def losses(arrs):
+        model = RMPS.MatrixProductState([np.array(a) for a in arrs])
+        return np.array([float(RM.NegLogLikelihood(model, RE.embed(xb, phi))) for xb in x])
+
+    per = losses(arrays)
+    fd = _finite_differences(lambda arrs: losses(arrs).mean(), arrays, seed=3)
+    np.savez_compressed(os.path.join(OUT, "reference_mps_nll.npz"), x=x, per_sample_loss=per, L=L, chi=chi, d=d,
+                        fd_index=fd[0], fd_grad=fd[1], **{f"site{i}": a for i, a in enumerate(arrays)})
+    return per
+
+
+def _finite_differences(f, arrays, seed, n=10, h=1e-5):
+    """Central differences of f with respect to n random entries (site, flat index) of the site tensors."""
+    rng = np.random.default_rng(seed)
+    idx, grads = [], []
+    for _ in range(n):
+        s = int(rng.integers(len(arrays)))
+        k = int(rng.integers(arrays[s].size))
+        base = [a.copy() for a in arrays]
+        e = np.zeros(arrays[s].size)
+        e[k] = h
+        base[s] = arrays[s] + e.reshape(arrays[s].shape)
+        fp = f(base)
+        base[s] = arrays[s] - e.reshape(arrays[s].shape)
+        fm = f(base)
+        idx.append((s, k))
+        grads.append((fp - fm) / (2 * h))
+    return np.array(idx), np.array(grads)
+
+
+def classifier_file():
+    L, chi, d, C, B, cls = 7, 4, 2, 3, 5, 3  # class tensor at 0-based site 3 == class_index 4 (1-based, mps.py:183-213)
+    arrays = [a.numpy() for a in S.make_mps_arrays(L, chi, d, class_site=cls, C=C, std=0.2, seed=21)]
+    x = S.make_inputs(B, L, seed=22).numpy()
+    y = S.make_labels(B, C, seed=23).numpy()
+    phi = RE.TrigonometricEmbedding(k=1)
+    cw = np.array([0.7, 1.6, 1.1])
+
+    def build(arrs):
+        return RMPS.MPS_initialize(L, arrays=[np.array(a) for a in arrs], class_index=cls + 1)
+
+    def run(loss, arrs, with_targets=True):
+        model = build(arrs)
+        out = []
+        for xb, yb in zip(x, y):
+            v = loss(model, RE.embed(xb, phi), yb) if with_targets else loss(model, RE.embed(xb, phi))
+            out.append(float(np.asarray(v).reshape(-1)[0]))
+        return np.array(out)
+
+    heads = {
+        "softmax_xent": RM.OptaxWrapper(optax.softmax_cross_entropy),
+        "mse": RM.MeanSquaredError,
+        "softmax_xent_weighted": RM.CrossEntropyWeighted(cw),
+    }
+    out = {"x": x, "y": y, "class_weights": cw, "L": L, "chi": chi, "d": d, "C": C, "class_site": cls}
+    for name, loss in heads.items():
+        out[f"loss_{name}"] = run(loss, arrays)
+        fd = _finite_differences(lambda arrs, loss=loss: run(loss, arrs).mean(), arrays, seed=5)
+        out[f"fd_index_{name}"], out[f"fd_grad_{name}"] = fd
+    # raw outputs y[c] of the contraction (what Model.forward returns, model.py:312-316)
+    model = build(arrays)
+    ys = []
+    for xb in x:
+        t = (model & RE.embed(xb, phi)) ^ all
+        ys.append(np.asarray(t.data).reshape(-1))
+    out["outputs"] = np.stack(ys)
+    out.update({f"site{i}": a for i, a in enumerate(arrays)})
+    np.savez_compressed(os.path.join(OUT, "reference_classifier.npz"), **out)
+    return out
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    e = embeddings_file()
+    print("embeddings:", sorted(k for k in e if k.startswith("phi_")))
+    print("nll per sample:", mps_nll_file())
+    c = classifier_file()
+    print("classifier:", {k: v for k, v in c.items() if k.startswith("loss_")})
