@@ -169,6 +169,30 @@ int tnb_adam_update_dev(int32_t dtype, int64_t n, void *params, const void *grad
 int64_t tnb_gradient_clip_scratch_bytes(const tnb_problem *prob);
 int tnb_gradient_clip(const tnb_problem *prob, void *grads, double threshold, double pre_scale, void *scratch, void *stream);
 
+/* ---- model-only operations of the training loop ------------------------------------------------------
+ * tnb_problem.{kind, dtype, L, chi, d, n_out, out_site, spacing} describe the packed model; embedding / head are ignored. */
+/* regulariser kinds -- tn4ml/metrics.py:89-168.  l = log(norm) with norm = sqrt(<A|A>); kind + TNB_REG_TRACE selects the
+ * form the reference uses when type(model) is SpacedMatrixProductOperator, where "norm" is Tr(P^dag P) = <A|A> itself
+ * (metrics.py:99-103: model.H.apply(model) contracted, smpo.py:406-438). */
+enum {
+  TNB_REG_LOG_FROB = 0,      /* LogFrobNorm      l                 metrics.py:89-105   */
+  TNB_REG_LOG_POW_FROB = 1,  /* LogPowFrobNorm   log(norm^2) = 2 l metrics.py:108-124  */
+  TNB_REG_LOG_RELU_FROB = 2, /* LogReLUFrobNorm  max(0, l)         metrics.py:127-146  */
+  TNB_REG_QUAD_FROB = 3,     /* QuadFrobNorm     (l - 1)^2         metrics.py:149-168  */
+  TNB_REG_TRACE = 4
+};
+int64_t tnb_norm_workspace_bytes(const tnb_problem *prob);
+/* <A|A> of the model by a device transfer-matrix sweep (tn4ml/models/tn.py:66-80, smpo.py:234-248):
+ *   log2_norm2 [1] float64 (device): log2 <A|A>  (a logarithm: models of several hundred sites leave the float range)
+ * and, if n_regs > 0: reg_value [1] float64 (device, may be NULL) += sum_r reg_coefs[r] * reg_r(model), and grads (packed,
+ * dtype, may be NULL) += the gradient of that sum -- what jax.grad produces for the `reg(model)` term of CombinedLoss
+ * (metrics.py:535-592). */
+int tnb_norm(const tnb_problem *prob, const void *params, double *log2_norm2, int32_t n_regs, const int32_t *reg_kinds,
+             const double *reg_coefs, void *grads, double *reg_value, void *workspace, int64_t workspace_bytes, void *stream);
+/* params[i] *= 2^(mult * *log2_value) for n elements: Model.normalize() is mult = -1 / (2 L) with log2_value = log2 <A|A>
+ * (every site divided by norm^(1/L), tn.py:103-107), or mult = -1/2 on one site (insert=). */
+int tnb_scale(int32_t dtype, int64_t n, void *params, const double *log2_value, double mult, void *stream);
+
 /* Embedding.__call__ for n scalars: phi [n, d] (dtype), before embed()'s normaliser. */
 int tnb_embed(const tnb_embedding *emb, int32_t dtype, int64_t n, const void *x, void *phi,
               void *stream);

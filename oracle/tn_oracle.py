@@ -490,6 +490,39 @@ def smpo_dense_sqnorm(phi: torch.Tensor, arrays: Sequence[torch.Tensor], spacing
 
 
 # ----------------------------------------------------------------------------
+# Model-only quantities: <A|A>, the Frobenius regularisers, normalize
+# ----------------------------------------------------------------------------
+
+
+def model_log_sqnorm(sites4: Sequence[torch.Tensor]) -> torch.Tensor:
+    """log <A|A> of a chain of 4-D sites (chi_l, chi_r, d, n) by the transfer-matrix sweep (tn.py:66-80: norm = sqrt(conj & self
+    contracted)), renormalised per site so that long chains stay in range."""
+    E = torch.ones(1, 1, dtype=sites4[0].dtype)
+    logs = torch.zeros((), dtype=sites4[0].dtype)
+    for A in sites4:
+        E = torch.einsum("lm,lrsk,mnsk->rn", E, A, A)
+        m = E.abs().max()
+        E = E / m
+        logs = logs + torch.log(m)
+    return logs + torch.log(E[0, 0])
+
+
+def regulariser(sites4: Sequence[torch.Tensor], kind: str, norm_is_trace: bool = False) -> torch.Tensor:
+    """metrics.py:89-168.  l = log(norm); norm = sqrt(<A|A>) (model.norm()), or <A|A> itself when the model is a
+    SpacedMatrixProductOperator (metrics.py:99-103: model.H.apply(model) fully contracted = Tr(P^dag P))."""
+    l = model_log_sqnorm(sites4) * (1.0 if norm_is_trace else 0.5)
+    if kind == "log_frob":
+        return l  # metrics.py:105
+    if kind == "log_pow_frob":
+        return 2.0 * l  # log(norm^2)  metrics.py:124
+    if kind == "log_relu_frob":
+        return torch.clamp(l, min=0.0)  # metrics.py:146
+    if kind == "quad_frob":
+        return (l - 1.0) ** 2  # metrics.py:168
+    raise ValueError(kind)
+
+
+# ----------------------------------------------------------------------------
 # Synthetic problems of the five BASELINE.json configs (SURVEY 8d): framework-neutral DATA generators, shared with
 # bench.py's product arm, live in tn4ml_b200/synthetic.py (no algorithm of the path in there); re-exported here so that
 # the tests keep one namespace.

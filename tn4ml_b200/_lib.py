@@ -16,6 +16,7 @@ KIND_MPS, KIND_SMPO = 0, 1
 F32, F64 = 0, 1
 PREC_SIMT, PREC_TENSOR = 0, 1
 EMB_TRIG, EMB_FOURIER, EMB_POLY, EMB_RBF = 0, 1, 2, 3
+REG_LOG_FROB, REG_LOG_POW_FROB, REG_LOG_RELU_FROB, REG_QUAD_FROB = range(4)
 (HEAD_NLL, HEAD_SOFTMAX_XENT, HEAD_SOFTMAX_XENT_WEIGHTED, HEAD_XENT_SOFTMAX_ARGMAX, HEAD_MSE,
  HEAD_TSN, HEAD_LOGQUAD, HEAD_QUAD) = range(8)
 
@@ -68,6 +69,10 @@ SYMBOLS = {
     "tnb_backward_part": (C.c_int, [_P(TnbProblem), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32]),
     "tnb_part_sites": (C.c_int32, [_P(TnbProblem), C.c_int32, C.c_int32, _P(C.c_int32), _P(C.c_int32)]),
+    "tnb_norm_workspace_bytes": (C.c_int64, [_P(TnbProblem)]),
+    "tnb_norm": (C.c_int, [_P(TnbProblem), C.c_void_p, C.c_void_p, C.c_int32, _P(C.c_int32), _P(C.c_double), C.c_void_p,
+                           C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "tnb_scale": (C.c_int, [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
     "tnb_profile": (C.c_int, [C.c_int32]),
     "tnb_profile_read": (C.c_int32, [C.c_char_p, _P(C.c_float), C.c_int32]),
     "tnb_launch_count": (C.c_int64, []),

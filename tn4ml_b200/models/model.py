@@ -168,34 +168,126 @@ class Model:
 
     # ---- model-only operations (plain device tensor algebra) -----
     def _canon4(self, i: int) -> torch.Tensor:
+        return self._canon4_of(self._packed, i)
+
+    def _canon4_of(self, packed: torch.Tensor, i: int) -> torch.Tensor:
+        """Site i of a packed buffer (parameters or gradients) as its (chi_l, chi_r, d, n_i) block."""
         offs, _ = self._site_offsets()
         cl, cr, d, nj, _ = self._canon[i]
-        return self._packed[offs[i]: offs[i] + self.chi * self.chi * d * nj].view(self.chi, self.chi, d, nj)[:cl, :cr]
+        return packed[offs[i]: offs[i] + self.chi * self.chi * d * nj].view(self.chi, self.chi, d, nj)[:cl, :cr]
+
+    # the reference's regularisers take "norm" = Tr(P^dag P) for a SpacedMatrixProductOperator (exact type) and
+    # sqrt(<A|A>) for everything else (metrics.py:99-103)
+    _reg_norm_is_trace = False
+
+    def _norm_problem(self):
+        p = _lib.TnbProblem()
+        p.kind, p.dtype = self.kind, (_lib.F64 if self.dtype == torch.float64 else _lib.F32)
+        p.L, p.chi, p.d, p.n_out, p.out_site, p.spacing = self.L, self.chi, self.phys_dim, self.n_out, self.out_site, max(self.spacing, 1)
+        return p
+
+    def _log2_norm2(self, regs=None, grads: torch.Tensor | None = None):
+        """log2 <A|A> (device float64 [1]) by the transfer-matrix kernels (tnb_norm); with `regs`, also the value of
+        sum coef * reg(model) (device float64 [1]) and its gradient ADDED to `grads`."""
+        import ctypes as C
+        if not self._packed.is_cuda:
+            raise RuntimeError("tn4ml_b200 runs on CUDA devices only (no CPU fallback)")
+        lib = _lib.lib()
+        prob = self._norm_problem()
+        dev = self._packed.device
+        ws = getattr(self, "_norm_ws", None)
+        need = int(lib.tnb_norm_workspace_bytes(C.byref(prob)))
+        if ws is None or ws.numel() < need or ws.device != dev:
+            ws = self._norm_ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        out = torch.zeros(2, dtype=torch.float64, device=dev)
+        kinds = coefs = None
+        n = 0
+        if regs:
+            names = {"log_frob": _lib.REG_LOG_FROB, "log_pow_frob": _lib.REG_LOG_POW_FROB,
+                     "log_relu_frob": _lib.REG_LOG_RELU_FROB, "quad_frob": _lib.REG_QUAD_FROB}
+            n = len(regs)
+            kinds = (C.c_int32 * n)(*[names[r.kind] + (4 if self._reg_norm_is_trace else 0) for r in regs])
+            coefs = (C.c_double * n)(*[float(r.coef) for r in regs])
+        with torch.cuda.device(dev):
+            _lib.check(lib.tnb_norm(C.byref(prob), self._packed.data_ptr(), out.data_ptr(), n, kinds, coefs,
+                                    None if grads is None else grads.data_ptr(), out[1:].data_ptr() if n else None,
+                                    ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
+        return out[0], out[1]
 
     def norm(self, **_opts) -> torch.Tensor:
-        """sqrt(<A|A>) by a transfer-matrix sweep (tn.py:66-80, smpo.py:234-248)."""
-        E = torch.ones(1, 1, dtype=self.dtype, device=self._packed.device)
-        logscale = 0.0
-        for i in range(self.L):
-            A = self._canon4(i)
-            E = torch.einsum("lm,lrsk,mnsk->rn", E, A, A)
-            s = E.abs().max()
-            E = E / s
-            logscale = logscale + torch.log(s)
-        return torch.exp(0.5 * (torch.log(E[0, 0]) + logscale))
+        """sqrt(<A|A>) by a device transfer-matrix sweep (tn.py:66-80, smpo.py:234-248)."""
+        l2, _ = self._log2_norm2()
+        return torch.exp2(0.5 * l2).to(self.dtype)
 
     def normalize(self, insert=None):
-        """tn.py:82-113 / mps.py:34-51 / smpo.py:208-232.  L > 200 uses the reference's
-        site-by-site scheme in its norm-only form (each site divided by its Frobenius norm)."""
+        """tn.py:82-113 / mps.py:34-51 / smpo.py:208-232.  L <= 200: every site divided by norm^(1/L) (or one site by norm);
+        L > 200: the reference's site-by-site scheme -- site i divided by its Frobenius norm, then left-canonised (QR, R into
+        site i+1) -- which leaves a left-canonical chain with <A|A> = 1."""
+        import ctypes as C
         if self.L > 200:
-            for v in self._arrays:
-                v.div_(torch.linalg.norm(v))
+            self._qr_sweep(range(self.L - 1), left=True, normalize_sites=True)
             return
-        nrm = self.norm()
-        if insert is None:
-            self._packed.div_(nrm ** (1.0 / self.L))
-        else:
-            self._arrays[insert].div_(nrm)
+        l2, _ = self._log2_norm2()
+        lib = _lib.lib()
+        code = _lib.F64 if self.dtype == torch.float64 else _lib.F32
+        dev = self._packed.device
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            if insert is None:
+                _lib.check(lib.tnb_scale(code, self._packed.numel(), self._packed.data_ptr(), l2.data_ptr(), -0.5 / self.L, st))
+            else:
+                if not (0 <= insert < self.L):
+                    raise IndexError(f"Insert index {insert} is out of bounds for the tensor list.")  # tn.py:109-112
+                offs, total = self._site_offsets()
+                end = offs[insert + 1] if insert + 1 < self.L else total
+                seg = self._packed[offs[insert]:end]
+                _lib.check(lib.tnb_scale(code, seg.numel(), seg.data_ptr(), l2.data_ptr(), -0.5, st))
+
+    # ---- QR sweeps: canonicalize(center) and the L > 200 normalize (model.py:879-883, tn.py:93-101) -----------------
+    def _qr_sweep(self, sites, left: bool, normalize_sites: bool = False):
+        """left=True: for i in sites: (optionally A_i /= ||A_i||), A_i = Q R over (chi_l * d * n_i, chi_r), A_i <- Q,
+        A_{i+1} <- R A_{i+1}.  left=False: the mirror image (rows = chi_l, R into site i-1).  Householder QR (LAPACK geqrf
+        convention, the one jnp.linalg.qr uses) through torch.linalg.qr on the device: plumbing, not the hot path."""
+        for i in sites:
+            A = self._canon4(i)                      # (cl, cr, d, n) view of the packed slab
+            if normalize_sites and i > 0:
+                A.div_(torch.linalg.norm(A))
+            cl, cr, d, n = A.shape
+            nb = i + 1 if left else i - 1
+            B = self._canon4(nb)
+            if left:
+                M = A.permute(0, 2, 3, 1).reshape(cl * d * n, cr)
+                Q, R = torch.linalg.qr(M)            # Q (rows, k), R (k, cr), k = min(rows, cr)
+                k = Q.shape[1]
+                if k < cr:                            # fewer rows than columns: pad back to the slab's bond
+                    Q = torch.cat([Q, Q.new_zeros(Q.shape[0], cr - k)], dim=1)
+                    R = torch.cat([R, R.new_zeros(cr - k, cr)], dim=0)
+                A.copy_(Q.reshape(cl, d, n, cr).permute(0, 3, 1, 2))
+                B.copy_(torch.einsum("ab,brsk->arsk", R, B))
+            else:
+                M = A.permute(1, 2, 3, 0).reshape(cr * d * n, cl)
+                Q, R = torch.linalg.qr(M)
+                k = Q.shape[1]
+                if k < cl:
+                    Q = torch.cat([Q, Q.new_zeros(Q.shape[0], cl - k)], dim=1)
+                    R = torch.cat([R, R.new_zeros(cl - k, cl)], dim=0)
+                A.copy_(Q.reshape(cr, d, n, cl).permute(3, 0, 1, 2))
+                B.copy_(torch.einsum("lask,ba->lbsk", B, R))
+        if normalize_sites:
+            last = self._canon4(self.L - 1)
+            last.div_(torch.linalg.norm(last))
+
+    def canonicalize(self, where: int, inplace: bool = True, **_opts):
+        """Mixed-canonical form around site `where` (quimb's canonicalize, used by train(canonize=(True, c)),
+        model.py:882-883): sites left of it left-orthogonal, sites right of it right-orthogonal; the state is unchanged."""
+        if not (0 <= where < self.L):
+            raise ValueError(f"canonical center {where} out of range")
+        m = self if inplace else self.copy()
+        m._qr_sweep(range(0, where), left=True)
+        m._qr_sweep(range(m.L - 1, where, -1), left=False)
+        return m
+
+    canonize = canonicalize
 
     # ---- configure (model.py:155-276) ---------------------------------------------
     def configure(self, **kwargs):
@@ -259,26 +351,13 @@ class Model:
             self._engine_cache[key] = eng
         return eng, expr
 
-    def _reg_value_and_grad(self, expr: LossExpr):
-        """Model-only regularisers (metrics.py:89-168): value and packed gradient by autograd
-        over the transfer-matrix norm.  Batch independent; not part of the fused kernels."""
+    def _reg_value_and_grad(self, expr: LossExpr, grads: torch.Tensor | None = None):
+        """Model-only regularisers (metrics.py:89-168): value (device scalar) from the transfer-matrix kernels; the gradient is
+        ADDED to `grads` in place by the same call (tnb_norm).  Batch independent."""
         if not expr or not expr.regs:
-            return None, None
-        p = self._packed.detach().clone().requires_grad_(True)
-        saved = self._packed
-        self._packed = p
-        try:
-            nrm = self.norm()
-        finally:
-            self._packed = saved
-        total = 0.0
-        for r in expr.regs:
-            ln = torch.log(nrm)
-            v = {"log_frob": ln, "log_pow_frob": 2 * ln, "log_relu_frob": torch.clamp(ln, min=0.0),
-                 "quad_frob": (ln - 1.0) ** 2}[r.kind]
-            total = total + r.coef * v
-        (g,) = torch.autograd.grad(total, p)
-        return total.detach(), g
+            return None
+        _, val = self._log2_norm2(expr.regs, grads)
+        return val
 
     def create_train_step(self, params=None, loss_func=None, *, embedding=None, dtype=None):
         """model.py:529-618: returns (train_step, opt_state).  ``train_step(params, opt_state, data,
@@ -314,16 +393,15 @@ class Model:
                 loss_sum, g = eng.value_and_grad(self._packed, x, t, denom=1, grads=grads, reducer=reducer)
                 loss = loss_sum / n_cnt
                 gscale = (1.0 / n_cnt).to(self._packed.dtype)
-            rv, rg = self._reg_value_and_grad(expr)
             fused = (isinstance(self._opt, optim._Adam) and g.is_cuda and g.dtype == self._packed.dtype
                      and g.is_contiguous())
-            if rv is not None or grad_clip_threshold or not fused:
+            has_reg = bool(expr and expr.regs)
+            if has_reg or grad_clip_threshold or not fused:
                 if torch.is_tensor(gscale):
                     g.mul_(gscale)
                     gscale = 1.0
-            if rv is not None:
-                loss = loss + rv
-                g = g.add_(rg)
+            if has_reg:
+                loss = loss + self._reg_value_and_grad(expr, g)  # value; gradient added to g by the kernel
             if grad_clip_threshold:  # util.gradient_clip (util.py:131-155): one factor per SITE tensor, eps 1e-6
                 eng.gradient_clip(g, grad_clip_threshold)
             if fused:  # optimizer + update_tensors of train_step (model.py:591-614) as one kernel on the packed buffer
@@ -344,8 +422,6 @@ class Model:
             embedding = TrigonometricEmbedding()
         if self.strategy != "global":
             raise ValueError("Only Global Gradient Descent and DMRG Sweeping strategy is supported for now!")
-        if canonize and canonize[0]:
-            raise NotImplementedError("canonize=(True, c) is a model-only QR sweep outside the fused path")
         if not hasattr(self, "_opt"):
             raise AttributeError("Provide 'optimizer' or sequence of 'gradient_transforms'! ")
         inputs = np.asarray(inputs)
@@ -388,6 +464,8 @@ class Model:
                 loss_batch = loss_batch + loss_curr.reshape(())
                 if normalize:
                     self.normalize()
+                if canonize and canonize[0]:  # model.py:882-883
+                    self.canonicalize(canonize[1], inplace=True)
             loss_epoch = float((loss_batch / n_batches).item())  # the one D2H sync per epoch (model.py:887)
             self.history["loss"].append(loss_epoch)
             self.history["epoch_time"].append(time() - time_epoch)
@@ -445,7 +523,7 @@ class Model:
             nb += 1
         if nb == 0:
             raise ValueError("No evaluation batches were produced.")
-        rv, _ = self._reg_value_and_grad(expr)
+        rv = self._reg_value_and_grad(expr)
         if return_list:
             out = torch.cat(losses)
             if rv is not None:

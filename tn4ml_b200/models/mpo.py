@@ -13,6 +13,8 @@ from .smpo import SpacedMatrixProductOperator
 class MatrixProductOperator(SpacedMatrixProductOperator):
     """Every site (chi_l, chi_r, d, d_o); boundaries squeezed (mpo.py:14-47, :99-104)."""
 
+    _reg_norm_is_trace = False  # the reference's MPO is not a SpacedMatrixProductOperator: regularisers use model.norm()
+
     def __init__(self, arrays, **kwargs):
         super().__init__(arrays, spacing=1, **kwargs)
 

@@ -17,6 +17,7 @@ class SpacedMatrixProductOperator(Model):
     last (chi, d) [l,u] or (chi, d, d_o)."""
 
     kind = _lib.KIND_SMPO
+    _reg_norm_is_trace = True  # metrics.py:99-103: type(model) in [SpacedMatrixProductOperator]
 
     def __init__(self, arrays, output_inds=None, shape="lrud", spacing: int | None = None, **kwargs):
         if output_inds:
