@@ -207,6 +207,13 @@ int32_t tnb_profile_read(char *names, float *ms, int32_t max_records);
 /* Number of kernel launches issued by this library since load (all threads). */
 int64_t tnb_launch_count(void);
 
+/* Deterministic gradient reduction for debugging: on != 0 makes the MPS weight-gradient GEMMs run ONE K-split per
+ * output tile (every gradient entry has a single writer accumulating in a fixed order), so two runs on the same inputs give
+ * bitwise identical gradients; slower, and on the tensor path the longer TMEM accumulation costs accuracy.  The
+ * loss sum is an atomic reduction either way: sum the per-sample losses for a fixed-order value.  The SMPO backward kernel
+ * reduces over CTAs with atomics and is not covered.  Also settable with TNB_DETERMINISTIC=1 at load. */
+int tnb_set_deterministic(int32_t on);
+
 /* 1 when the XLA-FFI handler symbols of csrc/xla_ffi_shim.cc (forward and backward) were compiled in (the build found
  * xla/ffi/api/ffi.h), else 0.  See INTEGRATION.md. */
 int32_t tnb_ffi_available(void);

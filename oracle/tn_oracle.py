@@ -336,7 +336,13 @@ def per_sample_loss(prob: Problem, x: torch.Tensor, arrays: Sequence[torch.Tenso
                     targets: torch.Tensor | None = None, order: str = "gemm") -> torch.Tensor:
     """evaluate()'s closure (model.py:1048-1076): embed, contract, head -> [B]."""
     phi = embed_batch(x, prob.emb)
-    if prob.kind == "mps":
+    if prob.kind == "mps" and phi.shape[1] > len(arrays):
+        # len(model) < len(data) (metrics.py:36-43, 312-319, 448-455): every k_i of the data is contracted; the sites the model
+        # does not reach carry no partner and are summed over their physical index
+        Lm = len(arrays)
+        extra = phi[:, Lm:].sum(-1).prod(dim=1)  # [B]
+        out = mps_outputs(phi[:, :Lm], arrays, order=order) * extra[:, None]
+    elif prob.kind == "mps":
         out = mps_outputs(phi, arrays, order=order)
     elif prob.kind == "smpo":
         out = smpo_sqnorm(phi, arrays, prob.spacing)

@@ -206,3 +206,23 @@ def test_two_gpu_allreduced_gradient_equals_one_gpu_gradient(dtype_name, chi):
     print(f"[2-GPU] {dtype_name}: loss rel err {loss_err:.2e}, max grad err / max|g| {grad_err:.2e}")
     tol = 1e-12 if dtype_name == "float64" else 1e-5
     assert loss_err <= tol and grad_err <= tol
+
+
+@pytest.mark.parametrize("dtype,chi", [(torch.float32, 64), (torch.float64, 24)], ids=["f32_tensor", "f64_simt"])
+def test_deterministic_mode_gives_bitwise_identical_gradients(dtype, chi):
+    """SURVEY 8e "Determinism": with tnb_set_deterministic(1) every gradient entry has one writer in a fixed order."""
+    from tn4ml_b200 import _lib
+    model, eng, x, t = _mps_case(dtype, chi, L=8, B=9000)
+    lib = _lib.lib()
+    _, g0 = eng.value_and_grad(model._packed, x, t)
+    g0 = g0.clone()
+    try:
+        lib.tnb_set_deterministic(1)
+        _, g1 = eng.value_and_grad(model._packed, x, t)
+        g1 = g1.clone()
+        _, g2 = eng.value_and_grad(model._packed, x, t)
+        assert torch.equal(g1, g2)
+    finally:
+        lib.tnb_set_deterministic(0)
+    tol = 1e-5 if dtype == torch.float32 else 1e-12
+    assert float((g1 - g0).abs().max()) <= tol * float(g0.abs().max())

@@ -164,3 +164,36 @@ def test_engine_cache_is_keyed_on_the_embedding_contents():
     ref = O.per_sample_loss(prob, x, arrays)
     assert not np.allclose(a, b)
     assert np.allclose(b, ref.numpy(), rtol=1e-10)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("head", ["nll", "softmax_xent"])
+def test_model_shorter_than_the_data(head, dtype):
+    """metrics.py:36-43 / 448-455: len(model) < len(data) -- the data sites beyond the model are summed over their physical
+    index (a per-sample factor; embed() normalises over ALL data sites)."""
+    from tests.test_gpu_parity import _heads
+    Lm, Ld, B = 7, 10, 9
+    tol = 1e-10 if dtype == torch.float64 else 1e-4
+    if head == "nll":
+        arrays = O.make_mps_arrays(Lm, 5, 3, std=0.2, seed=4, squeeze_ends=True, identity_all=True)
+        model, t = T.MatrixProductState(arrays, dtype=dtype, device="cuda:0"), None
+    else:
+        arrays = O.make_mps_arrays(Lm, 5, 3, class_site=3, C=3, std=0.2, seed=4)
+        model, t = T.TensorNetwork(arrays, dtype=dtype, device="cuda:0"), O.make_labels(B, 3)
+    x = O.make_inputs(B, Ld, seed=6)
+    spec = O.EmbSpec("poly", degree=2, include_bias=True)
+    prob = O.Problem("mps", spec, head)
+    arr = [a.to(dtype).double() for a in arrays]
+    xr = x.to(dtype).double()
+    loss_ref, grads_ref = O.value_and_grad(prob, xr, arr, t)
+    per_ref = O.per_sample_loss(prob, xr, arr, t)
+    eng, _ = model._engine(T.PolynomialEmbedding(degree=2, n=1, include_bias=True), _heads()[head], t is not None, dtype)
+    ls, g = eng.value_and_grad(model._packed, x.to(dtype), None if t is None else t.to(dtype))
+    assert abs(float(ls) / B - float(loss_ref)) <= tol * max(1.0, abs(float(loss_ref)))
+    gmax = max(float(q.abs().max()) for q in grads_ref)
+    for a, b in zip(model._views(g), grads_ref):
+        assert float((a.double().cpu() - b).abs().max()) <= tol * gmax
+    per, _, _ = eng.forward(model._packed, x.to(dtype), None if t is None else t.to(dtype))
+    assert torch.allclose(per.double().cpu(), per_ref, rtol=tol * 10, atol=tol * 10)
+    with pytest.raises(ValueError):  # metrics.py:49-51: the model must not be longer than the data
+        eng.forward(model._packed, x[:, :5].to(dtype), None if t is None else t.to(dtype))

@@ -69,6 +69,9 @@ def test_plain_mps_nll_matches_the_reference_source():
     per = O.per_sample_loss(prob, x, arrays).numpy()
     assert np.allclose(per, z["per_sample_loss"], rtol=1e-12)
     _check_fd(prob, x, arrays, None, z["fd_index"], z["fd_grad"])
+    # len(model) < len(data): the reference sums the uncontracted data sites over their physical index (metrics.py:36-43)
+    per_long = O.per_sample_loss(prob, torch.tensor(z["x_long"]), arrays).numpy()
+    assert np.allclose(per_long, z["per_sample_loss_long"], rtol=1e-12)
 
 
 @pytest.mark.parametrize("head", ["softmax_xent", "mse", "softmax_xent_weighted"])

@@ -73,6 +73,7 @@ SYMBOLS = {
     "tnb_norm": (C.c_int, [_P(TnbProblem), C.c_void_p, C.c_void_p, C.c_int32, _P(C.c_int32), _P(C.c_double), C.c_void_p,
                            C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "tnb_scale": (C.c_int, [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
+    "tnb_set_deterministic": (C.c_int, [C.c_int32]),
     "tnb_profile": (C.c_int, [C.c_int32]),
     "tnb_profile_read": (C.c_int32, [C.c_char_p, _P(C.c_float), C.c_int32]),
     "tnb_launch_count": (C.c_int64, []),

@@ -75,6 +75,8 @@ static Knobs read_knobs() {
 }
 static const Knobs g_knobs = read_knobs();
 const Knobs &knobs() { return g_knobs; }
+static std::atomic<int> g_deterministic{getenv("TNB_DETERMINISTIC") ? atoi(getenv("TNB_DETERMINISTIC")) : 0};
+bool deterministic() { return g_deterministic.load(std::memory_order_relaxed) != 0; }
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: done by tnb_init(device), and guarded here for callers
 // that skipped it (one relaxed load per call once the device is ready).
@@ -277,6 +279,7 @@ extern "C" {
 const char *tnb_version(void) { return "tn4ml_b200 0.1.0 (sm_100a)"; }
 const char *tnb_last_error(void) { return g_err; }
 int64_t tnb_launch_count(void) { return g_launches.load(); }
+int tnb_set_deterministic(int32_t on) { g_deterministic.store(on ? 1 : 0); return 0; }
 
 int32_t tnb_site_nout(const tnb_problem *p, int32_t site) {
   if (!p || site < 0 || site >= p->L) return 0;

@@ -54,6 +54,8 @@ struct Knobs {
   int tc_dbg = 0;
 };
 const Knobs &knobs();
+// tnb_set_deterministic: fixed-order gradient reduction (one K-split per output tile: a single writer per gradient entry)
+bool deterministic();
 
 // ---- MPS workspace plan --------------------------------------------------------------------------
 struct MpsPlan {

@@ -88,7 +88,7 @@ static int mps_backward_t(const tnb_problem *p, const MpsPlan &P, long long B, c
   long long ns = (148LL * 4 + work - 1) / work;
   long long maxsplit = (B + 255) / 256;
   if (ns > maxsplit) ns = maxsplit;
-  if (ns < 1) ns = 1;
+  if (ns < 1 || deterministic()) ns = 1;  // (deterministic: a single writer per gradient entry)
   Dg.nsplit = (int)ns;
   Dg.bchunk = (B + ns - 1) / ns;
   Dg.bchunk = (Dg.bchunk + 15) / 16 * 16;
@@ -105,7 +105,7 @@ static int mps_backward_t(const tnb_problem *p, const MpsPlan &P, long long B, c
   work = (long long)Dg.tiles_m * Dg.tiles_r * p->n_out;
   ns = (148LL * 2 + work - 1) / work;
   if (ns > maxsplit) ns = maxsplit;
-  if (ns < 1) ns = 1;
+  if (ns < 1 || deterministic()) ns = 1;
   Dg.nsplit = (int)ns;
   Dg.bchunk = ((B + ns - 1) / ns + 15) / 16 * 16;
   dim3 gridc(Dg.tiles_m * Dg.tiles_r * Dg.nsplit, 1, p->n_out);

@@ -208,6 +208,7 @@ int mps_tc_backward(const tnb_problem *p, const MpsPlan &P, long long B, const v
       const double score = eff - (n < 148 * 3 ? 1.0 : 0.0) - 0.002 * (double)nsp;  // prefer >= 3 waves, fewer splits
       if (nsp == nsp_min || score > best_eff) { best = nsp; best_eff = score; }
     }
+    if (deterministic()) best = 1;  // one CTA per output tile: every gradient entry has a single writer, in a fixed order
     Da.nsplit = (int)best;
     Da.bchunk = ((B + Da.nsplit - 1) / Da.nsplit + kDaKC - 1) / kDaKC * kDaKC;
     dim3 gda((unsigned)(Da.mgroups * Da.nsplit), (unsigned)(pass == 0 ? s1 - s0 : 1));

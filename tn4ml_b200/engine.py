@@ -101,8 +101,6 @@ class Engine:
         x = x.contiguous()
         if x.ndim != 2 or x.shape[1] < self.prob.L:
             raise ValueError(f"Input data must have at least {self.prob.L} elements!")  # model.py:306-307
-        if x.shape[1] != self.prob.L:
-            raise NotImplementedError("len(model) < len(data) is not on the fused path")
         if targets is not None:
             targets = torch.as_tensor(targets)
             if targets.device != self.device or targets.dtype != self.dtype:
@@ -112,10 +110,42 @@ class Engine:
                 raise ValueError(f"targets must have {self.prob.n_out} columns, got {targets.shape[1]}")
         return x, targets
 
+    # -- len(model) < len(data) ------------------------------------------------------
+    def _split_extra(self, x):
+        """The reference's branch for a model shorter than the data (metrics.py:36-43, 312-319, 357-364, 448-455): every
+        physical index of the data is contracted, and the sites the model does not reach are summed over their physical
+        index.  That multiplies the contraction by T[b] = prod_{i >= L} sum_s phi_hat_i[b, s], a per-sample constant that
+        does not depend on the model: for NegLogLikelihood it adds -2 ln|T[b]| to the loss and leaves the gradient alone;
+        the classifier heads act on y / ||y|| and are unchanged for T > 0.  Returns (x[:, :L], -2 ln|T| or None)."""
+        L = self.prob.L
+        if x.shape[1] == L:
+            return x, None
+        if self.prob.kind == _lib.KIND_SMPO:
+            raise NotImplementedError("len(model) < len(data) for SMPO/MPO heads (the factor enters the head non-linearly) "
+                                      "is not built")
+        xe = x[:, L:].contiguous()
+        phi = torch.empty(xe.shape + (self.prob.d,), dtype=self.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.tnb_embed(C.byref(self.prob.emb), _dtype_code(self.dtype), xe.numel(), xe.data_ptr(),
+                                          phi.data_ptr(), self._stream()))
+        # embed() normalises the product state over ALL sites of the data: the same as unit-norm sites (embeddings.py:1374-1387)
+        t = phi.sum(-1) / torch.linalg.norm(phi, dim=-1)
+        if self.prob.head != _lib.HEAD_NLL and bool((t.prod(dim=1) <= 0).any()):
+            raise NotImplementedError("negative feature sums on the sites beyond the model flip the sign of the logits")
+        return x[:, :L].contiguous(), -2.0 * torch.log(t.abs()).sum(dim=1)
+
     # -- forward only -------------------------------------------------------------
     def forward(self, params: torch.Tensor, x, targets=None, want_loss=True):
         """Per-sample losses [B], output mantissas [B, n_out] (or [B]) and exponents [B]."""
         x, targets = self._prep(x, targets)
+        x, extra = self._split_extra(x)
+        if extra is not None:
+            loss, out, oexp = self.forward(params, x, targets, want_loss)
+            if self.prob.head == _lib.HEAD_NLL:
+                loss = loss + extra.to(loss.dtype)
+                # raw output s = mantissa * 2^exp picks up T = exp(-extra / 2)
+                out = out * torch.exp(-0.5 * extra).to(out.dtype)[:, None]
+            return loss, out, oexp
         B = x.shape[0]
         smpo = self.prob.kind == _lib.KIND_SMPO
         loss = torch.empty(B, dtype=self.dtype, device=self.device)
@@ -147,12 +177,15 @@ class Engine:
         the GEMMs of the next range; the loss sum is all-reduced too.  On return both are the sums over all ranks
         (in stream order)."""
         x, targets = self._prep(x, targets)
+        x, extra = self._split_extra(x)
         B = x.shape[0]
         denom = B if denom is None else denom
         if grads is None:
             grads = torch.empty(self.n_params, dtype=self.dtype, device=self.device)
             accumulate = False
         self._loss_sum.zero_()
+        if extra is not None and self.prob.head == _lib.HEAD_NLL:
+            self._loss_sum.add_(extra.double().sum())  # (a model-independent constant: no gradient)
         mb = self.microbatch(B, True)
         with torch.cuda.device(self.device):
             for s in range(0, B, mb):

@@ -84,8 +84,8 @@ def _check_lengths(model, data):
         if len(model) > data.n_sites:
             raise ValueError(  # metrics.py:49-51
                 "Number of tensors for input data MPS needs to be higher or equal number of tensors in model.")
-        if len(model) < data.n_sites:
-            raise NotImplementedError("len(model) < len(data) (partial contraction) is not on the fused path")
+        # len(model) < len(data): the sites beyond the model are summed over their physical index (metrics.py:36-43);
+        # handled by Engine._split_extra
 
 
 def NegLogLikelihood(model, data):  # noqa: N802

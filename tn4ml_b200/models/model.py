@@ -191,7 +191,18 @@ class Model:
         sum coef * reg(model) (device float64 [1]) and its gradient ADDED to `grads`."""
         import ctypes as C
         if not self._packed.is_cuda:
-            raise RuntimeError("tn4ml_b200 runs on CUDA devices only (no CPU fallback)")
+            # CPU tensors are STORAGE ONLY (layout tests, initialisers run before the model is moved to its GPU): the
+            # initialiser's one-off normalisation is plain torch; anything on the training path needs the device
+            if regs or grads is not None:
+                raise RuntimeError("tn4ml_b200 runs on CUDA devices only (no CPU fallback)")
+            E = torch.ones(1, 1, dtype=torch.float64)
+            acc = torch.zeros((), dtype=torch.float64)
+            for i in range(self.L):
+                A = self._canon4(i).double()
+                E = torch.einsum("lm,lrsk,mnsk->rn", E, A, A)
+                m = E.abs().max()
+                E, acc = E / m, acc + torch.log2(m)
+            return acc + torch.log2(E[0, 0]), None
         lib = _lib.lib()
         prob = self._norm_problem()
         dev = self._packed.device
@@ -228,6 +239,12 @@ class Model:
             self._qr_sweep(range(self.L - 1), left=True, normalize_sites=True)
             return
         l2, _ = self._log2_norm2()
+        if not self._packed.is_cuda:  # storage-only model (see _log2_norm2)
+            if insert is None:
+                self._packed.mul_(float(torch.exp2(-0.5 * l2 / self.L)))
+            else:
+                self._arrays[insert].mul_(float(torch.exp2(-0.5 * l2)))
+            return
         lib = _lib.lib()
         code = _lib.F64 if self.dtype == torch.float64 else _lib.F32
         dev = self._packed.device

@@ -82,8 +82,13 @@ def mps_nll_file():
 
     per = losses(arrays)
     fd = _finite_differences(lambda arrs: losses(arrs).mean(), arrays, seed=3)
+    # len(model) < len(data) (metrics.py:36-43): the same model on data with three more features
+    x_long = S.make_inputs(B, L + 3, seed=13).numpy()
+    model = RMPS.MatrixProductState([np.array(a) for a in arrays])
+    per_long = np.array([float(RM.NegLogLikelihood(model, RE.embed(xb, phi))) for xb in x_long])
     np.savez_compressed(os.path.join(OUT, "reference_mps_nll.npz"), x=x, per_sample_loss=per, L=L, chi=chi, d=d,
-                        fd_index=fd[0], fd_grad=fd[1], **{f"site{i}": a for i, a in enumerate(arrays)})
+                        fd_index=fd[0], fd_grad=fd[1], x_long=x_long, per_sample_loss_long=per_long,
+                        **{f"site{i}": a for i, a in enumerate(arrays)})
     return per
 
 

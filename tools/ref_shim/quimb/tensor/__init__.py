@@ -223,6 +223,11 @@ class TensorNetwork:
 
     def contract_ind(self, ind, **_kw):
         ks = self.ind_map().get(ind, [])
+        if len(ks) == 1:  # an outer index: quimb contracts the tensor with output_inds = its other indices, i.e. sums over it
+            t = self._tensors[ks[0]]
+            ax = t.inds.index(ind)
+            t.modify(data=t.data.sum(axis=ax), inds=tuple(i for i in t.inds if i != ind))
+            return
         if len(ks) != 2:
             raise ValueError(f"index {ind} is on {len(ks)} tensors")
         c = _contract_pair(self._tensors[ks[0]], self._tensors[ks[1]])
