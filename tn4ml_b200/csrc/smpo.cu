@@ -12,11 +12,14 @@ cudaError_t smpo_set_attrs() {
 }
 
 int64_t smpo_workspace_bytes(const tnb_problem *p, long long B, int need_grad) {
+  if (rr_smpo_supported(p, need_grad)) return rr_smpo_workspace_bytes(p, B, need_grad);
   return (int64_t)plan_smpo(p, B, need_grad).total;
 }
 
 int smpo_forward(const tnb_problem *p, long long B, const void *x, const void *params, void *loss, double *loss_sum,
                  void *out, int32_t *out_exp, int keep_stash, void *ws, int64_t ws_bytes, cudaStream_t st) {
+  if (rr_smpo_supported(p, keep_stash))
+    return rr_smpo_forward(p, B, x, params, loss, loss_sum, out, out_exp, keep_stash, ws, ws_bytes, st);
   SmpoPlan P = plan_smpo(p, B, keep_stash);
   if ((int64_t)P.total > ws_bytes) return fail("workspace too small: need %zu bytes, got %lld", P.total, (long long)ws_bytes);
   int rc;
@@ -34,6 +37,7 @@ int smpo_forward(const tnb_problem *p, long long B, const void *x, const void *p
 
 int smpo_backward(const tnb_problem *p, long long B, const void *x, const void *params, double loss_scale, void *grads,
                   int accumulate, void *ws, int64_t ws_bytes, cudaStream_t st) {
+  if (rr_smpo_supported(p, 1)) return rr_smpo_backward(p, B, x, params, loss_scale, grads, accumulate, ws, ws_bytes, st);
   SmpoPlan P = plan_smpo(p, B, 1);
   if ((int64_t)P.total > ws_bytes) return fail("workspace too small: need %zu bytes, got %lld", P.total, (long long)ws_bytes);
   int rc;

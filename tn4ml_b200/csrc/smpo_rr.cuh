@@ -1,0 +1,606 @@
+// K5 (register-resident family): SMPO / MPO double-layer environments for bond <= 32, float32, d = 2.
+//
+// One WARP owns one sample.  Every per-sample chi x chi matrix of the window recursion
+//     P_w = M_{w0+1} ... M_{w1-1},   T^o = M^o_{w0} P_w,   U^o = E_w T^o,   E_{w+1} = sum_o T^o^T U^o
+// (tn4ml/models/smpo.py:269-404 + tn4ml/metrics.py:56-81; the association of SURVEY 8d, cfg 3) lives in the warp's registers as
+// tensor-core fragments: the fp32 accumulator of one product is re-split in registers into the fp16 hi/lo operand of the next
+// (`mma.sync.m16n8k16`), transposed operands come from `movmatrix`, and nothing but the window's entry environment (the
+// VJP's stash) ever goes to memory.  No shared memory, no block barrier.
+//
+// Why mma.sync and not tcgen05 here: these are products of two PER-SAMPLE 32 x 32 matrices.  A tcgen05.mma shares its B
+// operand between all 128 rows of the tile, so four samples' products would run block-diagonally at 25 % efficiency with a
+// TMEM round trip (tcgen05.ld -> convert -> tcgen05.st) between every two products; the shared-weight reformulation
+// (E <- sum M^T E M as chain steps with chi rows per sample) costs 3x the flops.  DESIGN.md has the numbers.
+//
+// Arithmetic: "fp16x3" as on the tcgen05 family -- x * 2^s = hi + lo (two fp16, 22 bits), hi*hi + lo*hi + hi*lo accumulated in
+// fp32.  Tensor-core accumulation truncates, so per output tile the two small terms are issued first and the hi*hi terms
+// last (two truncations at full magnitude per product), and sums over the output index o are added in fp32 on the CUDA cores.
+// Every matrix is carried as (fp32 fragment, binary exponent): the split rescales by the exact power of two of the warp-wide
+// max-abs, so no chain length leaves the fp16 / fp32 range.
+#pragma once
+#include <cuda_fp16.h>
+#include <limits.h>
+
+#include "common.cuh"
+#include "consts.h"
+
+namespace tnb {
+namespace rr {
+
+constexpr int kN = 32;  // padded bond
+
+struct RrArgs {
+  int L, chi, D, DO, S, nwin, head;
+  long long B;
+  EmbParams<float> emb;
+  const float *x;
+  const float *params;
+  float *Estash;  // [nwin][B][32 regs][32 lanes]  entry environment of every window (C-layout fragment image)
+  int *Eexp;      // [nwin][B]
+  int *esum;      // [B]
+  float *nm;      // [B] mantissa of n = nm * 2^esum
+  float *loss;
+  double *loss_sum;
+  float *out;
+  int *out_exp;
+  float *grads;
+  float loss_scale;
+  int stash;
+  // VJP
+  float *dEscr;   // [B][1024] adjoint of the window environment between two windows (fragment image) ...
+  int *dEexp;     // [B]       ... and its exponent
+  uint32_t *Qscr; // [grid * warps][S][1056] prefix products Q_k = M_1 .. M_k of the current window (Q-form images + exponent)
+  int per_cta;    // samples per CTA (window-major loop: every warp takes per_cta / warps samples one after the other)
+};
+
+// fp32 matrix in accumulator (C) layout: tile (mt, nt) = rows 16 mt .. +15, cols 8 nt .. +7; lane (g = lane / 4, t = lane % 4)
+// holds [0],[1] = (row g, cols 2t, 2t+1) and [2],[3] = (row g + 8, cols 2t, 2t+1).   true matrix = c * 2^ex
+struct Mat {
+  float c[2][4][4];
+  int ex;
+};
+// fp16 hi / lo image.  "P" form: reg [mt][nt][r] = the two values (row 16 mt + 8 r + g, cols 8 nt + 2t, +1) -- the row
+// fragments of the matrix.  "Q" form: every 8 x 8 block of P transposed (movmatrix): reg [mt][nt][r] = (rows 16 mt + 8 r + 2t,
+// +1; col 8 nt + g).  P(X) is the left operand X and the right operand X^T; Q(X) the right operand X and the left operand X^T.
+struct Img {
+  uint32_t hi[2][4][2], lo[2][4][2];
+  int ex;
+};
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
+  return v;
+}
+
+// split a matrix into its fp16 hi / lo row-fragment image, rescaled so that the largest entry is in [2^13, 2^14)
+__device__ __forceinline__ void split(const Mat &X, Img &P) {
+  float m = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) m = fmaxf(m, fabsf(X.c[i][j][q]));
+  m = warp_max(m);
+  // m = f * 2^e with f in [0.5, 1): scale by 2^(14 - e).  (Clamped: products are renormalised at every split, so |14 - e| > 120
+  // only occurs for an all-zero or non-finite matrix.)
+  int e = 0;
+  const bool ok = m > 0.f && m < 3.0e38f;
+  if (ok) frexpf(m, &e);
+  const int sh = ok ? max(-120, min(120, 14 - e)) : 0;
+  const float fs = ok ? ldexpf(1.f, sh) : 0.f;
+  P.ex = X.ex - sh;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const float a = X.c[i][j][2 * r] * fs, b = X.c[i][j][2 * r + 1] * fs;
+        const __half2 h = __floats2half2_rn(a, b);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+        P.hi[i][j][r] = *reinterpret_cast<const uint32_t *>(&h);
+        P.lo[i][j][r] = *reinterpret_cast<const uint32_t *>(&l);
+      }
+}
+
+__device__ __forceinline__ uint32_t movm(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;\n" : "=r"(d) : "r"(a));
+  return d;
+}
+// Q form of an image in P form (and back: the transposition is an involution)
+__device__ __forceinline__ void transpose_blocks(const Img &P, Img &Q) {
+  Q.ex = P.ex;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        Q.hi[i][j][r] = movm(P.hi[i][j][r]);
+        Q.lo[i][j][r] = movm(P.lo[i][j][r]);
+      }
+}
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// Z = op(X) * op(Y) for 32 x 32 matrices.
+//   LT = false: left operand X from P(X);  LT = true: left operand X^T from Q(X)
+//   RT = false: right operand Y from Q(Y); RT = true: right operand Y^T from P(Y)
+template <bool LT, bool RT> __device__ __forceinline__ void product(const Img &Lm, const Img &Rm, Mat &Z) {
+  Z.ex = Lm.ex + Rm.ex;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t ah[2][4], al[2][4], bh[2][2], bl[2][2];
+#pragma unroll
+      for (int kt = 0; kt < 2; ++kt) {
+        if (!LT) {
+          ah[kt][0] = Lm.hi[mt][2 * kt][0]; ah[kt][1] = Lm.hi[mt][2 * kt][1];
+          ah[kt][2] = Lm.hi[mt][2 * kt + 1][0]; ah[kt][3] = Lm.hi[mt][2 * kt + 1][1];
+          al[kt][0] = Lm.lo[mt][2 * kt][0]; al[kt][1] = Lm.lo[mt][2 * kt][1];
+          al[kt][2] = Lm.lo[mt][2 * kt + 1][0]; al[kt][3] = Lm.lo[mt][2 * kt + 1][1];
+        } else {
+          ah[kt][0] = Lm.hi[kt][2 * mt][0]; ah[kt][1] = Lm.hi[kt][2 * mt + 1][0];
+          ah[kt][2] = Lm.hi[kt][2 * mt][1]; ah[kt][3] = Lm.hi[kt][2 * mt + 1][1];
+          al[kt][0] = Lm.lo[kt][2 * mt][0]; al[kt][1] = Lm.lo[kt][2 * mt + 1][0];
+          al[kt][2] = Lm.lo[kt][2 * mt][1]; al[kt][3] = Lm.lo[kt][2 * mt + 1][1];
+        }
+        if (!RT) {
+          bh[kt][0] = Rm.hi[kt][nt][0]; bh[kt][1] = Rm.hi[kt][nt][1];
+          bl[kt][0] = Rm.lo[kt][nt][0]; bl[kt][1] = Rm.lo[kt][nt][1];
+        } else {
+          bh[kt][0] = Rm.hi[nt >> 1][2 * kt][nt & 1]; bh[kt][1] = Rm.hi[nt >> 1][2 * kt + 1][nt & 1];
+          bl[kt][0] = Rm.lo[nt >> 1][2 * kt][nt & 1]; bl[kt][1] = Rm.lo[nt >> 1][2 * kt + 1][nt & 1];
+        }
+      }
+      // small terms first, the hi * hi terms last: the tensor core truncates every accumulation
+      mma16816(c, al[0], bh[0]);
+      mma16816(c, ah[0], bl[0]);
+      mma16816(c, al[1], bh[1]);
+      mma16816(c, ah[1], bl[1]);
+      mma16816(c, ah[0], bh[0]);
+      mma16816(c, ah[1], bh[1]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) Z.c[mt][nt][q] = c[q];
+    }
+}
+
+// Z += X with the exponents aligned (exact powers of two); empty Z (ex == INT_MIN) takes X
+__device__ __forceinline__ void add_aligned(Mat &Z, const Mat &X) {
+  if (Z.ex == INT_MIN) {
+    Z = X;
+    return;
+  }
+  const int e = max(Z.ex, X.ex);
+  const float fz = ldexpf(1.f, max(Z.ex - e, -200)), fx = ldexpf(1.f, max(X.ex - e, -200));
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) Z.c[i][j][q] = fmaf(Z.c[i][j][q], fz, X.c[i][j][q] * fx);
+  Z.ex = e;
+}
+
+// site matrix M[a][r] = sum_s phi[s] * A_site[a][r][s][o] in C layout (ex = 0).  chi == 32, D == 2: 16-byte loads.
+template <int DO>
+__device__ __forceinline__ void form_site(const RrArgs &A, int site, int o, float ph0, float ph1, Mat &M, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const bool has_out = site % A.S == 0;
+  const int nj = has_out ? A.DO : 1;
+  const long long per = (long long)A.chi * A.chi * A.D;
+  const long long nwith = (site + A.S - 1) / A.S;
+  const float *W = A.params + per * (site - nwith) + per * A.DO * nwith;
+  M.ex = 0;
+  if (A.chi == kN && A.D == 2 && (nj == 1 || (DO == 2 && nj == 2))) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int row = 16 * mt + 8 * r + g, col = 8 * nt + 2 * t;
+          if (nj == 1) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(W + ((size_t)row * kN + col) * 2));
+            M.c[mt][nt][2 * r] = fmaf(ph1, v.y, ph0 * v.x);
+            M.c[mt][nt][2 * r + 1] = fmaf(ph1, v.w, ph0 * v.z);
+          } else {
+            const float4 v0 = __ldg(reinterpret_cast<const float4 *>(W + ((size_t)row * kN + col) * 4));
+            const float4 v1 = __ldg(reinterpret_cast<const float4 *>(W + ((size_t)row * kN + col + 1) * 4));
+            M.c[mt][nt][2 * r] = o == 0 ? fmaf(ph1, v0.z, ph0 * v0.x) : fmaf(ph1, v0.w, ph0 * v0.y);
+            M.c[mt][nt][2 * r + 1] = o == 0 ? fmaf(ph1, v1.z, ph0 * v1.x) : fmaf(ph1, v1.w, ph0 * v1.y);
+          }
+        }
+    return;
+  }
+  // general bond <= 32 / output dimension: guarded scalar loads
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int row = 16 * mt + 8 * (q >> 1) + g, col = 8 * nt + 2 * t + (q & 1);
+        float v = 0.f;
+        if (row < A.chi && col < A.chi) {
+          const float *w = W + (((size_t)row * A.chi + col) * 2) * nj + o;
+          v = fmaf(ph1, __ldg(w + nj), ph0 * __ldg(w));
+        }
+        M.c[mt][nt][q] = v;
+      }
+}
+
+// phi of the window's sites: lane k evaluates site w0 + k; read with __shfl_sync
+__device__ __forceinline__ void window_phi(const RrArgs &A, long long b, int w0, int w1, int lane, float &p0, float &p1) {
+  p0 = p1 = 0.f;
+  if (w0 + lane < w1) {
+    float ph[2];
+    embed_site_d<2>(A.emb, A.x[(size_t)b * A.L + w0 + lane], ph);
+    p0 = ph[0];
+    p1 = ph[1];
+  }
+}
+
+// The forward recursion of one window: E (entry environment) -> Enew.  When `keep` is set the images the VJP needs are
+// left in qP (Q(P_w)) and the caller's o-loop callback is used instead (the backward kernel has its own loop).
+template <int DO>
+__device__ __forceinline__ void window_chain(const RrArgs &A, int w0, int w1, float p0, float p1, int lane, bool &havep, Img &qP) {
+  const int K = w1 - w0 - 1;
+  havep = K > 0;
+  if (!havep) return;
+  Mat Pm;
+  form_site<DO>(A, w0 + 1, 0, __shfl_sync(0xffffffffu, p0, 1), __shfl_sync(0xffffffffu, p1, 1), Pm, lane);
+  for (int k = 2; k <= K; ++k) {
+    Img a, pm, q;
+    split(Pm, a);
+    Mat Mk;
+    form_site<DO>(A, w0 + k, 0, __shfl_sync(0xffffffffu, p0, k), __shfl_sync(0xffffffffu, p1, k), Mk, lane);
+    split(Mk, pm);
+    transpose_blocks(pm, q);
+    product<false, false>(a, q, Pm);
+  }
+  Img pP;
+  split(Pm, pP);
+  transpose_blocks(pP, qP);
+}
+
+template <int DO> __global__ void __launch_bounds__(128) smpo_rr_fwd_kernel(RrArgs A) {
+  const int lane = threadIdx.x & 31;
+  const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= A.B) return;  // (no block-level synchronisation anywhere in this kernel)
+  Mat E;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) E.c[i][j][q] = 0.f;
+  if (lane == 0) E.c[0][0][0] = 1.f;
+  E.ex = 0;
+  for (int w = 0; w < A.nwin; ++w) {
+    const int w0 = w * A.S, w1 = min(w0 + A.S, A.L);
+    if (A.stash) {
+      float *dst = A.Estash + ((size_t)w * A.B + b) * 1024 + lane;
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dst[((i * 4 + j) * 4 + q) * 32] = E.c[i][j][q];
+      if (lane == 0) A.Eexp[(size_t)w * A.B + b] = E.ex;
+    }
+    float p0, p1;
+    window_phi(A, b, w0, w1, lane, p0, p1);
+    bool havep;
+    Img qP;
+    window_chain<DO>(A, w0, w1, p0, p1, lane, havep, qP);
+    Img pE;
+    split(E, pE);
+    Mat En;
+    En.ex = INT_MIN;
+    const float q0 = __shfl_sync(0xffffffffu, p0, 0), q1 = __shfl_sync(0xffffffffu, p1, 0);
+#pragma unroll 1
+    for (int o = 0; o < A.DO; ++o) {
+      Mat T;
+      form_site<DO>(A, w0, o, q0, q1, T, lane);
+      Img pT, qT;
+      if (havep) {
+        Img pM;
+        split(T, pM);
+        product<false, false>(pM, qP, T);
+      }
+      split(T, pT);
+      transpose_blocks(pT, qT);
+      Mat U;
+      product<false, false>(pE, qT, U);
+      Img pU, qU;
+      split(U, pU);
+      transpose_blocks(pU, qU);
+      Mat C;
+      product<true, false>(qT, qU, C);
+      add_aligned(En, C);
+    }
+    E = En;
+  }
+  // n = E[0][0] * 2^ex
+  float lval = 0.f;
+  if (lane == 0) {
+    int e2 = 0;
+    const float nmv = frexpf(E.c[0][0][0], &e2);
+    const int es = E.ex + e2;
+    A.nm[b] = nmv;
+    A.esum[b] = es;
+    if (A.out) A.out[b] = nmv;
+    if (A.out_exp) A.out_exp[b] = es;
+    lval = smpo_head<float>(A.head, nmv, es, (float *)nullptr);
+    if (A.loss) A.loss[b] = lval;
+    if (A.loss_sum) atomicAdd(A.loss_sum, (double)lval);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// VJP.  Window-major: a CTA owns `per_cta` samples and walks the windows backwards; inside a window its W warps take the
+// samples W at a time.  For one sample and window (E = stashed entry environment, dE' = adjoint of the exit environment):
+//     recompute  Q_k = M_1 .. M_k (prefixes to scratch),  P = Q_K,  T^o = M^o P,  U^o = E T^o
+//     dT^o = 2 U^o dE'      dE += T^o dE' T^o^T      dM^o = dT^o P^T      dP += M^o^T dT^o
+//     G = dP;  for k = K .. 1:  dM_k = Q_{k-1}^T G,  G <- G M_k^T
+// The per-site gradients dA[a, r, s(, o)] = sum_b phi_s[b] dM[b][a, r] are reduced over the CTA's samples in shared memory
+// (every warp stages its phi-weighted fragment, the warps then sum disjoint slices of the W slots into the window's
+// accumulator) and go to global memory with one RED per element, window and CTA.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kBwdWarps = 8;
+
+__device__ __forceinline__ void store_mat(float *dst, const Mat &X, int lane) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dst[((i * 4 + j) * 4 + q) * 32 + lane] = X.c[i][j][q];
+}
+__device__ __forceinline__ void load_mat(const float *src, Mat &X, int lane) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) X.c[i][j][q] = src[((i * 4 + j) * 4 + q) * 32 + lane];
+}
+__device__ __forceinline__ void store_img(uint32_t *dst, const Img &X, int lane) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        dst[((i * 4 + j) * 2 + r) * 32 + lane] = X.hi[i][j][r];
+        dst[(16 + (i * 4 + j) * 2 + r) * 32 + lane] = X.lo[i][j][r];
+      }
+  if (lane == 0) dst[1024] = (uint32_t)X.ex;
+}
+__device__ __forceinline__ void load_img(const uint32_t *src, Img &X, int lane) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        X.hi[i][j][r] = src[((i * 4 + j) * 2 + r) * 32 + lane];
+        X.lo[i][j][r] = src[(16 + (i * 4 + j) * 2 + r) * 32 + lane];
+      }
+  X.ex = (int)src[1024];
+}
+
+// Stage phi_s * dM of this warp's sample, reduce over the CTA's warps, add into the window accumulator `acc` ([2][1024]:
+// s, fragment element).  Called by EVERY warp of the CTA (two block barriers); `on` = this warp has something to add.
+__device__ __forceinline__ void reduce_grad(float *stage, float *acc, const Mat &dM, bool on, float ph0, float ph1, int warp,
+                                            int lane) {
+  float *mine = stage + warp * 2048;
+  const float f = on ? ldexpf(1.f, max(-126, min(126, dM.ex))) : 0.f;
+  const float f0 = ph0 * f, f1 = ph1 * f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float v = on ? dM.c[i][j][q] : 0.f;
+        mine[((i * 4 + j) * 4 + q) * 32 + lane] = v * f0;
+        mine[1024 + ((i * 4 + j) * 4 + q) * 32 + lane] = v * f1;
+      }
+  __syncthreads();
+  constexpr int per_warp = 2048 / kBwdWarps;  // elements of the slice a warp sums
+#pragma unroll
+  for (int i = 0; i < per_warp / 32; ++i) {
+    const int e = warp * per_warp + i * 32 + lane;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < kBwdWarps; ++w) v += stage[w * 2048 + e];
+    acc[e] += v;
+  }
+  __syncthreads();
+}
+
+template <int DO> __global__ void __launch_bounds__(kBwdWarps * 32, 1) smpo_rr_bwd_kernel(RrArgs A) {
+  extern __shared__ __align__(16) float smem[];
+  float *stage = smem;                        // [warps][2][1024]
+  float *wacc = smem + kBwdWarps * 2048;      // window accumulator: site 0: [DO][2][1024], sites 1 .. S-1: [2][1024]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int acc_floats = (A.DO + A.S - 1) * 2048;
+  const long long base = (long long)blockIdx.x * A.per_cta;
+  const int rounds = (A.per_cta + kBwdWarps - 1) / kBwdWarps;
+  uint32_t *Qs = A.Qscr + ((size_t)blockIdx.x * kBwdWarps + warp) * (size_t)A.S * 1056;
+  for (int i = threadIdx.x; i < acc_floats; i += blockDim.x) wacc[i] = 0.f;
+  __syncthreads();
+  for (int w = A.nwin - 1; w >= 0; --w) {
+    const int w0 = w * A.S, w1 = min(w0 + A.S, A.L), K = w1 - w0 - 1;
+    for (int r = 0; r < rounds; ++r) {
+      const long long b = base + (long long)r * kBwdWarps + warp;
+      const bool on = r * kBwdWarps + warp < A.per_cta && b < A.B;
+      const long long bs = on ? b : 0;
+      float p0, p1;
+      window_phi(A, bs, w0, w1, lane, p0, p1);
+      Mat E, dEn;
+      load_mat(A.Estash + ((size_t)w * A.B + bs) * 1024, E, lane);
+      E.ex = A.Eexp[(size_t)w * A.B + bs];
+      if (w == A.nwin - 1) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dEn.c[i][j][q] = 0.f;
+        float dn = 0.f;
+        if (lane == 0) {
+          smpo_head<float>(A.head, A.nm[bs], A.esum[bs], &dn);
+          dn *= A.loss_scale;
+        }
+        dEn.c[0][0][0] = dn;
+        dEn.ex = -A.esum[bs];
+      } else {
+        load_mat(A.dEscr + (size_t)bs * 1024, dEn, lane);
+        dEn.ex = A.dEexp[bs];
+      }
+      // ---- recompute the chain, prefixes Q_2 .. Q_{K-1} to scratch ----
+      Img pP, qP;
+      if (K > 0) {
+        Mat Pm;
+        form_site<DO>(A, w0 + 1, 0, __shfl_sync(0xffffffffu, p0, 1), __shfl_sync(0xffffffffu, p1, 1), Pm, lane);
+        for (int k = 2; k <= K; ++k) {
+          Img a, pm, q;
+          split(Pm, a);
+          Mat Mk;
+          form_site<DO>(A, w0 + k, 0, __shfl_sync(0xffffffffu, p0, k), __shfl_sync(0xffffffffu, p1, k), Mk, lane);
+          split(Mk, pm);
+          transpose_blocks(pm, q);
+          product<false, false>(a, q, Pm);
+          if (k < K) {
+            Img pq, qq;
+            split(Pm, pq);
+            transpose_blocks(pq, qq);
+            store_img(Qs + (size_t)k * 1056, qq, lane);
+          }
+        }
+        split(Pm, pP);
+        transpose_blocks(pP, qP);
+      }
+      Img pE, pdE;
+      split(E, pE);
+      split(dEn, pdE);
+      Mat dE, dP;
+      dE.ex = INT_MIN;
+      dP.ex = INT_MIN;
+      const float q0 = __shfl_sync(0xffffffffu, p0, 0), q1 = __shfl_sync(0xffffffffu, p1, 0);
+#pragma unroll 1
+      for (int o = 0; o < A.DO; ++o) {
+        Mat T;
+        form_site<DO>(A, w0, o, q0, q1, T, lane);
+        Img pM;
+        split(T, pM);
+        if (K > 0) product<false, false>(pM, qP, T);
+        Img pT, qT;
+        split(T, pT);
+        transpose_blocks(pT, qT);
+        Mat U;
+        product<false, false>(pE, qT, U);
+        Img pU;
+        split(U, pU);
+        Mat dT;
+        product<false, true>(pU, pdE, dT);  // U dE'   (dE' symmetric: the right operand dE'^T from P(dE'))
+        dT.ex += 1;                         // x 2
+        Mat X;
+        product<false, true>(pT, pdE, X);   // T dE'
+        Img pX;
+        split(X, pX);
+        Mat dEc;
+        product<false, true>(pX, pT, dEc);  // (T dE') T^T
+        add_aligned(dE, dEc);
+        Img pdT;
+        split(dT, pdT);
+        Mat dMo;
+        if (K > 0) product<false, true>(pdT, pP, dMo);  // dT P^T
+        else dMo = dT;
+        reduce_grad(stage, wacc + (size_t)o * 2048, dMo, on, q0, q1, warp, lane);
+        if (K > 0) {
+          Img qM, qdT;
+          transpose_blocks(pM, qM);
+          transpose_blocks(pdT, qdT);
+          Mat dPc;
+          product<true, false>(qM, qdT, dPc);  // M^o^T dT
+          add_aligned(dP, dPc);
+        }
+      }
+      // ---- chain backward ----
+      Mat G = dP;
+      for (int k = K; k >= 1; --k) {
+        const float pk0 = __shfl_sync(0xffffffffu, p0, k), pk1 = __shfl_sync(0xffffffffu, p1, k);
+        float *acc_k = wacc + (size_t)(A.DO + k - 1) * 2048;
+        if (k == 1) {
+          reduce_grad(stage, acc_k, G, on, pk0, pk1, warp, lane);
+          break;
+        }
+        Img pG, qG, qQ;
+        split(G, pG);
+        transpose_blocks(pG, qG);
+        if (k - 1 >= 2) {
+          load_img(Qs + (size_t)(k - 1) * 1056, qQ, lane);
+        } else {  // Q_1 = M_1
+          Mat M1;
+          form_site<DO>(A, w0 + 1, 0, __shfl_sync(0xffffffffu, p0, 1), __shfl_sync(0xffffffffu, p1, 1), M1, lane);
+          Img p1i;
+          split(M1, p1i);
+          transpose_blocks(p1i, qQ);
+        }
+        Mat dMk;
+        product<true, false>(qQ, qG, dMk);  // Q_{k-1}^T G
+        reduce_grad(stage, acc_k, dMk, on, pk0, pk1, warp, lane);
+        Mat Mk;
+        form_site<DO>(A, w0 + k, 0, pk0, pk1, Mk, lane);
+        Img pMk;
+        split(Mk, pMk);
+        product<false, true>(pG, pMk, G);  // G M_k^T
+      }
+      if (on && w > 0) {
+        store_mat(A.dEscr + (size_t)b * 1024, dE, lane);
+        if (lane == 0) A.dEexp[b] = dE.ex;
+      }
+    }
+    // ---- flush the window's gradients: one RED per element, window and CTA ----
+    __syncthreads();
+    const int nsite = w1 - w0;
+    for (int idx = 0; idx < nsite; ++idx) {
+      const int site = w0 + idx;
+      const bool has_out = site % A.S == 0;
+      const int nj = has_out ? A.DO : 1;
+      const long long per = (long long)A.chi * A.chi * A.D;
+      const long long nwith = (site + A.S - 1) / A.S;
+      float *g = A.grads + per * (site - nwith) + per * A.DO * nwith;
+      for (int o = 0; o < nj; ++o) {
+        float *acc = wacc + (size_t)(idx == 0 ? o : A.DO + idx - 1) * 2048;
+        for (int e = threadIdx.x; e < 2048; e += blockDim.x) {
+          const int s = e >> 10, fe = e & 1023, reg = fe >> 5, ln = fe & 31;
+          const int q = reg & 3, nt = (reg >> 2) & 3, mt = reg >> 4, gg = ln >> 2, tt = ln & 3;
+          const int row = 16 * mt + 8 * (q >> 1) + gg, col = 8 * nt + 2 * tt + (q & 1);
+          const float v = acc[e];
+          acc[e] = 0.f;
+          if (row < A.chi && col < A.chi && v != 0.f) atomicAdd(&g[(((size_t)row * A.chi + col) * A.D + s) * nj + o], v);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace rr
+}  // namespace tnb
