@@ -6,7 +6,9 @@ namespace tnb {
 
 using rr::RrArgs;
 
-static size_t bwd_smem(const tnb_problem *p) { return (size_t)(rr::kBwdWarps + p->n_out + p->spacing - 1) * 2048 * sizeof(float); }
+static size_t bwd_smem(const tnb_problem *p) {
+  return (size_t)(rr::kBwdWarps + p->n_out + p->spacing - 1) * 2048 * sizeof(float) + (size_t)rr::kRingStages * rr::kImgFloat4 * sizeof(float4);
+}
 
 cudaError_t rr_set_attrs() {
   cudaError_t e = cudaFuncSetAttribute(rr::smpo_rr_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax);
@@ -24,8 +26,8 @@ bool rr_smpo_supported(const tnb_problem *p, int need_grad) {
 }
 
 struct RrPlan {
-  int nwin, per_cta, grid_bwd;
-  size_t off_E, off_Eexp, off_esum, off_nm, off_dE, off_dEexp, off_Q, total;
+  int nwin, per_cta, grid_bwd, nunit;
+  size_t off_E, off_Eexp, off_esum, off_nm, off_dE, off_dEexp, off_Q, off_Wimg, off_Wsh, total;
 };
 
 static RrPlan plan_rr(const tnb_problem *p, long long B, int need_grad) {
@@ -37,6 +39,9 @@ static RrPlan plan_rr(const tnb_problem *p, long long B, int need_grad) {
   P.off_Eexp = take(need_grad ? (size_t)P.nwin * B * sizeof(int) : 0);
   P.off_esum = take((size_t)B * sizeof(int));
   P.off_nm = take((size_t)B * sizeof(float));
+  P.nunit = P.nwin * (p->spacing - 1 + p->n_out);
+  P.off_Wimg = take((size_t)P.nunit * 2 * rr::kImgFloat4 * sizeof(float4));
+  P.off_Wsh = take((size_t)P.nunit * sizeof(int));
   // VJP: samples per CTA so that one wave of 148 CTAs covers the batch (whole rounds of kBwdWarps samples where possible)
   long long per = (B + 147) / 148;
   per = (per + rr::kBwdWarps - 1) / rr::kBwdWarps * rr::kBwdWarps;
@@ -64,6 +69,7 @@ static void fill(const tnb_problem *p, const RrPlan &P, long long B, const void 
   A.nm = (float *)(w + P.off_nm);
   A.dEscr = (float *)(w + P.off_dE); A.dEexp = (int *)(w + P.off_dEexp); A.Qscr = (uint32_t *)(w + P.off_Q);
   A.per_cta = P.per_cta;
+  A.Wimg = (const float4 *)(w + P.off_Wimg); A.Wsh = (const int *)(w + P.off_Wsh);
   A.loss = nullptr; A.loss_sum = nullptr; A.out = nullptr; A.out_exp = nullptr; A.grads = nullptr; A.loss_scale = 1.f;
   A.stash = 0;
 }
@@ -76,11 +82,23 @@ int rr_smpo_forward(const tnb_problem *p, long long B, const void *x, const void
   fill(p, P, B, x, params, ws, A);
   A.stash = keep_stash ? 1 : 0;
   A.loss = (float *)loss; A.loss_sum = loss_sum; A.out = (float *)out; A.out_exp = out_exp;
-  const int wpb = 4;  // warps (= samples) per CTA
-  const unsigned grid = (unsigned)((B + wpb - 1) / wpb);
+  // weight images in fragment order + the a-priori power-of-two scale of every unit (once per call: 16 KB per unit)
   prof_begin(st);
-  if (p->n_out == 2) rr::smpo_rr_fwd_kernel<2><<<grid, wpb * 32, 0, st>>>(A);
-  else rr::smpo_rr_fwd_kernel<0><<<grid, wpb * 32, 0, st>>>(A);
+  rr::smpo_rr_unitmax_kernel<<<P.nunit, 256, 0, st>>>((const float *)params, (int *)A.Wsh, p->L, p->chi, p->spacing, p->n_out);
+  TNB_LAUNCH_CHECK("smpo_rr_unitmax_kernel");
+  {
+    const long long total = (long long)P.nunit * 2 * rr::kImgFloat4;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    prof_begin(st);
+    rr::smpo_rr_prep_kernel<<<blocks, 256, 0, st>>>((const float *)params, A.Wsh, (float4 *)A.Wimg, P.nunit, p->L, p->chi,
+                                                    p->spacing, p->n_out);
+    TNB_LAUNCH_CHECK("smpo_rr_prep_kernel");
+  }
+  const unsigned grid = (unsigned)((B + rr::kFwdWarps - 1) / rr::kFwdWarps);
+  prof_begin(st);
+  if (p->n_out == 2) rr::smpo_rr_fwd_kernel<2><<<grid, rr::kFwdWarps * 32, 0, st>>>(A);
+  else rr::smpo_rr_fwd_kernel<0><<<grid, rr::kFwdWarps * 32, 0, st>>>(A);
   TNB_LAUNCH_CHECK("smpo_rr_fwd_kernel");
   return 0;
 }

@@ -51,7 +51,20 @@ struct RrArgs {
   int *dEexp;     // [B]       ... and its exponent
   uint32_t *Qscr; // [grid * warps][S][1056] prefix products Q_k = M_1 .. M_k of the current window (Q-form images + exponent)
   int per_cta;    // samples per CTA (window-major loop: every warp takes per_cta / warps samples one after the other)
+  // weight images (smpo_rr_prep_kernel): per unit (a leg-less site, or one output index of an output site) the two slices
+  // A[:, :, s = 0 / 1] in FRAGMENT ORDER, pre-scaled by 2^Wsh[unit]:  Wimg[(unit * 2 + form) * 512 + reg * 32 + lane]
+  //   form 0 ("P"): (A0, A1 at (row, col), A0, A1 at (row, col + 1)), row = 16 mt + 8 r + g, col = 8 nt + 2 t
+  //   form 1 ("Q"): (A0, A1 at (row, col), A0, A1 at (row + 1, col)), row = 16 mt + 8 r + 2 t, col = 8 nt + g
+  const float4 *Wimg;
+  const int *Wsh;
 };
+
+constexpr int kRingStages = 3;              // staging ring of weight images in shared memory (8 KB each)
+constexpr int kImgFloat4 = 512;             // float4 per image
+
+__host__ __device__ inline int unit_of(int site, int o, int S, int DO) {
+  return site + (DO - 1) * ((site + S - 1) / S) + (site % S == 0 ? o : 0);
+}
 
 // fp32 matrix in accumulator (C) layout: tile (mt, nt) = rows 16 mt .. +15, cols 8 nt .. +7; lane (g = lane / 4, t = lane % 4)
 // holds [0],[1] = (row g, cols 2t, 2t+1) and [2],[3] = (row g + 8, cols 2t, 2t+1).   true matrix = c * 2^ex
@@ -193,164 +206,8 @@ __device__ __forceinline__ void add_aligned(Mat &Z, const Mat &X) {
   Z.ex = e;
 }
 
-// site matrix M[a][r] = sum_s phi[s] * A_site[a][r][s][o] in C layout (ex = 0).  chi == 32, D == 2: 16-byte loads.
-template <int DO>
-__device__ __forceinline__ void form_site(const RrArgs &A, int site, int o, float ph0, float ph1, Mat &M, int lane) {
-  const int g = lane >> 2, t = lane & 3;
-  const bool has_out = site % A.S == 0;
-  const int nj = has_out ? A.DO : 1;
-  const long long per = (long long)A.chi * A.chi * A.D;
-  const long long nwith = (site + A.S - 1) / A.S;
-  const float *W = A.params + per * (site - nwith) + per * A.DO * nwith;
-  M.ex = 0;
-  if (A.chi == kN && A.D == 2 && (nj == 1 || (DO == 2 && nj == 2))) {
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const int row = 16 * mt + 8 * r + g, col = 8 * nt + 2 * t;
-          if (nj == 1) {
-            const float4 v = __ldg(reinterpret_cast<const float4 *>(W + ((size_t)row * kN + col) * 2));
-            M.c[mt][nt][2 * r] = fmaf(ph1, v.y, ph0 * v.x);
-            M.c[mt][nt][2 * r + 1] = fmaf(ph1, v.w, ph0 * v.z);
-          } else {
-            const float4 v0 = __ldg(reinterpret_cast<const float4 *>(W + ((size_t)row * kN + col) * 4));
-            const float4 v1 = __ldg(reinterpret_cast<const float4 *>(W + ((size_t)row * kN + col + 1) * 4));
-            M.c[mt][nt][2 * r] = o == 0 ? fmaf(ph1, v0.z, ph0 * v0.x) : fmaf(ph1, v0.w, ph0 * v0.y);
-            M.c[mt][nt][2 * r + 1] = o == 0 ? fmaf(ph1, v1.z, ph0 * v1.x) : fmaf(ph1, v1.w, ph0 * v1.y);
-          }
-        }
-    return;
-  }
-  // general bond <= 32 / output dimension: guarded scalar loads
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int row = 16 * mt + 8 * (q >> 1) + g, col = 8 * nt + 2 * t + (q & 1);
-        float v = 0.f;
-        if (row < A.chi && col < A.chi) {
-          const float *w = W + (((size_t)row * A.chi + col) * 2) * nj + o;
-          v = fmaf(ph1, __ldg(w + nj), ph0 * __ldg(w));
-        }
-        M.c[mt][nt][q] = v;
-      }
-}
-
-// phi of the window's sites: lane k evaluates site w0 + k; read with __shfl_sync
-__device__ __forceinline__ void window_phi(const RrArgs &A, long long b, int w0, int w1, int lane, float &p0, float &p1) {
-  p0 = p1 = 0.f;
-  if (w0 + lane < w1) {
-    float ph[2];
-    embed_site_d<2>(A.emb, A.x[(size_t)b * A.L + w0 + lane], ph);
-    p0 = ph[0];
-    p1 = ph[1];
-  }
-}
-
-// The forward recursion of one window: E (entry environment) -> Enew.  When `keep` is set the images the VJP needs are
-// left in qP (Q(P_w)) and the caller's o-loop callback is used instead (the backward kernel has its own loop).
-template <int DO>
-__device__ __forceinline__ void window_chain(const RrArgs &A, int w0, int w1, float p0, float p1, int lane, bool &havep, Img &qP) {
-  const int K = w1 - w0 - 1;
-  havep = K > 0;
-  if (!havep) return;
-  Mat Pm;
-  form_site<DO>(A, w0 + 1, 0, __shfl_sync(0xffffffffu, p0, 1), __shfl_sync(0xffffffffu, p1, 1), Pm, lane);
-  for (int k = 2; k <= K; ++k) {
-    Img a, pm, q;
-    split(Pm, a);
-    Mat Mk;
-    form_site<DO>(A, w0 + k, 0, __shfl_sync(0xffffffffu, p0, k), __shfl_sync(0xffffffffu, p1, k), Mk, lane);
-    split(Mk, pm);
-    transpose_blocks(pm, q);
-    product<false, false>(a, q, Pm);
-  }
-  Img pP;
-  split(Pm, pP);
-  transpose_blocks(pP, qP);
-}
-
-template <int DO> __global__ void __launch_bounds__(128) smpo_rr_fwd_kernel(RrArgs A) {
-  const int lane = threadIdx.x & 31;
-  const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (b >= A.B) return;  // (no block-level synchronisation anywhere in this kernel)
-  Mat E;
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) E.c[i][j][q] = 0.f;
-  if (lane == 0) E.c[0][0][0] = 1.f;
-  E.ex = 0;
-  for (int w = 0; w < A.nwin; ++w) {
-    const int w0 = w * A.S, w1 = min(w0 + A.S, A.L);
-    if (A.stash) {
-      float *dst = A.Estash + ((size_t)w * A.B + b) * 1024 + lane;
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) dst[((i * 4 + j) * 4 + q) * 32] = E.c[i][j][q];
-      if (lane == 0) A.Eexp[(size_t)w * A.B + b] = E.ex;
-    }
-    float p0, p1;
-    window_phi(A, b, w0, w1, lane, p0, p1);
-    bool havep;
-    Img qP;
-    window_chain<DO>(A, w0, w1, p0, p1, lane, havep, qP);
-    Img pE;
-    split(E, pE);
-    Mat En;
-    En.ex = INT_MIN;
-    const float q0 = __shfl_sync(0xffffffffu, p0, 0), q1 = __shfl_sync(0xffffffffu, p1, 0);
-#pragma unroll 1
-    for (int o = 0; o < A.DO; ++o) {
-      Mat T;
-      form_site<DO>(A, w0, o, q0, q1, T, lane);
-      Img pT, qT;
-      if (havep) {
-        Img pM;
-        split(T, pM);
-        product<false, false>(pM, qP, T);
-      }
-      split(T, pT);
-      transpose_blocks(pT, qT);
-      Mat U;
-      product<false, false>(pE, qT, U);
-      Img pU, qU;
-      split(U, pU);
-      transpose_blocks(pU, qU);
-      Mat C;
-      product<true, false>(qT, qU, C);
-      add_aligned(En, C);
-    }
-    E = En;
-  }
-  // n = E[0][0] * 2^ex
-  float lval = 0.f;
-  if (lane == 0) {
-    int e2 = 0;
-    const float nmv = frexpf(E.c[0][0][0], &e2);
-    const int es = E.ex + e2;
-    A.nm[b] = nmv;
-    A.esum[b] = es;
-    if (A.out) A.out[b] = nmv;
-    if (A.out_exp) A.out_exp[b] = es;
-    lval = smpo_head<float>(A.head, nmv, es, (float *)nullptr);
-    if (A.loss) A.loss[b] = lval;
-    if (A.loss_sum) atomicAdd(A.loss_sum, (double)lval);
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------------
-// VJP.  Window-major: a CTA owns `per_cta` samples and walks the windows backwards; inside a window its W warps take the
+// VJP helpers + kernel.  Window-major: a CTA owns `per_cta` samples and walks the windows backwards; inside a window its W warps take the
 // samples W at a time.  For one sample and window (E = stashed entry environment, dE' = adjoint of the exit environment):
 //     recompute  Q_k = M_1 .. M_k (prefixes to scratch),  P = Q_K,  T^o = M^o P,  U^o = E T^o
 //     dT^o = 2 U^o dE'      dE += T^o dE' T^o^T      dM^o = dT^o P^T      dP += M^o^T dT^o
@@ -432,16 +289,278 @@ __device__ __forceinline__ void reduce_grad(float *stage, float *acc, const Mat 
   __syncthreads();
 }
 
+// ---- weight images ---------------------------------------------------------------------------------------------------
+// One thread per (unit, form, reg, lane).  The power-of-two scale of a unit comes from an a-priori bound: |phi0 A0 + phi1 A1|
+// <= sqrt(2) max|A| for a unit-norm phi, so sh = 14 - exponent(sqrt(2) max|A|) puts every site matrix below 2^14 without a
+// per-sample maximum.
+__global__ void smpo_rr_unitmax_kernel(const float *__restrict__ params, int *__restrict__ Wsh, int L, int chi, int S, int DO) {
+  const int unit = blockIdx.x;
+  // unit -> (site, o)
+  int site = 0, o = 0;
+  {
+    // units are ordered by site; an output site contributes DO units
+    const int per_win = S - 1 + DO;
+    const int w = unit / per_win, rem = unit - w * per_win;
+    if (rem < DO) { site = w * S; o = rem; }
+    else { site = w * S + (rem - DO + 1); o = 0; }
+  }
+  if (site >= L) { if (threadIdx.x == 0) Wsh[unit] = 0; return; }
+  const int nj = site % S == 0 ? DO : 1;
+  const long long per = (long long)chi * chi * 2;
+  const long long nwith = (site + S - 1) / S;
+  const float *W = params + per * (site - nwith) + per * DO * nwith;
+  float m = 0.f;
+  for (int i = threadIdx.x; i < chi * chi * 2; i += blockDim.x) m = fmaxf(m, fabsf(W[(size_t)i * nj + o]));
+  __shared__ float red[32];
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x + 31) / 32; ++w) m = fmaxf(m, red[w]);
+    int e = 0;
+    if (m > 0.f) frexpf(m * 1.41421357f, &e);
+    Wsh[unit] = m > 0.f ? max(-100, min(100, 14 - e)) : 0;
+  }
+}
+
+__global__ void smpo_rr_prep_kernel(const float *__restrict__ params, const int *__restrict__ Wsh, float4 *__restrict__ Wimg,
+                                    int nunit, int L, int chi, int S, int DO) {
+  const long long total = (long long)nunit * 2 * kImgFloat4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int lane = (int)(i & 31), reg = (int)((i >> 5) & 15), form = (int)((i >> 9) & 1), unit = (int)(i >> 10);
+    const int per_win = S - 1 + DO;
+    const int w = unit / per_win, rem = unit - w * per_win;
+    int site, o;
+    if (rem < DO) { site = w * S; o = rem; }
+    else { site = w * S + (rem - DO + 1); o = 0; }
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (site < L) {
+      const int nj = site % S == 0 ? DO : 1;
+      const long long per = (long long)chi * chi * 2;
+      const long long nwith = (site + S - 1) / S;
+      const float *W = params + per * (site - nwith) + per * DO * nwith;
+      const float sc = ldexpf(1.f, Wsh[unit]);
+      const int g = lane >> 2, t = lane & 3, r = reg & 1, nt = (reg >> 1) & 3, mt = reg >> 3;
+      int row0, col0, row1, col1;
+      if (form == 0) { row0 = row1 = 16 * mt + 8 * r + g; col0 = 8 * nt + 2 * t; col1 = col0 + 1; }
+      else { row0 = 16 * mt + 8 * r + 2 * t; row1 = row0 + 1; col0 = col1 = 8 * nt + g; }
+      auto at = [&](int row, int col, int sidx) -> float {
+        return (row < chi && col < chi) ? W[(((size_t)row * chi + col) * 2 + sidx) * nj + o] * sc : 0.f;
+      };
+      v = make_float4(at(row0, col0, 0), at(row0, col0, 1), at(row1, col1, 0), at(row1, col1, 1));
+    }
+    Wimg[i] = v;
+  }
+}
+
+// ---- staging ring: the CTA's warps walk the same sequence of weight images; image q of the sequence sits in ring slot
+//      q % kRingStages, fetched kRingStages - 1 requests ahead with cp.async (every thread copies its share) ----
+struct Request {
+  int unit, form;
+};
+
+__device__ __forceinline__ void ring_issue(float4 *ring, int q, const RrArgs &A, Request rq, bool valid) {
+  if (valid) {
+    const float4 *src = A.Wimg + ((size_t)rq.unit * 2 + rq.form) * kImgFloat4;
+    float4 *dst = ring + (size_t)(q % kRingStages) * kImgFloat4;
+    for (int i = threadIdx.x; i < kImgFloat4; i += blockDim.x) cp_async16(dst + i, src + i);
+  }
+  cp_async_commit();  // (always: the group count must advance uniformly)
+}
+// image q is complete and visible to the whole CTA; the slot of image q - 1 may be refilled afterwards
+__device__ __forceinline__ const float4 *ring_acquire(float4 *ring, int q) {
+  cp_async_wait<kRingStages - 2>();
+  __syncthreads();
+  return ring + (size_t)(q % kRingStages) * kImgFloat4;
+}
+
+// site matrix M = phi0 A0 + phi1 A1 straight into its fp16 hi / lo image (P or Q form, as staged); ex = -Wsh[unit]
+__device__ __forceinline__ void form_img(const float4 *buf, int sh, float ph0, float ph1, Img &X, int lane) {
+  X.ex = -sh;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const float4 v = buf[((mt * 4 + nt) * 2 + r) * 32 + lane];
+        const float a = fmaf(ph1, v.y, ph0 * v.x), b = fmaf(ph1, v.w, ph0 * v.z);
+        const __half2 h = __floats2half2_rn(a, b);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+        X.hi[mt][nt][r] = *reinterpret_cast<const uint32_t *>(&h);
+        X.lo[mt][nt][r] = *reinterpret_cast<const uint32_t *>(&l);
+      }
+}
+
+// phi of the window's sites: lane k evaluates site w0 + k; read with __shfl_sync
+__device__ __forceinline__ void window_phi(const RrArgs &A, long long b, int w0, int w1, int lane, float &p0, float &p1) {
+  p0 = p1 = 0.f;
+  if (w0 + lane < w1) {
+    float ph[2];
+    embed_site_d<2>(A.emb, A.x[(size_t)b * A.L + w0 + lane], ph);
+    p0 = ph[0];
+    p1 = ph[1];
+  }
+}
+
+// Request j of window w.  Forward: chain sites k = 1 .. K (k = 1 in P form: it starts the product as a left operand; the rest
+// in Q form: right operands), then the output site's DO units in P form.  VJP: the same, then for k = K .. 2 the P form of
+// site k (G M_k^T), preceded at k = 2 by the Q form of site 1 (Q_1 = M_1).
+__device__ __forceinline__ int nreq_of(const RrArgs &A, int w, bool bwd) {
+  const int w0 = w * A.S, K = min(w0 + A.S, A.L) - w0 - 1;
+  return K + A.DO + (bwd ? (K > 1 ? K : 0) : 0);
+}
+__device__ __forceinline__ Request request_of(const RrArgs &A, int w, int j) {
+  const int w0 = w * A.S, K = min(w0 + A.S, A.L) - w0 - 1;
+  Request rq;
+  if (j < K) { rq.unit = unit_of(w0 + j + 1, 0, A.S, A.DO); rq.form = j == 0 ? 0 : 1; return rq; }
+  j -= K;
+  if (j < A.DO) { rq.unit = unit_of(w0, j, A.S, A.DO); rq.form = 0; return rq; }
+  j -= A.DO;  // VJP tail: P(K), P(K-1), ..., P(3), Q(1), P(2)
+  if (j < K - 2) { rq.unit = unit_of(w0 + K - j, 0, A.S, A.DO); rq.form = 0; return rq; }
+  if (j == K - 2) { rq.unit = unit_of(w0 + 1, 0, A.S, A.DO); rq.form = 1; return rq; }
+  rq.unit = unit_of(w0 + 2, 0, A.S, A.DO);
+  rq.form = 0;
+  return rq;
+}
+// walks the request sequence of the whole kernel (windows ascending for the forward pass, descending for the VJP, `reps`
+// passes over every window: the VJP's sample rounds)
+struct Cursor {
+  int w, j, rep;
+  bool done;
+};
+__device__ __forceinline__ void cursor_next(const RrArgs &A, Cursor &c, bool bwd, int reps) {
+  if (c.done) return;
+  if (++c.j < nreq_of(A, c.w, bwd)) return;
+  c.j = 0;
+  if (++c.rep < reps) return;
+  c.rep = 0;
+  if (bwd) { if (--c.w < 0) c.done = true; }
+  else { if (++c.w >= A.nwin) c.done = true; }
+}
+
+constexpr int kFwdWarps = 8;
+
+template <int DO> __global__ void __launch_bounds__(kFwdWarps * 32, 1) smpo_rr_fwd_kernel(RrArgs A) {
+  __shared__ __align__(16) float4 ring[kRingStages * kImgFloat4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long b = (long long)blockIdx.x * kFwdWarps + warp;
+  const bool on = b < A.B;  // (every warp takes part in the staging barriers)
+  const long long bs = on ? b : 0;
+  Cursor pf{0, 0, 0, false};
+  int q_issue = 0, q_use = 0;
+  for (; q_issue < kRingStages - 1; ++q_issue) {
+    ring_issue(ring, q_issue, A, pf.done ? Request{0, 0} : request_of(A, pf.w, pf.j), !pf.done);
+    cursor_next(A, pf, false, 1);
+  }
+  auto next_image = [&]() -> const float4 * {
+    const float4 *buf = ring_acquire(ring, q_use);
+    ring_issue(ring, q_issue, A, pf.done ? Request{0, 0} : request_of(A, pf.w, pf.j), !pf.done);
+    cursor_next(A, pf, false, 1);
+    ++q_issue;
+    ++q_use;
+    return buf;
+  };
+  Mat E;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) E.c[i][j][q] = 0.f;
+  if (lane == 0) E.c[0][0][0] = 1.f;
+  E.ex = 0;
+  for (int w = 0; w < A.nwin; ++w) {
+    const int w0 = w * A.S, w1 = min(w0 + A.S, A.L), K = w1 - w0 - 1;
+    if (A.stash && on) {
+      store_mat(A.Estash + ((size_t)w * A.B + b) * 1024, E, lane);
+      if (lane == 0) A.Eexp[(size_t)w * A.B + b] = E.ex;
+    }
+    float p0, p1;
+    window_phi(A, bs, w0, w1, lane, p0, p1);
+    Img qP;
+    if (K > 0) {
+      Img a;
+      form_img(next_image(), A.Wsh[unit_of(w0 + 1, 0, A.S, A.DO)], __shfl_sync(0xffffffffu, p0, 1), __shfl_sync(0xffffffffu, p1, 1), a,
+               lane);
+      for (int k = 2; k <= K; ++k) {
+        Img q;
+        form_img(next_image(), A.Wsh[unit_of(w0 + k, 0, A.S, A.DO)], __shfl_sync(0xffffffffu, p0, k),
+                 __shfl_sync(0xffffffffu, p1, k), q, lane);
+        Mat Pm;
+        product<false, false>(a, q, Pm);
+        split(Pm, a);
+      }
+      transpose_blocks(a, qP);
+    }
+    Img pE;
+    split(E, pE);
+    Mat En;
+    En.ex = INT_MIN;
+    const float q0 = __shfl_sync(0xffffffffu, p0, 0), q1 = __shfl_sync(0xffffffffu, p1, 0);
+#pragma unroll 1
+    for (int o = 0; o < A.DO; ++o) {
+      Img pT, qT;
+      form_img(next_image(), A.Wsh[unit_of(w0, o, A.S, A.DO)], q0, q1, pT, lane);
+      if (K > 0) {
+        Mat T;
+        product<false, false>(pT, qP, T);
+        split(T, pT);
+      }
+      transpose_blocks(pT, qT);
+      Mat U;
+      product<false, false>(pE, qT, U);
+      Img pU, qU;
+      split(U, pU);
+      transpose_blocks(pU, qU);
+      Mat C;
+      product<true, false>(qT, qU, C);
+      add_aligned(En, C);
+    }
+    E = En;
+  }
+  // n = E[0][0] * 2^ex
+  if (lane == 0 && on) {
+    int e2 = 0;
+    const float nmv = frexpf(E.c[0][0][0], &e2);
+    const int es = E.ex + e2;
+    A.nm[b] = nmv;
+    A.esum[b] = es;
+    if (A.out) A.out[b] = nmv;
+    if (A.out_exp) A.out_exp[b] = es;
+    const float lval = smpo_head<float>(A.head, nmv, es, (float *)nullptr);
+    if (A.loss) A.loss[b] = lval;
+    if (A.loss_sum) atomicAdd(A.loss_sum, (double)lval);
+  }
+  cp_async_wait<0>();
+}
+
 template <int DO> __global__ void __launch_bounds__(kBwdWarps * 32, 1) smpo_rr_bwd_kernel(RrArgs A) {
   extern __shared__ __align__(16) float smem[];
   float *stage = smem;                        // [warps][2][1024]
   float *wacc = smem + kBwdWarps * 2048;      // window accumulator: site 0: [DO][2][1024], sites 1 .. S-1: [2][1024]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int acc_floats = (A.DO + A.S - 1) * 2048;
+  float4 *ring = reinterpret_cast<float4 *>(wacc + acc_floats);
   const long long base = (long long)blockIdx.x * A.per_cta;
   const int rounds = (A.per_cta + kBwdWarps - 1) / kBwdWarps;
   uint32_t *Qs = A.Qscr + ((size_t)blockIdx.x * kBwdWarps + warp) * (size_t)A.S * 1056;
   for (int i = threadIdx.x; i < acc_floats; i += blockDim.x) wacc[i] = 0.f;
+  Cursor pf{A.nwin - 1, 0, 0, false};
+  int q_issue = 0, q_use = 0;
+  for (; q_issue < kRingStages - 1; ++q_issue) {
+    ring_issue(ring, q_issue, A, pf.done ? Request{0, 0} : request_of(A, pf.w, pf.j), !pf.done);
+    cursor_next(A, pf, true, rounds);
+  }
+  auto next_image = [&]() -> const float4 * {
+    const float4 *buf = ring_acquire(ring, q_use);
+    ring_issue(ring, q_issue, A, pf.done ? Request{0, 0} : request_of(A, pf.w, pf.j), !pf.done);
+    cursor_next(A, pf, true, rounds);
+    ++q_issue;
+    ++q_use;
+    return buf;
+  };
   __syncthreads();
   for (int w = A.nwin - 1; w >= 0; --w) {
     const int w0 = w * A.S, w1 = min(w0 + A.S, A.L), K = w1 - w0 - 1;
@@ -475,24 +594,21 @@ template <int DO> __global__ void __launch_bounds__(kBwdWarps * 32, 1) smpo_rr_b
       // ---- recompute the chain, prefixes Q_2 .. Q_{K-1} to scratch ----
       Img pP, qP;
       if (K > 0) {
-        Mat Pm;
-        form_site<DO>(A, w0 + 1, 0, __shfl_sync(0xffffffffu, p0, 1), __shfl_sync(0xffffffffu, p1, 1), Pm, lane);
+        form_img(next_image(), A.Wsh[unit_of(w0 + 1, 0, A.S, A.DO)], __shfl_sync(0xffffffffu, p0, 1),
+                 __shfl_sync(0xffffffffu, p1, 1), pP, lane);
         for (int k = 2; k <= K; ++k) {
-          Img a, pm, q;
-          split(Pm, a);
-          Mat Mk;
-          form_site<DO>(A, w0 + k, 0, __shfl_sync(0xffffffffu, p0, k), __shfl_sync(0xffffffffu, p1, k), Mk, lane);
-          split(Mk, pm);
-          transpose_blocks(pm, q);
-          product<false, false>(a, q, Pm);
+          Img q;
+          form_img(next_image(), A.Wsh[unit_of(w0 + k, 0, A.S, A.DO)], __shfl_sync(0xffffffffu, p0, k),
+                   __shfl_sync(0xffffffffu, p1, k), q, lane);
+          Mat Pm;
+          product<false, false>(pP, q, Pm);
+          split(Pm, pP);
           if (k < K) {
-            Img pq, qq;
-            split(Pm, pq);
-            transpose_blocks(pq, qq);
+            Img qq;
+            transpose_blocks(pP, qq);
             store_img(Qs + (size_t)k * 1056, qq, lane);
           }
         }
-        split(Pm, pP);
         transpose_blocks(pP, qP);
       }
       Img pE, pdE;
@@ -504,13 +620,16 @@ template <int DO> __global__ void __launch_bounds__(kBwdWarps * 32, 1) smpo_rr_b
       const float q0 = __shfl_sync(0xffffffffu, p0, 0), q1 = __shfl_sync(0xffffffffu, p1, 0);
 #pragma unroll 1
       for (int o = 0; o < A.DO; ++o) {
-        Mat T;
-        form_site<DO>(A, w0, o, q0, q1, T, lane);
-        Img pM;
-        split(T, pM);
-        if (K > 0) product<false, false>(pM, qP, T);
-        Img pT, qT;
-        split(T, pT);
+        Img pM, pT;
+        form_img(next_image(), A.Wsh[unit_of(w0, o, A.S, A.DO)], q0, q1, pM, lane);
+        if (K > 0) {
+          Mat T;
+          product<false, false>(pM, qP, T);
+          split(T, pT);
+        } else {
+          pT = pM;
+        }
+        Img qT;
         transpose_blocks(pT, qT);
         Mat U;
         product<false, false>(pE, qT, U);
@@ -553,22 +672,15 @@ template <int DO> __global__ void __launch_bounds__(kBwdWarps * 32, 1) smpo_rr_b
         Img pG, qG, qQ;
         split(G, pG);
         transpose_blocks(pG, qG);
-        if (k - 1 >= 2) {
-          load_img(Qs + (size_t)(k - 1) * 1056, qQ, lane);
-        } else {  // Q_1 = M_1
-          Mat M1;
-          form_site<DO>(A, w0 + 1, 0, __shfl_sync(0xffffffffu, p0, 1), __shfl_sync(0xffffffffu, p1, 1), M1, lane);
-          Img p1i;
-          split(M1, p1i);
-          transpose_blocks(p1i, qQ);
-        }
+        if (k - 1 >= 2) load_img(Qs + (size_t)(k - 1) * 1056, qQ, lane);
+        else  // Q_1 = M_1
+          form_img(next_image(), A.Wsh[unit_of(w0 + 1, 0, A.S, A.DO)], __shfl_sync(0xffffffffu, p0, 1),
+                   __shfl_sync(0xffffffffu, p1, 1), qQ, lane);
         Mat dMk;
         product<true, false>(qQ, qG, dMk);  // Q_{k-1}^T G
         reduce_grad(stage, acc_k, dMk, on, pk0, pk1, warp, lane);
-        Mat Mk;
-        form_site<DO>(A, w0 + k, 0, pk0, pk1, Mk, lane);
         Img pMk;
-        split(Mk, pMk);
+        form_img(next_image(), A.Wsh[unit_of(w0 + k, 0, A.S, A.DO)], pk0, pk1, pMk, lane);
         product<false, true>(pG, pMk, G);  // G M_k^T
       }
       if (on && w > 0) {
@@ -600,6 +712,7 @@ template <int DO> __global__ void __launch_bounds__(kBwdWarps * 32, 1) smpo_rr_b
     }
     __syncthreads();
   }
+  cp_async_wait<0>();
 }
 
 }  // namespace rr
