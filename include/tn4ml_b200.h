@@ -40,8 +40,18 @@ enum { TNB_KIND_MPS = 0, TNB_KIND_SMPO = 1 };
 enum { TNB_F32 = 0, TNB_F64 = 1 };
 /* tnb_problem.precision (f32 only): arithmetic of the chain GEMMs */
 enum { TNB_PREC_SIMT = 0, TNB_PREC_TENSOR = 1 };
-/* tnb_embedding.kind -- tn4ml/embeddings.py:287-351, 354-423, 605-717, 544-602 */
-enum { TNB_EMB_TRIG = 0, TNB_EMB_FOURIER = 1, TNB_EMB_POLY = 2, TNB_EMB_RBF = 3 };
+/* tnb_embedding.kind -- tn4ml/embeddings.py:287-351, 354-423, 605-717, 544-602, 426-484, 720-869, 872-928 */
+enum {
+  TNB_EMB_TRIG = 0,
+  TNB_EMB_FOURIER = 1,
+  TNB_EMB_POLY = 2,
+  TNB_EMB_RBF = 3,
+  TNB_EMB_LINCOMP = 4,  /* LinearComplementEmbedding  [x, 1-x] / [1, x, 1-x], unit norm   embeddings.py:426-484 */
+  TNB_EMB_LEGENDRE = 5, /* LegendreEmbedding          P_0 .. P_degree                      embeddings.py:720-768 */
+  TNB_EMB_LAGUERRE = 6, /* LaguerreEmbedding          exp(-x/2) L_k                        embeddings.py:771-820 */
+  TNB_EMB_HERMITE = 7,  /* HermiteEmbedding           exp(-x^2/2) H_k                      embeddings.py:823-869 */
+  TNB_EMB_ARRAYS = 8    /* JaxArraysEmbedding         pre-embedded inputs [1?] + x[0..n_in) embeddings.py:872-928 */
+};
 /* tnb_problem.head -- tn4ml/metrics.py */
 enum {
   TNB_HEAD_NLL = 0,                 /* NegLogLikelihood            metrics.py:17-53   */
@@ -59,10 +69,12 @@ enum {
 typedef struct tnb_embedding {
   int32_t kind;
   int32_t k;            /* trig: number of frequencies, d = 2k          */
-  int32_t p;            /* fourier: d = p                               */
-  int32_t degree;       /* poly: d = degree + include_bias (n = 1)      */
-  int32_t include_bias; /* poly                                         */
+  int32_t p;            /* fourier: d = p; lincomp: d = p (2 or 3)      */
+  int32_t degree;       /* poly; legendre / laguerre / hermite: d = degree + 1 */
+  int32_t include_bias; /* poly; arrays (add_bias)                      */
   int32_t n_centers;    /* rbf: d = n_centers                           */
+  int32_t n_in;         /* raw input values per site (Embedding.input_dim; 0 or 1 = scalar features): poly n, arrays */
+  int32_t cross;        /* poly: include_cross_terms                    */
   double gamma;         /* rbf                                          */
   double centers[TNB_MAX_PHYS];
 } tnb_embedding;
@@ -117,7 +129,7 @@ int tnb_unpack_grads(const tnb_problem *prob, const void *packed, void *const *s
 int64_t tnb_workspace_bytes(const tnb_problem *prob, int64_t batch, int32_t need_grad);
 
 /* Forward: embed + contract + head for `batch` samples.
- *   x        [batch, L]        raw features (dtype)
+ *   x        [batch, L(, n_in)] raw features (dtype); n_in = emb.n_in values per site when > 1
  *   targets  [batch, n_out]    one-hot / soft labels (dtype) or NULL
  *   params   packed site tensors (dtype)
  *   loss     [batch]           per-sample loss (dtype)            (evaluate(): model.py:1048-1076)
@@ -193,7 +205,7 @@ int tnb_norm(const tnb_problem *prob, const void *params, double *log2_norm2, in
  * (every site divided by norm^(1/L), tn.py:103-107), or mult = -1/2 on one site (insert=). */
 int tnb_scale(int32_t dtype, int64_t n, void *params, const double *log2_value, double mult, void *stream);
 
-/* Embedding.__call__ for n scalars: phi [n, d] (dtype), before embed()'s normaliser. */
+/* Embedding.__call__ for n inputs (x [n, n_in]): phi [n, d] (dtype), before embed()'s normaliser. */
 int tnb_embed(const tnb_embedding *emb, int32_t dtype, int64_t n, const void *x, void *phi,
               void *stream);
 

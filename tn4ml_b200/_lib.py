@@ -15,7 +15,7 @@ TNB_MAX_OUT = 32
 KIND_MPS, KIND_SMPO = 0, 1
 F32, F64 = 0, 1
 PREC_SIMT, PREC_TENSOR = 0, 1
-EMB_TRIG, EMB_FOURIER, EMB_POLY, EMB_RBF = 0, 1, 2, 3
+EMB_TRIG, EMB_FOURIER, EMB_POLY, EMB_RBF, EMB_LINCOMP, EMB_LEGENDRE, EMB_LAGUERRE, EMB_HERMITE, EMB_ARRAYS = range(9)
 REG_LOG_FROB, REG_LOG_POW_FROB, REG_LOG_RELU_FROB, REG_QUAD_FROB = range(4)
 (HEAD_NLL, HEAD_SOFTMAX_XENT, HEAD_SOFTMAX_XENT_WEIGHTED, HEAD_XENT_SOFTMAX_ARGMAX, HEAD_MSE,
  HEAD_TSN, HEAD_LOGQUAD, HEAD_QUAD) = range(8)
@@ -24,7 +24,8 @@ REG_LOG_FROB, REG_LOG_POW_FROB, REG_LOG_RELU_FROB, REG_QUAD_FROB = range(4)
 class TnbEmbedding(C.Structure):
     _fields_ = [
         ("kind", C.c_int32), ("k", C.c_int32), ("p", C.c_int32), ("degree", C.c_int32),
-        ("include_bias", C.c_int32), ("n_centers", C.c_int32), ("gamma", C.c_double),
+        ("include_bias", C.c_int32), ("n_centers", C.c_int32), ("n_in", C.c_int32), ("cross", C.c_int32),
+        ("gamma", C.c_double),
         ("centers", C.c_double * TNB_MAX_PHYS),
     ]
 

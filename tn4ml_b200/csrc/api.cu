@@ -105,8 +105,23 @@ static int emb_dim(const tnb_embedding &e) {
   switch (e.kind) {
     case TNB_EMB_TRIG: return 2 * e.k;
     case TNB_EMB_FOURIER: return e.p;
-    case TNB_EMB_POLY: return e.degree + (e.include_bias ? 1 : 0);
+    case TNB_EMB_POLY: {
+      const int n = e.n_in > 0 ? e.n_in : 1;
+      long long total = e.include_bias ? 1 : 0;
+      for (int dg = 1; dg <= e.degree; ++dg) {
+        if (!e.cross) { total += n; continue; }
+        long long c = 1;  // C(n + dg - 1, dg)
+        for (int q = 1; q <= dg; ++q) c = c * (n + dg - q) / q;
+        total += c;
+      }
+      return total > TNB_MAX_PHYS ? -1 : (int)total;
+    }
     case TNB_EMB_RBF: return e.n_centers;
+    case TNB_EMB_LINCOMP: return e.p == 2 || e.p == 3 ? e.p : -1;
+    case TNB_EMB_LEGENDRE:
+    case TNB_EMB_LAGUERRE:
+    case TNB_EMB_HERMITE: return e.degree + 1;
+    case TNB_EMB_ARRAYS: return (e.n_in > 0 ? e.n_in : 1) + (e.include_bias ? 1 : 0);
   }
   return -1;
 }

@@ -37,17 +37,28 @@ template <> struct Num<double> {
   static __device__ __forceinline__ double max(double a, double b) { return ::fmax(a, b); }
 };
 
-// Embedding parameters in kernel-argument form (typed copy of tnb_embedding).
+// Embedding parameters in kernel-argument form (typed copy of tnb_embedding).  n_in = number of raw input values per site
+// (Embedding.input_dim; 1 for the scalar feature maps): site i of sample b reads x[(b * L + i) * n_in ...].
 template <typename T> struct EmbParams {
-  int kind, k, p, degree, include_bias, n_centers, d;
+  int kind, k, p, degree, include_bias, n_centers, d, n_in, cross;
   T gamma;
   T centers[kMaxPhys];
 };
 
-// Raw feature map phi(x) -> out[0..d)   (tn4ml/embeddings.py:340-351, 407-423, 693-717, 601-602)
+// typed copy of the ABI struct (host side, every family's argument builder)
+template <typename T> static inline void fill_emb(const tnb_embedding &e, EmbParams<T> &o, int d) {
+  o.kind = e.kind; o.k = e.k; o.p = e.p; o.degree = e.degree; o.include_bias = e.include_bias;
+  o.n_centers = e.n_centers; o.d = d; o.gamma = (T)e.gamma;
+  o.n_in = e.n_in > 0 ? e.n_in : 1; o.cross = e.cross;
+  for (int i = 0; i < kMaxPhys; ++i) o.centers[i] = (T)e.centers[i];
+}
+
+// Raw feature map phi(xp[0 .. n_in)) -> out[0..d)
+// (tn4ml/embeddings.py:340-351, 407-423, 693-717, 601-602, 478-484, 754-768, 805-820, 857-869, 913-928)
 template <typename T>
-__device__ __forceinline__ void feature_map(const EmbParams<T> &e, T x, T *out) {
+__device__ __forceinline__ void feature_map(const EmbParams<T> &e, const T *xp, T *out) {
   using N = Num<T>;
+  const T x = xp[0];
   switch (e.kind) {
     case TNB_EMB_TRIG: {
       // 1/sqrt(k) [cos(pi x / 2^i), i=1..k ; sin(pi x / 2^i), i=1..k]
@@ -84,12 +95,38 @@ __device__ __forceinline__ void feature_map(const EmbParams<T> &e, T x, T *out) 
       break;
     }
     case TNB_EMB_POLY: {
+      // [1?] then, degree by degree, the monomials over the n_in inputs in itertools.combinations_with_replacement order
+      // (non-decreasing index tuples, lexicographic); without cross terms only the pure powers x_j^dg survive.
       int o = 0;
       if (e.include_bias) out[o++] = T(1);
-      T pw = x;
-      for (int dg = 1; dg <= e.degree; ++dg) {
-        out[o++] = pw;
-        pw *= x;
+      if (e.n_in == 1) {
+        T pw = x;
+        for (int dg = 1; dg <= e.degree; ++dg) {
+          out[o++] = pw;
+          pw *= x;
+        }
+      } else if (!e.cross) {
+        for (int dg = 1; dg <= e.degree; ++dg)
+          for (int j = 0; j < e.n_in; ++j) {
+            T pw = xp[j];
+            for (int q = 1; q < dg; ++q) pw *= xp[j];
+            out[o++] = pw;
+          }
+      } else {
+        for (int dg = 1; dg <= e.degree && dg <= 8; ++dg) {
+          int idx[8];
+          for (int q = 0; q < dg; ++q) idx[q] = 0;
+          while (true) {
+            T pr = T(1);
+            for (int q = 0; q < dg; ++q) pr *= xp[idx[q]];
+            if (o < kMaxPhys) out[o++] = pr;
+            int q = dg - 1;  // next non-decreasing tuple
+            while (q >= 0 && idx[q] == e.n_in - 1) --q;
+            if (q < 0) break;
+            const int v = idx[q] + 1;
+            for (int r = q; r < dg; ++r) idx[r] = v;
+          }
+        }
       }
       break;
     }
@@ -104,25 +141,92 @@ __device__ __forceinline__ void feature_map(const EmbParams<T> &e, T x, T *out) 
       for (int j = 0; j < e.n_centers; ++j) out[j] *= inv;
       break;
     }
+    case TNB_EMB_LINCOMP: {
+      // [x, 1 - x] or [1, x, 1 - x], divided by its 2-norm
+      int o = 0;
+      if (e.p == 3) out[o++] = T(1);
+      out[o++] = x;
+      out[o++] = T(1) - x;
+      T n2 = 0;
+      for (int j = 0; j < o; ++j) n2 += out[j] * out[j];
+      T inv = T(1) / N::sqrt(n2);
+      for (int j = 0; j < o; ++j) out[j] *= inv;
+      break;
+    }
+    case TNB_EMB_LEGENDRE: {
+      // P_0 = 1, P_1 = x, (i + 1) P_{i+1} = (2 i + 1) x P_i - i P_{i-1}        (tn4ml/scipy/special.py:6-28)
+      T pm = T(1), pc = x;
+      out[0] = pm;
+      if (e.degree >= 1) out[1] = pc;
+      for (int i = 1; i < e.degree; ++i) {
+        T pn = (T(2 * i + 1) * x * pc - T(i) * pm) / T(i + 1);
+        pm = pc; pc = pn;
+        out[i + 1] = pn;
+      }
+      break;
+    }
+    case TNB_EMB_LAGUERRE: {
+      // exp(-x / 2) L_k(x):  L_0 = 1, L_1 = 1 - x, i L_i = (2 i - 1 - x) L_{i-1} - (i - 1) L_{i-2}   (special.py:57-79)
+      const T w = N::exp(-x * T(0.5));
+      T lm = T(1), lc = T(1) - x;
+      out[0] = w * lm;
+      if (e.degree >= 1) out[1] = w * lc;
+      for (int i = 2; i <= e.degree; ++i) {
+        T ln = ((T(2 * i - 1) - x) * lc - T(i - 1) * lm) / T(i);
+        lm = lc; lc = ln;
+        out[i] = w * ln;
+      }
+      break;
+    }
+    case TNB_EMB_HERMITE: {
+      // exp(-x^2 / 2) H_k(x):  H_0 = 1, H_1 = 2 x, H_i = 2 x H_{i-1} - 2 (i - 1) H_{i-2}             (special.py:108-130)
+      const T w = N::exp(-T(0.5) * x * x);
+      T hm = T(1), hc = T(2) * x;
+      out[0] = w * hm;
+      if (e.degree >= 1) out[1] = w * hc;
+      for (int i = 2; i <= e.degree; ++i) {
+        T hn = T(2) * x * hc - T(2 * (i - 1)) * hm;
+        hm = hc; hc = hn;
+        out[i] = w * hn;
+      }
+      break;
+    }
+    case TNB_EMB_ARRAYS: {
+      // pre-embedded inputs: [1?] + x[0 .. n_in)                                                    (embeddings.py:913-928)
+      int o = 0;
+      if (e.include_bias) out[o++] = T(1);
+      for (int j = 0; j < e.n_in; ++j) out[o++] = xp[j];
+      break;
+    }
   }
 }
 
 // embed(): the product state is normalised (embeddings.py:1374-1387); the global factor
 // prod_i ||phi_i||^-1 is applied site by site, which is the same product state.
 template <typename T>
-__device__ __forceinline__ void embed_site(const EmbParams<T> &e, T x, T *out) {
-  feature_map(e, x, out);
+__device__ __forceinline__ void embed_site(const EmbParams<T> &e, const T *xp, T *out) {
+  feature_map(e, xp, out);
   T n2 = 0;
   for (int s = 0; s < e.d; ++s) n2 += out[s] * out[s];
   T inv = T(1) / Num<T>::sqrt(n2);
   for (int s = 0; s < e.d; ++s) out[s] *= inv;
 }
 
+template <typename T>
+__device__ __noinline__ void feature_map_generic(const EmbParams<T> &e, const T *xp, T *out, int d) {
+  T xin[kMaxPhys], tmp[kMaxPhys];
+  for (int j = 0; j < e.n_in; ++j) xin[j] = xp ? xp[j] : T(0.5);  // xp == nullptr: padding row
+  feature_map(e, xin, tmp);
+  for (int s = 0; s < d; ++s) out[s] = tmp[s];
+}
+
 // Same map with the physical dimension as a compile-time constant: every loop unrolls and phi stays in
 // registers (the tensor-core chain kernel evaluates it once per site and sample inside its epilogue warps).
+// xp == nullptr stands for a padding row (any finite input).
 template <int D, typename T>
-__device__ __forceinline__ void embed_site_d(const EmbParams<T> &e, T x, T (&out)[D]) {
+__device__ __forceinline__ void embed_site_d(const EmbParams<T> &e, const T *xp, T (&out)[D]) {
   using N = Num<T>;
+  const T x = xp ? xp[0] : T(0.5);
   if (e.kind == TNB_EMB_TRIG) {
     constexpr int K = D / 2 > 0 ? D / 2 : 1;
     const T inv = T(1) / N::sqrt(T(K));
@@ -153,16 +257,22 @@ __device__ __forceinline__ void embed_site_d(const EmbParams<T> &e, T x, T (&out
       }
       out[j] = v;
     }
-  } else if (e.kind == TNB_EMB_POLY) {
+  } else if (e.kind == TNB_EMB_POLY && e.n_in == 1) {
     T pw = e.include_bias ? T(1) : x;
 #pragma unroll
     for (int s = 0; s < D; ++s) {
       out[s] = pw;
       pw *= x;
     }
-  } else {
+  } else if (e.kind == TNB_EMB_RBF) {
 #pragma unroll
     for (int j = 0; j < D; ++j) out[j] = N::exp(-e.gamma * (x - e.centers[j]));
+  } else {
+    // the less common maps: the generic routine out of line (its local arrays stay out of the caller's frame)
+    T tmp[D];
+    feature_map_generic(e, xp, tmp, D);
+#pragma unroll
+    for (int s = 0; s < D; ++s) out[s] = tmp[s];
   }
   T n2 = 0;
 #pragma unroll

@@ -5,12 +5,6 @@
 
 namespace tnb {
 
-template <typename T> static void fill_emb(const tnb_embedding &e, EmbParams<T> &o, int d) {
-  o.kind = e.kind; o.k = e.k; o.p = e.p; o.degree = e.degree; o.include_bias = e.include_bias;
-  o.n_centers = e.n_centers; o.d = d; o.gamma = (T)e.gamma;
-  for (int i = 0; i < kMaxPhys; ++i) o.centers[i] = (T)e.centers[i];
-}
-
 template <typename T>
 static void fill_mps_args(const tnb_problem *p, const MpsPlan &P, long long B, const void *x, const void *targets,
                           void *ws, MpsArgs<T> &A) {

@@ -346,9 +346,10 @@ template <typename T>
 __device__ __forceinline__ void load_phi(const MpsArgs<T> &A, long long b0, int BT, int site, T *phi_s) {
   for (int r = threadIdx.x; r < BT; r += blockDim.x) {
     long long b = b0 + r;
-    T xv = b < A.B ? A.x[(size_t)b * A.L + site] : T(0.5);
-    T ph[kMaxPhys];
-    embed_site(A.emb, xv, ph);
+    T ph[kMaxPhys], pad[kMaxPhys];
+    if (b >= A.B)
+      for (int j = 0; j < A.emb.n_in; ++j) pad[j] = T(0.5);
+    embed_site(A.emb, b < A.B ? A.x + ((size_t)b * A.L + site) * A.emb.n_in : pad, ph);
     for (int s = 0; s < A.D; ++s) phi_s[r * A.D + s] = ph[s];
   }
 }
@@ -617,7 +618,7 @@ template <typename T> __global__ void mps_wq_kernel(MpsArgs<T> A) {
   const int site = (int)(i / A.B);
   const long long b = i - (long long)site * A.B;
   T ph[kMaxPhys];
-  embed_site(A.emb, A.x[(size_t)b * A.L + site], ph);
+  embed_site(A.emb, A.x + ((size_t)b * A.L + site) * A.emb.n_in, ph);
   const T f = site == A.c ? T(1) : Num<T>::ldexp(T(1), -A.exps[(size_t)site * A.B + b]);
   for (int s = 0; s < A.D; ++s) A.wq[((size_t)site * A.D + s) * A.B + b] = ph[s] * f;
 }
@@ -818,7 +819,7 @@ __global__ void embed_kernel(EmbParams<T> e, long long n, const T *__restrict__ 
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   T ph[kMaxPhys];
-  feature_map(e, x[i], ph);
+  feature_map(e, x + i * e.n_in, ph);
   for (int s = 0; s < e.d; ++s) phi[i * e.d + s] = ph[s];
 }
 

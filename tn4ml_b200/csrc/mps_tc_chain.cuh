@@ -652,7 +652,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       const bool valid = T[t].valid;
       const long long b = T[t].b;
       float ph[D];
-      embed_site_d<D>(M.emb, valid ? M.x[T[t].bs * L + site] : 0.5f, ph);
+      embed_site_d<D>(M.emb, valid ? M.x + (T[t].bs * L + site) * M.emb.n_in : nullptr, ph);
       const int dsite = (mode == 1 && valid && lead) ? M.exps[(size_t)site * M.B + b] : 0;
       const int kw = A.kW[slab];
       int e;
@@ -714,7 +714,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       float y[TILES][kMaxOut];
       float phc[TILES][D];
 #pragma unroll
-      for (int t = 0; t < TILES; ++t) embed_site_d<D>(M.emb, T[t].valid ? M.x[T[t].bs * L + c] : 0.5f, phc[t]);
+      for (int t = 0; t < TILES; ++t) embed_site_d<D>(M.emb, T[t].valid ? M.x + (T[t].bs * L + c) * M.emb.n_in : nullptr, phc[t]);
       for (int k = 0; k < C; ++k) {
 #pragma unroll
         for (int t = 0; t < TILES; ++t) {
@@ -801,7 +801,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
           mps_head<float>(M.head, C, yl, E, tl, M.cw, dy[t]);
           for (int k = 0; k < C; ++k) dy[t][k] = valid ? dy[t][k] * M.loss_scale : 0.f;
         }
-        embed_site_d<D>(M.emb, valid ? M.x[T[t].bs * L + c] : 0.5f, phc[t]);
+        embed_site_d<D>(M.emb, valid ? M.x + (T[t].bs * L + c) * M.emb.n_in : nullptr, phc[t]);
         float dmax = 0.f;
         for (int k = 0; k < C; ++k) dmax = fmaxf(dmax, fabsf(dy[t][k]));
         ed[t] = 0;
@@ -877,7 +877,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
             const long long b = T[t].b;
             const int q = T[t].ea - M.exps[(size_t)jb * M.B + b];
             float ph[D];
-            embed_site_d<D>(M.emb, M.x[(size_t)b * L + jb], ph);
+            embed_site_d<D>(M.emb, M.x + ((size_t)b * L + jb) * M.emb.n_in, ph);
 #pragma unroll
             for (int s = 0; s < D; ++s) A.wq[((size_t)jb * D + s) * M.B + b] = ph[s] * ldexpf(1.f, q);
             qm = q;

@@ -60,10 +60,7 @@ int64_t rr_smpo_workspace_bytes(const tnb_problem *p, long long B, int need_grad
 static void fill(const tnb_problem *p, const RrPlan &P, long long B, const void *x, const void *params, void *ws, RrArgs &A) {
   char *w = (char *)ws;
   A.L = p->L; A.chi = p->chi; A.D = p->d; A.DO = p->n_out; A.S = p->spacing; A.nwin = P.nwin; A.head = p->head; A.B = B;
-  A.emb.kind = p->emb.kind; A.emb.k = p->emb.k; A.emb.p = p->emb.p; A.emb.degree = p->emb.degree;
-  A.emb.include_bias = p->emb.include_bias; A.emb.n_centers = p->emb.n_centers; A.emb.d = p->d;
-  A.emb.gamma = (float)p->emb.gamma;
-  for (int i = 0; i < kMaxPhys; ++i) A.emb.centers[i] = (float)p->emb.centers[i];
+  fill_emb<float>(p->emb, A.emb, p->d);
   A.x = (const float *)x; A.params = (const float *)params;
   A.Estash = (float *)(w + P.off_E); A.Eexp = (int *)(w + P.off_Eexp); A.esum = (int *)(w + P.off_esum);
   A.nm = (float *)(w + P.off_nm);

@@ -153,40 +153,45 @@ template <bool LT, bool RT> __device__ __forceinline__ void product(const Img &L
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      float c[4] = {0.f, 0.f, 0.f, 0.f};
-      uint32_t ah[2][4], al[2][4], bh[2][2], bl[2][2];
+    for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-      for (int kt = 0; kt < 2; ++kt) {
-        if (!LT) {
-          ah[kt][0] = Lm.hi[mt][2 * kt][0]; ah[kt][1] = Lm.hi[mt][2 * kt][1];
-          ah[kt][2] = Lm.hi[mt][2 * kt + 1][0]; ah[kt][3] = Lm.hi[mt][2 * kt + 1][1];
-          al[kt][0] = Lm.lo[mt][2 * kt][0]; al[kt][1] = Lm.lo[mt][2 * kt][1];
-          al[kt][2] = Lm.lo[mt][2 * kt + 1][0]; al[kt][3] = Lm.lo[mt][2 * kt + 1][1];
-        } else {
-          ah[kt][0] = Lm.hi[kt][2 * mt][0]; ah[kt][1] = Lm.hi[kt][2 * mt + 1][0];
-          ah[kt][2] = Lm.hi[kt][2 * mt][1]; ah[kt][3] = Lm.hi[kt][2 * mt + 1][1];
-          al[kt][0] = Lm.lo[kt][2 * mt][0]; al[kt][1] = Lm.lo[kt][2 * mt + 1][0];
-          al[kt][2] = Lm.lo[kt][2 * mt][1]; al[kt][3] = Lm.lo[kt][2 * mt + 1][1];
-        }
-        if (!RT) {
-          bh[kt][0] = Rm.hi[kt][nt][0]; bh[kt][1] = Rm.hi[kt][nt][1];
-          bl[kt][0] = Rm.lo[kt][nt][0]; bl[kt][1] = Rm.lo[kt][nt][1];
-        } else {
-          bh[kt][0] = Rm.hi[nt >> 1][2 * kt][nt & 1]; bh[kt][1] = Rm.hi[nt >> 1][2 * kt + 1][nt & 1];
-          bl[kt][0] = Rm.lo[nt >> 1][2 * kt][nt & 1]; bl[kt][1] = Rm.lo[nt >> 1][2 * kt + 1][nt & 1];
-        }
+      for (int q = 0; q < 4; ++q) Z.c[mt][nt][q] = 0.f;
+  // Term-major order: the eight output tiles take the same term one after the other, so that consecutive MMAs are independent
+  // (a tile's six accumulations are a dependent chain of ~21 cycles each).  Small terms first, the hi * hi terms last: the
+  // tensor core truncates every accumulation.
+#pragma unroll
+  for (int term = 0; term < 6; ++term) {
+    const int kt = term < 4 ? (term >> 1) : term - 4;       // 0 0 1 1 | 0 1
+    const bool a_lo = term < 4 && (term & 1) == 0;           // lo*hi, hi*lo, lo*hi, hi*lo | hi*hi, hi*hi
+    const bool b_lo = term < 4 && (term & 1) == 1;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      uint32_t a[4];
+      if (!LT) {
+        a[0] = a_lo ? Lm.lo[mt][2 * kt][0] : Lm.hi[mt][2 * kt][0];
+        a[1] = a_lo ? Lm.lo[mt][2 * kt][1] : Lm.hi[mt][2 * kt][1];
+        a[2] = a_lo ? Lm.lo[mt][2 * kt + 1][0] : Lm.hi[mt][2 * kt + 1][0];
+        a[3] = a_lo ? Lm.lo[mt][2 * kt + 1][1] : Lm.hi[mt][2 * kt + 1][1];
+      } else {
+        a[0] = a_lo ? Lm.lo[kt][2 * mt][0] : Lm.hi[kt][2 * mt][0];
+        a[1] = a_lo ? Lm.lo[kt][2 * mt + 1][0] : Lm.hi[kt][2 * mt + 1][0];
+        a[2] = a_lo ? Lm.lo[kt][2 * mt][1] : Lm.hi[kt][2 * mt][1];
+        a[3] = a_lo ? Lm.lo[kt][2 * mt + 1][1] : Lm.hi[kt][2 * mt + 1][1];
       }
-      // small terms first, the hi * hi terms last: the tensor core truncates every accumulation
-      mma16816(c, al[0], bh[0]);
-      mma16816(c, ah[0], bl[0]);
-      mma16816(c, al[1], bh[1]);
-      mma16816(c, ah[1], bl[1]);
-      mma16816(c, ah[0], bh[0]);
-      mma16816(c, ah[1], bh[1]);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) Z.c[mt][nt][q] = c[q];
+      for (int nt = 0; nt < 4; ++nt) {
+        uint32_t bb[2];
+        if (!RT) {
+          bb[0] = b_lo ? Rm.lo[kt][nt][0] : Rm.hi[kt][nt][0];
+          bb[1] = b_lo ? Rm.lo[kt][nt][1] : Rm.hi[kt][nt][1];
+        } else {
+          bb[0] = b_lo ? Rm.lo[nt >> 1][2 * kt][nt & 1] : Rm.hi[nt >> 1][2 * kt][nt & 1];
+          bb[1] = b_lo ? Rm.lo[nt >> 1][2 * kt + 1][nt & 1] : Rm.hi[nt >> 1][2 * kt + 1][nt & 1];
+        }
+        mma16816(Z.c[mt][nt], a, bb);
+      }
     }
+  }
 }
 
 // Z += X with the exponents aligned (exact powers of two); empty Z (ex == INT_MIN) takes X
@@ -209,8 +214,8 @@ __device__ __forceinline__ void add_aligned(Mat &Z, const Mat &X) {
 // ---------------------------------------------------------------------------------------------------------------
 // VJP helpers + kernel.  Window-major: a CTA owns `per_cta` samples and walks the windows backwards; inside a window its W warps take the
 // samples W at a time.  For one sample and window (E = stashed entry environment, dE' = adjoint of the exit environment):
-//     recompute  Q_k = M_1 .. M_k (prefixes to scratch),  P = Q_K,  T^o = M^o P,  U^o = E T^o
-//     dT^o = 2 U^o dE'      dE += T^o dE' T^o^T      dM^o = dT^o P^T      dP += M^o^T dT^o
+//     recompute  Q_k = M_1 .. M_k (prefixes to scratch),  P = Q_K,  T^o = M^o P,  X^o = T^o dE'
+//     dT^o = 2 E X^o (= 2 U^o dE')      dE += X^o T^o^T      dM^o = dT^o P^T      dP += M^o^T dT^o
 //     G = dP;  for k = K .. 1:  dM_k = Q_{k-1}^T G,  G <- G M_k^T
 // The per-site gradients dA[a, r, s(, o)] = sum_b phi_s[b] dM[b][a, r] are reduced over the CTA's samples in shared memory
 // (every warp stages its phi-weighted fragment, the warps then sum disjoint slices of the W slots into the window's
@@ -398,7 +403,7 @@ __device__ __forceinline__ void window_phi(const RrArgs &A, long long b, int w0,
   p0 = p1 = 0.f;
   if (w0 + lane < w1) {
     float ph[2];
-    embed_site_d<2>(A.emb, A.x[(size_t)b * A.L + w0 + lane], ph);
+    embed_site_d<2>(A.emb, A.x + ((size_t)b * A.L + w0 + lane) * A.emb.n_in, ph);
     p0 = ph[0];
     p1 = ph[1];
   }
@@ -407,20 +412,23 @@ __device__ __forceinline__ void window_phi(const RrArgs &A, long long b, int w0,
 // Request j of window w.  Forward: chain sites k = 1 .. K (k = 1 in P form: it starts the product as a left operand; the rest
 // in Q form: right operands), then the output site's DO units in P form.  VJP: the same, then for k = K .. 2 the P form of
 // site k (G M_k^T), preceded at k = 2 by the Q form of site 1 (Q_1 = M_1).
+// (No integer division on this path: every thread evaluates it once per image.  Units of window w start at w * (S - 1 + DO):
+//  the DO output units first, then the chain sites.)
+__device__ __forceinline__ int win_K(const RrArgs &A, int w) { return min(A.S, A.L - w * A.S) - 1; }
 __device__ __forceinline__ int nreq_of(const RrArgs &A, int w, bool bwd) {
-  const int w0 = w * A.S, K = min(w0 + A.S, A.L) - w0 - 1;
+  const int K = win_K(A, w);
   return K + A.DO + (bwd ? (K > 1 ? K : 0) : 0);
 }
 __device__ __forceinline__ Request request_of(const RrArgs &A, int w, int j) {
-  const int w0 = w * A.S, K = min(w0 + A.S, A.L) - w0 - 1;
+  const int K = win_K(A, w), u0 = w * (A.S - 1 + A.DO), uc = u0 + A.DO - 1;  // chain site k is unit uc + k
   Request rq;
-  if (j < K) { rq.unit = unit_of(w0 + j + 1, 0, A.S, A.DO); rq.form = j == 0 ? 0 : 1; return rq; }
+  if (j < K) { rq.unit = uc + j + 1; rq.form = j == 0 ? 0 : 1; return rq; }
   j -= K;
-  if (j < A.DO) { rq.unit = unit_of(w0, j, A.S, A.DO); rq.form = 0; return rq; }
+  if (j < A.DO) { rq.unit = u0 + j; rq.form = 0; return rq; }
   j -= A.DO;  // VJP tail: P(K), P(K-1), ..., P(3), Q(1), P(2)
-  if (j < K - 2) { rq.unit = unit_of(w0 + K - j, 0, A.S, A.DO); rq.form = 0; return rq; }
-  if (j == K - 2) { rq.unit = unit_of(w0 + 1, 0, A.S, A.DO); rq.form = 1; return rq; }
-  rq.unit = unit_of(w0 + 2, 0, A.S, A.DO);
+  if (j < K - 2) { rq.unit = uc + K - j; rq.form = 0; return rq; }
+  if (j == K - 2) { rq.unit = uc + 1; rq.form = 1; return rq; }
+  rq.unit = uc + 2;
   rq.form = 0;
   return rq;
 }
@@ -440,7 +448,7 @@ __device__ __forceinline__ void cursor_next(const RrArgs &A, Cursor &c, bool bwd
   else { if (++c.w >= A.nwin) c.done = true; }
 }
 
-constexpr int kFwdWarps = 8;
+constexpr int kFwdWarps = 16;
 
 template <int DO> __global__ void __launch_bounds__(kFwdWarps * 32, 1) smpo_rr_fwd_kernel(RrArgs A) {
   __shared__ __align__(16) float4 ring[kRingStages * kImgFloat4];
@@ -473,6 +481,7 @@ template <int DO> __global__ void __launch_bounds__(kFwdWarps * 32, 1) smpo_rr_f
   E.ex = 0;
   for (int w = 0; w < A.nwin; ++w) {
     const int w0 = w * A.S, w1 = min(w0 + A.S, A.L), K = w1 - w0 - 1;
+    const int uc = w * (A.S - 1 + A.DO) + A.DO - 1;  // chain site k of this window is weight unit uc + k
     if (A.stash && on) {
       store_mat(A.Estash + ((size_t)w * A.B + b) * 1024, E, lane);
       if (lane == 0) A.Eexp[(size_t)w * A.B + b] = E.ex;
@@ -482,11 +491,11 @@ template <int DO> __global__ void __launch_bounds__(kFwdWarps * 32, 1) smpo_rr_f
     Img qP;
     if (K > 0) {
       Img a;
-      form_img(next_image(), A.Wsh[unit_of(w0 + 1, 0, A.S, A.DO)], __shfl_sync(0xffffffffu, p0, 1), __shfl_sync(0xffffffffu, p1, 1), a,
+      form_img(next_image(), A.Wsh[uc + 1], __shfl_sync(0xffffffffu, p0, 1), __shfl_sync(0xffffffffu, p1, 1), a,
                lane);
       for (int k = 2; k <= K; ++k) {
         Img q;
-        form_img(next_image(), A.Wsh[unit_of(w0 + k, 0, A.S, A.DO)], __shfl_sync(0xffffffffu, p0, k),
+        form_img(next_image(), A.Wsh[uc + k], __shfl_sync(0xffffffffu, p0, k),
                  __shfl_sync(0xffffffffu, p1, k), q, lane);
         Mat Pm;
         product<false, false>(a, q, Pm);
@@ -502,7 +511,7 @@ template <int DO> __global__ void __launch_bounds__(kFwdWarps * 32, 1) smpo_rr_f
 #pragma unroll 1
     for (int o = 0; o < A.DO; ++o) {
       Img pT, qT;
-      form_img(next_image(), A.Wsh[unit_of(w0, o, A.S, A.DO)], q0, q1, pT, lane);
+      form_img(next_image(), A.Wsh[uc + 1 - A.DO + o], q0, q1, pT, lane);
       if (K > 0) {
         Mat T;
         product<false, false>(pT, qP, T);
@@ -564,6 +573,7 @@ template <int DO> __global__ void __launch_bounds__(kBwdWarps * 32, 1) smpo_rr_b
   __syncthreads();
   for (int w = A.nwin - 1; w >= 0; --w) {
     const int w0 = w * A.S, w1 = min(w0 + A.S, A.L), K = w1 - w0 - 1;
+    const int uc = w * (A.S - 1 + A.DO) + A.DO - 1;  // chain site k of this window is weight unit uc + k
     for (int r = 0; r < rounds; ++r) {
       const long long b = base + (long long)r * kBwdWarps + warp;
       const bool on = r * kBwdWarps + warp < A.per_cta && b < A.B;
@@ -594,11 +604,11 @@ template <int DO> __global__ void __launch_bounds__(kBwdWarps * 32, 1) smpo_rr_b
       // ---- recompute the chain, prefixes Q_2 .. Q_{K-1} to scratch ----
       Img pP, qP;
       if (K > 0) {
-        form_img(next_image(), A.Wsh[unit_of(w0 + 1, 0, A.S, A.DO)], __shfl_sync(0xffffffffu, p0, 1),
+        form_img(next_image(), A.Wsh[uc + 1], __shfl_sync(0xffffffffu, p0, 1),
                  __shfl_sync(0xffffffffu, p1, 1), pP, lane);
         for (int k = 2; k <= K; ++k) {
           Img q;
-          form_img(next_image(), A.Wsh[unit_of(w0 + k, 0, A.S, A.DO)], __shfl_sync(0xffffffffu, p0, k),
+          form_img(next_image(), A.Wsh[uc + k], __shfl_sync(0xffffffffu, p0, k),
                    __shfl_sync(0xffffffffu, p1, k), q, lane);
           Mat Pm;
           product<false, false>(pP, q, Pm);
@@ -621,7 +631,7 @@ template <int DO> __global__ void __launch_bounds__(kBwdWarps * 32, 1) smpo_rr_b
 #pragma unroll 1
       for (int o = 0; o < A.DO; ++o) {
         Img pM, pT;
-        form_img(next_image(), A.Wsh[unit_of(w0, o, A.S, A.DO)], q0, q1, pM, lane);
+        form_img(next_image(), A.Wsh[uc + 1 - A.DO + o], q0, q1, pM, lane);
         if (K > 0) {
           Mat T;
           product<false, false>(pM, qP, T);
@@ -629,19 +639,14 @@ template <int DO> __global__ void __launch_bounds__(kBwdWarps * 32, 1) smpo_rr_b
         } else {
           pT = pM;
         }
-        Img qT;
-        transpose_blocks(pT, qT);
-        Mat U;
-        product<false, false>(pE, qT, U);
-        Img pU;
-        split(U, pU);
-        Mat dT;
-        product<false, true>(pU, pdE, dT);  // U dE'   (dE' symmetric: the right operand dE'^T from P(dE'))
-        dT.ex += 1;                         // x 2
         Mat X;
-        product<false, true>(pT, pdE, X);   // T dE'
-        Img pX;
+        product<false, true>(pT, pdE, X);   // X = T dE'   (dE' symmetric: the right operand dE'^T from P(dE'))
+        Img pX, qX;
         split(X, pX);
+        transpose_blocks(pX, qX);
+        Mat dT;
+        product<false, false>(pE, qX, dT);  // dT = 2 U dE' = 2 E T dE' = 2 E X   (U itself is not needed in the VJP)
+        dT.ex += 1;
         Mat dEc;
         product<false, true>(pX, pT, dEc);  // (T dE') T^T
         add_aligned(dE, dEc);
@@ -674,13 +679,13 @@ template <int DO> __global__ void __launch_bounds__(kBwdWarps * 32, 1) smpo_rr_b
         transpose_blocks(pG, qG);
         if (k - 1 >= 2) load_img(Qs + (size_t)(k - 1) * 1056, qQ, lane);
         else  // Q_1 = M_1
-          form_img(next_image(), A.Wsh[unit_of(w0 + 1, 0, A.S, A.DO)], __shfl_sync(0xffffffffu, p0, 1),
+          form_img(next_image(), A.Wsh[uc + 1], __shfl_sync(0xffffffffu, p0, 1),
                    __shfl_sync(0xffffffffu, p1, 1), qQ, lane);
         Mat dMk;
         product<true, false>(qQ, qG, dMk);  // Q_{k-1}^T G
         reduce_grad(stage, acc_k, dMk, on, pk0, pk1, warp, lane);
         Img pMk;
-        form_img(next_image(), A.Wsh[unit_of(w0 + k, 0, A.S, A.DO)], pk0, pk1, pMk, lane);
+        form_img(next_image(), A.Wsh[uc + k], pk0, pk1, pMk, lane);
         product<false, true>(pG, pMk, G);  // G M_k^T
       }
       if (on && w > 0) {

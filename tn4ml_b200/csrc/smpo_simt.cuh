@@ -353,7 +353,7 @@ __device__ __forceinline__ void window_phi(const SmpoArgs<T> &A, long long b0, i
     long long b = b0 + sl;
     T ph[kMaxPhys];
     if (b < A.B) {
-      embed_site(A.emb, A.x[(size_t)b * A.L + w0 + k], ph);
+      embed_site(A.emb, A.x + ((size_t)b * A.L + w0 + k) * A.emb.n_in, ph);
     } else {
       for (int s = 0; s < A.D; ++s) ph[s] = T(0);
     }
@@ -640,10 +640,7 @@ static void fill_smpo_args(const tnb_problem *p, const SmpoPlan &P, long long B,
   char *w = (char *)ws;
   A.L = p->L; A.chi = p->chi; A.chip = P.chip; A.ld = P.ld; A.D = p->d; A.DO = p->n_out; A.S = p->spacing;
   A.nwin = P.nwin; A.head = p->head; A.B = B;
-  A.emb.kind = p->emb.kind; A.emb.k = p->emb.k; A.emb.p = p->emb.p; A.emb.degree = p->emb.degree;
-  A.emb.include_bias = p->emb.include_bias; A.emb.n_centers = p->emb.n_centers; A.emb.d = p->d;
-  A.emb.gamma = (T)p->emb.gamma;
-  for (int i = 0; i < kMaxPhys; ++i) A.emb.centers[i] = (T)p->emb.centers[i];
+  fill_emb<T>(p->emb, A.emb, p->d);
   A.x = (const T *)x; A.params = (const T *)params;
   A.Estash = (T *)(w + P.off_E); A.dexp = (int *)(w + P.off_dexp); A.esum = (int *)(w + P.off_esum);
   A.nm = (T *)(w + P.off_nm); A.Qscr = (T *)(w + P.off_Q);
