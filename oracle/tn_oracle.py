@@ -38,13 +38,15 @@ import torch
 class EmbSpec:
     """Static description of one feature map (the four on the hot path)."""
 
-    kind: str  # "trig" | "fourier" | "poly" | "rbf"
+    kind: str  # "trig" | "fourier" | "poly" | "rbf" | "lincomp" | "legendre" | "laguerre" | "hermite" | "arrays"
     k: int = 1  # trig: number of frequencies (dim = 2k)
-    p: int = 2  # fourier: dim = p
-    degree: int = 1  # poly
-    include_bias: bool = False  # poly
+    p: int = 2  # fourier: dim = p; lincomp: 2 or 3
+    degree: int = 1  # poly, legendre, laguerre, hermite
+    include_bias: bool = False  # poly; arrays (add_bias)
     gamma: float = 1.0  # rbf
     centers: tuple = field(default_factory=tuple)  # rbf
+    n: int = 1  # poly / arrays: input values per site (Embedding.input_dim)
+    cross: bool = False  # poly: include_cross_terms
 
     @property
     def dim(self) -> int:
@@ -52,17 +54,70 @@ class EmbSpec:
             return 2 * self.k  # embeddings.py:317-320
         if self.kind == "fourier":
             return self.p  # embeddings.py:385-387 (returns p, not 2p)
-        if self.kind == "poly":
-            return self.degree + (1 if self.include_bias else 0)  # :655-673, n=1
+        if self.kind == "poly":  # embeddings.py:655-673
+            total = 1 if self.include_bias else 0
+            for dg in range(1, self.degree + 1):
+                total += math.comb(self.n + dg - 1, dg) if self.cross else self.n
+            return total
         if self.kind == "rbf":
             return len(self.centers)  # embeddings.py:581-583
+        if self.kind == "lincomp":
+            return self.p  # embeddings.py:458-461
+        if self.kind in ("legendre", "laguerre", "hermite"):
+            return self.degree + 1  # embeddings.py:743-746, 794-797, 846-849
+        if self.kind == "arrays":
+            return self.n + (1 if self.include_bias else 0)  # embeddings.py:913-928
         raise ValueError(self.kind)
 
 
 def feature_map(x: torch.Tensor, spec: EmbSpec) -> torch.Tensor:
-    """phi(x) for every scalar in ``x`` -> [..., d], *before* embed()'s normaliser."""
-    x = x.unsqueeze(-1)
+    """phi(x) for every scalar in ``x`` (every vector x[..., :n] for the maps with input_dim n > 1) -> [..., d], *before*
+    embed()'s normaliser."""
     dt = x.dtype
+    if spec.kind == "arrays":
+        # embeddings.py:913-928 : the input vector itself, behind a constant 1 if add_bias
+        return torch.cat([torch.ones_like(x[..., :1]), x], dim=-1) if spec.include_bias else x.clone()
+    if spec.kind == "poly" and spec.n > 1:
+        # embeddings.py:693-717 : degree by degree, itertools.combinations_with_replacement over the inputs; cross terms
+        # (more than one distinct input) are skipped unless include_cross_terms
+        import itertools
+        feats = [torch.ones_like(x[..., 0])] if spec.include_bias else []
+        for dg in range(1, spec.degree + 1):
+            for comb in itertools.combinations_with_replacement(range(spec.n), dg):
+                if len(set(comb)) > 1 and not spec.cross:
+                    continue
+                feats.append(torch.prod(x[..., list(comb)], dim=-1))
+        return torch.stack(feats, dim=-1)
+    if spec.n > 1 and spec.kind == "poly":
+        raise ValueError("unreachable")
+    if spec.kind in ("legendre", "laguerre", "hermite"):
+        # tn4ml/scipy/special.py:6-28, 57-79, 108-130 (three-term recurrences), embeddings.py:754-768, 805-820, 857-869
+        vals = [torch.ones_like(x)]
+        if spec.kind == "legendre":
+            if spec.degree >= 1:
+                vals.append(x.clone())
+            for i in range(1, spec.degree):
+                vals.append(((2 * i + 1) * x * vals[i] - i * vals[i - 1]) / (i + 1))
+            w = torch.ones_like(x)
+        elif spec.kind == "laguerre":
+            if spec.degree >= 1:
+                vals.append(1.0 - x)
+            for i in range(2, spec.degree + 1):
+                vals.append(((2 * i - 1 - x) * vals[i - 1] - (i - 1) * vals[i - 2]) / i)
+            w = torch.exp(-x / 2)
+        else:
+            if spec.degree >= 1:
+                vals.append(2.0 * x)
+            for i in range(2, spec.degree + 1):
+                vals.append(2 * x * vals[i - 1] - 2 * (i - 1) * vals[i - 2])
+            w = torch.exp(-0.5 * x**2)
+        return torch.stack([w * v for v in vals], dim=-1)
+    if spec.kind == "lincomp":
+        # embeddings.py:478-484 : [x, 1 - x] or [1, x, 1 - x], / ||.||
+        comps = [x, 1.0 - x] if spec.p == 2 else [torch.ones_like(x), x, 1.0 - x]
+        v = torch.stack(comps, dim=-1)
+        return v / torch.linalg.norm(v, dim=-1, keepdim=True)
+    x = x.unsqueeze(-1)
     if spec.kind == "trig":
         # embeddings.py:340-351 : 1/sqrt(k) * [cos(pi x/2^i) i=1..k, sin(pi x/2^i) i=1..k]
         i = torch.arange(1, spec.k + 1, dtype=dt)

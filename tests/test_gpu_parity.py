@@ -35,7 +35,15 @@ def _emb(spec):
     if spec.kind == "fourier":
         return T.FourierEmbedding(p=spec.p)
     if spec.kind == "poly":
-        return T.PolynomialEmbedding(degree=spec.degree, n=1, include_bias=spec.include_bias)
+        return T.PolynomialEmbedding(degree=spec.degree, n=spec.n, include_bias=spec.include_bias,
+                                     include_cross_terms=spec.cross)
+    if spec.kind == "lincomp":
+        return T.LinearComplementEmbedding(p=spec.p)
+    if spec.kind in ("legendre", "laguerre", "hermite"):
+        return {"legendre": T.LegendreEmbedding, "laguerre": T.LaguerreEmbedding,
+                "hermite": T.HermiteEmbedding}[spec.kind](degree=spec.degree)
+    if spec.kind == "arrays":
+        return T.JaxArraysEmbedding(dim=spec.dim, add_bias=spec.include_bias, input_dim=spec.n)
     return T.GaussianRBFEmbedding(centers=np.array(spec.centers), gamma=spec.gamma)
 
 
@@ -187,6 +195,72 @@ def test_embedding_call_matches_oracle():
                  O.EmbSpec("rbf", gamma=0.5, centers=(0.1, 0.9))]:
         phi = _emb(spec)(x.numpy())
         assert torch.allclose(phi.cpu(), O.feature_map(x, spec), atol=1e-12)
+
+
+MORE_MAPS = [O.EmbSpec("lincomp", p=2), O.EmbSpec("lincomp", p=3), O.EmbSpec("legendre", degree=3), O.EmbSpec("laguerre", degree=2),
+             O.EmbSpec("hermite", degree=4), O.EmbSpec("poly", degree=2, n=3, include_bias=True),
+             O.EmbSpec("poly", degree=2, n=3, include_bias=True, cross=True), O.EmbSpec("poly", degree=3, n=2, cross=True),
+             O.EmbSpec("arrays", n=3), O.EmbSpec("arrays", n=3, include_bias=True)]
+MORE_IDS = ["lincomp2", "lincomp3", "legendre3", "laguerre2", "hermite4", "poly_n3", "poly_n3_cross", "poly_n2_d3_cross", "arrays3",
+            "arrays3_bias"]
+
+
+def _inputs_for(spec, B, L, seed):
+    """x [B, L] (scalar maps) or [B, L, n] (maps with input_dim n > 1), in U(0, 1]."""
+    rng = np.random.default_rng(seed)
+    shape = (B, L) if spec.n == 1 else (B, L, spec.n)
+    return torch.tensor(1.0 - rng.random(shape))
+
+
+@pytest.mark.parametrize("spec", MORE_MAPS, ids=MORE_IDS)
+def test_more_embeddings_call_matches_oracle(spec):
+    """Embedding.__call__ of the remaining feature maps (embeddings.py:426-484, 605-717 with n > 1, 720-869, 872-928)."""
+    x = _inputs_for(spec, 57, 1, 3)[:, 0]
+    if spec.kind in ("legendre", "hermite"):
+        x = 2.0 * x - 1.0
+    phi = _emb(spec)(x.numpy())
+    ref = O.feature_map(x, spec)
+    assert phi.shape == ref.shape and phi.shape[-1] == spec.dim == _emb(spec).dim
+    assert torch.allclose(phi.cpu(), ref, atol=1e-12)
+    phi32 = _emb(spec)(x.float())
+    assert torch.allclose(phi32.double().cpu(), ref, atol=2e-5, rtol=2e-5)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("spec", MORE_MAPS, ids=MORE_IDS)
+def test_more_embeddings_mps_parity(spec, dtype):
+    """value_and_grad of a plain MPS (NegLogLikelihood) and of a classifier over every remaining feature map, fused in-kernel
+    like the four headline maps (the normaliser of embed() matters for all but lincomp)."""
+    import tn4ml_b200 as T
+    L, chi, B, C = 9, 12, 37, 3
+    d = spec.dim
+    x = _inputs_for(spec, B, L, 21)
+    arrays = O.make_mps_arrays(L, chi, d, std=0.05, seed=4, squeeze_ends=True, identity_all=True)
+    _check(T.MatrixProductState(arrays, dtype=dtype, device="cuda:0"), O.Problem("mps", spec, "nll"), _heads()["nll"], x, arrays,
+           None, dtype)
+    arrays = O.make_mps_arrays(L, chi, d, class_site=4, C=C, std=0.2, seed=3)
+    t = O.make_labels(B, C)
+    _check(T.TensorNetwork(arrays, dtype=dtype, device="cuda:0"), O.Problem("mps", spec, "softmax_xent"),
+           _heads()["softmax_xent"], x, arrays, t, dtype)
+
+
+@pytest.mark.parametrize("spec", [O.EmbSpec("lincomp", p=2), O.EmbSpec("legendre", degree=1), O.EmbSpec("arrays", n=2)],
+                         ids=["lincomp2", "legendre1", "arrays2"])
+def test_more_embeddings_tensor_and_smpo_families(spec):
+    """The same maps through the tcgen05 chain kernels (float32, chi = 64) and the SMPO kernels (register-resident family at
+    chi = 32, d = 2)."""
+    import tn4ml_b200 as T
+    L, chi, B, C = 10, 64, 200, 4
+    x = _inputs_for(spec, B, L, 5)
+    arrays = [a.float() for a in O.make_mps_arrays(L, chi, 2, class_site=4, C=C, std=0.05, seed=3)]
+    t = O.make_labels(B, C)
+    model = T.TensorNetwork(arrays, dtype=torch.float32, device="cuda:0")
+    _check(model, O.Problem("mps", spec, "softmax_xent"), _heads()["softmax_xent"], x, arrays, t, torch.float32, precision=1)
+    arrays = O.make_smpo_arrays(24, 32, 2, 2, 8, std=0.05, seed=8)
+    xs = _inputs_for(spec, 11, 24, 9)
+    for dtype in (torch.float64, torch.float32):
+        model = T.SpacedMatrixProductOperator(arrays, spacing=8, dtype=dtype, device="cuda:0")
+        _check(model, O.Problem("smpo", spec, "logquad", spacing=8), _heads()["logquad"], xs, arrays, None, dtype)
 
 
 @pytest.mark.parametrize("case", [

@@ -50,6 +50,38 @@ def test_embed_normaliser_matches_the_reference_source(branch, name):
     assert np.prod(signs) == 1.0  # the signs the QRs move around cancel in the product state
 
 
+MORE = {
+    "lincomp_p2": O.EmbSpec("lincomp", p=2), "lincomp_p3": O.EmbSpec("lincomp", p=3),
+    "legendre_d3": O.EmbSpec("legendre", degree=3), "legendre_d0": O.EmbSpec("legendre", degree=0),
+    "laguerre_d3": O.EmbSpec("laguerre", degree=3), "hermite_d4": O.EmbSpec("hermite", degree=4),
+    "hermite_d1": O.EmbSpec("hermite", degree=1),
+    "poly_n3_d2": O.EmbSpec("poly", degree=2, n=3), "poly_n3_d2_bias": O.EmbSpec("poly", degree=2, n=3, include_bias=True),
+    "poly_n3_d2_cross": O.EmbSpec("poly", degree=2, n=3, include_bias=True, cross=True),
+    "poly_n2_d3_cross": O.EmbSpec("poly", degree=3, n=2, cross=True),
+    "arrays_n3": O.EmbSpec("arrays", n=3), "arrays_n3_bias": O.EmbSpec("arrays", n=3, include_bias=True),
+}
+
+
+@pytest.mark.parametrize("name", sorted(MORE))
+def test_remaining_feature_maps_match_the_reference_source(name):
+    """LinearComplement / Legendre / Laguerre / Hermite (over the reference's tn4ml/scipy/special.py recurrences) / Polynomial
+    with n > 1 and cross terms / JaxArrays, executed from the reference's files (tools/make_reference_golden.py)."""
+    z = np.load(os.path.join(G, "reference_embeddings_more.npz"))
+    spec = MORE[name]
+    x = torch.tensor(z["xv"][:, :spec.n]) if spec.n > 1 else torch.tensor(z[f"x_{name}"])
+    phi = O.feature_map(x, spec).numpy()
+    assert phi.shape[1] == int(z[f"dim_{name}"]) == spec.dim
+    assert np.allclose(phi, z[f"phi_{name}"], rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("name,spec", [("hermite_d2", O.EmbSpec("hermite", degree=2)), ("arrays_n3", O.EmbSpec("arrays", n=3))])
+def test_plain_mps_nll_over_remaining_maps_matches_the_reference_source(name, spec):
+    z = np.load(os.path.join(G, "reference_embeddings_more.npz"))
+    arrays = [torch.tensor(z[f"nll_{name}_site{i}"]) for i in range(6)]
+    per = O.per_sample_loss(O.Problem("mps", spec, "nll"), torch.tensor(z[f"nll_{name}_x"]), arrays).numpy()
+    assert np.allclose(per, z[f"nll_{name}"], rtol=1e-12)
+
+
 def _sites(z):
     n = len([k for k in z.files if k.startswith("site")])
     return [torch.tensor(z[f"site{i}"]) for i in range(n)]

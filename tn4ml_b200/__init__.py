@@ -4,7 +4,8 @@ states through MPS / MPO / SMPO chains, forward and backward) on hand-written sm
 Public names mirror ``tn4ml`` (reference: tn4ml/__init__.py)."""
 from . import embeddings, initializers, metrics, models, optim, util  # noqa: F401
 from .embeddings import (  # noqa: F401
-    Embedding, FourierEmbedding, GaussianRBFEmbedding, PolynomialEmbedding, TrigonometricEmbedding)
+    Embedding, FourierEmbedding, GaussianRBFEmbedding, HermiteEmbedding, JaxArraysEmbedding, LaguerreEmbedding,
+    LegendreEmbedding, LinearComplementEmbedding, PolynomialEmbedding, TrigonometricEmbedding)
 from .models import (  # noqa: F401
     Model, MatrixProductOperator, MatrixProductState, MPO_initialize, MPS_initialize, SMPO_initialize,
     SpacedMatrixProductOperator, TensorNetwork, load_model)

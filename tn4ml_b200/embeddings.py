@@ -43,10 +43,17 @@ class Embedding(abc.ABC):
         if xt.dtype not in (torch.float32, torch.float64):
             xt = xt.to(torch.float64 if np.dtype(self.dtype) == np.float64 else torch.float32)
         xt = xt.cuda().contiguous()
-        out = torch.empty(xt.shape + (self.dim,), dtype=xt.dtype, device=xt.device)
+        n_in = self.input_dim or 1
+        if n_in > 1:  # one input is a vector of input_dim values (the last axis)
+            if xt.ndim < 1 or xt.shape[-1] != n_in:
+                raise ValueError(f"expected inputs with a last axis of {n_in} values, got shape {tuple(xt.shape)}")
+            lead = xt.shape[:-1]
+        else:
+            lead = xt.shape
+        out = torch.empty(tuple(lead) + (self.dim,), dtype=xt.dtype, device=xt.device)
         spec = self._spec()
         _lib.check(_lib.lib().tnb_embed(C.byref(spec), _lib.F64 if xt.dtype == torch.float64 else _lib.F32,
-                                        xt.numel(), xt.data_ptr(), out.data_ptr(),
+                                        xt.numel() // n_in, xt.data_ptr(), out.data_ptr(),
                                         torch.cuda.current_stream().cuda_stream))
         return out
 
@@ -143,12 +150,100 @@ class PolynomialEmbedding(Embedding):
         return self.n
 
     def _spec(self):
-        if self.n != 1:
-            raise NotImplementedError("the fused kernels take one scalar feature per site (n == 1)")
-        if self.dim > _lib.TNB_MAX_PHYS:
+        if self.dim > _lib.TNB_MAX_PHYS or self.n > _lib.TNB_MAX_PHYS:
             raise ValueError(f"embedding dimension {self.dim} exceeds {_lib.TNB_MAX_PHYS}")
+        if self.include_cross_terms and self.n > 1 and self.degree > 8:
+            raise ValueError("cross terms are built for degree <= 8")
         s = _lib.TnbEmbedding()
         s.kind, s.degree, s.include_bias = _lib.EMB_POLY, self.degree, int(bool(self.include_bias))
+        s.n_in, s.cross = int(self.n), int(bool(self.include_cross_terms))
+        return s
+
+
+class LinearComplementEmbedding(Embedding):
+    """[x, 1 - x] (p = 2) or [1, x, 1 - x] (p = 3), divided by its 2-norm  (embeddings.py:426-484)."""
+
+    def __init__(self, p: int = 2, **kwargs):
+        if p not in [2, 3]:
+            raise ValueError("p must be 2 or 3")
+        self.p = p
+        super().__init__(**kwargs)
+
+    @property
+    def dim(self) -> int:
+        return self.p
+
+    def _spec(self):
+        s = _lib.TnbEmbedding()
+        s.kind, s.p = _lib.EMB_LINCOMP, self.p
+        return s
+
+
+class _OrthogonalPolynomialEmbedding(Embedding):
+    """degree + 1 features from a three-term recurrence (tn4ml/scipy/special.py), evaluated in-kernel."""
+    _kind = -1
+
+    def __init__(self, degree: int = 2, **kwargs):
+        self.degree = degree
+        super().__init__(**kwargs)
+
+    @property
+    def dim(self) -> int:
+        return self.degree + 1
+
+    def _spec(self):
+        if self.degree < 0 or self.dim > _lib.TNB_MAX_PHYS:
+            raise ValueError(f"embedding dimension {self.dim} must be in [1, {_lib.TNB_MAX_PHYS}]")
+        s = _lib.TnbEmbedding()
+        s.kind, s.degree = self._kind, self.degree
+        return s
+
+
+class LegendreEmbedding(_OrthogonalPolynomialEmbedding):
+    """[P_0(x) .. P_degree(x)], x in [-1, 1]  (embeddings.py:720-768)."""
+    _kind = _lib.EMB_LEGENDRE
+
+
+class LaguerreEmbedding(_OrthogonalPolynomialEmbedding):
+    """exp(-x/2) [L_0(x) .. L_degree(x)], x >= 0  (embeddings.py:771-820)."""
+    _kind = _lib.EMB_LAGUERRE
+
+
+class HermiteEmbedding(_OrthogonalPolynomialEmbedding):
+    """exp(-x^2/2) [H_0(x) .. H_degree(x)] (physicists' H)  (embeddings.py:823-869)."""
+    _kind = _lib.EMB_HERMITE
+
+
+class JaxArraysEmbedding(Embedding):
+    """Pre-embedded inputs: site i of a sample is the vector x[i, :input_dim] itself, optionally behind a constant 1
+    (embeddings.py:872-928).  The kernels read ``x [B, L, input_dim]``; named after the reference class it mirrors (the arrays
+    here are torch / numpy)."""
+
+    def __init__(self, dim: int | None = None, add_bias: bool = False, input_dim: int | None = None, **kwargs):
+        super().__init__(**kwargs)
+        self._dim = dim
+        self.add_bias = add_bias
+        self._input_dim = input_dim
+
+    @property
+    def dim(self) -> int:
+        return self._dim
+
+    @property
+    def input_dim(self) -> int:
+        return self._input_dim
+
+    def _spec(self):
+        n_in = self._input_dim if self._input_dim is not None else (self._dim - int(bool(self.add_bias)) if self._dim else None)
+        if n_in is None or n_in < 1:
+            raise ValueError("JaxArraysEmbedding needs dim or input_dim")
+        d = n_in + int(bool(self.add_bias))
+        if self._dim is not None and self._dim != d:
+            raise ValueError(f"dim ({self._dim}) must equal input_dim ({n_in}) + add_bias")
+        if d > _lib.TNB_MAX_PHYS:
+            raise ValueError(f"embedding dimension {d} exceeds {_lib.TNB_MAX_PHYS}")
+        s = _lib.TnbEmbedding()
+        s.kind, s.n_in, s.include_bias = _lib.EMB_ARRAYS, int(n_in), int(bool(self.add_bias))
         return s
 
 

@@ -99,7 +99,10 @@ class Engine:
         if x.device != self.device or x.dtype != self.dtype:
             x = x.to(self.device, self.dtype, non_blocking=True)
         x = x.contiguous()
-        if x.ndim != 2 or x.shape[1] < self.prob.L:
+        n_in = max(1, int(self.prob.emb.n_in))  # Embedding.input_dim: values per site (pre-embedded inputs, polynomial n > 1)
+        if n_in > 1 and (x.ndim != 3 or x.shape[2] != n_in):
+            raise ValueError(f"Input data must have shape [batch, sites, {n_in}] for this embedding, got {tuple(x.shape)}")
+        if x.ndim != (3 if n_in > 1 else 2) or x.shape[1] < self.prob.L:
             raise ValueError(f"Input data must have at least {self.prob.L} elements!")  # model.py:306-307
         if targets is not None:
             targets = torch.as_tensor(targets)
@@ -124,10 +127,10 @@ class Engine:
             raise NotImplementedError("len(model) < len(data) for SMPO/MPO heads (the factor enters the head non-linearly) "
                                       "is not built")
         xe = x[:, L:].contiguous()
-        phi = torch.empty(xe.shape + (self.prob.d,), dtype=self.dtype, device=self.device)
+        phi = torch.empty(xe.shape[:2] + (self.prob.d,), dtype=self.dtype, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.tnb_embed(C.byref(self.prob.emb), _dtype_code(self.dtype), xe.numel(), xe.data_ptr(),
-                                          phi.data_ptr(), self._stream()))
+            _lib.check(self.lib.tnb_embed(C.byref(self.prob.emb), _dtype_code(self.dtype), xe.shape[0] * xe.shape[1],
+                                          xe.data_ptr(), phi.data_ptr(), self._stream()))
         # embed() normalises the product state over ALL sites of the data: the same as unit-norm sites (embeddings.py:1374-1387)
         t = phi.sum(-1) / torch.linalg.norm(phi, dim=-1)
         if self.prob.head != _lib.HEAD_NLL and bool((t.prod(dim=1) <= 0).any()):

@@ -70,6 +70,50 @@ def embeddings_file():
     return out
 
 
+def embeddings_more_file():
+    """The remaining scalar and vector-input feature maps: embeddings.py:426-484, 605-717 with n > 1,
+    720-869 (over tn4ml/scipy/special.py), 872-928; and NegLogLikelihood of a plain MPS over two of them."""
+    xs = np.linspace(0.013, 1.0, 23)
+    out = {"x": xs}
+    maps = {
+        "lincomp_p2": RE.LinearComplementEmbedding(p=2), "lincomp_p3": RE.LinearComplementEmbedding(p=3),
+        "legendre_d3": RE.LegendreEmbedding(degree=3), "laguerre_d3": RE.LaguerreEmbedding(degree=3),
+        "hermite_d4": RE.HermiteEmbedding(degree=4), "legendre_d0": RE.LegendreEmbedding(degree=0),
+        "hermite_d1": RE.HermiteEmbedding(degree=1),
+    }
+    for name, phi in maps.items():
+        xin = 2.0 * xs - 1.0 if name.startswith("legendre") else (3.0 * xs if name.startswith("laguerre") else 2.5 * xs - 1.0
+                                                                   if name.startswith("hermite") else xs)
+        out[f"x_{name}"] = xin
+        out[f"phi_{name}"] = np.stack([np.asarray(phi(np.asarray(x)), dtype=np.float64).reshape(-1) for x in xin])
+        out[f"dim_{name}"] = np.array(phi.dim)
+    rng = np.random.default_rng(9)
+    xv = 1.0 - rng.random((11, 3))
+    vmaps = {
+        "poly_n3_d2": RE.PolynomialEmbedding(degree=2, n=3), "poly_n3_d2_bias": RE.PolynomialEmbedding(degree=2, n=3, include_bias=True),
+        "poly_n3_d2_cross": RE.PolynomialEmbedding(degree=2, n=3, include_bias=True, include_cross_terms=True),
+        "poly_n2_d3_cross": RE.PolynomialEmbedding(degree=3, n=2, include_cross_terms=True),
+        "arrays_n3": RE.JaxArraysEmbedding(dim=3, input_dim=3), "arrays_n3_bias": RE.JaxArraysEmbedding(dim=4, add_bias=True, input_dim=3),
+    }
+    out["xv"] = xv
+    for name, phi in vmaps.items():
+        n = phi.input_dim
+        out[f"phi_{name}"] = np.stack([np.asarray(phi(np.asarray(x[:n])), dtype=np.float64).reshape(-1) for x in xv])
+        out[f"dim_{name}"] = np.array(phi.dim)
+    # NegLogLikelihood of a plain MPS over embed(x, phi) for a scalar map and a vector-input map
+    L, chi, B = 6, 4, 5
+    for name, phi, xin in (("hermite_d2", RE.HermiteEmbedding(degree=2), S.make_inputs(B, L, seed=31).numpy()),
+                           ("arrays_n3", vmaps["arrays_n3"], 1.0 - np.random.default_rng(32).random((B, L, 3)))):
+        arrays = [a.numpy() for a in S.make_mps_arrays(L, chi, 3, std=0.2, seed=33, squeeze_ends=True, identity_all=True)]
+        model = RMPS.MatrixProductState([np.array(a) for a in arrays])
+        out[f"nll_{name}_x"] = xin
+        out[f"nll_{name}"] = np.array([float(RM.NegLogLikelihood(model, RE.embed(xb, phi))) for xb in xin])
+        for i, a in enumerate(arrays):
+            out[f"nll_{name}_site{i}"] = a
+    np.savez_compressed(os.path.join(OUT, "reference_embeddings_more.npz"), **out)
+    return out
+
+
 def mps_nll_file():
     L, chi, d, B = 8, 5, 3, 6
     arrays = [a.numpy() for a in S.make_mps_arrays(L, chi, d, std=0.2, seed=11, squeeze_ends=True, identity_all=True)]
@@ -156,6 +200,8 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     e = embeddings_file()
     print("embeddings:", sorted(k for k in e if k.startswith("phi_")))
+    m = embeddings_more_file()
+    print("more embeddings:", sorted(k for k in m if k.startswith("phi_")), m["nll_hermite_d2"], m["nll_arrays_n3"])
     print("nll per sample:", mps_nll_file())
     c = classifier_file()
     print("classifier:", {k: v for k, v in c.items() if k.startswith("loss_")})

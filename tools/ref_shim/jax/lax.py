@@ -9,7 +9,9 @@ cos = _np.cos
 sin = _np.sin
 
 
-def cond(pred, t, f, *ops):
+def cond(pred, t, f, *ops, operand=None):
+    if not ops:
+        ops = (operand,)
     return t(*ops) if pred else f(*ops)
 
 
