@@ -161,6 +161,16 @@ int tnb_backward_part(const tnb_problem *prob, int64_t batch, const void *x, con
                       void *stream, int32_t part, int32_t nparts);
 int32_t tnb_part_sites(const tnb_problem *prob, int32_t part, int32_t nparts, int32_t *site_begin, int32_t *site_end);
 
+/* Sweeps / DMRG-like strategy (tn4ml/strategy.py:51-258; the training loop around it: tn4ml/models/model.py:753-773, 829-866):
+ * the pair (site, site + 1) is contracted into one tensor T[a, r, s, s'(, k)] = sum_m A_site[a, m, s(, k)] A_site+1[m, r, s'(, k)]
+ * and the loss is differentiated with respect to T.  tnb_pair_grad writes that gradient,
+ *     dT [chi][chi][d][d][n_k]   (dtype; n_k = n_out when one of the two sites carries the class leg, else 1),
+ * of  loss_scale * sum_b loss_b  from the environments left in `workspace` by tnb_forward(keep_stash = 1) followed by
+ * tnb_backward_part(part = 0, ...) (the adjoint sweep; its loss_scale is the one that applies) on the same arguments.
+ * TNB_KIND_MPS with TNB_PREC_SIMT arithmetic (float32 or float64). */
+int tnb_pair_grad(const tnb_problem *prob, int64_t batch, const void *x, const void *targets, int32_t site, void *dT,
+                  void *workspace, int64_t workspace_bytes, void *stream);
+
 /* One optax.adam step on the packed buffers (the update side of train_step, tn4ml/models/model.py:591-614, where the
  * reference runs eager optax over an L-leaf pytree):  mu, nu updated in place, params += -lr * mu_hat / (sqrt(nu_hat +
  * eps_root) + eps) with the bias corrections of step `count` (1-based).  grad_scale multiplies the gradient first

@@ -1,7 +1,9 @@
 """CPU restatement of tn4ml's batched product-state contraction (fwd + bwd).
 
-TEST INFRASTRUCTURE ONLY -- see ``oracle/__init__.py``.  PARITY UNPINNED (no
-reference golden vectors exist and the reference cannot be imported here).
+TEST INFRASTRUCTURE ONLY -- see ``oracle/__init__.py``.  PINNED by golden vectors produced by executing the reference's own
+source (tools/make_reference_golden.py over the stand-ins in tools/ref_shim; tests/test_reference_golden.py): feature maps,
+embed()'s normaliser, MPS / classifier index conventions, every MPS loss head and finite differences of the executed loss.
+Not pinned that way: the SMPO apply_mps path (too deep into quimb to stand in for; checked by dense contraction instead).
 
 Every function cites the reference file:line (relative to /root/reference) it
 restates.  Arithmetic is torch on the CPU (float64 unless a dtype is passed);
@@ -590,3 +592,122 @@ def regulariser(sites4: Sequence[torch.Tensor], kind: str, norm_is_trace: bool =
 # ----------------------------------------------------------------------------
 from tn4ml_b200.synthetic import (  # noqa: E402,F401
     make_inputs, make_labels, make_mps_arrays, make_smpo_arrays, mps_model_sqnorm)
+
+
+# ----------------------------------------------------------------------------
+# Sweeps / DMRG-like strategy  (tn4ml/strategy.py:51-258; training loop tn4ml/models/model.py:753-773, 829-866)
+# ----------------------------------------------------------------------------
+
+
+def _qr_left(sites, i):
+    """left_canonize_site: A_i = Q R over rows (l, s, k); R into site i+1."""
+    A = sites[i]
+    cl, cr, d, n = A.shape
+    Q, R = torch.linalg.qr(A.permute(0, 2, 3, 1).reshape(cl * d * n, cr))
+    k = Q.shape[1]
+    if k < cr:
+        Q = torch.cat([Q, Q.new_zeros(Q.shape[0], cr - k)], dim=1)
+        R = torch.cat([R, R.new_zeros(cr - k, cr)], dim=0)
+    sites[i] = Q.reshape(cl, d, n, cr).permute(0, 3, 1, 2)
+    sites[i + 1] = torch.einsum("ab,brsk->arsk", R, sites[i + 1])
+
+
+def _qr_right(sites, i):
+    A = sites[i]
+    cl, cr, d, n = A.shape
+    Q, R = torch.linalg.qr(A.permute(1, 2, 3, 0).reshape(cr * d * n, cl))
+    k = Q.shape[1]
+    if k < cl:
+        Q = torch.cat([Q, Q.new_zeros(Q.shape[0], cl - k)], dim=1)
+        R = torch.cat([R, R.new_zeros(cl - k, cl)], dim=0)
+    sites[i] = Q.reshape(cr, d, n, cl).permute(3, 0, 1, 2)
+    sites[i - 1] = torch.einsum("lask,ba->lbsk", sites[i - 1], R)
+
+
+def _as_arrays(sites, cls):
+    return [a if i == cls else a[..., 0] for i, a in enumerate(sites)]
+
+
+def pair_loss_and_grad(prob: Problem, x, sites, cls, i, targets=None):
+    """Mean loss and its gradient with respect to the merged tensor T[a, r, s, s', k] of sites (i, i+1), by autograd: the pair
+    is replaced by T itself on site i (its right bond enlarged to (r, s', k)) and a constant selection tensor on site i+1."""
+    A, B = sites[i], sites[i + 1]
+    T = torch.einsum("amsk,mrtq->arstkq", A, B)
+    cl, cr, d = T.shape[0], T.shape[1], T.shape[2]
+    T = T.reshape(cl, cr, d, d, -1).detach().clone().requires_grad_(True)
+    nk = T.shape[4]
+    left = T.permute(0, 1, 3, 4, 2).reshape(cl, cr * d * nk, d, 1)           # [a, (r, s', k), s]
+    sel = torch.eye(cr * d * nk, dtype=T.dtype).reshape(cr * d * nk, cr, d, nk)  # [(r, s', k), r, s', k]
+    new = list(sites)
+    new[i], new[i + 1] = left, sel
+    new_cls = i + 1 if nk > 1 else cls
+    arrays = [a if j == new_cls else a[..., 0] for j, a in enumerate(new)]
+    loss = loss_fn(prob, x, arrays, targets)
+    (g,) = torch.autograd.grad(loss, T)
+    return loss.detach(), T.detach(), g
+
+
+def sweeps_train(prob: Problem, x, arrays, targets=None, *, epochs=1, lr=1e-2, two_way=True, optimizer="sgd", clip=None,
+                 b1=0.9, b2=0.999, eps=1e-8):
+    """One full-batch training run with the Sweeps strategy.  Returns (site arrays, [loss per epoch], [loss per pair step])."""
+    sites, cls = canon_mps_sites([a.clone() for a in arrays])
+    L = len(sites)
+    pairs = [(i, i + 1) for i in range(L - 1)]
+    if two_way:
+        pairs += [(i, i - 1) for i in reversed(range(1, L))]
+
+    def canonicalize(lo, hi):
+        for j in range(lo):
+            _qr_left(sites, j)
+        for j in range(L - 1, hi, -1):
+            _qr_right(sites, j)
+
+    def split(i, T, keep):
+        cl, cr, d, _, nk = T.shape
+        na = sites[i].shape[3]
+        if na > 1:
+            M = T.permute(0, 2, 4, 1, 3).reshape(cl * d * na, cr * d)
+        else:
+            M = T.permute(0, 2, 1, 3, 4).reshape(cl * d, cr * d * nk)
+        U, S, Vh = torch.linalg.svd(M, full_matrices=False)
+        k = min(keep, S.numel())
+        rs = torch.sqrt(S[:k])
+        A = torch.zeros(cl, keep, d, na, dtype=T.dtype)
+        Bn = torch.zeros(keep, cr, d, sites[i + 1].shape[3], dtype=T.dtype)
+        A[:, :k] = (U[:, :k] * rs).reshape(cl, d, na, k).permute(0, 3, 1, 2)
+        Bn[:k] = (rs[:, None] * Vh[:k]).reshape(k, cr, d, sites[i + 1].shape[3])
+        sites[i], sites[i + 1] = A, Bn
+
+    state = {}
+    for pr in pairs:  # model.py:753-773: the initialisation loop contracts and splits every pair once
+        i = min(pr)
+        canonicalize(i, i + 1)
+        keep = sites[i].shape[1]
+        T = torch.einsum("amsk,mrtq->arstkq", sites[i], sites[i + 1])
+        T = T.reshape(T.shape[0], T.shape[1], T.shape[2], T.shape[3], -1)
+        state[pr] = {"count": 0, "mu": torch.zeros_like(T), "nu": torch.zeros_like(T)}
+        split(i, T, keep)
+    history, steps = [], []
+    for _ in range(epochs):
+        acc = 0.0
+        for pr in pairs:
+            i = min(pr)
+            canonicalize(i, i + 1)
+            keep = sites[i].shape[1]
+            loss, T, g = pair_loss_and_grad(prob, x, sites, cls, i, targets)
+            if clip:
+                g = g * min(1.0, clip / (float(g.norm()) + 1e-6))
+            if optimizer == "sgd":
+                T = T - lr * g
+            else:  # optax.adam
+                st = state[pr]
+                st["count"] += 1
+                t = st["count"]
+                st["mu"] = b1 * st["mu"] + (1 - b1) * g
+                st["nu"] = b2 * st["nu"] + (1 - b2) * g * g
+                T = T - lr * (st["mu"] / (1 - b1**t)) / (torch.sqrt(st["nu"] / (1 - b2**t)) + eps)
+            split(i, T, keep)
+            steps.append(float(loss))
+            acc += float(loss)
+        history.append(acc / len(pairs))
+    return _as_arrays(sites, cls), history, steps

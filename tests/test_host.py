@@ -147,6 +147,30 @@ def test_configure_error_behaviour_matches_reference():
             m.configure(train_type=0, device=("gpu", 0))    # model.py:262-266
 
 
+def test_sweeps_strategy_host_logic():
+    """Sweeps (strategy.py:51-131): pair order of a two-way / one-way sweep, constructor errors, the split of a contracted pair
+    (storage-only model on the CPU: prehook / posthook are plain tensor algebra, exact for max_bond = the bond's size)."""
+    m = T.MPS_initialize(5, bond_dim=4, phys_dim=2, device="cpu")
+    assert list(T.Sweeps().iterate_sites(m)) == [(0, 1), (1, 2), (2, 3), (3, 4), (4, 3), (3, 2), (2, 1), (1, 0)]
+    assert list(T.Sweeps(two_way=False).iterate_sites(m)) == [(0, 1), (1, 2), (2, 3), (3, 4)]
+    with pytest.raises(ValueError):
+        T.Sweeps(grouping=1)
+    with pytest.raises(ValueError):
+        T.Sweeps(grouping=3)
+    with pytest.raises(TypeError):
+        list(T.Sweeps().iterate_sites(T.SMPO_initialize(6, spacing=2, device="cpu")))
+    x = torch.rand(3, 5, dtype=m.dtype)
+    prob = O.Problem("mps", O.EmbSpec("trig"), "nll")
+    before = O.per_sample_loss(prob, x.double(), [a.double() for a in m.arrays])
+    s = T.Sweeps()
+    for sites in s.iterate_sites(m):
+        Tm = s.prehook(m, sites)
+        assert Tm.shape[2:] == (2, 2, 1)
+        s.posthook(m, sites)
+    after = O.per_sample_loss(prob, x.double(), [a.double() for a in m.arrays])
+    assert torch.allclose(before, after, rtol=1e-9)
+
+
 def test_embedding_descriptors():
     assert T.TrigonometricEmbedding(k=3).dim == 6 and T.FourierEmbedding(p=8).dim == 8   # embeddings.py:385-387
     assert T.PolynomialEmbedding(degree=2, n=1, include_bias=True).dim == 3

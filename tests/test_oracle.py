@@ -195,3 +195,39 @@ def test_model_init_norm_is_one():
     # tests/test_mps.py:14-44 (norm() == approx(1) after init)
     arrays = O.make_mps_arrays(20, 6, 2, class_site=9, C=3)
     assert abs(float(O.mps_model_sqnorm(arrays)) - 1.0) < 1e-10
+
+
+def test_sweeps_restatement_preserves_the_model_then_descends():
+    """oracle.sweeps_train (strategy.py:51-258, model.py:753-773, 829-866): contracting and splitting a pair with max_bond = the
+    bond's size is exact, so the first pair step sees the loss of the given model; later steps descend; the two-site gradient
+    agrees with central finite differences of the loss of the merged tensor."""
+    arrays = O.make_mps_arrays(6, 4, 2, class_site=2, C=3, std=0.2, seed=3)
+    x, t = O.make_inputs(15, 6, seed=5), O.make_labels(15, 3)
+    prob = O.Problem("mps", O.EmbSpec("trig"), "softmax_xent")
+    l0 = float(O.loss_fn(prob, x, arrays, t))
+    arr, hist, steps = O.sweeps_train(prob, x, arrays, t, epochs=2, lr=0.05)
+    assert abs(steps[0] - l0) < 1e-12 and hist[1] < hist[0] and len(steps) == 2 * 10
+    assert [tuple(a.shape) for a in arr] == [tuple(a.shape) for a in arrays]
+    sites, cls = O.canon_mps_sites(arrays)
+    for i in (1, 2, 4):  # class site on the right of the pair, on the left, away from it
+        loss, T, g = O.pair_loss_and_grad(prob, x, sites, cls, i, t)
+        assert abs(float(loss) - l0) < 1e-12
+        rng = np.random.default_rng(i)
+        for _ in range(4):
+            idx = tuple(int(rng.integers(n)) for n in T.shape)
+            h = 1e-6
+
+            def f(delta):
+                Tn = T.clone()
+                Tn[idx] += delta
+                A, B = sites[i], sites[i + 1]
+                cl, cr, d, _, nk = Tn.shape
+                left = Tn.permute(0, 1, 3, 4, 2).reshape(cl, cr * d * nk, d, 1)
+                sel = torch.eye(cr * d * nk, dtype=Tn.dtype).reshape(cr * d * nk, cr, d, nk)
+                new = list(sites)
+                new[i], new[i + 1] = left, sel
+                ncls = i + 1 if nk > 1 else cls
+                return float(O.loss_fn(prob, x, [a if j == ncls else a[..., 0] for j, a in enumerate(new)], t))
+
+            fd = (f(h) - f(-h)) / (2 * h)
+            assert abs(fd - float(g[idx])) < 1e-7 * max(1.0, abs(fd))

@@ -69,6 +69,8 @@ SYMBOLS = {
     "tnb_gradient_clip": (C.c_int, [_P(TnbProblem), C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
     "tnb_backward_part": (C.c_int, [_P(TnbProblem), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32]),
+    "tnb_pair_grad": (C.c_int, [_P(TnbProblem), C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
+                                C.c_void_p]),
     "tnb_part_sites": (C.c_int32, [_P(TnbProblem), C.c_int32, C.c_int32, _P(C.c_int32), _P(C.c_int32)]),
     "tnb_norm_workspace_bytes": (C.c_int64, [_P(TnbProblem)]),
     "tnb_norm": (C.c_int, [_P(TnbProblem), C.c_void_p, C.c_void_p, C.c_int32, _P(C.c_int32), _P(C.c_double), C.c_void_p,

@@ -382,6 +382,21 @@ int tnb_backward_part(const tnb_problem *p, int64_t batch, const void *x, const 
                        part, nparts);
 }
 
+int tnb_pair_grad(const tnb_problem *p, int64_t batch, const void *x, const void *targets, int32_t site, void *dT,
+                  void *workspace, int64_t workspace_bytes, void *stream) {
+  if (validate(p)) return 1;
+  if (batch < 1) return fail("batch must be >= 1");
+  if (!x || !dT || !workspace) return fail("null device pointer");
+  if (p->kind != TNB_KIND_MPS) return fail("tnb_pair_grad: MPS models only (the reference's Sweeps strategy, strategy.py)");
+  if (site < 0 || site + 1 >= p->L) return fail("pair (%d, %d) out of range", site, site + 1);
+  if (ensure_device_ready()) return 1;
+  MpsPlan P = plan_mps(p, batch, 1);
+  if (P.tc) return fail("tnb_pair_grad reads the SIMT family's environment stash: set precision = TNB_PREC_SIMT");
+  if ((int64_t)P.total > workspace_bytes)
+    return fail("workspace too small: need %zu bytes, got %lld", P.total, (long long)workspace_bytes);
+  return mps_simt_pair_grad(p, P, batch, x, targets, site, dT, workspace, (cudaStream_t)stream);
+}
+
 int32_t tnb_part_sites(const tnb_problem *p, int32_t part, int32_t nparts, int32_t *site_begin, int32_t *site_end) {
   if (!p || !site_begin || !site_end || nparts < 1 || part < 0 || part >= nparts) return fail("bad arguments");
   int s0, s1;

@@ -78,6 +78,9 @@ int mps_simt_forward(const tnb_problem *p, const MpsPlan &P, long long B, const 
 // part / nparts: the backward pass in site ranges (tnb_backward_part): part 0 also runs the adjoint sweep
 int mps_simt_backward(const tnb_problem *p, const MpsPlan &P, long long B, const void *x, const void *targets,
                       double loss_scale, void *grads, int accumulate, void *ws, cudaStream_t st, int part, int nparts);
+// two-site gradient of the Sweeps strategy from the stash of forward + backward part 0 (tnb_pair_grad)
+int mps_simt_pair_grad(const tnb_problem *p, const MpsPlan &P, long long B, const void *x, const void *targets, int site,
+                       void *dT, void *ws, cudaStream_t st);
 cudaError_t mps_simt_set_attrs();
 // tcgen05 family (mps_tc.cu): float32, TNB_PREC_TENSOR
 int mps_tc_forward(const tnb_problem *p, const MpsPlan &P, long long B, const void *x, const void *targets,

@@ -142,6 +142,36 @@ int mps_simt_backward(const tnb_problem *p, const MpsPlan &P, long long B, const
   TNB_DISPATCH_MPS(mps_backward_t, p, P, B, x, targets, loss_scale, grads, accumulate, ws, st, part, nparts);
 }
 
+// tnb_pair_grad: the two-site gradient of the Sweeps strategy from the stash of forward + tnb_backward_part(part 0)
+template <typename T>
+static int mps_pair_t(const tnb_problem *p, const MpsPlan &P, long long B, const void *x, const void *targets, int site,
+                      void *dT, void *ws, cudaStream_t st) {
+  MpsArgs<T> A;
+  fill_mps_args<T>(p, P, B, x, targets, ws, A);
+  A.stash = 1;
+  const bool cls = site == p->out_site || site + 1 == p->out_site;
+  const int nk = cls ? p->n_out : 1;
+  const int tiles = (p->chi + 15) / 16;
+  const long long work = (long long)tiles * tiles * p->d * p->d * nk;
+  long long ns = (148LL * 2 + work - 1) / work;
+  const long long maxsplit = (B + 255) / 256;
+  if (ns > maxsplit) ns = maxsplit;
+  if (ns < 1 || deterministic()) ns = 1;
+  long long bchunk = ((B + ns - 1) / ns + 31) / 32 * 32;
+  if (ns > 1) TNB_CUDA(cudaMemsetAsync(dT, 0, (size_t)p->chi * p->chi * p->d * p->d * nk * sizeof(T), st));
+  dim3 grid((unsigned)(tiles * tiles * ns), (unsigned)(p->d * p->d), (unsigned)nk);
+  prof_begin(st);
+  mps_pair_kernel<T><<<grid, 256, 0, st>>>(A, site, (T *)dT, (int)ns, bchunk);
+  TNB_LAUNCH_CHECK("mps_pair_kernel");
+  return 0;
+}
+
+int mps_simt_pair_grad(const tnb_problem *p, const MpsPlan &P, long long B, const void *x, const void *targets, int site,
+                       void *dT, void *ws, cudaStream_t st) {
+  if (p->dtype == TNB_F64) return mps_pair_t<double>(p, P, B, x, targets, site, dT, ws, st);
+  return mps_pair_t<float>(p, P, B, x, targets, site, dT, ws, st);
+}
+
 // Embedding.__call__ for n scalars (tnb_embed)
 int embed_launch(const tnb_embedding *emb, int d, int32_t dtype, int64_t n, const void *x, void *phi, cudaStream_t st) {
   int blocks = (int)((n + 255) / 256);

@@ -777,6 +777,64 @@ template <typename T, int RM> __global__ void __launch_bounds__(256) mps_da_kern
 }
 
 // ---------------------------------------------------------------------------------------
+// Two-site gradient of the Sweeps strategy (tn4ml/strategy.py:135-176: the pair (site, site + 1) is contracted into one
+// tensor T and the loss is differentiated with respect to T):
+//     dT[a][r][s][s'][k] = sum_b U[b, a] * V[b, r] * w_s[b] * w'_{s'}[b] * (dy[b, k] if the pair holds the class site)
+// from the stash of a forward + adjoint pass: U = F[site] (left environment) or, right of the class site, the adjoint
+// G[site]; V = the adjoint G[site + 2] left of the class site, else the right environment F[site + 2]; w, w' = the per-sample
+// weights of the two sites (phi_s * 2^-delta, mps_wq_kernel).  One CTA per 16 x 16 tile of (a, r), per (s, s'), per class
+// index and per batch split; split-K partial sums are added atomically (dT is zeroed by the caller).
+// ---------------------------------------------------------------------------------------
+template <typename T> __global__ void __launch_bounds__(256) mps_pair_kernel(MpsArgs<T> A, int site, T *dT, int nsplit, long long bchunk) {
+  constexpr int BK = 32;
+  __shared__ T U_s[BK][17];
+  __shared__ T V_s[BK][17];
+  const int chi = A.chi, chip = A.chip, D = A.D, C = A.C, c = A.c;
+  const bool cls = site == c || site + 1 == c;
+  const int nk = cls ? C : 1;
+  const int tiles = (chi + 15) / 16;
+  int bx = blockIdx.x;
+  const int split = bx % nsplit;
+  bx /= nsplit;
+  const int tr = bx % tiles, ta = bx / tiles;
+  const int s = blockIdx.y / D, sp = blockIdx.y - s * D, k = blockIdx.z;
+  const T *U = site > c ? A.G + (size_t)site * A.B * chip : mps_fenv(A, site);
+  const T *V = site + 1 < c ? A.G + (size_t)(site + 2) * A.B * chip : mps_fenv(A, site + 2);
+  const T *W0 = A.wq + ((size_t)site * D + s) * A.B;
+  const T *W1 = A.wq + ((size_t)(site + 1) * D + sp) * A.B;
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  const long long bbeg = (long long)split * bchunk, bend = min(A.B, bbeg + bchunk);
+  T acc = T(0);
+  for (long long bb = bbeg; bb < bend; bb += BK) {
+    // 256 threads stage 32 samples x 16 columns of U (weighted) and V, two rows each
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int kk = ty + 16 * e;
+      const long long b = bb + kk;
+      const bool ok = b < bend;
+      const int a = ta * 16 + tx, r = tr * 16 + tx;
+      T w = T(0);
+      if (ok) {
+        w = W0[b] * W1[b];
+        if (cls) w *= A.dy[(size_t)b * C + k];
+      }
+      U_s[kk][tx] = ok && a < chi ? U[(size_t)b * chip + a] * w : T(0);
+      V_s[kk][tx] = ok && r < chi ? V[(size_t)b * chip + r] : T(0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) acc = fma(U_s[kk][ty], V_s[kk][tx], acc);
+    __syncthreads();
+  }
+  const int a = ta * 16 + ty, r = tr * 16 + tx;
+  if (a < chi && r < chi) {
+    T *dst = &dT[((((size_t)a * chi + r) * D + s) * D + sp) * nk + k];
+    if (nsplit > 1) atomicAdd(dst, acc);
+    else *dst = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Weight re-layout (once per step; parameters are tiny next to the batch work):
 //   packed A_j[a][r][s][o]  ->  Wn[slab][k=a][s][n=r] and Wt[slab][k=r][s][n=a], zero padded to chip.
 // ---------------------------------------------------------------------------------------

@@ -216,6 +216,50 @@ class Engine:
                 reducer.finish()
         return self._loss_sum, grads
 
+    # -- Sweeps strategy: loss and the gradient with respect to a merged pair of sites --------------------
+    def pair_value_and_grad(self, params: torch.Tensor, x, targets, site: int, *, denom: int | None = None):
+        """(sum_b loss_b as a device float64 scalar, dT [chi, chi, d, d, n_k]): the gradient of sum_b loss_b / denom with
+        respect to T = A_site . A_site+1 (strategy.py:135-176, model.py:829-866), from the environments of one forward pass
+        and one adjoint sweep (tnb_forward with the stash kept, tnb_backward_part part 0 of L, tnb_pair_grad)."""
+        if self.prob.kind != _lib.KIND_MPS:
+            raise NotImplementedError("Sweeps is built for matrix product states (the reference's strategy.py)")
+        x, targets = self._prep(x, targets)
+        x, extra = self._split_extra(x)
+        B = x.shape[0]
+        denom = B if denom is None else denom
+        L = self.prob.L
+        cls = self.prob.n_out > 1 and site in (self.prob.out_site, self.prob.out_site - 1)
+        nk = self.prob.n_out if cls else 1
+        chi, d = self.prob.chi, self.prob.d
+        dT = torch.zeros(chi, chi, d, d, nk, dtype=self.dtype, device=self.device)
+        if getattr(self, "_pair_scratch", None) is None:
+            self._pair_scratch = (torch.empty(self.n_params, dtype=self.dtype, device=self.device), torch.empty_like(dT))
+        scratch_g, part = self._pair_scratch
+        if part.shape != dT.shape:
+            part = torch.empty_like(dT)
+            self._pair_scratch = (scratch_g, part)
+        self._loss_sum.zero_()
+        if extra is not None and self.prob.head == _lib.HEAD_NLL:
+            self._loss_sum.add_(extra.double().sum())
+        mb = self.microbatch(B, True)
+        with torch.cuda.device(self.device):
+            for s in range(0, B, mb):
+                e = min(B, s + mb)
+                ws = self._workspace(e - s, True)
+                t_ptr = targets[s:e].data_ptr() if targets is not None else None
+                _lib.check(self.lib.tnb_forward(
+                    C.byref(self.prob), e - s, x[s:e].data_ptr(), t_ptr, params.data_ptr(), None,
+                    self._loss_sum.data_ptr(), None, None, 1, ws.data_ptr(), ws.numel(), self._stream()))
+                # the adjoint sweep (part 0 of L also forms the gradient of site 0 alone, which is discarded)
+                _lib.check(self.lib.tnb_backward_part(
+                    C.byref(self.prob), e - s, x[s:e].data_ptr(), t_ptr, params.data_ptr(), 1.0 / denom,
+                    scratch_g.data_ptr(), 0, ws.data_ptr(), ws.numel(), self._stream(), 0, L))
+                _lib.check(self.lib.tnb_pair_grad(
+                    C.byref(self.prob), e - s, x[s:e].data_ptr(), t_ptr, site, part.data_ptr(), ws.data_ptr(), ws.numel(),
+                    self._stream()))
+                dT.add_(part)
+        return self._loss_sum, dT
+
     def part_range(self, part: int, nparts: int) -> tuple[int, int]:
         """Element range of the packed gradient that is final after part `part` of `nparts` (tnb_part_sites)."""
         s0, s1 = C.c_int32(), C.c_int32()

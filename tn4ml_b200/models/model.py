@@ -21,6 +21,7 @@ from .. import _lib, optim
 from ..embeddings import Embedding, TrigonometricEmbedding, spec_of
 from ..engine import Engine
 from ..metrics import LossExpr, resolve
+from ..strategy import Strategy, Sweeps
 from ..util import EarlyStopping, TrainingType
 
 logger = logging.getLogger(__name__)
@@ -294,27 +295,51 @@ class Model:
             last = self._canon4(self.L - 1)
             last.div_(torch.linalg.norm(last))
 
-    def canonicalize(self, where: int, inplace: bool = True, **_opts):
-        """Mixed-canonical form around site `where` (quimb's canonicalize, used by train(canonize=(True, c)),
-        model.py:882-883): sites left of it left-orthogonal, sites right of it right-orthogonal; the state is unchanged."""
-        if not (0 <= where < self.L):
+    def canonicalize(self, where, inplace: bool = True, **_opts):
+        """Mixed-canonical form around site `where` -- or around the section min(where) .. max(where) of a set of sites, as
+        the Sweeps strategy asks for (strategy.py:150-154) -- (quimb's canonicalize, used by train(canonize=(True, c)),
+        model.py:882-883): sites left of it left-orthogonal, sites right of it right-orthogonal; the state is unchanged.
+
+        Inside a sweep the sites known to be canonical already (`_canon_known`, kept by the strategy's hooks) are skipped:
+        a QR of an isometry returns it up to signs, so this only fixes a sign gauge the reference leaves to LAPACK."""
+        lo, hi = (where, where) if isinstance(where, (int, np.integer)) else (min(where), max(where))
+        if not (0 <= lo <= hi < self.L):
             raise ValueError(f"canonical center {where} out of range")
         m = self if inplace else self.copy()
-        m._qr_sweep(range(0, where), left=True)
-        m._qr_sweep(range(m.L - 1, where, -1), left=False)
+        known = getattr(m, "_canon_known", None)
+        first, last = (0, m.L - 1) if known is None else (min(known[0], lo), max(known[1], hi))
+        m._qr_sweep(range(first, lo), left=True)
+        m._qr_sweep(range(last, hi, -1), left=False)
+        if known is not None:
+            m._canon_known = (lo, hi)
         return m
+
+    def _mark_modified(self, lo: int, hi: int):
+        """Sites lo .. hi were rewritten: they are no longer known to be canonical."""
+        known = getattr(self, "_canon_known", None)
+        if known is not None:
+            self._canon_known = (min(known[0], lo), max(known[1], hi))
 
     canonize = canonicalize
 
     # ---- configure (model.py:155-276) ---------------------------------------------
     def configure(self, **kwargs):
         for key, value in kwargs.items():
-            if key == "strategy":
-                if value in ["global", "sgd", "gd", "gradient_descent"]:
-                    self.strategy = "global"
+            if key == "strategy":  # model.py:186-214
+                if isinstance(value, Strategy):
+                    self.strategy = value
                 elif value in ["sweeps", "local", "dmrg", "dmrg-like", "sweeps-one-way",
                                "sweeps-one-way-per-site", "sweeps-per-site"]:
-                    raise NotImplementedError("the Sweeps strategy is outside the data-parallel hot path")
+                    if value == "sweeps-one-way-per-site":
+                        self.strategy = Sweeps(two_way=False, grouping=1)  # (raises like the reference: grouping == 1)
+                    elif value == "sweeps-per-site":
+                        self.strategy = Sweeps(two_way=True, grouping=1)
+                    elif value == "sweeps-one-way":
+                        self.strategy = Sweeps(two_way=False, grouping=2)
+                    else:
+                        self.strategy = Sweeps()
+                elif value in ["global", "sgd", "gd", "gradient_descent"]:
+                    self.strategy = "global"
                 else:
                     raise ValueError(f'Strategy "{value}" not found')
             elif key in ["optimizer", "loss", "train_type", "learning_rate", "gradient_transforms", "device",
@@ -430,14 +455,64 @@ class Model:
 
         return train_step, opt_state
 
+    # ---- Sweeps strategy (strategy.py:51-258; model.py:753-773, 829-866) -------------------------------------------
+    def create_pair_train_step(self, *, embedding=None, dtype=None):
+        """train_step(T, opt_state, data, sites, grad_clip_threshold) -> (T, opt_state, loss) for the merged tensor T of one
+        pair of sites: loss and dLoss/dT from the environment kernels (Engine.pair_value_and_grad), util.gradient_clip on the
+        one tensor, the optimizer's update applied to T in place.  What create_train_step(params=params_i, ...) returns in the
+        reference when the strategy is Sweeps."""
+        supervised = self.train_type == TrainingType.SUPERVISED
+        if self.process_group is not None:
+            raise NotImplementedError("Sweeps is single-device (as in the reference)")
+        prec = self.precision
+        self.precision = _lib.PREC_SIMT  # tnb_pair_grad reads the SIMT family's environment stash
+        try:
+            eng, expr = self._engine(embedding or TrigonometricEmbedding(), self.loss, supervised, dtype)
+        finally:
+            self.precision = prec
+        if expr is not None and expr.regs:
+            raise NotImplementedError("model-only regularisers inside a Sweeps step are not built")
+
+        def train_step(T, opt_state, data=None, sites=None, grad_clip_threshold=None):
+            if isinstance(data, tuple) and len(data) == 2:
+                x, t = data
+            else:
+                x, t = data, None
+            i = min(sites)
+            loss_sum, dT = eng.pair_value_and_grad(self._packed, x, t, i, denom=x.shape[0])
+            g = dT[:T.shape[0], :T.shape[1]]
+            if grad_clip_threshold:  # util.gradient_clip on the single tensor (util.py:131-155)
+                g = g * torch.clamp(grad_clip_threshold / (torch.linalg.norm(g) + 1e-6), max=1.0)
+            if opt_state is None or opt_state_shape(opt_state) != tuple(T.shape):
+                opt_state = self._opt.init(T)  # (model.py:596-604: the moments are re-initialised when the shape changed)
+            updates, opt_state = self._opt.update(g.contiguous(), opt_state, T)
+            T.add_(updates.to(T.dtype))
+            return T, opt_state, loss_sum / x.shape[0]
+
+        def opt_state_shape(state):
+            for v in (state.values() if isinstance(state, dict) else ()):
+                if torch.is_tensor(v):
+                    return tuple(v.shape)
+            return None
+
+        return train_step
+
     # ---- train (model.py:620-976) ----------------------------------------------------
-    def train(self, inputs=None, val_inputs=None, targets=None, val_targets=None, tn_target=None, batch_size=None,
-              epochs=1, embedding=None, normalize=False, canonize=(False, None), time_limit=None, earlystop=None,
-              gradient_clip_threshold=None, val_batch_size=None, eval_metric=None, display_val_acc=False,
-              accuracy_fn=None, dtype=None, shuffle=False, seed=42, alternate_flip=False):
+    def train(self, *args, **kwargs):
+        """model.py:620-976 (same arguments as the reference's train)."""
+        try:
+            return self._train(*args, **kwargs)
+        finally:
+            self._canon_known = None  # (the canonical-section bookkeeping of a sweep is only valid inside it)
+
+    def _train(self, inputs=None, val_inputs=None, targets=None, val_targets=None, tn_target=None, batch_size=None,
+               epochs=1, embedding=None, normalize=False, canonize=(False, None), time_limit=None, earlystop=None,
+               gradient_clip_threshold=None, val_batch_size=None, eval_metric=None, display_val_acc=False,
+               accuracy_fn=None, dtype=None, shuffle=False, seed=42, alternate_flip=False):
         if embedding is None:
             embedding = TrigonometricEmbedding()
-        if self.strategy != "global":
+        sweeps = isinstance(self.strategy, Sweeps)
+        if not sweeps and self.strategy != "global":
             raise ValueError("Only Global Gradient Descent and DMRG Sweeping strategy is supported for now!")
         if not hasattr(self, "_opt"):
             raise AttributeError("Provide 'optimizer' or sequence of 'gradient_transforms'! ")
@@ -464,7 +539,20 @@ class Model:
         return_value = 0
         if earlystop:
             earlystop.on_begin_train(self.history, self)
-        self.step, self.opt_state = self.create_train_step(embedding=embedding, dtype=dtype)
+        if sweeps:
+            # model.py:753-773: one optimizer state per pair and direction; the reference's initialisation loop contracts and
+            # splits every pair once (a change of gauge: the splits are exact)
+            self.step = self.create_pair_train_step(embedding=embedding, dtype=dtype)
+            self.opt_states = {}
+            self._canon_known = None
+            self.canonicalize(0)
+            self._canon_known = (0, 0)
+            for sites in self.strategy.iterate_sites(self):
+                T = self.strategy.prehook(self, sites)
+                self.opt_states[sites] = self._opt.init(T)
+                self.strategy.posthook(self, sites)
+        else:
+            self.step, self.opt_state = self.create_train_step(embedding=embedding, dtype=dtype)
         start_train = time()
         for epoch in range(epochs):
             time_epoch = time()
@@ -476,11 +564,24 @@ class Model:
                     batch_data = tuple(_to_device(b, dev, self.dtype) for b in batch_data)
                 else:
                     batch_data = _to_device(batch_data, dev, self.dtype)
-                _, self.opt_state, loss_curr = self.step(self.arrays, self.opt_state, batch_data,
-                                                         grad_clip_threshold=gradient_clip_threshold)
+                if sweeps:  # model.py:829-866
+                    loss_curr = torch.zeros((), dtype=torch.float64, device=dev)
+                    site_count = 0
+                    for sites in self.strategy.iterate_sites(self):
+                        site_count += 1
+                        T = self.strategy.prehook(self, sites)
+                        _, self.opt_states[sites], loss_group = self.step(
+                            T, self.opt_states[sites], batch_data, sites=sites, grad_clip_threshold=gradient_clip_threshold)
+                        self.strategy.posthook(self, sites)
+                        loss_curr = loss_curr + loss_group.reshape(())
+                    loss_curr = loss_curr / site_count
+                else:
+                    _, self.opt_state, loss_curr = self.step(self.arrays, self.opt_state, batch_data,
+                                                             grad_clip_threshold=gradient_clip_threshold)
                 loss_batch = loss_batch + loss_curr.reshape(())
                 if normalize:
                     self.normalize()
+                    self._canon_known = None if getattr(self, "_canon_known", None) is None else (0, self.L - 1)
                 if canonize and canonize[0]:  # model.py:882-883
                     self.canonicalize(canonize[1], inplace=True)
             loss_epoch = float((loss_batch / n_batches).item())  # the one D2H sync per epoch (model.py:887)
