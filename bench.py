@@ -238,7 +238,7 @@ def ncu_traffic(kernel: str, tiles: int):
             ir, iw = cols.index("dram__bytes_read.sum"), cols.index("dram__bytes_write.sum")
         except ValueError:
             continue
-        rows = [ln for ln in lines if ln.startswith('"' + want)]
+        rows = [ln for ln in lines if ln.startswith('"') and re.search(r'\b' + re.escape(want) + r'\b', ln.split('"')[1])]
         if want == "tc_chain_kernel" and len(rows) >= 2:
             rows = [rows[1 if adj else 0]]  # first launch of the step = forward sweep, second = adjoint
         if not rows:

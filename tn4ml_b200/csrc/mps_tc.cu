@@ -132,19 +132,15 @@ int mps_tc_forward(const tnb_problem *p, const MpsPlan &P, long long B, const vo
   // weight images, then ONE kernel for both chains, the class site and the head
   TcArgs Tc;
   fill_tc_args(P, ws, A, Tc);
+  TNB_CUDA(cudaMemsetAsync((void *)Tc.kW, 0, (size_t)P.nslab * sizeof(int), st));
+  TNB_CUDA(cudaMemsetAsync((void *)Tc.colsum, 0, (size_t)2 * P.nslab * sizeof(float), st));
   prof_begin(st);
-  tc_sitemax_kernel<<<P.nslab, 256, 0, st>>>((const float *)params, (int *)Tc.kW, p->L, p->chi, p->d, p->n_out,
-                                             p->out_site);
-  TNB_LAUNCH_CHECK("tc_sitemax_kernel");
-  if (p->n_out > 1) {
-    prof_begin(st);
-    tc_classmin_kernel<<<1, 32, 0, st>>>((int *)Tc.kW, p->out_site, p->n_out);
-    TNB_LAUNCH_CHECK("tc_classmin_kernel");
-  }
+  tc_stats_kernel<<<dim3(P.nslab, kTcStatGroups), 256, 0, st>>>((const float *)params, (int *)Tc.kW, (int *)Tc.colsum, p->L,
+                                                                 p->chi, p->d, p->n_out, p->out_site);
+  TNB_LAUNCH_CHECK("tc_stats_kernel");
   prof_begin(st);
-  tc_colsum_kernel<<<dim3(P.nslab, 2), 256, 0, st>>>((const float *)params, Tc.kW, (float *)Tc.colsum, p->L, p->chi,
-                                                     p->d, p->n_out, p->out_site);
-  TNB_LAUNCH_CHECK("tc_colsum_kernel");
+  tc_finalize_kernel<<<1, 256, 0, st>>>((int *)Tc.kW, (float *)Tc.colsum, p->L, p->n_out, p->out_site);
+  TNB_LAUNCH_CHECK("tc_finalize_kernel");
   size_t items = (size_t)P.tc_N * (p->chi / 8) * P.nslab;
   int ib = (int)((items + 255) / 256);
   if (ib > 148 * 32) ib = 148 * 32;

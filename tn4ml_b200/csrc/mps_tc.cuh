@@ -60,67 +60,95 @@ struct TcArgs {
 };
 
 // ---- weight images ----------------------------------------------------------------------
-// kW[slab] = 14 - exponent(max |W|)  so that  max |W * 2^kW| is in [2^13, 2^14)
-__global__ void tc_sitemax_kernel(const float *__restrict__ params, int *__restrict__ kW, int L, int chi, int D, int C,
-                                  int c) {
-  const int slab = blockIdx.x;
-  int site, nj;
-  if (slab < c) { site = slab; nj = 1; }
-  else if (slab < c + C) { site = c; nj = C; }
-  else { site = slab - C + 1; nj = 1; }
-  const size_t site_off = (size_t)site * chi * chi * D + (site > c ? (size_t)chi * chi * D * (C - 1) : 0);
-  float m = 0.f;
-  const int o = slab - site - (site > c ? C - 1 : 0);  // class slabs: o = slab - c ; otherwise 0
-  const int n = chi * chi * D;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(params[site_off + (size_t)i * nj + o]));
-  __shared__ float red[32];
-  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < (int)(blockDim.x + 31) / 32; ++w) m = fmaxf(m, red[w]);
-    int e = 0;
-    if (m > 0.f) frexpf(m, &e);
-    kW[slab] = kTcKA - e;
-  }
-}
-
-// class slabs share one scale (the seed phase accumulates all of them into one TMEM tile): kW <- min over the C slabs
-__global__ void tc_classmin_kernel(int *__restrict__ kW, int c, int C) {
-  int m = INT_MAX;
-  for (int k = threadIdx.x; k < C; k += 32) m = min(m, kW[c + k]);
-  for (int off = 16; off > 0; off >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, off));
-  for (int k = threadIdx.x; k < C; k += 32) kW[c + k] = m;
-}
-
-// colsum[dir][slab] = max_n sum_{k,s} |W[k,s,n]| * 2^kW[slab]: with |phi_s| <= 1 and an operand row of max-abs m, every
-// output of the chain step through this slab is bounded by m * colsum, which fixes the step's power-of-two scale
-// BEFORE the step runs (no row maximum on the critical path).  One block per (slab, direction), thread = column n.
-__global__ void tc_colsum_kernel(const float *__restrict__ params, const int *__restrict__ kW, float *__restrict__ colsum,
-                                 int L, int chi, int D, int C, int c) {
-  const int slab = blockIdx.x, dir = blockIdx.y, nslab = L - 1 + C;
+// Per-slab statistics of the site tensors, one pass per step (the weights change with every optimizer update):
+//   max |W|                        -> kW[slab] = 14 - exponent(max |W|), so that max |W * 2^kW| is in [2^13, 2^14)
+//   max_n sum_{k,s} |W[k,s,n]|     -> colsum[dir][slab] (dir 0: n = right bond, dir 1: n = left bond): with |phi_s| <= 1 and an
+//                                     operand row of max-abs m, every output of the chain step through this slab is bounded
+//                                     by m * colsum, which fixes the step's power-of-two scale BEFORE the step runs (no row
+//                                     maximum on the critical path).
+// grid (slab, kTcStatGroups): block g takes the rows a of its quarter (row sums: one warp per row, lanes along the contiguous
+// (r, s) run) and the columns r of its quarter (column sums: threads along r, phases along a); the three maxima are
+// non-negative floats combined with atomicMax on their bit patterns (kW and colsum hold raw bits until tc_finalize_kernel).
+constexpr int kTcStatGroups = 4;
+__global__ void __launch_bounds__(256) tc_stats_kernel(const float *__restrict__ params, int *__restrict__ kW,
+                                                       int *__restrict__ colsum_bits, int L, int chi, int D, int C, int c) {
+  const int slab = blockIdx.x, g = blockIdx.y, nslab = L - 1 + C;
   int site, o, nj;
   if (slab < c) { site = slab; o = 0; nj = 1; }
   else if (slab < c + C) { site = c; o = slab - c; nj = C; }
   else { site = slab - C + 1; o = 0; nj = 1; }
-  const size_t site_off = (size_t)site * chi * chi * D + (site > c ? (size_t)chi * chi * D * (C - 1) : 0);
-  float best = 0.f;
-  for (int n = threadIdx.x; n < chi; n += blockDim.x) {
+  const float *W = params + (size_t)site * chi * chi * D + (site > c ? (size_t)chi * chi * D * (C - 1) : 0) + o;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = (chi + kTcStatGroups - 1) / kTcStatGroups;
+  const int lo = g * q, hi = min(chi, lo + q);
+  float wmax = 0.f, rowbest = 0.f, colbest = 0.f;
+  // rows a in [lo, hi): sum over (r, s)
+  const int run = chi * D;
+  for (int a = lo + warp; a < hi; a += 8) {
+    const float *row = W + (size_t)a * run * nj;
     float acc = 0.f;
-    for (int k = 0; k < chi; ++k) {
-      const int a = dir == 0 ? k : n, r = dir == 0 ? n : k;
-      const float *w = params + site_off + (((size_t)a * chi + r) * D) * nj + o;
-      for (int s = 0; s < D; ++s) acc += fabsf(w[(size_t)s * nj]);
+    for (int i = lane; i < run; i += 32) {
+      const float v = fabsf(row[(size_t)i * nj]);
+      acc += v;
+      wmax = fmaxf(wmax, v);
     }
-    best = fmaxf(best, acc);
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    rowbest = fmaxf(rowbest, acc);
   }
-  __shared__ float red[32];
-  for (int off = 16; off > 0; off >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, off));
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+  // columns r in [lo, hi): sum over (a, s); thread = (column, phase of a)
+  __shared__ float part[256];
+  const int ncol = hi - lo;
+  if (ncol > 0) {
+    const int nph = max(1, 256 / ncol);
+    for (int c0 = 0; c0 < ncol; c0 += 256) {  // (chi / 4 <= 256 columns: one trip)
+      const int col = c0 + tid % min(ncol, 256), ph = tid / min(ncol, 256);
+      float acc = 0.f;
+      if (col < ncol && ph < nph)
+        for (int a = ph; a < chi; a += nph) {
+          const float *w = W + (((size_t)a * chi + lo + col) * D) * nj;
+          for (int s2 = 0; s2 < D; ++s2) acc += fabsf(w[(size_t)s2 * nj]);
+        }
+      part[tid] = acc;
+      __syncthreads();
+      if (ph == 0 && col < ncol) {
+        for (int p2 = 1; p2 < nph; ++p2) acc += part[p2 * min(ncol, 256) + (col - c0)];
+        colbest = fmaxf(colbest, acc);
+      }
+      __syncthreads();
+    }
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, off));
+    rowbest = fmaxf(rowbest, __shfl_xor_sync(0xffffffffu, rowbest, off));
+    colbest = fmaxf(colbest, __shfl_xor_sync(0xffffffffu, colbest, off));
+  }
+  if (lane == 0) {
+    atomicMax(&kW[slab], __float_as_int(wmax));
+    atomicMax(&colsum_bits[slab], __float_as_int(colbest));          // dir 0: n = right bond
+    atomicMax(&colsum_bits[nslab + slab], __float_as_int(rowbest));  // dir 1: n = left bond
+  }
+}
+
+// raw maxima -> kW (class slabs share one scale: the seed phase accumulates all of them into one TMEM tile, so kW <- the min
+// over the C class slabs) and colsum * 2^kW with a margin for the fp16x3 rounding of the products.  One block.
+__global__ void tc_finalize_kernel(int *__restrict__ kW, float *__restrict__ colsum, int L, int C, int c) {
+  const int nslab = L - 1 + C;
+  __shared__ int kmin;
+  if (threadIdx.x == 0) kmin = INT_MAX;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < (int)(blockDim.x + 31) / 32; ++w) best = fmaxf(best, red[w]);
-    colsum[dir * nslab + slab] = ldexpf(best, kW[slab]) * 1.001f;  // margin for the fp16x3 rounding of the products
+  for (int slab = threadIdx.x; slab < nslab; slab += blockDim.x) {
+    const float m = __int_as_float(kW[slab]);
+    int e = 0;
+    if (m > 0.f) frexpf(m, &e);
+    const int k = kTcKA - e;
+    kW[slab] = k;
+    if (C > 1 && slab >= c && slab < c + C) atomicMin(&kmin, k);
+  }
+  __syncthreads();
+  for (int slab = threadIdx.x; slab < nslab; slab += blockDim.x) {
+    int k = kW[slab];
+    if (C > 1 && slab >= c && slab < c + C) { k = kmin; kW[slab] = k; }
+    for (int dir = 0; dir < 2; ++dir) colsum[dir * nslab + slab] = ldexpf(colsum[dir * nslab + slab], k) * 1.001f;
   }
 }
 

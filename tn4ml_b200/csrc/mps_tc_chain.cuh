@@ -23,7 +23,7 @@
 // A-priori scaling.  The next operand must be a row of bounded magnitude (fp16 range) times an exact power of two.
 // Instead of the row maximum of the outputs (a reduction on the critical path) the scale comes from a bound known
 // before the step runs: |o[n]| <= m * colsum, m = max-abs of the operand row (found while the NEXT step's MMAs run),
-// colsum = max_n sum_{k,s} |W[k,s,n]| (tc_colsum_kernel; |phi_s| <= 1).  The row then peaks a few bits below 2^14
+// colsum = max_n sum_{k,s} |W[k,s,n]| (tc_stats_kernel; |phi_s| <= 1).  The row then peaks a few bits below 2^14
 // (the looseness of the bound, never accumulating because m is exact), which costs nothing in fp16 hi/lo.
 //
 // Warp roles (608 threads):

@@ -14,7 +14,7 @@ if not line:
     print("FAILED", out.stderr[-500:])
     sys.exit(1)
 d = json.loads(line[-1])
-k = d["roofline"]["kernel_ms"]
+k = d["roofline"].get("kernel_ms_per_step") or d["roofline"]["kernel_ms"]
 print(f"chi={sys.argv[1]} {sys.argv[2] if len(sys.argv) > 2 else ''} step={d['ms_per_step']:.3f} ms  "
       + "  ".join(f"{n.replace('tc_', '').replace('_kernel', '')}={v:.3f}" for n, v in k.items() if v > 0.05)
       + f"  loss={d['loss']:.6f}")
