@@ -368,7 +368,8 @@ def run_native(args):
     x_dev, t_dev = x_host.to(dev), t_host.to(dev)
     grads = torch.zeros(eng.n_params, dtype=dtype, device=dev)
     denom = B * world
-    reducer = OverlappedAllReduce(dist.group.WORLD, dev) if (world > 1 and not args.no_overlap) else None
+    reducer = (OverlappedAllReduce(dist.group.WORLD, dev, grad_bytes=eng.n_params * grads.element_size())
+               if (world > 1 and not args.no_overlap) else None)
 
     def step_resident():
         if reducer is not None:

@@ -413,7 +413,8 @@ class Model:
         reducer = None
         if group is not None:
             from ..distributed import OverlappedAllReduce
-            reducer = OverlappedAllReduce(group, self._packed.device)
+            reducer = OverlappedAllReduce(group, self._packed.device,
+                                          grad_bytes=self._packed.numel() * self._packed.element_size())
         n_cnt = torch.zeros(1, dtype=torch.float64, device=self._packed.device)
 
         def train_step(params, opt_state, data=None, grad_clip_threshold=None):
