@@ -223,7 +223,9 @@ __device__ __noinline__ void feature_map_generic(const EmbParams<T> &e, const T 
 // Same map with the physical dimension as a compile-time constant: every loop unrolls and phi stays in
 // registers (the tensor-core chain kernel evaluates it once per site and sample inside its epilogue warps).
 // xp == nullptr stands for a padding row (any finite input).
-template <int D, typename T>
+// GENERIC = false: the four headline maps only, no out-of-line call (kernels at their register limit: the register-resident
+// SMPO family; its dispatcher sends the other maps to the shared-memory family).
+template <int D, typename T, bool GENERIC = true>
 __device__ __forceinline__ void embed_site_d(const EmbParams<T> &e, const T *xp, T (&out)[D]) {
   using N = Num<T>;
   const T x = xp ? xp[0] : T(0.5);
@@ -264,7 +266,7 @@ __device__ __forceinline__ void embed_site_d(const EmbParams<T> &e, const T *xp,
       out[s] = pw;
       pw *= x;
     }
-  } else if (e.kind == TNB_EMB_RBF) {
+  } else if (e.kind == TNB_EMB_RBF || !GENERIC) {
 #pragma unroll
     for (int j = 0; j < D; ++j) out[j] = N::exp(-e.gamma * (x - e.centers[j]));
   } else {

@@ -20,6 +20,9 @@ bool rr_smpo_supported(const tnb_problem *p, int need_grad) {
   if (!knobs().rr) return false;
   if (p->kind != TNB_KIND_SMPO || p->dtype != TNB_F32) return false;
   if (p->chi > rr::kN || p->d != 2 || p->n_out > 4) return false;
+  // the four headline feature maps with one scalar per site (the others go through the shared-memory family: this family's VJP
+  // kernel sits at the 255-register limit and an out-of-line feature-map call costs it 15 %)
+  if (p->emb.kind > TNB_EMB_RBF || p->emb.n_in > 1) return false;
   if (p->spacing > 32) return false;  // (phi of a window's sites: one lane per site)
   if (need_grad && bwd_smem(p) > (size_t)kTcSmemMax) return false;  // (the window's gradient accumulator lives in shared memory)
   return true;

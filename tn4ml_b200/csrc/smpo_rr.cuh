@@ -221,7 +221,10 @@ __device__ __forceinline__ void add_aligned(Mat &Z, const Mat &X) {
 // (every warp stages its phi-weighted fragment, the warps then sum disjoint slices of the W slots into the window's
 // accumulator) and go to global memory with one RED per element, window and CTA.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kBwdWarps = 8;
+#ifndef TNB_RR_BWD_WARPS
+#define TNB_RR_BWD_WARPS 8
+#endif
+constexpr int kBwdWarps = TNB_RR_BWD_WARPS;
 
 __device__ __forceinline__ void store_mat(float *dst, const Mat &X, int lane) {
 #pragma unroll
@@ -403,7 +406,7 @@ __device__ __forceinline__ void window_phi(const RrArgs &A, long long b, int w0,
   p0 = p1 = 0.f;
   if (w0 + lane < w1) {
     float ph[2];
-    embed_site_d<2>(A.emb, A.x + ((size_t)b * A.L + w0 + lane) * A.emb.n_in, ph);
+    embed_site_d<2, float, false>(A.emb, A.x + ((size_t)b * A.L + w0 + lane), ph);  // (n_in == 1: rr_smpo_supported)
     p0 = ph[0];
     p1 = ph[1];
   }
@@ -448,7 +451,10 @@ __device__ __forceinline__ void cursor_next(const RrArgs &A, Cursor &c, bool bwd
   else { if (++c.w >= A.nwin) c.done = true; }
 }
 
-constexpr int kFwdWarps = 16;
+#ifndef TNB_RR_FWD_WARPS
+#define TNB_RR_FWD_WARPS 16
+#endif
+constexpr int kFwdWarps = TNB_RR_FWD_WARPS;
 
 template <int DO> __global__ void __launch_bounds__(kFwdWarps * 32, 1) smpo_rr_fwd_kernel(RrArgs A) {
   __shared__ __align__(16) float4 ring[kRingStages * kImgFloat4];
