@@ -80,11 +80,12 @@ struct Img {
   int ex;
 };
 
+// max over the warp of a NON-NEGATIVE float (its bit pattern orders like the value; a NaN comes out on top): one redux.sync
 __device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
-  return v;
+  return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(v)));
 }
+// 2^e for e in [-126, 127] without the ldexpf sequence
+__device__ __forceinline__ float pow2i(int e) { return __int_as_float((e + 127) << 23); }
 
 // split a matrix into its fp16 hi / lo row-fragment image, rescaled so that the largest entry is in [2^13, 2^14)
 __device__ __forceinline__ void split(const Mat &X, Img &P) {
@@ -98,11 +99,10 @@ __device__ __forceinline__ void split(const Mat &X, Img &P) {
   m = warp_max(m);
   // m = f * 2^e with f in [0.5, 1): scale by 2^(14 - e).  (Clamped: products are renormalised at every split, so |14 - e| > 120
   // only occurs for an all-zero or non-finite matrix.)
-  int e = 0;
   const bool ok = m > 0.f && m < 3.0e38f;
-  if (ok) frexpf(m, &e);
+  const int e = ((__float_as_int(m) >> 23) & 0xff) - 126;  // frexp exponent of a normal float (denormals clamp below)
   const int sh = ok ? max(-120, min(120, 14 - e)) : 0;
-  const float fs = ok ? ldexpf(1.f, sh) : 0.f;
+  const float fs = ok ? pow2i(sh) : 0.f;
   P.ex = X.ex - sh;
 #pragma unroll
   for (int i = 0; i < 2; ++i)
@@ -201,7 +201,8 @@ __device__ __forceinline__ void add_aligned(Mat &Z, const Mat &X) {
     return;
   }
   const int e = max(Z.ex, X.ex);
-  const float fz = ldexpf(1.f, max(Z.ex - e, -200)), fx = ldexpf(1.f, max(X.ex - e, -200));
+  const int dz = Z.ex - e, dx = X.ex - e;  // one of them is 0, the other <= 0
+  const float fz = dz < -126 ? 0.f : pow2i(dz), fx = dx < -126 ? 0.f : pow2i(dx);
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -225,6 +226,11 @@ __device__ __forceinline__ void add_aligned(Mat &Z, const Mat &X) {
 #define TNB_RR_BWD_WARPS 8
 #endif
 constexpr int kBwdWarps = TNB_RR_BWD_WARPS;
+
+// four adjacent floats added to global memory with one instruction (16-byte aligned address)
+__device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 __device__ __forceinline__ void store_mat(float *dst, const Mat &X, int lane) {
 #pragma unroll
@@ -272,7 +278,7 @@ __device__ __forceinline__ void load_img(const uint32_t *src, Img &X, int lane) 
 __device__ __forceinline__ void reduce_grad(float *stage, float *acc, const Mat &dM, bool on, float ph0, float ph1, int warp,
                                             int lane) {
   float *mine = stage + warp * 2048;
-  const float f = on ? ldexpf(1.f, max(-126, min(126, dM.ex))) : 0.f;
+  const float f = on ? pow2i(max(-126, min(126, dM.ex))) : 0.f;
   const float f0 = ph0 * f, f1 = ph1 * f;
 #pragma unroll
   for (int i = 0; i < 2; ++i)
@@ -699,25 +705,50 @@ template <int DO> __global__ void __launch_bounds__(kBwdWarps * 32, 1) smpo_rr_b
         if (lane == 0) A.dEexp[b] = dE.ex;
       }
     }
-    // ---- flush the window's gradients: one RED per element, window and CTA ----
+    // ---- flush the window's gradients: one 16-byte RED per four elements, window and CTA.  In the packed layout
+    //      [row][col][s][o] a leg-less site's (col, col + 1) x (s = 0, 1) and an output site's (s, o) quadruple (DO = 2) are
+    //      contiguous; the accumulator holds them as [o][s][fragment element], element q / q + 1 = columns col / col + 1 ----
     __syncthreads();
     const int nsite = w1 - w0;
+    const long long per = (long long)A.chi * A.chi * A.D;
+    const bool vec_ok = (A.chi & 1) == 0;
     for (int idx = 0; idx < nsite; ++idx) {
-      const int site = w0 + idx;
-      const bool has_out = site % A.S == 0;
-      const int nj = has_out ? A.DO : 1;
-      const long long per = (long long)A.chi * A.chi * A.D;
-      const long long nwith = (site + A.S - 1) / A.S;
-      float *g = A.grads + per * (site - nwith) + per * A.DO * nwith;
-      for (int o = 0; o < nj; ++o) {
-        float *acc = wacc + (size_t)(idx == 0 ? o : A.DO + idx - 1) * 2048;
-        for (int e = threadIdx.x; e < 2048; e += blockDim.x) {
-          const int s = e >> 10, fe = e & 1023, reg = fe >> 5, ln = fe & 31;
+      // site w0 is the window's output site; nwith = output sites before this one
+      const long long nwith = w + (idx > 0 ? 1 : 0);
+      float *g = A.grads + per * (w0 + idx - nwith) + per * A.DO * nwith;
+      if (idx == 0 && DO == 2) {
+        float *a0 = wacc, *a1 = wacc + 2048;
+        for (int fe = threadIdx.x; fe < 1024; fe += blockDim.x) {
+          const int reg = fe >> 5, ln = fe & 31;
           const int q = reg & 3, nt = (reg >> 2) & 3, mt = reg >> 4, gg = ln >> 2, tt = ln & 3;
           const int row = 16 * mt + 8 * (q >> 1) + gg, col = 8 * nt + 2 * tt + (q & 1);
-          const float v = acc[e];
-          acc[e] = 0.f;
-          if (row < A.chi && col < A.chi && v != 0.f) atomicAdd(&g[(((size_t)row * A.chi + col) * A.D + s) * nj + o], v);
+          const float v0 = a0[fe], v1 = a1[fe], v2 = a0[1024 + fe], v3 = a1[1024 + fe];  // (s0,o0) (s0,o1) (s1,o0) (s1,o1)
+          a0[fe] = a1[fe] = a0[1024 + fe] = a1[1024 + fe] = 0.f;
+          if (row < A.chi && col < A.chi) red_add_v4(&g[((size_t)row * A.chi + col) * 4], v0, v1, v2, v3);
+        }
+      } else if (idx > 0 && vec_ok) {
+        float *acc = wacc + (size_t)(A.DO + idx - 1) * 2048;
+        for (int pi = threadIdx.x; pi < 512; pi += blockDim.x) {
+          const int ln = pi & 31, r2 = pi >> 5;              // r2 = (mt, nt, q / 2)
+          const int qh = r2 & 1, nt = (r2 >> 1) & 3, mt = r2 >> 3, gg = ln >> 2, tt = ln & 3;
+          const int row = 16 * mt + 8 * qh + gg, col = 8 * nt + 2 * tt;
+          const int fe = (r2 * 2) * 32 + ln;                 // element q = 2 qh (column col); q + 1 (column col + 1) at + 32
+          const float v0 = acc[fe], v1 = acc[1024 + fe], v2 = acc[fe + 32], v3 = acc[1024 + fe + 32];
+          acc[fe] = acc[1024 + fe] = acc[fe + 32] = acc[1024 + fe + 32] = 0.f;
+          if (row < A.chi && col < A.chi) red_add_v4(&g[((size_t)row * A.chi + col) * 2], v0, v1, v2, v3);
+        }
+      } else {
+        const int nj = idx == 0 ? A.DO : 1;
+        for (int o = 0; o < nj; ++o) {
+          float *acc = wacc + (size_t)(idx == 0 ? o : A.DO + idx - 1) * 2048;
+          for (int e = threadIdx.x; e < 2048; e += blockDim.x) {
+            const int sx = e >> 10, fe = e & 1023, reg = fe >> 5, ln = fe & 31;
+            const int q = reg & 3, nt = (reg >> 2) & 3, mt = reg >> 4, gg = ln >> 2, tt = ln & 3;
+            const int row = 16 * mt + 8 * (q >> 1) + gg, col = 8 * nt + 2 * tt + (q & 1);
+            const float v = acc[e];
+            acc[e] = 0.f;
+            if (row < A.chi && col < A.chi && v != 0.f) atomicAdd(&g[(((size_t)row * A.chi + col) * A.D + sx) * nj + o], v);
+          }
         }
       }
     }
