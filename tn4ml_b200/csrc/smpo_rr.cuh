@@ -275,6 +275,8 @@ __device__ __forceinline__ void load_img(const uint32_t *src, Img &X, int lane) 
 
 // Stage phi_s * dM of this warp's sample, reduce over the CTA's warps, add into the window accumulator `acc` ([2][1024]:
 // s, fragment element).  Called by EVERY warp of the CTA (two block barriers); `on` = this warp has something to add.
+// Element order of a staged / accumulated plane: ((mt * 4 + nt) * 32 + lane) * 4 + q  -- a lane's four values of one tile are
+// one 16-byte store, and a lane sums four consecutive elements of the eight slots with 16-byte loads.
 __device__ __forceinline__ void reduce_grad(float *stage, float *acc, const Mat &dM, bool on, float ph0, float ph1, int warp,
                                             int lane) {
   float *mine = stage + warp * 2048;
@@ -283,22 +285,30 @@ __device__ __forceinline__ void reduce_grad(float *stage, float *acc, const Mat 
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < 4; ++j) {
+      float v[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float v = on ? dM.c[i][j][q] : 0.f;
-        mine[((i * 4 + j) * 4 + q) * 32 + lane] = v * f0;
-        mine[1024 + ((i * 4 + j) * 4 + q) * 32 + lane] = v * f1;
-      }
+      for (int q = 0; q < 4; ++q) v[q] = on ? dM.c[i][j][q] : 0.f;
+      float4 *dst = reinterpret_cast<float4 *>(mine + ((i * 4 + j) * 32 + lane) * 4);
+      dst[0] = make_float4(v[0] * f0, v[1] * f0, v[2] * f0, v[3] * f0);
+      dst[256] = make_float4(v[0] * f1, v[1] * f1, v[2] * f1, v[3] * f1);  // plane s = 1: + 1024 floats
+    }
   __syncthreads();
   constexpr int per_warp = 2048 / kBwdWarps;  // elements of the slice a warp sums
+  static_assert(per_warp % 128 == 0, "a warp sums whole rows of 32 float4");
 #pragma unroll
-  for (int i = 0; i < per_warp / 32; ++i) {
-    const int e = warp * per_warp + i * 32 + lane;
-    float v = 0.f;
+  for (int i = 0; i < per_warp / 128; ++i) {
+    const int e = warp * per_warp + i * 128 + lane * 4;
+    float4 v = *reinterpret_cast<const float4 *>(stage + e);
 #pragma unroll
-    for (int w = 0; w < kBwdWarps; ++w) v += stage[w * 2048 + e];
-    acc[e] += v;
+    for (int w = 1; w < kBwdWarps; ++w) {
+      const float4 u = *reinterpret_cast<const float4 *>(stage + w * 2048 + e);
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
+    float4 *a = reinterpret_cast<float4 *>(acc + e);
+    float4 t = *a;
+    t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    *a = t;
   }
   __syncthreads();
 }
@@ -719,8 +729,7 @@ template <int DO> __global__ void __launch_bounds__(kBwdWarps * 32, 1) smpo_rr_b
       if (idx == 0 && DO == 2) {
         float *a0 = wacc, *a1 = wacc + 2048;
         for (int fe = threadIdx.x; fe < 1024; fe += blockDim.x) {
-          const int reg = fe >> 5, ln = fe & 31;
-          const int q = reg & 3, nt = (reg >> 2) & 3, mt = reg >> 4, gg = ln >> 2, tt = ln & 3;
+          const int q = fe & 3, ln = (fe >> 2) & 31, nt = (fe >> 7) & 3, mt = fe >> 9, gg = ln >> 2, tt = ln & 3;
           const int row = 16 * mt + 8 * (q >> 1) + gg, col = 8 * nt + 2 * tt + (q & 1);
           const float v0 = a0[fe], v1 = a1[fe], v2 = a0[1024 + fe], v3 = a1[1024 + fe];  // (s0,o0) (s0,o1) (s1,o0) (s1,o1)
           a0[fe] = a1[fe] = a0[1024 + fe] = a1[1024 + fe] = 0.f;
@@ -729,12 +738,13 @@ template <int DO> __global__ void __launch_bounds__(kBwdWarps * 32, 1) smpo_rr_b
       } else if (idx > 0 && vec_ok) {
         float *acc = wacc + (size_t)(A.DO + idx - 1) * 2048;
         for (int pi = threadIdx.x; pi < 512; pi += blockDim.x) {
-          const int ln = pi & 31, r2 = pi >> 5;              // r2 = (mt, nt, q / 2)
-          const int qh = r2 & 1, nt = (r2 >> 1) & 3, mt = r2 >> 3, gg = ln >> 2, tt = ln & 3;
+          const int fe = pi * 2;                             // elements q = 2 qh (column col) and q + 1 (column col + 1)
+          const int qh = (fe >> 1) & 1, ln = (fe >> 2) & 31, nt = (fe >> 7) & 3, mt = fe >> 9, gg = ln >> 2, tt = ln & 3;
           const int row = 16 * mt + 8 * qh + gg, col = 8 * nt + 2 * tt;
-          const int fe = (r2 * 2) * 32 + ln;                 // element q = 2 qh (column col); q + 1 (column col + 1) at + 32
-          const float v0 = acc[fe], v1 = acc[1024 + fe], v2 = acc[fe + 32], v3 = acc[1024 + fe + 32];
-          acc[fe] = acc[1024 + fe] = acc[fe + 32] = acc[1024 + fe + 32] = 0.f;
+          const float2 p0 = *reinterpret_cast<const float2 *>(acc + fe), p1 = *reinterpret_cast<const float2 *>(acc + 1024 + fe);
+          const float v0 = p0.x, v1 = p1.x, v2 = p0.y, v3 = p1.y;
+          *reinterpret_cast<float2 *>(acc + fe) = make_float2(0.f, 0.f);
+          *reinterpret_cast<float2 *>(acc + 1024 + fe) = make_float2(0.f, 0.f);
           if (row < A.chi && col < A.chi) red_add_v4(&g[((size_t)row * A.chi + col) * 2], v0, v1, v2, v3);
         }
       } else {
@@ -742,8 +752,8 @@ template <int DO> __global__ void __launch_bounds__(kBwdWarps * 32, 1) smpo_rr_b
         for (int o = 0; o < nj; ++o) {
           float *acc = wacc + (size_t)(idx == 0 ? o : A.DO + idx - 1) * 2048;
           for (int e = threadIdx.x; e < 2048; e += blockDim.x) {
-            const int sx = e >> 10, fe = e & 1023, reg = fe >> 5, ln = fe & 31;
-            const int q = reg & 3, nt = (reg >> 2) & 3, mt = reg >> 4, gg = ln >> 2, tt = ln & 3;
+            const int sx = e >> 10, fe = e & 1023;
+            const int q = fe & 3, ln = (fe >> 2) & 31, nt = (fe >> 7) & 3, mt = fe >> 9, gg = ln >> 2, tt = ln & 3;
             const int row = 16 * mt + 8 * (q >> 1) + gg, col = 8 * nt + 2 * tt + (q & 1);
             const float v = acc[e];
             acc[e] = 0.f;
