@@ -263,16 +263,21 @@ MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
     }
   }
   P.total = o;
-  size_t base = ((size_t)P.BT * P.chip + (size_t)2 * P.KT * p->d * P.WS + (size_t)P.BT * p->d +
-                 (size_t)P.BT * p->n_out) * w;
-  P.smem_sweep = base;
-  P.smem_class = base + (size_t)P.BT * P.chip * w;
-  // float64, d = 2, one column group, full 256-thread CTAs: the step GEMM runs as DMMA warp tiles and needs one more
-  // [BT][chip] tile behind everything else (TNB_SIMT_DMMA=0 keeps the FMA loop)
+  // float64, d = 2, one or two column groups, full 256-thread CTAs: the step GEMM runs as DMMA warp tiles and needs one more
+  // [BT][chip] tile behind everything else (TNB_SIMT_DMMA=0 keeps the FMA loop).  With it the environment tile, the weight
+  // segments and the output tile get 4 elements of padding per row (bank conflicts of the fragment loads, mps_simt.cuh).
   const int dmma_knob = knobs().simt_dmma;
-  P.dmma_sweep = P.dmma_class = 0;
-  if (p->dtype == TNB_F64 && p->d == 2 && P.NG <= 2 && P.RB == 4 && P.TN >= 8 && P.NT == 256 && P.KT % 4 == 0 && dmma_knob) {
-    const size_t tile = (size_t)P.BT * P.chip * w, cap = kSimtSmemMax;  // (each kernel only if it still fits)
+  const bool dmma_ok = p->dtype == TNB_F64 && p->d == 2 && P.NG <= 2 && P.RB == 4 && P.TN >= 8 && P.NT == 256 &&
+                       P.KT % 4 == 0 && dmma_knob;
+  for (int pad = dmma_ok ? 4 : 0; pad >= 0; pad -= 4) {
+    P.vst = P.chip + pad;
+    P.wsz = 2 * P.KT * p->d * P.WS + (pad ? 2 * P.KT * P.NG * p->d * 4 : 0);
+    size_t base = ((size_t)P.BT * P.vst + (size_t)P.wsz + (size_t)P.BT * p->d + (size_t)P.BT * p->n_out) * w;
+    P.smem_sweep = base;
+    P.smem_class = base + (size_t)P.BT * P.chip * w;
+    P.dmma_sweep = P.dmma_class = 0;
+    if (!dmma_ok) break;
+    const size_t tile = (size_t)P.BT * P.vst * w, cap = kSimtSmemMax;  // (each kernel only if it still fits)
     if (align_up(P.smem_sweep, 16) + tile <= cap) {
       P.dmma_sweep = (int)align_up(P.smem_sweep, 16);
       P.smem_sweep = P.dmma_sweep + tile;
@@ -281,6 +286,7 @@ MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
       P.dmma_class = (int)align_up(P.smem_class, 16);
       P.smem_class = P.dmma_class + tile;
     }
+    if (pad == 0 || (P.dmma_sweep && (P.dmma_class || P.chip > 128))) break;  // else: retry without the padding
   }
   return P;
 }

@@ -59,7 +59,7 @@ bool deterministic();
 
 // ---- MPS workspace plan --------------------------------------------------------------------------
 struct MpsPlan {
-  int chip, nslab, TN, NG, NT, BT, KT, WS, dmma_sweep, dmma_class;
+  int chip, nslab, TN, NG, NT, BT, KT, WS, dmma_sweep, dmma_class, vst, wsz;
   size_t off_Wn, off_Wt, off_F, off_G, off_exps, off_esum, off_y, off_dy, off_wsimt, total;
   size_t smem_sweep, smem_class;
   int RB;  // register-tile rows of the SIMT sweep / class kernels

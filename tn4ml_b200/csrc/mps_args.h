@@ -20,7 +20,7 @@ static void fill_mps_args(const tnb_problem *p, const MpsPlan &P, long long B, c
   A.y = (T *)(w + P.off_y); A.dy = (T *)(w + P.off_dy);
   A.wq = (T *)(w + P.off_wsimt);
   A.loss = nullptr; A.loss_sum = nullptr; A.out = nullptr; A.out_exp = nullptr;
-  A.stash = 0; A.KT = P.KT; A.TN = P.TN; A.WS = P.WS; A.dmma_sweep = P.dmma_sweep; A.dmma_class = P.dmma_class; A.loss_scale = T(1); A.seed_only = 0;
+  A.stash = 0; A.KT = P.KT; A.TN = P.TN; A.WS = P.WS; A.dmma_sweep = P.dmma_sweep; A.dmma_class = P.dmma_class; A.vst = P.vst; A.wsz = P.wsz; A.loss_scale = T(1); A.seed_only = 0;
 }
 
 }  // namespace tnb

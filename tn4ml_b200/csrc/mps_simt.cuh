@@ -40,6 +40,9 @@ template <typename T> struct MpsArgs {
   int KT, TN;
   int dmma_sweep, dmma_class;  // byte offsets of the DMMA output tile in the sweep / class kernels' shared memory (0: off)
   int WS;        // shared-memory stride of one (k, s) weight row: chip, or NG*TN*4 for float64 (bank-conflict-free pair layout)
+  int vst;       // row stride of the environment tile v_s in shared memory: chip, or chip + 4 when the DMMA step GEMM reads it
+                 // (eight rows at a stride of chip * 8 bytes fall on the same banks: an 8-way conflict on every A fragment)
+  int wsz;       // elements of the weight staging region W_s (two chunk buffers)
   T loss_scale;
   int seed_only;  // adjoint launch: write the seeds G[c], G[c+1] (and dy) only; the chains run elsewhere
 };
@@ -79,14 +82,18 @@ template <> __device__ __forceinline__ void lds_pair<double>(const double *p, do
 // `out_s` in natural column order, from where every thread picks up its (tb, tn) register tile as before.
 template <int NG, int RB, bool ZERO>
 __device__ __forceinline__ void step_gemm_dmma(const double *__restrict__ Wg, int K, int chip, int KT, const double *v_s,
-                                               const double *phi_s, const double *rs_s, int rs_stride, double *W_s,
+                                               int vst, const double *phi_s, const double *rs_s, int rs_stride, double *W_s,
                                                double *out_s, double (&acc)[NG][RB][kRN], int tb, int tn, int TN, int WS) {
   const int tid = threadIdx.x, NT = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int ncg = TN >> 2, wc = warp % ncg, wr = warp / ncg;
   const int R0 = wr * 32, P0 = wc * 16;
   const int GW = TN * 4;          // positions of one column group
-  const int srow = 2 * GW;        // one k-row of one group in shared memory: [s][GW]
+  // shared-memory stride of one (k, s) segment: + 4 elements, so that the four k-rows a B fragment reads (2 segments apart)
+  // start 64 bytes apart instead of on the same banks; the output tile's rows are padded the same way
+  const int GWp = vst > chip ? GW + 4 : GW;
+  const int ost = vst;            // row stride of out_s
+  const int srow = 2 * GWp;       // one k-row of one group in shared memory: [s][GWp]
   const int grow = 2 * WS;        // one k-row in global memory: [s][NG groups][GW]
   const int nchunks = (K + KT - 1) / KT;
   const int pieces = GW / 2;      // 16-byte pieces of one (k, s) segment (a power of two: TN is)
@@ -101,7 +108,7 @@ __device__ __forceinline__ void step_gemm_dmma(const double *__restrict__ Wg, in
       double *dst = W_s + (size_t)(ch & 1) * KT * srow;
       for (int i = tid; i < n16; i += NT) {
         const int seg = i >> pshift, q = i & (pieces - 1);  // seg = k * 2 + s
-        cp_async16(reinterpret_cast<char *>(dst + (size_t)seg * GW) + q * 16,
+        cp_async16(reinterpret_cast<char *>(dst + (size_t)seg * GWp) + q * 16,
                    reinterpret_cast<const char *>(src + (size_t)seg * WS) + q * 16);
       }
       cp_async_commit();
@@ -125,16 +132,16 @@ __device__ __forceinline__ void step_gemm_dmma(const double *__restrict__ Wg, in
       const int k0 = ch * KT;
       const int kt = min(KT, K - k0);
       const double *Wb = W_s + (size_t)(ch & 1) * KT * srow + P0 + g;
-      const double *va = v_s + (size_t)(R0 + g) * chip + k0 + t;
+      const double *va = v_s + (size_t)(R0 + g) * vst + k0 + t;
 #pragma unroll 2
       for (int kk = 0; kk < kt; kk += 4) {
         double a[4], b[2][2];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) a[r] = va[(size_t)(8 * r) * chip + kk];
+        for (int r = 0; r < 4; ++r) a[r] = va[(size_t)(8 * r) * vst + kk];
 #pragma unroll
         for (int q = 0; q < 2; ++q)
 #pragma unroll
-          for (int p = 0; p < 2; ++p) b[p][q] = Wb[(size_t)((kk + t) * 2 + q) * GW + 8 * p];
+          for (int p = 0; p < 2; ++p) b[p][q] = Wb[(size_t)((kk + t) * 2 + q) * GWp + 8 * p];
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -162,7 +169,7 @@ __device__ __forceinline__ void step_gemm_dmma(const double *__restrict__ Wg, in
           double2 o;
           o.x = fma(r0, c[r][p][0][0], r1 * c[r][p][1][0]);
           o.y = fma(r0, c[r][p][0][1], r1 * c[r][p][1][1]);
-          *reinterpret_cast<double2 *>(&out_s[(size_t)row * chip + n]) = o;
+          *reinterpret_cast<double2 *>(&out_s[(size_t)row * ost + n]) = o;
         }
       }
     }
@@ -176,7 +183,7 @@ __device__ __forceinline__ void step_gemm_dmma(const double *__restrict__ Wg, in
       for (int rb = 0; rb < RB; ++rb)
 #pragma unroll
         for (int rn = 0; rn < kRN; ++rn) {
-          const double v = out_s[(size_t)(tb * RB + rb) * chip + n0 + rn];
+          const double v = out_s[(size_t)(tb * RB + rb) * ost + n0 + rn];
           acc[grp][rb][rn] = ZERO ? v : acc[grp][rb][rn] + v;
         }
     }
@@ -189,10 +196,10 @@ template <typename T, int NG, int RB, bool ZERO> struct StepDmma {
 };
 template <int NG, int RB, bool ZERO> struct StepDmma<double, NG, RB, ZERO> {
   static constexpr bool kAvail = NG <= 2;
-  static __device__ __forceinline__ void run(const double *Wg, int K, int chip, int KT, const double *v_s,
+  static __device__ __forceinline__ void run(const double *Wg, int K, int chip, int KT, const double *v_s, int vst,
                                              const double *phi_s, const double *rs_s, int rs_stride, double *W_s,
                                              double *out_s, double (&acc)[NG][RB][kRN], int tb, int tn, int TN, int WS) {
-    step_gemm_dmma<NG, RB, ZERO>(Wg, K, chip, KT, v_s, phi_s, rs_s, rs_stride, W_s, out_s, acc, tb, tn, TN, WS);
+    step_gemm_dmma<NG, RB, ZERO>(Wg, K, chip, KT, v_s, vst, phi_s, rs_s, rs_stride, W_s, out_s, acc, tb, tn, TN, WS);
   }
 };
 
@@ -201,13 +208,13 @@ template <int NG, int RB, bool ZERO> struct StepDmma<double, NG, RB, ZERO> {
 // ZERO: acc is known to be zero on entry (lets the d = 2 fast path drop it from the live registers).
 template <typename T, int NG, int RB, bool ZERO = false>
 __device__ __forceinline__ void step_gemm(const T *__restrict__ Wg, int K, int D, int chip, int KT,
-                                          const T *v_s, const T *phi_s, const T *rs_s, int rs_stride,
+                                          const T *v_s, int vst, const T *phi_s, const T *rs_s, int rs_stride,
                                           T *W_s, T (&acc)[NG][RB][kRN], int tb, int tn, int TN, int WS,
                                           T *out_s = nullptr) {
   if constexpr (StepDmma<T, NG, RB, ZERO>::kAvail) {
     if (out_s != nullptr && D == 2) {
       // (a group's rows are 1/NG of the full rows the buffers were sized for: NG times the k-rows per chunk)
-      StepDmma<T, NG, RB, ZERO>::run(Wg, K, chip, KT * NG, v_s, phi_s, rs_s, rs_stride, W_s, out_s, acc, tb, tn, TN, WS);
+      StepDmma<T, NG, RB, ZERO>::run(Wg, K, chip, KT * NG, v_s, vst, phi_s, rs_s, rs_stride, W_s, out_s, acc, tb, tn, TN, WS);
       return;
     }
   }
@@ -258,13 +265,13 @@ __device__ __forceinline__ void step_gemm(const T *__restrict__ Wg, int K, int D
       // D == 2, one column group: plain v x W products into one accumulator set per physical index (no multiply by phi
       // in the loop; 28 % of the executed instructions were FMAs before), kk unrolled
       if (tn * kRN < chip) {
-        const T *vrow = v_s + (size_t)(tb * RB) * chip + k0;
+        const T *vrow = v_s + (size_t)(tb * RB) * vst + k0;
         const T *wp = Wb + (kPairs ? tn * 2 : tn * kRN);
 #pragma unroll 2
         for (int kk = 0; kk < kt; ++kk) {
           T vv[RB], w0[kRN], w1[kRN];
 #pragma unroll
-          for (int rb = 0; rb < RB; ++rb) vv[rb] = vrow[rb * chip + kk];
+          for (int rb = 0; rb < RB; ++rb) vv[rb] = vrow[rb * vst + kk];
           const T *p0 = wp + (size_t)(2 * kk) * WS, *p1 = p0 + WS;
           if (kPairs) {
             lds_pair<T>(p0, w0[0], w0[1]);
@@ -290,7 +297,7 @@ __device__ __forceinline__ void step_gemm(const T *__restrict__ Wg, int K, int D
     for (int kk = 0; kk < kt; ++kk) {
       T vv[RB];
 #pragma unroll
-      for (int rb = 0; rb < RB; ++rb) vv[rb] = v_s[(tb * RB + rb) * chip + k0 + kk];
+      for (int rb = 0; rb < RB; ++rb) vv[rb] = v_s[(tb * RB + rb) * vst + k0 + kk];
       for (int s = 0; s < D; ++s) {
         T a[RB];
         if (D == 2) {  // the common case keeps rs * phi in registers (one shared-memory load less per row and (k, s))
@@ -356,11 +363,11 @@ __device__ __forceinline__ void load_phi(const MpsArgs<T> &A, long long b0, int 
 
 // copy rows [b0, b0+BT) of an environment into smem (zero beyond the batch)
 template <typename T>
-__device__ __forceinline__ void load_env(const T *env, long long b0, long long B, int BT, int chip, T *dst) {
+__device__ __forceinline__ void load_env(const T *env, long long b0, long long B, int BT, int chip, T *dst, int dstride) {
   for (int i = threadIdx.x; i < BT * chip; i += blockDim.x) {
     int r = i / chip;
     long long b = b0 + r;
-    dst[i] = b < B ? env[(size_t)b * chip + (i - r * chip)] : T(0);
+    dst[r * dstride + (i - r * chip)] = b < B ? env[(size_t)b * chip + (i - r * chip)] : T(0);
   }
 }
 
@@ -375,9 +382,10 @@ __global__ void __launch_bounds__(256, (NG == 1 && RB == 4) ? 2 : 1) mps_sweep_k
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int TN = A.TN, TB = blockDim.x / TN, BT = TB * RB;
   const int chip = A.chip, D = A.D, C = A.C, c = A.c, L = A.L;
+  const int vst = A.vst;
   T *v_s = reinterpret_cast<T *>(smem_raw);
-  T *W_s = v_s + (size_t)BT * chip;
-  T *phi_s = W_s + (size_t)2 * A.KT * D * A.WS;
+  T *W_s = v_s + (size_t)BT * vst;
+  T *phi_s = W_s + (size_t)A.wsz;
   T *dy_s = phi_s + (size_t)BT * D;
   T *out_s = A.dmma_sweep ? reinterpret_cast<T *>(smem_raw + A.dmma_sweep) : nullptr;  // DMMA output tile (float64)
   const int tid = threadIdx.x;
@@ -414,7 +422,7 @@ __global__ void __launch_bounds__(256, (NG == 1 && RB == 4) ? 2 : 1) mps_sweep_k
 #pragma unroll
           for (int rn = 0; rn < kRN; ++rn) {
             T val = acc[g][rb][rn] * sc[rb];
-            v_s[r * chip + n0 + rn] = val;
+            v_s[r * vst + n0 + rn] = val;
             if (env && b < A.B) env[(size_t)b * chip + n0 + rn] = val;
           }
         }
@@ -428,7 +436,7 @@ __global__ void __launch_bounds__(256, (NG == 1 && RB == 4) ? 2 : 1) mps_sweep_k
     for (int i = tid; i < BT * chip; i += blockDim.x) {
       int r = i / chip, n = i - r * chip;
       T val = n == 0 ? T(1) : T(0);
-      v_s[i] = val;
+      v_s[r * vst + n] = val;
       long long b = b0 + r;
       if (env && b < A.B) env[(size_t)b * chip + n] = val;
     }
@@ -454,13 +462,13 @@ __global__ void __launch_bounds__(256, (NG == 1 && RB == 4) ? 2 : 1) mps_sweep_k
       }
       for (int k = 0; k < C; ++k) dy_s[r * C + k] = dyl[k];
     }
-    load_env(mps_fenv(A, half == 0 ? c + 1 : c), b0, A.B, BT, chip, v_s);
+    load_env(mps_fenv(A, half == 0 ? c + 1 : c), b0, A.B, BT, chip, v_s, vst);
     load_phi(A, b0, BT, c, phi_s);
     __syncthreads();
     zero_acc<T, NG, RB>(acc);
     const T *Wc = (half == 0 ? A.Wt : A.Wn) + (size_t)c * chip * D * A.WS;
     for (int k = 0; k < C; ++k)
-      step_gemm<T, NG, RB>(Wc + (size_t)k * chip * D * A.WS, chip, D, chip, A.KT, v_s, phi_s, dy_s + k, C, W_s,
+      step_gemm<T, NG, RB>(Wc + (size_t)k * chip * D * A.WS, chip, D, chip, A.KT, v_s, vst, phi_s, dy_s + k, C, W_s,
                        acc, tb, tn, TN, A.WS, out_s);
     T one[RB];
 #pragma unroll
@@ -476,7 +484,7 @@ __global__ void __launch_bounds__(256, (NG == 1 && RB == 4) ? 2 : 1) mps_sweep_k
     __syncthreads();
     zero_acc<T, NG, RB>(acc);
     const T *W = (transposed ? A.Wt : A.Wn) + (size_t)mps_slab(A, site) * chip * D * A.WS;
-    step_gemm<T, NG, RB, true>(W, chip, D, chip, A.KT, v_s, phi_s, (const T *)nullptr, 0, W_s, acc, tb, tn, TN, A.WS, out_s);
+    step_gemm<T, NG, RB, true>(W, chip, D, chip, A.KT, v_s, vst, phi_s, (const T *)nullptr, 0, W_s, acc, tb, tn, TN, A.WS, out_s);
     T sc[RB];
     if (!adjoint) {
       T m[RB];
@@ -525,9 +533,10 @@ __global__ void __launch_bounds__(256, (NG == 1 && RB == 4) ? 2 : 1) mps_class_k
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int TN = A.TN, TB = blockDim.x / TN, BT = TB * RB;
   const int chip = A.chip, D = A.D, C = A.C, c = A.c;
+  const int vst = A.vst;
   T *v_s = reinterpret_cast<T *>(smem_raw);
-  T *W_s = v_s + (size_t)BT * chip;
-  T *phi_s = W_s + (size_t)2 * A.KT * D * A.WS;
+  T *W_s = v_s + (size_t)BT * vst;
+  T *phi_s = W_s + (size_t)A.wsz;
   T *y_s = phi_s + (size_t)BT * D;
   T *fr_s = y_s + (size_t)BT * C;
   T *out_s = A.dmma_class ? reinterpret_cast<T *>(smem_raw + A.dmma_class) : nullptr;
@@ -536,15 +545,15 @@ __global__ void __launch_bounds__(256, (NG == 1 && RB == 4) ? 2 : 1) mps_class_k
   const int tn = tid % TN, tb = tid / TN;
   const long long b0 = (long long)blockIdx.x * BT;
 
-  load_env(mps_fenv(A, c), b0, A.B, BT, chip, v_s);
-  load_env(mps_fenv(A, c + 1), b0, A.B, BT, chip, fr_s);
+  load_env(mps_fenv(A, c), b0, A.B, BT, chip, v_s, vst);
+  load_env(mps_fenv(A, c + 1), b0, A.B, BT, chip, fr_s, chip);
   load_phi(A, b0, BT, c, phi_s);
   __syncthreads();
   T acc[NG][RB][kRN];
   const T *Wc = A.Wn + (size_t)c * chip * D * A.WS;
   for (int k = 0; k < C; ++k) {
     zero_acc<T, NG, RB>(acc);
-    step_gemm<T, NG, RB, true>(Wc + (size_t)k * chip * D * A.WS, chip, D, chip, A.KT, v_s, phi_s, (const T *)nullptr, 0,
+    step_gemm<T, NG, RB, true>(Wc + (size_t)k * chip * D * A.WS, chip, D, chip, A.KT, v_s, vst, phi_s, (const T *)nullptr, 0,
                      W_s, acc, tb, tn, TN, A.WS, out_s);
 #pragma unroll
     for (int rb = 0; rb < RB; ++rb) {
@@ -628,8 +637,10 @@ template <typename T, int RM> __global__ void __launch_bounds__(256) mps_da_kern
   constexpr int TM = 16 * RM, TR = 64, BK = 16;
   constexpr int UE = BK * TM / 256, VE = BK * TR / 256;  // staged elements per thread and chunk
   constexpr int UROWS = 256 / TM, VROWS = 256 / TR;      // samples covered by one pass of the CTA
-  __shared__ __align__(16) T U_s[BK][TM];
-  __shared__ __align__(16) T V_s[BK][TR];
+  // rows padded by 8 elements: the four k-rows a DMMA fragment load touches (lanes wt = 0 .. 3) would otherwise start on the
+  // same banks (row strides of 1024 / 512 bytes): a 4-way conflict on every operand load of the float64 path
+  __shared__ __align__(16) T U_s[BK][TM + 8];
+  __shared__ __align__(16) T V_s[BK][TR + 8];
   const int site = P.only_site >= 0 ? P.only_site : P.site0 + (int)blockIdx.y;
   const int c = A.c, chip = A.chip, chi = A.chi, D = A.D, C = A.C;
   if (P.only_site < 0 && site == c) return;

@@ -14,7 +14,7 @@ for chi in (sys.argv[1:] or ["32", "64", "128"]):
         print("FAILED", out.stderr[-500:])
         continue
     d = json.loads(line[-1])
-    k = d["roofline"]["kernel_ms"]
+    k = d["roofline"].get("kernel_ms_per_step") or d["roofline"]["kernel_ms"]
     print(f"f64 chi={chi} step={d['ms_per_step']:.2f} ms {d['value']:.0f} samples/s {d['roofline'].get('step_tflops', 0):.2f} TF/s  "
           + "  ".join(f"{n.replace('mps_', '').replace('_kernel', '')}={v:.2f}" for n, v in k.items() if v > 0.05)
           + f"  loss={d['loss']:.9f}")
