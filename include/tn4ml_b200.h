@@ -145,7 +145,10 @@ int tnb_forward(const tnb_problem *prob, int64_t batch, const void *x, const voi
 /* Backward: gradients of  loss_scale * sum_b loss_b  w.r.t. every site tensor, from the
  * environments left in `workspace` by tnb_forward(..., keep_stash=1, ...) on the same
  * arguments.  grads is the packed layout; accumulate != 0 adds to its contents
- * (micro-batching / gradient accumulation), otherwise it is overwritten. */
+ * (micro-batching / gradient accumulation), otherwise it is overwritten.
+ * TNB_KIND_SMPO (whose heads take no targets): `targets`, if not NULL, is a vector of per-sample WEIGHTS w[batch] (dtype) and
+ * the gradient is that of loss_scale * sum_b w_b loss_b -- what a loss that post-processes the per-sample value needs
+ * (SemiSupervisedLoss, tn4ml/metrics.py:209-233: the caller passes dLoss/dLogQuadNorm_b). */
 int tnb_backward(const tnb_problem *prob, int64_t batch, const void *x, const void *targets,
                  const void *params, double loss_scale, void *grads, int32_t accumulate,
                  void *workspace, int64_t workspace_bytes, void *stream);

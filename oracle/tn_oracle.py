@@ -585,6 +585,23 @@ def regulariser(sites4: Sequence[torch.Tensor], kind: str, norm_is_trace: bool =
     raise ValueError(kind)
 
 
+def semisup_per_sample(emb: EmbSpec, x, arrays, spacing: int, y, coef: float = 0.3, norm_is_trace: bool = True):
+    """SemiSupervisedLoss (metrics.py:209-233): m = LogQuadNorm(model, data) + 0.3 LogReLUFrobNorm(model);
+    loss = (y / m + (1 - y) m)^2 per sample, y the target class fraction."""
+    phi = embed_batch(x, emb)
+    lq = head_loss(smpo_sqnorm(phi, arrays, spacing), "logquad")
+    m = lq + coef * regulariser(canon_smpo_sites(arrays, spacing), "log_relu_frob", norm_is_trace)
+    y = y.reshape(-1)
+    return (y / m + (1.0 - y) * m) ** 2
+
+
+def semisup_value_and_grad(emb: EmbSpec, x, arrays, spacing: int, y, coef: float = 0.3, norm_is_trace: bool = True):
+    leaves = [a.detach().clone().requires_grad_(True) for a in arrays]
+    loss = semisup_per_sample(emb, x, leaves, spacing, y, coef, norm_is_trace).mean()
+    grads = torch.autograd.grad(loss, leaves)
+    return loss.detach(), [g.detach() for g in grads]
+
+
 # ----------------------------------------------------------------------------
 # Synthetic problems of the five BASELINE.json configs (SURVEY 8d): framework-neutral DATA generators, shared with
 # bench.py's product arm, live in tn4ml_b200/synthetic.py (no algorithm of the path in there); re-exported here so that

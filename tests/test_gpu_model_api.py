@@ -197,3 +197,33 @@ def test_model_shorter_than_the_data(head, dtype):
     assert torch.allclose(per.double().cpu(), per_ref, rtol=tol * 10, atol=tol * 10)
     with pytest.raises(ValueError):  # metrics.py:49-51: the model must not be longer than the data
         eng.forward(model._packed, x[:, :5].to(dtype), None if t is None else t.to(dtype))
+
+
+@pytest.mark.parametrize("dtype,chi,S", [(torch.float64, 8, 4), (torch.float32, 32, 8), (torch.float32, 12, 1)],
+                         ids=["f64_shared_memory_family", "f32_register_resident_family", "f32_mpo"])
+def test_semi_supervised_loss_matches_oracle(dtype, chi, S):
+    """SemiSupervisedLoss (metrics.py:209-233): per-sample values through evaluate(), and loss + gradient through one plain
+    gradient-descent step of train() (params_new = params - lr * grad), against the oracle's autograd."""
+    L, B, lr = 16, 12, 1e-3
+    arrays = [a.to(dtype) for a in O.make_smpo_arrays(L, chi, 2, 2, S, std=0.2 if chi <= 12 else 0.05, seed=8)]
+    x = O.make_inputs(B, L, seed=9).to(dtype)
+    y = torch.tensor(np.random.default_rng(3).integers(0, 2, size=B), dtype=dtype)
+    cls = T.MatrixProductOperator if S == 1 else T.SpacedMatrixProductOperator
+    model = cls(arrays, dtype=dtype, device="cuda:0", **({} if S == 1 else {"spacing": S}))
+    model.configure(optimizer=T.optim.sgd, loss=M.SemiSupervisedLoss, train_type=T.TrainingType.SUPERVISED,
+                    learning_rate=lr, device=("gpu", 0))
+    emb = O.EmbSpec("trig")
+    arr64 = [a.double() for a in arrays]
+    trace = model._reg_norm_is_trace
+    per_ref = O.semisup_per_sample(emb, x.double(), arr64, S, y.double(), norm_is_trace=trace)
+    per = model.evaluate(x.cpu().numpy(), y.cpu().numpy(), batch_size=5, evaluate_type=T.TrainingType.SUPERVISED,
+                         return_list=True, metric=M.SemiSupervisedLoss, dtype=dtype)
+    tol = 1e-10 if dtype == torch.float64 else 1e-4
+    assert np.allclose(per, per_ref.numpy(), rtol=tol * 10, atol=tol)
+    loss_ref, grads_ref = O.semisup_value_and_grad(emb, x.double(), arr64, S, y.double(), norm_is_trace=trace)
+    hist = model.train(x.cpu().numpy(), targets=y.cpu().numpy(), batch_size=B, epochs=1, dtype=dtype)
+    assert abs(hist["loss"][0] - float(loss_ref)) <= tol * max(1.0, abs(float(loss_ref)))
+    gmax = max(float(g.abs().max()) for g in grads_ref)
+    for a_new, a_old, g in zip(model.arrays, arrays, grads_ref):
+        got = (a_old.double() - a_new.double().cpu()) / lr          # the gradient the step applied
+        assert float((got - g).abs().max()) <= (1e-7 if dtype == torch.float64 else 2e-3) * gmax

@@ -147,6 +147,17 @@ def test_configure_error_behaviour_matches_reference():
             m.configure(train_type=0, device=("gpu", 0))    # model.py:262-266
 
 
+def test_semi_supervised_loss_resolves_to_the_logquad_head_with_a_model_term():
+    """metrics.SemiSupervisedLoss (metrics.py:209-233): LogQuadNorm head + 0.3 LogReLUFrobNorm inside the per-sample value."""
+    m = T.SMPO_initialize(8, spacing=4, device="cpu")
+    e = M.resolve(M.SemiSupervisedLoss, m, 8, 2, True)
+    assert e.head == _lib.HEAD_LOGQUAD and e.semisup == 0.3 and not e.regs
+    from tn4ml_b200.engine import Engine
+    f, dfdm = Engine.semisup_value(torch.tensor([0.5, 2.0]), torch.tensor([1.0, 0.0]), torch.tensor(0.25))
+    assert torch.allclose(f, torch.tensor([(1 / 0.75) ** 2, 2.25 ** 2], dtype=torch.float64))
+    assert torch.allclose(dfdm, torch.tensor([2 * (1 / 0.75) * (-1 / 0.75**2), 2 * 2.25], dtype=torch.float64))
+
+
 def test_sweeps_strategy_host_logic():
     """Sweeps (strategy.py:51-131): pair order of a two-way / one-way sweep, constructor errors, the split of a contracted pair
     (storage-only model on the CPU: prehook / posthook are plain tensor algebra, exact for max_bond = the bond's size)."""

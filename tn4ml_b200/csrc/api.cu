@@ -372,7 +372,8 @@ static int backward_impl(const tnb_problem *p, int64_t batch, const void *x, con
     return mps_simt_backward(p, P, batch, x, targets, loss_scale, grads, accumulate, workspace, st, part, nparts);
   }
   if (part > 0) return 0;  // the double-layer VJP is one kernel over all sites: part 0 computes everything
-  return smpo_backward(p, batch, x, params, loss_scale, grads, accumulate, workspace, workspace_bytes, st);
+  // SMPO / MPO heads take no targets: the `targets` argument carries optional per-sample loss weights [batch] instead
+  return smpo_backward(p, batch, x, params, loss_scale, targets, grads, accumulate, workspace, workspace_bytes, st);
 }
 
 int tnb_backward(const tnb_problem *p, int64_t batch, const void *x, const void *targets, const void *params,

@@ -93,8 +93,8 @@ cudaError_t mps_tc_set_attrs();
 int64_t smpo_workspace_bytes(const tnb_problem *p, long long B, int need_grad);
 int smpo_forward(const tnb_problem *p, long long B, const void *x, const void *params, void *loss, double *loss_sum,
                  void *out, int32_t *out_exp, int keep_stash, void *ws, int64_t ws_bytes, cudaStream_t st);
-int smpo_backward(const tnb_problem *p, long long B, const void *x, const void *params, double loss_scale, void *grads,
-                  int accumulate, void *ws, int64_t ws_bytes, cudaStream_t st);
+int smpo_backward(const tnb_problem *p, long long B, const void *x, const void *params, double loss_scale,
+                  const void *sample_w, void *grads, int accumulate, void *ws, int64_t ws_bytes, cudaStream_t st);
 cudaError_t smpo_set_attrs();
 // register-resident small-bond family (rr.cu): SMPO / MPO, float32, bond <= 32, d = 2
 cudaError_t rr_set_attrs();
@@ -102,8 +102,8 @@ bool rr_smpo_supported(const tnb_problem *p, int need_grad);
 int64_t rr_smpo_workspace_bytes(const tnb_problem *p, long long B, int need_grad);
 int rr_smpo_forward(const tnb_problem *p, long long B, const void *x, const void *params, void *loss, double *loss_sum,
                     void *out, int32_t *out_exp, int keep_stash, void *ws, int64_t ws_bytes, cudaStream_t st);
-int rr_smpo_backward(const tnb_problem *p, long long B, const void *x, const void *params, double loss_scale, void *grads,
-                     int accumulate, void *ws, int64_t ws_bytes, cudaStream_t st);
+int rr_smpo_backward(const tnb_problem *p, long long B, const void *x, const void *params, double loss_scale,
+                     const void *sample_w, void *grads, int accumulate, void *ws, int64_t ws_bytes, cudaStream_t st);
 // Embedding.__call__ for n scalars (mps_simt.cu)
 int embed_launch(const tnb_embedding *emb, int d, int32_t dtype, int64_t n, const void *x, void *phi, cudaStream_t st);
 

@@ -64,7 +64,7 @@ static void fill(const tnb_problem *p, const RrPlan &P, long long B, const void 
   char *w = (char *)ws;
   A.L = p->L; A.chi = p->chi; A.D = p->d; A.DO = p->n_out; A.S = p->spacing; A.nwin = P.nwin; A.head = p->head; A.B = B;
   fill_emb<float>(p->emb, A.emb, p->d);
-  A.x = (const float *)x; A.params = (const float *)params;
+  A.x = (const float *)x; A.params = (const float *)params; A.sw = nullptr;
   A.Estash = (float *)(w + P.off_E); A.Eexp = (int *)(w + P.off_Eexp); A.esum = (int *)(w + P.off_esum);
   A.nm = (float *)(w + P.off_nm);
   A.dEscr = (float *)(w + P.off_dE); A.dEexp = (int *)(w + P.off_dEexp); A.Qscr = (uint32_t *)(w + P.off_Q);
@@ -103,8 +103,8 @@ int rr_smpo_forward(const tnb_problem *p, long long B, const void *x, const void
   return 0;
 }
 
-int rr_smpo_backward(const tnb_problem *p, long long B, const void *x, const void *params, double loss_scale, void *grads,
-                     int accumulate, void *ws, int64_t ws_bytes, cudaStream_t st) {
+int rr_smpo_backward(const tnb_problem *p, long long B, const void *x, const void *params, double loss_scale,
+                     const void *sample_w, void *grads, int accumulate, void *ws, int64_t ws_bytes, cudaStream_t st) {
   RrPlan P = plan_rr(p, B, 1);
   if ((int64_t)P.total > ws_bytes) return fail("workspace too small: need %zu bytes, got %lld", P.total, (long long)ws_bytes);
   RrArgs A;
@@ -112,6 +112,7 @@ int rr_smpo_backward(const tnb_problem *p, long long B, const void *x, const voi
   A.stash = 1;
   A.grads = (float *)grads;
   A.loss_scale = (float)loss_scale;
+  A.sw = (const float *)sample_w;
   if (!accumulate) TNB_CUDA(cudaMemsetAsync(grads, 0, (size_t)tnb_param_count(p) * sizeof(float), st));
   const size_t smem = bwd_smem(p);
   prof_begin(st);

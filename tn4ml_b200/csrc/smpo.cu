@@ -35,18 +35,19 @@ int smpo_forward(const tnb_problem *p, long long B, const void *x, const void *p
   return 0;
 }
 
-int smpo_backward(const tnb_problem *p, long long B, const void *x, const void *params, double loss_scale, void *grads,
-                  int accumulate, void *ws, int64_t ws_bytes, cudaStream_t st) {
-  if (rr_smpo_supported(p, 1)) return rr_smpo_backward(p, B, x, params, loss_scale, grads, accumulate, ws, ws_bytes, st);
+int smpo_backward(const tnb_problem *p, long long B, const void *x, const void *params, double loss_scale,
+                  const void *sample_w, void *grads, int accumulate, void *ws, int64_t ws_bytes, cudaStream_t st) {
+  if (rr_smpo_supported(p, 1))
+    return rr_smpo_backward(p, B, x, params, loss_scale, sample_w, grads, accumulate, ws, ws_bytes, st);
   SmpoPlan P = plan_smpo(p, B, 1);
   if ((int64_t)P.total > ws_bytes) return fail("workspace too small: need %zu bytes, got %lld", P.total, (long long)ws_bytes);
   int rc;
   const char *what = "";
   prof_begin(st);
   if (p->dtype == TNB_F64)
-    rc = smpo_backward_t<double>(p, P, B, x, params, loss_scale, grads, accumulate, ws, st, &what);
+    rc = smpo_backward_t<double>(p, P, B, x, params, loss_scale, sample_w, grads, accumulate, ws, st, &what);
   else
-    rc = smpo_backward_t<float>(p, P, B, x, params, loss_scale, grads, accumulate, ws, st, &what);
+    rc = smpo_backward_t<float>(p, P, B, x, params, loss_scale, sample_w, grads, accumulate, ws, st, &what);
   prof_end("smpo_bwd_kernel", st);
   count_launches(P.launches_bwd);
   if (rc) return fail("%s", what);

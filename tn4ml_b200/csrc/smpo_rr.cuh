@@ -45,6 +45,7 @@ struct RrArgs {
   int *out_exp;
   float *grads;
   float loss_scale;
+  const float *sw;  // [B] per-sample weight of the loss in the VJP (may be null)
   int stash;
   // VJP
   float *dEscr;   // [B][1024] adjoint of the window environment between two windows (fragment image) ...
@@ -616,6 +617,7 @@ template <int DO> __global__ void __launch_bounds__(kBwdWarps * 32, 1) smpo_rr_b
         if (lane == 0) {
           smpo_head<float>(A.head, A.nm[bs], A.esum[bs], &dn);
           dn *= A.loss_scale;
+          if (A.sw) dn *= A.sw[bs];
         }
         dEn.c[0][0][0] = dn;
         dEn.ex = -A.esum[bs];

@@ -34,6 +34,7 @@ template <typename T> struct SmpoArgs {
   int *out_exp;
   T *grads;
   T loss_scale;
+  const T *sw;  // [B] per-sample weight of the loss in the VJP (may be null)
   int stash, SPC, TPS;
 };
 
@@ -517,6 +518,7 @@ template <typename T> __global__ void __launch_bounds__(256) smpo_bwd_kernel(Smp
     if (valid) {
       smpo_head<T>(A.head, A.nm[b], A.esum[b], &dn);
       dn *= A.loss_scale;
+      if (A.sw) dn *= A.sw[b];
     }
     de[0] = dn;
   }
@@ -645,7 +647,7 @@ static void fill_smpo_args(const tnb_problem *p, const SmpoPlan &P, long long B,
   A.Estash = (T *)(w + P.off_E); A.dexp = (int *)(w + P.off_dexp); A.esum = (int *)(w + P.off_esum);
   A.nm = (T *)(w + P.off_nm); A.Qscr = (T *)(w + P.off_Q);
   A.loss = nullptr; A.loss_sum = nullptr; A.out = nullptr; A.out_exp = nullptr; A.grads = nullptr;
-  A.loss_scale = T(1); A.stash = 0; A.SPC = P.SPC; A.TPS = P.TPS;
+  A.loss_scale = T(1); A.sw = nullptr; A.stash = 0; A.SPC = P.SPC; A.TPS = P.TPS;
 }
 
 template <typename T> static cudaError_t smpo_set_attrs_t() {
@@ -672,14 +674,15 @@ static int smpo_forward_t(const tnb_problem *p, const SmpoPlan &P, long long B, 
 
 template <typename T>
 static int smpo_backward_t(const tnb_problem *p, const SmpoPlan &P, long long B, const void *x, const void *params,
-                           double loss_scale, void *grads, int accumulate, void *ws, cudaStream_t st,
-                           const char **what) {
+                           double loss_scale, const void *sample_w, void *grads, int accumulate, void *ws,
+                           cudaStream_t st, const char **what) {
   if (P.SPC < 1) { *what = "bond dimension too large for the SMPO shared-memory plan"; return 1; }
   SmpoArgs<T> A;
   fill_smpo_args<T>(p, P, B, x, params, ws, A);
   A.stash = 1;
   A.grads = (T *)grads;
   A.loss_scale = (T)loss_scale;
+  A.sw = (const T *)sample_w;
   if (!accumulate) {
     long long n = smpo_site_off(p->chi, p->d, p->n_out, p->spacing, p->L);
     cudaError_t e = cudaMemsetAsync(grads, 0, (size_t)n * sizeof(T), st);

@@ -216,6 +216,45 @@ class Engine:
                 reducer.finish()
         return self._loss_sum, grads
 
+    # -- SemiSupervisedLoss (metrics.py:209-233) on the SMPO kernels ---------------------------------------
+    @staticmethod
+    def semisup_value(lq: torch.Tensor, y: torch.Tensor, reg: torch.Tensor):
+        """f = (y / m + (1 - y) m)^2 and df/dm for m = LogQuadNorm_b + reg (all device tensors; y in [0, 1])."""
+        m = lq.double() + reg.double()
+        u = y.double() / m + (1.0 - y.double()) * m
+        return u * u, 2.0 * u * (-y.double() / (m * m) + (1.0 - y.double()))
+
+    def semisup_value_and_grad(self, params: torch.Tensor, x, y, reg: torch.Tensor, *, denom: int, grads: torch.Tensor):
+        """(sum_b f_b, grads += d/dparams of sum_b f_b / denom THROUGH LogQuadNorm_b, sum_b df_b/dm_b): the forward pass returns
+        the per-sample LogQuadNorm, the VJP takes df_b/dm_b as per-sample weights (tnb_backward, TNB_KIND_SMPO).  The part of
+        the gradient that goes through the model-only regulariser is added by the caller (tnb_norm)."""
+        if self.prob.kind != _lib.KIND_SMPO or self.prob.head != _lib.HEAD_LOGQUAD:
+            raise ValueError("SemiSupervisedLoss is defined for SMPO / MPO models (LogQuadNorm inside)")
+        x, _ = self._prep(x, None)
+        B = x.shape[0]
+        y = torch.as_tensor(y).to(self.device, self.dtype).reshape(-1)
+        if y.numel() != B:
+            raise ValueError(f"SemiSupervisedLoss takes one target value per sample, got {tuple(y.shape)} for {B} samples")
+        lq = torch.empty(B, dtype=self.dtype, device=self.device)
+        loss_sum = torch.zeros((), dtype=torch.float64, device=self.device)
+        wsum = torch.zeros((), dtype=torch.float64, device=self.device)
+        mb = self.microbatch(B, True)
+        with torch.cuda.device(self.device):
+            for s in range(0, B, mb):
+                e = min(B, s + mb)
+                ws = self._workspace(e - s, True)
+                _lib.check(self.lib.tnb_forward(
+                    C.byref(self.prob), e - s, x[s:e].data_ptr(), None, params.data_ptr(), lq[s:e].data_ptr(), None, None,
+                    None, 1, ws.data_ptr(), ws.numel(), self._stream()))
+                f, dfdm = self.semisup_value(lq[s:e], y[s:e], reg)
+                w = dfdm.to(self.dtype).contiguous()
+                _lib.check(self.lib.tnb_backward(
+                    C.byref(self.prob), e - s, x[s:e].data_ptr(), w.data_ptr(), params.data_ptr(), 1.0 / denom,
+                    grads.data_ptr(), 1, ws.data_ptr(), ws.numel(), self._stream()))
+                loss_sum += f.sum()
+                wsum += dfdm.sum()
+        return loss_sum, grads, wsum
+
     # -- Sweeps strategy: loss and the gradient with respect to a merged pair of sites --------------------
     def pair_value_and_grad(self, params: torch.Tensor, x, targets, site: int, *, denom: int | None = None):
         """(sum_b loss_b as a device float64 scalar, dT [chi, chi, d, d, n_k]): the gradient of sum_b loss_b / denom with

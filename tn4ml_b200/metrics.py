@@ -65,13 +65,14 @@ class LossExpr:
     head: int
     class_weights: tuple | None = None
     regs: list = field(default_factory=list)
+    semisup: float | None = None  # SemiSupervisedLoss: coefficient of LogReLUFrobNorm inside the per-sample value
 
     def mean(self, *a, **k):  # the per-sample loss is a scalar: .mean() is the identity
         return self
 
     def __add__(self, other):
         if isinstance(other, RegExpr):
-            return LossExpr(self.head, self.class_weights, self.regs + [other])
+            return LossExpr(self.head, self.class_weights, self.regs + [other], self.semisup)
         if isinstance(other, (int, float)) and other == 0:
             return self
         return NotImplemented
@@ -112,6 +113,14 @@ def QuadNorm(model, data):  # noqa: N802
     """(TSN - 1)^2  (metrics.py:190-206)."""
     _check_lengths(model, data)
     return LossExpr(_lib.HEAD_QUAD)
+
+
+def SemiSupervisedLoss(model, data, y_true, **_kwargs):  # noqa: N802
+    """(y / m + (1 - y) m)^2 with m = LogQuadNorm(model, data) + 0.3 LogReLUFrobNorm(model), y the target class fraction
+    (metrics.py:209-233).  The per-sample LogQuadNorm and its gradient come from the SMPO kernels (the VJP takes the
+    per-sample factor dLoss/dm as a weight); the regulariser from the transfer-matrix kernels."""
+    _check_lengths(model, data)
+    return LossExpr(_lib.HEAD_LOGQUAD, semisup=0.3)
 
 
 def CrossEntropySoftmax(model, data, targets):  # noqa: N802

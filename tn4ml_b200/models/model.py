@@ -385,6 +385,8 @@ class Model:
             expr = resolve(loss_fn, self, self.L, embedding.dim, supervised)
         # keyed on the CONTENTS of the feature-map spec (id() of a temporary embedding is reused by CPython)
         key = (bytes(spec_of(embedding)), None if expr is None else (expr.head, expr.class_weights), dt, self.precision)
+        if expr is not None and expr.semisup is not None and self.kind != _lib.KIND_SMPO:
+            raise ValueError("SemiSupervisedLoss is defined for SpacedMatrixProductOperator / MatrixProductOperator models")
         eng = self._engine_cache.get(key)
         if eng is None:
             eng = Engine(kind=self.kind, L=self.L, chi=self.chi, d=self.phys_dim, n_out=self.n_out,
@@ -417,13 +419,27 @@ class Model:
                                           grad_bytes=self._packed.numel() * self._packed.element_size())
         n_cnt = torch.zeros(1, dtype=torch.float64, device=self._packed.device)
 
+        semisup = expr.semisup if expr is not None else None
+        if semisup is not None and group is not None:
+            raise NotImplementedError("SemiSupervisedLoss is single-device here")
+
         def train_step(params, opt_state, data=None, grad_clip_threshold=None):
             if isinstance(data, tuple) and len(data) == 2:
                 x, t = data
             else:
                 x, t = data, None
             n_local = x.shape[0]
-            if group is None:
+            if semisup is not None:
+                # metrics.py:209-233: the per-sample value depends on the model-only term too, so the regulariser's gradient
+                # enters with the batch sum of df/dm as its coefficient (one host read of that sum per step)
+                from ..metrics import RegExpr
+                _, reg = self._log2_norm2([RegExpr("log_relu_frob", semisup)])
+                grads.zero_()
+                loss_sum, g, wsum = eng.semisup_value_and_grad(self._packed, x, t, reg, denom=n_local, grads=grads)
+                self._log2_norm2([RegExpr("log_relu_frob", semisup * float(wsum.item()) / n_local)], grads=g)
+                loss = loss_sum / n_local
+                gscale = 1.0
+            elif group is None:
                 loss_sum, g = eng.value_and_grad(self._packed, x, t, denom=n_local, grads=grads)
                 loss = loss_sum / n_local
                 gscale = 1.0
@@ -637,7 +653,12 @@ class Model:
         for batch_data in _batch_iterator(inputs, targets if supervised else None, batch_size, dtype=self.dtype,
                                           shuffle=shuffle, seed=seed, alternate_flip=alternate_flip):
             x, y = batch_data if isinstance(batch_data, tuple) else (batch_data, None)
-            per, _, _ = eng.forward(self._packed, x, y)
+            per, _, _ = eng.forward(self._packed, x, None if (expr is not None and expr.semisup is not None) else y)
+            if expr is not None and expr.semisup is not None:  # SemiSupervisedLoss: the per-sample LogQuadNorm is post-processed
+                from ..metrics import RegExpr
+                _, reg = self._log2_norm2([RegExpr("log_relu_frob", expr.semisup)])
+                yv = torch.as_tensor(y).to(per.device, per.dtype).reshape(-1)
+                per = eng.semisup_value(per, yv, reg)[0].to(per.dtype)
             losses.append(per)
             nb += 1
         if nb == 0:
