@@ -149,7 +149,7 @@ def test_configure_error_behaviour_matches_reference():
 
 def test_semi_supervised_loss_resolves_to_the_logquad_head_with_a_model_term():
     """metrics.SemiSupervisedLoss (metrics.py:209-233): LogQuadNorm head + 0.3 LogReLUFrobNorm inside the per-sample value."""
-    m = T.SMPO_initialize(8, spacing=4, device="cpu")
+    m = T.SMPO_initialize(8, randn(0.1), 1, spacing=4, device="cpu")
     e = M.resolve(M.SemiSupervisedLoss, m, 8, 2, True)
     assert e.head == _lib.HEAD_LOGQUAD and e.semisup == 0.3 and not e.regs
     from tn4ml_b200.engine import Engine
@@ -169,7 +169,7 @@ def test_sweeps_strategy_host_logic():
     with pytest.raises(ValueError):
         T.Sweeps(grouping=3)
     with pytest.raises(TypeError):
-        list(T.Sweeps().iterate_sites(T.SMPO_initialize(6, spacing=2, device="cpu")))
+        list(T.Sweeps().iterate_sites(T.SMPO_initialize(6, randn(0.1), 1, spacing=2, device="cpu")))
     x = torch.rand(3, 5, dtype=m.dtype)
     prob = O.Problem("mps", O.EmbSpec("trig"), "nll")
     before = O.per_sample_loss(prob, x.double(), [a.double() for a in m.arrays])
