@@ -18,7 +18,10 @@ static void fill_tc_args(const MpsPlan &P, void *ws, const MpsArgs<float> &M, Tc
   T.dbg = knobs().tc_dbg;
 #endif
   T.colsum = (const float *)(w + P.off_cs);
-  T.pace_ns = knobs().tc_pace_ns >= 0 ? knobs().tc_pace_ns : P.tc_N * 2 / 5;
+  // stash writer: pause between pieces.  N = 512 accumulator columns (chi = 256, d = 2): every unpaced variant starved the weight
+  // loads; N <= 256: the writer serves the CTA's two tiles one after the other and any pause puts it on the step's path
+  // (chi = 128: chain kernels 6.75 / 7.10 -> 5.9 / 6.6 ms without it)
+  T.pace_ns = knobs().tc_pace_ns >= 0 ? knobs().tc_pace_ns : (P.tc_N > 256 ? P.tc_N * 2 / 5 : 0);
   T.wq = (float *)(w + P.off_wq);
   T.qmax = (int *)(w + P.off_qmax);
   T.wqc = (float *)(w + P.off_wqc);
