@@ -3,7 +3,9 @@
 TEST INFRASTRUCTURE ONLY -- see ``oracle/__init__.py``.  PINNED by golden vectors produced by executing the reference's own
 source (tools/make_reference_golden.py over the stand-ins in tools/ref_shim; tests/test_reference_golden.py): feature maps,
 embed()'s normaliser, MPS / classifier index conventions, every MPS loss head and finite differences of the executed loss.
-Not pinned that way: the SMPO apply_mps path (too deep into quimb to stand in for; checked by dense contraction instead).
+The SMPO double layer is pinned through the reference's SpacedMatrixProductOperator constructor and its metrics' len(model) <
+len(data) branch (same network, contracted by index names); apply_mps's own array bookkeeping is not executed (it depends on
+quimb's internal index order).
 
 Every function cites the reference file:line (relative to /root/reference) it
 restates.  Arithmetic is torch on the CPU (float64 unless a dtype is passed);

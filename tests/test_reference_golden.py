@@ -127,3 +127,33 @@ def test_classifier_outputs_match_the_reference_source():
     ratio = out / z["outputs"]
     assert ratio.min() > 0 and np.allclose(ratio, ratio.mean(), rtol=1e-10)
     assert int(z["class_site"]) == O.canon_mps_sites(arrays)[1]
+
+
+@pytest.mark.parametrize("name", ["s2", "s4_lastout"])
+def test_smpo_double_layer_matches_the_reference_source(name):
+    """SpacedMatrixProductOperator built by the reference's constructor: <v|v> of the network TransformedSquaredNorm is defined
+    on, and TransformedSquaredNorm / LogQuadNorm / QuadNorm executed from metrics.py through its len(model) < len(data) branch (the
+    extra feature's site is summed over its physical index: a known factor on <v|v>); gradients by finite differences."""
+    z = np.load(os.path.join(G, "reference_smpo.npz"))
+    L, Sp = int(z[f"{name}_L"]), int(z[f"{name}_spacing"])
+    arrays = [torch.tensor(z[f"{name}_site{i}"]) for i in range(L)]
+    x = torch.tensor(z[f"{name}_x"])
+    emb = O.EmbSpec("trig")
+    n = O.smpo_sqnorm(O.embed_batch(x[:, :L], emb), arrays, Sp)
+    assert np.allclose(n.numpy(), z[f"{name}_n_dense"], rtol=1e-12)
+    assert np.allclose(O.per_sample_loss(O.Problem("smpo", emb, "tsn", spacing=Sp), x[:, :L], arrays).numpy(),
+                       z[f"{name}_n_dense"] ** 2, rtol=1e-12)
+    extra = O.feature_map(x[:, L], emb).sum(-1) ** 2          # the site beyond the model, summed over its physical index
+
+    def heads(arrs):
+        nn = O.smpo_sqnorm(O.embed_batch(x[:, :L], emb), arrs, Sp) * extra
+        return {"tsn": O.head_loss(nn, "tsn"), "lqn": O.head_loss(nn, "logquad"), "qn": O.head_loss(nn, "quad")}
+
+    h = heads(arrays)
+    for k in ("tsn", "lqn", "qn"):
+        assert np.allclose(h[k].numpy(), z[f"{name}_{k}_long"], rtol=1e-11), k
+    leaves = [a.clone().requires_grad_(True) for a in arrays]
+    grads = torch.autograd.grad(heads(leaves)["lqn"].mean(), leaves)
+    for (s, k), g in zip(z[f"{name}_fd_index"], z[f"{name}_fd_grad"]):
+        mine = float(grads[int(s)].reshape(-1)[int(k)])
+        assert abs(mine - g) <= 1e-6 * max(1.0, abs(g)), (int(s), int(k), mine, g)

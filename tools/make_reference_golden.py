@@ -13,6 +13,9 @@ For every case the script stores the inputs and what the reference code returned
   reference_classifier.npz   OptaxWrapper(optax.softmax_cross_entropy), CrossEntropySoftmax-style heads, MeanSquaredError,
                              CrossEntropyWeighted on a classifier built by the reference's MPS_initialize(arrays=...,
                              class_index=...) (mps.py:296-330 index naming) -- metrics.py:291-333, 336-396, 423-532
+  reference_smpo.npz         tn4ml.models.smpo.SpacedMatrixProductOperator(arrays) (constructor conventions, smpo.py:61-206) with
+                             <v|v> by generic contraction and TransformedSquaredNorm / LogQuadNorm / QuadNorm executed through the
+                             reference's len(model) < len(data) branch (metrics.py:56-81, 171-206)
   + central finite differences of the reference-executed mean loss with respect to a few site-tensor entries (the shim has no
     autodiff), which pin value_and_grad (model.py:554-566) entry by entry.
 
@@ -155,6 +158,53 @@ def _finite_differences(f, arrays, seed, n=10, h=1e-5):
     return np.array(idx), np.array(grads)
 
 
+def smpo_file():
+    """SMPO double layer (BASELINE configs[2]'s model): the reference's SpacedMatrixProductOperator constructor (axis orders
+    rud / lru / lrud / lu(d), spacing detection, index names -- smpo.py:61-206) and its metrics executed from source.
+
+      n_dense       <v|v> with v = (model & embed(x)) ^ all: the network TransformedSquaredNorm is defined on, contracted by
+                    the stand-in's generic contraction (no hot-path knowledge)
+      tsn / lqn / qn_long   TransformedSquaredNorm / LogQuadNorm / QuadNorm of the reference (metrics.py:56-81, 171-206) on data
+                    with ONE more feature than the model has sites: that takes the reference's `len(model) < len(data)` branch,
+                    which contracts the same network through `model.H & data` + `contract_ind` and leaves the extra site summed
+                    over its physical index (a factor (sum_s phi_s(x_L))^2 on <v|v>).  The equal-length branch goes through
+                    apply_mps, whose array bookkeeping depends on quimb's internal index ordering and is NOT reproduced by the
+                    stand-in (tools/ref_shim/README.md).
+      fd_*          central finite differences of the reference-executed mean LogQuadNorm."""
+    import tn4ml.models.smpo as RSMPO
+    phi = RE.TrigonometricEmbedding(k=1)
+    out = {}
+    for name, (L, Sp, chi, do) in {"s2": (6, 2, 3, 2), "s4_lastout": (9, 4, 4, 3)}.items():
+        arrays = [a.numpy() for a in S.make_smpo_arrays(L, chi, 2, do, Sp, std=0.3, seed=8)]
+        x = 1.0 - np.random.default_rng(17).random((4, L + 1))
+
+        def build(arrs):
+            return RSMPO.SpacedMatrixProductOperator([np.array(a) for a in arrs])
+
+        model = build(arrays)
+        assert model.spacing == Sp
+        n_dense = []
+        for xb in x:
+            v = (model & RE.embed(xb[:L], phi)) ^ all
+            n_dense.append(float((np.asarray(v.data) ** 2).sum()))
+
+        def metric(fn, arrs):
+            m = build(arrs)
+            return np.array([float(fn(m, RE.embed(xb, phi))) for xb in x])
+
+        out[f"{name}_L"], out[f"{name}_spacing"], out[f"{name}_chi"], out[f"{name}_do"] = L, Sp, chi, do
+        out[f"{name}_x"] = x
+        out[f"{name}_n_dense"] = np.array(n_dense)
+        out[f"{name}_tsn_long"] = metric(RM.TransformedSquaredNorm, arrays)
+        out[f"{name}_lqn_long"] = metric(RM.LogQuadNorm, arrays)
+        out[f"{name}_qn_long"] = metric(RM.QuadNorm, arrays)
+        fd = _finite_differences(lambda arrs: metric(RM.LogQuadNorm, arrs).mean(), arrays, seed=9, n=8)
+        out[f"{name}_fd_index"], out[f"{name}_fd_grad"] = fd
+        out.update({f"{name}_site{i}": a for i, a in enumerate(arrays)})
+    np.savez_compressed(os.path.join(OUT, "reference_smpo.npz"), **out)
+    return out
+
+
 def classifier_file():
     L, chi, d, C, B, cls = 7, 4, 2, 3, 5, 3  # class tensor at 0-based site 3 == class_index 4 (1-based, mps.py:183-213)
     arrays = [a.numpy() for a in S.make_mps_arrays(L, chi, d, class_site=cls, C=C, std=0.2, seed=21)]
@@ -203,5 +253,7 @@ if __name__ == "__main__":
     m = embeddings_more_file()
     print("more embeddings:", sorted(k for k in m if k.startswith("phi_")), m["nll_hermite_d2"], m["nll_arrays_n3"])
     print("nll per sample:", mps_nll_file())
+    sm = smpo_file()
+    print("smpo:", {k: v for k, v in sm.items() if k.endswith("_n_dense") or k.endswith("_lqn_long")})
     c = classifier_file()
     print("classifier:", {k: v for k, v in c.items() if k.startswith("loss_")})

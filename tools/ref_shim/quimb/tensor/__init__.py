@@ -191,7 +191,16 @@ class TensorNetwork:
     H = property(conj)
 
     def _combine(self, other, virtual):
-        others = other.tensors if isinstance(other, TensorNetwork) else [other]
+        if isinstance(other, TensorNetwork):
+            # quimb (check_collisions): inner indices of the second network that are also inner indices of the first are
+            # renamed -- so that `tn.H & tn` is the overlap and not a sum over four-fold repeated bonds
+            clash = set(self.inner_inds()) & set(other.inner_inds())
+            if clash:
+                other = other.copy()
+                other.reindex({i: rand_uuid() for i in clash}, inplace=True)
+            others = other.tensors
+        else:
+            others = [other]
         return TensorNetwork(list(self._tensors) + list(others), virtual=virtual)
 
     def __and__(self, other):
@@ -222,6 +231,11 @@ class TensorNetwork:
         raise NotImplementedError("only `^ all` is supported by the stand-in")
 
     def contract_ind(self, ind, **_kw):
+        if isinstance(ind, (list, tuple)):  # several indices: the tensors carrying any of them are contracted together
+            for i in ind:
+                if i in self.ind_map():
+                    self.contract_ind(i)
+            return
         ks = self.ind_map().get(ind, [])
         if len(ks) == 1:  # an outer index: quimb contracts the tensor with output_inds = its other indices, i.e. sums over it
             t = self._tensors[ks[0]]
@@ -347,7 +361,37 @@ class TensorNetwork1DVector(TensorNetwork1D):
 
 
 class TensorNetwork1DOperator(TensorNetwork1D):
-    pass
+    """Upper / lower site indices named by format strings; assigning a new format string renames the indices (quimb's
+    documented behaviour of `upper_ind_id` / `lower_ind_id`)."""
+    _NDIMS = 1
+
+    def upper_ind(self, i):
+        return self._upper_ind_id.format(i)
+
+    def lower_ind(self, i):
+        return self._lower_ind_id.format(i)
+
+    def _rename(self, old_id, new_id):
+        if old_id == new_id:
+            return
+        self.reindex({old_id.format(i): new_id.format(i) for i in range(self._L)}, inplace=True)
+
+    def _get_upper(self):
+        return self._upper_ind_id
+
+    def _set_upper(self, new):
+        self._rename(self._upper_ind_id, new)
+        self._upper_ind_id = new
+
+    def _get_lower(self):
+        return self._lower_ind_id
+
+    def _set_lower(self, new):
+        self._rename(self._lower_ind_id, new)
+        self._lower_ind_id = new
+
+    upper_ind_id = property(_get_upper, _set_upper)
+    lower_ind_id = property(_get_lower, _set_lower)
 
 
 class TensorNetwork1DFlat(TensorNetwork1D):
@@ -408,3 +452,10 @@ for _name in ("TensorNetwork1D", "TensorNetwork1DVector", "TensorNetwork1DOperat
               "MatrixProductOperator", "TensorNetwork"):
     setattr(tensor_1d, _name, globals()[_name])
 tensor_arbgeom.get_coordinate_formatter = lambda ndims: "{}"
+
+
+class _ArrayOps:
+    ndim = staticmethod(np.ndim)
+
+
+array_ops = _ArrayOps()
