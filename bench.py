@@ -281,6 +281,69 @@ def quick_point(args, chi, dtype, dev, steps=10, batch=None, microbatch=0):
     return out
 
 
+def other_configs(dev):
+    """Device-resident fwd+bwd throughput of the other BASELINE.json configs (the parity-test cases of the contract; quoted here
+    so that the driver's record holds them too): cfg 2 (MPS classifier, polynomial d = 3, chi = 32), cfg 3 (SMPO L = 784,
+    spacing 8, chi = 32, batch 4096; float32 and the reference's float64), cfg 4 (MPS NLL, Fourier d = 8, chi = 64)."""
+    import tn4ml_b200 as T
+    from tn4ml_b200 import metrics as M, synthetic as S
+    res = {}
+
+    def timed(eng, model, x, t, B, flops, steps):
+        g = torch.zeros(eng.n_params, dtype=model.dtype, device=dev)
+        for _ in range(3):
+            eng.value_and_grad(model._packed, x, t, grads=g)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            eng.value_and_grad(model._packed, x, t, grads=g)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        return {"samples_per_s": B / ms * 1e3, "ms_per_step": ms, "tflops": flops * B / ms / 1e9, "steps": steps, "batch": B}
+
+    rng = np.random.default_rng(1)
+    for name, dtype, steps in (("cfg3_smpo_f32", torch.float32, 10), ("cfg3_smpo_f64", torch.float64, 3)):
+        try:
+            L, Sp, chi, B = 784, 8, 32, 4096
+            model = T.SpacedMatrixProductOperator(S.make_smpo_arrays(L, chi, 2, 2, Sp, std=1e-2, seed=42, dtype=dtype), spacing=Sp,
+                                                  dtype=dtype, device=dev)
+            eng, _ = model._engine(T.TrigonometricEmbedding(), M.LogQuadNorm, False, dtype)
+            x = torch.from_numpy(1.0 - rng.random((B, L))).to(dev, dtype)
+            w = (Sp - 2) * 2 * chi**3 + 2 * chi**3 * 2 + 4 * chi**3 * 2 + Sp * 2 * chi**2 * 2 + 2 * chi**2 * 2
+            res[name] = timed(eng, model, x, None, B, 3 * (L // Sp) * w, steps)
+            del eng, model, x
+        except Exception as exc:  # pragma: no cover
+            res[name] = {"error": str(exc)[:200]}
+        torch.cuda.empty_cache()
+    try:
+        L, chi, d, B = 16, 64, 8, 65536
+        model = T.MatrixProductState(S.make_mps_arrays(L, chi, d, std=1e-2, seed=42, dtype=torch.float32, squeeze_ends=True,
+                                                       identity_all=True), dtype=torch.float32, device=dev)
+        eng, _ = model._engine(T.FourierEmbedding(p=8), M.NegLogLikelihood, False, torch.float32)
+        x = torch.from_numpy(1.0 - rng.random((B, L))).to(dev, torch.float32)
+        res["cfg4_nll_fourier_f32"] = timed(eng, model, x, None, B, flops_per_sample(L, chi, d, 1, L - 1), 20)
+        del eng, model, x
+    except Exception as exc:  # pragma: no cover
+        res["cfg4_nll_fourier_f32"] = {"error": str(exc)[:200]}
+    torch.cuda.empty_cache()
+    try:
+        L, chi, d, C, B = 30, 32, 3, 2, 65536
+        model = T.TensorNetwork(S.make_mps_arrays(L, chi, d, class_site=14, C=C, std=1e-2, seed=42, dtype=torch.float32),
+                                dtype=torch.float32, device=dev)
+        eng, _ = model._engine(T.PolynomialEmbedding(degree=2, n=1, include_bias=True), M.CrossEntropyWeighted([0.7, 1.6]), True,
+                               torch.float32)
+        x = torch.from_numpy(1.0 - rng.random((B, L))).to(dev, torch.float32)
+        t = torch.nn.functional.one_hot(torch.from_numpy(rng.integers(0, C, size=B)), C).to(dev, torch.float32)
+        res["cfg2_poly_classifier_f32"] = timed(eng, model, x, t, B, flops_per_sample(L, chi, d, C, 14), 20)
+        del eng, model, x, t
+    except Exception as exc:  # pragma: no cover
+        res["cfg2_poly_classifier_f32"] = {"error": str(exc)[:200]}
+    torch.cuda.empty_cache()
+    return res
+
+
 def parity_check(args, eng, model, emb, loss_fn, x_dev, t_dev, dtype, n=256):
     """Ties the perf line to correctness: the oracle (float64, CPU) on the first `n` samples of the timed batch against the
     same kernels on the same samples -- per-sample losses and every site gradient.  Runs after the timed regions."""
@@ -535,6 +598,13 @@ def run_native(args):
                 except Exception as exc:  # pragma: no cover
                     sweep[f"f64_chi{chi2}"] = {"error": str(exc)[:200]}
 
+    others = None
+    if rank == 0 and world == 1 and not args.no_chi_sweep:
+        try:
+            others = other_configs(dev)
+        except Exception as exc:  # pragma: no cover
+            others = {"error": str(exc)[:200]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -562,7 +632,7 @@ def run_native(args):
                     "includes": "H2D of x and targets from pinned memory (double-buffered on a copy stream), value_and_grad, "
                                 "all-reduce, Adam update, loss D2H"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "parity": parity, "chi_sweep": sweep,
+            "parity": parity, "chi_sweep": sweep, "other_configs": others,
             "loss": lval,
         }
         print(json.dumps(line), flush=True)
