@@ -280,3 +280,24 @@ def test_mps_classifier_parity_f64_tensor_pipe(case):
     prob = O.Problem("mps", O.EmbSpec("trig"), "softmax_xent")
     model = T.TensorNetwork(arrays, dtype=torch.float64, device="cuda:0")
     _check(model, prob, _heads()["softmax_xent"], x, arrays, t, torch.float64)
+
+
+@pytest.mark.parametrize("case", [
+    dict(L=6, chi=32, d=3, cls=2, C=2, B=9700, emb=O.EmbSpec("poly", degree=2, include_bias=True)),   # cfg 2's map: odd d
+    dict(L=5, chi=64, d=8, cls=None, C=1, B=9600, emb=O.EmbSpec("fourier", p=8)),                     # cfg 4's map
+    dict(L=5, chi=136, d=4, cls=1, C=3, B=4900, emb=O.EmbSpec("trig", k=2)),                          # two column groups
+], ids=["d3_chi32", "d8_chi64", "d4_chi136"])
+def test_f64_tensor_pipe_general_physical_dimension(case):
+    """float64 step GEMM on DMMA for d != 2: one pass per pair of physical indices (an odd d ends with a single one), full
+    256-thread CTAs -- same 1e-10 bar."""
+    import tn4ml_b200 as T
+    if case["cls"] is None:
+        arrays = O.make_mps_arrays(case["L"], case["chi"], case["d"], std=0.05, seed=4, squeeze_ends=True, identity_all=True)
+        t, head = None, "nll"
+        model = T.MatrixProductState(arrays, dtype=torch.float64, device="cuda:0")
+    else:
+        arrays = O.make_mps_arrays(case["L"], case["chi"], case["d"], class_site=case["cls"], C=case["C"], std=0.1, seed=11)
+        t, head = O.make_labels(case["B"], case["C"]), "softmax_xent"
+        model = T.TensorNetwork(arrays, dtype=torch.float64, device="cuda:0")
+    x = O.make_inputs(case["B"], case["L"], seed=12)
+    _check(model, O.Problem("mps", case["emb"], head), _heads()[head], x, arrays, t, torch.float64)

@@ -267,8 +267,8 @@ MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
   // [BT][chip] tile behind everything else (TNB_SIMT_DMMA=0 keeps the FMA loop).  With it the environment tile, the weight
   // segments and the output tile get 4 elements of padding per row (bank conflicts of the fragment loads, mps_simt.cuh).
   const int dmma_knob = knobs().simt_dmma;
-  const bool dmma_ok = p->dtype == TNB_F64 && p->d == 2 && P.NG <= 2 && P.RB == 4 && P.TN >= 8 && P.NT == 256 &&
-                       P.KT % 4 == 0 && dmma_knob;
+  const bool dmma_ok = p->dtype == TNB_F64 && p->d >= 2 && P.NG <= 2 && P.RB == 4 && P.TN >= 8 && P.NT == 256 &&
+                       (P.KT % 4 == 0 || (long)P.KT * P.NG * p->d / 2 >= 4) && dmma_knob;
   for (int pad = dmma_ok ? 4 : 0; pad >= 0; pad -= 4) {
     P.vst = P.chip + pad;
     P.wsz = 2 * P.KT * p->d * P.WS + (pad ? 2 * P.KT * P.NG * p->d * 4 : 0);

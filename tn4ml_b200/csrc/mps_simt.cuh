@@ -75,13 +75,15 @@ template <> __device__ __forceinline__ void lds_pair<double>(const double *p, do
 
 // kRN (consts.h): register tile of RB rows (template parameter, 4 or 8) x kRN columns per thread
 
-// float64, d = 2, one column group, 256 threads: the step GEMM on the FP64 tensor pipe (`mma.sync.m8n8k4.f64`).
-// out[BT, 2*WS] = v[BT, K] x W[K, 2*WS] as 8x8 tiles; a warp owns 4 row tiles x 2 position tiles x both physical indices
+// float64, one or two column groups, 256 threads: the step GEMM on the FP64 tensor pipe (`mma.sync.m8n8k4.f64`).
+// out[BT, D*WS] = v[BT, K] x W[K, D*WS] as 8x8 tiles; a warp owns 4 row tiles x 2 position tiles x TWO physical indices at a time
 // (16 MMAs per k-step of 4 for 4 + 4 operand loads; the FMA loop issued 128 FMAs and 32 loads per thread for the same
-// work).  Columns are the POSITIONS of the pair layout (see step_gemm); phi is applied when the tile is written to
-// `out_s` in natural column order, from where every thread picks up its (tb, tn) register tile as before.
-template <int NG, int RB, bool ZERO>
-__device__ __forceinline__ void step_gemm_dmma(const double *__restrict__ Wg, int K, int chip, int KT, const double *v_s,
+// work).  D = 2 (D2): one pass.  Other D: one pass per pair of physical indices (each streams only its own two (k, s)
+// segments of the weight rows, so the weights are still read once), the phi-weighted sum carried in registers between passes.
+// Columns are the POSITIONS of the pair layout (see step_gemm); phi is applied when the tile is written to `out_s` in
+// natural column order, from where every thread picks up its (tb, tn) register tile as before.
+template <int NG, int RB, bool ZERO, bool D2>
+__device__ __forceinline__ void step_gemm_dmma(const double *__restrict__ Wg, int K, int D, int chip, int KT, const double *v_s,
                                                int vst, const double *phi_s, const double *rs_s, int rs_stride, double *W_s,
                                                double *out_s, double (&acc)[NG][RB][kRN], int tb, int tn, int TN, int WS) {
   const int tid = threadIdx.x, NT = blockDim.x;
@@ -93,83 +95,109 @@ __device__ __forceinline__ void step_gemm_dmma(const double *__restrict__ Wg, in
   // start 64 bytes apart instead of on the same banks; the output tile's rows are padded the same way
   const int GWp = vst > chip ? GW + 4 : GW;
   const int ost = vst;            // row stride of out_s
-  const int srow = 2 * GWp;       // one k-row of one group in shared memory: [s][GWp]
-  const int grow = 2 * WS;        // one k-row in global memory: [s][NG groups][GW]
+  const int srow = 2 * GWp;       // one k-row of one group and pass in shared memory: [2 physical indices][GWp]
+  const int grow = D * WS;        // one k-row in global memory: [s][NG groups][GW]
   const int nchunks = (K + KT - 1) / KT;
   const int pieces = GW / 2;      // 16-byte pieces of one (k, s) segment (a power of two: TN is)
   const int pshift = __ffs(pieces) - 1;
   // column groups one after the other (chi > 128 has two): each streams its own part of the weight rows
   for (int grp = 0; grp < NG; ++grp) {
-    auto issue = [&](int ch) {
-      const int k0 = ch * KT;
-      const int kt = min(KT, K - k0);
-      const int n16 = kt * 2 * pieces;
-      const double *src = Wg + (size_t)k0 * grow + (size_t)grp * GW;
-      double *dst = W_s + (size_t)(ch & 1) * KT * srow;
-      for (int i = tid; i < n16; i += NT) {
-        const int seg = i >> pshift, q = i & (pieces - 1);  // seg = k * 2 + s
-        cp_async16(reinterpret_cast<char *>(dst + (size_t)seg * GWp) + q * 16,
-                   reinterpret_cast<const char *>(src + (size_t)seg * WS) + q * 16);
-      }
-      cp_async_commit();
-    };
-    double c[4][2][2][2];  // [row tile][position tile][s][2]
+    double o[4][2][2];  // phi-weighted sum over the passes (D != 2)
+    if constexpr (!D2) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+      for (int r = 0; r < 4; ++r)
 #pragma unroll
-      for (int p = 0; p < 2; ++p)
-#pragma unroll
-        for (int q = 0; q < 2; ++q) c[r][p][q][0] = c[r][p][q][1] = 0.0;
-    issue(0);
-    for (int ch = 0; ch < nchunks; ++ch) {
-      if (ch + 1 < nchunks) {
-        issue(ch + 1);
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
-      }
-      __syncthreads();
-      const int k0 = ch * KT;
-      const int kt = min(KT, K - k0);
-      const double *Wb = W_s + (size_t)(ch & 1) * KT * srow + P0 + g;
-      const double *va = v_s + (size_t)(R0 + g) * vst + k0 + t;
-#pragma unroll 2
-      for (int kk = 0; kk < kt; kk += 4) {
-        double a[4], b[2][2];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) a[r] = va[(size_t)(8 * r) * vst + kk];
-#pragma unroll
-        for (int q = 0; q < 2; ++q)
-#pragma unroll
-          for (int p = 0; p < 2; ++p) b[p][q] = Wb[(size_t)((kk + t) * 2 + q) * GWp + 8 * p];
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int p = 0; p < 2; ++p)
-#pragma unroll
-            for (int q = 0; q < 2; ++q)
-              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
-                           : "+d"(c[r][p][q][0]), "+d"(c[r][p][q][1])
-                           : "d"(a[r]), "d"(b[p][q]));
-      }
-      __syncthreads();
+        for (int p = 0; p < 2; ++p) o[r][p][0] = o[r][p][1] = 0.0;
     }
-    // phi-weighted combination of the two physical indices -> out_s[row][n]
+    for (int sp = 0; sp < (D2 ? 2 : D); sp += 2) {
+      const bool two = D2 || sp + 1 < D;  // (odd D: the last pass has one physical index; its second segment is not loaded)
+      auto issue = [&](int ch) {
+        const int k0 = ch * KT;
+        const int kt = min(KT, K - k0);
+        const int n16 = kt * 2 * pieces;
+        const double *src = Wg + (size_t)k0 * grow + (size_t)sp * WS + (size_t)grp * GW;
+        double *dst = W_s + (size_t)(ch & 1) * KT * srow;
+        for (int i = tid; i < n16; i += NT) {
+          const int seg = i >> pshift, q = i & (pieces - 1);  // seg = k * 2 + (s - sp)
+          if (!two && (seg & 1)) continue;
+          cp_async16(reinterpret_cast<char *>(dst + (size_t)seg * GWp) + q * 16,
+                     reinterpret_cast<const char *>(src + (size_t)(seg >> 1) * grow + (size_t)(seg & 1) * WS) + q * 16);
+        }
+        cp_async_commit();
+      };
+      double c[4][2][2][2];  // [row tile][position tile][s - sp][2]
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) c[r][p][q][0] = c[r][p][q][1] = 0.0;
+      issue(0);
+      for (int ch = 0; ch < nchunks; ++ch) {
+        if (ch + 1 < nchunks) {
+          issue(ch + 1);
+          cp_async_wait<1>();
+        } else {
+          cp_async_wait<0>();
+        }
+        __syncthreads();
+        const int k0 = ch * KT;
+        const int kt = min(KT, K - k0);
+        const double *Wb = W_s + (size_t)(ch & 1) * KT * srow + P0 + g;
+        const double *va = v_s + (size_t)(R0 + g) * vst + k0 + t;
+#pragma unroll 2
+        for (int kk = 0; kk < kt; kk += 4) {
+          double a[4], b[2][2];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) a[r] = va[(size_t)(8 * r) * vst + kk];
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int p = 0; p < 2; ++p) b[p][q] = (q == 0 || two) ? Wb[(size_t)((kk + t) * 2 + q) * GWp + 8 * p] : 0.0;
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+#pragma unroll
+              for (int q = 0; q < 2; ++q)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
+                             : "+d"(c[r][p][q][0]), "+d"(c[r][p][q][1])
+                             : "d"(a[r]), "d"(b[p][q]));
+        }
+        __syncthreads();
+      }
+      // phi-weighted combination of the pass's physical indices
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int row = R0 + 8 * r + g;
+        const double rsv = rs_s ? rs_s[row * rs_stride] : 1.0;
+        const double r0 = rsv * phi_s[row * (D2 ? 2 : D) + sp], r1 = two ? rsv * phi_s[row * (D2 ? 2 : D) + sp + 1] : 0.0;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          if constexpr (D2) {
+            o[r][p][0] = fma(r0, c[r][p][0][0], r1 * c[r][p][1][0]);
+            o[r][p][1] = fma(r0, c[r][p][0][1], r1 * c[r][p][1][1]);
+          } else {
+            o[r][p][0] += fma(r0, c[r][p][0][0], r1 * c[r][p][1][0]);
+            o[r][p][1] += fma(r0, c[r][p][0][1], r1 * c[r][p][1][1]);
+          }
+        }
+      }
+    }
+    // -> out_s[row][n]
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int row = R0 + 8 * r + g;
-      const double rsv = rs_s ? rs_s[row * rs_stride] : 1.0;
-      const double r0 = rsv * phi_s[row * 2], r1 = rsv * phi_s[row * 2 + 1];
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
         const int pos = P0 + 8 * p + 2 * t;  // even: the two values are columns n, n + 1
         const int half = pos / (TN * 2), rem = pos - half * TN * 2;
         const int n = grp * GW + 4 * (rem >> 1) + 2 * half;
         if (n < chip) {
-          double2 o;
-          o.x = fma(r0, c[r][p][0][0], r1 * c[r][p][1][0]);
-          o.y = fma(r0, c[r][p][0][1], r1 * c[r][p][1][1]);
-          *reinterpret_cast<double2 *>(&out_s[(size_t)row * ost + n]) = o;
+          double2 ov;
+          ov.x = o[r][p][0];
+          ov.y = o[r][p][1];
+          *reinterpret_cast<double2 *>(&out_s[(size_t)row * ost + n]) = ov;
         }
       }
     }
@@ -196,10 +224,13 @@ template <typename T, int NG, int RB, bool ZERO> struct StepDmma {
 };
 template <int NG, int RB, bool ZERO> struct StepDmma<double, NG, RB, ZERO> {
   static constexpr bool kAvail = NG <= 2;
-  static __device__ __forceinline__ void run(const double *Wg, int K, int chip, int KT, const double *v_s, int vst,
+  static __device__ __forceinline__ void run(const double *Wg, int K, int D, int chip, int KT, const double *v_s, int vst,
                                              const double *phi_s, const double *rs_s, int rs_stride, double *W_s,
                                              double *out_s, double (&acc)[NG][RB][kRN], int tb, int tn, int TN, int WS) {
-    step_gemm_dmma<NG, RB, ZERO>(Wg, K, chip, KT, v_s, vst, phi_s, rs_s, rs_stride, W_s, out_s, acc, tb, tn, TN, WS);
+    if (D == 2)
+      step_gemm_dmma<NG, RB, ZERO, true>(Wg, K, 2, chip, KT, v_s, vst, phi_s, rs_s, rs_stride, W_s, out_s, acc, tb, tn, TN, WS);
+    else
+      step_gemm_dmma<NG, RB, ZERO, false>(Wg, K, D, chip, KT, v_s, vst, phi_s, rs_s, rs_stride, W_s, out_s, acc, tb, tn, TN, WS);
   }
 };
 
@@ -212,9 +243,11 @@ __device__ __forceinline__ void step_gemm(const T *__restrict__ Wg, int K, int D
                                           T *W_s, T (&acc)[NG][RB][kRN], int tb, int tn, int TN, int WS,
                                           T *out_s = nullptr) {
   if constexpr (StepDmma<T, NG, RB, ZERO>::kAvail) {
-    if (out_s != nullptr && D == 2) {
-      // (a group's rows are 1/NG of the full rows the buffers were sized for: NG times the k-rows per chunk)
-      StepDmma<T, NG, RB, ZERO>::run(Wg, K, chip, KT * NG, v_s, vst, phi_s, rs_s, rs_stride, W_s, out_s, acc, tb, tn, TN, WS);
+    if (out_s != nullptr && D >= 2) {
+      // (a group's rows of one pass (two physical indices) are 2 / (NG * D) of the full rows the buffers were sized for: that
+      //  many times the k-rows per chunk, in whole k-steps of 4)
+      const int ktd = max(4, (KT * NG * D / 2) / 4 * 4);
+      StepDmma<T, NG, RB, ZERO>::run(Wg, K, D, chip, ktd, v_s, vst, phi_s, rs_s, rs_stride, W_s, out_s, acc, tb, tn, TN, WS);
       return;
     }
   }
