@@ -18,10 +18,12 @@ static void fill_tc_args(const MpsPlan &P, void *ws, const MpsArgs<float> &M, Tc
   T.dbg = knobs().tc_dbg;
 #endif
   T.colsum = (const float *)(w + P.off_cs);
-  // stash writer: pause between pieces.  N = 512 accumulator columns (chi = 256, d = 2): every unpaced variant starved the weight
-  // loads; N <= 256: the writer serves the CTA's two tiles one after the other and any pause puts it on the step's path
-  // (chi = 128: chain kernels 6.75 / 7.10 -> 5.9 / 6.6 ms without it)
-  T.pace_ns = knobs().tc_pace_ns >= 0 ? knobs().tc_pace_ns : (P.tc_N > 256 ? P.tc_N * 2 / 5 : 0);
+  // stash writer: pause between pieces.  A __nanosleep costs >= ~250 cycles whatever its argument, and the writer copies an operand
+  // in 64 pieces: at chi = 256 (128 KB per operand, 16 k cycles per step) the pauses are hidden and keep the bulk copies from
+  // crowding the weight loads; for every smaller operand they ARE the step (in-kernel timeline, cfg 4: operand published 7.4 k
+  // cycles after the gather finished, waiting for the writer: chain kernels 0.65 / 0.74 -> 0.39 / 0.52 ms without pauses;
+  // chi = 128: 6.75 / 7.10 -> 6.2 / 6.7 ms).
+  T.pace_ns = knobs().tc_pace_ns >= 0 ? knobs().tc_pace_ns : (M.chip >= 256 ? P.tc_N * 2 / 5 : 0);
   T.wq = (float *)(w + P.off_wq);
   T.qmax = (int *)(w + P.off_qmax);
   T.wqc = (float *)(w + P.off_wqc);

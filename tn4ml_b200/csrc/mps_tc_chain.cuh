@@ -54,16 +54,19 @@ namespace tnb {
 // Optional in-kernel timeline (built only with -DTNB_TC_TRACE, tools/trace_chain.py): CTA (0,0) records clock64() at
 // fixed points of a few steady-state steps; read back with tnb_debug_trace_read.
 #ifdef TNB_TC_TRACE
+#ifndef TNB_TRACE_STEP0
+#define TNB_TRACE_STEP0 20  // first traced step (short chains: build with -DTNB_TRACE_STEP0=2)
+#endif
 __device__ long long g_tc_trace[64 * 32];
 #define TNB_TRACE(who, step_, ev)                                                                              \
   do {                                                                                                         \
-    if (blockIdx.x == 0 && blockIdx.y == 0 && (step_) >= 20 && (step_) < 52 && (threadIdx.x & 31) == 0 && (who) < 4) \
-      g_tc_trace[((step_)-20) * 64 + (who)*16 + (ev)] = clock64();                                              \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && (step_) >= TNB_TRACE_STEP0 && (step_) < TNB_TRACE_STEP0 + 32 && (threadIdx.x & 31) == 0 && (who) < 4) \
+      g_tc_trace[((step_)-TNB_TRACE_STEP0) * 64 + (who)*16 + (ev)] = clock64();                                              \
   } while (0)
 #define TNB_TRACE_SET(who, step_, ev, val)                                                                      \
   do {                                                                                                         \
-    if (blockIdx.x == 0 && blockIdx.y == 0 && (step_) >= 20 && (step_) < 52 && (threadIdx.x & 31) == 0 && (who) < 4) \
-      g_tc_trace[((step_)-20) * 64 + (who)*16 + (ev)] = (val);                                                  \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && (step_) >= TNB_TRACE_STEP0 && (step_) < TNB_TRACE_STEP0 + 32 && (threadIdx.x & 31) == 0 && (who) < 4) \
+      g_tc_trace[((step_)-TNB_TRACE_STEP0) * 64 + (who)*16 + (ev)] = (val);                                                  \
   } while (0)
 #define TNB_CLOCK() clock64()
 #define TNB_DBG(bit) (A.dbg & (bit))   // timing experiments of the trace build (TNB_TC_DBG); some give wrong results

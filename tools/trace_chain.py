@@ -18,7 +18,9 @@ SO = os.path.join(ROOT, "tools", "libtn4ml_b200_trace.so")
 
 def build():
     import __graft_entry__ as G
-    G.build(extra_flags=("-DTNB_TC_TRACE",), target=SO)
+    step0 = os.environ.get("TRACE_STEP0")  # first traced step (default 20; short chains such as cfg 4: TRACE_STEP0=2)
+    flags = ("-DTNB_TC_TRACE",) + ((f"-DTNB_TRACE_STEP0={int(step0)}",) if step0 else ())
+    G.build(extra_flags=flags, target=SO)
 
 
 if __name__ == "__main__":
