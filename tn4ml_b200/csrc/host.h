@@ -51,6 +51,7 @@ struct Knobs {
   int tc_nh = 0, tc_tiles = 0, tc_pace_ns = -1, da_stages = 0, tc_cg = 0;
   int simt_rb = 0, simt_nt = 0, simt_kt = 0, simt_dmma = 1, da_rm = 0;
   int rr = 1;
+  int da_small = 1;  // TNB_DA_SMALL=0: one 576-thread CTA per SM in the dA GEMM at every bond
   int tc_dbg = 0;
 };
 const Knobs &knobs();

@@ -247,6 +247,7 @@ struct TcDaArgs {
   int Dv;            // weighted copies sigma < Dv: D for chain sites, D*C for the class site
   int ra;            // bond rows per copy and CTA: min(chi, 128)
   int cpg;           // copies per CTA: 256 / ra
+  uint32_t stage_bytes;  // one pipeline stage: the U region (kDaU) + the V chunk of this bond (chi * 4 * kDaKC bytes), 1 KB aligned
   int only_site;     // >= 0: this site only (the class site; wq/qmax point at its own tables)
   int site0;         // first site of this launch (site = site0 + blockIdx.y): the backward pass may run in site ranges
 };
@@ -263,9 +264,13 @@ struct TcDaArgs {
 #define TNB_DA_TRACE(ch_, ev) do { } while (0)
 #endif
 
-// CPG: upper bound of the copies per CTA (compile time, so that the producer loop is straight-line code)
-template <int CPG>
-__global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
+// CPG: upper bound of the copies per CTA (compile time, so that the producer loop is straight-line code).
+// PW: producer warps.  16 (one CTA of 576 threads per SM) for bonds of 128 and more; 8 for smaller bonds, where a CTA has at
+// most 8 row octets per copy to re-weight and a chunk is a handful of small MMAs whose cost is the issue latency of the one
+// MMA warp (~120 cycles each): two CTAs of 320 threads per SM (stages sized by the bond) run two such pipelines side by side.
+template <int CPG, int PW = 16>
+__global__ void __launch_bounds__(PW * 32 + 64, PW == 16 ? 1 : 2) tc_da_kernel(TcDaArgs A) {
+  constexpr int kThreads = PW * 32 + 64;
   extern __shared__ __align__(1024) uint8_t smem[];
   const MpsArgs<float> &M = A.M;
   const int chi = M.chip, Dv = A.Dv, c = M.c;
@@ -294,15 +299,16 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
   const uint8_t *Vimg = (site < c ? A.gimg : A.fimg) + (size_t)(site + 1) * A.img_bond_bytes + chunk0;
   const uint32_t b_bytes = (uint32_t)chi * 4 * kDaKC;  // one chunk (16 samples) of an image
 
-  constexpr int kMmaWarp = kDaProducers / 32, kCopyWarp = kMmaWarp + 1;
+  constexpr int kMmaWarp = PW, kCopyWarp = kMmaWarp + 1;
+  const uint32_t kStage = A.stage_bytes;
   uint8_t *stages = smem;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(stages + (size_t)A.nstage * kDaStage);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(stages + (size_t)A.nstage * kStage);
   uint64_t *loaded = bars, *ready = bars + A.nstage, *empty = bars + 2 * A.nstage, *done = bars + 3 * A.nstage;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done + 1);
   if (tid == 0) {
     for (int i = 0; i < A.nstage; ++i) {
       ptx::mbar_init(&loaded[i], 1);                 // the bulk copies' expect_tx arrival
-      ptx::mbar_init(&ready[i], kDaProducers / 32);  // one arrival per producer warp
+      ptx::mbar_init(&ready[i], PW);                 // one arrival per producer warp
       ptx::mbar_init(&empty[i], 1);
     }
     ptx::mbar_init(done, 1);
@@ -314,8 +320,8 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
   }
   // operand rows that no copy fills (partial last tile) must read as zero
   for (int st = 0; st < A.nstage; ++st)
-    for (uint32_t i = tid * 16u; i < kDaU; i += kDaThreads * 16u)
-      *reinterpret_cast<uint4 *>(stages + (size_t)st * kDaStage + i) = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = tid * 16u; i < kDaU; i += kThreads * 16u)
+      *reinterpret_cast<uint4 *>(stages + (size_t)st * kStage + i) = make_uint4(0, 0, 0, 0);
   ptx::fence_proxy_async();
   ptx::tc_fence_before();
   __syncthreads();
@@ -336,7 +342,7 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
         ptx::tc_fence_after();
         TNB_DA_TRACE(ch, 0);
         if (ptx::elect_one()) {
-          const uint32_t st = ptx::smem_u32(stages + (size_t)stage * kDaStage);
+          const uint32_t st = ptx::smem_u32(stages + (size_t)stage * kStage);
           for (int t = 0; t < ntile; ++t) {
 #pragma unroll
             for (int ks = 0; ks < kDaKC / 16; ++ks) {
@@ -376,7 +382,7 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
         }
         ptx::mbar_wait(&empty[stage], phase ^ 1);
         TNB_DA_TRACE(ch, 2);
-        uint8_t *st = stages + (size_t)stage * kDaStage;
+        uint8_t *st = stages + (size_t)stage * kStage;
         const uint32_t u_bytes = (uint32_t)noct * 128;  // the CTA's rows of one (sample block, plane)
         ptx::mbar_expect_tx(&loaded[stage], 2 * (kDaKC / 8) * u_bytes + b_bytes);
         const uint8_t *usrc = Uimg + (size_t)ch * b_bytes + (size_t)(a0 / 8) * 128;
@@ -417,8 +423,8 @@ __global__ void __launch_bounds__(kDaThreads, 1) tc_da_kernel(TcDaArgs A) {
       if (ch + 1 < nchunks) load_w(ch + 1);
       ptx::mbar_wait(&loaded[stage], phase);
       if (warp == 0) TNB_DA_TRACE(ch, 3);
-      uint8_t *st = stages + (size_t)stage * kDaStage + lane_off;
-      for (int o = o0; o < noct; o += kOctPerWarp * (kDaProducers / 32)) {
+      uint8_t *st = stages + (size_t)stage * kStage + lane_off;
+      for (int o = o0; o < noct; o += kOctPerWarp * PW) {
         const uint4 hv = *reinterpret_cast<const uint4 *>(st + o * 128);
         const uint4 lv = *reinterpret_cast<const uint4 *>(st + kDaUPlane + o * 128);
         const __half2 *h_ = reinterpret_cast<const __half2 *>(&hv);
