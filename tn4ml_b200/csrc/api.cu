@@ -60,7 +60,8 @@ static Knobs read_knobs() {
   k.tc_nh = geti("TNB_TC_NH", 0);
   k.tc_tiles = geti("TNB_TC_TILES", 0);
   k.tc_pace_ns = geti("TNB_TC_PACE_NS", -1);
-  k.da_small = geti("TNB_DA_SMALL", 1);
+  k.da_small = geti("TNB_DA_SMALL", 64);
+  k.da_pw4 = geti("TNB_DA_PW4", 1);
   k.da_stages = geti("TNB_DA_STAGES", 0);
   k.tc_cg = geti("TNB_TC_CG", 0);
   k.simt_rb = geti("TNB_SIMT_RB", 0);

@@ -51,7 +51,8 @@ struct Knobs {
   int tc_nh = 0, tc_tiles = 0, tc_pace_ns = -1, da_stages = 0, tc_cg = 0;
   int simt_rb = 0, simt_nt = 0, simt_kt = 0, simt_dmma = 1, da_rm = 0;
   int rr = 1;
-  int da_small = 1;  // TNB_DA_SMALL=0: one 576-thread CTA per SM in the dA GEMM at every bond
+  int da_small = 64;  // TNB_DA_SMALL: largest bond whose dA GEMM runs several small CTAs per SM (0: never)
+  int da_pw4 = 1;     // bonds up to 32: three CTAs of 4 producer warps per SM (TNB_DA_PW4=0: two of 8)
   int tc_dbg = 0;
 };
 const Knobs &knobs();

@@ -59,6 +59,10 @@ cudaError_t mps_tc_set_attrs() {
     e = cudaFuncSetAttribute(tc_da_kernel<kDaMaxCpg>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax - 2048);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(tc_da_kernel<kDaMaxCpg, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax - 2048);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(tc_da_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax - 2048);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(tc_da_kernel<kDaMaxCpg, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax - 2048);
   return e;
 }
 
@@ -183,8 +187,10 @@ int mps_tc_backward(const tnb_problem *p, const MpsPlan &P, long long B, const v
   // stages sized by the bond: the U region is fixed (a virtual image of 256 rows), the V chunk is chi * 4 * kDaKC bytes.
   // Bonds up to 64: two CTAs of 8 producer warps per SM (see tc_da_kernel), each with half of the shared memory.
   Da.stage_bytes = (uint32_t)align_up((size_t)kDaU + (size_t)p->chi * 4 * kDaKC, 1024);
-  const bool small = p->chi <= 64 && knobs().da_small;
-  const size_t smem_avail = small ? (size_t)(kTcSmemMax - 2048) / 2 - 1024 - 1024 : (size_t)(kTcSmemMax - 2048 - 1024);
+  // da_small: largest bond that takes the several-CTAs-per-SM variants (knob TNB_DA_SMALL; 0 = never)
+  const bool small = p->chi <= knobs().da_small;
+  const int ncta = !small ? 1 : ((p->chi <= 32 && knobs().da_pw4) ? 3 : 2);   // CTAs per SM the stages are sized for
+  const size_t smem_avail = (size_t)(kTcSmemMax - 2048) / ncta - 1024 - (ncta > 1 ? 1024 : 0);
   Da.nstage = (int)(smem_avail / Da.stage_bytes);
   if (Da.nstage > 6) Da.nstage = 6;
   if (knobs().da_stages >= 2 && knobs().da_stages < Da.nstage) Da.nstage = knobs().da_stages;
@@ -223,7 +229,9 @@ int mps_tc_backward(const tnb_problem *p, const MpsPlan &P, long long B, const v
     dim3 gda((unsigned)(Da.mgroups * Da.nsplit), (unsigned)(pass == 0 ? s1 - s0 : 1));
     prof_begin(st);
     const size_t da_smem = (size_t)Da.nstage * Da.stage_bytes + 1024;
-    if (Da.cpg == 2) tc_da_kernel<2><<<gda, kDaThreads, da_smem, st>>>(Da);
+    if (Da.cpg == 2 && small) tc_da_kernel<2, 8><<<gda, 8 * 32 + 64, da_smem, st>>>(Da);
+    else if (Da.cpg == 2) tc_da_kernel<2><<<gda, kDaThreads, da_smem, st>>>(Da);
+    else if (ncta == 3) tc_da_kernel<kDaMaxCpg, 4><<<gda, 4 * 32 + 64, da_smem, st>>>(Da);
     else if (small) tc_da_kernel<kDaMaxCpg, 8><<<gda, 8 * 32 + 64, da_smem, st>>>(Da);
     else tc_da_kernel<kDaMaxCpg><<<gda, kDaThreads, da_smem, st>>>(Da);
     TNB_LAUNCH_CHECK(pass == 0 ? "tc_da_kernel" : "tc_da_kernel(class)");

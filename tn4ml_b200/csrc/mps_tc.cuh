@@ -265,11 +265,12 @@ struct TcDaArgs {
 #endif
 
 // CPG: upper bound of the copies per CTA (compile time, so that the producer loop is straight-line code).
-// PW: producer warps.  16 (one CTA of 576 threads per SM) for bonds of 128 and more; 8 for smaller bonds, where a CTA has at
-// most 8 row octets per copy to re-weight and a chunk is a handful of small MMAs whose cost is the issue latency of the one
-// MMA warp (~120 cycles each): two CTAs of 320 threads per SM (stages sized by the bond) run two such pipelines side by side.
+// PW: producer warps.  16 (one CTA of 576 threads per SM) for bonds of 128 and more; 8 / 4 for bonds up to 64 / 32, where a
+// CTA has at most 8 / 4 row octets per copy to re-weight and a chunk is a handful of small MMAs whose cost is the issue latency
+// of the one MMA warp (~120 cycles each): two CTAs of 320 threads (three of 192) per SM, stages sized by the bond, run that many
+// pipelines side by side (chi = 32: 3.99 -> 2.13 -> 1.71 ms; chi = 64: 4.22 -> 2.86 ms; chi = 128: no gain, 5.6 ms either way).
 template <int CPG, int PW = 16>
-__global__ void __launch_bounds__(PW * 32 + 64, PW == 16 ? 1 : 2) tc_da_kernel(TcDaArgs A) {
+__global__ void __launch_bounds__(PW * 32 + 64, PW == 16 ? 1 : (PW == 8 ? 2 : 3)) tc_da_kernel(TcDaArgs A) {
   constexpr int kThreads = PW * 32 + 64;
   extern __shared__ __align__(1024) uint8_t smem[];
   const MpsArgs<float> &M = A.M;
