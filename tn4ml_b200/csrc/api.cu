@@ -60,6 +60,7 @@ static Knobs read_knobs() {
   k.tc_nh = geti("TNB_TC_NH", 0);
   k.tc_tiles = geti("TNB_TC_TILES", 0);
   k.tc_pace_ns = geti("TNB_TC_PACE_NS", -1);
+  k.tc_ngrp2 = geti("TNB_TC_NGRP2", 1);
   k.da_small = geti("TNB_DA_SMALL", 64);
   k.da_pw4 = geti("TNB_DA_PW4", 1);
   k.da_stages = geti("TNB_DA_STAGES", 0);
@@ -233,8 +234,12 @@ MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
     P.tc_stage_bytes /= (uint32_t)P.tc_cg;  // one CTA's half of a stage
     P.tc_cols = 32;
     while (P.tc_cols < P.tc_tiles * P.tc_N) P.tc_cols <<= 1;
+    // small steps (one column chunk of at most 256 columns, bond up to 64, one tile): the 352-thread kernel, two CTAs per SM,
+    // each with half of the shared memory and at most 256 TMEM columns
+    P.tc_ngrp = (P.tc_NH == 1 && P.tc_N <= 256 && p->chi <= 64 && P.tc_tiles == 1 && P.tc_cg == 1 && knobs().tc_ngrp2) ? 2 : 4;
     const size_t fixed = (size_t)P.tc_tiles * 4096 /* row exchange */ + 1024 /* tables, barriers */;
-    long ns = (long)((kTcSmemMax - (long)fixed - (long)(P.tc_tiles * a_bytes)) / (long)P.tc_stage_bytes);
+    const long smem_cap = P.tc_ngrp == 2 ? (long)kTcSmemMax / 2 - 1024 : (long)kTcSmemMax;
+    long ns = (long)((smem_cap - (long)fixed - (long)(P.tc_tiles * a_bytes)) / (long)P.tc_stage_bytes);
     P.tc_nstage = ns > 12 ? 12 : (int)ns;
     P.tc_smem = P.tc_tiles * a_bytes + (size_t)P.tc_nstage * P.tc_stage_bytes + fixed;
     if (P.tc_nstage < 2) P.tc = 0;

@@ -51,6 +51,7 @@ struct Knobs {
   int tc_nh = 0, tc_tiles = 0, tc_pace_ns = -1, da_stages = 0, tc_cg = 0;
   int simt_rb = 0, simt_nt = 0, simt_kt = 0, simt_dmma = 1, da_rm = 0;
   int rr = 1;
+  int tc_ngrp2 = 1;   // TNB_TC_NGRP2=0: never run the 352-thread chain kernel (two CTAs per SM) at small steps
   int da_small = 64;  // TNB_DA_SMALL: largest bond whose dA GEMM runs several small CTAs per SM (0: never)
   int da_pw4 = 1;     // bonds up to 32: three CTAs of 4 producer warps per SM (TNB_DA_PW4=0: two of 8)
   int tc_dbg = 0;
@@ -66,7 +67,7 @@ struct MpsPlan {
   size_t smem_sweep, smem_class;
   int RB;  // register-tile rows of the SIMT sweep / class kernels
   // tensor-core sweep (f32, TNB_PREC_TENSOR)
-  int tc, tc_N, tc_NH, tc_NMMA, tc_nstage, tc_cols, tc_tiles, tc_cg;
+  int tc, tc_N, tc_NH, tc_NMMA, tc_nstage, tc_cols, tc_tiles, tc_cg, tc_ngrp;
   uint32_t tc_stage_bytes;
   size_t tc_site_img, off_img_n, off_img_t, off_kW, off_cs, off_wq, off_qmax, off_wqc, off_fimg, off_gimg, tc_smem, img_bond_bytes;
 };

@@ -36,8 +36,8 @@ static void fill_tc_args(const MpsPlan &P, void *ws, const MpsArgs<float> &M, Tc
   T.stage_bytes = P.tc_stage_bytes; T.site_img_bytes = P.tc_site_img;
 }
 
-template <int D, int SLOTS, int TILES, int CG> static cudaError_t tc_set_attr() {
-  return cudaFuncSetAttribute(tc_chain_kernel<D, SLOTS, TILES, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax);
+template <int D, int SLOTS, int TILES, int CG, int NGRP = 4> static cudaError_t tc_set_attr() {
+  return cudaFuncSetAttribute(tc_chain_kernel<D, SLOTS, TILES, CG, NGRP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax);
 }
 
 // every instantiation tc_launch_sweep can reach + the dA GEMM, for the current device
@@ -53,6 +53,11 @@ cudaError_t mps_tc_set_attrs() {
   if (e == cudaSuccess) e = tc_set_attr<6, 2, 1, 1>();
   if (e == cudaSuccess) e = tc_set_attr<8, 2, 1, 1>();
   if (e == cudaSuccess) e = tc_set_attr<8, 2, 2, 1>();
+  if (e == cudaSuccess) e = tc_set_attr<2, 2, 1, 1, 2>();
+  if (e == cudaSuccess) e = tc_set_attr<3, 2, 1, 1, 2>();
+  if (e == cudaSuccess) e = tc_set_attr<4, 2, 1, 1, 2>();
+  if (e == cudaSuccess) e = tc_set_attr<6, 2, 1, 1, 2>();
+  if (e == cudaSuccess) e = tc_set_attr<8, 2, 1, 1, 2>();
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(tc_da_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax - 2048);
   if (e == cudaSuccess)
@@ -66,13 +71,13 @@ cudaError_t mps_tc_set_attrs() {
   return e;
 }
 
-template <int D, int SLOTS, int TILES, int CG = 1>
+template <int D, int SLOTS, int TILES, int CG = 1, int NGRP = 4>
 static cudaError_t tc_launch_one(long long ntiles, long long tile0, size_t smem, TcArgs T, int adjoint, cudaStream_t st) {
   if (ntiles <= 0) return cudaSuccess;
   T.tile0 = tile0 * kTcRows;
   if (CG == 1) {
     dim3 grid((unsigned)(ntiles / TILES), adjoint ? 2 : 1);
-    tc_chain_kernel<D, SLOTS, TILES, CG><<<grid, kTcThreads, smem, st>>>(T, adjoint);
+    tc_chain_kernel<D, SLOTS, TILES, CG, NGRP><<<grid, (4 * NGRP + 3) * 32, smem, st>>>(T, adjoint);
     return cudaSuccess;
   }
   // CTA pair: clusters of two CTAs along x (consecutive sample tiles); an odd tile count gets an all-padding tile
@@ -112,7 +117,18 @@ static int tc_launch_sweep(const tnb_problem *p, const MpsPlan &P, const TcArgs 
   } while (0)
 #define TNB_TC_GO1(DD, SS) e = tc_launch_one<DD, SS, 1>(ntiles, 0, P.tc_smem, T, adjoint, st)
 #define TNB_TC_PAIR(DD, SS) e = tc_launch_one<DD, SS, 1, 2>(ntiles, 0, P.tc_smem, T, adjoint, st)
+#define TNB_TC_SMALL(DD) e = tc_launch_one<DD, 2, 1, 1, 2>(ntiles, 0, P.tc_smem, T, adjoint, st)
   prof_begin(st);
+  if (P.tc_ngrp == 2) {
+    switch (p->d) {
+      case 2: TNB_TC_SMALL(2); break;
+      case 3: TNB_TC_SMALL(3); break;
+      case 4: TNB_TC_SMALL(4); break;
+      case 6: TNB_TC_SMALL(6); break;
+      case 8: TNB_TC_SMALL(8); break;
+      default: return fail("tensor path: unsupported physical dimension %d", p->d);
+    }
+  } else
   switch (p->d) {
     case 2:
       if (wide && P.tc_cg == 2) TNB_TC_PAIR(2, 4);
@@ -125,6 +141,7 @@ static int tc_launch_sweep(const tnb_problem *p, const MpsPlan &P, const TcArgs 
     case 8: TNB_TC_GO(8, 2); break;
     default: return fail("tensor path: unsupported physical dimension %d", p->d);
   }
+#undef TNB_TC_SMALL
 #undef TNB_TC_GO
 #undef TNB_TC_GO1
 #undef TNB_TC_PAIR

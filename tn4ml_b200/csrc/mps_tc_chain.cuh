@@ -161,9 +161,15 @@ __device__ __forceinline__ float tc_combine_pack16(uint32_t col, uint32_t cstrid
 // `tcgen05.mma.cta_group::2` for both tiles (M = 256), each CTA holds -- and loads -- only its half of the B columns of a
 // weight stage, which takes the operand fetch of an MMA from 96 to 64 B/clk per SM (shared-memory bandwidth is what caps
 // the MMA rate of the one-CTA kernel).  Epilogue, operand, TMEM accumulator and stash writer stay per CTA.
-template <int D, int SLOTS, int TILES, int CG>
-__global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int adjoint) {
+// NGRP: epilogue warps per lane quarter (4 lane quarters x NGRP column-group owners).  4 (608 threads, one CTA per SM) in
+// general; 2 (352 threads, TWO CTAs per SM) for steps of at most 256 accumulator columns and bonds up to 64, where half of the
+// 16 epilogue warps would own no column group and a step is a handful of small MMAs: the second CTA's chain runs in the
+// latencies of the first (issue, commit, TMEM read, publish), which nothing inside one CTA could hide there.
+template <int D, int SLOTS, int TILES, int CG, int NGRP = 4>
+__global__ void __launch_bounds__((4 * NGRP + 3) * 32, NGRP == 4 ? 1 : 2) tc_chain_kernel(TcArgs A, int adjoint) {
   static_assert(CG == 1 || TILES == 1, "the CTA pair carries one tile per CTA");
+  static_assert(NGRP == 4 || NGRP == 2, "4 or 2 column-group owners per lane quarter");
+  constexpr int kEpiWarps = 4 * NGRP, kMmaWarp = kEpiWarps;  // + 1: weight producer warp, + 2: image writer warp
   extern __shared__ __align__(1024) uint8_t smem[];
   const MpsArgs<float> &M = A.M;
   const int chi = M.chip, L = M.L, c = M.c, C = M.C;
@@ -241,12 +247,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
     }
     for (int t = 0; t < TILES; ++t) {
       for (int h = 0; h < NH; ++h) ptx::mbar_init(&acc_full[t * kTcMaxNH + h], 1);
-      ptx::mbar_init(&a_ready[t], kTcEpiWarps);
+      ptx::mbar_init(&a_ready[t], kEpiWarps);
       ptx::mbar_init(&img_done[t], 1);
       ptx::mbar_init(&img_half[t], 1);
       ptx::mbar_init(&a_rel[t], 1);
     }
-    ptx::mbar_init(a_mma, kTcEpiWarps * CG);
+    ptx::mbar_init(a_mma, kEpiWarps * CG);
     for (int i = 0; i < A.nstage; ++i) ptx::mbar_init(&pfull[i], 1);
     ptx::fence_mbar_init();
   }
@@ -256,7 +262,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
     gchunk[tid] = (uint32_t)h;
     gcol[tid] = (uint32_t)(h * A.NMMA + (n0 - h * chi_h));
   }
-  if (warp == kTcMmaWarp) {
+  if (warp == kMmaWarp) {
     if (CG == 2) {
       ptx::tmem_alloc2(tmem_slot, (uint32_t)A.tmem_cols);
       ptx::tmem_relinquish2();
@@ -297,7 +303,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
     return k >= KS ? k - KS : k;
   };
 
-  if (warp == kTcMmaWarp + 2) {
+  if (warp == kMmaWarp + 2) {
     // ===== image writer: operand generation g (published as phase g of a_ready) -> HBM stash, in paced pieces =====
     // Columns n < 16*krel first (they are overwritten early, see krel), then the rest.
     if (lane == 0) {
@@ -341,7 +347,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       }
       ptx::bulk_wait0();
     }
-  } else if (warp == kTcMmaWarp + 1) {
+  } else if (warp == kMmaWarp + 1) {
     // ===== weight producer: one bulk async copy per pipeline stage (= one K-slab of one column chunk); the step's
     //       image is streamed once per tile =====
     if (lane == 0) {
@@ -367,7 +373,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
         }
       }
     }
-  } else if (warp == kTcMmaWarp) {
+  } else if (warp == kMmaWarp) {
     // ===== MMA issuer (CTA pair: the leader issues for both CTAs; the follower relays its `full` barriers) =====
     if (lane == 0 && rank != 0) {
       int stage = 0;
@@ -453,12 +459,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
       }
     }
   } else {
-    // ===== epilogue: 4 threads per sample row (one per warp group), each owning every 4th 16-column group =====
+    // ===== epilogue: NGRP threads per sample row (one per warp group), each owning every NGRP-th 16-column group =====
     const int lq = warp & 3, grp = warp >> 2;
     const int row = lq * 32 + lane;
     const bool lead = grp == 0;  // the thread of the row that does the per-sample bookkeeping
     const uint32_t lo_off = (uint32_t)chi * 16;  // lo plane of a unit, in the operand and in the bond images
-    const int nmine = (chi / 16 - grp + 3) >> 2;  // my 16-column groups: j = 4*i + grp, i < nmine (<= SLOTS)
+    const int nmine = (chi / 16 - grp + NGRP - 1) / NGRP;  // my 16-column groups: j = NGRP*i + grp, i < nmine (<= SLOTS)
     const int nslab = L - 1 + C;
     int step = 0;
 #ifdef TNB_TC_TRACE
@@ -520,7 +526,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
 #pragma unroll
       for (int i = 0; i < SLOTS; ++i) {
         if (i >= nmine) continue;
-        const int j = 4 * i + grp;
+        const int j = NGRP * i + grp;
 #pragma unroll
         for (int o = 0; o < 2; ++o) {
           uint4 z = make_uint4(0, 0, 0, 0), zh = z;
@@ -534,7 +540,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
 #pragma unroll
       for (int i = 0; i < SLOTS; ++i) {
         if (i >= nmine) continue;
-        const int j = 4 * i + grp;
+        const int j = NGRP * i + grp;
         float w[16];
         if (irow) load_img16(irow, j, w);
         else {
@@ -567,12 +573,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
     auto row_exchange = [&](int t, float v) -> const float * {
       float *x = xch + (t * 2 + (step & 1)) * (4 * kTcRows);
       x[grp * kTcRows + row] = v;
-      ptx::named_bar_sync(1 + lq, 4 * 32);
+      ptx::named_bar_sync(1 + lq, NGRP * 32);
       return x + row;
     };
     auto row_max = [&](int t, float v) -> float {
       const float *x = row_exchange(t, v);
-      return fmaxf(fmaxf(x[0], x[kTcRows]), fmaxf(x[2 * kTcRows], x[3 * kTcRows]));
+      float m = fmaxf(x[0], x[kTcRows]);
+      if (NGRP == 4) m = fmaxf(m, fmaxf(x[2 * kTcRows], x[3 * kTcRows]));
+      return m;
     };
     // Scale of a step whose outputs are bounded by `bnd`: 2^(14 - e), bnd = f * 2^e, f in [0.5, 1).  *e_out = e.
     auto bound_scale = [&](float bnd, bool valid, int *e_out) -> float {
@@ -601,7 +609,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
 #pragma unroll
         for (int i = 0; i < SLOTS; ++i) {
           if (i >= nmine) continue;
-          const int j = 4 * i + grp;
+          const int j = NGRP * i + grp;
           if ((int)gchunk[j] == NH - 1) continue;
           uint4 pk[4];
           ptx::tmem_ld16u(trow + gcol[j], pk);
@@ -616,7 +624,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
 #pragma unroll
       for (int i = 0; i < SLOTS; ++i) {
         if (i >= nmine) continue;
-        const int j = 4 * i + grp;
+        const int j = NGRP * i + grp;
         const int h = (int)gchunk[j];
         if (h != hprev) {
           if (h == NH - 1 && !moved) {
@@ -728,7 +736,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
 #pragma unroll
           for (int i = 0; i < SLOTS; ++i) {
             if (i >= nmine) continue;
-            const int j = 4 * i + grp;
+            const int j = NGRP * i + grp;
             float f[16];
             if (fr) load_img16(fr, j, f);
             else {
@@ -751,7 +759,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
             ptx::tc_fence_after();
           }
           const float *x = row_exchange(t, acc);
-          y[t][k] = ((x[0] + x[kTcRows]) + (x[2 * kTcRows] + x[3 * kTcRows])) * ysc;
+          y[t][k] = (NGRP == 4 ? ((x[0] + x[kTcRows]) + (x[2 * kTcRows] + x[3 * kTcRows])) : (x[0] + x[kTcRows])) * ysc;
           publish(t);
         }
         ++step;
@@ -831,7 +839,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
           for (int i = 0; i < SLOTS; ++i) {
             if (i >= nmine) continue;
             float w[16];
-            load_img16(vrow[t], 4 * i + grp, w);
+            load_img16(vrow[t], NGRP * i + grp, w);
 #pragma unroll
             for (int q = 0; q < 16; ++q) mrow = fmaxf(mrow, fabsf(w[q]));
           }
@@ -896,7 +904,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_chain_kernel(TcArgs A, int a
   if (CG == 2) ptx::cluster_sync();  // both CTAs are done with each other's barriers and TMEM
   else __syncthreads();
   ptx::tc_fence_after();
-  if (warp == kTcMmaWarp) {
+  if (warp == kMmaWarp) {
     if (CG == 2) ptx::tmem_dealloc2(tmem_base, (uint32_t)A.tmem_cols);
     else ptx::tmem_dealloc(tmem_base, (uint32_t)A.tmem_cols);
   }
