@@ -745,6 +745,9 @@ template <typename T, int RM> __global__ void __launch_bounds__(256) mps_da_kern
     const bool more = bb + BK < bend;
     if (more) fetch(bb + BK);
     if constexpr (kDmma) {
+      // (a warp whose 32 x 32 part of the tile lies outside the matrix -- bonds of 32 and less fill only the first column half,
+      //  short rows only some row quarters -- issues no MMAs: it would only take the FP64 tensor pipe away from its neighbours)
+      if (m0 + M0 < Mrows && r0 + N0 < chi)
 #pragma unroll
       for (int kk = 0; kk < BK; kk += 4) {
         double a[4], b[4];
