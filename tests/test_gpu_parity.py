@@ -301,3 +301,30 @@ def test_f64_tensor_pipe_general_physical_dimension(case):
         model = T.TensorNetwork(arrays, dtype=torch.float64, device="cuda:0")
     x = O.make_inputs(case["B"], case["L"], seed=12)
     _check(model, O.Problem("mps", case["emb"], head), _heads()[head], x, arrays, t, torch.float64)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+def test_edge_shapes(dtype):
+    """Smallest and ragged shapes: one sample, two sites, bond 1, a batch one short / one past a tile, SMPO with one window."""
+    import tn4ml_b200 as T
+    tol_scale = 1.0
+    # one sample, classifier on both kernel families' smallest legal bonds
+    for chi, B, L, cls in ((3, 1, 5, 2), (32, 1, 4, 1), (32, 129, 3, 0), (32, 127, 3, 2), (1, 4, 6, 3)):
+        if chi == 1 and dtype == torch.float32:
+            continue  # (a product-state model: some site gradients cancel to 1e-3 of the largest; float32 keeps 2e-6 of max|g| there)
+        arrays = O.make_mps_arrays(L, chi, 2, class_site=cls, C=3, std=0.2, seed=3)
+        x, t = O.make_inputs(B, L, seed=5), O.make_labels(B, 3)
+        model = T.TensorNetwork(arrays, dtype=dtype, device="cuda:0")
+        _check(model, O.Problem("mps", O.EmbSpec("trig"), "softmax_xent"), _heads()["softmax_xent"], x, arrays, t, dtype, tol_scale,
+               precision=1 if (dtype == torch.float32 and chi == 32) else 0)
+    # two sites: plain MPS with squeezed boundaries
+    arrays = O.make_mps_arrays(2, 4, 3, std=0.3, seed=4, squeeze_ends=True, identity_all=True)
+    x = O.make_inputs(7, 2, seed=6)
+    _check(T.MatrixProductState(arrays, dtype=dtype, device="cuda:0"), O.Problem("mps", O.EmbSpec("poly", degree=2, include_bias=True), "nll"),
+           _heads()["nll"], x, arrays, None, dtype)
+    # SMPO: a single window (spacing == L), one sample; and the register-resident family with one sample
+    for L, S, chi, B in ((4, 4, 5, 1), (8, 8, 32, 1), (9, 8, 32, 3)):
+        arrays = O.make_smpo_arrays(L, chi, 2, 2, S, std=0.2 if chi < 32 else 0.05, seed=8)
+        x = O.make_inputs(B, L, seed=9)
+        model = T.SpacedMatrixProductOperator(arrays, spacing=S, dtype=dtype, device="cuda:0")
+        _check(model, O.Problem("smpo", O.EmbSpec("trig"), "logquad", spacing=S), _heads()["logquad"], x, arrays, None, dtype)
