@@ -114,3 +114,37 @@ def test_cta_pair_chain_kernel_opt_in():
     loss, ref, err = (float(v) for v in m.groups())
     assert abs(loss - ref) <= 1e-4 * abs(ref)
     assert err <= 1e-4
+
+
+# ---- bond 32: the register-resident chain kernel (mps_rr_chain.cuh, `mma.sync` fp16x3) ------------------------------------
+@pytest.mark.parametrize("case", [
+    dict(L=10, d=2, cls=0, C=3, B=130, head="softmax_xent"),        # class site on the left boundary: no left chain
+    dict(L=10, d=2, cls=9, C=4, B=17, head="softmax_xent"),         # ... on the right boundary; one partial warp
+    dict(L=7, d=3, cls=3, C=2, B=129, head="softmax_xent"),         # d = 3, one sample in the second tile
+    dict(L=12, d=2, cls=5, C=10, B=1, head="mse"),                  # a single sample
+    dict(L=12, d=2, cls=6, C=5, B=257, head="xent_softmax_argmax"),
+], ids=["cls0", "clsL", "d3", "one_sample_mse", "argmax"])
+def test_rr_chain_classifier(case):
+    import tn4ml_b200 as T
+    from tn4ml_b200 import _lib
+    arrays = O.make_mps_arrays(case["L"], 32, case["d"], class_site=case["cls"], C=case["C"], std=0.05, seed=11)
+    x = O.make_inputs(case["B"], case["L"], seed=12)
+    t = O.make_labels(case["B"], case["C"])
+    emb = {2: O.EmbSpec("trig"), 3: O.EmbSpec("poly", degree=2, include_bias=True)}[case["d"]]
+    model = _tensor_model(T.TensorNetwork, arrays)
+    _check(model, O.Problem("mps", emb, case["head"]), _heads()[case["head"]], x, arrays, t, torch.float32, precision=1)
+
+
+def test_rr_chain_nll_and_long_chain():
+    """Unsupervised NLL at bond 32 (d = 2 trig), and the cfg-5 chain length at the metric's small-bond point (L = 196, 10 classes)."""
+    import tn4ml_b200 as T
+    arrays = O.make_mps_arrays(20, 32, 2, std=0.05, seed=4, squeeze_ends=True, identity_all=True)
+    x = O.make_inputs(200, 20, seed=6)
+    model = _tensor_model(T.MatrixProductState, arrays)
+    _check(model, O.Problem("mps", O.EmbSpec("trig"), "nll"), _heads()["nll"], x, arrays, None, torch.float32, precision=1)
+    arrays = O.make_mps_arrays(196, 32, 2, class_site=97, C=10, std=1e-2, seed=42)
+    x = O.make_inputs(300, 196, seed=1)
+    t = O.make_labels(300, 10)
+    model = _tensor_model(T.TensorNetwork, arrays)
+    _check(model, O.Problem("mps", O.EmbSpec("trig"), "softmax_xent"), _heads()["softmax_xent"], x, arrays, t, torch.float32,
+           precision=1)

@@ -71,6 +71,7 @@ static Knobs read_knobs() {
   k.simt_dmma = geti("TNB_SIMT_DMMA", 1);
   k.da_rm = geti("TNB_DA_RM", 0);
   k.rr = geti("TNB_RR", 1);
+  k.rr_chain = geti("TNB_RR_CHAIN", 1);
 #ifdef TNB_TC_TRACE
   k.tc_dbg = geti("TNB_TC_DBG", 0);
 #endif
@@ -99,6 +100,7 @@ int ensure_device_ready() {
   if (e == cudaSuccess) e = mps_tc_set_attrs();
   if (e == cudaSuccess) e = smpo_set_attrs();
   if (e == cudaSuccess) e = rr_set_attrs();
+  if (e == cudaSuccess) e = mps_rr_set_attrs();
   if (e != cudaSuccess) return fail("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   g_dev_ready[dev].store(1, std::memory_order_release);
   return 0;
@@ -243,6 +245,7 @@ MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
     P.tc_nstage = ns > 12 ? 12 : (int)ns;
     P.tc_smem = P.tc_tiles * a_bytes + (size_t)P.tc_nstage * P.tc_stage_bytes + fixed;
     if (P.tc_nstage < 2) P.tc = 0;
+    P.tc_rr = (P.tc && P.tc_NH == 1 && P.tc_cg == 1 && mps_rr_supported(p)) ? 1 : 0;
   }
   const bool tc_mode = P.tc != 0;
   size_t fslots = need_grad ? (size_t)p->L + 1 : 2;

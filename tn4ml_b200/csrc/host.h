@@ -51,6 +51,7 @@ struct Knobs {
   int tc_nh = 0, tc_tiles = 0, tc_pace_ns = -1, da_stages = 0, tc_cg = 0;
   int simt_rb = 0, simt_nt = 0, simt_kt = 0, simt_dmma = 1, da_rm = 0;
   int rr = 1;
+  int rr_chain = 1;  // TNB_RR_CHAIN=0: bond-32 MPS chains stay on the tcgen05 kernel (two 352-thread CTAs per SM)
   int tc_ngrp2 = 1;   // TNB_TC_NGRP2=0: never run the 352-thread chain kernel (two CTAs per SM) at small steps
   int da_small = 64;  // TNB_DA_SMALL: largest bond whose dA GEMM runs several small CTAs per SM (0: never)
   int da_pw4 = 1;     // bonds up to 32: three CTAs of 4 producer warps per SM (TNB_DA_PW4=0: two of 8)
@@ -68,6 +69,7 @@ struct MpsPlan {
   int RB;  // register-tile rows of the SIMT sweep / class kernels
   // tensor-core sweep (f32, TNB_PREC_TENSOR)
   int tc, tc_N, tc_NH, tc_NMMA, tc_nstage, tc_cols, tc_tiles, tc_cg, tc_ngrp;
+  int tc_rr;  // bond 32: the chains run register resident on mma.sync (mps_rr_chain.cuh); images, stash and dA GEMM as planned
   uint32_t tc_stage_bytes;
   size_t tc_site_img, off_img_n, off_img_t, off_kW, off_cs, off_wq, off_qmax, off_wqc, off_fimg, off_gimg, tc_smem, img_bond_bytes;
 };
@@ -92,6 +94,9 @@ int mps_tc_forward(const tnb_problem *p, const MpsPlan &P, long long B, const vo
 int mps_tc_backward(const tnb_problem *p, const MpsPlan &P, long long B, const void *x, const void *targets,
                     double loss_scale, void *grads, int accumulate, void *ws, cudaStream_t st, int part, int nparts);
 cudaError_t mps_tc_set_attrs();
+// register-resident chain at bond 32 (mps_rr.cu): same images and outputs as the tcgen05 chain kernel
+cudaError_t mps_rr_set_attrs();
+bool mps_rr_supported(const tnb_problem *p);
 // SMPO / MPO double layer (smpo.cu)
 int64_t smpo_workspace_bytes(const tnb_problem *p, long long B, int need_grad);
 int smpo_forward(const tnb_problem *p, long long B, const void *x, const void *params, void *loss, double *loss_sum,

@@ -1,0 +1,31 @@
+// Register-resident MPS chain at bond 32 (float32 tensor family, `mma.sync` fp16x3): host-side launch code.
+// Kernel: mps_rr_chain.cuh.  Called from the tcgen05 family's sweep launcher (mps_tc.cu) when the plan selects it.
+#include "host.h"
+#include "mps_rr_chain.cuh"
+
+namespace tnb {
+
+static size_t rrc_smem(int d) { return (size_t)kRrcStages * 4096 * d + 128; }
+
+cudaError_t mps_rr_set_attrs() {
+  cudaError_t e = cudaFuncSetAttribute(rr_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rrc_smem(2));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(rr_chain_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rrc_smem(3));
+  return e;
+}
+
+bool mps_rr_supported(const tnb_problem *p) {
+  return knobs().rr_chain && p->kind == TNB_KIND_MPS && p->dtype == TNB_F32 && p->chi == 32 && (p->d == 2 || p->d == 3);
+}
+
+// forward (adjoint = 0) or adjoint (1) sweep over B samples; T as filled by the tcgen05 family (same images, same outputs)
+int mps_rr_launch_sweep(const TcArgs &T, int d, long long B, int adjoint, cudaStream_t st) {
+  const long long ntiles = (B + kTcRows - 1) / kTcRows;
+  dim3 grid((unsigned)ntiles, adjoint ? 2 : 1);
+  prof_begin(st);
+  if (d == 2) rr_chain_kernel<2><<<grid, kRrcThreads, rrc_smem(2), st>>>(T, adjoint);
+  else rr_chain_kernel<3><<<grid, kRrcThreads, rrc_smem(3), st>>>(T, adjoint);
+  TNB_LAUNCH_CHECK(adjoint ? "rr_chain_kernel(adj)" : "rr_chain_kernel(fwd)");
+  return 0;
+}
+
+}  // namespace tnb

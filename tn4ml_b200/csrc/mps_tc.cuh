@@ -70,7 +70,7 @@ struct TcArgs {
 // (r, s) run) and the columns r of its quarter (column sums: threads along r, phases along a); the three maxima are
 // non-negative floats combined with atomicMax on their bit patterns (kW and colsum hold raw bits until tc_finalize_kernel).
 constexpr int kTcStatGroups = 4;
-__global__ void __launch_bounds__(256) tc_stats_kernel(const float *__restrict__ params, int *__restrict__ kW,
+static __global__ void __launch_bounds__(256) tc_stats_kernel(const float *__restrict__ params, int *__restrict__ kW,
                                                        int *__restrict__ colsum_bits, int L, int chi, int D, int C, int c) {
   const int slab = blockIdx.x, g = blockIdx.y, nslab = L - 1 + C;
   int site, o, nj;
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(256) tc_stats_kernel(const float *__restrict__
 
 // raw maxima -> kW (class slabs share one scale: the seed phase accumulates all of them into one TMEM tile, so kW <- the min
 // over the C class slabs) and colsum * 2^kW with a margin for the fp16x3 rounding of the products.  One block.
-__global__ void tc_finalize_kernel(int *__restrict__ kW, float *__restrict__ colsum, int L, int C, int c) {
+static __global__ void tc_finalize_kernel(int *__restrict__ kW, float *__restrict__ colsum, int L, int C, int c) {
   const int nslab = L - 1 + C;
   __shared__ int kmin;
   if (threadIdx.x == 0) kmin = INT_MAX;
@@ -155,7 +155,7 @@ __global__ void tc_finalize_kernel(int *__restrict__ kW, float *__restrict__ col
 // one thread per (slab, n', k-octet): 8 weights -> 16 B of hi and 16 B of lo, both directions.
 // Stage (h, ks) of a slab holds the K-slab ks of column chunk h: columns n'' = s*chi_h + (n - h*chi_h).
 // cg = 2 (CTA pair): a stage is [rank][plane hi|lo][NMMA / 2 columns], rank r holding the columns the r-th CTA supplies.
-__global__ void tc_image_kernel(const float *__restrict__ params, const int *__restrict__ kW, uint8_t *__restrict__ img_n,
+static __global__ void tc_image_kernel(const float *__restrict__ params, const int *__restrict__ kW, uint8_t *__restrict__ img_n,
                                 uint8_t *__restrict__ img_t, int L, int chi, int D, int C, int c, int NH, int cg) {
   const int nslab = L - 1 + C;
   const int N = D * chi, KO = chi / 8, KS = chi / 16;
