@@ -5,25 +5,28 @@
 
 namespace tnb {
 
-static size_t rrc_smem(int d) { return (size_t)kRrcStages * 4096 * d + 128; }
+// ring of site images + barriers + the step table (site, kW) of at most L + n_out + 1 steps
+static size_t rrc_smem(int d, int steps) { return (size_t)kRrcStages * 4096 * d + 128 + (size_t)(steps + 2) * 8; }
 
 cudaError_t mps_rr_set_attrs() {
-  cudaError_t e = cudaFuncSetAttribute(rr_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rrc_smem(2));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(rr_chain_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rrc_smem(3));
+  cudaError_t e = cudaFuncSetAttribute(rr_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(rr_chain_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax);
   return e;
 }
 
 bool mps_rr_supported(const tnb_problem *p) {
-  return knobs().rr_chain && p->kind == TNB_KIND_MPS && p->dtype == TNB_F32 && p->chi == 32 && (p->d == 2 || p->d == 3);
+  return knobs().rr_chain && p->kind == TNB_KIND_MPS && p->dtype == TNB_F32 && p->chi == 32 && (p->d == 2 || p->d == 3) &&
+         rrc_smem(p->d, p->L + p->n_out) <= (size_t)kTcSmemMax;
 }
 
 // forward (adjoint = 0) or adjoint (1) sweep over B samples; T as filled by the tcgen05 family (same images, same outputs)
 int mps_rr_launch_sweep(const TcArgs &T, int d, long long B, int adjoint, cudaStream_t st) {
+  const size_t smem = rrc_smem(d, T.M.L + T.M.C);
   const long long ntiles = (B + kTcRows - 1) / kTcRows;
-  dim3 grid((unsigned)ntiles, adjoint ? 2 : 1);
+  dim3 grid((unsigned)((ntiles + 1) / 2), adjoint ? 2 : 1);  // two sample tiles per CTA
   prof_begin(st);
-  if (d == 2) rr_chain_kernel<2><<<grid, kRrcThreads, rrc_smem(2), st>>>(T, adjoint);
-  else rr_chain_kernel<3><<<grid, kRrcThreads, rrc_smem(3), st>>>(T, adjoint);
+  if (d == 2) rr_chain_kernel<2><<<grid, kRrcThreads, smem, st>>>(T, adjoint);
+  else rr_chain_kernel<3><<<grid, kRrcThreads, smem, st>>>(T, adjoint);
   TNB_LAUNCH_CHECK(adjoint ? "rr_chain_kernel(adj)" : "rr_chain_kernel(fwd)");
   return 0;
 }

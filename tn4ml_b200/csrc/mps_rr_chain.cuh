@@ -17,23 +17,35 @@
 //   16-byte unit and the 32 lanes of a warp cover one 128-byte line, so an environment leaves the SM as 16 coalesced
 //   32-bit stores per step and warp, and the weight-gradient GEMM (tc_da_kernel) reads the images unchanged.
 //
-// CTA: 8 compute warps (one 128-sample tile, like the tcgen05 kernel) + 1 producer warp that streams one site image
-// (D * 4 KB) per step through a ring of bulk async copies; two CTAs per SM for D = 2.
+// CTA: 16 warps (two 128-sample tiles), one CTA per SM, 128 registers per thread.  The site images (D * 4 KB per step)
+// come through a ring of bulk async copies issued by the compute warps in turn (warp s % 16 issues the copy of step s + 4
+// at the top of its step s; registers are allocated in units of four warps, so a 17th producer warp capped the kernel at
+// 96 registers and spilled the ring cursor into the step loop: ncu long-scoreboard stalls on the barrier address).  The step's feature
+// maps, weight scale and forward exponents are fetched ONE STEP AHEAD and the maps are evaluated underneath the step's
+// HMMAs: with four warps per scheduler nothing else hides a global-load latency in front of every dependent step.
 // Programs, bookkeeping (exps / esum / y / dy / wq / qmax / wqc / qmaxc) and results are those of tc_chain_kernel.
 #pragma once
 #include "mps_tc.cuh"
 
 namespace tnb {
 
-constexpr int kRrcWarps = 8;                         // compute warps: 16 samples each
-constexpr int kRrcThreads = (kRrcWarps + 1) * 32;    // + weight producer warp
-constexpr int kRrcStages = 4;                        // site images in flight
+constexpr int kRrcWarps = 16;                        // compute warps: 16 samples each (two sample tiles of 128 per CTA)
+constexpr int kRrcThreads = kRrcWarps * 32;
+constexpr int kRrcStages = 6;                        // ring slots
+constexpr int kRrcAhead = 4;                         // the copy of step s + kRrcAhead is issued at the top of step s
 
 __device__ __forceinline__ void rrc_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};\n"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// the same with a zero accumulator input (the first product term of a step: no accumulator clearing)
+__device__ __forceinline__ void rrc_mma0(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%10, %10, %10, %10};\n"
+      : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
 }
 __device__ __forceinline__ void rrc_ldsm4(uint32_t saddr, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];\n"
@@ -48,6 +60,35 @@ __device__ __forceinline__ void rrc_split2(float a, float b, uint32_t &hi, uint3
   hi = *reinterpret_cast<const uint32_t *>(&h);
   lo = *reinterpret_cast<const uint32_t *>(&l);
 }
+// a scaled fp32 pair -> fp16x2 hi and lo words (packed subtraction)
+__device__ __forceinline__ void rrc_split2p(uint64_t w, uint32_t &hi, uint32_t &lo) {
+  float a, b;
+  ptx::f2_unpack(w, a, b);
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  float la, lb;
+  ptx::f2_unpack(ptx::f2_sub(w, ptx::f2_pack(hf.x, hf.y)), la, lb);
+  const __half2 l = __floats2half2_rn(la, lb);
+  hi = *reinterpret_cast<const uint32_t *>(&h);
+  lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+// Feature map of one input.  The headline map of the small-bond regime (trigonometric, k = 1, d = 2) takes one sincospif:
+// (cos, sin)(pi x / 2) has unit norm to rounding, so embed()'s normaliser (embeddings.py:1374-1387) is the identity in float32.
+template <int D>
+__device__ __forceinline__ void rrc_embed(const EmbParams<float> &e, const float *xp, float (&ph)[D]) {
+  if (D == 2 && e.kind == TNB_EMB_TRIG) {
+    float sn, cs;
+    sincospif(0.5f * (xp ? xp[0] : 0.5f), &sn, &cs);
+    ph[0] = cs;
+    ph[D - 1] = sn;
+  } else {
+    embed_site_d<D>(e, xp, ph);
+  }
+}
+// 2^q as a float (q clamped to the normal range; the slow ldexpf only outside it)
+__device__ __forceinline__ float rrc_pow2(int q) {
+  return (q >= -126 && q <= 127) ? __int_as_float((q + 127) << 23) : ldexpf(1.f, q);
+}
 __device__ __forceinline__ float2 rrc_join2(uint32_t hi, uint32_t lo) {
   const float2 h = __half22float2(*reinterpret_cast<const __half2 *>(&hi));
   const float2 l = __half22float2(*reinterpret_cast<const __half2 *>(&lo));
@@ -55,7 +96,7 @@ __device__ __forceinline__ float2 rrc_join2(uint32_t hi, uint32_t lo) {
 }
 
 template <int D>
-__global__ void __launch_bounds__(kRrcThreads, D == 2 ? 2 : 1) rr_chain_kernel(TcArgs A, int adjoint) {
+__global__ void __launch_bounds__(kRrcThreads, 1) rr_chain_kernel(const __grid_constant__ TcArgs A, int adjoint) {
   constexpr int NT = 4 * D;                      // n-tiles of 8 accumulator columns: tile s*4 + j holds n = 8j .. 8j+7 of slice s
   constexpr uint32_t kStage = 2048u * D;         // one K-slab (16 rows) of the site image: hi plane, lo plane
   constexpr uint32_t kLoPlane = 1024u * D;
@@ -93,52 +134,71 @@ __global__ void __launch_bounds__(kRrcThreads, D == 2 ? 2 : 1) rr_chain_kernel(T
     return (tr ? A.img_t : A.img_n) + (size_t)slab * A.site_img_bytes;
   };
 
+  // step table in shared memory: site whose feature map / forward exponents step s needs (s == total: the adjoint's
+  // boundary site) and the weight scale of its slab
+  auto site_at = [&](int s) -> int {
+    if (!adjoint) return s < nR ? L - 1 - s : (s < nR + nL ? s - nR : c);
+    if (s < nseed) return c;
+    if (s >= total) return half == 0 ? 0 : L - 1;
+    return half == 0 ? c - 1 - (s - nseed) : c + 1 + (s - nseed);
+  };
+  auto slab_at = [&](int s) -> int {
+    if (!adjoint) return s < nR + nL ? mps_slab(M, site_at(s)) : c;
+    return (s < nseed || s >= total) ? c : mps_slab(M, site_at(s));
+  };
+
+  // the CTA's second sample tile may lie beyond the batch: its warps leave, the ring counts the others
+  const long long ntiles = (M.B + kTcRows - 1) / kTcRows;
+  const long long tile_first = A.tile0 / kTcRows + (long long)blockIdx.x * 2;
+  const int nact = tile_first + 1 < ntiles ? kRrcWarps : kRrcWarps / 2;
+
   uint8_t *ring = smem;  // [kRrcStages][kSite]
   uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)kRrcStages * kSite), *empty = full + kRrcStages;
+  int2 *tbl = reinterpret_cast<int2 *>(empty + kRrcStages);  // [total + 2]: (site, kW)
   if (tid == 0) {
     for (int i = 0; i < kRrcStages; ++i) {
       ptx::mbar_init(&full[i], 1);
-      ptx::mbar_init(&empty[i], kRrcWarps);
+      ptx::mbar_init(&empty[i], (uint32_t)nact);
     }
     ptx::fence_mbar_init();
   }
+  for (int s0 = tid; s0 <= total + 1; s0 += kRrcThreads) {
+    const int sc = s0 <= total ? s0 : total;
+    tbl[s0] = make_int2(site_at(sc), A.kW[slab_at(sc)]);
+  }
   __syncthreads();
 
-  if (warp == kRrcWarps) {
-    // ===== weight producer: one bulk async copy (the whole site image) per step =====
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int step = 0; step < total; ++step) {
-        ptx::mbar_wait(&empty[stage], phase ^ 1);
-        ptx::mbar_expect_tx(&full[stage], kSite);
-        ptx::bulk_g2s(ring + (size_t)stage * kSite, step_image(step), kSite, &full[stage]);
-        if (++stage == kRrcStages) { stage = 0; phase ^= 1; }
-      }
+  // the first kRrcAhead site images (fresh ring slots: nothing to wait for)
+  if (tid == 0) {
+    for (int s0 = 0; s0 < kRrcAhead && s0 < total; ++s0) {
+      ptx::mbar_expect_tx(&full[s0], kSite);
+      ptx::bulk_g2s(ring + (size_t)s0 * kSite, step_image(s0), kSite, &full[s0]);
     }
-    return;
   }
+  if (warp >= nact) return;
 
   // ===== compute warps =====
   const int g = lane >> 2, t = lane & 3;
-  const long long row0 = A.tile0 + (long long)blockIdx.x * kTcRows + warp * 16;  // a multiple of 8
-  const long long bA = row0 + g, bB = bA + 8;                                    // this thread's two sample rows
+  const long long row0 = tile_first * kTcRows + warp * 16;  // a multiple of 8
+  const long long bA = row0 + g, bB = bA + 8;               // this thread's two sample rows
   const bool vA = bA < M.B, vB = bB < M.B;
   const bool headlane = t < 2;                     // lane t == 0 keeps the books of row A, t == 1 of row B
   const long long bH = t == 0 ? bA : bB;
   const bool vH = headlane && (t == 0 ? vA : vB);
-  const long long bE = (t & 1) ? bB : bA;          // the row whose feature map this lane evaluates (shared by shuffle)
+  const long long bE = (t & 1) ? bB : bA;          // the row whose feature maps this lane evaluates (shared by shuffle)
   const bool vE = (t & 1) ? vB : vA;
-  const int srcA = lane & ~3, srcB = srcA + 1;
+  const int qbase = lane & ~3;
+  const bool scalar_in = M.emb.n_in == 1;
+  const float *xrow = M.x + (size_t)(vE ? bE : 0) * L * M.emb.n_in;
   // byte offset of this thread's word in the image of a bond: unit (row, octet o, plane p) at (row/8)*1024 + p*512 + o*128 + (row%8)*16
   const size_t img_off = (size_t)(row0 >> 3) * 1024 + (size_t)lane * 4;
-  const uint32_t ring_s = ptx::smem_u32(ring);
   // ldmatrix.x4 of one (k-step, n-tile): matrices {hi k-octet 0, hi k-octet 1, lo k-octet 0, lo k-octet 1}
-  const uint32_t ld_off = (uint32_t)(lane & 7) * 16 + (uint32_t)((lane >> 3) & 1) * 128 + (uint32_t)(lane >> 4) * kLoPlane;
+  const uint32_t ld_base = ptx::smem_u32(ring) + (uint32_t)(lane & 7) * 16 + (uint32_t)((lane >> 3) & 1) * 128 +
+                           (uint32_t)(lane >> 4) * kLoPlane;
 
   uint32_t ahi[2][4], alo[2][4];  // operand row block v[16, 32] as A fragments of the two k-steps
   float acc[NT][4];
-  int stage = 0;
+  int stage = 0, gs = 0;  // ring slot and index of the next step
   uint32_t phase = 0;
 
   auto set_e0 = [&](bool gateA, bool gateB) {  // boundary vector e0 * 2^14 (fp16 0x7400 in element 0)
@@ -168,54 +228,117 @@ __global__ void __launch_bounds__(kRrcThreads, D == 2 ? 2 : 1) rr_chain_kernel(T
         *reinterpret_cast<uint32_t *>(p + 512) = alo[kk][i];
       }
   };
-  auto zero_acc = [&]() {
-#pragma unroll
-    for (int j = 0; j < NT; ++j)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
-  };
-  // acc += operand x site image of the ring's current stage
-  auto mma_step = [&]() {
-    ptx::mbar_wait(&full[stage], phase);
-    const uint32_t st = ring_s + (uint32_t)stage * kSite + ld_off;
+  auto load_image = [&](const uint8_t *src, float2 (&v)[2][4]) {  // this thread's elements of an image, hi + lo
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        uint32_t bh0, bh1, bl0, bl1;
-        rrc_ldsm4(st + (uint32_t)kk * kStage + (uint32_t)j * 256, bh0, bh1, bl0, bl1);
-        rrc_mma(acc[j], ahi[kk], bh0, bh1);
-        rrc_mma(acc[j], alo[kk], bh0, bh1);
-        rrc_mma(acc[j], ahi[kk], bl0, bl1);
+      for (int i = 0; i < 4; ++i) {
+        const uint8_t *p = src + (size_t)(i & 1) * 1024 + (size_t)(2 * kk + (i >> 1)) * 128;
+        v[kk][i] = rrc_join2(*reinterpret_cast<const uint32_t *>(p), *reinterpret_cast<const uint32_t *>(p + 512));
+      }
+  };
+  // acc (+)= operand x site image of the ring's current stage
+  auto mma_step = [&](bool accumulate) {
+    // this warp's turn to fetch: the image of step gs + kRrcAhead, into the slot every warp has left at step gs - 2
+    if ((gs & (nact - 1)) == warp && gs + kRrcAhead < total && lane == 0) {
+      const int sf = gs + kRrcAhead, slot = sf % kRrcStages, use = sf / kRrcStages;
+      if (use > 0) ptx::mbar_wait(&empty[slot], (uint32_t)(use - 1) & 1u);
+      ptx::mbar_expect_tx(&full[slot], kSite);
+      ptx::bulk_g2s(ring + (size_t)slot * kSite, step_image(sf), kSite, &full[slot]);
+    }
+    __syncwarp();
+    ++gs;
+    ptx::mbar_wait(&full[stage], phase);
+    const uint32_t st = ld_base + (uint32_t)stage * kSite;
+    // Four n-tiles at a time, one product term after the other: two HMMAs into the same accumulator are four
+    // instructions apart (a dependent HMMA waits ~21 cycles; back to back the three terms of a tile were a serial chain).
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+      for (int j0 = 0; j0 < NT; j0 += 4) {
+        uint32_t bh0[4], bh1[4], bl0[4], bl1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rrc_ldsm4(st + (uint32_t)kk * kStage + (uint32_t)(j0 + j) * 256, bh0[j], bh1[j], bl0[j], bl1[j]);
+        if (kk == 0 && !accumulate) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rrc_mma0(acc[j0 + j], ahi[kk], bh0[j], bh1[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rrc_mma(acc[j0 + j], ahi[kk], bh0[j], bh1[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rrc_mma(acc[j0 + j], alo[kk], bh0[j], bh1[j]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rrc_mma(acc[j0 + j], ahi[kk], bl0[j], bl1[j]);
       }
     __syncwarp();
     if (lane == 0) ptx::mbar_arrive(&empty[stage]);
     if (++stage == kRrcStages) { stage = 0; phase ^= 1; }
   };
-  // feature maps of the warp's rows at `site`: every lane evaluates one row, the quad shares them
-  auto phis = [&](int site, float (&pa)[D], float (&pb)[D]) {
-    float ph[D];
-    embed_site_d<D>(M.emb, vE ? M.x + ((size_t)bE * L + site) * M.emb.n_in : nullptr, ph);
-#pragma unroll
-    for (int s = 0; s < D; ++s) {
-      pa[s] = __shfl_sync(0xffffffffu, ph[s], srcA);
-      pb[s] = __shfl_sync(0xffffffffu, ph[s], srcB);
+
+  // ---- feature maps: a lane evaluates ONE map per two steps -- row A or B (t & 1) at step 2b + (t >> 1) of block b --
+  // from an input fetched two steps earlier; the quad shares the values by shuffle.
+  float phq[D];      // this lane's map of the current block
+  float xq = 0.5f;   // this lane's input of the NEXT block (one-scalar maps)
+  auto load_xq = [&](int blk) {
+    const int sb = min(2 * blk + (t >> 1), total);
+    if (scalar_in) xq = vE ? xrow[tbl[sb].x] : 0.5f;
+  };
+  auto eval_block = [&](int blk, float (&ph)[D]) {
+    if (scalar_in) {
+      const float xv = xq;
+      rrc_embed<D>(M.emb, &xv, ph);
+    } else {
+      const int sb = min(2 * blk + (t >> 1), total);
+      rrc_embed<D>(M.emb, vE ? xrow + (size_t)tbl[sb].x * M.emb.n_in : nullptr, ph);
     }
   };
-  // o[j][i] = sum_s phi_s acc[s*4 + j][i]   (i = 0, 1: row A; 2, 3: row B)
-  auto contract = [&](const float (&pa)[D], const float (&pb)[D], float (&o)[4][4]) {
+  float pa[D], pb[D];  // maps of rows A / B at the current step
+  auto take_phis = [&](int s) {  // (pa, pb) <- the maps of step s out of the quad's block values
+    const int src = qbase + 2 * (s & 1);
+#pragma unroll
+    for (int q = 0; q < D; ++q) {
+      pa[q] = __shfl_sync(0xffffffffu, phq[q], src);
+      pb[q] = __shfl_sync(0xffffffffu, phq[q], src + 1);
+    }
+  };
+  // called once per step s after its MMAs are issued and BEFORE (pa, pb) of step s are last used: evaluates the next block at
+  // odd steps (underneath the HMMAs); finish_step then moves on to the maps of step s + 1.
+  float phn[D];
+  auto eval_ahead = [&](int s) {
+    if (s & 1) {
+      eval_block((s + 1) >> 1, phn);
+      load_xq(((s + 1) >> 1) + 1);
+    }
+  };
+  auto finish_step = [&](int s) {
+    if (s & 1) {
+#pragma unroll
+      for (int q = 0; q < D; ++q) phq[q] = phn[q];
+    }
+    take_phis(s + 1);
+  };
+  load_xq(0);
+  eval_block(0, phq);
+  load_xq(1);
+  take_phis(0);
+
+  // o[j] (packed pairs; A rows: oA, B rows: oB) = sum_s phi_s acc[s*4 + j]
+  auto contract = [&](uint64_t (&oA)[4], uint64_t (&oB)[4]) {
+    uint64_t PA[D], PB[D];
+#pragma unroll
+    for (int q = 0; q < D; ++q) {
+      PA[q] = ptx::f2_pack(pa[q], pa[q]);
+      PB[q] = ptx::f2_pack(pb[q], pb[q]);
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      o[j][0] = pa[0] * acc[j][0];
-      o[j][1] = pa[0] * acc[j][1];
-      o[j][2] = pb[0] * acc[j][2];
-      o[j][3] = pb[0] * acc[j][3];
+      oA[j] = ptx::f2_mul(PA[0], ptx::f2_pack(acc[j][0], acc[j][1]));
+      oB[j] = ptx::f2_mul(PB[0], ptx::f2_pack(acc[j][2], acc[j][3]));
 #pragma unroll
-      for (int s = 1; s < D; ++s) {
-        o[j][0] = fmaf(pa[s], acc[s * 4 + j][0], o[j][0]);
-        o[j][1] = fmaf(pa[s], acc[s * 4 + j][1], o[j][1]);
-        o[j][2] = fmaf(pb[s], acc[s * 4 + j][2], o[j][2]);
-        o[j][3] = fmaf(pb[s], acc[s * 4 + j][3], o[j][3]);
+      for (int q = 1; q < D; ++q) {
+        oA[j] = ptx::f2_fma(PA[q], ptx::f2_pack(acc[q * 4 + j][0], acc[q * 4 + j][1]), oA[j]);
+        oB[j] = ptx::f2_fma(PB[q], ptx::f2_pack(acc[q * 4 + j][2], acc[q * 4 + j][3]), oB[j]);
       }
     }
   };
@@ -226,30 +349,46 @@ __global__ void __launch_bounds__(kRrcThreads, D == 2 ? 2 : 1) rr_chain_kernel(T
     *e_out = ok ? ef - 126 : 0;
     return ok ? __uint_as_float((uint32_t)(127 + 126 + kTcKA - ef) << 23) : 0.f;
   };
-  // contracted rows -> normalised fp16 hi/lo operand; eA / eB: the rows' exponents (0 and a zero row if flushed)
-  auto renorm = [&](const float (&o)[4][4], int &eA, int &eB, bool &nzA, bool &nzB) {
+  // contracted rows -> normalised fp16 hi/lo operand; dA / dB: the rows' exponents in units of the true recurrence
+  // (e - 14 - kw; 0 and a zero row if flushed)
+  auto renorm = [&](const uint64_t (&oA)[4], const uint64_t (&oB)[4], int kw, int &dA, int &dB) {
     float mA = 0.f, mB = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      mA = fmaxf(mA, fmaxf(fabsf(o[j][0]), fabsf(o[j][1])));
-      mB = fmaxf(mB, fmaxf(fabsf(o[j][2]), fabsf(o[j][3])));
+      float a0, a1, b0, b1;
+      ptx::f2_unpack(oA[j], a0, a1);
+      ptx::f2_unpack(oB[j], b0, b1);
+      mA = fmaxf(mA, fmaxf(fabsf(a0), fabsf(a1)));
+      mB = fmaxf(mB, fmaxf(fabsf(b0), fabsf(b1)));
     }
     mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 1));
     mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 1));
     mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 2));
     mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 2));
+    int eA, eB;
     const float sA = row_scale(mA, vA, &eA), sB = row_scale(mB, vB, &eB);
-    nzA = sA != 0.f;
-    nzB = sB != 0.f;
+    dA = sA != 0.f ? eA - kTcKA - kw : 0;
+    dB = sB != 0.f ? eB - kTcKA - kw : 0;
+    const uint64_t SA = ptx::f2_pack(sA, sA), SB = ptx::f2_pack(sB, sB);
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk) {
-      rrc_split2(o[2 * kk][0] * sA, o[2 * kk][1] * sA, ahi[kk][0], alo[kk][0]);
-      rrc_split2(o[2 * kk][2] * sB, o[2 * kk][3] * sB, ahi[kk][1], alo[kk][1]);
-      rrc_split2(o[2 * kk + 1][0] * sA, o[2 * kk + 1][1] * sA, ahi[kk][2], alo[kk][2]);
-      rrc_split2(o[2 * kk + 1][2] * sB, o[2 * kk + 1][3] * sB, ahi[kk][3], alo[kk][3]);
+      rrc_split2p(ptx::f2_mul(oA[2 * kk], SA), ahi[kk][0], alo[kk][0]);
+      rrc_split2p(ptx::f2_mul(oB[2 * kk], SB), ahi[kk][1], alo[kk][1]);
+      rrc_split2p(ptx::f2_mul(oA[2 * kk + 1], SA), ahi[kk][2], alo[kk][2]);
+      rrc_split2p(ptx::f2_mul(oB[2 * kk + 1], SB), ahi[kk][3], alo[kk][3]);
     }
   };
   auto sel = [&](int a, int b) -> int { return t == 0 ? a : b; };  // the head lane's row
+
+  // One chain step s: acc = operand x slab, next operand = normalised phi-contraction; moves (pa, pb) on to step s + 1.
+  auto chain_step = [&](int s, int &dA, int &dB) {
+    mma_step(false);
+    eval_ahead(s);
+    uint64_t oA[4], oB[4];
+    contract(oA, oB);
+    renorm(oA, oB, tbl[s].y, dA, dB);
+    finish_step(s);
+  };
 
   if (!adjoint) {
     // ---------------- forward program ----------------
@@ -258,34 +397,20 @@ __global__ void __launch_bounds__(kRrcThreads, D == 2 ? 2 : 1) rr_chain_kernel(T
     store_image(img_slot(A.fimg, L));
     store_image(img_slot(A.fimg, 0));
     set_e0(true, true);
-    for (int i = 0; i < nR; ++i) {
-      const int site = L - 1 - i, kw = A.kW[mps_slab(M, site)];
-      float pa[D], pb[D], o[4][4];
-      phis(site, pa, pb);
-      zero_acc();
-      mma_step();
-      contract(pa, pb, o);
-      int eA, eB;
-      bool nzA, nzB;
-      renorm(o, eA, eB, nzA, nzB);
-      const int dA = nzA ? eA - kTcKA - kw : 0, dB = nzB ? eB - kTcKA - kw : 0;
+    int s = 0;
+    for (int i = 0; i < nR; ++i, ++s) {
+      const int site = L - 1 - i;
+      int dA, dB;
+      chain_step(s, dA, dB);
       ebA += dA;
       ebB += dB;
       if (vH) M.exps[(size_t)site * M.B + bH] = sel(dA, dB);
       store_image(img_slot(A.fimg, site));
       if (i == nR - 1) set_e0(true, true);  // F[c+1] is in its image; the left chain starts from the boundary vector
     }
-    for (int i = 0; i < nL; ++i) {
-      const int kw = A.kW[i];
-      float pa[D], pb[D], o[4][4];
-      phis(i, pa, pb);
-      zero_acc();
-      mma_step();
-      contract(pa, pb, o);
-      int eA, eB;
-      bool nzA, nzB;
-      renorm(o, eA, eB, nzA, nzB);
-      const int dA = nzA ? eA - kTcKA - kw : 0, dB = nzB ? eB - kTcKA - kw : 0;
+    for (int i = 0; i < nL; ++i, ++s) {
+      int dA, dB;
+      chain_step(s, dA, dB);
       eaA += dA;
       eaB += dB;
       if (vH) M.exps[(size_t)i * M.B + bH] = sel(dA, dB);
@@ -294,38 +419,33 @@ __global__ void __launch_bounds__(kRrcThreads, D == 2 ? 2 : 1) rr_chain_kernel(T
     // ---------------- class site + head ----------------
     {
       const float ysc = ldexpf(1.f, -(2 * kTcKA + A.kW[c]));
-      float pa[D], pb[D];
-      phis(c, pa, pb);
       // F[c+1] of this thread's elements, from its image (written by this thread: at the start if c + 1 == L)
       float2 fr[2][4];
-      {
-        const uint8_t *src = img_slot(A.fimg, c + 1);
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint8_t *p = src + (size_t)(i & 1) * 1024 + (size_t)(2 * kk + (i >> 1)) * 128;
-            fr[kk][i] = rrc_join2(*reinterpret_cast<const uint32_t *>(p), *reinterpret_cast<const uint32_t *>(p + 512));
-          }
-      }
-      for (int k = 0; k < C; ++k) {
-        float o[4][4];
-        zero_acc();
-        mma_step();
-        contract(pa, pb, o);
+      load_image(img_slot(A.fimg, c + 1), fr);
+      for (int k = 0; k < C; ++k, ++s) {
+        mma_step(false);
+        eval_ahead(s);
+        uint64_t oA[4], oB[4];
+        contract(oA, oB);
         float yA = 0.f, yB = 0.f;
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk) {
-          yA = fmaf(o[2 * kk][0], fr[kk][0].x, fmaf(o[2 * kk][1], fr[kk][0].y, yA));
-          yB = fmaf(o[2 * kk][2], fr[kk][1].x, fmaf(o[2 * kk][3], fr[kk][1].y, yB));
-          yA = fmaf(o[2 * kk + 1][0], fr[kk][2].x, fmaf(o[2 * kk + 1][1], fr[kk][2].y, yA));
-          yB = fmaf(o[2 * kk + 1][2], fr[kk][3].x, fmaf(o[2 * kk + 1][3], fr[kk][3].y, yB));
+          float a0, a1, b0, b1;
+          ptx::f2_unpack(oA[2 * kk], a0, a1);
+          ptx::f2_unpack(oB[2 * kk], b0, b1);
+          yA = fmaf(a0, fr[kk][0].x, fmaf(a1, fr[kk][0].y, yA));
+          yB = fmaf(b0, fr[kk][1].x, fmaf(b1, fr[kk][1].y, yB));
+          ptx::f2_unpack(oA[2 * kk + 1], a0, a1);
+          ptx::f2_unpack(oB[2 * kk + 1], b0, b1);
+          yA = fmaf(a0, fr[kk][2].x, fmaf(a1, fr[kk][2].y, yA));
+          yB = fmaf(b0, fr[kk][3].x, fmaf(b1, fr[kk][3].y, yB));
         }
         yA += __shfl_xor_sync(0xffffffffu, yA, 1);
         yB += __shfl_xor_sync(0xffffffffu, yB, 1);
         yA += __shfl_xor_sync(0xffffffffu, yA, 2);
         yB += __shfl_xor_sync(0xffffffffu, yB, 2);
         if (vH) M.y[(size_t)bH * C + k] = (t == 0 ? yA : yB) * ysc;
+        finish_step(s);
       }
       float lval = 0.f;
       if (vH) {
@@ -367,14 +487,13 @@ __global__ void __launch_bounds__(kRrcThreads, D == 2 ? 2 : 1) rr_chain_kernel(T
       }
       if (dmax > 0.f) frexpf(dmax, &edH);
       if (vH) {
-        float ph[D];
-        embed_site_d<D>(M.emb, M.x + ((size_t)bH * L + c) * M.emb.n_in, ph);
+        // class-site dA weights: wqc[(s,k)][b] = phi_s * dy'_k (this lane's own row: t == 0 -> A, 1 -> B)
         int qm = INT_MIN;
 #pragma unroll
-        for (int s = 0; s < D; ++s)
+        for (int q = 0; q < D; ++q)
           for (int k = 0; k < C; ++k) {
-            const float w = ph[s] * dyl[k];
-            A.wqc[((size_t)s * C + k) * M.B + bH] = w;
+            const float w = (t == 0 ? pa[q] : pb[q]) * dyl[k];
+            A.wqc[((size_t)q * C + k) * M.B + bH] = w;
             if (w != 0.f) { int ew; frexpf(w, &ew); qm = max(qm, ew); }
           }
         for (int k = 0; k < C; ++k) M.dy[(size_t)bH * C + k] = dyl[k];
@@ -382,24 +501,13 @@ __global__ void __launch_bounds__(kRrcThreads, D == 2 ? 2 : 1) rr_chain_kernel(T
       }
     }
     __syncwarp();
-    const int edA = __shfl_sync(0xffffffffu, edH, srcA), edB = __shfl_sync(0xffffffffu, edH, srcB);
-    const float dscA = vA ? ldexpf(1.f, -edA) : 0.f, dscB = vB ? ldexpf(1.f, -edB) : 0.f;  // |dy_k * dsc| < 1
-    float pa[D], pb[D];
-    phis(c, pa, pb);
+    const int edA = __shfl_sync(0xffffffffu, edH, qbase), edB = __shfl_sync(0xffffffffu, edH, qbase + 1);
+    const float dscA = vA ? rrc_pow2(-edA) : 0.f, dscB = vB ? rrc_pow2(-edB) : 0.f;  // |dy_k * dsc| < 1
     // forward environment rows (operand units) of this thread's elements
     float2 vr[2][4];
-    {
-      const uint8_t *src = img_slot(A.fimg, half == 0 ? c + 1 : c);
-#pragma unroll
-      for (int kk = 0; kk < 2; ++kk)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint8_t *p = src + (size_t)(i & 1) * 1024 + (size_t)(2 * kk + (i >> 1)) * 128;
-          vr[kk][i] = rrc_join2(*reinterpret_cast<const uint32_t *>(p), *reinterpret_cast<const uint32_t *>(p + 512));
-        }
-    }
-    zero_acc();
-    for (int k = 0; k < C; ++k) {
+    load_image(img_slot(A.fimg, half == 0 ? c + 1 : c), vr);
+    int s = 0;
+    for (int k = 0; k < C; ++k, ++s) {
       // seed operand of slab c + k: F row * dy_k * 2^-ed (rows normalised to 2^14, |factor| < 1)
       const float fA = vA ? M.dy[(size_t)bA * C + k] * dscA : 0.f, fB = vB ? M.dy[(size_t)bB * C + k] * dscB : 0.f;
 #pragma unroll
@@ -409,56 +517,59 @@ __global__ void __launch_bounds__(kRrcThreads, D == 2 ? 2 : 1) rr_chain_kernel(T
           const float f = (i & 1) ? fB : fA;
           rrc_split2(vr[kk][i].x * f, vr[kk][i].y * f, ahi[kk][i], alo[kk][i]);
         }
-      mma_step();  // accumulates over k
+      mma_step(k > 0);  // accumulates over k
+      eval_ahead(s);
+      if (k < C - 1) finish_step(s);  // (the class site's maps again)
     }
+    // forward exponents of the two rows at the step's site, fetched one step ahead
+    auto load_ds = [&](int sn, int &a, int &b) {
+      const int site = tbl[sn].x;
+      a = vA ? M.exps[(size_t)site * M.B + bA] : 0;
+      b = vB ? M.exps[(size_t)site * M.B + bB] : 0;
+    };
+    int dsA, dsB;
+    load_ds(nseed, dsA, dsB);
     int hA, hB;  // running exponents of the adjoint rows
     {
-      float o[4][4];
-      contract(pa, pb, o);
-      int eA, eB;
-      bool nzA, nzB;
-      renorm(o, eA, eB, nzA, nzB);
-      const int kw = A.kW[c];
-      hA = (nzA ? eA - kTcKA - kw : 0) + edA;  // G = row * 2^h (the operand carried dy * 2^-ed)
-      hB = (nzB ? eB - kTcKA - kw : 0) + edB;
+      uint64_t oA[4], oB[4];
+      contract(oA, oB);
+      int dA, dB;
+      renorm(oA, oB, A.kW[c], dA, dB);
+      hA = dA + edA;  // G = row * 2^h (the operand carried dy * 2^-ed)
+      hB = dB + edB;
       store_image(img_slot(A.gimg, half == 0 ? c : c + 1));
+      finish_step(nseed - 1);
     }
-    for (int i = 0; i < nchain; ++i) {
+    for (int i = 0; i < nchain; ++i, ++s) {
       const int site = half == 0 ? c - 1 - i : c + 1 + i;
-      const int kw = A.kW[mps_slab(M, site)];
-      float qa[D], qb[D], o[4][4];
-      phis(site, qa, qb);
-      const int dsA = vA ? M.exps[(size_t)site * M.B + bA] : 0, dsB = vB ? M.exps[(size_t)site * M.B + bB] : 0;
-      zero_acc();
-      mma_step();
-      contract(qa, qb, o);
-      int eA, eB;
-      bool nzA, nzB;
-      renorm(o, eA, eB, nzA, nzB);
-      store_image(img_slot(A.gimg, half == 0 ? c - 1 - i : c + 2 + i));
       // dA_site = sum_b 2^q (F x phi x G), q = h_in - delta_site, h_in = exponent of the input adjoint
       const int qA = hA - dsA, qB = hB - dsB;
       if (vH) {
-        const float sc2 = ldexpf(1.f, sel(qA, qB));
+        const float sc2 = rrc_pow2(sel(qA, qB));
 #pragma unroll
-        for (int s = 0; s < D; ++s) A.wq[((size_t)site * D + s) * M.B + bH] = (t == 0 ? qa[s] : qb[s]) * sc2;
+        for (int q = 0; q < D; ++q) A.wq[((size_t)site * D + q) * M.B + bH] = (t == 0 ? pa[q] : pb[q]) * sc2;
       }
       int qm = max(vA ? qA : INT_MIN, vB ? qB : INT_MIN);
       for (int off = 16; off > 0; off >>= 1) qm = max(qm, __shfl_xor_sync(0xffffffffu, qm, off));
       if (lane == 0 && qm != INT_MIN) atomicMax(&A.qmax[site], qm);
-      hA += (nzA ? eA - kTcKA - kw : 0) - dsA;
-      hB += (nzB ? eB - kTcKA - kw : 0) - dsB;
+      int nA, nB;
+      load_ds(s + 1, nA, nB);  // (s + 1 == total: the boundary site)
+      int dA, dB;
+      chain_step(s, dA, dB);
+      store_image(img_slot(A.gimg, half == 0 ? c - 1 - i : c + 2 + i));
+      hA += dA - dsA;
+      hB += dB - dsB;
+      dsA = nA;
+      dsB = nB;
     }
-    // boundary site: no chain step, but it has a gradient
+    // boundary site: no chain step, but it has a gradient ((pa, pb) and ds hold its inputs)
     {
       const int jb = half == 0 ? 0 : L - 1;
-      float qa[D], qb[D];
-      phis(jb, qa, qb);
-      const int qA = vA ? hA - M.exps[(size_t)jb * M.B + bA] : INT_MIN, qB = vB ? hB - M.exps[(size_t)jb * M.B + bB] : INT_MIN;
+      const int qA = vA ? hA - dsA : INT_MIN, qB = vB ? hB - dsB : INT_MIN;
       if (vH) {
-        const float sc2 = ldexpf(1.f, sel(qA, qB));
+        const float sc2 = rrc_pow2(sel(qA, qB));
 #pragma unroll
-        for (int s = 0; s < D; ++s) A.wq[((size_t)jb * D + s) * M.B + bH] = (t == 0 ? qa[s] : qb[s]) * sc2;
+        for (int q = 0; q < D; ++q) A.wq[((size_t)jb * D + q) * M.B + bH] = (t == 0 ? pa[q] : pb[q]) * sc2;
       }
       int qm = max(qA, qB);
       for (int off = 16; off > 0; off >>= 1) qm = max(qm, __shfl_xor_sync(0xffffffffu, qm, off));
