@@ -101,11 +101,7 @@ static cudaError_t tc_launch_one(long long ntiles, long long tile0, size_t smem,
 // launch the tcgen05 sweep (forward environments or adjoint chains)
 static int tc_launch_sweep(const tnb_problem *p, const MpsPlan &P, const TcArgs &T, long long B, int adjoint,
                            cudaStream_t st) {
-  if (P.tc_rr) {
-    TcArgs R = T;
-    R.pace_ns = knobs().tc_pace_ns >= 0 ? knobs().tc_pace_ns : 200;  // start offset between the warps of a scheduler
-    return mps_rr_launch_sweep(R, p->d, B, adjoint, st);
-  }  // bond 32: register-resident chains on mma.sync
+  if (P.tc_rr) return mps_rr_launch_sweep(T, p->d, B, adjoint, st);  // bond 32: register-resident chains on mma.sync
   cudaError_t e = cudaSuccess;
   const bool wide = p->chi > 128;   // 16-column groups per epilogue thread: 4 (chi <= 256) or 2 (chi <= 128)
   const long long ntiles = (B + kTcRows - 1) / kTcRows;
