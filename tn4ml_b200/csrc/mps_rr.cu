@@ -6,7 +6,10 @@
 namespace tnb {
 
 // ring of site images + barriers + the step table (site, kW) of at most L + n_out + 1 steps
-static size_t rrc_smem(int d, int steps) { return (size_t)kRrcStages * 4096 * d + 128 + (size_t)(steps + 2) * 8; }
+#ifndef TNB_RRC_PAD_SMEM
+#define TNB_RRC_PAD_SMEM 0  // (occupancy experiments: extra bytes that keep a second CTA off the SM)
+#endif
+static size_t rrc_smem(int d, int steps) { return (size_t)kRrcStages * 4096 * d + 128 + (size_t)(steps + 2) * 8 + TNB_RRC_PAD_SMEM; }
 
 cudaError_t mps_rr_set_attrs() {
   cudaError_t e = cudaFuncSetAttribute(rr_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax);
@@ -23,7 +26,7 @@ bool mps_rr_supported(const tnb_problem *p) {
 int mps_rr_launch_sweep(const TcArgs &T, int d, long long B, int adjoint, cudaStream_t st) {
   const size_t smem = rrc_smem(d, T.M.L + T.M.C);
   const long long ntiles = (B + kTcRows - 1) / kTcRows;
-  dim3 grid((unsigned)((ntiles + 1) / 2), adjoint ? 2 : 1);  // two sample tiles per CTA
+  dim3 grid((unsigned)((ntiles + kRrcTiles - 1) / kRrcTiles), adjoint ? 2 : 1);  // kRrcTiles sample tiles per CTA
   prof_begin(st);
   if (d == 2) rr_chain_kernel<2><<<grid, kRrcThreads, smem, st>>>(T, adjoint);
   else rr_chain_kernel<3><<<grid, kRrcThreads, smem, st>>>(T, adjoint);

@@ -29,7 +29,11 @@
 
 namespace tnb {
 
-constexpr int kRrcWarps = 16;                        // compute warps: 16 samples each (two sample tiles of 128 per CTA)
+#ifndef TNB_RRC_WARPS
+#define TNB_RRC_WARPS 16
+#endif
+constexpr int kRrcWarps = TNB_RRC_WARPS;             // warps of 16 samples each: 16 (two sample tiles of 128 per CTA) or 8 (one)
+constexpr int kRrcTiles = kRrcWarps / 8;
 constexpr int kRrcThreads = kRrcWarps * 32;
 constexpr int kRrcStages = 6;                        // ring slots
 constexpr int kRrcAhead = 4;                         // the copy of step s + kRrcAhead is issued at the top of step s
@@ -149,8 +153,8 @@ __global__ void __launch_bounds__(kRrcThreads, 1) rr_chain_kernel(const __grid_c
 
   // the CTA's second sample tile may lie beyond the batch: its warps leave, the ring counts the others
   const long long ntiles = (M.B + kTcRows - 1) / kTcRows;
-  const long long tile_first = A.tile0 / kTcRows + (long long)blockIdx.x * 2;
-  const int nact = tile_first + 1 < ntiles ? kRrcWarps : kRrcWarps / 2;
+  const long long tile_first = A.tile0 / kTcRows + (long long)blockIdx.x * kRrcTiles;
+  const int nact = tile_first + kRrcTiles <= ntiles ? kRrcWarps : 8;
 
   uint8_t *ring = smem;  // [kRrcStages][kSite]
   uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)kRrcStages * kSite), *empty = full + kRrcStages;
