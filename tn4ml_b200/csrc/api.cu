@@ -72,6 +72,7 @@ static Knobs read_knobs() {
   k.da_rm = geti("TNB_DA_RM", 0);
   k.rr = geti("TNB_RR", 1);
   k.rr_chain = geti("TNB_RR_CHAIN", 1);
+  k.rr_da = geti("TNB_RR_DA", 1);
 #ifdef TNB_TC_TRACE
   k.tc_dbg = geti("TNB_TC_DBG", 0);
 #endif

@@ -2,6 +2,7 @@
 // Kernel: mps_rr_chain.cuh.  Called from the tcgen05 family's sweep launcher (mps_tc.cu) when the plan selects it.
 #include "host.h"
 #include "mps_rr_chain.cuh"
+#include "mps_rr_da.cuh"
 
 namespace tnb {
 
@@ -11,9 +12,13 @@ namespace tnb {
 #endif
 static size_t rrc_smem(int d, int steps) { return (size_t)kRrcStages * 4096 * d + 128 + (size_t)(steps + 2) * 8 + TNB_RRC_PAD_SMEM; }
 
+static constexpr size_t kRdSmem = (size_t)kRdWarps * kRdStages * kRdStage + (size_t)kRdWarps * kRdStages * 8;
+
 cudaError_t mps_rr_set_attrs() {
   cudaError_t e = cudaFuncSetAttribute(rr_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(rr_chain_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(rr_da_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRdSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(rr_da_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRdSmem);
   return e;
 }
 
@@ -31,6 +36,25 @@ int mps_rr_launch_sweep(const TcArgs &T, int d, long long B, int adjoint, cudaSt
   if (d == 2) rr_chain_kernel<2><<<grid, kRrcThreads, smem, st>>>(T, adjoint);
   else rr_chain_kernel<3><<<grid, kRrcThreads, smem, st>>>(T, adjoint);
   TNB_LAUNCH_CHECK(adjoint ? "rr_chain_kernel(adj)" : "rr_chain_kernel(fwd)");
+  return 0;
+}
+
+// weight gradients of the chain sites [Da.site0, Da.site0 + nsites) at bond 32 (the class site is skipped: tc_da_kernel's pass 1);
+// Da as filled by mps_tc_backward (operands, weights, output)
+int mps_rr_launch_da(const TcDaArgs &Da_in, int d, long long B, int nsites, cudaStream_t st) {
+  TcDaArgs Da = Da_in;
+  // split the batch so that the grid is a few waves of 2 CTAs per SM; one split (a single writer per entry) when deterministic
+  long long nsplit = deterministic() ? 1 : (148LL * 2 * 3 + nsites - 1) / nsites;
+  const long long maxsp = (B + 1023) / 1024;  // at least 8 chunks of 16 samples per warp
+  if (nsplit > maxsp) nsplit = maxsp;
+  if (nsplit < 1) nsplit = 1;
+  Da.nsplit = (int)nsplit;
+  Da.bchunk = ((B + nsplit - 1) / nsplit + 127) / 128 * 128;
+  dim3 grid((unsigned)nsplit, (unsigned)nsites);
+  prof_begin(st);
+  if (d == 2) rr_da_kernel<2><<<grid, kRdWarps * 32, kRdSmem, st>>>(Da);
+  else rr_da_kernel<3><<<grid, kRdWarps * 32, kRdSmem, st>>>(Da);
+  TNB_LAUNCH_CHECK("rr_da_kernel");
   return 0;
 }
 

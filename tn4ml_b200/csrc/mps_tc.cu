@@ -7,6 +7,7 @@
 namespace tnb {
 
 int mps_rr_launch_sweep(const TcArgs &T, int d, long long B, int adjoint, cudaStream_t st);  // mps_rr.cu
+int mps_rr_launch_da(const TcDaArgs &Da, int d, long long B, int nsites, cudaStream_t st);    // mps_rr.cu
 
 static void fill_tc_args(const MpsPlan &P, void *ws, const MpsArgs<float> &M, TcArgs &T) {
   char *w = (char *)ws;
@@ -228,6 +229,10 @@ int mps_tc_backward(const tnb_problem *p, const MpsPlan &P, long long B, const v
     Da.only_site = pass == 0 ? -1 : p->out_site;
     Da.wq = pass == 0 ? Tc.wq : Tc.wqc;
     Da.qmax = pass == 0 ? Tc.qmax : Tc.qmaxc;
+    if (pass == 0 && P.tc_rr && knobs().rr_da) {  // bond 32: the chain sites' gradients register resident on mma.sync
+      if (mps_rr_launch_da(Da, p->d, B, s1 - s0, st)) return 1;
+      continue;
+    }
     Da.mgroups = ((p->chi + Da.ra - 1) / Da.ra) * ((Da.Dv + Da.cpg - 1) / Da.cpg);
     // split K (the batch) so that the grid fills the 148 SMs about four times over with little wave quantisation
     const long long ctas = (long long)(pass == 0 ? s1 - s0 : 1) * Da.mgroups;
