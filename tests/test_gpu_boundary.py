@@ -29,8 +29,8 @@ def _mps_case(dtype, chi, L=10, C_=4, B=300, seed=3):
     return model, eng, x.cuda(), t.cuda()
 
 
-@pytest.mark.parametrize("dtype,chi", [(torch.float32, 64), (torch.float64, 24), (torch.float32, 256)],
-                         ids=["f32_tensor_chi64", "f64_simt", "f32_tensor_chi256"])
+@pytest.mark.parametrize("dtype,chi", [(torch.float32, 64), (torch.float64, 24), (torch.float32, 256), (torch.float32, 32)],
+                         ids=["f32_tensor_chi64", "f64_simt", "f32_tensor_chi256", "f32_bond32_rr"])
 def test_step_is_cuda_graph_capturable(dtype, chi):
     """Capture forward(keep_stash) + backward + the fused Adam update into one CUDA graph, replay it twice, and compare with
     the same two steps run eagerly (bitwise for the loss sum of step 1; gradients to accumulation-order noise)."""
@@ -208,7 +208,8 @@ def test_two_gpu_allreduced_gradient_equals_one_gpu_gradient(dtype_name, chi):
     assert loss_err <= tol and grad_err <= tol
 
 
-@pytest.mark.parametrize("dtype,chi", [(torch.float32, 64), (torch.float64, 24)], ids=["f32_tensor", "f64_simt"])
+@pytest.mark.parametrize("dtype,chi", [(torch.float32, 64), (torch.float32, 32), (torch.float64, 24)],
+                         ids=["f32_tensor", "f32_bond32_rr", "f64_simt"])
 def test_deterministic_mode_gives_bitwise_identical_gradients(dtype, chi):
     """SURVEY 8e "Determinism": with tnb_set_deterministic(1) every gradient entry has one writer in a fixed order."""
     from tn4ml_b200 import _lib
@@ -226,3 +227,28 @@ def test_deterministic_mode_gives_bitwise_identical_gradients(dtype, chi):
         lib.tnb_set_deterministic(0)
     tol = 1e-4 if dtype == torch.float32 else 1e-12  # (another accumulation order: float32 rounding, not bitwise)
     assert float((g1 - g0).abs().max()) <= tol * float(g0.abs().max())
+
+
+@pytest.mark.parametrize("chi", [32, 64], ids=["bond32_rr", "bond64_tcgen05"])
+def test_backward_in_site_ranges_equals_one_piece(chi):
+    """tnb_backward_part (the data-parallel step's site ranges) on one GPU with a reducer that does nothing: the packed gradient
+    equals the one-piece backward pass up to the order of the float32 atomics."""
+    model, eng, x, t = _mps_case(torch.float32, chi, L=11, B=700)
+
+    class _NoReduce:
+        nparts = 4
+        calls = 0
+
+        def reduce(self, tensor):
+            self.calls += 1
+
+        def finish(self):
+            pass
+
+    ls0, g0 = eng.value_and_grad(model._packed, x, t)
+    ls0, g0 = float(ls0.item()), g0.clone()
+    red = _NoReduce()
+    ls1, g1 = eng.value_and_grad(model._packed, x, t, reducer=red)
+    assert red.calls >= 2
+    assert abs(float(ls1.item()) - ls0) <= 1e-6 * abs(ls0)
+    assert float((g1 - g0).abs().max()) <= 1e-5 * float(g0.abs().max())
