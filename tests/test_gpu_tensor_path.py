@@ -148,3 +148,53 @@ def test_rr_chain_nll_and_long_chain():
     model = _tensor_model(T.TensorNetwork, arrays)
     _check(model, O.Problem("mps", O.EmbSpec("trig"), "softmax_xent"), _heads()["softmax_xent"], x, arrays, t, torch.float32,
            precision=1)
+
+
+def _launched_kernels(fn):
+    """Names of the library's kernels launched by fn() (tnb_profile: every launch bracketed with CUDA events)."""
+    import ctypes as C
+    from tn4ml_b200 import _lib
+    lib = _lib.lib()
+    lib.tnb_profile(1)
+    try:
+        fn()
+        torch.cuda.synchronize()
+        nmax = 4096
+        names = C.create_string_buffer(48 * nmax)
+        ms = (C.c_float * nmax)()
+        n = lib.tnb_profile_read(names, ms, nmax)
+        return {names.raw[i * 48:(i + 1) * 48].split(b"\0")[0].decode() for i in range(n)}
+    finally:
+        lib.tnb_profile(0)
+
+
+@pytest.mark.parametrize("case", [
+    dict(L=20, chi=10, d=2, cls=9, C=10, B=64, kw={}),                          # BASELINE cfg 1's bond and batch
+    dict(L=9, chi=24, d=3, cls=4, C=2, B=130, kw={}),                           # d = 3 (252-register dA variant)
+    dict(L=8, chi=16, d=2, cls=3, C=3, B=77, kw={}),
+    dict(L=10, chi=31, d=2, cls=0, C=4, B=200, kw={}),                          # odd bond, class site on the boundary
+], ids=["chi10_cfg1", "chi24_d3", "chi16", "chi31_cls0"])
+def test_small_bonds_run_zero_padded_on_the_register_resident_family(case):
+    """float32 bonds of 8 .. 31 (d = 2, 3): the library builds bond-32 weight images from the caller's [chi][chi][d] slabs and
+    runs the mma.sync kernels; gradients come back in the caller's layout.  Oracle parity at 1e-4 and the kernels that ran."""
+    import tn4ml_b200 as T
+    arrays = O.make_mps_arrays(case["L"], case["chi"], case["d"], class_site=case["cls"], C=case["C"], std=0.05, seed=21)
+    x = O.make_inputs(case["B"], case["L"], seed=22)
+    t = O.make_labels(case["B"], case["C"])
+    emb = {2: O.EmbSpec("trig"), 3: O.EmbSpec("poly", degree=2, include_bias=True)}[case["d"]]
+    model = _tensor_model(T.TensorNetwork, arrays)
+    seen = _launched_kernels(lambda: _check(model, O.Problem("mps", emb, "softmax_xent"), _heads()["softmax_xent"], x, arrays, t,
+                                            torch.float32, precision=1))
+    assert {"rr_chain_kernel(fwd)", "rr_chain_kernel(adj)", "rr_da_kernel", "tc_da_kernel(class)"} <= seen, seen
+    assert not any(k.startswith("mps_sweep") or k.startswith("tc_chain") for k in seen), seen
+
+
+def test_small_bond_ragged_shapes_and_nll_zero_padded():
+    """Ragged ("noteven") bonds and squeezed boundaries below 32, NLL head: the padded path against the oracle."""
+    import tn4ml_b200 as T
+    arrays = O.make_mps_arrays(14, 12, 2, std=0.05, seed=4, squeeze_ends=True, shape_method="noteven", identity_all=True)
+    x = O.make_inputs(150, 14, seed=6)
+    model = _tensor_model(T.MatrixProductState, arrays)
+    seen = _launched_kernels(lambda: _check(model, O.Problem("mps", O.EmbSpec("trig"), "nll"), _heads()["nll"], x, arrays, None,
+                                            torch.float32, precision=1))
+    assert "rr_da_kernel" in seen, seen

@@ -156,19 +156,29 @@ static int validate(const tnb_problem *p) {
   return 0;
 }
 
+// Bond the tensor path runs at.  Bonds of 8 .. 31 (float32, d = 2 or 3) run ZERO-PADDED to 32 on the register-resident mma.sync
+// family: the weight images are built padded from the caller's [chi][chi][d] slabs, the environments' extra entries stay exactly
+// zero, and the gradient kernels write the caller's layout.  (Measured against the SIMT fp32 family at L = 196: chi = 10: 0.68 ->
+// 0.35 ms per step at B = 64, 9.2 M -> 31.8 M samples/s at B = 65536; chi = 24: 6.0 M -> 31.3 M samples/s.)
+static int tc_bond(const tnb_problem *p) {
+  if (p->chi >= 8 && p->chi < 32 && (p->d == 2 || p->d == 3) && knobs().rr_chain && knobs().rr_da) return 32;
+  return p->chi;
+}
+
 // The tcgen05 sweep covers: float32, chi a multiple of 16 in [32, 256], D*chi <= 512 TMEM columns.
 static bool tc_supported(const tnb_problem *p) {
   if (p->kind != TNB_KIND_MPS || p->dtype != TNB_F32 || p->precision != TNB_PREC_TENSOR) return false;
-  if (p->chi % 16 != 0 || p->chi < 32 || p->chi > 256) return false;
-  if (p->d * p->chi > 512) return false;
+  const int chi = tc_bond(p);
+  if (chi % 16 != 0 || chi < 32 || chi > 256) return false;
+  if (p->d * chi > 512) return false;
   if (!(p->d == 2 || p->d == 3 || p->d == 4 || p->d == 6 || p->d == 8)) return false;
   return true;
 }
 
 // Column chunks per chain step: the smallest NH dividing chi/16 whose chunk (D*chi/NH columns) fits one MMA (N <= 256).
-static int tc_pick_nh(const tnb_problem *p) {
-  const int groups = p->chi / 16;
-  auto legal = [&](int nh) { return nh >= 1 && nh <= kTcMaxNH && groups % nh == 0 && p->d * p->chi / nh <= 256; };
+static int tc_pick_nh(const tnb_problem *p, int chi) {
+  const int groups = chi / 16;
+  auto legal = [&](int nh) { return nh >= 1 && nh <= kTcMaxNH && groups % nh == 0 && p->d * chi / nh <= 256; };
   if (legal(knobs().tc_nh)) return knobs().tc_nh;
   for (int nh = 1; nh <= groups; ++nh)
     if (legal(nh)) return nh;
@@ -219,13 +229,15 @@ MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
   // decide the kernel family (incl. the shared-memory check of the tensor path) BEFORE laying out the workspace, so that
   // the SIMT buffers always exist when the SIMT family will run
   P.tc = tc_supported(p) ? 1 : 0;
+  P.tc_chi = tc_bond(p);
   if (P.tc) {
-    P.tc_N = p->d * p->chi;
-    P.tc_NH = tc_pick_nh(p);
+    const int tchi = P.tc_chi;
+    P.tc_N = p->d * tchi;
+    P.tc_NH = tc_pick_nh(p, tchi);
     P.tc_NMMA = P.tc_N / P.tc_NH;
     P.tc_stage_bytes = 64u * P.tc_NMMA;  // one K-slab (16 rows) of one column chunk, hi and lo planes
-    P.tc_site_img = (size_t)P.tc_NH * (p->chi / 16) * P.tc_stage_bytes;  // (stage_bytes: still the whole stage here)
-    const size_t a_bytes = (size_t)2 * kTcRows * p->chi * 2;
+    P.tc_site_img = (size_t)P.tc_NH * (tchi / 16) * P.tc_stage_bytes;  // (stage_bytes: still the whole stage here)
+    const size_t a_bytes = (size_t)2 * kTcRows * tchi * 2;
     // two sample tiles per CTA when one column chunk covers the step (nothing else hides the epilogue); TNB_TC_TILES=1 forces one
     // (pays when the step's MMA time is comparable to its exposed tail: N = 256; measured slower at N <= 128)
     P.tc_tiles = (P.tc_NH == 1 && P.tc_N == 256) ? 2 : 1;
@@ -233,20 +245,21 @@ MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
     if (knobs().tc_tiles == 2 && P.tc_NH == 1 && (p->d == 2 || p->d == 4 || p->d == 8)) P.tc_tiles = 2;
     // CTA pair (cta_group::2), opt-in: the wide-bond case (chi > 128, d = 2).  Parity-green; within the box-to-box spread of
     // the one-CTA kernel under the power cap, hence not the default.
-    P.tc_cg = (p->chi > 128 && p->d == 2 && P.tc_tiles == 1 && knobs().tc_cg == 2) ? 2 : 1;
+    P.tc_cg = (tchi > 128 && p->d == 2 && P.tc_tiles == 1 && knobs().tc_cg == 2) ? 2 : 1;
     P.tc_stage_bytes /= (uint32_t)P.tc_cg;  // one CTA's half of a stage
     P.tc_cols = 32;
     while (P.tc_cols < P.tc_tiles * P.tc_N) P.tc_cols <<= 1;
     // small steps (one column chunk of at most 256 columns, bond up to 64, one tile): the 352-thread kernel, two CTAs per SM,
     // each with half of the shared memory and at most 256 TMEM columns
-    P.tc_ngrp = (P.tc_NH == 1 && P.tc_N <= 256 && p->chi <= 64 && P.tc_tiles == 1 && P.tc_cg == 1 && knobs().tc_ngrp2) ? 2 : 4;
+    P.tc_ngrp = (P.tc_NH == 1 && P.tc_N <= 256 && tchi <= 64 && P.tc_tiles == 1 && P.tc_cg == 1 && knobs().tc_ngrp2) ? 2 : 4;
     const size_t fixed = (size_t)P.tc_tiles * 4096 /* row exchange */ + 1024 /* tables, barriers */;
     const long smem_cap = P.tc_ngrp == 2 ? (long)kTcSmemMax / 2 - 1024 : (long)kTcSmemMax;
     long ns = (long)((smem_cap - (long)fixed - (long)(P.tc_tiles * a_bytes)) / (long)P.tc_stage_bytes);
     P.tc_nstage = ns > 12 ? 12 : (int)ns;
     P.tc_smem = P.tc_tiles * a_bytes + (size_t)P.tc_nstage * P.tc_stage_bytes + fixed;
     if (P.tc_nstage < 2) P.tc = 0;
-    P.tc_rr = (P.tc && P.tc_NH == 1 && P.tc_cg == 1 && mps_rr_supported(p)) ? 1 : 0;
+    P.tc_rr = (P.tc && P.tc_NH == 1 && P.tc_cg == 1 && tchi == 32 && mps_rr_supported(p)) ? 1 : 0;
+    if (tchi != p->chi && !P.tc_rr) P.tc = 0;  // (a padded bond has no tcgen05 kernels)
   }
   const bool tc_mode = P.tc != 0;
   size_t fslots = need_grad ? (size_t)p->L + 1 : 2;
@@ -260,7 +273,7 @@ MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
   if (P.tc) {
     // the tensor path keeps its environments as fp16 hi/lo bond images instead of F / G
     const size_t span = (size_t)kTcRows * P.tc_cg;  // a CTA pair always writes both tiles
-    P.img_bond_bytes = (size_t)((B + span - 1) / span * span) * p->chi * 4;  // whole 128-sample tiles
+    P.img_bond_bytes = (size_t)((B + span - 1) / span * span) * P.tc_chi * 4;  // whole 128-sample tiles
     P.off_fimg = take((need_grad ? (size_t)p->L + 1 : 1) * P.img_bond_bytes);
     P.off_img_n = take(P.tc_site_img * P.nslab);
     P.off_img_t = take(P.tc_site_img * P.nslab);

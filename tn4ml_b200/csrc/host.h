@@ -70,6 +70,7 @@ struct MpsPlan {
   int RB;  // register-tile rows of the SIMT sweep / class kernels
   // tensor-core sweep (f32, TNB_PREC_TENSOR)
   int tc, tc_N, tc_NH, tc_NMMA, tc_nstage, tc_cols, tc_tiles, tc_cg, tc_ngrp;
+  int tc_chi;  // bond of the tensor path's images and kernels: p->chi, or 32 when a smaller bond runs zero-padded on the register-resident family
   int tc_rr;  // bond 32: the chains run register resident on mma.sync (mps_rr_chain.cuh); images, stash and dA GEMM as planned
   uint32_t tc_stage_bytes;
   size_t tc_site_img, off_img_n, off_img_t, off_kW, off_cs, off_wq, off_qmax, off_wqc, off_fimg, off_gimg, tc_smem, img_bond_bytes;

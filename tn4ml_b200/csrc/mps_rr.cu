@@ -23,7 +23,7 @@ cudaError_t mps_rr_set_attrs() {
 }
 
 bool mps_rr_supported(const tnb_problem *p) {
-  return knobs().rr_chain && p->kind == TNB_KIND_MPS && p->dtype == TNB_F32 && p->chi == 32 && (p->d == 2 || p->d == 3) &&
+  return knobs().rr_chain && p->kind == TNB_KIND_MPS && p->dtype == TNB_F32 && p->chi <= 32 && (p->d == 2 || p->d == 3) &&
          rrc_smem(p->d, p->L + p->n_out) <= (size_t)kTcSmemMax;
 }
 

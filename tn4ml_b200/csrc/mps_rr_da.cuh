@@ -169,13 +169,15 @@ __global__ void __launch_bounds__(kRdWarps * 32, D == 2 ? 2 : 1) rr_da_kernel(co
   }
   __syncthreads();
   const float sc = rrc_pow2(qmax - 2 * kTcKA);
-  const size_t site_off = (size_t)site * 32 * 32 * D + (site > c ? (size_t)32 * 32 * D * (M.C - 1) : 0);
+  const int chi_w = M.chi;  // bond of the caller's gradient slabs (< 32 when the path runs zero-padded)
+  const size_t site_off = (size_t)site * chi_w * chi_w * D + (site > c ? (size_t)chi_w * chi_w * D * (M.C - 1) : 0);
   float *gout = A.grads + site_off;
   for (int e = tid; e < kTile; e += kRdWarps * 32) {
     float v = 0.f;
 #pragma unroll
     for (int w = 0; w < kRdWarps; ++w) v += red[(size_t)w * kTile + e];
-    atomicAdd(&gout[e], v * sc);
+    const int a = e / (32 * D), r = (e / D) & 31, s_ = e % D;
+    if (a < chi_w && r < chi_w) atomicAdd(&gout[((size_t)a * chi_w + r) * D + s_], v * sc);
   }
 }
 

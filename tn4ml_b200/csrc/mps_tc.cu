@@ -104,7 +104,7 @@ static int tc_launch_sweep(const tnb_problem *p, const MpsPlan &P, const TcArgs 
                            cudaStream_t st) {
   if (P.tc_rr) return mps_rr_launch_sweep(T, p->d, B, adjoint, st);  // bond 32: register-resident chains on mma.sync
   cudaError_t e = cudaSuccess;
-  const bool wide = p->chi > 128;   // 16-column groups per epilogue thread: 4 (chi <= 256) or 2 (chi <= 128)
+  const bool wide = P.tc_chi > 128;   // 16-column groups per epilogue thread: 4 (chi <= 256) or 2 (chi <= 128)
   const long long ntiles = (B + kTcRows - 1) / kTcRows;
   // Two-tile CTAs take whole rounds of 148 SMs (per half of the adjoint grid); the remaining tiles run as one-tile
   // CTAs behind them, so that the last round is not half empty with double-length CTAs.
@@ -159,6 +159,7 @@ int mps_tc_forward(const tnb_problem *p, const MpsPlan &P, long long B, const vo
                    void *ws, cudaStream_t st) {
   MpsArgs<float> A;
   fill_mps_args<float>(p, P, B, x, targets, ws, A);
+  A.chip = P.tc_chi;  // the tensor path's bond (32 for a zero-padded smaller one); A.chi stays the caller's
   A.stash = keep_stash ? 1 : 0;
   A.loss = (float *)loss; A.loss_sum = loss_sum; A.out = (float *)out; A.out_exp = out_exp;
   // weight images, then ONE kernel for both chains, the class site and the head
@@ -173,12 +174,12 @@ int mps_tc_forward(const tnb_problem *p, const MpsPlan &P, long long B, const vo
   prof_begin(st);
   tc_finalize_kernel<<<1, 256, 0, st>>>((int *)Tc.kW, (float *)Tc.colsum, p->L, p->n_out, p->out_site);
   TNB_LAUNCH_CHECK("tc_finalize_kernel");
-  size_t items = (size_t)P.tc_N * (p->chi / 8) * P.nslab;
+  size_t items = (size_t)P.tc_N * (P.tc_chi / 8) * P.nslab;
   int ib = (int)((items + 255) / 256);
   if (ib > 148 * 32) ib = 148 * 32;
   prof_begin(st);
   tc_image_kernel<<<ib, 256, 0, st>>>((const float *)params, Tc.kW, (uint8_t *)Tc.img_n, (uint8_t *)Tc.img_t, p->L,
-                                      p->chi, p->d, p->n_out, p->out_site, P.tc_NH, P.tc_cg);
+                                      p->chi, P.tc_chi, p->d, p->n_out, p->out_site, P.tc_NH, P.tc_cg);
   TNB_LAUNCH_CHECK("tc_image_kernel");
   return tc_launch_sweep(p, P, Tc, B, 0, st);
 }
@@ -187,6 +188,7 @@ int mps_tc_backward(const tnb_problem *p, const MpsPlan &P, long long B, const v
                     double loss_scale, void *grads, int accumulate, void *ws, cudaStream_t st, int part, int nparts) {
   MpsArgs<float> A;
   fill_mps_args<float>(p, P, B, x, targets, ws, A);
+  A.chip = P.tc_chi;
   A.stash = 1;
   A.loss_scale = (float)loss_scale;
   TcArgs Tc;
@@ -207,18 +209,19 @@ int mps_tc_backward(const tnb_problem *p, const MpsPlan &P, long long B, const v
   Da.img_bond_bytes = Tc.img_bond_bytes;
   // stages sized by the bond: the U region is fixed (a virtual image of 256 rows), the V chunk is chi * 4 * kDaKC bytes.
   // Bonds up to 64: two CTAs of 8 producer warps per SM (see tc_da_kernel), each with half of the shared memory.
-  Da.stage_bytes = (uint32_t)align_up((size_t)kDaU + (size_t)p->chi * 4 * kDaKC, 1024);
+  const int tchi = P.tc_chi;
+  Da.stage_bytes = (uint32_t)align_up((size_t)kDaU + (size_t)tchi * 4 * kDaKC, 1024);
   // da_small: largest bond that takes the several-CTAs-per-SM variants (knob TNB_DA_SMALL; 0 = never)
-  const bool small = p->chi <= knobs().da_small;
-  const int ncta = !small ? 1 : ((p->chi <= 32 && knobs().da_pw4) ? 3 : 2);   // CTAs per SM the stages are sized for
+  const bool small = tchi <= knobs().da_small;
+  const int ncta = !small ? 1 : ((tchi <= 32 && knobs().da_pw4) ? 3 : 2);   // CTAs per SM the stages are sized for
   const size_t smem_avail = (size_t)(kTcSmemMax - 2048) / ncta - 1024 - (ncta > 1 ? 1024 : 0);
   Da.nstage = (int)(smem_avail / Da.stage_bytes);
   if (Da.nstage > 6) Da.nstage = 6;
   if (knobs().da_stages >= 2 && knobs().da_stages < Da.nstage) Da.nstage = knobs().da_stages;
   Da.tmem_cols = 32;
-  while (Da.tmem_cols < 2 * p->chi) Da.tmem_cols <<= 1;
+  while (Da.tmem_cols < 2 * tchi) Da.tmem_cols <<= 1;
   const long long maxsp = (B + 2047) / 2048;
-  Da.ra = p->chi < 128 ? p->chi : 128;
+  Da.ra = tchi < 128 ? tchi : 128;
   Da.cpg = 256 / Da.ra;
   Da.site0 = s0;
   for (int pass = 0; pass < 2; ++pass) {
@@ -233,7 +236,7 @@ int mps_tc_backward(const tnb_problem *p, const MpsPlan &P, long long B, const v
       if (mps_rr_launch_da(Da, p->d, B, s1 - s0, st)) return 1;
       continue;
     }
-    Da.mgroups = ((p->chi + Da.ra - 1) / Da.ra) * ((Da.Dv + Da.cpg - 1) / Da.cpg);
+    Da.mgroups = ((tchi + Da.ra - 1) / Da.ra) * ((Da.Dv + Da.cpg - 1) / Da.cpg);
     // split K (the batch) so that the grid fills the 148 SMs about four times over with little wave quantisation
     const long long ctas = (long long)(pass == 0 ? s1 - s0 : 1) * Da.mgroups;
     // ... and so that no TMEM accumulator takes more than ~3 k MMAs: tcgen05 accumulates with truncation, and a coherent

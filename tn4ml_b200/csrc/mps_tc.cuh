@@ -156,7 +156,8 @@ static __global__ void tc_finalize_kernel(int *__restrict__ kW, float *__restric
 // Stage (h, ks) of a slab holds the K-slab ks of column chunk h: columns n'' = s*chi_h + (n - h*chi_h).
 // cg = 2 (CTA pair): a stage is [rank][plane hi|lo][NMMA / 2 columns], rank r holding the columns the r-th CTA supplies.
 static __global__ void tc_image_kernel(const float *__restrict__ params, const int *__restrict__ kW, uint8_t *__restrict__ img_n,
-                                uint8_t *__restrict__ img_t, int L, int chi, int D, int C, int c, int NH, int cg) {
+                                uint8_t *__restrict__ img_t, int L, int chi_w, int chi, int D, int C, int c, int NH, int cg) {
+  // chi_w: bond of the caller's [chi_w][chi_w][D] slabs; chi >= chi_w: bond of the images (entries beyond chi_w are zero)
   const int nslab = L - 1 + C;
   const int N = D * chi, KO = chi / 8, KS = chi / 16;
   const int chi_h = chi / NH, NMMA = N / NH;
@@ -175,7 +176,7 @@ static __global__ void tc_image_kernel(const float *__restrict__ params, const i
     if (slab < c) { site = slab; o = 0; nj = 1; }
     else if (slab < c + C) { site = c; o = slab - c; nj = C; }
     else { site = slab - C + 1; o = 0; nj = 1; }
-    const size_t site_off = (size_t)site * chi * chi * D + (site > c ? (size_t)chi * chi * D * (C - 1) : 0);
+    const size_t site_off = (size_t)site * chi_w * chi_w * D + (site > c ? (size_t)chi_w * chi_w * D * (C - 1) : 0);
     const float sc = ldexpf(1.f, kW[slab]);
     const int ks = ko / 2, kc = ko & 1;
     const int ncol = NMMA / cg;  // columns per CTA
@@ -189,7 +190,7 @@ static __global__ void tc_image_kernel(const float *__restrict__ params, const i
       for (int j = 0; j < 8; ++j) {
         const int k = ko * 8 + j;
         const int a = dir == 0 ? k : n, r = dir == 0 ? n : k;
-        const float w = params[site_off + (((size_t)a * chi + r) * D + s) * nj + o] * sc;
+        const float w = (a < chi_w && r < chi_w) ? params[site_off + (((size_t)a * chi_w + r) * D + s) * nj + o] * sc : 0.f;
         hi[j] = __float2half_rn(w);
         lo[j] = __float2half_rn(w - __half2float(hi[j]));
       }
@@ -469,7 +470,8 @@ __global__ void __launch_bounds__(PW * 32 + 64, PW == 16 ? 1 : (PW == 8 ? 2 : 3)
       ptx::mbar_wait(done, 0);
       ptx::tc_fence_after();
       const float sc = ldexpf(1.f, qmax - 2 * kTcKA);
-      const size_t site_off = (size_t)site * chi * chi * M.D + (site > c ? (size_t)chi * chi * M.D * (M.C - 1) : 0);
+      const int chi_w = M.chi;  // bond of the caller's gradient slabs (< chi when the tensor path runs zero-padded)
+      const size_t site_off = (size_t)site * chi_w * chi_w * M.D + (site > c ? (size_t)chi_w * chi_w * M.D * (M.C - 1) : 0);
       float *g = A.grads + site_off;
       if (ra == 128 && ncopy == 2) {
         // tile t == copy t of rows a0 .. a0+127: transpose 32 rows x (16 columns x 2 copies) through shared memory (the
@@ -492,7 +494,7 @@ __global__ void __launch_bounds__(PW * 32 + 64, PW == 16 ? 1 : (PW == 8 ? 2 : 3)
           for (int rr = 0; rr < 32; ++rr) {
             const int a = abase + rr;
             if (a >= a0 + ra_eff) break;
-            atomicAdd(&g[((size_t)a * chi + n0 + (lane >> 1)) * Dv + sig0 + (lane & 1)], stg[rr * 33 + lane]);
+            atomicAdd(&g[((size_t)a * chi_w + n0 + (lane >> 1)) * Dv + sig0 + (lane & 1)], stg[rr * 33 + lane]);  // (chi_w == chi: bonds of 128 and more are never padded)
           }
         }
       } else {
@@ -500,7 +502,7 @@ __global__ void __launch_bounds__(PW * 32 + 64, PW == 16 ? 1 : (PW == 8 ? 2 : 3)
           if (t * 128 + warp * 32 >= nrows) continue;  // warp-uniform: tcgen05.ld is a warp-collective instruction
           const int mm = t * 128 + tid;
           const int sl = mm / ra, al = mm - sl * ra;
-          const bool on = sl < ncopy && al < ra_eff;
+          const bool on = sl < ncopy && al < ra_eff && a0 + al < chi_w;
           const int a = a0 + al, sg = sig0 + sl;
           const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)t * chi;
           for (int n0 = 0; n0 < chi; n0 += 16) {
@@ -509,7 +511,8 @@ __global__ void __launch_bounds__(PW * 32 + 64, PW == 16 ? 1 : (PW == 8 ? 2 : 3)
             ptx::tmem_ld_wait();
             if (on) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) atomicAdd(&g[((size_t)a * chi + n0 + j) * Dv + sg], v[j] * sc);
+              for (int j = 0; j < 16; ++j)
+                if (n0 + j < chi_w) atomicAdd(&g[((size_t)a * chi_w + n0 + j) * Dv + sg], v[j] * sc);
             }
           }
         }
