@@ -283,7 +283,7 @@ def quick_point(args, chi, dtype, dev, steps=10, batch=None, microbatch=0):
 
 def other_configs(dev):
     """Device-resident fwd+bwd throughput of the other BASELINE.json configs (the parity-test cases of the contract; quoted here
-    so that the driver's record holds them too): cfg 2 (MPS classifier, polynomial d = 3, chi = 32), cfg 3 (SMPO L = 784,
+    so that the driver's record holds them too): cfg 1 (MPS classifier, chi = 10, batch 64), cfg 2 (MPS classifier, polynomial d = 3, chi = 32), cfg 3 (SMPO L = 784,
     spacing 8, chi = 32, batch 4096; float32 and the reference's float64), cfg 4 (MPS NLL, Fourier d = 8, chi = 64)."""
     import tn4ml_b200 as T
     from tn4ml_b200 import metrics as M, synthetic as S
@@ -340,6 +340,19 @@ def other_configs(dev):
         del eng, model, x, t
     except Exception as exc:  # pragma: no cover
         res["cfg2_poly_classifier_f32"] = {"error": str(exc)[:200]}
+    torch.cuda.empty_cache()
+    for name, dtype in (("cfg1_classifier_f32", torch.float32), ("cfg1_classifier_f64", torch.float64)):
+        try:  # BASELINE configs[0]: L = 196, chi = 10, 10 classes, batch 64 (the reference's own CPU-runnable case; latency bound)
+            L, chi, C, B = 196, 10, 10, 64
+            model = T.TensorNetwork(S.make_mps_arrays(L, chi, 2, class_site=97, C=C, std=1e-2, seed=42, dtype=dtype), dtype=dtype, device=dev)
+            eng, _ = model._engine(T.TrigonometricEmbedding(), lambda *a, **k: M.OptaxWrapper(M.softmax_cross_entropy)(*a, **k).mean(),
+                                   True, dtype)
+            x = torch.from_numpy(1.0 - rng.random((B, L))).to(dev, dtype)
+            t = torch.nn.functional.one_hot(torch.from_numpy(rng.integers(0, C, size=B)), C).to(dev, dtype)
+            res[name] = timed(eng, model, x, t, B, flops_per_sample(L, chi, 2, C, 97), 50)
+            del eng, model, x, t
+        except Exception as exc:  # pragma: no cover
+            res[name] = {"error": str(exc)[:200]}
     torch.cuda.empty_cache()
     return res
 

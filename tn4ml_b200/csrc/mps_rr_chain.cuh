@@ -555,14 +555,14 @@ __global__ void __launch_bounds__(kRrcThreads, 1) rr_chain_kernel(const __grid_c
       }
       // max_b q: one RED per warp and step on ONE address would serialise in L2 (16 k warps x ~100 steps); the value
       // settles after the first few warps, so the current maximum is read ahead of the step and most REDs are skipped
-      const int qseen = lane == 0 ? *reinterpret_cast<const volatile int *>(&A.qmax[site]) : 0;
-      int qm = max(vA ? qA : INT_MIN, vB ? qB : INT_MIN);
-      for (int off = 16; off > 0; off >>= 1) qm = max(qm, __shfl_xor_sync(0xffffffffu, qm, off));
+      // (no warp reduction either: every head lane compares its own row)
+      const int qseen = vH ? *reinterpret_cast<const volatile int *>(&A.qmax[site]) : INT_MAX;
+      const int qm = sel(qA, qB);
       int nA, nB;
       load_ds(s + 1, nA, nB);  // (s + 1 == total: the boundary site)
       int dA, dB;
       chain_step(s, dA, dB);
-      if (lane == 0 && qm > qseen) atomicMax(&A.qmax[site], qm);  // (qmax starts at INT_MIN)
+      if (qm > qseen) atomicMax(&A.qmax[site], qm);  // (qmax starts far below any exponent; invalid rows: qseen = INT_MAX)
       store_image(img_slot(A.gimg, half == 0 ? c - 1 - i : c + 2 + i));
       hA += dA - dsA;
       hB += dB - dsB;
