@@ -198,3 +198,25 @@ def test_small_bond_ragged_shapes_and_nll_zero_padded():
     seen = _launched_kernels(lambda: _check(model, O.Problem("mps", O.EmbSpec("trig"), "nll"), _heads()["nll"], x, arrays, None,
                                             torch.float32, precision=1))
     assert "rr_da_kernel" in seen, seen
+
+
+@pytest.mark.parametrize("case", [
+    dict(L=8, chi=50, d=2, cls=3, C=3, B=140),      # -> 64: the two-CTA small-step kernel, general dA epilogue
+    dict(L=7, chi=20, d=4, cls=2, C=2, B=70),       # -> 32 with d = 4: tcgen05 kernels (the mma.sync family has d = 2, 3)
+    dict(L=7, chi=100, d=2, cls=3, C=4, B=130),     # -> 112: N = 224, one column chunk
+    dict(L=6, chi=120, d=2, cls=2, C=3, B=129),     # -> 128: two-tile CTAs, the transposing dA epilogue with both guards
+    dict(L=6, chi=200, d=2, cls=3, C=2, B=64),      # -> 208: N = 416, two column chunks
+], ids=["chi50", "chi20_d4", "chi100", "chi120", "chi200"])
+def test_bonds_between_the_tensor_kernels_sizes_run_zero_padded(case):
+    """float32 bonds that are not multiples of 16 run zero-padded to the next one on the tcgen05 kernels (weight images padded,
+    gradients in the caller's layout): oracle parity at 1e-4, and no SIMT sweep in the launch list."""
+    import tn4ml_b200 as T
+    arrays = O.make_mps_arrays(case["L"], case["chi"], case["d"], class_site=case["cls"], C=case["C"], std=0.05, seed=31)
+    x = O.make_inputs(case["B"], case["L"], seed=32)
+    t = O.make_labels(case["B"], case["C"])
+    emb = {2: O.EmbSpec("trig"), 4: O.EmbSpec("trig", k=2)}[case["d"]]
+    model = _tensor_model(T.TensorNetwork, arrays)
+    seen = _launched_kernels(lambda: _check(model, O.Problem("mps", emb, "softmax_xent"), _heads()["softmax_xent"], x, arrays, t,
+                                            torch.float32, precision=1))
+    assert "tc_chain_kernel(fwd)" in seen and "tc_da_kernel" in seen, seen
+    assert not any(k.startswith("mps_sweep") for k in seen), seen

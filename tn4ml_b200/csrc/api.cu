@@ -73,6 +73,7 @@ static Knobs read_knobs() {
   k.rr = geti("TNB_RR", 1);
   k.rr_chain = geti("TNB_RR_CHAIN", 1);
   k.rr_da = geti("TNB_RR_DA", 1);
+  k.tc_pad = geti("TNB_TC_PAD", 1);
 #ifdef TNB_TC_TRACE
   k.tc_dbg = geti("TNB_TC_DBG", 0);
 #endif
@@ -156,13 +157,15 @@ static int validate(const tnb_problem *p) {
   return 0;
 }
 
-// Bond the tensor path runs at.  Bonds of 8 .. 31 (float32, d = 2 or 3) run ZERO-PADDED to 32 on the register-resident mma.sync
-// family: the weight images are built padded from the caller's [chi][chi][d] slabs, the environments' extra entries stay exactly
-// zero, and the gradient kernels write the caller's layout.  (Measured against the SIMT fp32 family at L = 196: chi = 10: 0.68 ->
-// 0.35 ms per step at B = 64, 9.2 M -> 31.8 M samples/s at B = 65536; chi = 24: 6.0 M -> 31.3 M samples/s.)
+// Bond the tensor path runs at.  The tensor kernels take bonds that are multiples of 16 from 32 to 256; any other float32 bond
+// from 8 up runs ZERO-PADDED to the next such bond: the weight images are built padded from the caller's [chi][chi][d] slabs, the
+// environments' extra entries stay exactly zero, and the gradient kernels write the caller's layout.  Bonds below 32 with
+// d = 2 or 3 land on the register-resident mma.sync family (measured against the SIMT fp32 family at L = 196: chi = 10: 0.68 ->
+// 0.35 ms per step at B = 64, 9.2 M -> 31.8 M samples/s at B = 65536; chi = 24: 6.0 M -> 31.3 M samples/s).
 static int tc_bond(const tnb_problem *p) {
-  if (p->chi >= 8 && p->chi < 32 && (p->d == 2 || p->d == 3) && knobs().rr_chain && knobs().rr_da) return 32;
-  return p->chi;
+  if (p->chi < 8 || p->chi > 256 || !knobs().tc_pad) return p->chi;
+  const int up = (p->chi + 15) / 16 * 16;
+  return up < 32 ? 32 : up;
 }
 
 // The tcgen05 sweep covers: float32, chi a multiple of 16 in [32, 256], D*chi <= 512 TMEM columns.
@@ -259,7 +262,6 @@ MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
     P.tc_smem = P.tc_tiles * a_bytes + (size_t)P.tc_nstage * P.tc_stage_bytes + fixed;
     if (P.tc_nstage < 2) P.tc = 0;
     P.tc_rr = (P.tc && P.tc_NH == 1 && P.tc_cg == 1 && tchi == 32 && mps_rr_supported(p)) ? 1 : 0;
-    if (tchi != p->chi && !P.tc_rr) P.tc = 0;  // (a padded bond has no tcgen05 kernels)
   }
   const bool tc_mode = P.tc != 0;
   size_t fslots = need_grad ? (size_t)p->L + 1 : 2;

@@ -51,6 +51,7 @@ struct Knobs {
   int tc_nh = 0, tc_tiles = 0, tc_pace_ns = -1, da_stages = 0, tc_cg = 0;
   int simt_rb = 0, simt_nt = 0, simt_kt = 0, simt_dmma = 1, da_rm = 0;
   int rr = 1;
+  int tc_pad = 1;    // TNB_TC_PAD=0: bonds that are not multiples of 16 in [32, 256] stay on the SIMT family (no zero padding)
   int rr_da = 1;     // TNB_RR_DA=0: bond-32 weight gradients stay on tc_da_kernel
   int rr_chain = 1;  // TNB_RR_CHAIN=0: bond-32 MPS chains stay on the tcgen05 kernel (two 352-thread CTAs per SM)
   int tc_ngrp2 = 1;   // TNB_TC_NGRP2=0: never run the 352-thread chain kernel (two CTAs per SM) at small steps

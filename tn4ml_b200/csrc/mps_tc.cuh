@@ -493,8 +493,8 @@ __global__ void __launch_bounds__(PW * 32 + 64, PW == 16 ? 1 : (PW == 8 ? 2 : 3)
           __syncwarp();
           for (int rr = 0; rr < 32; ++rr) {
             const int a = abase + rr;
-            if (a >= a0 + ra_eff) break;
-            atomicAdd(&g[((size_t)a * chi_w + n0 + (lane >> 1)) * Dv + sig0 + (lane & 1)], stg[rr * 33 + lane]);  // (chi_w == chi: bonds of 128 and more are never padded)
+            if (a >= a0 + ra_eff || a >= chi_w) break;
+            if (n0 + (lane >> 1) < chi_w) atomicAdd(&g[((size_t)a * chi_w + n0 + (lane >> 1)) * Dv + sig0 + (lane & 1)], stg[rr * 33 + lane]);
           }
         }
       } else {
