@@ -38,7 +38,11 @@ extern "C" {
 enum { TNB_KIND_MPS = 0, TNB_KIND_SMPO = 1 };
 /* tnb_problem.dtype */
 enum { TNB_F32 = 0, TNB_F64 = 1 };
-/* tnb_problem.precision (f32 only): arithmetic of the chain GEMMs */
+/* tnb_problem.precision (f32 only): arithmetic of the chain GEMMs.
+ * TNB_PREC_TENSOR: fp16x3 on the tensor cores (fp32-class accuracy) for MPS chains with 8 <= chi <= 256 and d in {2, 3, 4, 6, 8}:
+ * tcgen05 / TMEM kernels from bond 32 up, register-resident mma.sync kernels at bonds up to 32 with d = 2, 3; a bond that is not a
+ * multiple of 16 runs zero-padded to the next one INSIDE the library (params / grads keep the caller's [chi][chi][d] slabs).
+ * Any other shape falls back to the SIMT family silently (same results to float32 rounding). */
 enum { TNB_PREC_SIMT = 0, TNB_PREC_TENSOR = 1 };
 /* tnb_embedding.kind -- tn4ml/embeddings.py:287-351, 354-423, 605-717, 544-602, 426-484, 720-869, 872-928 */
 enum {
