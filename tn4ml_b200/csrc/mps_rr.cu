@@ -1,5 +1,8 @@
 // Register-resident MPS chain at bond 32 (float32 tensor family, `mma.sync` fp16x3): host-side launch code.
 // Kernel: mps_rr_chain.cuh.  Called from the tcgen05 family's sweep launcher (mps_tc.cu) when the plan selects it.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "host.h"
 #include "mps_rr_chain.cuh"
 #include "mps_rr_da.cuh"
@@ -32,6 +35,11 @@ int mps_rr_launch_sweep(const TcArgs &T, int d, long long B, int adjoint, cudaSt
   const size_t smem = rrc_smem(d, T.M.L + T.M.C);
   const long long ntiles = (B + kTcRows - 1) / kTcRows;
   dim3 grid((unsigned)((ntiles + kRrcTiles - 1) / kRrcTiles), adjoint ? 2 : 1);  // kRrcTiles sample tiles per CTA
+  if (getenv("TNB_RRC_OCC")) {  // (measurement aid)
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_chain_kernel<2>, kRrcThreads, smem);
+    fprintf(stderr, "[rr_chain] %d threads, %zu B smem: %d CTAs per SM\n", kRrcThreads, smem, nb);
+  }
   prof_begin(st);
   if (d == 2) rr_chain_kernel<2><<<grid, kRrcThreads, smem, st>>>(T, adjoint);
   else rr_chain_kernel<3><<<grid, kRrcThreads, smem, st>>>(T, adjoint);
@@ -43,11 +51,20 @@ int mps_rr_launch_sweep(const TcArgs &T, int d, long long B, int adjoint, cudaSt
 // Da as filled by mps_tc_backward (operands, weights, output)
 int mps_rr_launch_da(const TcDaArgs &Da_in, int d, long long B, int nsites, cudaStream_t st) {
   TcDaArgs Da = Da_in;
-  // split the batch so that the grid is a few waves of 2 CTAs per SM; one split (a single writer per entry) when deterministic
-  long long nsplit = deterministic() ? 1 : (148LL * 2 * 3 + nsites - 1) / nsites;
-  const long long maxsp = (B + 1023) / 1024;  // at least 8 chunks of 16 samples per warp
-  if (nsplit > maxsp) nsplit = maxsp;
-  if (nsplit < 1) nsplit = 1;
+  // split the batch so that the grid is a whole number of rounds of 2 CTAs per SM (all CTAs take the same time: a partly
+  // filled last round is lost bandwidth), at least two rounds, every warp with at least 8 chunks of 16 samples; one split
+  // (a single writer per entry) when deterministic
+  const long long maxsp = (B + 1023) / 1024;
+  const int nwork = nsites - ((Da.M.c >= Da.site0 && Da.M.c < Da.site0 + nsites) ? 1 : 0);  // (the class site's CTAs leave at once)
+  long long nsplit = 1;
+  double best = -1.0;
+  for (long long sp = 1; sp <= maxsp && sp <= 16; ++sp) {
+    const long long n = (long long)(nwork > 0 ? nwork : 1) * sp;
+    const double eff = (double)n / (double)((n + 295) / 296 * 296);
+    const double score = eff - (n < 2 * 296 ? 0.5 : 0.0) - 0.004 * (double)sp;
+    if (score > best) { best = score; nsplit = sp; }
+  }
+  if (deterministic()) nsplit = 1;
   Da.nsplit = (int)nsplit;
   Da.bchunk = ((B + nsplit - 1) / nsplit + 127) / 128 * 128;
   dim3 grid((unsigned)nsplit, (unsigned)nsites);

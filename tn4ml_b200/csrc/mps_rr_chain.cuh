@@ -17,10 +17,13 @@
 //   16-byte unit and the 32 lanes of a warp cover one 128-byte line, so an environment leaves the SM as 16 coalesced
 //   32-bit stores per step and warp, and the weight-gradient GEMM (tc_da_kernel) reads the images unchanged.
 //
-// CTA: 16 warps (two 128-sample tiles), one CTA per SM, 128 registers per thread.  The site images (D * 4 KB per step)
-// come through a ring of bulk async copies issued by the compute warps in turn (warp s % 16 issues the copy of step s + 4
-// at the top of its step s; registers are allocated in units of four warps, so a 17th producer warp capped the kernel at
-// 96 registers and spilled the ring cursor into the step loop: ncu long-scoreboard stalls on the barrier address).  The step's feature
+// CTA: 8 warps (one 128-sample tile), two CTAs per SM, 128 registers per thread.  The site images (D * 4 KB per step)
+// come through a ring of bulk async copies issued by the compute warps in turn (warp s % 8 issues the copy of step s + 4
+// at the top of its step s; registers are allocated in units of four warps, so a 9th producer warp capped the kernel at
+// 96 registers and spilled the ring cursor into the step loop: ncu long-scoreboard stalls on the barrier address).
+// One-tile CTAs (rather than one 16-warp CTA per SM) because all CTAs take the same time: in the last, partly filled
+// round an SM holds one CTA instead of two and that CTA runs 1.5 x faster (cfg-5 batch: 1024 tiles on 148 SMs, forward
+// kernel 1.19 -> 1.09 ms).  The step's feature
 // maps, weight scale and forward exponents are fetched ONE STEP AHEAD and the maps are evaluated underneath the step's
 // HMMAs: with four warps per scheduler nothing else hides a global-load latency in front of every dependent step.
 // Programs, bookkeeping (exps / esum / y / dy / wq / qmax / wqc / qmaxc) and results are those of tc_chain_kernel.
@@ -30,7 +33,7 @@
 namespace tnb {
 
 #ifndef TNB_RRC_WARPS
-#define TNB_RRC_WARPS 16
+#define TNB_RRC_WARPS 8
 #endif
 constexpr int kRrcWarps = TNB_RRC_WARPS;             // warps of 16 samples each: 16 (two sample tiles of 128 per CTA) or 8 (one)
 constexpr int kRrcTiles = kRrcWarps / 8;
@@ -100,7 +103,7 @@ __device__ __forceinline__ float2 rrc_join2(uint32_t hi, uint32_t lo) {
 }
 
 template <int D>
-__global__ void __launch_bounds__(kRrcThreads, 1) rr_chain_kernel(const __grid_constant__ TcArgs A, int adjoint) {
+__global__ void __launch_bounds__(kRrcThreads, kRrcWarps == 16 ? 1 : 2) rr_chain_kernel(const __grid_constant__ TcArgs A, int adjoint) {
   constexpr int NT = 4 * D;                      // n-tiles of 8 accumulator columns: tile s*4 + j holds n = 8j .. 8j+7 of slice s
   constexpr uint32_t kStage = 2048u * D;         // one K-slab (16 rows) of the site image: hi plane, lo plane
   constexpr uint32_t kLoPlane = 1024u * D;
