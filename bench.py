@@ -249,6 +249,15 @@ def ncu_traffic(kernel: str, tiles: int):
     return None, None
 
 
+def measured_peaks():
+    """MEASURED_PEAKS.json (driver-written) or the profiling recipe's fallback figures."""
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pk = {}
+    return {"hbm_gbs": float(pk.get("hbm_gbs", 6454.0)), "bf16_tflops_sustained": float(pk.get("bf16_tflops_sustained", 1400.0))}
+
+
 def quick_point(args, chi, dtype, dev, steps=10, batch=None, microbatch=0):
     """Device-resident fwd+bwd throughput at another bond dimension / dtype (the metric's chi = 32 / 128 points and the
     float64 variant), >= 10 timed steps."""
@@ -276,6 +285,14 @@ def quick_point(args, chi, dtype, dev, steps=10, batch=None, microbatch=0):
     ms = e0.elapsed_time(e1) / steps
     fl = flops_per_sample(args.L, chi, 2, args.classes, c) * B
     out = {"samples_per_s": B / ms * 1e3, "ms_per_step": ms, "tflops": fl / ms / 1e9, "steps": steps, "batch": B}
+    # fractions of both rooflines: tensor pipe (TF32 denominator, float32 only) and HBM -- algorithmic bytes = x +
+    # params in + grads out + loss + ONE environment set written and read once; the small-bond point is bound by the second
+    w = 4 if dtype == torch.float32 else 8
+    nbytes = B * args.L * w + 2 * eng.n_params * w + B * w + 2 * B * args.L * chi * w
+    peaks = measured_peaks()
+    out["hbm_frac"] = nbytes / (ms * 1e-3) / (peaks["hbm_gbs"] * 1e9)
+    if dtype == torch.float32:
+        out["tensor_frac"] = fl / ms / 1e9 / (0.5 * peaks["bf16_tflops_sustained"])
     del eng, model, g, x, t
     torch.cuda.empty_cache()
     return out
@@ -598,7 +615,7 @@ def run_native(args):
         torch.cuda.empty_cache()
         sweep = {str(args.chi): {"samples_per_s": value, "ms_per_step": ms_per_step,
                                  "tflops": fps * B / (ms_per_step * 1e-3) / 1e12, "steps": args.steps, "batch": B}}
-        for chi2 in (128, 32):
+        for chi2 in (128, 64, 32):  # (the metric's chi = 32 / 128 / 256, and the smallest bond of the north star's chi >= 64 target)
             if chi2 != args.chi:
                 try:
                     sweep[str(chi2)] = quick_point(args, chi2, dtype, dev)
