@@ -59,6 +59,23 @@ __device__ __forceinline__ void rrc_ldsm4(uint32_t saddr, uint32_t &r0, uint32_t
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
                : "r"(saddr));
 }
+// mbarrier wait / arrive on a 32-bit shared-memory address (the step loop keeps the ring's barrier addresses as integers)
+__device__ __forceinline__ void rrc_mbar_wait(uint32_t addr, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "RRC_WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra RRC_WAIT_DONE;\n\t"
+      "bra RRC_WAIT_LOOP;\n\t"
+      "RRC_WAIT_DONE:\n\t"
+      "}\n" ::"r"(addr),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void rrc_mbar_arrive(uint32_t addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(addr) : "memory");
+}
 // two scaled floats -> fp16x2 hi and lo words
 __device__ __forceinline__ void rrc_split2(float a, float b, uint32_t &hi, uint32_t &lo) {
   const __half2 h = __floats2half2_rn(a, b);
@@ -207,6 +224,8 @@ __global__ void __launch_bounds__(kRrcThreads, kRrcWarps == 16 ? 1 : 2) rr_chain
   float acc[NT][4];
   int stage = 0, gs = 0;  // ring slot and index of the next step
   uint32_t phase = 0;
+  const uint32_t full_s = ptx::smem_u32(full), empty_s = ptx::smem_u32(empty);
+  int turn = warp;        // steps until this warp's next turn to fetch a site image (every nact steps)
 
   auto set_e0 = [&](bool gateA, bool gateB) {  // boundary vector e0 * 2^14 (fp16 0x7400 in element 0)
 #pragma unroll
@@ -247,15 +266,19 @@ __global__ void __launch_bounds__(kRrcThreads, kRrcWarps == 16 ? 1 : 2) rr_chain
   // acc (+)= operand x site image of the ring's current stage
   auto mma_step = [&](bool accumulate) {
     // this warp's turn to fetch: the image of step gs + kRrcAhead, into the slot every warp has left at step gs - 2
-    if ((gs & (nact - 1)) == warp && gs + kRrcAhead < total && lane == 0) {
-      const int sf = gs + kRrcAhead, slot = sf % kRrcStages, use = sf / kRrcStages;
-      if (use > 0) ptx::mbar_wait(&empty[slot], (uint32_t)(use - 1) & 1u);
-      ptx::mbar_expect_tx(&full[slot], kSite);
-      ptx::bulk_g2s(ring + (size_t)slot * kSite, step_image(sf), kSite, &full[slot]);
+    if (turn == 0) {
+      turn = nact;
+      if (gs + kRrcAhead < total && lane == 0) {
+        const int sf = gs + kRrcAhead, slot = sf % kRrcStages, use = sf / kRrcStages;
+        if (use > 0) rrc_mbar_wait(empty_s + (uint32_t)slot * 8, (uint32_t)(use - 1) & 1u);
+        ptx::mbar_expect_tx(&full[slot], kSite);
+        ptx::bulk_g2s(ring + (size_t)slot * kSite, step_image(sf), kSite, &full[slot]);
+      }
+      __syncwarp();
     }
-    __syncwarp();
+    --turn;
     ++gs;
-    ptx::mbar_wait(&full[stage], phase);
+    rrc_mbar_wait(full_s + (uint32_t)stage * 8, phase);
     const uint32_t st = ld_base + (uint32_t)stage * kSite;
     // Four n-tiles at a time, one product term after the other: two HMMAs into the same accumulator are four
     // instructions apart (a dependent HMMA waits ~21 cycles; back to back the three terms of a tile were a serial chain).
@@ -279,7 +302,7 @@ __global__ void __launch_bounds__(kRrcThreads, kRrcWarps == 16 ? 1 : 2) rr_chain
         for (int j = 0; j < 4; ++j) rrc_mma(acc[j0 + j], ahi[kk], bl0[j], bl1[j]);
       }
     __syncwarp();
-    if (lane == 0) ptx::mbar_arrive(&empty[stage]);
+    if (lane == 0) rrc_mbar_arrive(empty_s + (uint32_t)stage * 8);
     if (++stage == kRrcStages) { stage = 0; phase ^= 1; }
   };
 
