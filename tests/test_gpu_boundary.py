@@ -252,3 +252,46 @@ def test_backward_in_site_ranges_equals_one_piece(chi):
     assert red.calls >= 2
     assert abs(float(ls1.item()) - ls0) <= 1e-6 * abs(ls0)
     assert float((g1 - g0).abs().max()) <= 1e-5 * float(g0.abs().max())
+
+
+@pytest.mark.parametrize("dtype,chi,d,B", [
+    (torch.float32, 32, 2, 333),    # register-resident mma.sync kernels, ragged last tile
+    (torch.float32, 10, 2, 77),     # ... zero-padded from bond 10
+    (torch.float32, 24, 3, 130),    # ... d = 3
+    (torch.float32, 50, 2, 130),    # tcgen05 kernels, zero-padded to 64
+    (torch.float32, 128, 2, 200),   # two-tile CTAs
+    (torch.float32, 256, 2, 129),
+    (torch.float64, 24, 2, 100),    # SIMT / DMMA family
+], ids=["rr32", "rr_pad10", "rr_pad24_d3", "tc_pad50", "tc128", "tc256", "f64"])
+def test_no_kernel_writes_outside_its_buffers(dtype, chi, d, B):
+    """Guard bands (a byte pattern) around the workspace and the gradient buffer survive a forward + backward step and a
+    forward-only call: no kernel of any family stores outside what tnb_workspace_bytes / tnb_param_count promised."""
+    import tn4ml_b200 as T
+    L, C_ = 9, 3
+    arrays = O.make_mps_arrays(L, chi, d, class_site=4, C=C_, std=0.05, seed=3)
+    x = O.make_inputs(B, L, seed=5).to(dtype).cuda()
+    t = O.make_labels(B, C_).to(dtype).cuda()
+    model = T.TensorNetwork(arrays, dtype=dtype, device="cuda:0")
+    emb = T.TrigonometricEmbedding() if d == 2 else T.PolynomialEmbedding(degree=2, n=1, include_bias=True)
+    eng, _ = model._engine(emb, _heads()["softmax_xent"], True, dtype)
+    G = 1 << 20
+    held = {}
+
+    def guarded(batch, need_grad):
+        key = (batch, need_grad)
+        if key not in held:
+            n = int(eng.lib.tnb_workspace_bytes(C.byref(eng.prob), batch, int(need_grad)))
+            held[key] = torch.full((n + 2 * G,), 0xA5, dtype=torch.uint8, device="cuda:0")
+        buf = held[key]
+        return buf[G: buf.numel() - G]
+
+    eng._workspace = guarded
+    esz = 4 if dtype == torch.float32 else 8
+    gbuf = torch.full((eng.n_params * esz + 2 * G,), 0xA5, dtype=torch.uint8, device="cuda:0")
+    grads = gbuf[G: G + eng.n_params * esz].view(dtype)
+    ls, g = eng.value_and_grad(model._packed, x, t, grads=grads)
+    per, out, _ = eng.forward(model._packed, x, t)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(g).all()) and bool(torch.isfinite(per).all())
+    for buf in list(held.values()) + [gbuf]:
+        assert bool((buf[:G] == 0xA5).all()) and bool((buf[-G:] == 0xA5).all())
