@@ -1,8 +1,6 @@
-// Register-resident MPS chain at bond 32 (float32 tensor family, `mma.sync` fp16x3): host-side launch code.
-// Kernel: mps_rr_chain.cuh.  Called from the tcgen05 family's sweep launcher (mps_tc.cu) when the plan selects it.
-#include <stdio.h>
-#include <stdlib.h>
-
+// Register-resident MPS kernels at bond 32 (float32 tensor family, `mma.sync` fp16x3; smaller bonds run zero-padded): host-side
+// launch code.  Kernels: mps_rr_chain.cuh (chains, class site, head, adjoint seeds), mps_rr_da.cuh (weight gradients of the chain
+// sites).  Called from the tcgen05 family's launchers (mps_tc.cu) when the plan selects them.
 #include "host.h"
 #include "mps_rr_chain.cuh"
 #include "mps_rr_da.cuh"
@@ -35,11 +33,6 @@ int mps_rr_launch_sweep(const TcArgs &T, int d, long long B, int adjoint, cudaSt
   const size_t smem = rrc_smem(d, T.M.L + T.M.C);
   const long long ntiles = (B + kTcRows - 1) / kTcRows;
   dim3 grid((unsigned)((ntiles + kRrcTiles - 1) / kRrcTiles), adjoint ? 2 : 1);  // kRrcTiles sample tiles per CTA
-  if (getenv("TNB_RRC_OCC")) {  // (measurement aid)
-    int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rr_chain_kernel<2>, kRrcThreads, smem);
-    fprintf(stderr, "[rr_chain] %d threads, %zu B smem: %d CTAs per SM\n", kRrcThreads, smem, nb);
-  }
   prof_begin(st);
   if (d == 2) rr_chain_kernel<2><<<grid, kRrcThreads, smem, st>>>(T, adjoint);
   else rr_chain_kernel<3><<<grid, kRrcThreads, smem, st>>>(T, adjoint);
@@ -56,12 +49,13 @@ int mps_rr_launch_da(const TcDaArgs &Da_in, int d, long long B, int nsites, cuda
   // (a single writer per entry) when deterministic
   const long long maxsp = (B + 1023) / 1024;
   const int nwork = nsites - ((Da.M.c >= Da.site0 && Da.M.c < Da.site0 + nsites) ? 1 : 0);  // (the class site's CTAs leave at once)
+  const long long slots = d == 2 ? 296 : 148;  // CTAs resident on the machine (two per SM for d = 2)
   long long nsplit = 1;
   double best = -1.0;
   for (long long sp = 1; sp <= maxsp && sp <= 16; ++sp) {
     const long long n = (long long)(nwork > 0 ? nwork : 1) * sp;
-    const double eff = (double)n / (double)((n + 295) / 296 * 296);
-    const double score = eff - (n < 2 * 296 ? 0.5 : 0.0) - 0.004 * (double)sp;
+    const double eff = (double)n / (double)((n + slots - 1) / slots * slots);
+    const double score = eff - (n < 2 * slots ? 0.5 : 0.0) - 0.004 * (double)sp;
     if (score > best) { best = score; nsplit = sp; }
   }
   if (deterministic()) nsplit = 1;
