@@ -97,6 +97,30 @@ def test_float32_model_uses_tensor_path_by_default_and_trains():
     assert np.all(np.isfinite(hist["loss"])) and hist["loss"][-1] < hist["loss"][0]
 
 
+def test_cfg1_bond_float32_trains_on_the_register_resident_kernels():
+    """BASELINE configs[0]'s shape family (chi = 10, 10 classes, batch 64) in float32 through Model.train(): the step runs
+    zero-padded on the mma.sync kernels, the model keeps its own [10][10][2] site tensors, the loss goes down, and training in
+    float32 follows the same run in float64 (SIMT family) to float32 accuracy."""
+    import tn4ml_b200 as T
+    from tests.test_gpu_tensor_path import _launched_kernels
+    arrays = O.make_mps_arrays(24, 10, 2, class_site=11, C=10, std=0.05, seed=2)
+    x, t = O.make_inputs(128, 24, seed=3), O.make_labels(128, 10)
+    losses = {}
+    for dt, npdt in ((torch.float32, np.float32), (torch.float64, np.float64)):
+        model = T.TensorNetwork([a.to(dt) for a in arrays], dtype=dt, device="cuda:0")
+        model.configure(optimizer=T.optim.adam, loss=T.metrics.CrossEntropySoftmax, train_type=T.TrainingType.SUPERVISED,
+                        learning_rate=1e-3, device=("gpu", 0))
+        run = lambda: losses.__setitem__(dt, model.train(x.numpy(), targets=t.numpy(), batch_size=64, epochs=5,  # noqa: E731
+                                                         embedding=T.TrigonometricEmbedding(), dtype=npdt)["loss"])
+        seen = _launched_kernels(run)
+        if dt == torch.float32:
+            assert "rr_chain_kernel(fwd)" in seen and "rr_da_kernel" in seen, seen
+            assert tuple(model.arrays[3].shape) == (10, 10, 2)
+    l32, l64 = np.asarray(losses[torch.float32]), np.asarray(losses[torch.float64])
+    assert np.all(np.isfinite(l32)) and l32[-1] < l32[0]
+    assert np.allclose(l32, l64, rtol=2e-4)
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     from tn4ml_b200 import _lib
     monkeypatch.setattr(_lib, "_lib", None)
