@@ -8,7 +8,7 @@ import time
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import tn_oracle as O  # noqa: E402  (input generators only)
+from tn4ml_b200 import synthetic as O  # noqa: E402  (input generators)
 import tn4ml_b200 as T  # noqa: E402
 from tn4ml_b200 import metrics as M  # noqa: E402
 
