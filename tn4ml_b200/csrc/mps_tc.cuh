@@ -271,7 +271,7 @@ struct TcDaArgs {
 // of the one MMA warp (~120 cycles each): two CTAs of 320 threads (three of 192) per SM, stages sized by the bond, run that many
 // pipelines side by side (chi = 32: 3.99 -> 2.13 -> 1.71 ms; chi = 64: 4.22 -> 2.86 ms; chi = 128: no gain, 5.6 ms either way).
 template <int CPG, int PW = 16>
-__global__ void __launch_bounds__(PW * 32 + 64, PW == 16 ? 1 : (PW == 8 ? 2 : 3)) tc_da_kernel(TcDaArgs A) {
+__global__ void __launch_bounds__(PW * 32 + 64, PW == 16 ? 1 : (PW == 8 ? 2 : 3)) tc_da_kernel(const __grid_constant__ TcDaArgs A) {
   constexpr int kThreads = PW * 32 + 64;
   extern __shared__ __align__(1024) uint8_t smem[];
   const MpsArgs<float> &M = A.M;

@@ -166,7 +166,7 @@ __device__ __forceinline__ float tc_combine_pack16(uint32_t col, uint32_t cstrid
 // 16 epilogue warps would own no column group and a step is a handful of small MMAs: the second CTA's chain runs in the
 // latencies of the first (issue, commit, TMEM read, publish), which nothing inside one CTA could hide there.
 template <int D, int SLOTS, int TILES, int CG, int NGRP = 4>
-__global__ void __launch_bounds__((4 * NGRP + 3) * 32, NGRP == 4 ? 1 : 2) tc_chain_kernel(TcArgs A, int adjoint) {
+__global__ void __launch_bounds__((4 * NGRP + 3) * 32, NGRP == 4 ? 1 : 2) tc_chain_kernel(const __grid_constant__ TcArgs A, int adjoint) {
   static_assert(CG == 1 || TILES == 1, "the CTA pair carries one tile per CTA");
   static_assert(NGRP == 4 || NGRP == 2, "4 or 2 column-group owners per lane quarter");
   constexpr int kEpiWarps = 4 * NGRP, kMmaWarp = kEpiWarps;  // + 1: weight producer warp, + 2: image writer warp
