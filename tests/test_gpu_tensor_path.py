@@ -96,16 +96,18 @@ def test_micro_batched_step_equals_one_piece(precision):
     assert float((g2 - g1).abs().max()) <= 2e-5 * float(g1.abs().max())
 
 
-def test_cta_pair_chain_kernel_opt_in():
-    """The opt-in CTA-pair chain kernel (TNB_TC_CG=2: cta_group::2 MMAs, each CTA of a cluster of two holding half of the
-    weight columns) against the oracle: chi = 256, an odd number of sample tiles (the pair's second tile is all padding).
-    The knob is read once per process, hence the subprocess (tools/pair_case.py prints the errors)."""
+@pytest.mark.parametrize("cg", ["1", "2"], ids=["one_cta", "cta_pair"])
+def test_chain_kernel_variants_at_chi_256(cg):
+    """Both chain kernels of the wide-bond case against the oracle at chi = 256 with an odd number of sample tiles: the CTA pair
+    (TNB_TC_CG=2: cta_group::2 MMAs, each CTA of a cluster of two holding half of the weight columns, the pair's second tile all
+    padding here; the default at chi = 256) and the one-CTA kernel (TNB_TC_CG=1).  The knob is read once per process, hence the
+    subprocess (tools/pair_case.py prints the errors)."""
     import os
     import re
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, TNB_TC_CG="2")
+    env = dict(os.environ, TNB_TC_CG=cg)
     out = subprocess.run([sys.executable, os.path.join(root, "tools", "pair_case.py"), "300"], env=env, capture_output=True,
                          text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]

@@ -64,7 +64,7 @@ static Knobs read_knobs() {
   k.da_small = geti("TNB_DA_SMALL", 64);
   k.da_pw4 = geti("TNB_DA_PW4", 1);
   k.da_stages = geti("TNB_DA_STAGES", 0);
-  k.tc_cg = geti("TNB_TC_CG", 0);
+  k.tc_cg = geti("TNB_TC_CG", 0);  // 0: the default rule of plan_mps; 1: never the CTA pair; 2: wherever it is legal
   k.simt_rb = geti("TNB_SIMT_RB", 0);
   k.simt_nt = geti("TNB_SIMT_NT", 0);
   k.simt_kt = geti("TNB_SIMT_KT", 0);
@@ -246,9 +246,14 @@ MpsPlan plan_mps(const tnb_problem *p, long long B, int need_grad) {
     P.tc_tiles = (P.tc_NH == 1 && P.tc_N == 256) ? 2 : 1;
     if (knobs().tc_tiles == 1) P.tc_tiles = 1;
     if (knobs().tc_tiles == 2 && P.tc_NH == 1 && (p->d == 2 || p->d == 4 || p->d == 8)) P.tc_tiles = 2;
-    // CTA pair (cta_group::2), opt-in: the wide-bond case (chi > 128, d = 2).  Parity-green; within the box-to-box spread of
-    // the one-CTA kernel under the power cap, hence not the default.
-    P.tc_cg = (tchi > 128 && p->d == 2 && P.tc_tiles == 1 && knobs().tc_cg == 2) ? 2 : 1;
+    // CTA pair (cta_group::2): legal for the wide-bond case (chi > 128, d = 2); the default at chi = 256, where it was measured
+    // (same box, four alternations of 10-step runs: 59.8 -> 58.7 ms per step, e2e 2.18 -> 2.22 M samples/s; chain kernels
+    // 19.5 + 21.2 -> 18.8 + 20.2 ms).  TNB_TC_CG=1 turns it off, TNB_TC_CG=2 takes it wherever it is legal.
+    {
+      const bool legal = tchi > 128 && p->d == 2 && P.tc_tiles == 1;
+      const int want = knobs().tc_cg == 0 ? (tchi == 256 ? 2 : 1) : knobs().tc_cg;
+      P.tc_cg = (legal && want == 2) ? 2 : 1;
+    }
     P.tc_stage_bytes /= (uint32_t)P.tc_cg;  // one CTA's half of a stage
     P.tc_cols = 32;
     while (P.tc_cols < P.tc_tiles * P.tc_N) P.tc_cols <<= 1;
