@@ -260,9 +260,10 @@ def test_backward_in_site_ranges_equals_one_piece(chi):
     (torch.float32, 24, 3, 130),    # ... d = 3
     (torch.float32, 50, 2, 130),    # tcgen05 kernels, zero-padded to 64
     (torch.float32, 128, 2, 200),   # two-tile CTAs
-    (torch.float32, 256, 2, 129),
+    (torch.float32, 256, 2, 129),   # CTA pair
+    (torch.float32, 256, 2, 64),    # CTA pair with one sample tile: the second CTA of the cluster is all padding
     (torch.float64, 24, 2, 100),    # SIMT / DMMA family
-], ids=["rr32", "rr_pad10", "rr_pad24_d3", "tc_pad50", "tc128", "tc256", "f64"])
+], ids=["rr32", "rr_pad10", "rr_pad24_d3", "tc_pad50", "tc128", "tc256", "tc256_one_tile", "f64"])
 def test_no_kernel_writes_outside_its_buffers(dtype, chi, d, B):
     """Guard bands (a byte pattern) around the workspace and the gradient buffer survive a forward + backward step and a
     forward-only call: no kernel of any family stores outside what tnb_workspace_bytes / tnb_param_count promised."""

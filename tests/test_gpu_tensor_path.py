@@ -26,7 +26,10 @@ def _tensor_model(cls, arrays):
     dict(L=14, chi=32, d=2, cls=6, C=10, B=300),      # chi = 32 (the metric's small-bond point): dA tile half empty
     dict(L=30, chi=32, d=3, cls=14, C=2, B=160),      # cfg 2 shape: N = 96, partial dA tile
     dict(L=8, chi=48, d=2, cls=3, C=3, B=70),         # chi = 48: N = 96
-], ids=["chi64", "chi64_ragged", "chi128_cls0", "chi32_d4_clsL", "chi256", "chi128_d3", "chi32", "cfg2_shape", "chi48"])
+    dict(L=6, chi=256, d=2, cls=2, C=3, B=64),        # one sample tile on the CTA-pair kernel (its second CTA is all padding)
+    dict(L=6, chi=192, d=2, cls=3, C=2, B=130),       # a wide bond that stays on the one-CTA kernel by default
+], ids=["chi64", "chi64_ragged", "chi128_cls0", "chi32_d4_clsL", "chi256", "chi128_d3", "chi32", "cfg2_shape", "chi48",
+        "chi256_one_tile", "chi192"])
 def test_tensor_path_classifier(case):
     import tn4ml_b200 as T
     from tn4ml_b200 import _lib
